@@ -1,0 +1,197 @@
+"""Pin the CPU oracle (oracle/spectral.py) before anything trusts it:
+  1. the reference's own golden vectors (reference tests/test_cpp_extension.py:525-546),
+  2. outputs of the reference's own Python code (tests/golden/reference_outputs.npz,
+     made by tests/golden/generate_golden.py),
+  3. the libraries the reference's tests use as oracle that exist here
+     (torch.stft / istft, torchaudio mel, scipy windows and DCT) at the reference's tolerances.
+"""
+import numpy as np
+import pytest
+
+from oracle import spectral as o
+
+
+# ---- 1. reference golden vectors -------------------------------------------
+def test_ref_golden_pad_constant():
+    x = np.ones((1, 10), np.float32)
+    p = o.pad_signal(x, 3, "constant")
+    assert p.shape == (1, 16)
+    assert np.array_equal(p[0, :3], [0, 0, 0]) and np.array_equal(p[0, -3:], [0, 0, 0])
+
+
+def test_ref_golden_pad_reflect():
+    x = np.arange(10, dtype=np.float32)[None]
+    p = o.pad_signal(x, 3, "reflect")
+    assert np.array_equal(p[0, :3], [3, 2, 1])
+    assert np.array_equal(p[0, -3:], [8, 7, 6])
+
+
+# ---- 2. reference-code outputs ---------------------------------------------
+def test_constants_bit_exact(golden):
+    for key in golden.files:
+        parts = key.split("/")
+        if parts[0] == "window":
+            w = o.get_window(parts[1], int(parts[2]), bool(int(parts[3])))
+            assert np.array_equal(w, golden[key]), key
+        elif parts[0] == "melfb":
+            sr, n_fft, n_mels = int(parts[1]), int(parts[2]), int(parts[3])
+            fmax = None if parts[5] == "None" else float(parts[5])
+            norm = None if parts[7] == "None" else parts[7]
+            fb = o.mel_filterbank(sr, n_fft, n_mels, float(parts[4]), fmax, bool(int(parts[6])), norm)
+            assert np.array_equal(fb, golden[key]), key
+        elif parts[0] == "dctmat":
+            norm = None if parts[3] == "None" else parts[3]
+            assert np.array_equal(o.dct_matrix(int(parts[1]), int(parts[2]), norm), golden[key]), key
+    assert np.array_equal(o.linear_filterbank(22050, 1024, 32), golden["linfb/22050/1024/32"])
+    hz = golden["hz"]
+    assert np.array_equal(o.hz_to_mel(hz), golden["hz_to_mel/slaney"])
+    assert np.array_equal(o.hz_to_mel(hz, True), golden["hz_to_mel/htk"])
+    assert np.array_equal(o.mel_to_hz(o.hz_to_mel(hz)), golden["mel_to_hz/slaney"])
+    assert np.array_equal(o.mel_to_hz(o.hz_to_mel(hz, True), True), golden["mel_to_hz/htk"])
+
+
+def test_pad_frame_bit_exact(golden):
+    x = golden["pad/input"]
+    for mode in o.PAD_MODES:
+        for pad in [0, 3, 8, 19]:
+            assert np.array_equal(o.pad_signal(x, pad, mode), golden[f"pad/{mode}/{pad}"])
+    f = golden["frame/input"]
+    for fl, hop in [(8, 2), (16, 16), (10, 3), (50, 1)]:
+        assert np.array_equal(o.frame_signal(f, fl, hop), golden[f"frame/{fl}/{hop}"])
+
+
+def test_stft_istft_match_reference_code(golden, cases):
+    y = golden["stft/input"]
+    for i, kw in enumerate(cases["stft"]):
+        yin = y[:, :300] if kw.get("hop_length") == 1 else y
+        S = o.stft(yin, **kw)
+        ref = golden[f"stft/{i}"]
+        assert S.shape == ref.shape
+        assert np.abs(S - ref).max() <= 1e-6 * np.abs(ref).max(), (i, kw)
+        ikw = {k: v for k, v in kw.items() if k != "pad_mode"}
+        r = o.istft(ref, **ikw)
+        assert r.shape == golden[f"istft/{i}"].shape
+        np.testing.assert_allclose(r, golden[f"istft/{i}"], atol=2e-6)
+        if kw.get("center", True):
+            r = o.istft(ref, length=yin.shape[1], **ikw)
+            np.testing.assert_allclose(r, golden[f"istft_len/{i}"], atol=2e-6)
+    S1 = golden["stft1d"]
+    assert np.abs(o.stft(y[0], 512, 128) - S1).max() <= 1e-6 * np.abs(S1).max()
+    for L in [5000, 6000, 7000]:
+        np.testing.assert_allclose(o.istft(S1, 128, length=L), golden[f"istft1d_len/{L}"], atol=2e-6)
+    Snc = o.stft(y, 512, 128, center=False)
+    for L in [4000, 6500]:
+        np.testing.assert_allclose(o.istft(Snc, 128, center=False, length=L),
+                                   golden[f"istft_nc_len/{L}"], atol=2e-6)
+    np.testing.assert_allclose(o.magnitude(S1), golden["magnitude"], rtol=1e-6)
+    np.testing.assert_allclose(o.phase(S1), golden["phase"], atol=1e-6)
+
+
+def test_mel_db_mfcc_match_reference_code(golden, cases):
+    y = golden["stft/input"]
+    for i, kw in enumerate(cases["mel"]):
+        M = o.melspectrogram(y, **kw)
+        ref = golden[f"mel/{i}"]
+        assert np.abs(M - ref).max() <= 2e-6 * np.abs(ref).max(), (i, kw)
+        np.testing.assert_allclose(o.power_to_db(ref), golden[f"db_default/{i}"], atol=1e-4)
+        np.testing.assert_allclose(o.power_to_db(ref, ref=np.max), golden[f"db_refmax/{i}"], atol=1e-4)
+        np.testing.assert_allclose(o.power_to_db(ref, ref=np.max, top_db=None),
+                                   golden[f"db_refmax_notop/{i}"], atol=1e-4)
+        np.testing.assert_allclose(o.power_to_db(ref, ref=0.5, amin=1e-5, top_db=60.0),
+                                   golden[f"db_ref05_amin/{i}"], atol=1e-4)
+    amp = np.abs(golden["stft1d"])
+    np.testing.assert_allclose(o.amplitude_to_db(amp), golden["ampdb"], atol=1e-4)
+    np.testing.assert_allclose(o.amplitude_to_db(amp, ref=np.max, top_db=None), golden["ampdb_refmax"], atol=1e-4)
+    np.testing.assert_allclose(o.db_to_power(golden["dbv"], 2.0), golden["db_to_power"], rtol=1e-6)
+    np.testing.assert_allclose(o.db_to_amplitude(golden["dbv"]), golden["db_to_amplitude"], rtol=1e-6)
+    for i, kw in enumerate(cases["mfcc"]):
+        np.testing.assert_allclose(o.mfcc(y, **kw), golden[f"mfcc/{i}"], atol=2e-4, rtol=1e-5)
+    x = golden["dct/input"]
+    np.testing.assert_allclose(o.dct(x), golden["dct/ortho"], atol=1e-5)
+    np.testing.assert_allclose(o.dct(x, n=20, norm=None), golden["dct/n20_none"], atol=1e-4)
+    np.testing.assert_allclose(o.dct(x, axis=1, n=5), golden["dct/axis1"], atol=1e-5)
+
+
+def test_griffinlim_matches_reference_code(golden):
+    S = golden["gl/S"]
+    np.testing.assert_allclose(o.griffinlim(S, 8, 128, random_state=0), golden["gl/random8"], atol=1e-4)
+    np.testing.assert_allclose(o.griffinlim(S, 4, 128, init="zeros", momentum=0.0),
+                               golden["gl/zeros4_m0"], atol=1e-4)
+    np.testing.assert_allclose(o.griffinlim(S, 3, 128, random_state=1, length=4000), golden["gl/len"], atol=1e-4)
+    np.testing.assert_allclose(o.griffinlim(S[0], 2, 128, random_state=2), golden["gl/1d"], atol=1e-4)
+
+
+# ---- 3. the reference tests' third-party oracles that exist here ------------
+@pytest.mark.parametrize("n_fft,hop", [(512, 128), (1024, 256), (2048, 512), (400, 160)])
+@pytest.mark.parametrize("pad_mode", ["constant", "reflect"])
+def test_stft_vs_torch(random_signal, n_fft, hop, pad_mode):
+    torch = pytest.importorskip("torch")
+    y = random_signal
+    ref = torch.stft(torch.from_numpy(y), n_fft, hop, window=torch.hann_window(n_fft),
+                     center=True, pad_mode=pad_mode, return_complex=True).numpy()
+    S = o.stft(y, n_fft, hop, pad_mode=pad_mode)
+    # reference tolerance: tests/test_torchaudio_crossval.py:26-78 (rtol=atol=1e-4)
+    np.testing.assert_allclose(S, ref, rtol=1e-4, atol=1e-4)
+    S64 = o.stft(y, n_fft, hop, pad_mode=pad_mode, dtype=np.float64)
+    assert np.abs(S64 - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_istft_round_trip_and_torch(random_signal):
+    torch = pytest.importorskip("torch")
+    y = random_signal
+    S = o.stft(y, 2048, 512)
+    r = o.istft(S, 512, length=len(y))
+    assert np.abs(r[1:] - y[1:]).max() < 1e-5  # sample 0 has zero window sum (hann) -> 0
+    rt = torch.istft(torch.from_numpy(S), 2048, 512, window=torch.hann_window(2048), length=len(y)).numpy()
+    assert np.abs(r[1024:-1024] - rt[1024:-1024]).max() < 1e-5
+
+
+def test_mel_vs_torchaudio(random_signal):
+    torch = pytest.importorskip("torch")
+    ta = pytest.importorskip("torchaudio")
+    y = random_signal
+    tr = ta.transforms.MelSpectrogram(22050, n_fft=2048, hop_length=512, n_mels=128, center=True,
+                                      pad_mode="constant", norm="slaney", mel_scale="slaney", power=2.0)
+    ref = tr(torch.from_numpy(y)).numpy()
+    M = o.melspectrogram(y)
+    np.testing.assert_allclose(M, ref, rtol=1e-3, atol=1e-4 * ref.max())
+
+
+@pytest.mark.parametrize("name", ["hann", "hamming", "blackman", "bartlett"])
+@pytest.mark.parametrize("n", [256, 400, 1024, 2048])
+@pytest.mark.parametrize("fftbins", [True, False])
+def test_windows_vs_scipy(name, n, fftbins):
+    sig = pytest.importorskip("scipy.signal")
+    np.testing.assert_allclose(o.get_window(name, n, fftbins), sig.get_window(name, n, fftbins=fftbins),
+                               rtol=1e-5, atol=1e-5)
+    w = o.get_window(name, n, False)
+    assert np.array_equal(w, w[::-1])  # exact symmetry (test_torchaudio_crossval.py:199-224)
+
+
+def test_dct_vs_scipy():
+    sf = pytest.importorskip("scipy.fft")
+    x = np.random.default_rng(0).standard_normal((5, 128)).astype(np.float32)
+    np.testing.assert_allclose(o.dct(x, n=40), sf.dct(x.astype(np.float64), type=2, norm="ortho")[:, :40],
+                               rtol=1e-4, atol=1e-4)
+
+
+def test_error_messages():
+    y = np.zeros(100, np.float32)
+    with pytest.raises(ValueError, match="hop_length must be positive"):
+        o.stft(y, 64, 0)
+    with pytest.raises(ValueError, match="must be <= n_fft"):
+        o.stft(y, 64, 16, 128)
+    with pytest.raises(ValueError, match="must be >= frame_length"):
+        o.stft(y, 256, 64, center=False)
+    with pytest.raises(ValueError, match="Unknown pad_mode"):
+        o.stft(y, 64, 16, pad_mode="wrap")
+    with pytest.raises(ValueError, match="Unknown window type"):
+        o.get_window("kaiser", 64)
+    with pytest.raises(ValueError, match="cannot exceed Nyquist"):
+        o.mel_filterbank(16000, 512, fmax=9000.0)
+    with pytest.raises(ValueError, match="top_db must be positive"):
+        o.power_to_db(np.ones(4, np.float32), top_db=-1)
+    with pytest.raises(ValueError, match="Only DCT type 2"):
+        o.dct(np.ones(4, np.float32), type=3)
+    with pytest.raises(ValueError, match="Unknown init"):
+        o.griffinlim(np.ones((5, 3), np.float32), init="ones")
