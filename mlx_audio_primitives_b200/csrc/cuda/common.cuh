@@ -1,0 +1,106 @@
+// Shared helpers for the sm_100a spectral kernels: compile-time loops, constexpr
+// trigonometry (so every in-register twiddle becomes an FFMA immediate), error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <type_traits>
+#include <utility>
+
+#define MLXA_HD __host__ __device__ __forceinline__
+#define MLXA_D __device__ __forceinline__
+
+namespace mlxa {
+
+// ---- compile-time loop: f(integral_constant<int, I>) for I in [0, N) ----------------------
+template <class F, int... I>
+MLXA_HD void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+MLXA_HD void static_for(F&& f) {
+    static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
+}
+
+// ---- constexpr cos / sin of (2*pi*num/den), exact octant reduction on integers ------------
+constexpr double kPi = 3.141592653589793238462643383279502884;
+
+constexpr double taylor_cos(double x) {  // |x| <= pi/4
+    double x2 = x * x, term = 1.0, sum = 1.0;
+    for (int i = 1; i <= 12; ++i) {
+        term *= -x2 / double((2 * i - 1) * (2 * i));
+        sum += term;
+    }
+    return sum;
+}
+constexpr double taylor_sin(double x) {  // |x| <= pi/4
+    double x2 = x * x, term = x, sum = x;
+    for (int i = 1; i <= 12; ++i) {
+        term *= -x2 / double((2 * i) * (2 * i + 1));
+        sum += term;
+    }
+    return sum;
+}
+// angle = 2*pi*m/(8*d); m any integer.  8d units make half/quarter/eighth turns integers.
+constexpr double cos_units8(long long m, long long d) {
+    const long long full = 8 * d;
+    m %= full;
+    if (m < 0) m += full;
+    if (m > 4 * d) m = full - m;           // cos(-x) = cos(x)          -> [0, half turn]
+    double sign = 1.0;
+    if (m > 2 * d) { m = 4 * d - m; sign = -1.0; }  // cos(pi - x) = -cos x -> [0, quarter]
+    if (m == 0) return sign;
+    if (m == 2 * d) return 0.0;
+    if (m > d) return sign * taylor_sin(2.0 * kPi * double(2 * d - m) / double(full));
+    return sign * taylor_cos(2.0 * kPi * double(m) / double(full));
+}
+constexpr double cos_turn(long long num, long long den) { return cos_units8(8 * num, den); }
+constexpr double sin_turn(long long num, long long den) { return cos_units8(8 * num - 2 * den, den); }
+
+// ---- tiny complex helpers on float2 -----------------------------------------------------
+MLXA_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+MLXA_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+MLXA_HD float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
+}
+MLXA_HD float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -(a.x * b.y)));
+}
+MLXA_HD float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+MLXA_HD float2 mul_pos_i(float2 a) { return make_float2(-a.y, a.x); }  // a * (+i)
+MLXA_HD float2 cswap(float2 a) { return make_float2(a.y, a.x); }
+
+// v * exp(-2*pi*i*NUM/DEN) with every special angle folded at compile time
+template <int NUM, int DEN>
+MLXA_HD float2 mul_tw(float2 v) {
+    constexpr int n = ((NUM % DEN) + DEN) % DEN;
+    if constexpr (n == 0) {
+        return v;
+    } else if constexpr (4 * n == DEN) {
+        return mul_neg_i(v);
+    } else if constexpr (2 * n == DEN) {
+        return make_float2(-v.x, -v.y);
+    } else if constexpr (4 * n == 3 * DEN) {
+        return mul_pos_i(v);
+    } else if constexpr (8 * n == DEN) {  // (1 - i)/sqrt2
+        constexpr float h = 0.70710678118654752440f;
+        return make_float2(h * (v.x + v.y), h * (v.y - v.x));
+    } else if constexpr (8 * n == 3 * DEN) {  // (-1 - i)/sqrt2
+        constexpr float h = 0.70710678118654752440f;
+        return make_float2(h * (v.y - v.x), -h * (v.x + v.y));
+    } else if constexpr (8 * n == 5 * DEN) {  // (-1 + i)/sqrt2
+        constexpr float h = 0.70710678118654752440f;
+        return make_float2(-h * (v.x + v.y), h * (v.x - v.y));
+    } else if constexpr (8 * n == 7 * DEN) {  // (1 + i)/sqrt2
+        constexpr float h = 0.70710678118654752440f;
+        return make_float2(h * (v.x - v.y), h * (v.x + v.y));
+    } else {
+        constexpr float c = float(cos_turn(n, DEN));
+        constexpr float s = float(sin_turn(n, DEN));
+        // (x + iy)(c - is) = (xc + ys) + i(yc - xs)
+        return make_float2(fmaf(v.x, c, v.y * s), fmaf(v.y, c, -(v.x * s)));
+    }
+}
+
+constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace mlxa

@@ -1,0 +1,69 @@
+// CPU emulation of the warp-group FFT engine (test infrastructure).  The per-lane pass
+// functions in csrc/cuda/fft_plan.cuh are __host__ __device__; here the lanes of a group are
+// executed one after another with the phases separated exactly where the kernels synchronise.
+#include <cmath>
+#include <vector>
+#include "fft_plans_list.cuh"
+
+using namespace mlxa;
+
+template <class P>
+static void run_plan(const float2* in, float2* out) {
+    std::vector<float2> buf(P::BUF, make_float2(0.f, 0.f)), tw(P::TW > 0 ? P::TW : 1);
+    fill_plan_twiddles<P>(tw.data());
+    std::vector<std::vector<float2>> regs(P::G, std::vector<float2>(P::E));
+    for (int g = 0; g < P::G; ++g) {
+        float2* v = regs[g].data();
+        pass_load_fn<P, 0>(g, v, [&](int idx) { return in[idx]; });
+        pass_compute<P, 0>(g, v, tw.data());
+        pass_store_buf<P, 0>(g, v, buf.data());
+    }
+    for (int g = 0; g < P::G; ++g) pass_load_buf<P, 1>(g, regs[g].data(), buf.data());
+    for (int g = 0; g < P::G; ++g) {
+        pass_compute<P, 1>(g, regs[g].data(), tw.data());
+        pass_store_buf<P, 1>(g, regs[g].data(), buf.data());
+    }
+    if constexpr (P::NPASS == 3) {
+        for (int g = 0; g < P::G; ++g) pass_load_buf<P, 2>(g, regs[g].data(), buf.data());
+        for (int g = 0; g < P::G; ++g) {
+            pass_compute<P, 2>(g, regs[g].data(), tw.data());
+            pass_store_buf<P, 2>(g, regs[g].data(), buf.data());
+        }
+    }
+    for (int k = 0; k < P::N; ++k) out[k] = buf[P::phys(k)];
+}
+
+template <int R>
+static void run_radix(const float2* in, float2* out) {
+    float2 v[R];
+    for (int i = 0; i < R; ++i) v[i] = in[i];
+    dft_inplace<R>(v);
+    for (int i = 0; i < R; ++i) out[dft_perm(R, i)] = v[i];
+}
+
+extern "C" {
+int emul_plan_length(int n_fft) {
+    switch (n_fft) {
+#define X(NF) case NF: return PlanFor<NF>::Plan::N;
+        MLXA_FOR_EACH_NFFT(X)
+#undef X
+    }
+    return -1;
+}
+int emul_plan_fft(int n_fft, const float* in, float* out) {
+    switch (n_fft) {
+#define X(NF) case NF: run_plan<PlanFor<NF>::Plan>((const float2*)in, (float2*)out); return 0;
+        MLXA_FOR_EACH_NFFT(X)
+#undef X
+    }
+    return -1;
+}
+int emul_radix(int R, const float* in, float* out) {
+    switch (R) {
+#define X(RR) case RR: run_radix<RR>((const float2*)in, (float2*)out); return 0;
+        X(2) X(3) X(4) X(5) X(8) X(9) X(10) X(16) X(20) X(25) X(32) X(64)
+#undef X
+    }
+    return -1;
+}
+}
