@@ -1,0 +1,167 @@
+/*
+ * mlxa_cuda.h -- C ABI of libmlxaudio_cuda.so, the sm_100a replacement for the reference's
+ * native extension `mlx_audio_primitives._ext` (reference csrc/bindings.cpp:11) on the spectral
+ * hot path.  Plain pointers and sizes only; every pointer is a DEVICE pointer unless the name
+ * says `host`.  Every entry point is asynchronous on `stream` (a cudaStream_t passed as void*),
+ * never allocates or frees caller-visible memory, and returns 0 on success, a negative
+ * MLXA_E_* code for an invalid argument or a positive cudaError_t.  `mlxa_last_error()` gives
+ * the message of the last failure on the calling thread.  Nothing throws across this boundary
+ * (the reference throws std::invalid_argument -> ValueError; the Python host layer raises the
+ * same ValueErrors before calling in).
+ *
+ * Layouts (row-major, contiguous unless a leading dimension is given):
+ *   clips      y      (B, L)        float32, row stride ldy elements
+ *   spectrum   spec   (B, T, F)     complex64 {re, im}, F = n_fft/2 + 1.  This is the physical
+ *                                   buffer behind the reference's logical (B, F, T) result,
+ *                                   which is itself a transposed view of (B, T, F)
+ *                                   (reference stft.py:216, :292).
+ *   mel / mfcc        (B, n_mels|n_mfcc, T)   float32 (reference mel.py:344, mfcc.py:271)
+ */
+#ifndef MLXA_CUDA_H
+#define MLXA_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLXA_ABI_VERSION 1
+
+#define MLXA_E_INVALID (-1)   /* bad size / null pointer / unknown mode            */
+#define MLXA_E_UNSUPPORTED (-2)
+
+/* pad modes (reference stft.py:434-468, csrc/primitives/pad_signal.cpp:36-48) */
+#define MLXA_PAD_CONSTANT 0
+#define MLXA_PAD_REFLECT 1
+#define MLXA_PAD_EDGE 2
+
+typedef struct { float re, im; } mlxa_c64;
+
+int mlxa_abi_version(void);
+const char* mlxa_last_error(void);
+/* 1 when n_fft runs on a compiled Stockham plan, 0 when it falls to the O(n^2) DFT kernel. */
+int mlxa_has_fast_plan(int n_fft);
+
+/* ---- reference-boundary entry points (same granularity as the nanobind module) ---------- */
+
+/* replaces _ext.pad_signal (csrc/bindings.cpp:77, primitives/pad_signal.cpp:133):
+ * out (B, L + 2*pad).  reflect requires pad <= L - 1. */
+int mlxa_pad_signal_f32(const float* x, int64_t B, int64_t L, int64_t pad, int mode,
+                        float* out, void* stream);
+
+/* replaces _ext.frame_signal (csrc/bindings.cpp:49, primitives/frame_signal.cpp:119):
+ * out (B, T, frame_length), T = 1 + (L - frame_length) / hop. */
+int mlxa_frame_signal_f32(const float* x, int64_t B, int64_t L, int frame_length, int hop,
+                          float* out, void* stream);
+
+/* replaces _ext.overlap_add (csrc/bindings.cpp:16, primitives/overlap_add.cpp:195,
+ * metal/overlap_add.metal:16): gather OLA of raw frames (B, T, n_fft) with window applied
+ * inside and division by max(sum w^2, 1e-8); out (B, out_len). */
+int mlxa_overlap_add_f32(const float* frames, const float* window, int64_t B, int64_t T,
+                         int n_fft, int hop, int64_t out_len, float* out, void* stream);
+
+/* sum_f w[i - f*hop]^2 over the T existing frames, ascending f (overlap_add.metal:36-50);
+ * wss (out_len).  The fused ISTFT takes this envelope as an input. */
+int mlxa_window_sumsquare_f32(const float* window, int n_fft, int hop, int64_t T,
+                              int64_t out_len, float* wss, void* stream);
+
+/* ---- fused hot-path kernels -------------------------------------------------------------- */
+
+/* pad -> frame -> window -> rFFT in one kernel (replaces the chain stft.py:118-130 ->
+ * _ext.pad_signal -> _ext.frame_signal -> mx.fft.rfft).  window: n_fft floats, already
+ * centre-padded (stft.py:88-107).  center != 0 pads n_fft/2 per side with pad_mode.
+ * spec (B, T, F), T = 1 + (L + 2*pad - n_fft) / hop. */
+int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window,
+                  int n_fft, int hop, int center, int pad_mode, mlxa_c64* spec, void* stream);
+
+/* STFT with the |X|^power + band-sparse filterbank epilogue (replaces mel.py:309-352 =
+ * stft -> abs -> power -> dense matmul); the spectrum never reaches HBM.
+ * Filterbank rows are given by their contiguous support: row m has band_len[m] weights
+ * starting at bin band_start[m], stored at band_w[band_off[m] ...].
+ * mel (B, n_bands, T).  gmax (optional, may be NULL): device float, atomically raised to
+ * max(mel) -- the producer side of power_to_db(ref=max / top_db) (convert.py:42-58).
+ * db_mode != 0 writes db_coef*log10(max(v, db_amin)/max(db_ref, db_amin)) instead of v
+ * (the no-global-max form of convert.py:48-52). */
+int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window,
+                     int n_fft, int hop, int center, int pad_mode, float power,
+                     const int32_t* band_start, const int32_t* band_len,
+                     const int32_t* band_off, const float* band_w, int n_bands,
+                     float* mel, float* gmax, int db_mode, float db_coef, float db_amin,
+                     float db_ref, void* stream);
+
+/* irFFT -> window -> gather overlap-add -> / max(sum w^2, 1e-8) -> trim in one kernel
+ * (replaces stft.py:292-338 = mx.fft.irfft -> _ext.overlap_add -> slices).
+ * spec (B, T, F_in) complex64; bins k >= F_in are zero, bins beyond n_fft/2 ignored
+ * (irfft(n=n_fft) semantics, stft.py:295).  OLA runs over ola_len samples; output sample j
+ * is OLA sample j + trim for j < min(out_len, ola_len - trim), zero after that
+ * (stft.py:315-338).  wss: ola_len floats from mlxa_window_sumsquare_f32. */
+int mlxa_istft_f32(const mlxa_c64* spec, int64_t B, int64_t T, int F_in, const float* window,
+                   const float* wss, int n_fft, int hop, int64_t ola_len, int64_t trim,
+                   int64_t out_len, float* y, int64_t ldy, void* stream);
+
+/* One Griffin-Lim projection (griffinlim.py:143-178) fused into the STFT epilogue:
+ *   X = stft(y); new = mag * X/|X| (mag + 0j where X == 0, i.e. angle 0);
+ *   rebuilt = new + momentum*(new - tprev); tprev = new.
+ * mag, tprev, rebuilt are (B, T, F); frames t >= T_valid see X = 0 (zero-padded frames,
+ * griffinlim.py:159-165).  tprev is updated in place. */
+int mlxa_griffinlim_project_f32(const float* y, int64_t B, int64_t L, int64_t ldy,
+                                const float* window, int n_fft, int hop, int center,
+                                int pad_mode, int64_t T, int64_t T_valid, const float* mag,
+                                mlxa_c64* tprev, mlxa_c64* rebuilt, float momentum,
+                                void* stream);
+
+/* rebuilt = mag * exp(i*angles) elementwise over n values (griffinlim.py:123) */
+int mlxa_polar_f32(const float* mag, const float* angles, int64_t n, mlxa_c64* out, void* stream);
+
+/* |z| and atan2(im, re) over n complex values (stft.py:347-379) */
+int mlxa_magnitude_f32(const mlxa_c64* z, int64_t n, float* out, void* stream);
+int mlxa_phase_f32(const mlxa_c64* z, int64_t n, float* out, void* stream);
+/* strided (B,T,F) -> contiguous logical (B,F,T) transposing variants for the Python layer */
+int mlxa_transpose_f32(const float* in, int64_t B, int64_t R, int64_t C, float* out, void* stream);
+int mlxa_transpose_c64(const mlxa_c64* in, int64_t B, int64_t R, int64_t C, mlxa_c64* out, void* stream);
+
+/* max over n floats, atomically folded into *gmax (caller zero-initialises; values >= 0 or
+ * any sign: the kernel uses an order-preserving integer key). */
+int mlxa_max_f32(const float* x, int64_t n, float* gmax, void* stream);
+int mlxa_fill_f32(float* x, int64_t n, float value, void* stream);
+
+/* convert.py:14-60.  out = coef*log10(max(x, amin)/max(ref, amin)); ref is *ref_dev when
+ * ref_dev != NULL (a device scalar, e.g. the fused max for ref=max) else ref_host.
+ * use_top_db: clamp at coef*log10(max(*gmax_dev, amin)/max(ref, amin)) - top_db, the global
+ * max of the output by monotonicity.  In-place (out == x) is allowed. */
+int mlxa_to_db_f32(const float* x, int64_t n, float coef, float amin, float ref_host,
+                   const float* ref_dev, int use_top_db, float top_db, const float* gmax_dev,
+                   float* out, void* stream);
+/* convert.py:100-129,169-198: out = ref * 10^(x/div) */
+int mlxa_from_db_f32(const float* x, int64_t n, float ref, float div, float* out, void* stream);
+
+/* mfcc.py:69-140 / csrc/primitives/dct.cpp:103: out (rows, n_out) = x (rows, n_in) @ D^T,
+ * D (n_out, n_in) row-major. */
+int mlxa_dct_f32(const float* x, int64_t rows, int n_in, const float* D, int n_out, float* out,
+                 void* stream);
+
+/* mfcc.py:257-282 in one pass over a (B, n_mels, T) mel tensor: dB (ref, amin, top_db against
+ * *gmax_dev), DCT over the mel axis with D (n_mfcc, n_mels), optional lifter (n_mfcc) ->
+ * out (B, n_mfcc, T).  apply_db == 0 skips the dB step (caller-supplied log-mel, mfcc.py:229). */
+int mlxa_mfcc_tail_f32(const float* mel, int64_t B, int n_mels, int64_t T, const float* D,
+                       int n_mfcc, const float* lifter, int apply_db, float amin, float ref,
+                       int use_top_db, float top_db, const float* gmax_dev, float* out,
+                       void* stream);
+
+/* ---- host-buffer convenience (the e2e path: pinned or pageable HOST pointers) ------------ */
+/* log-mel of host clips with chunked H2D / compute / D2H overlap on internal streams.
+ * y_host (B, L), out_host (B, n_bands, T).  The dB step is power_to_db(ref, amin, top_db)
+ * with the max taken over the whole batch; ref_is_max != 0 means ref = max(mel).
+ * Synchronous: returns when out_host is complete. */
+int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float* window_host,
+                         int n_fft, int hop, int center, int pad_mode, float power,
+                         const int32_t* band_start_host, const int32_t* band_len_host,
+                         const int32_t* band_off_host, const float* band_w_host, int n_bands,
+                         int64_t n_weights, int apply_db, int ref_is_max, float ref, float amin,
+                         int use_top_db, float top_db, float* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLXA_CUDA_H */

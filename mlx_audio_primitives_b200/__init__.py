@@ -1,0 +1,29 @@
+"""mlx_audio_primitives_b200 -- the spectral hot path of zkeown/mlx-audio-primitives
+(stft, istft, magnitude, melspectrogram, mel_filterbank, get_window, power_to_db, mfcc, griffinlim
+and friends) rebuilt from scratch for NVIDIA B200 (sm_100a).
+
+Same librosa-compatible signatures as the reference; arrays are ``torch`` CUDA tensors (or any
+``__dlpack__`` / NumPy input, which is moved to the current CUDA device).  All arithmetic runs in
+hand-written CUDA kernels behind the C ABI of ``include/mlxa_cuda.h``; there is no CPU fallback.
+"""
+from ._extension import HAS_CPP_EXT as _HAS_CPP_EXT  # noqa: F401  (loads the CUDA library or raises)
+from .convert import amplitude_to_db, db_to_amplitude, db_to_power, power_to_db
+from .filterbanks import bark_filterbank, bark_to_hz, hz_to_bark, linear_filterbank
+from .framing import frame
+from .griffinlim import griffinlim, griffinlim_iter
+from .mel import hz_to_mel, mel_filterbank, mel_to_hz, melspectrogram
+from .mfcc import dct, dct_matrix, mfcc
+from .stft import check_nola, istft, magnitude, overlap_add, pad_signal, phase, stft
+from .windows import get_window
+from . import distributed
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "stft", "istft", "magnitude", "phase", "check_nola", "get_window",
+    "mel_filterbank", "melspectrogram", "hz_to_mel", "mel_to_hz",
+    "power_to_db", "amplitude_to_db", "db_to_power", "db_to_amplitude",
+    "dct", "dct_matrix", "mfcc", "griffinlim", "griffinlim_iter", "frame",
+    "linear_filterbank", "bark_filterbank", "hz_to_bark", "bark_to_hz",
+    "pad_signal", "overlap_add", "distributed",
+]

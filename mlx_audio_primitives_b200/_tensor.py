@@ -1,0 +1,53 @@
+"""PyTorch / DLPack plumbing: device tensors in, raw pointers to the C ABI, current stream."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("mlx_audio_primitives_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def to_tensor(x, dtype=None, device=None) -> torch.Tensor:
+    """Accept a torch tensor, any ``__dlpack__`` producer or a NumPy array; return a CUDA tensor."""
+    require_cuda()
+    if isinstance(x, torch.Tensor):
+        t = x
+    elif isinstance(x, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    elif hasattr(x, "__dlpack__"):
+        t = torch.from_dlpack(x)
+    else:
+        t = torch.as_tensor(x)
+    if not t.is_cuda:
+        t = t.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t
+
+
+def f32c(x) -> torch.Tensor:
+    """float32, contiguous, on the GPU."""
+    return to_tensor(x, torch.float32).contiguous()
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def dense_like(x: torch.Tensor, dtype=None) -> tuple[torch.Tensor, torch.Tensor]:
+    """(x_dense, out): a densely laid-out version of x (any permutation of a contiguous block is
+    kept as is) and an empty output with identical strides, so flat elementwise kernels apply."""
+    if not x.is_non_overlapping_and_dense():
+        x = x.contiguous()
+    out = torch.empty_like(x, dtype=dtype if dtype is not None else x.dtype, memory_format=torch.preserve_format)
+    if out.stride() != x.stride():  # pragma: no cover - defensive
+        x = x.contiguous()
+        out = torch.empty_like(x, dtype=dtype if dtype is not None else x.dtype)
+    return x, out

@@ -1,0 +1,96 @@
+"""In-tree build of libmlxaudio_cuda.so (sm_100a only) with plain nvcc.
+
+    python -m mlx_audio_primitives_b200.build [--force] [--verbose]
+
+The forward / inverse transform kernels are compiled once per planned n_fft
+(-DMLXA_NFFT=...) so the translation units build in parallel.  The result is
+``mlx_audio_primitives_b200/_lib/libmlxaudio_cuda.so``; it is git-ignored but
+travels to the GPU box with the working tree.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(PKG, "csrc", "cuda")
+OBJ = os.path.join(PKG, "csrc", "build")
+LIBDIR = os.path.join(PKG, "_lib")
+LIB = os.path.join(LIBDIR, "libmlxaudio_cuda.so")
+PLANNED_NFFT = (64, 128, 256, 400, 512, 1024, 2048, 4096)
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "--expt-relaxed-constexpr",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-Xcompiler", "-fPIC",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA extension cannot be built (there is no CPU fallback)")
+
+
+def _newest_header() -> float:
+    hs = [os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(os.path.dirname(PKG), "include", "mlxa_cuda.h"))
+    hs.append(os.path.abspath(__file__))
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def _units():
+    units = [("api.o", "api.cu", []), ("util_kernels.o", "util_kernels.cu", [])]
+    for nf in PLANNED_NFFT:
+        units.append((f"fwd_{nf}.o", "fwd_inst.cu", [f"-DMLXA_NFFT={nf}"]))
+        units.append((f"inv_{nf}.o", "inv_inst.cu", [f"-DMLXA_NFFT={nf}"]))
+    return units
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    hdr_time = _newest_header()
+    jobs = []
+    for obj, src, defs in _units():
+        o, s = os.path.join(OBJ, obj), os.path.join(SRC, src)
+        stale = force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_time)
+        if stale:
+            cmd = [nvcc, *NVCC_FLAGS, *defs, "-c", s, "-o", o]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            jobs.append((obj, cmd))
+
+    def run(job):
+        name, cmd = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return name, r.returncode, r.stdout + r.stderr
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
+            for name, rc, log in ex.map(run, jobs):
+                if verbose and log.strip():
+                    print(f"--- {name}\n{log}")
+                if rc != 0:
+                    raise RuntimeError(f"nvcc failed on {name}:\n{log}")
+    objs = [os.path.join(OBJ, u[0]) for u in _units()]
+    if jobs or force or not os.path.exists(LIB):
+        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(a.force, a.verbose))

@@ -1,0 +1,435 @@
+// extern "C" boundary of libmlxaudio_cuda.so (declared in include/mlxa_cuda.h): argument
+// checks, per-device constant tables (twiddles), dispatch to the per-n_fft kernels.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../../include/mlxa_cuda.h"
+#include "common.cuh"
+#include "util_kernels.cuh"
+
+namespace mlxa {
+#define X(NF) MLXA_DECL_LAUNCHERS(NF)
+X(64) X(128) X(256) X(400) X(512) X(1024) X(2048) X(4096)
+#undef X
+}  // namespace mlxa
+
+using namespace mlxa;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+#define CHECK_ARG(cond, msg) \
+    if (!(cond)) return fail(MLXA_E_INVALID, msg)
+#define CHECK_CUDA(expr, where)                      \
+    do {                                             \
+        cudaError_t e__ = (expr);                    \
+        if (e__ != cudaSuccess) return cuda_fail(e__, where); \
+    } while (0)
+
+bool has_plan(int n_fft) {
+    switch (n_fft) {
+        case 64: case 128: case 256: case 400: case 512: case 1024: case 2048: case 4096: return true;
+    }
+    return false;
+}
+
+// ---- per-(device, n_fft) constant tables; the only device memory the library owns ----------
+struct Tables {
+    float2* tw_plan = nullptr;    // plan twiddles, or exp(-2*pi*i*j/n_fft) j<n_fft for the naive DFT
+    float2* tw_unpack = nullptr;  // exp(-i*pi*k/N)
+};
+std::mutex g_mu;
+std::map<std::pair<int, int>, Tables> g_tables;
+
+cudaError_t upload(const std::vector<float2>& h, float2** d) {
+    *d = nullptr;
+    if (h.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc(d, h.size() * sizeof(float2));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice);
+}
+
+cudaError_t get_tables(int n_fft, Tables* out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_pair(dev, n_fft);
+    auto it = g_tables.find(key);
+    if (it != g_tables.end()) { *out = it->second; return cudaSuccess; }
+    std::vector<float2> plan, unpack;
+    int np = 0, nu = 0;
+    switch (n_fft) {
+#define X(NF)                                                        \
+    case NF:                                                         \
+        plan_tables_##NF(nullptr, &np, nullptr, &nu);                \
+        plan.resize(np); unpack.resize(nu);                          \
+        plan_tables_##NF(plan.data(), &np, unpack.data(), &nu);      \
+        break;
+        X(64) X(128) X(256) X(400) X(512) X(1024) X(2048) X(4096)
+#undef X
+        default:
+            plan.resize(n_fft);
+            for (int j = 0; j < n_fft; ++j) {
+                const double a = -2.0 * kPi * double(j) / double(n_fft);
+                plan[j] = make_float2(float(std::cos(a)), float(std::sin(a)));
+            }
+    }
+    Tables t;
+    if ((e = upload(plan, &t.tw_plan)) != cudaSuccess) return e;
+    if ((e = upload(unpack, &t.tw_unpack)) != cudaSuccess) return e;
+    g_tables[key] = t;
+    *out = t;
+    return cudaSuccess;
+}
+
+cudaError_t dispatch_fwd(int ep, FwdParams& p, cudaStream_t s) {
+    switch (p.n_fft) {
+#define X(NF) case NF: return launch_fwd_##NF(ep, p, s);
+        X(64) X(128) X(256) X(400) X(512) X(1024) X(2048) X(4096)
+#undef X
+    }
+    return launch_fwd_naive(ep, p, s);
+}
+
+int frames_for(int64_t L, int n_fft, int hop, int center, int64_t* T, int* pad) {
+    *pad = center ? n_fft / 2 : 0;
+    const int64_t Lp = L + 2 * (int64_t)(*pad);
+    if (Lp < n_fft) return -1;
+    *T = 1 + (Lp - n_fft) / hop;
+    return 0;
+}
+
+int fill_fwd_common(FwdParams& p, const float* y, int64_t B, int64_t L, int64_t ldy, const float* window, int n_fft,
+                    int hop, int center, int pad_mode) {
+    CHECK_ARG(y && window, "null pointer");
+    CHECK_ARG(B > 0 && L > 0 && B < (1LL << 31) && L < (1LL << 30), "bad clip shape");
+    CHECK_ARG(ldy >= L, "ldy < L");
+    CHECK_ARG(n_fft >= 2 && hop >= 1 && hop <= n_fft, "bad n_fft / hop");
+    CHECK_ARG(pad_mode >= 0 && pad_mode <= 2, "unknown pad mode");
+    int pad = 0;
+    int64_t T = 0;
+    CHECK_ARG(frames_for(L, n_fft, hop, center, &T, &pad) == 0, "signal shorter than n_fft");
+    CHECK_ARG(!(center && pad_mode == MLXA_PAD_REFLECT && pad > L - 1), "reflect padding needs n_fft/2 <= L-1");
+    CHECK_ARG(T < (1LL << 31) && B <= 65535, "too many frames / clips per launch");
+    std::memset(&p, 0, sizeof(p));
+    p.y = y; p.ldy = ldy; p.L = (int)L; p.B = (int)B;
+    p.T = (int)T; p.T_valid = (int)T; p.F = n_fft / 2 + 1;
+    p.n_fft = n_fft; p.hop = hop; p.pad = pad; p.pad_mode = pad_mode;
+    p.window = window;
+    Tables t;
+    CHECK_CUDA(get_tables(n_fft, &t), "twiddle tables");
+    p.tw_plan = t.tw_plan; p.tw_unpack = t.tw_unpack;
+    return 0;
+}
+
+// clips are launched in slabs of <= 65535 along grid.y
+template <class F>
+int for_clip_slabs(int64_t B, F&& f) {
+    for (int64_t b0 = 0; b0 < B; b0 += 65535) {
+        int rc = f(b0, std::min<int64_t>(65535, B - b0));
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mlxa_abi_version(void) { return MLXA_ABI_VERSION; }
+const char* mlxa_last_error(void) { return g_err.c_str(); }
+int mlxa_has_fast_plan(int n_fft) { return has_plan(n_fft) ? 1 : 0; }
+
+int mlxa_pad_signal_f32(const float* x, int64_t B, int64_t L, int64_t pad, int mode, float* out, void* stream) {
+    CHECK_ARG(x && out, "null pointer");
+    CHECK_ARG(B > 0 && L > 0 && pad >= 0 && L < (1LL << 30) && pad < (1LL << 30), "bad shape");
+    CHECK_ARG(mode >= 0 && mode <= 2, "unknown pad mode");
+    CHECK_ARG(!(mode == MLXA_PAD_REFLECT && pad > L - 1), "reflect padding needs pad <= L-1");
+    CHECK_CUDA(run_pad(x, B, (int)L, (int)pad, mode, out, (cudaStream_t)stream), "pad_signal");
+    return 0;
+}
+
+int mlxa_frame_signal_f32(const float* x, int64_t B, int64_t L, int frame_length, int hop, float* out, void* stream) {
+    CHECK_ARG(x && out, "null pointer");
+    CHECK_ARG(B > 0 && frame_length > 0 && hop > 0, "bad shape");
+    CHECK_ARG(L >= frame_length, "signal shorter than frame_length");
+    const int64_t T = 1 + (L - frame_length) / hop;
+    CHECK_CUDA(run_frame(x, B, L, frame_length, hop, T, out, (cudaStream_t)stream), "frame_signal");
+    return 0;
+}
+
+int mlxa_overlap_add_f32(const float* frames, const float* window, int64_t B, int64_t T, int n_fft, int hop,
+                         int64_t out_len, float* out, void* stream) {
+    CHECK_ARG(frames && window && out, "null pointer");
+    CHECK_ARG(B > 0 && T > 0 && n_fft > 0 && hop > 0 && out_len > 0, "bad shape");
+    CHECK_CUDA(run_ola(frames, window, B, T, n_fft, hop, out_len, 0, out_len, out_len, out, (cudaStream_t)stream), "overlap_add");
+    return 0;
+}
+
+int mlxa_window_sumsquare_f32(const float* window, int n_fft, int hop, int64_t T, int64_t out_len, float* wss, void* stream) {
+    CHECK_ARG(window && wss, "null pointer");
+    CHECK_ARG(T > 0 && n_fft > 0 && hop > 0 && out_len > 0, "bad shape");
+    CHECK_CUDA(run_wss(window, n_fft, hop, T, out_len, wss, (cudaStream_t)stream), "window_sumsquare");
+    return 0;
+}
+
+int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window, int n_fft, int hop,
+                  int center, int pad_mode, mlxa_c64* spec, void* stream) {
+    CHECK_ARG(spec, "null pointer");
+    return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
+        FwdParams p;
+        int rc = fill_fwd_common(p, y + b0 * ldy, nb, L, ldy, window, n_fft, hop, center, pad_mode);
+        if (rc) return rc;
+        p.spec = reinterpret_cast<float2*>(spec) + b0 * (int64_t)p.T * p.F;
+        CHECK_CUDA(dispatch_fwd(EP_STFT, p, (cudaStream_t)stream), "stft");
+        return 0;
+    });
+}
+
+int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window, int n_fft, int hop,
+                     int center, int pad_mode, float power, const int32_t* band_start, const int32_t* band_len,
+                     const int32_t* band_off, const float* band_w, int n_bands, float* mel, float* gmax, int db_mode,
+                     float db_coef, float db_amin, float db_ref, void* stream) {
+    CHECK_ARG(band_start && band_len && band_off && band_w && mel, "null pointer");
+    CHECK_ARG(n_bands > 0, "n_bands must be positive");
+    return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
+        FwdParams p;
+        int rc = fill_fwd_common(p, y + b0 * ldy, nb, L, ldy, window, n_fft, hop, center, pad_mode);
+        if (rc) return rc;
+        p.power = power;
+        p.power_mode = (power == 2.0f) ? POW_SQUARE : (power == 1.0f ? POW_ABS : POW_GENERAL);
+        p.band_start = band_start; p.band_len = band_len; p.band_off = band_off; p.band_w = band_w;
+        p.n_bands = n_bands;
+        p.mel = mel + b0 * (int64_t)n_bands * p.T;
+        p.gmax = gmax;
+        p.db_mode = db_mode; p.db_coef = db_coef; p.db_amin = db_amin; p.db_ref = db_ref;
+        CHECK_CUDA(dispatch_fwd(EP_MEL, p, (cudaStream_t)stream), "melspec");
+        return 0;
+    });
+}
+
+int mlxa_griffinlim_project_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window, int n_fft,
+                                int hop, int center, int pad_mode, int64_t T, int64_t T_valid, const float* mag,
+                                mlxa_c64* tprev, mlxa_c64* rebuilt, float momentum, void* stream) {
+    CHECK_ARG(mag && rebuilt && (tprev || momentum <= 0.f), "null pointer");
+    CHECK_ARG(T > 0 && T_valid >= 0 && T_valid <= T, "bad frame counts");
+    return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
+        FwdParams p;
+        int rc = fill_fwd_common(p, y + b0 * ldy, nb, L, ldy, window, n_fft, hop, center, pad_mode);
+        if (rc) return rc;
+        CHECK_ARG(T_valid <= p.T, "T_valid exceeds the frames the signal yields");
+        p.T = (int)T; p.T_valid = (int)T_valid;
+        const int64_t off = b0 * T * p.F;
+        p.mag = mag + off;
+        p.tprev = tprev ? reinterpret_cast<float2*>(tprev) + off : nullptr;
+        p.rebuilt = reinterpret_cast<float2*>(rebuilt) + off;
+        p.momentum = momentum;
+        CHECK_CUDA(dispatch_fwd(EP_GL, p, (cudaStream_t)stream), "griffinlim_project");
+        return 0;
+    });
+}
+
+int mlxa_istft_f32(const mlxa_c64* spec, int64_t B, int64_t T, int F_in, const float* window, const float* wss,
+                   int n_fft, int hop, int64_t ola_len, int64_t trim, int64_t out_len, float* y, int64_t ldy,
+                   void* stream) {
+    CHECK_ARG(spec && window && wss && y, "null pointer");
+    CHECK_ARG(B > 0 && T > 0 && F_in > 0 && n_fft >= 2 && hop >= 1, "bad shape");
+    CHECK_ARG(ola_len > 0 && trim >= 0 && out_len > 0 && ldy >= out_len, "bad output geometry");
+    CHECK_ARG(T < (1LL << 31) && ola_len < (1LL << 40), "too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    Tables t;
+    CHECK_CUDA(get_tables(n_fft, &t), "twiddle tables");
+    if (has_plan(n_fft)) {
+        return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
+            InvParams p;
+            std::memset(&p, 0, sizeof(p));
+            p.spec = reinterpret_cast<const float2*>(spec) + b0 * T * F_in;
+            p.B = (int)nb; p.T = (int)T; p.F_in = F_in; p.n_fft = n_fft; p.hop = hop;
+            p.window = window; p.wss = wss; p.tw_plan = t.tw_plan; p.tw_unpack = t.tw_unpack;
+            p.ola_len = ola_len; p.trim = trim; p.out_len = out_len; p.ldy = ldy;
+            p.y = y + b0 * ldy;
+            cudaError_t e = cudaErrorInvalidValue;
+            switch (n_fft) {
+#define X(NF) case NF: e = launch_inv_##NF(p, s); break;
+                X(64) X(128) X(256) X(400) X(512) X(1024) X(2048) X(4096)
+#undef X
+            }
+            CHECK_CUDA(e, "istft");
+            return 0;
+        });
+    }
+    // no compiled plan: O(n^2) inverse DFT into stream-ordered scratch, then the gather OLA
+    float* frames = nullptr;
+    CHECK_CUDA(cudaMallocAsync(&frames, sizeof(float) * (size_t)B * T * n_fft, s), "istft scratch");
+    cudaError_t e = launch_irdft_naive(reinterpret_cast<const float2*>(spec), B * T, F_in, n_fft, t.tw_plan, frames, s);
+    if (e == cudaSuccess) e = run_ola(frames, window, B, T, n_fft, hop, ola_len, trim, out_len, ldy, y, s);
+    cudaFreeAsync(frames, s);
+    CHECK_CUDA(e, "istft (dft fallback)");
+    return 0;
+}
+
+int mlxa_polar_f32(const float* mag, const float* angles, int64_t n, mlxa_c64* out, void* stream) {
+    CHECK_ARG(mag && angles && out && n > 0, "bad argument");
+    CHECK_CUDA(run_polar(mag, angles, n, reinterpret_cast<float2*>(out), (cudaStream_t)stream), "polar");
+    return 0;
+}
+int mlxa_magnitude_f32(const mlxa_c64* z, int64_t n, float* out, void* stream) {
+    CHECK_ARG(z && out && n > 0, "bad argument");
+    CHECK_CUDA(run_magnitude(reinterpret_cast<const float2*>(z), n, out, (cudaStream_t)stream), "magnitude");
+    return 0;
+}
+int mlxa_phase_f32(const mlxa_c64* z, int64_t n, float* out, void* stream) {
+    CHECK_ARG(z && out && n > 0, "bad argument");
+    CHECK_CUDA(run_phase(reinterpret_cast<const float2*>(z), n, out, (cudaStream_t)stream), "phase");
+    return 0;
+}
+int mlxa_transpose_f32(const float* in, int64_t B, int64_t R, int64_t C, float* out, void* stream) {
+    CHECK_ARG(in && out && B > 0 && R > 0 && C > 0 && B <= 65535, "bad argument");
+    CHECK_CUDA(run_transpose_f32(in, B, R, C, out, (cudaStream_t)stream), "transpose");
+    return 0;
+}
+int mlxa_transpose_c64(const mlxa_c64* in, int64_t B, int64_t R, int64_t C, mlxa_c64* out, void* stream) {
+    CHECK_ARG(in && out && B > 0 && R > 0 && C > 0 && B <= 65535, "bad argument");
+    CHECK_CUDA(run_transpose_c64(reinterpret_cast<const float2*>(in), B, R, C, reinterpret_cast<float2*>(out),
+                                 (cudaStream_t)stream), "transpose");
+    return 0;
+}
+int mlxa_max_f32(const float* x, int64_t n, float* gmax, void* stream) {
+    CHECK_ARG(x && gmax && n > 0, "bad argument");
+    CHECK_CUDA(run_max(x, n, gmax, (cudaStream_t)stream), "max");
+    return 0;
+}
+int mlxa_fill_f32(float* x, int64_t n, float value, void* stream) {
+    CHECK_ARG(x && n > 0, "bad argument");
+    CHECK_CUDA(run_fill(x, n, value, (cudaStream_t)stream), "fill");
+    return 0;
+}
+int mlxa_to_db_f32(const float* x, int64_t n, float coef, float amin, float ref_host, const float* ref_dev,
+                   int use_top_db, float top_db, const float* gmax_dev, float* out, void* stream) {
+    CHECK_ARG(x && out && n > 0, "bad argument");
+    CHECK_ARG(!use_top_db || (gmax_dev && top_db > 0), "top_db needs a positive value and the global max");
+    CHECK_CUDA(run_to_db(x, n, coef, amin, ref_host, ref_dev, use_top_db, top_db, gmax_dev, out, (cudaStream_t)stream), "to_db");
+    return 0;
+}
+int mlxa_from_db_f32(const float* x, int64_t n, float ref, float div, float* out, void* stream) {
+    CHECK_ARG(x && out && n > 0 && div != 0.f, "bad argument");
+    CHECK_CUDA(run_from_db(x, n, ref, div, out, (cudaStream_t)stream), "from_db");
+    return 0;
+}
+int mlxa_dct_f32(const float* x, int64_t rows, int n_in, const float* D, int n_out, float* out, void* stream) {
+    CHECK_ARG(x && D && out && rows > 0 && n_in > 0 && n_out > 0, "bad argument");
+    CHECK_ARG((size_t)n_in * 32 <= 200 * 1024, "n_in too large");
+    CHECK_CUDA(run_dct(x, rows, n_in, D, n_out, out, (cudaStream_t)stream), "dct");
+    return 0;
+}
+int mlxa_mfcc_tail_f32(const float* mel, int64_t B, int n_mels, int64_t T, const float* D, int n_mfcc,
+                       const float* lifter, int apply_db, float amin, float ref, int use_top_db, float top_db,
+                       const float* gmax_dev, float* out, void* stream) {
+    CHECK_ARG(mel && D && out && B > 0 && n_mels > 0 && T > 0 && n_mfcc > 0, "bad argument");
+    CHECK_ARG(!(apply_db && use_top_db) || gmax_dev, "top_db needs the global max");
+    CHECK_ARG(B <= 65535, "too many clips per launch");
+    CHECK_ARG((size_t)n_mels * 33 * 4 + (size_t)n_mels * n_mfcc * 4 <= 220 * 1024, "n_mels * n_mfcc too large");
+    CHECK_CUDA(run_mfcc_tail(mel, B, n_mels, T, D, n_mfcc, lifter, apply_db, amin, ref, use_top_db, top_db, gmax_dev,
+                             out, (cudaStream_t)stream), "mfcc_tail");
+    return 0;
+}
+
+// ---- host-buffer end-to-end log-mel -----------------------------------------------------------
+// Clips are processed in chunks on three internal streams so that the H2D copy of chunk i+1,
+// the kernels of chunk i and the D2H copy of chunk i-1 overlap.  When the dB step needs the
+// batch-global max, mel stays on the device until every chunk is done; the dB pass + D2H then
+// run chunk by chunk as well.
+int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float* window_host, int n_fft, int hop,
+                         int center, int pad_mode, float power, const int32_t* band_start_host,
+                         const int32_t* band_len_host, const int32_t* band_off_host, const float* band_w_host,
+                         int n_bands, int64_t n_weights, int apply_db, int ref_is_max, float ref, float amin,
+                         int use_top_db, float top_db, float* out_host) {
+    CHECK_ARG(y_host && window_host && out_host && band_start_host && band_len_host && band_off_host && band_w_host,
+              "null pointer");
+    CHECK_ARG(B > 0 && L > 0 && n_bands > 0 && n_weights > 0, "bad shape");
+    int pad = 0;
+    int64_t T = 0;
+    CHECK_ARG(n_fft >= 2 && hop >= 1 && hop <= n_fft, "bad n_fft / hop");
+    CHECK_ARG(frames_for(L, n_fft, hop, center, &T, &pad) == 0, "signal shorter than n_fft");
+    const bool need_max = apply_db && (ref_is_max || use_top_db);
+    const int NS = 3;
+    cudaStream_t st[NS];
+    cudaEvent_t done[NS];
+    for (int i = 0; i < NS; ++i) {
+        CHECK_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking), "stream");
+        CHECK_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming), "event");
+    }
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(B, (B + 7) / 8));
+    float *d_y = nullptr, *d_mel = nullptr, *d_win = nullptr, *d_w = nullptr, *d_gmax = nullptr;
+    int32_t* d_bands = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaFree(d_y); cudaFree(d_mel); cudaFree(d_win); cudaFree(d_w); cudaFree(d_gmax); cudaFree(d_bands);
+        for (int i = 0; i < NS; ++i) { cudaStreamDestroy(st[i]); cudaEventDestroy(done[i]); }
+    };
+#define E2E(expr, where) { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { rc = cuda_fail(e__, where); cleanup(); return rc; } }
+    E2E(cudaMalloc(&d_y, sizeof(float) * (size_t)B * L), "malloc clips");
+    E2E(cudaMalloc(&d_mel, sizeof(float) * (size_t)B * n_bands * T), "malloc mel");
+    E2E(cudaMalloc(&d_win, sizeof(float) * n_fft), "malloc window");
+    E2E(cudaMalloc(&d_w, sizeof(float) * n_weights), "malloc weights");
+    E2E(cudaMalloc(&d_bands, sizeof(int32_t) * 3 * n_bands), "malloc bands");
+    E2E(cudaMalloc(&d_gmax, sizeof(float)), "malloc gmax");
+    E2E(cudaMemcpy(d_win, window_host, sizeof(float) * n_fft, cudaMemcpyHostToDevice), "copy window");
+    E2E(cudaMemcpy(d_w, band_w_host, sizeof(float) * n_weights, cudaMemcpyHostToDevice), "copy weights");
+    E2E(cudaMemcpy(d_bands, band_start_host, sizeof(int32_t) * n_bands, cudaMemcpyHostToDevice), "copy bands");
+    E2E(cudaMemcpy(d_bands + n_bands, band_len_host, sizeof(int32_t) * n_bands, cudaMemcpyHostToDevice), "copy bands");
+    E2E(cudaMemcpy(d_bands + 2 * n_bands, band_off_host, sizeof(int32_t) * n_bands, cudaMemcpyHostToDevice), "copy bands");
+    E2E(cudaMemset(d_gmax, 0, sizeof(float)), "memset");
+    const bool fuse_db = apply_db && !need_max;
+    int ci = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++ci) {
+        const int64_t nb = std::min(chunk, B - b0);
+        cudaStream_t s = st[ci % NS];
+        E2E(cudaMemcpyAsync(d_y + b0 * L, y_host + b0 * L, sizeof(float) * (size_t)nb * L, cudaMemcpyHostToDevice, s), "h2d");
+        rc = mlxa_melspec_f32(d_y + b0 * L, nb, L, L, d_win, n_fft, hop, center, pad_mode, power, d_bands,
+                              d_bands + n_bands, d_bands + 2 * n_bands, d_w, n_bands, d_mel + b0 * n_bands * T,
+                              need_max ? d_gmax : nullptr, fuse_db ? 1 : 0, 10.0f, amin, ref, s);
+        if (rc) { cleanup(); return rc; }
+        if (!need_max)
+            E2E(cudaMemcpyAsync(out_host + b0 * n_bands * T, d_mel + b0 * n_bands * T, sizeof(float) * (size_t)nb * n_bands * T,
+                                cudaMemcpyDeviceToHost, s), "d2h");
+        E2E(cudaEventRecord(done[ci % NS], s), "event");
+    }
+    if (need_max) {
+        for (int i = 0; i < NS; ++i)
+            for (int j = 0; j < NS; ++j)
+                if (i != j) E2E(cudaStreamWaitEvent(st[i], done[j], 0), "wait");
+        ci = 0;
+        for (int64_t b0 = 0; b0 < B; b0 += chunk, ++ci) {
+            const int64_t nb = std::min(chunk, B - b0);
+            cudaStream_t s = st[ci % NS];
+            float* m = d_mel + b0 * n_bands * T;
+            rc = mlxa_to_db_f32(m, nb * n_bands * T, 10.0f, amin, ref, ref_is_max ? d_gmax : nullptr, use_top_db, top_db,
+                                d_gmax, m, s);
+            if (rc) { cleanup(); return rc; }
+            E2E(cudaMemcpyAsync(out_host + b0 * n_bands * T, m, sizeof(float) * (size_t)nb * n_bands * T,
+                                cudaMemcpyDeviceToHost, s), "d2h");
+        }
+    }
+    for (int i = 0; i < NS; ++i) E2E(cudaStreamSynchronize(st[i]), "sync");
+#undef E2E
+    cleanup();
+    return 0;
+}
+
+}  // extern "C"

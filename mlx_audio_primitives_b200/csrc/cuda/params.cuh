@@ -1,0 +1,70 @@
+// Parameter blocks shared by the per-n_fft translation units and the C-ABI dispatcher.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mlxa {
+
+enum : int { EP_STFT = 0, EP_MEL = 1, EP_GL = 2 };
+enum : int { POW_SQUARE = 0, POW_ABS = 1, POW_GENERAL = 2 };
+
+struct FwdParams {
+    // input clips
+    const float* y;
+    long long ldy;
+    int L, B;
+    // framing
+    int T;        // frames produced per clip
+    int T_valid;  // frames >= T_valid see all-zero input (Griffin-Lim frame padding)
+    int F;        // n_fft/2 + 1
+    int n_fft, hop, pad, pad_mode;
+    int tile_frames;  // frames per CTA
+    const float* window;      // n_fft
+    const float2* tw_plan;    // inter-pass twiddles of the plan (or the full table for the naive DFT)
+    const float2* tw_unpack;  // exp(-i*pi*k/N), k in [0, N]  (packed real transform)
+    // EP_STFT
+    float2* spec;  // (B, T, F)
+    // EP_MEL
+    int power_mode;
+    float power;
+    const int* band_start;
+    const int* band_len;
+    const int* band_off;
+    const float* band_w;
+    int n_bands;
+    float* mel;   // (B, n_bands, T)
+    float* gmax;  // optional running max
+    int db_mode;
+    float db_coef, db_amin, db_ref;
+    // EP_GL
+    const float* mag;  // (B, T, F)
+    float2* tprev;     // (B, T, F), in/out
+    float2* rebuilt;   // (B, T, F), out
+    float momentum;
+};
+
+struct InvParams {
+    const float2* spec;  // (B, T, F_in)
+    int B, T, F_in;
+    int n_fft, hop;
+    int tile_hops;       // output tile = tile_hops * hop samples
+    const float* window; // n_fft
+    const float* wss;    // ola_len
+    const float2* tw_plan;
+    const float2* tw_unpack;
+    long long ola_len, trim, out_len, ldy;
+    float* y;            // (B, out_len)
+};
+
+// one launcher per compiled n_fft (fwd_inst.cu / inv_inst.cu built with -DMLXA_NFFT=...)
+#define MLXA_DECL_LAUNCHERS(NF)                                                            \
+    cudaError_t launch_fwd_##NF(int ep, FwdParams& p, cudaStream_t s);                     \
+    cudaError_t launch_inv_##NF(InvParams& p, cudaStream_t s);                             \
+    void plan_tables_##NF(float2* tw_plan_host, int* n_plan, float2* tw_unpack_host, int* n_unpack);
+
+// naive O(n^2) DFT fallback for any other n_fft
+cudaError_t launch_fwd_naive(int ep, FwdParams& p, cudaStream_t s);
+cudaError_t launch_irdft_naive(const float2* spec, long long rows, int F_in, int n_fft,
+                               const float2* tw_full, float* frames, cudaStream_t s);
+
+}  // namespace mlxa

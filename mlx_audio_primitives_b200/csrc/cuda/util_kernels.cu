@@ -1,0 +1,411 @@
+// Small kernels around the fused transforms: the reference-granularity pad / frame /
+// overlap-add entry points, the dB family with its global-max reduction, the MFCC tail,
+// elementwise complex helpers and the O(n^2) DFT used for n_fft values without a compiled plan.
+#include "fwd_epilogue.cuh"
+#include "util_kernels.cuh"
+
+namespace mlxa {
+
+constexpr int kThreads = 256;
+static inline unsigned grid_for(long long n, int per_block, unsigned cap = 148u * 32u) {
+    long long g = (n + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    return (unsigned)(g > cap ? cap : g);
+}
+
+// ---- pad / frame / overlap-add (reference granularity) -----------------------------------
+__global__ void pad_kernel(const float* __restrict__ x, long long B, int L, int pad, int mode,
+                           float* __restrict__ out) {
+    const long long W = (long long)L + 2 * pad;
+    const long long n = B * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / W;
+        const int q = int(i - b * W);
+        out[i] = load_padded(x + b * L, L, q - pad, mode);
+    }
+}
+
+__global__ void frame_kernel(const float* __restrict__ x, long long B, long long L, int fl, int hop,
+                             long long T, float* __restrict__ out) {
+    const long long n = B * T * fl;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int s = int(i % fl);
+        const long long bt = i / fl;
+        const long long t = bt % T, b = bt / T;
+        out[i] = __ldg(x + b * L + t * hop + s);  // frames[b,t,s] = x[b, t*hop + s]
+    }
+}
+
+// frame range covering output sample i: overlap_add.metal:36-37
+__device__ __forceinline__ void ola_range(long long i, int n_fft, int hop, long long T, long long& f0, long long& f1) {
+    f0 = (i < n_fft) ? 0 : (i - n_fft) / hop + 1;
+    f1 = i / hop;
+    if (f1 > T - 1) f1 = T - 1;
+}
+
+__global__ void wss_kernel(const float* __restrict__ w, int n_fft, int hop, long long T, long long out_len,
+                           float* __restrict__ wss) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < out_len; i += (long long)gridDim.x * blockDim.x) {
+        long long f0, f1;
+        ola_range(i, n_fft, hop, T, f0, f1);
+        float s = 0.f;
+        for (long long f = f0; f <= f1; ++f) {
+            const float v = __ldg(w + (i - f * hop));
+            s += v * v;
+        }
+        wss[i] = s;
+    }
+}
+
+__global__ void ola_kernel(const float* __restrict__ frames, const float* __restrict__ w, long long B, long long T,
+                           int n_fft, int hop, long long ola_len, long long trim, long long out_len, long long ldy,
+                           float* __restrict__ y) {
+    const long long n = B * out_len;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / out_len, j = idx - b * out_len;
+        const long long i = j + trim;
+        float val = 0.f;
+        if (i < ola_len) {
+            long long f0, f1;
+            ola_range(i, n_fft, hop, T, f0, f1);
+            float s = 0.f, ws = 0.f;
+            const float* fb = frames + b * T * n_fft;
+            for (long long f = f0; f <= f1; ++f) {
+                const int k = int(i - f * hop);
+                const float wv = __ldg(w + k);
+                s += wv * __ldg(fb + f * n_fft + k);
+                ws += wv * wv;
+            }
+            val = s / fmaxf(ws, 1e-8f);
+        }
+        y[b * ldy + j] = val;
+    }
+}
+
+// ---- elementwise ------------------------------------------------------------------------
+__global__ void magnitude_kernel(const float2* __restrict__ z, long long n, float* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 v = z[i];
+        out[i] = hypotf(v.x, v.y);
+    }
+}
+__global__ void phase_kernel(const float2* __restrict__ z, long long n, float* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 v = z[i];
+        out[i] = atan2f(v.y, v.x);
+    }
+}
+__global__ void polar_kernel(const float* __restrict__ mag, const float* __restrict__ ang, long long n,
+                             float2* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float s, c;
+        sincosf(ang[i], &s, &c);
+        const float m = mag[i];
+        out[i] = make_float2(m * c, m * s);
+    }
+}
+__global__ void fill_kernel(float* x, long long n, float v) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = v;
+}
+
+// batched (R, C) -> (C, R) through a padded smem tile (coalesced both ways)
+template <class T>
+__global__ void transpose_kernel(const T* __restrict__ in, long long R, long long C, T* __restrict__ out) {
+    __shared__ T tile[32][33];
+    const long long b = blockIdx.z;
+    const T* ib = in + b * R * C;
+    T* ob = out + b * R * C;
+    const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const long long r = r0 + j, c = c0 + threadIdx.x;
+        if (r < R && c < C) tile[j][threadIdx.x] = ib[r * C + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const long long c = c0 + j, r = r0 + threadIdx.x;
+        if (r < R && c < C) ob[c * R + r] = tile[threadIdx.x][j];
+    }
+}
+
+// ---- global max ---------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+__global__ void max_kernel(const float* __restrict__ x, long long n, float* gmax) {
+    float m = -INFINITY;
+    const long long n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = x4[i];
+        m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, x[i]);
+    __shared__ float s[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < kThreads / 32; ++i) m = fmaxf(m, s[i]);
+        if (m > -INFINITY) atomic_max_float(gmax, m);
+    }
+}
+
+// ---- dB family (convert.py:14-60) ---------------------------------------------------------
+__device__ __forceinline__ float to_db_one(float x, float coef, float amin, float refc) {
+    return coef * log10f(fmaxf(x, amin) / refc);
+}
+__global__ void to_db_kernel(const float* __restrict__ x, long long n, float coef, float amin, float ref_host,
+                             const float* __restrict__ ref_dev, int use_top, float top_db,
+                             const float* __restrict__ gmax, float* __restrict__ out) {
+    const float ref = ref_dev ? __ldg(ref_dev) : ref_host;
+    const float refc = fmaxf(ref, amin);
+    float floor_db = -INFINITY;
+    if (use_top) floor_db = to_db_one(__ldg(gmax), coef, amin, refc) - top_db;
+    const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const long long n4 = al ? n / 4 : 0;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = x4[i];
+        v.x = fmaxf(to_db_one(v.x, coef, amin, refc), floor_db);
+        v.y = fmaxf(to_db_one(v.y, coef, amin, refc), floor_db);
+        v.z = fmaxf(to_db_one(v.z, coef, amin, refc), floor_db);
+        v.w = fmaxf(to_db_one(v.w, coef, amin, refc), floor_db);
+        o4[i] = v;
+    }
+    for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = fmaxf(to_db_one(x[i], coef, amin, refc), floor_db);
+}
+__global__ void from_db_kernel(const float* __restrict__ x, long long n, float ref, float div, float* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = ref * powf(10.0f, x[i] / div);
+}
+
+// ---- DCT (rows, n_in) @ D^T and the fused MFCC tail -----------------------------------------
+__global__ void dct_kernel(const float* __restrict__ x, long long rows, int n_in, const float* __restrict__ D,
+                           int n_out, float* __restrict__ out) {
+    extern __shared__ float s_x[];  // [8][n_in]
+    const long long r0 = (long long)blockIdx.x * 8;
+    const int nr = int(min(8LL, rows - r0));
+    for (int i = threadIdx.x; i < nr * n_in; i += blockDim.x) s_x[i] = x[r0 * n_in + i];
+    __syncthreads();
+    for (int o = threadIdx.x; o < nr * n_out; o += blockDim.x) {
+        const int r = o / n_out, k = o - r * n_out;
+        const float* d = D + (long long)k * n_in;
+        const float* xr = s_x + r * n_in;
+        float acc = 0.f;
+        for (int m = 0; m < n_in; ++m) acc = fmaf(xr[m], __ldg(d + m), acc);
+        out[(r0 + r) * n_out + k] = acc;
+    }
+}
+
+// mel (B, n_mels, T) -> dB -> DCT over the mel axis -> lifter -> (B, n_mfcc, T); lanes along T
+__global__ void mfcc_tail_kernel(const float* __restrict__ mel, int n_mels, long long T, const float* __restrict__ D,
+                                 int n_mfcc, const float* __restrict__ lifter, int apply_db, float amin, float ref,
+                                 int use_top, float top_db, const float* __restrict__ gmax, float* __restrict__ out) {
+    extern __shared__ float s_m[];          // [n_mels][33] dB tile, then D^T [n_mels][n_mfcc]
+    float* s_d = s_m + n_mels * 33;
+    const long long b = blockIdx.y, t0 = (long long)blockIdx.x * 32;
+    const int nt = int(min(32LL, T - t0));
+    const float refc = fmaxf(ref, amin);
+    float floor_db = -INFINITY;
+    if (apply_db && use_top) floor_db = to_db_one(__ldg(gmax), 10.0f, amin, refc) - top_db;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int m = warp; m < n_mels; m += nw) {
+        float v = 0.f;
+        if (lane < nt) {
+            v = __ldg(mel + (b * n_mels + m) * T + t0 + lane);
+            if (apply_db) v = fmaxf(to_db_one(v, 10.0f, amin, refc), floor_db);
+        }
+        s_m[m * 33 + lane] = v;
+    }
+    for (int i = threadIdx.x; i < n_mels * n_mfcc; i += blockDim.x) {
+        const int k = i / n_mels, m = i - k * n_mels;
+        s_d[m * n_mfcc + k] = __ldg(D + i);
+    }
+    __syncthreads();
+    for (int k = warp; k < n_mfcc; k += nw) {
+        float a0 = 0.f, a1 = 0.f;
+        int m = 0;
+        for (; m + 1 < n_mels; m += 2) {
+            a0 = fmaf(s_d[m * n_mfcc + k], s_m[m * 33 + lane], a0);
+            a1 = fmaf(s_d[(m + 1) * n_mfcc + k], s_m[(m + 1) * 33 + lane], a1);
+        }
+        if (m < n_mels) a0 = fmaf(s_d[m * n_mfcc + k], s_m[m * 33 + lane], a0);
+        float v = a0 + a1;
+        if (lifter) v *= __ldg(lifter + k);
+        if (lane < nt) out[(b * n_mfcc + k) * T + t0 + lane] = v;
+    }
+}
+
+// ---- O(n^2) DFT fallback: any n_fft, same epilogues as the planned kernels -----------------
+template <int EP>
+__global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int TT = p.tile_frames, n_fft = p.n_fft;
+    const int b = blockIdx.y, t0 = blockIdx.x * TT, nt = min(TT, p.T - t0);
+    float* s_x = reinterpret_cast<float*>(smem_raw);  // [8 warps][n_fft] windowed frames
+    float* s_ep = s_x + 8 * n_fft;
+    __shared__ float s_red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* yb = p.y + (long long)b * p.ldy;
+    float* xw = s_x + warp * n_fft;
+    for (int f = warp; f < nt; f += 8) {
+        const int t = t0 + f;
+        const bool valid = t < p.T_valid;
+        for (int n = lane; n < n_fft; n += 32)
+            xw[n] = valid ? load_padded(yb, p.L, t * p.hop - p.pad + n, p.pad_mode) * __ldg(p.window + n) : 0.f;
+        __syncwarp();
+        for (int k = lane; k < p.F; k += 32) {
+            float re = 0.f, im = 0.f;
+            int idx = 0;
+            for (int n = 0; n < n_fft; ++n) {
+                const float2 w = __ldg(p.tw_plan + idx);  // exp(-2*pi*i*idx/n_fft)
+                re = fmaf(xw[n], w.x, re);
+                im = fmaf(xw[n], w.y, im);
+                idx += k;
+                if (idx >= n_fft) idx -= n_fft;
+            }
+            epilogue_bin<EP>(p, b, t, f, k, make_float2(re, im), s_ep, TT + 1);
+        }
+        __syncwarp();
+    }
+    if constexpr (EP == EP_MEL) {
+        __syncthreads();
+        mel_phase<256>(p, b, t0, nt, s_ep, TT, s_red);
+    }
+}
+
+cudaError_t launch_fwd_naive(int ep, FwdParams& p, cudaStream_t s) {
+    int TT = (ep == EP_MEL) ? 8 : 8;
+    size_t smem = size_t(8) * p.n_fft * 4 + (ep == EP_MEL ? size_t(p.F) * (TT + 1) * 4 : 0);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    p.tile_frames = TT;
+    dim3 grid((p.T + TT - 1) / TT, p.B);
+    cudaError_t e;
+#define MLXA_LAUNCH(EPV)                                                                               \
+    e = cudaFuncSetAttribute(fwd_naive_kernel<EPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                    \
+    fwd_naive_kernel<EPV><<<grid, 256, smem, s>>>(p);
+    if (ep == EP_STFT) { MLXA_LAUNCH(EP_STFT) }
+    else if (ep == EP_MEL) { MLXA_LAUNCH(EP_MEL) }
+    else { MLXA_LAUNCH(EP_GL) }
+#undef MLXA_LAUNCH
+    return cudaGetLastError();
+}
+
+// frames[row, n] = irfft(spec[row, :F_in], n=n_fft)[n]  (1/n normalised; imag of DC/Nyquist ignored)
+__global__ void irdft_naive_kernel(const float2* __restrict__ spec, long long rows, int F_in, int n_fft,
+                                   const float2* __restrict__ tw, float* __restrict__ frames) {
+    extern __shared__ float2 s_X[];  // [F] bins of this row
+    const long long row = blockIdx.x;
+    const int F = n_fft / 2 + 1;
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+        float2 v = (k < F_in) ? spec[row * F_in + k] : make_float2(0.f, 0.f);
+        if (k == 0 || 2 * k == n_fft) v.y = 0.f;
+        s_X[k] = v;
+    }
+    __syncthreads();
+    const float inv = 1.0f / float(n_fft);
+    for (int n = threadIdx.x; n < n_fft; n += blockDim.x) {
+        float acc = s_X[0].x;
+        int idx = 0;
+        for (int k = 1; k < F; ++k) {
+            idx += n;
+            if (idx >= n_fft) idx -= n_fft;
+            const float2 w = __ldg(tw + idx);  // exp(-2*pi*i*k*n/n_fft); need Re(X * conj(w))
+            const float term = fmaf(s_X[k].x, w.x, s_X[k].y * w.y);
+            acc += (2 * k == n_fft) ? term : 2.0f * term;
+        }
+        frames[row * n_fft + n] = acc * inv;
+    }
+}
+
+cudaError_t launch_irdft_naive(const float2* spec, long long rows, int F_in, int n_fft, const float2* tw_full,
+                               float* frames, cudaStream_t s) {
+    const size_t smem = size_t(n_fft / 2 + 1) * 8;
+    irdft_naive_kernel<<<(unsigned)rows, 256, smem, s>>>(spec, rows, F_in, n_fft, tw_full, frames);
+    return cudaGetLastError();
+}
+
+// ---- host launch wrappers -----------------------------------------------------------------
+cudaError_t run_pad(const float* x, long long B, int L, int pad, int mode, float* out, cudaStream_t s) {
+    pad_kernel<<<grid_for(B * ((long long)L + 2 * pad), kThreads), kThreads, 0, s>>>(x, B, L, pad, mode, out);
+    return cudaGetLastError();
+}
+cudaError_t run_frame(const float* x, long long B, long long L, int fl, int hop, long long T, float* out, cudaStream_t s) {
+    frame_kernel<<<grid_for(B * T * fl, kThreads), kThreads, 0, s>>>(x, B, L, fl, hop, T, out);
+    return cudaGetLastError();
+}
+cudaError_t run_wss(const float* w, int n_fft, int hop, long long T, long long out_len, float* wss, cudaStream_t s) {
+    wss_kernel<<<grid_for(out_len, kThreads), kThreads, 0, s>>>(w, n_fft, hop, T, out_len, wss);
+    return cudaGetLastError();
+}
+cudaError_t run_ola(const float* frames, const float* w, long long B, long long T, int n_fft, int hop,
+                    long long ola_len, long long trim, long long out_len, long long ldy, float* y, cudaStream_t s) {
+    ola_kernel<<<grid_for(B * out_len, kThreads), kThreads, 0, s>>>(frames, w, B, T, n_fft, hop, ola_len, trim, out_len, ldy, y);
+    return cudaGetLastError();
+}
+cudaError_t run_magnitude(const float2* z, long long n, float* out, cudaStream_t s) {
+    magnitude_kernel<<<grid_for(n, kThreads), kThreads, 0, s>>>(z, n, out);
+    return cudaGetLastError();
+}
+cudaError_t run_phase(const float2* z, long long n, float* out, cudaStream_t s) {
+    phase_kernel<<<grid_for(n, kThreads), kThreads, 0, s>>>(z, n, out);
+    return cudaGetLastError();
+}
+cudaError_t run_polar(const float* mag, const float* ang, long long n, float2* out, cudaStream_t s) {
+    polar_kernel<<<grid_for(n, kThreads), kThreads, 0, s>>>(mag, ang, n, out);
+    return cudaGetLastError();
+}
+cudaError_t run_fill(float* x, long long n, float v, cudaStream_t s) {
+    fill_kernel<<<grid_for(n, kThreads), kThreads, 0, s>>>(x, n, v);
+    return cudaGetLastError();
+}
+cudaError_t run_transpose_f32(const float* in, long long B, long long R, long long C, float* out, cudaStream_t s) {
+    dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)B), blk(32, 8);
+    transpose_kernel<float><<<grid, blk, 0, s>>>(in, R, C, out);
+    return cudaGetLastError();
+}
+cudaError_t run_transpose_c64(const float2* in, long long B, long long R, long long C, float2* out, cudaStream_t s) {
+    dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)B), blk(32, 8);
+    transpose_kernel<float2><<<grid, blk, 0, s>>>(in, R, C, out);
+    return cudaGetLastError();
+}
+cudaError_t run_max(const float* x, long long n, float* gmax, cudaStream_t s) {
+    max_kernel<<<grid_for(n, kThreads * 8, 148u * 8u), kThreads, 0, s>>>(x, n, gmax);
+    return cudaGetLastError();
+}
+cudaError_t run_to_db(const float* x, long long n, float coef, float amin, float ref_host, const float* ref_dev,
+                      int use_top, float top_db, const float* gmax, float* out, cudaStream_t s) {
+    to_db_kernel<<<grid_for(n, kThreads * 8, 148u * 16u), kThreads, 0, s>>>(x, n, coef, amin, ref_host, ref_dev, use_top, top_db, gmax, out);
+    return cudaGetLastError();
+}
+cudaError_t run_from_db(const float* x, long long n, float ref, float div, float* out, cudaStream_t s) {
+    from_db_kernel<<<grid_for(n, kThreads * 4), kThreads, 0, s>>>(x, n, ref, div, out);
+    return cudaGetLastError();
+}
+cudaError_t run_dct(const float* x, long long rows, int n_in, const float* D, int n_out, float* out, cudaStream_t s) {
+    const size_t smem = size_t(8) * n_in * 4;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dct_kernel<<<(unsigned)((rows + 7) / 8), 128, smem, s>>>(x, rows, n_in, D, n_out, out);
+    return cudaGetLastError();
+}
+cudaError_t run_mfcc_tail(const float* mel, long long B, int n_mels, long long T, const float* D, int n_mfcc,
+                          const float* lifter, int apply_db, float amin, float ref, int use_top, float top_db,
+                          const float* gmax, float* out, cudaStream_t s) {
+    const size_t smem = size_t(n_mels) * 33 * 4 + size_t(n_mels) * n_mfcc * 4;
+    cudaError_t e = cudaFuncSetAttribute(mfcc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((T + 31) / 32), (unsigned)B);
+    mfcc_tail_kernel<<<grid, 256, smem, s>>>(mel, n_mels, T, D, n_mfcc, lifter, apply_db, amin, ref, use_top, top_db, gmax, out);
+    return cudaGetLastError();
+}
+
+}  // namespace mlxa

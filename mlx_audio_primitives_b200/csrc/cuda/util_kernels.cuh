@@ -1,0 +1,25 @@
+// Host launch wrappers implemented in util_kernels.cu
+#pragma once
+#include "params.cuh"
+
+namespace mlxa {
+cudaError_t run_pad(const float* x, long long B, int L, int pad, int mode, float* out, cudaStream_t s);
+cudaError_t run_frame(const float* x, long long B, long long L, int fl, int hop, long long T, float* out, cudaStream_t s);
+cudaError_t run_wss(const float* w, int n_fft, int hop, long long T, long long out_len, float* wss, cudaStream_t s);
+cudaError_t run_ola(const float* frames, const float* w, long long B, long long T, int n_fft, int hop,
+                    long long ola_len, long long trim, long long out_len, long long ldy, float* y, cudaStream_t s);
+cudaError_t run_magnitude(const float2* z, long long n, float* out, cudaStream_t s);
+cudaError_t run_phase(const float2* z, long long n, float* out, cudaStream_t s);
+cudaError_t run_polar(const float* mag, const float* ang, long long n, float2* out, cudaStream_t s);
+cudaError_t run_fill(float* x, long long n, float v, cudaStream_t s);
+cudaError_t run_transpose_f32(const float* in, long long B, long long R, long long C, float* out, cudaStream_t s);
+cudaError_t run_transpose_c64(const float2* in, long long B, long long R, long long C, float2* out, cudaStream_t s);
+cudaError_t run_max(const float* x, long long n, float* gmax, cudaStream_t s);
+cudaError_t run_to_db(const float* x, long long n, float coef, float amin, float ref_host, const float* ref_dev,
+                      int use_top, float top_db, const float* gmax, float* out, cudaStream_t s);
+cudaError_t run_from_db(const float* x, long long n, float ref, float div, float* out, cudaStream_t s);
+cudaError_t run_dct(const float* x, long long rows, int n_in, const float* D, int n_out, float* out, cudaStream_t s);
+cudaError_t run_mfcc_tail(const float* mel, long long B, int n_mels, long long T, const float* D, int n_mfcc,
+                          const float* lifter, int apply_db, float amin, float ref, int use_top, float top_db,
+                          const float* gmax, float* out, cudaStream_t s);
+}  // namespace mlxa

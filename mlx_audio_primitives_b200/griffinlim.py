@@ -1,0 +1,95 @@
+"""Griffin-Lim phase reconstruction (reference ``griffinlim.py``): the loop chains the fused ISTFT
+kernel and the fused STFT+projection kernel on one stream, with no host round-trip inside."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._extension import _ext, check
+from ._tensor import f32c, ptr, stream_ptr
+from ._validation import validate_positive, validate_range
+from .mel import frames_or_raise, pad_mode_code
+from .stft import _istft_physical, istft, magnitude, phase, stft
+from .windows import padded_window
+
+
+def _to_physical_f32(x: torch.Tensor) -> torch.Tensor:
+    """logical (B, F, T) float32 -> contiguous (B, T, F)."""
+    P = x.transpose(1, 2)
+    if P.is_contiguous():
+        return P
+    x = x.contiguous()
+    B, F, T = x.shape
+    out = torch.empty((B, T, F), dtype=torch.float32, device=x.device)
+    check(_ext.mlxa_transpose_f32(ptr(x), B, F, T, ptr(out), stream_ptr(x)), "transpose")
+    return out
+
+
+def griffinlim(S, n_iter: int = 32, hop_length: int | None = None, win_length: int | None = None,
+               n_fft: int | None = None, window="hann", center: bool = True, length: int | None = None,
+               pad_mode: str = "constant", momentum: float = 0.99, init: str = "random", random_state=None):
+    """Reconstruct a signal from a magnitude spectrogram (reference griffinlim.py:17-196).
+
+    The update is the reference's: new = S*exp(j*angle(stft(istft(rebuilt)))),
+    rebuilt = new + momentum*(new - tprev), tprev = new.  The random initial phase is drawn on the
+    host with NumPy's default_rng in (B, F, T) order, like the reference, so seeds reproduce."""
+    validate_positive(n_iter, "n_iter")
+    validate_range(momentum, "momentum", min_val=0.0, max_val=1.0, max_inclusive=False)
+    S = f32c(S)
+    batched = S.ndim == 3
+    if not batched:
+        S = S[None]
+    B, F, T = S.shape
+    if n_fft is None:
+        n_fft = 2 * (F - 1)
+    if hop_length is None:
+        hop_length = n_fft // 4
+    if win_length is None:
+        win_length = n_fft
+    mode = pad_mode_code(pad_mode)
+    rng = np.random.default_rng(random_state)
+    if init == "random":
+        angles_host = rng.uniform(-np.pi, np.pi, (B, F, T)).astype(np.float32)
+        angles = torch.from_numpy(angles_host).to(S.device)
+    elif init == "zeros":
+        angles = torch.zeros((B, F, T), dtype=torch.float32, device=S.device)
+    else:
+        raise ValueError(f"Unknown init: '{init}'. Supported: 'random', 'zeros'")
+    win = padded_window(window, win_length, n_fft)
+    mag = _to_physical_f32(S)                 # (B, T, F)
+    ang = _to_physical_f32(angles)
+    rebuilt = torch.empty((B, T, F, 2), dtype=torch.float32, device=S.device)
+    check(_ext.mlxa_polar_f32(ptr(mag), ptr(ang), mag.numel(), ptr(rebuilt), stream_ptr(S)), "polar")
+    del ang, angles
+    tprev = rebuilt.clone() if momentum > 0 else None
+    rebuilt_c = torch.view_as_complex(rebuilt)
+    y = None
+    for _ in range(n_iter):
+        y = _istft_physical(rebuilt_c, n_fft, hop_length, win, center, length, out=y)
+        L = y.shape[1]
+        T_new = frames_or_raise(L, n_fft, hop_length, center, pad_mode)
+        check(_ext.mlxa_griffinlim_project_f32(ptr(y), B, L, y.stride(0), ptr(win), n_fft, hop_length, int(center),
+                                               mode, T, min(T, T_new), ptr(mag), ptr(tprev), ptr(rebuilt),
+                                               float(momentum), stream_ptr(S)), "griffinlim")
+    y = _istft_physical(rebuilt_c, n_fft, hop_length, win, center, length, out=y)
+    return y if batched else y[0]
+
+
+def griffinlim_iter(S, angles, hop_length: int, win_length: int, n_fft: int, window="hann", center: bool = True,
+                    pad_mode: str = "constant", momentum: float = 0.99, tprev=None):
+    """One iteration + reconstruction MSE (reference griffinlim.py:199-284), composed from the
+    public kernels; meant for custom stopping rules, not for speed."""
+    S = f32c(S)
+    angles = f32c(angles)
+    rebuilt = torch.polar(S, angles)
+    y = istft(rebuilt, hop_length=hop_length, win_length=win_length, n_fft=n_fft, window=window, center=center)
+    new = stft(y, n_fft=n_fft, hop_length=hop_length, win_length=win_length, window=window, center=center,
+               pad_mode=pad_mode)
+    error = torch.mean((S - magnitude(new)) ** 2)
+    new_angles = phase(new)
+    new = torch.polar(S, new_angles)
+    if momentum > 0 and tprev is not None:
+        out = new + momentum * (new - tprev)
+    else:
+        out = new
+    return new_angles, out, error

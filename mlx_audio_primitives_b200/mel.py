@@ -1,0 +1,235 @@
+"""Mel scale, triangular filterbanks and the fused mel spectrogram (reference ``mel.py``).
+
+Filterbank matrices are built on the host exactly like the reference builds them (float64
+slopes, +1e-10 in the denominators, float32 cast *before* the Slaney area scaling) and kept
+resident per device in two forms: the dense (n_bands, F) matrix the public API returns, and the
+band-sparse rows (contiguous support per band) that the fused kernel consumes.
+"""
+from __future__ import annotations
+
+import math
+import threading
+from dataclasses import dataclass
+from functools import lru_cache
+
+import numpy as np
+import torch
+
+from . import _peaks
+from ._extension import _ext, check
+from ._tensor import f32c, ptr, require_cuda, stream_ptr
+from ._validation import validate_non_negative, validate_positive
+from .windows import padded_window
+
+# Slaney auditory-toolbox constants (reference mel.py:25-28)
+_LIN_STEP_HZ = 200.0 / 3
+_BREAK_HZ = 1000.0
+_BREAK_MEL = _BREAK_HZ / _LIN_STEP_HZ
+_LOG_STEP = math.log(6.4) / 27.0
+
+
+def hz_to_mel(frequencies, htk: bool = False) -> np.ndarray:
+    """Host NumPy in/out like the reference (mel.py:31-62)."""
+    f = np.asarray(frequencies, dtype=np.float64)
+    if htk:
+        return 2595.0 * np.log10(1.0 + f / 700.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        log_part = _BREAK_MEL + np.log(f / _BREAK_HZ) / _LOG_STEP
+    return np.where(f < _BREAK_HZ, f / _LIN_STEP_HZ, log_part)
+
+
+def mel_to_hz(mels, htk: bool = False) -> np.ndarray:
+    """Host NumPy in/out like the reference (mel.py:65-93)."""
+    m = np.asarray(mels, dtype=np.float64)
+    if htk:
+        return 700.0 * (10.0 ** (m / 2595.0) - 1.0)
+    return np.where(m < _BREAK_MEL, _LIN_STEP_HZ * m, _BREAK_HZ * np.exp(_LOG_STEP * (m - _BREAK_MEL)))
+
+
+def triangular_bank_host(edges_hz: np.ndarray, sr: int, n_fft: int, norm) -> np.ndarray:
+    """Triangles between consecutive edge triples (reference mel.py:137-165; the same pattern in
+    filterbanks.py:126-152, 248-265)."""
+    if norm not in ("slaney", None):
+        raise ValueError(f"Unknown norm: '{norm}'. Supported: 'slaney', None")
+    n_bands = edges_hz.shape[0] - 2
+    bin_hz = np.linspace(0, sr / 2.0, 1 + n_fft // 2)[None, :]
+    left, mid, right = edges_hz[:-2, None], edges_hz[1:-1, None], edges_hz[2:, None]
+    up = (bin_hz - left) / (mid - left + 1e-10)
+    down = (right - bin_hz) / (right - mid + 1e-10)
+    bank = np.maximum(0, np.minimum(up, down)).astype(np.float32)
+    if norm == "slaney":
+        bank *= (2.0 / (edges_hz[2:n_bands + 2] - edges_hz[:n_bands]))[:, None]
+    return bank
+
+
+def check_band_args(n_bands, name: str, fmin, fmax, sr):
+    validate_positive(n_bands, name)
+    validate_non_negative(fmin, "fmin")
+    if fmax is None:
+        fmax = sr / 2.0
+    if fmin >= fmax:
+        raise ValueError(f"fmin ({fmin}) must be less than fmax ({fmax})")
+    if fmax > sr / 2.0:
+        raise ValueError(f"fmax ({fmax}) cannot exceed Nyquist frequency ({sr / 2.0})")
+    return fmax
+
+
+@lru_cache(maxsize=64)
+def mel_filterbank_host(sr, n_fft, n_mels, fmin, fmax, htk, norm) -> np.ndarray:
+    edges = mel_to_hz(np.linspace(hz_to_mel(fmin, htk), hz_to_mel(fmax, htk), n_mels + 2), htk)
+    bank = triangular_bank_host(edges, sr, n_fft, norm)
+    bank.setflags(write=False)
+    return bank
+
+
+@dataclass
+class SparseBank:
+    """Band-sparse rows of a filterbank on one device: row m covers bins
+    [start[m], start[m] + length[m]) with weights[offset[m] ...]."""
+    start: torch.Tensor
+    length: torch.Tensor
+    offset: torch.Tensor
+    weights: torch.Tensor
+    n_bands: int
+    n_weights: int
+    host: tuple  # (start, length, offset, weights) NumPy copies for the host-buffer entry point
+
+
+def sparse_rows_host(bank: np.ndarray):
+    n_bands = bank.shape[0]
+    start = np.zeros(n_bands, np.int32)
+    length = np.zeros(n_bands, np.int32)
+    offset = np.zeros(n_bands, np.int32)
+    chunks = []
+    pos = 0
+    for m in range(n_bands):
+        nz = np.flatnonzero(bank[m])
+        if nz.size:
+            start[m], length[m] = nz[0], nz[-1] - nz[0] + 1
+            chunks.append(bank[m, nz[0]:nz[-1] + 1])
+        offset[m] = pos
+        pos += int(length[m])
+    weights = np.concatenate(chunks).astype(np.float32) if chunks else np.zeros(1, np.float32)
+    return start, length, offset, weights
+
+
+_lock = threading.Lock()
+_dense_cache: dict[tuple, torch.Tensor] = {}
+_sparse_cache: dict[tuple, SparseBank] = {}
+
+
+def dense_bank_device(key: tuple, host_fn) -> torch.Tensor:
+    require_cuda()
+    k = key + (torch.cuda.current_device(),)
+    with _lock:
+        t = _dense_cache.get(k)
+        if t is None:
+            t = torch.from_numpy(np.array(host_fn())).cuda()
+            _dense_cache[k] = t
+        return t
+
+
+def sparse_bank_device(key: tuple, host_fn) -> SparseBank:
+    require_cuda()
+    k = key + (torch.cuda.current_device(),)
+    with _lock:
+        sb = _sparse_cache.get(k)
+        if sb is None:
+            rows = sparse_rows_host(np.asarray(host_fn()))
+            dev = [torch.from_numpy(a).cuda() for a in rows]
+            sb = SparseBank(*dev, n_bands=rows[0].shape[0], n_weights=int(rows[3].shape[0]), host=rows)
+            _sparse_cache[k] = sb
+        return sb
+
+
+def mel_filterbank(sr: int, n_fft: int, n_mels: int = 128, fmin: float = 0.0, fmax: float | None = None,
+                   htk: bool = False, norm: str | None = "slaney") -> torch.Tensor:
+    """(n_mels, n_fft // 2 + 1) float32 filterbank resident on the current device
+    (reference mel.py:171-242)."""
+    fmax = check_band_args(n_mels, "n_mels", fmin, fmax, sr)
+    key = ("mel", sr, n_fft, n_mels, float(fmin), float(fmax), bool(htk), norm)
+    return dense_bank_device(key, lambda: mel_filterbank_host(sr, n_fft, n_mels, float(fmin), float(fmax), bool(htk), norm))
+
+
+def _resolve_stft_args(n_fft, hop_length, win_length):
+    if hop_length is None:
+        hop_length = n_fft // 4
+    if win_length is None:
+        win_length = n_fft
+    if hop_length <= 0:
+        raise ValueError(f"hop_length must be positive, got {hop_length}")
+    if win_length <= 0:
+        raise ValueError(f"win_length must be positive, got {win_length}")
+    if win_length > n_fft:
+        raise ValueError(f"win_length ({win_length}) must be <= n_fft ({n_fft})")
+    if hop_length > n_fft:
+        raise ValueError(f"hop_length ({hop_length}) should typically be <= n_fft ({n_fft})")
+    return int(hop_length), int(win_length)
+
+
+_PAD_MODES = {"constant": 0, "reflect": 1, "edge": 2}
+
+
+def pad_mode_code(pad_mode: str) -> int:
+    if pad_mode not in _PAD_MODES:
+        raise ValueError(f"Unknown pad_mode: '{pad_mode}'. Supported: reflect, constant, edge")
+    return _PAD_MODES[pad_mode]
+
+
+def frames_or_raise(L: int, n_fft: int, hop: int, center: bool, pad_mode: str) -> int:
+    """Frame count of the fused kernel, with the reference's error behaviour
+    (_frame_impl.py:51-61; native reflect check pad_signal.cpp:102-105)."""
+    pad = n_fft // 2 if center else 0
+    if center and pad_mode == "reflect" and pad > L - 1:
+        raise ValueError(f"reflect padding ({pad}) requires pad <= signal_length - 1 ({L - 1})")
+    padded = L + 2 * pad
+    if padded < n_fft:
+        raise ValueError(f"Signal length ({padded}) must be >= frame_length ({n_fft}). Consider padding the signal.")
+    return 1 + (padded - n_fft) // hop
+
+
+def _melspec_from_bank(y, bank: SparseBank, n_fft, hop, win_length, window, center, pad_mode, power,
+                       want_peak=True, fused_db=None):
+    mode = pad_mode_code(pad_mode)
+    y = f32c(y)
+    one_d = y.ndim == 1
+    if one_d:
+        y = y[None, :]
+    if y.ndim != 2:
+        raise ValueError(f"y must be 1D or 2D, got {y.ndim}D")
+    B, L = y.shape
+    T = frames_or_raise(L, n_fft, hop, center, pad_mode)
+    win = padded_window(window, win_length, n_fft)
+    out = torch.empty((B, bank.n_bands, T), dtype=torch.float32, device=y.device)
+    peak = torch.zeros(1, dtype=torch.float32, device=y.device) if want_peak else None
+    db = fused_db or (0, 10.0, 1e-10, 1.0)
+    check(_ext.mlxa_melspec_f32(ptr(y), B, L, y.stride(0), ptr(win), n_fft, hop, int(center), mode, float(power),
+                                ptr(bank.start), ptr(bank.length), ptr(bank.offset), ptr(bank.weights),
+                                bank.n_bands, ptr(out), ptr(peak), int(db[0]), float(db[1]), float(db[2]),
+                                float(db[3]), stream_ptr(y)), "melspectrogram")
+    res = out[0] if one_d else out
+    if want_peak:
+        _peaks.remember(res, peak)
+    return res
+
+
+def melspectrogram(y, sr: int = 22050, n_fft: int = 2048, hop_length: int | None = None,
+                   win_length: int | None = None, window="hann", center: bool = True,
+                   pad_mode: str = "constant", power: float = 2.0, n_mels: int = 128, fmin: float = 0.0,
+                   fmax: float | None = None, htk: bool = False, norm: str | None = "slaney") -> torch.Tensor:
+    """Mel spectrogram (n_mels, T) / (B, n_mels, T) (reference mel.py:245-352) in ONE kernel:
+    pad -> frame -> window -> rFFT -> |X|^power -> band-sparse projection; the complex spectrum
+    stays on chip.  The kernel also leaves max(mel) on the device, so a following
+    ``power_to_db(ref=max)`` / ``top_db`` clamp needs no extra reduction pass."""
+    hop, win_length = _resolve_stft_args(n_fft, hop_length, win_length)
+    fmax = check_band_args(n_mels, "n_mels", fmin, fmax, sr)
+    key = ("mel", sr, n_fft, n_mels, float(fmin), float(fmax), bool(htk), norm)
+    bank = sparse_bank_device(key, lambda: mel_filterbank_host(sr, n_fft, n_mels, float(fmin), float(fmax), bool(htk), norm))
+    return _melspec_from_bank(y, bank, n_fft, hop, win_length, window, center, pad_mode, power)
+
+
+def clear_caches() -> None:
+    with _lock:
+        _dense_cache.clear()
+        _sparse_cache.clear()
+    mel_filterbank_host.cache_clear()

@@ -1,0 +1,369 @@
+"""GPU parity tests: the CUDA path (through the Python host layer -> C ABI) against the CPU oracle
+and the committed reference fixtures.  Tolerances are the ones BASELINE.json's north_star states:
+pad/frame indices bit-exact; STFT and mel within 1e-5 of peak magnitude; ISTFT round trip <= 1e-5;
+dB within 1e-3 dB; MFCC at the reference tests' rtol=atol=1e-4 scale."""
+import numpy as np
+import pytest
+
+from oracle import spectral as o
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def ap():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import mlx_audio_primitives_b200 as ap
+    return ap
+
+
+def H(t):
+    return t.detach().cpu().numpy()
+
+
+def rel_peak(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+# ---------------------------------------------------------------- indices: bit exact
+@pytest.mark.parametrize("mode", ["constant", "reflect", "edge"])
+@pytest.mark.parametrize("pad", [0, 1, 3, 19, 512])
+def test_pad_signal_bit_exact(ap, mode, pad):
+    L = 20 if pad < 20 else 1000
+    x = np.arange(1, 3 * L + 1, dtype=np.float32).reshape(3, L)
+    got = H(ap.pad_signal(x, pad, mode))
+    assert np.array_equal(got, o.pad_signal(x, pad, mode))
+
+
+def test_pad_reference_golden_vectors(ap):
+    # reference tests/test_cpp_extension.py:525-546
+    got = H(ap.pad_signal(np.arange(10, dtype=np.float32)[None], 3, "reflect"))[0]
+    assert list(got[:3]) == [3, 2, 1] and list(got[-3:]) == [8, 7, 6]
+    got = H(ap.pad_signal(np.ones((1, 10), np.float32), 3, "constant"))[0]
+    assert list(got[:3]) == [0, 0, 0] and list(got[-3:]) == [0, 0, 0] and got.shape == (16,)
+
+
+@pytest.mark.parametrize("fl,hop", [(8, 2), (16, 16), (10, 3), (50, 1), (2048, 512)])
+def test_frame_bit_exact(ap, fl, hop):
+    L = 50 if fl <= 50 else 9000
+    x = np.arange(2 * L, dtype=np.float32).reshape(2, L)
+    assert np.array_equal(H(ap.frame(x, fl, hop)), o.frame_signal(x, fl, hop))
+    assert np.array_equal(H(ap.frame(x[0], fl, hop)), o.frame_signal(x[:1], fl, hop)[0])
+
+
+@pytest.mark.parametrize("n_fft,hop", [(64, 16), (400, 160), (512, 128), (2048, 512), (600, 150)])
+@pytest.mark.parametrize("mode", ["constant", "reflect", "edge"])
+@pytest.mark.parametrize("center", [True, False])
+def test_fused_stft_indices_via_ramp(ap, n_fft, hop, mode, center):
+    """Rectangular window + index ramp: the DC bin of frame t is the exact integer sum of the source
+    indices the fused loader picked, so a single wrong pad/frame index shows up."""
+    L = 5 * n_fft + 37
+    x = np.arange(L, dtype=np.float32)[None] % 97  # small integers: sums stay exact in float32
+    S = H(ap.stft(x, n_fft, hop, window="rectangular", center=center, pad_mode=mode))
+    xp = o.pad_signal(x, n_fft // 2, mode) if center else x
+    fr = o.frame_signal(xp, n_fft, hop)
+    assert S.shape == (1, n_fft // 2 + 1, fr.shape[1])
+    np.testing.assert_allclose(S[0, 0].real, fr[0].sum(-1), rtol=0, atol=0.51)
+    ref = o.stft(x, n_fft, hop, window="rectangular", center=center, pad_mode=mode, dtype=np.float64)
+    assert rel_peak(S, ref) <= 1e-5
+
+
+# ---------------------------------------------------------------- STFT values
+STFT_CASES = [
+    dict(n_fft=2048, hop_length=512), dict(n_fft=1024, hop_length=256, pad_mode="reflect"),
+    dict(n_fft=512, hop_length=128, pad_mode="edge"), dict(n_fft=512, hop_length=128, center=False),
+    dict(n_fft=400, hop_length=160), dict(n_fft=400, hop_length=160, window="hamming", pad_mode="reflect"),
+    dict(n_fft=1024, hop_length=300, win_length=800, window="blackman"),
+    dict(n_fft=256, hop_length=256, window="bartlett"), dict(n_fft=4096, hop_length=1024),
+    dict(n_fft=128, hop_length=32), dict(n_fft=64, hop_length=1, center=False),
+    dict(n_fft=2048, hop_length=333), dict(n_fft=400, hop_length=77),
+    # no compiled plan -> O(n^2) DFT kernel
+    dict(n_fft=600, hop_length=150), dict(n_fft=1000, hop_length=250), dict(n_fft=255, hop_length=64),
+    dict(n_fft=32, hop_length=8), dict(n_fft=8192, hop_length=2048),
+]
+
+
+@pytest.mark.parametrize("kw", STFT_CASES, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+def test_stft_matches_oracle(ap, kw):
+    rng = np.random.default_rng(42)
+    L = 600 if kw.get("hop_length") == 1 else 22050
+    y = rng.standard_normal((3, L)).astype(np.float32)
+    S = H(ap.stft(y, **kw))
+    ref = o.stft(y, dtype=np.float64, **kw)
+    assert S.shape == ref.shape and S.dtype == np.complex64
+    assert rel_peak(S, ref) <= 1e-5, rel_peak(S, ref)
+    S1 = H(ap.stft(y[1], **kw))  # 1-D input
+    assert np.array_equal(S1, S[1])
+
+
+def test_stft_golden_fixtures(ap, golden, cases):
+    y = golden["stft/input"]
+    for i, kw in enumerate(cases["stft"]):
+        yin = y[:, :300] if kw.get("hop_length") == 1 else y
+        ref = golden[f"stft/{i}"]
+        S = H(ap.stft(yin, **kw))
+        assert S.shape == ref.shape
+        assert rel_peak(S, ref) <= 1e-5, (i, kw)
+
+
+def test_stft_scales_and_special_inputs(ap):
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal(8000).astype(np.float32)
+    for scale in [1e-7, 1e4]:  # reference test_mathematical_properties.py:430-451
+        S = H(ap.stft(y * np.float32(scale), 1024, 256))
+        ref = o.stft(y * np.float32(scale), 1024, 256, dtype=np.float64)
+        assert rel_peak(S, ref) <= 1e-5
+    assert np.all(H(ap.stft(np.zeros(4000, np.float32), 512, 128)) == 0)
+    # pure tone lands in its bin; DC signal lands in bin 0
+    sr, f0 = 22050, 440.0
+    tone = np.sin(2 * np.pi * f0 * np.arange(sr) / sr).astype(np.float32)
+    mag = np.abs(H(ap.stft(tone, 2048, 512)))
+    assert abs(int(mag[:, 10].argmax()) - round(f0 * 2048 / sr)) <= 1
+    dc = np.abs(H(ap.stft(np.ones(8192, np.float32), 1024, 256)))
+    assert dc[:, 8].argmax() == 0
+    # linearity (reference :133-212, 1e-5)
+    a, b = rng.standard_normal((2, 6000)).astype(np.float32)
+    lhs = H(ap.stft(2.0 * a + 3.0 * b, 512, 128))
+    rhs = 2.0 * H(ap.stft(a, 512, 128)) + 3.0 * H(ap.stft(b, 512, 128))
+    assert rel_peak(lhs, rhs) <= 1e-5
+
+
+def test_stft_errors(ap):
+    y = np.zeros(1000, np.float32)
+    with pytest.raises(ValueError, match="hop_length must be positive"):
+        ap.stft(y, 256, 0)
+    with pytest.raises(ValueError, match="win_length must be positive"):
+        ap.stft(y, 256, 64, 0)
+    with pytest.raises(ValueError, match="must be <= n_fft"):
+        ap.stft(y, 256, 64, 512)
+    with pytest.raises(ValueError, match="should typically be <= n_fft"):
+        ap.stft(y, 256, 512)
+    with pytest.raises(ValueError, match="must be >= frame_length"):
+        ap.stft(y, 2048, 512, center=False)
+    with pytest.raises(ValueError, match="Unknown pad_mode"):
+        ap.stft(y, 256, 64, pad_mode="wrap")
+    with pytest.raises(ValueError, match="Unknown window type"):
+        ap.stft(y, 256, 64, window="kaiser")
+    with pytest.raises(ValueError, match="must match n_fft"):
+        ap.get_window(np.ones(100, np.float32), 256)
+    with pytest.raises(TypeError):
+        ap.get_window(3.0, 256)
+
+
+# ---------------------------------------------------------------- ISTFT
+@pytest.mark.parametrize("n_fft,hop", [(64, 16), (128, 32), (256, 64), (400, 160), (400, 100), (512, 128),
+                                       (1024, 256), (2048, 512), (2048, 1024), (4096, 1024), (600, 150)])
+def test_round_trip(ap, n_fft, hop):
+    """reference tests/test_stft.py:122-178, NUMERICAL_ACCURACY.md:12,79: error <= 1e-5"""
+    rng = np.random.default_rng(42)
+    y = rng.standard_normal((2, 22050)).astype(np.float32)
+    S = ap.stft(y, n_fft, hop)
+    r = H(ap.istft(S, hop, length=y.shape[1]))
+    assert r.shape == y.shape
+    # sample 0 has zero window sum for hann -> reconstructed as 0, like the reference
+    assert np.abs(r[:, 1:] - y[:, 1:]).max() <= 1e-5
+    r2 = H(ap.istft(S, hop))  # natural length
+    n = r2.shape[1]
+    assert n == (S.shape[-1] - 1) * hop
+    assert np.abs(r2[:, 1:] - y[:, 1:n]).max() <= 1e-5
+
+
+def test_istft_matches_oracle_on_golden(ap, golden, cases):
+    for i, kw in enumerate(cases["stft"]):
+        S = golden[f"stft/{i}"]
+        ikw = {k: v for k, v in kw.items() if k != "pad_mode"}
+        ref = golden[f"istft/{i}"]
+        got = H(ap.istft(S, **ikw))  # (B, F, T)-contiguous input: exercises the transposing path
+        assert got.shape == ref.shape, (i, kw)
+        assert np.abs(got - ref).max() <= 1e-5, (i, kw, np.abs(got - ref).max())
+        if kw.get("center", True):
+            L = 300 if kw.get("hop_length") == 1 else 6000
+            got = H(ap.istft(S, length=L, **ikw))
+            assert np.abs(got - golden[f"istft_len/{i}"]).max() <= 1e-5, (i, kw)
+    S1 = golden["stft1d"]
+    for L in [5000, 6000, 7000]:
+        got = H(ap.istft(S1, 128, length=L))
+        assert got.shape == (L,)
+        assert np.abs(got - golden[f"istft1d_len/{L}"]).max() <= 1e-5
+    Snc = o.stft(golden["stft/input"], 512, 128, center=False)
+    for L in [4000, 6500]:
+        got = H(ap.istft(Snc, 128, center=False, length=L))
+        assert np.abs(got - golden[f"istft_nc_len/{L}"]).max() <= 1e-5
+
+
+def test_istft_n_fft_mismatch_and_short(ap):
+    rng = np.random.default_rng(3)
+    S = (rng.standard_normal((2, 200, 9)) + 1j * rng.standard_normal((2, 200, 9))).astype(np.complex64)
+    for n_fft in [512, 256]:  # spectrum zero-padded / cropped by irfft(n=n_fft) (reference stft.py:295)
+        got = H(ap.istft(S, hop_length=64, n_fft=n_fft))
+        ref = o.istft(S, hop_length=64, n_fft=n_fft, dtype=np.float64)
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    one = ap.istft(S[:, :129, :1], hop_length=64)  # T = 1 -> empty (reference stft.py:322-329)
+    assert tuple(one.shape) == (2, 0)
+    with pytest.raises(ValueError, match="2D or 3D"):
+        ap.istft(np.zeros(5, np.complex64))
+
+
+def test_overlap_add_primitive(ap):
+    rng = np.random.default_rng(5)
+    fr = rng.standard_normal((2, 9, 64)).astype(np.float32)
+    w = o.get_window("hann", 64)
+    got = H(ap.overlap_add(fr, w, 16, 64 + 8 * 16))
+    np.testing.assert_allclose(got, o.overlap_add(fr, w, 16, 64 + 8 * 16), atol=1e-5)
+
+
+def test_magnitude_phase(ap, golden):
+    S1 = golden["stft1d"]
+    np.testing.assert_allclose(H(ap.magnitude(S1)), np.abs(S1), rtol=1e-6, atol=1e-6)  # reference tol 1e-6
+    np.testing.assert_allclose(H(ap.phase(S1)), np.angle(S1), atol=1e-5)                # reference tol 1e-5
+    y = np.random.default_rng(1).standard_normal(4000).astype(np.float32)
+    S = ap.stft(y, 512, 128)  # transposed view in: same logical layout out
+    m = ap.magnitude(S)
+    assert m.shape == S.shape
+    np.testing.assert_allclose(H(m), np.abs(H(S)), rtol=1e-6, atol=1e-6)
+    assert ap.check_nola("hann", 512, 2048) is True
+
+
+# ---------------------------------------------------------------- windows / filterbanks on device
+def test_constants_bit_exact_on_device(ap, golden):
+    for key in golden.files:
+        parts = key.split("/")
+        if parts[0] == "window":
+            assert np.array_equal(H(ap.get_window(parts[1], int(parts[2]), bool(int(parts[3])))), golden[key]), key
+        elif parts[0] == "melfb":
+            fmax = None if parts[5] == "None" else float(parts[5])
+            norm = None if parts[7] == "None" else parts[7]
+            fb = ap.mel_filterbank(int(parts[1]), int(parts[2]), int(parts[3]), float(parts[4]), fmax,
+                                   bool(int(parts[6])), norm)
+            assert np.array_equal(H(fb), golden[key]), key
+        elif parts[0] == "dctmat":
+            norm = None if parts[3] == "None" else parts[3]
+            assert np.array_equal(H(ap.dct_matrix(int(parts[1]), int(parts[2]), norm)), golden[key]), key
+    assert np.array_equal(H(ap.linear_filterbank(22050, 1024, 32)), golden["linfb/22050/1024/32"])
+    assert ap.get_window("hann", 512) is ap.get_window("HANN", 512)  # device-resident cache hit
+    with pytest.raises(ValueError, match="cannot exceed Nyquist"):
+        ap.mel_filterbank(16000, 512, fmax=9000.0)
+    with pytest.raises(ValueError, match="n_mels must be positive"):
+        ap.mel_filterbank(16000, 512, n_mels=0)
+
+
+# ---------------------------------------------------------------- mel / dB / MFCC
+def test_mel_db_mfcc_golden(ap, golden, cases):
+    y = golden["stft/input"]
+    for i, kw in enumerate(cases["mel"]):
+        ref = golden[f"mel/{i}"]
+        M = ap.melspectrogram(y, **kw)
+        assert tuple(M.shape) == ref.shape
+        ref64 = o.melspectrogram(y, dtype=np.float64, **kw)
+        tol = 1e-5 if kw.get("power", 2.0) in (1.0, 2.0) else 3e-5  # powf adds a couple of ulp
+        assert rel_peak(H(M), ref64) <= tol, (i, kw, rel_peak(H(M), ref64))
+        # dB within 1e-3 dB of the float64 restatement applied to OUR mel (isolates the dB step) ...
+        M64 = H(M).astype(np.float64)
+        for name, args in [("db_default", {}), ("db_refmax", dict(ref=np.max)),
+                           ("db_refmax_notop", dict(ref=np.max, top_db=None)),
+                           ("db_ref05_amin", dict(ref=0.5, amin=1e-5, top_db=60.0))]:
+            targs = dict(args)
+            if "ref" in targs and callable(targs["ref"]):
+                targs["ref"] = torch.max
+            got = H(ap.power_to_db(M, **targs))
+            want = o.power_to_db(M64, dtype=np.float64, **args)
+            assert np.abs(got - want).max() <= 1e-3, (i, name)
+            # ... and end to end against the reference-code fixture where mel is well conditioned
+            mask = golden[f"mel/{i}"] > 1e-6 * golden[f"mel/{i}"].max()
+            assert np.abs(got - golden[f"{name}/{i}"])[mask].max() <= 2e-3, (i, name)
+    for i, kw in enumerate(cases["mfcc"]):
+        got = H(ap.mfcc(y, **kw))
+        ref = o.mfcc(y, dtype=np.float64, **kw)
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=1e-4, atol=2e-3, err_msg=str(kw))
+        np.testing.assert_allclose(got, golden[f"mfcc/{i}"], rtol=1e-3, atol=5e-3, err_msg=str(kw))
+
+
+def test_mel_1d_powers_and_batch_consistency(ap):
+    rng = np.random.default_rng(7)
+    y = rng.standard_normal((5, 16000)).astype(np.float32)
+    M = H(ap.melspectrogram(y, sr=16000, n_fft=400, hop_length=160, n_mels=80))
+    for b in range(5):  # clip alone == clip in batch (bit exact: same kernel, same order)
+        assert np.array_equal(H(ap.melspectrogram(y[b], sr=16000, n_fft=400, hop_length=160, n_mels=80)), M[b])
+    # odd frame count / tile edges: T not a multiple of the tile
+    for L in [400, 401, 559, 560, 5119, 5120, 5121]:
+        got = H(ap.melspectrogram(y[0, :L], sr=16000, n_fft=400, hop_length=160, n_mels=80))
+        ref = o.melspectrogram(y[0, :L], sr=16000, n_fft=400, hop_length=160, n_mels=80, dtype=np.float64)
+        assert got.shape == ref.shape and rel_peak(got, ref) <= 1e-5, L
+
+
+def test_db_family(ap, golden):
+    amp = np.abs(golden["stft1d"])
+    assert np.abs(H(ap.amplitude_to_db(amp)) - golden["ampdb"]).max() <= 1e-3
+    assert np.abs(H(ap.amplitude_to_db(amp, ref=torch.max, top_db=None)) - golden["ampdb_refmax"]).max() <= 1e-3
+    np.testing.assert_allclose(H(ap.db_to_power(golden["dbv"], 2.0)), golden["db_to_power"], rtol=1e-5)
+    np.testing.assert_allclose(H(ap.db_to_amplitude(golden["dbv"])), golden["db_to_amplitude"], rtol=1e-5)
+    # round trip and a non-max callable ref
+    x = np.random.default_rng(2).random((3, 40, 50)).astype(np.float32) + 1e-3
+    rt = H(ap.db_to_power(ap.power_to_db(x, top_db=None)))
+    np.testing.assert_allclose(rt, x, rtol=1e-5)
+    got = H(ap.power_to_db(x, ref=torch.median, top_db=None))
+    med = float(torch.median(torch.from_numpy(x)))
+    np.testing.assert_allclose(got, o.power_to_db(x, ref=med, top_db=None, dtype=np.float64), atol=1e-3)
+    zeros = H(ap.power_to_db(np.zeros((4, 4), np.float32)))
+    assert np.all(zeros == zeros[0, 0]) and np.isfinite(zeros).all()
+    with pytest.raises(ValueError, match="top_db must be positive"):
+        ap.power_to_db(x, top_db=0)
+
+
+def test_dct(ap, golden):
+    x = golden["dct/input"]
+    np.testing.assert_allclose(H(ap.dct(x)), golden["dct/ortho"], atol=1e-4)
+    np.testing.assert_allclose(H(ap.dct(x, n=20, norm=None)), golden["dct/n20_none"], atol=1e-3)
+    np.testing.assert_allclose(H(ap.dct(x, axis=1, n=5)), golden["dct/axis1"], atol=1e-4)
+    with pytest.raises(ValueError, match="Only DCT type 2"):
+        ap.dct(x, type=3)
+    with pytest.raises(ValueError, match="n_mfcc must be positive"):
+        ap.mfcc(np.zeros(4096, np.float32), n_mfcc=0)
+    # S= path: caller-supplied log-mel, no dB step (reference tests/test_mfcc.py:72)
+    logmel = np.random.default_rng(4).standard_normal((2, 40, 30)).astype(np.float32)
+    np.testing.assert_allclose(H(ap.mfcc(S=logmel, n_mfcc=13)), o.mfcc(S=logmel, n_mfcc=13, dtype=np.float64),
+                               rtol=1e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------- Griffin-Lim
+def test_griffinlim_matches_reference_code(ap, golden):
+    S = golden["gl/S"]
+    got = H(ap.griffinlim(S, n_iter=8, hop_length=128, random_state=0))
+    assert got.shape == golden["gl/random8"].shape
+    assert np.abs(got - golden["gl/random8"]).max() <= 2e-3
+    got = H(ap.griffinlim(S, n_iter=4, hop_length=128, init="zeros", momentum=0.0))
+    assert np.abs(got - golden["gl/zeros4_m0"]).max() <= 1e-3
+    got = H(ap.griffinlim(S, n_iter=3, hop_length=128, random_state=1, length=4000))
+    assert got.shape == (2, 4000) and np.abs(got - golden["gl/len"]).max() <= 1e-3
+    got = H(ap.griffinlim(S[0], n_iter=2, hop_length=128, random_state=2))
+    assert np.abs(got - golden["gl/1d"]).max() <= 1e-3
+    a = H(ap.griffinlim(S, n_iter=4, hop_length=128, random_state=5))
+    b = H(ap.griffinlim(S, n_iter=4, hop_length=128, random_state=5))
+    assert np.array_equal(a, b)  # deterministic kernels: same seed -> same bits
+
+
+def test_griffinlim_quality_and_errors(ap):
+    """reference tests/test_griffinlim.py:31,100-121: spectral MSE thresholds per iteration count"""
+    from tests.conftest import chirp_noise
+    y = chirp_noise(22050)
+    S = np.abs(o.stft(y, 1024, 256))
+    for n_iter, thr in [(16, 10.0), (32, 5.0)]:
+        r = H(ap.griffinlim(S, n_iter=n_iter, hop_length=256, random_state=0))
+        S2 = np.abs(o.stft(r, 1024, 256))
+        T = min(S.shape[1], S2.shape[1])
+        assert np.mean((S[:, :T] - S2[:, :T]) ** 2) < thr
+    with pytest.raises(ValueError, match="n_iter must be positive"):
+        ap.griffinlim(S, n_iter=0)
+    with pytest.raises(ValueError, match="momentum must be < 1.0"):
+        ap.griffinlim(S, momentum=1.0)
+    with pytest.raises(ValueError, match="momentum must be >= 0.0"):
+        ap.griffinlim(S, momentum=-0.1)
+    with pytest.raises(ValueError, match="Unknown init"):
+        ap.griffinlim(S, init="ones")
+    ang, reb, err = ap.griffinlim_iter(S, np.zeros_like(S), 256, 1024, 1024)
+    assert tuple(ang.shape) == S.shape and float(err) >= 0

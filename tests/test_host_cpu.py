@@ -1,0 +1,180 @@
+"""CPU-side tests: host constants of the product package against the reference fixtures, the
+C-ABI surface (library loads, exports every symbol include/mlxa_cuda.h declares), the FFT engine
+through its host emulation, and the sharding/all-reduce logic on a 2-rank gloo group."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    from mlx_audio_primitives_b200 import _extension as ext
+    hdr = open(os.path.join(ROOT, "include", "mlxa_cuda.h")).read()
+    declared = set(re.findall(r"\b(mlxa_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(ext.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in mlxa_cuda.h but not exported"
+    assert declared - {"mlxa_last_error"} == set(ext.SIGNATURES), "host-layer signature table out of sync"
+    assert ext._ext.mlxa_abi_version() == ext.ABI_VERSION
+    assert ext._ext.mlxa_has_fast_plan(400) == 1 and ext._ext.mlxa_has_fast_plan(2048) == 1
+    assert ext._ext.mlxa_has_fast_plan(600) == 0
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    rc = ext._ext.mlxa_pad_signal_f32(None, 1, 10, 3, 0, None, None)
+    assert rc == -1 and b"null" in ext._ext.mlxa_last_error()
+    with pytest.raises(ValueError):
+        ext.check(rc, "pad_signal")
+
+
+def test_host_constants_match_reference_fixtures(golden):
+    from mlx_audio_primitives_b200.windows import window_host
+    from mlx_audio_primitives_b200.mel import mel_filterbank_host, sparse_rows_host, hz_to_mel, mel_to_hz
+    from mlx_audio_primitives_b200.mfcc import dct_matrix_host
+    from mlx_audio_primitives_b200.filterbanks import _linear_host
+    for key in golden.files:
+        parts = key.split("/")
+        if parts[0] == "window":
+            assert np.array_equal(window_host(parts[1], int(parts[2]), bool(int(parts[3]))), golden[key]), key
+        elif parts[0] == "melfb":
+            sr, n_fft, n_mels, fmin = int(parts[1]), int(parts[2]), int(parts[3]), float(parts[4])
+            fmax = sr / 2.0 if parts[5] == "None" else float(parts[5])
+            norm = None if parts[7] == "None" else parts[7]
+            fb = mel_filterbank_host(sr, n_fft, n_mels, fmin, fmax, bool(int(parts[6])), norm)
+            assert np.array_equal(fb, golden[key]), key
+            # the band-sparse rows reproduce the dense matrix exactly
+            start, length, offset, w = sparse_rows_host(fb)
+            dense = np.zeros_like(fb)
+            for m in range(n_mels):
+                dense[m, start[m]:start[m] + length[m]] = w[offset[m]:offset[m] + length[m]]
+            assert np.array_equal(dense, fb)
+        elif parts[0] == "dctmat":
+            norm = None if parts[3] == "None" else parts[3]
+            assert np.array_equal(dct_matrix_host(int(parts[1]), int(parts[2]), norm), golden[key]), key
+    assert np.array_equal(_linear_host(22050, 1024, 32, 0.0, 11025.0, "slaney"), golden["linfb/22050/1024/32"])
+    assert np.array_equal(hz_to_mel(golden["hz"]), golden["hz_to_mel/slaney"])
+    assert np.array_equal(hz_to_mel(golden["hz"], True), golden["hz_to_mel/htk"])
+    assert np.array_equal(mel_to_hz(hz_to_mel(golden["hz"])), golden["mel_to_hz/slaney"])
+
+
+def test_host_validation_messages():
+    from mlx_audio_primitives_b200.mel import _resolve_stft_args, check_band_args, frames_or_raise, pad_mode_code
+    from mlx_audio_primitives_b200.windows import window_host
+    from mlx_audio_primitives_b200.stft import _istft_geometry
+    with pytest.raises(ValueError, match="hop_length must be positive"):
+        _resolve_stft_args(512, 0, None)
+    with pytest.raises(ValueError, match=r"win_length \(1024\) must be <= n_fft \(512\)"):
+        _resolve_stft_args(512, 128, 1024)
+    with pytest.raises(ValueError, match="should typically be <= n_fft"):
+        _resolve_stft_args(512, 1024, None)
+    assert _resolve_stft_args(2048, None, None) == (512, 2048)
+    with pytest.raises(ValueError, match="must be less than fmax"):
+        check_band_args(40, "n_mels", 5000.0, 4000.0, 16000)
+    with pytest.raises(ValueError, match="fmin must be non-negative"):
+        check_band_args(40, "n_mels", -1.0, None, 16000)
+    with pytest.raises(ValueError, match="Unknown pad_mode"):
+        pad_mode_code("wrap")
+    with pytest.raises(ValueError, match="Unknown window type"):
+        window_host("kaiser", 64, True)
+    with pytest.raises(ValueError, match="must be >= frame_length"):
+        frames_or_raise(100, 512, 128, False, "constant")
+    with pytest.raises(ValueError, match="reflect padding"):
+        frames_or_raise(100, 512, 128, True, "reflect")
+    assert frames_or_raise(22050, 2048, 512, True, "constant") == 44       # reference docstring stft.py:181
+    assert frames_or_raise(480000, 400, 160, True, "constant") == 3001     # BASELINE config C2
+    # ISTFT geometry (reference stft.py:300-338)
+    assert _istft_geometry(44, 2048, 512, True, None) == (2048 + 43 * 512, 1024, 43 * 512)
+    assert _istft_geometry(44, 2048, 512, True, 22050) == (22050 + 2048, 1024, 22050)
+    assert _istft_geometry(44, 2048, 512, False, 5000) == (5000, 0, 5000)
+    assert _istft_geometry(1, 2048, 512, True, None)[2] == 0
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(ROOT, "tests", "emul", "libfft_emul.so")
+    src = os.path.join(ROOT, "tests", "emul", "fft_emul.cpp")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I/usr/local/cuda/include",
+                        "-I" + os.path.join(ROOT, "mlx_audio_primitives_b200", "csrc", "cuda"), src, "-o", so],
+                       check=True)
+    return ctypes.CDLL(so)
+
+
+def _c(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize("R", [2, 3, 4, 5, 8, 9, 10, 16, 20, 25, 32, 64])
+def test_in_register_dft(emul, R):
+    rng = np.random.default_rng(R)
+    x = (rng.standard_normal(R) + 1j * rng.standard_normal(R)).astype(np.complex64)
+    out = np.zeros(R, np.complex64)
+    assert emul.emul_radix(R, _c(x), _c(out)) == 0
+    ref = np.fft.fft(x.astype(np.complex128))
+    assert np.abs(out - ref).max() <= 5e-7 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n_fft", [64, 128, 256, 400, 512, 1024, 2048, 4096])
+def test_plan_fft_emulated(emul, n_fft):
+    """The same __host__ __device__ pass functions the kernels run, lanes executed sequentially."""
+    N = emul.emul_plan_length(n_fft)
+    rng = np.random.default_rng(n_fft)
+    x = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    out = np.zeros(N, np.complex64)
+    assert emul.emul_plan_fft(n_fft, _c(x), _c(out)) == 0
+    ref = np.fft.fft(x.astype(np.complex128))
+    assert np.abs(out - ref).max() <= 5e-7 * np.abs(ref).max()
+
+
+def test_shard_bounds():
+    from mlx_audio_primitives_b200.distributed import shard_bounds
+    for n, w in [(1024, 8), (64, 8), (10, 4), (3, 8), (1, 2)]:
+        spans = [shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from mlx_audio_primitives_b200 import distributed as d
+from oracle import spectral as o
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+# global batch of mel-like data, sharded by clips; the dB clamp must use the GLOBAL peak
+full = np.random.default_rng(0).random((6, 8, 20)).astype(np.float32) * np.arange(1, 7, dtype=np.float32)[:, None, None]
+lo, hi = d.shard_bounds(6, rank, 2)
+local = full[lo:hi]
+d.enable()
+peak = torch.tensor([float(local.max())])
+d.all_reduce_max_(peak)
+assert float(peak) == float(full.max()), (float(peak), float(full.max()))
+mine = o.power_to_db(local, ref=float(peak), top_db=None)
+mine = np.maximum(mine, o.power_to_db(np.array([float(peak)], np.float32), ref=float(peak), top_db=None)[0] - 80.0)
+want = o.power_to_db(full, ref=np.max, top_db=80.0)[lo:hi]
+assert np.allclose(mine, want, atol=1e-5)
+d.disable()
+q = torch.tensor([float(rank)]); d.all_reduce_max_(q); assert float(q) == float(rank)  # disabled: untouched
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_global_peak_allreduce_gloo_world2(tmp_path):
+    """N>1 host path on CPU: shard -> local peak -> all_reduce(MAX) -> dB equals the unsharded result."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for p, out in zip(procs, outs):
+        assert p.returncode == 0, out
