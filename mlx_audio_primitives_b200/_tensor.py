@@ -41,10 +41,21 @@ def stream_ptr(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+def _is_dense_permutation(x: torch.Tensor) -> bool:
+    """True when x covers one contiguous block exactly once (any permutation of a contiguous tensor)."""
+    dims = sorted((st, sz) for st, sz in zip(x.stride(), x.shape) if sz != 1)
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
 def dense_like(x: torch.Tensor, dtype=None) -> tuple[torch.Tensor, torch.Tensor]:
     """(x_dense, out): a densely laid-out version of x (any permutation of a contiguous block is
     kept as is) and an empty output with identical strides, so flat elementwise kernels apply."""
-    if not x.is_non_overlapping_and_dense():
+    if not _is_dense_permutation(x):
         x = x.contiguous()
     out = torch.empty_like(x, dtype=dtype if dtype is not None else x.dtype, memory_format=torch.preserve_format)
     if out.stride() != x.stride():  # pragma: no cover - defensive

@@ -113,7 +113,7 @@ def sparse_rows_host(bank: np.ndarray):
     return start, length, offset, weights
 
 
-_lock = threading.Lock()
+_lock = threading.RLock()
 _dense_cache: dict[tuple, torch.Tensor] = {}
 _sparse_cache: dict[tuple, SparseBank] = {}
 

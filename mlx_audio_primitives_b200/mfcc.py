@@ -29,7 +29,7 @@ def dct_matrix_host(n_out: int, n_in: int, norm) -> np.ndarray:
     return D
 
 
-_lock = threading.Lock()
+_lock = threading.RLock()
 _dct_device: dict[tuple, torch.Tensor] = {}
 
 

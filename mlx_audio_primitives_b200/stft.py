@@ -62,7 +62,7 @@ def _spectrum_physical(S: torch.Tensor) -> torch.Tensor:
     return out
 
 
-_wss_lock = threading.Lock()
+_wss_lock = threading.RLock()
 _wss_cache: dict[tuple, torch.Tensor] = {}
 
 

@@ -44,7 +44,7 @@ def window_host(name: str, n_fft: int, fftbins: bool) -> np.ndarray:
     return out
 
 
-_lock = threading.Lock()
+_lock = threading.RLock()
 _device_windows: dict[tuple, torch.Tensor] = {}
 
 
