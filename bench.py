@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the spectral hot path (contract: one JSON line on stdout from rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+
+Workload c2 (default, BASELINE.json configs[1]): Whisper-style log-mel, 16 kHz, n_fft 400, hop 160,
+80 mels, 64 clips x 30 s per GPU, power_to_db(ref=1.0, amin=1e-10, top_db=80) -- one "step" is one
+pass over one such batch.  Weak scaling: every rank owns its own 64 clips; the only exchange is the
+one-float all-reduce(MAX) that top_db's batch-global max needs.
+Metric: audio-seconds per second.  `value` times the step with inputs resident in HBM;
+`e2e` times the same step through the C-ABI host-buffer entry point (pinned host in, host out).
+`--impl reference` times the CPU restatement of the reference path (oracle/) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (sr, n_fft, hop, n_mels, clips per GPU, seconds per clip)
+    "c2": dict(sr=16000, n_fft=400, hop=160, n_mels=80, clips=64, seconds=30.0,
+               label="Whisper-style log-mel: 16 kHz, n_fft=400 hop=160 n_mels=80, batch 64x30 s"),
+    "c3": dict(sr=22050, n_fft=2048, hop=512, n_mels=128, clips=128, seconds=30.0,
+               label="Music mel+power_to_db: 22.05 kHz, n_fft=2048 hop=512 n_mels=128, 128x30 s per GPU"),
+}
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4
+
+
+def algorithmic_cost(w, T, L):
+    """bytes = 4L + 4*n_mels*T per clip; flops per frame = 2.5 N log2 N (rFFT) + N (window)
+    + 3F (|X|^2) + 4F (band-sparse mel) + 3*n_mels (dB)."""
+    import math
+    N, F = w["n_fft"], w["n_fft"] // 2 + 1
+    bytes_clip = 4 * L + 4 * w["n_mels"] * T
+    flops_frame = 2.5 * N * math.log2(N) + N + 3 * F + 4 * F + 3 * w["n_mels"]
+    return bytes_clip, flops_frame * T
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def synth_clips_np(n, L, sr, seed0=42):
+    import numpy as np
+    t = np.arange(L) / sr
+    base = np.sin(2 * np.pi * (100 + 1000 * t) * t)
+    out = np.empty((n, L), np.float32)
+    for i in range(n):  # reference benchmarks/utils.py:92-115, one seed per clip
+        out[i] = base + 0.1 * np.random.default_rng(seed0 + i).standard_normal(L)
+    return out
+
+
+def cpu_reference_pass(y, w, threads):
+    """One pass of the reference's CPU path (float32 restatement, oracle/spectral.py) over clips y,
+    clips spread over `threads` host threads; the dB clamp uses the batch-global max like the reference."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import spectral as o
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:  # pragma: no cover
+        threadpool_limits = None
+
+    def mel_one(i):
+        return o.melspectrogram(y[i], sr=w["sr"], n_fft=w["n_fft"], hop_length=w["hop"], n_mels=w["n_mels"])
+
+    def run():
+        with ThreadPoolExecutor(threads) as ex:
+            mels = list(ex.map(mel_one, range(y.shape[0])))
+            peak = max(float(m.max()) for m in mels)
+            floor = float(o.power_to_db(np.array([peak], np.float32), top_db=None)[0]) - 80.0
+            return list(ex.map(lambda m: np.maximum(o.power_to_db(m, top_db=None), floor), mels))
+
+    t0 = time.perf_counter()
+    if threadpool_limits is not None and threads > 1:
+        with threadpool_limits(limits=1):
+            out = run()
+    else:
+        out = run()
+    return time.perf_counter() - t0, out
+
+
+def cpu_baseline(w, threads, clips):
+    L = int(w["sr"] * w["seconds"])
+    y = synth_clips_np(clips, L, w["sr"])
+    cpu_reference_pass(y[: max(1, min(2, clips))], w, threads)  # warm caches / thread pool
+    dt, _ = cpu_reference_pass(y, w, threads)
+    return {"value": clips * w["seconds"] / dt, "unit": "audio-s/s", "cores": threads, "kind": "port",
+            "sample": f"{clips} clips x {w['seconds']:.0f} s of the same workload, 1 pass, float32 NumPy/pocketfft "
+                      f"restatement of the reference CPU path (MLX not installable), {threads} host threads"}
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    L = int(w["sr"] * w["seconds"])
+    clips = min(w["clips"], 16)  # bounded sample per step
+    y = synth_clips_np(clips, L, w["sr"])
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_reference_pass(y, w, threads)
+    steps = max(1, min(args.steps, 5))
+    t = [cpu_reference_pass(y, w, threads)[0] for _ in range(steps)]
+    dt = sum(t) / len(t)
+    val = clips * w["seconds"] / dt
+    line = {"impl": "reference", "metric": "audio-seconds per second, log-mel", "value": val, "unit": "audio-s/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["label"], "sample_clips_per_step": clips},
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                             "sample": f"{clips} clips x {w['seconds']:.0f} s per step (bounded sample of the "
+                                       f"{w['clips']}-clip batch), float32 restatement of the reference CPU path"},
+            "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.thr = [], None, None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), line.strip()))
+        self.thr = threading.Thread(target=pump, daemon=True)
+        self.thr.start()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1]
+        note = None
+        if len(rows) < 3:
+            rows = [r for (_, r) in self.rows]
+            note = "timed region shorter than the sampling period; summary covers warm-up + timed + e2e steps"
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            p = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap_ = argparse.ArgumentParser()
+    ap_.add_argument("--gpus", type=int, default=1)
+    ap_.add_argument("--steps", type=int, default=2000)
+    ap_.add_argument("--warmup", type=int, default=20)
+    ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap_.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap_.add_argument("--e2e-steps", type=int, default=10)
+    ap_.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap_.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import mlx_audio_primitives_b200 as ap
+    from mlx_audio_primitives_b200._extension import _ext, check
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        ap.distributed.enable()
+    K, W = max(1, args.steps), max(3, args.warmup)
+
+    B, L, sr = w["clips"], int(w["sr"] * w["seconds"]), w["sr"]
+    plan = ap.LogMelPlan(B, L, sr=sr, n_fft=w["n_fft"], hop_length=w["hop"], n_mels=w["n_mels"],
+                         ref=1.0, amin=1e-10, top_db=80.0)
+    T = plan.T
+    # synthetic clips (chirp + 0.1*noise, reference benchmarks/utils.py:92-115), generated on the device;
+    # NBUF distinct batches are rotated so every step reads inputs that are not L2-resident.
+    in_bytes = B * L * 4
+    NBUF = max(2, int(np.ceil(3 * 126e6 / in_bytes)) + 1)
+    g = torch.Generator(device=dev); g.manual_seed(42 + rank)
+    t = torch.arange(L, device=dev, dtype=torch.float64) / sr
+    base = torch.sin(2 * np.pi * (100 + 1000 * t) * t).to(torch.float32)
+    ys = [base[None, :] + 0.1 * torch.randn((B, L), generator=g, device=dev, dtype=torch.float32) for _ in range(NBUF)]
+    outs = [plan.empty_output() for _ in range(2)]
+    del t
+
+    def step(i, ev=None):
+        y, out = ys[i % NBUF], outs[i % 2]
+        if ev is not None:
+            ev[0].record()
+        plan.mel(y, out)
+        if ev is not None:
+            ev[1].record()
+        plan.db(out)
+        return out
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start = time.perf_counter()
+    e0.record()
+    for i in range(K):
+        step(i, evs[i])
+    e1.record()
+    torch.cuda.synchronize()
+    t_end = time.perf_counter()
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = [a.elapsed_time(b) for a, b in evs]
+    tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    ms_step = ms_total / K
+    audio_s = B * w["seconds"] * world
+    value = audio_s / (ms_step * 1e-3)
+
+    # ---- end to end through the C-ABI host-buffer entry point (pinned host in / out) -----------
+    KE = max(1, min(args.e2e_steps, K))
+    yh = [torch.empty((B, L), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for h in yh:
+        h.copy_(ys[0])
+    oh = torch.empty((B, plan.n_mels, T), dtype=torch.float32).pin_memory()
+    plan.run_host(yh[0], oh)  # warm-up (workspace allocation)
+    plan.run_host(yh[1], oh)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    te0 = time.perf_counter()
+    for i in range(KE):
+        plan.run_host(yh[i % 2], oh)
+    te = (time.perf_counter() - te0) / KE
+    tt = torch.tensor([te], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    te = float(tt.item())
+    e2e_value = audio_s / te
+    # sanity: the e2e result equals the resident-path result for the same input
+    ref_out = plan(ys[0])
+    torch.cuda.synchronize()
+    e2e_match = bool(torch.equal(ref_out.cpu(), oh)) if world == 1 else None  # N>1: resident path uses the global peak
+
+    if sampler:
+        sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- FP32 peak probe (MEASURED_PEAKS.json has HBM and bf16 only) -----------------------------
+    scratch = torch.zeros(4, device=dev)
+    s_ptr = torch.cuda.current_stream().cuda_stream
+    blocks, threads, iters = 148 * 8, 256, 20000
+    check(_ext.mlxa_ffma_probe(scratch.data_ptr(), blocks, threads, iters, s_ptr), "probe")
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for _ in range(5):
+        p0.record(); check(_ext.mlxa_ffma_probe(scratch.data_ptr(), blocks, threads, iters, s_ptr), "probe"); p1.record()
+        torch.cuda.synchronize()
+        best = min(best, p0.elapsed_time(p1))
+    fp32_measured = blocks * threads * iters * 16 / (best * 1e-3) / 1e12
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks \
+        else (6650.0, "fallback (B200_PROFILING.md)")
+    bytes_clip, flops_clip = algorithmic_cost(w, T, L)
+    k_ms = statistics.mean(kern_ms)
+    achieved = bytes_clip * B / (k_ms * 1e-3) / 1e9
+    fl_ach = flops_clip * B / (k_ms * 1e-3) / 1e12
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "kernel": f"fwd_kernel<EP_MEL> n_fft={w['n_fft']}", "kernel_ms": k_ms,
+                "kernel_ms_min": min(kern_ms), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_clip * B, "algorithmic_flops_per_launch": flops_clip * B,
+                "fp32": {"achieved_tflops": fl_ach, "peak_measured_tflops": fp32_measured,
+                         "peak_nominal_tflops": FP32_NOMINAL_TFLOPS, "frac_of_measured": fl_ach / fp32_measured,
+                         "frac_of_nominal": fl_ach / FP32_NOMINAL_TFLOPS},
+                "t_roof_ms": max(bytes_clip * B / (hbm_peak * 1e9), flops_clip * B / (fp32_measured * 1e12)) * 1e3,
+                "frac_of_roofline_time": max(bytes_clip * B / (hbm_peak * 1e9), flops_clip * B / (fp32_measured * 1e12)) * 1e3 / k_ms}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            roofline["traffic"] = json.load(f).get(args.workload)
+    except Exception:
+        pass
+
+    line = {"metric": "audio-seconds per second, log-mel", "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["label"], "clips_per_gpu": B, "samples_per_clip": L, "frames_per_clip": T,
+                       "power_to_db": "ref=1.0 amin=1e-10 top_db=80 (batch-global max)",
+                       "parallelism": f"clips sharded x{world}, 1-float all-reduce(MAX)" if world > 1 else "single GPU",
+                       "l2": f"{NBUF} distinct input batches rotated ({NBUF * in_bytes / 1e6:.0f} MB > 126 MB L2)"},
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": B * plan.n_mels * T * 4, "ms_per_step": te * 1e3, "steps": KE,
+                    "api": "LogMelPlan.run_host -> mlxa_logmel_host_f32 (pinned host in/out, chunked copy/compute overlap)",
+                    "matches_resident_path": e2e_match},
+            "gpu_launches": K * plan.kernel_launches_per_call,
+            "clocks": sampler.summary(t_start, t_end) if sampler else None}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(w, os.cpu_count() or 1, min(B, 64))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -161,6 +161,11 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
                          int64_t n_weights, int apply_db, int ref_is_max, float ref, float amin,
                          int use_top_db, float top_db, float* out_host);
 
+/* Measurement aid: launches blocks x threads threads, each running 8 independent chains of
+ * `iters` FFMAs (16*iters flops per thread).  bench.py times it to get the FP32 CUDA-core peak
+ * of the box the roofline fractions are quoted against. */
+int mlxa_ffma_probe(float* scratch, int blocks, int threads, int iters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ from .mel import hz_to_mel, mel_filterbank, mel_to_hz, melspectrogram
 from .mfcc import dct, dct_matrix, mfcc
 from .stft import check_nola, istft, magnitude, overlap_add, pad_signal, phase, stft
 from .windows import get_window
+from .pipeline import LogMelPlan
 from . import distributed
 
 __version__ = "0.1.0"
@@ -25,5 +26,5 @@ __all__ = [
     "power_to_db", "amplitude_to_db", "db_to_power", "db_to_amplitude",
     "dct", "dct_matrix", "mfcc", "griffinlim", "griffinlim_iter", "frame",
     "linear_filterbank", "bark_filterbank", "hz_to_bark", "bark_to_hz",
-    "pad_signal", "overlap_add", "distributed",
+    "pad_signal", "overlap_add", "distributed", "LogMelPlan",
 ]

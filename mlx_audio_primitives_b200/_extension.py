@@ -43,6 +43,7 @@ SIGNATURES = {
     "mlxa_mfcc_tail_f32": [_p, _i64, _i32, _i64, _p, _i32, _p, _i32, _f32, _f32, _i32, _f32, _p, _p, _p],
     "mlxa_logmel_host_f32": [_p, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f32, _p, _p, _p, _p, _i32, _i64,
                              _i32, _i32, _f32, _f32, _i32, _f32, _p],
+    "mlxa_ffma_probe": [_p, _i32, _i32, _i32, _p],
 }
 
 
@@ -50,7 +51,7 @@ def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"CUDA extension not found at {LIB_PATH}. Build it with "
-            "`python -m mlx_audio_primitives_b200.build` (needs nvcc, targets sm_100a). "
+            "`python mlx_audio_primitives_b200/build.py` (needs nvcc, targets sm_100a). "
             "There is no CPU fallback."
         )
     lib = C.CDLL(LIB_PATH)

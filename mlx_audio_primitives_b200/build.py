@@ -1,6 +1,6 @@
 """In-tree build of libmlxaudio_cuda.so (sm_100a only) with plain nvcc.
 
-    python -m mlx_audio_primitives_b200.build [--force] [--verbose]
+    python mlx_audio_primitives_b200/build.py [--force] [--verbose]
 
 The forward / inverse transform kernels are compiled once per planned n_fft
 (-DMLXA_NFFT=...) so the translation units build in parallel.  The result is

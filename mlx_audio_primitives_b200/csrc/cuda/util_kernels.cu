@@ -243,35 +243,37 @@ __global__ void mfcc_tail_kernel(const float* __restrict__ mel, int n_mels, long
 
 // ---- O(n^2) DFT fallback: any n_fft, same epilogues as the planned kernels -----------------
 template <int EP>
-__global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p, int nwarps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TT = p.tile_frames, n_fft = p.n_fft;
     const int b = blockIdx.y, t0 = blockIdx.x * TT, nt = min(TT, p.T - t0);
-    float* s_x = reinterpret_cast<float*>(smem_raw);  // [8 warps][n_fft] windowed frames
-    float* s_ep = s_x + 8 * n_fft;
+    float* s_x = reinterpret_cast<float*>(smem_raw);  // [nwarps][n_fft] windowed frames
+    float* s_ep = s_x + nwarps * n_fft;
     __shared__ float s_red[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* yb = p.y + (long long)b * p.ldy;
     float* xw = s_x + warp * n_fft;
-    for (int f = warp; f < nt; f += 8) {
-        const int t = t0 + f;
-        const bool valid = t < p.T_valid;
-        for (int n = lane; n < n_fft; n += 32)
-            xw[n] = valid ? load_padded(yb, p.L, t * p.hop - p.pad + n, p.pad_mode) * __ldg(p.window + n) : 0.f;
-        __syncwarp();
-        for (int k = lane; k < p.F; k += 32) {
-            float re = 0.f, im = 0.f;
-            int idx = 0;
-            for (int n = 0; n < n_fft; ++n) {
-                const float2 w = __ldg(p.tw_plan + idx);  // exp(-2*pi*i*idx/n_fft)
-                re = fmaf(xw[n], w.x, re);
-                im = fmaf(xw[n], w.y, im);
-                idx += k;
-                if (idx >= n_fft) idx -= n_fft;
+    if (warp < nwarps) {
+        for (int f = warp; f < nt; f += nwarps) {
+            const int t = t0 + f;
+            const bool valid = t < p.T_valid;
+            for (int n = lane; n < n_fft; n += 32)
+                xw[n] = valid ? load_padded(yb, p.L, t * p.hop - p.pad + n, p.pad_mode) * __ldg(p.window + n) : 0.f;
+            __syncwarp();
+            for (int k = lane; k < p.F; k += 32) {
+                float re = 0.f, im = 0.f;
+                int idx = 0;
+                for (int n = 0; n < n_fft; ++n) {
+                    const float2 w = __ldg(p.tw_plan + idx);  // exp(-2*pi*i*idx/n_fft)
+                    re = fmaf(xw[n], w.x, re);
+                    im = fmaf(xw[n], w.y, im);
+                    idx += k;
+                    if (idx >= n_fft) idx -= n_fft;
+                }
+                epilogue_bin<EP>(p, b, t, f, k, make_float2(re, im), s_ep, TT + 1);
             }
-            epilogue_bin<EP>(p, b, t, f, k, make_float2(re, im), s_ep, TT + 1);
+            __syncwarp();
         }
-        __syncwarp();
     }
     if constexpr (EP == EP_MEL) {
         __syncthreads();
@@ -280,8 +282,11 @@ __global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p) {
 }
 
 cudaError_t launch_fwd_naive(int ep, FwdParams& p, cudaStream_t s) {
-    int TT = (ep == EP_MEL) ? 8 : 8;
-    size_t smem = size_t(8) * p.n_fft * 4 + (ep == EP_MEL ? size_t(p.F) * (TT + 1) * 4 : 0);
+    const int TT = 8;
+    const size_t ep_bytes = (ep == EP_MEL) ? size_t(p.F) * (TT + 1) * 4 : 0;
+    int nwarps = 8;
+    while (nwarps > 1 && size_t(nwarps) * p.n_fft * 4 + ep_bytes > 200 * 1024) nwarps >>= 1;
+    const size_t smem = size_t(nwarps) * p.n_fft * 4 + ep_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     p.tile_frames = TT;
     dim3 grid((p.T + TT - 1) / TT, p.B);
@@ -289,7 +294,7 @@ cudaError_t launch_fwd_naive(int ep, FwdParams& p, cudaStream_t s) {
 #define MLXA_LAUNCH(EPV)                                                                               \
     e = cudaFuncSetAttribute(fwd_naive_kernel<EPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                    \
-    fwd_naive_kernel<EPV><<<grid, 256, smem, s>>>(p);
+    fwd_naive_kernel<EPV><<<grid, 256, smem, s>>>(p, nwarps);
     if (ep == EP_STFT) { MLXA_LAUNCH(EP_STFT) }
     else if (ep == EP_MEL) { MLXA_LAUNCH(EP_MEL) }
     else { MLXA_LAUNCH(EP_GL) }

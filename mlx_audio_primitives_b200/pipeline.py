@@ -1,0 +1,103 @@
+"""Pre-planned log-mel pipeline: ``power_to_db(melspectrogram(y))`` for a fixed batch shape with
+every buffer and constant resident, so one call is two kernel launches (fused mel kernel +
+dB pass) plus, when sharding is enabled, the one-float all-reduce between them.
+
+This is the serving-shaped entry point the benchmark drives; results are identical to calling
+``melspectrogram`` then ``power_to_db`` (same kernels, same arguments)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import distributed
+from ._extension import _ext, check
+from ._tensor import ptr, require_cuda
+from .mel import (_resolve_stft_args, check_band_args, frames_or_raise, mel_filterbank_host, pad_mode_code,
+                  sparse_bank_device)
+from .windows import padded_window, window_host
+
+
+class LogMelPlan:
+    def __init__(self, batch: int, length: int, sr: int = 22050, n_fft: int = 2048, hop_length: int | None = None,
+                 win_length: int | None = None, window: str = "hann", center: bool = True,
+                 pad_mode: str = "constant", power: float = 2.0, n_mels: int = 128, fmin: float = 0.0,
+                 fmax: float | None = None, htk: bool = False, norm: str | None = "slaney", ref=1.0,
+                 amin: float = 1e-10, top_db: float | None = 80.0, to_db: bool = True, device=None):
+        require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.B, self.L = int(batch), int(length)
+        self.n_fft = int(n_fft)
+        self.hop, self.win_length = _resolve_stft_args(n_fft, hop_length, win_length)
+        self.center, self.pad_mode, self.mode = bool(center), pad_mode, pad_mode_code(pad_mode)
+        self.power, self.n_mels = float(power), int(n_mels)
+        fmax = check_band_args(n_mels, "n_mels", fmin, fmax, sr)
+        if top_db is not None and top_db <= 0:
+            raise ValueError(f"top_db must be positive, got {top_db}")
+        self.ref_is_max = ref in ("max", torch.max, torch.amax, np.max, max)
+        self.ref = 1.0 if self.ref_is_max else float(ref)
+        self.amin, self.top_db, self.to_db = float(amin), top_db, bool(to_db)
+        self.T = frames_or_raise(self.L, self.n_fft, self.hop, self.center, pad_mode)
+        with torch.cuda.device(self.device):
+            key = ("mel", sr, n_fft, n_mels, float(fmin), float(fmax), bool(htk), norm)
+            self.bank = sparse_bank_device(key, lambda: mel_filterbank_host(sr, n_fft, n_mels, float(fmin),
+                                                                            float(fmax), bool(htk), norm))
+            self.win = padded_window(window, self.win_length, self.n_fft)
+            self.peak = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._win_host = np.zeros(self.n_fft, np.float32)
+        left = (self.n_fft - self.win_length) // 2
+        self._win_host[left:left + self.win_length] = window_host(window, self.win_length, True)
+        self.need_peak = self.to_db and (self.ref_is_max or self.top_db is not None)
+        self.kernel_launches_per_call = 1 + (2 if self.need_peak else 0)
+
+    def empty_output(self) -> torch.Tensor:
+        return torch.empty((self.B, self.n_mels, self.T), dtype=torch.float32, device=self.device)
+
+    # -- the two launches, separately callable so a benchmark can time the dominant kernel ----
+    def mel(self, y: torch.Tensor, out: torch.Tensor) -> None:
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if self.need_peak:
+            check(_ext.mlxa_fill_f32(ptr(self.peak), 1, 0.0, s), "fill")
+        fuse = self.to_db and not self.need_peak
+        check(_ext.mlxa_melspec_f32(ptr(y), self.B, self.L, y.stride(0), ptr(self.win), self.n_fft, self.hop,
+                                    int(self.center), self.mode, self.power, ptr(self.bank.start),
+                                    ptr(self.bank.length), ptr(self.bank.offset), ptr(self.bank.weights),
+                                    self.n_mels, ptr(out), ptr(self.peak) if self.need_peak else None,
+                                    int(fuse), 10.0, self.amin, self.ref, s), "melspectrogram")
+
+    def db(self, out: torch.Tensor) -> None:
+        if not self.need_peak:
+            return
+        distributed.all_reduce_max_(self.peak)
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        check(_ext.mlxa_to_db_f32(ptr(out), out.numel(), 10.0, self.amin, self.ref,
+                                  ptr(self.peak) if self.ref_is_max else None, int(self.top_db is not None),
+                                  float(self.top_db or 0.0), ptr(self.peak), ptr(out), s), "to_db")
+
+    def __call__(self, y: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        if y.shape != (self.B, self.L) or y.dtype != torch.float32 or not y.is_cuda or y.stride(1) != 1:
+            raise ValueError(f"expected a float32 CUDA tensor of shape ({self.B}, {self.L})")
+        if out is None:
+            out = self.empty_output()
+        self.mel(y, out)
+        self.db(out)
+        return out
+
+    # -- host buffers in, host buffers out (H2D / kernels / D2H overlapped inside the library) --
+    def run_host(self, y_host: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
+        """y_host (B, L) and out_host (B, n_mels, T): contiguous float32 CPU tensors (pinned for full
+        copy bandwidth).  Synchronous.  Single-GPU semantics: the batch-global max is local."""
+        if y_host.is_cuda or out_host.is_cuda or not y_host.is_contiguous() or not out_host.is_contiguous():
+            raise ValueError("run_host takes contiguous CPU tensors")
+        if tuple(y_host.shape) != (self.B, self.L) or tuple(out_host.shape) != (self.B, self.n_mels, self.T):
+            raise ValueError("shape mismatch with the plan")
+        st, ln, of, w = self.bank.host
+        vp = lambda a: a.ctypes.data_as(C.c_void_p).value
+        with torch.cuda.device(self.device):
+            check(_ext.mlxa_logmel_host_f32(y_host.data_ptr(), self.B, self.L, vp(self._win_host), self.n_fft, self.hop,
+                                            int(self.center), self.mode, self.power, vp(st), vp(ln), vp(of), vp(w),
+                                            self.n_mels, int(w.shape[0]), int(self.to_db), int(self.ref_is_max),
+                                            self.ref, self.amin, int(self.top_db is not None),
+                                            float(self.top_db or 0.0), out_host.data_ptr()), "logmel_host")
+        return out_host

@@ -178,7 +178,17 @@ def test_istft_matches_oracle_on_golden(ap, golden, cases):
         ref = golden[f"istft/{i}"]
         got = H(ap.istft(S, **ikw))  # (B, F, T)-contiguous input: exercises the transposing path
         assert got.shape == ref.shape, (i, kw)
-        assert np.abs(got - ref).max() <= 1e-5, (i, kw, np.abs(got - ref).max())
+        # Without centring the first/last samples are divided by a near-zero window sum (w^2 ~ 1e-9),
+        # which amplifies any float32 rounding of the inverse FFT by 1/w; compare where the
+        # normaliser is well conditioned and bound the rest relative to that amplification.
+        ok = np.ones(ref.shape[-1], bool)
+        if not kw.get("center", True):
+            hop_, win_ = o._resolve(kw["n_fft"], kw.get("hop_length"), kw.get("win_length"))
+            wss = o.window_sumsquare(o.padded_window(kw.get("window", "hann"), win_, kw["n_fft"]),
+                                     S.shape[-1], hop_, ref.shape[-1])
+            ok = wss >= 1e-2 * wss.max()
+            assert np.all(np.abs(got - ref)[:, ~ok] <= 1e-6 / np.sqrt(np.maximum(wss[~ok], 1e-8)) + 1e-5)
+        assert np.abs(got - ref)[:, ok].max() <= 1e-5, (i, kw, np.abs(got - ref)[:, ok].max())
         if kw.get("center", True):
             L = 300 if kw.get("hop_length") == 1 else 6000
             got = H(ap.istft(S, length=L, **ikw))
@@ -349,8 +359,8 @@ def test_griffinlim_matches_reference_code(ap, golden):
 
 def test_griffinlim_quality_and_errors(ap):
     """reference tests/test_griffinlim.py:31,100-121: spectral MSE thresholds per iteration count"""
-    from tests.conftest import chirp_noise
-    y = chirp_noise(22050)
+    t = np.arange(22050) / 22050.0  # chirp + noise, the reference's benchmark signal (benchmarks/utils.py:92-115)
+    y = (np.sin(2 * np.pi * (100 + 1000 * t) * t) + 0.1 * np.random.default_rng(42).standard_normal(22050)).astype(np.float32)
     S = np.abs(o.stft(y, 1024, 256))
     for n_iter, thr in [(16, 10.0), (32, 5.0)]:
         r = H(ap.griffinlim(S, n_iter=n_iter, hop_length=256, random_state=0))
