@@ -78,7 +78,8 @@ int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float
 /* STFT with the |X|^power + band-sparse filterbank epilogue (replaces mel.py:309-352 =
  * stft -> abs -> power -> dense matmul); the spectrum never reaches HBM.
  * Filterbank rows are given by their contiguous support: row m has band_len[m] weights
- * starting at bin band_start[m], stored at band_w[band_off[m] ...].
+ * starting at bin band_start[m], stored at band_w[band_off[m] ...]; n_weights = total number of
+ * stored weights (sum of band_len).
  * mel (B, n_bands, T).  gmax (optional, may be NULL): device float, atomically raised to
  * max(mel) -- the producer side of power_to_db(ref=max / top_db) (convert.py:42-58).
  * db_mode != 0 writes db_coef*log10(max(v, db_amin)/max(db_ref, db_amin)) instead of v
@@ -87,7 +88,7 @@ int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const fl
                      int n_fft, int hop, int center, int pad_mode, float power,
                      const int32_t* band_start, const int32_t* band_len,
                      const int32_t* band_off, const float* band_w, int n_bands,
-                     float* mel, float* gmax, int db_mode, float db_coef, float db_amin,
+                     int64_t n_weights, float* mel, float* gmax, int db_mode, float db_coef, float db_amin,
                      float db_ref, void* stream);
 
 /* irFFT -> window -> gather overlap-add -> / max(sum w^2, 1e-8) -> trim in one kernel

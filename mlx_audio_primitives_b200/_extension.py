@@ -25,7 +25,7 @@ SIGNATURES = {
     "mlxa_overlap_add_f32": [_p, _p, _i64, _i64, _i32, _i32, _i64, _p, _p],
     "mlxa_window_sumsquare_f32": [_p, _i32, _i32, _i64, _i64, _p, _p],
     "mlxa_stft_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _p, _p],
-    "mlxa_melspec_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f32, _p, _p, _p, _p, _i32,
+    "mlxa_melspec_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f32, _p, _p, _p, _p, _i32, _i64,
                          _p, _p, _i32, _f32, _f32, _f32, _p],
     "mlxa_istft_f32": [_p, _i64, _i64, _i32, _p, _p, _i32, _i32, _i64, _i64, _i64, _p, _i64, _p],
     "mlxa_griffinlim_project_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _i64, _i64, _p, _p, _p,

@@ -203,10 +203,11 @@ int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float
 
 int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window, int n_fft, int hop,
                      int center, int pad_mode, float power, const int32_t* band_start, const int32_t* band_len,
-                     const int32_t* band_off, const float* band_w, int n_bands, float* mel, float* gmax, int db_mode,
+                     const int32_t* band_off, const float* band_w, int n_bands, int64_t n_weights, float* mel,
+                     float* gmax, int db_mode,
                      float db_coef, float db_amin, float db_ref, void* stream) {
     CHECK_ARG(band_start && band_len && band_off && band_w && mel, "null pointer");
-    CHECK_ARG(n_bands > 0, "n_bands must be positive");
+    CHECK_ARG(n_bands > 0 && n_weights > 0 && n_weights < (1LL << 24), "bad filterbank size");
     return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
         FwdParams p;
         int rc = fill_fwd_common(p, y + b0 * ldy, nb, L, ldy, window, n_fft, hop, center, pad_mode);
@@ -215,6 +216,7 @@ int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const fl
         p.power_mode = (power == 2.0f) ? POW_SQUARE : (power == 1.0f ? POW_ABS : POW_GENERAL);
         p.band_start = band_start; p.band_len = band_len; p.band_off = band_off; p.band_w = band_w;
         p.n_bands = n_bands;
+        p.n_weights = n_weights;
         p.mel = mel + b0 * (int64_t)n_bands * p.T;
         p.gmax = gmax;
         p.db_mode = db_mode; p.db_coef = db_coef; p.db_amin = db_amin; p.db_ref = db_ref;
@@ -430,7 +432,7 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
         cudaStream_t s = ws.st[ci % NS];
         CHECK_CUDA(cudaMemcpyAsync(ws.d_y + b0 * L, y_host + b0 * L, sizeof(float) * (size_t)nb * L, cudaMemcpyHostToDevice, s), "h2d");
         int rc = mlxa_melspec_f32(ws.d_y + b0 * L, nb, L, L, ws.d_win, n_fft, hop, center, pad_mode, power, ws.d_bands,
-                                  ws.d_bands + n_bands, ws.d_bands + 2 * n_bands, ws.d_w, n_bands,
+                                  ws.d_bands + n_bands, ws.d_bands + 2 * n_bands, ws.d_w, n_bands, n_weights,
                                   ws.d_mel + b0 * mel_per_clip, need_max ? ws.d_gmax : nullptr, fuse_db ? 1 : 0, 10.0f,
                                   amin, ref, s);
         if (rc) return rc;

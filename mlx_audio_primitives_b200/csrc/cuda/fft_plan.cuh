@@ -106,6 +106,22 @@ MLXA_HD void pass_store_buf(int g, const float2* v, float2* buf) {
     });
 }
 
+// last pass: natural-order, UNPADDED store (lanes write consecutive elements, so no padding is
+// needed and the unpack step can index Z[k] / Z[N-k] without the phys() division)
+template <class P, int PASS>
+MLXA_HD void pass_store_natural(int g, const float2* v, float2* buf) {
+    constexpr int R = P::radix(PASS), NB = P::nb(PASS), RD = P::rounds(PASS), NS = P::ns(PASS);
+    static_assert(PASS == P::NPASS - 1, "natural store is for the last pass");
+    static_for<RD>([&](auto rd) {
+        constexpr int o = decltype(rd)::value * R;
+        const int b = g + decltype(rd)::value * P::G;
+        if ((NB % P::G == 0) || b < NB) {
+            float2* dst = buf + b;  // b < NS here: index = b + k*NS
+            static_for<R>([&](auto i) { dst[dft_perm(R, decltype(i)::value) * NS] = v[o + decltype(i)::value]; });
+        }
+    });
+}
+
 // hand natural-order results to a functor store(idx, value)
 template <class P, int PASS, class StoreF>
 MLXA_HD void pass_store_fn(int g, const float2* v, StoreF&& store) {

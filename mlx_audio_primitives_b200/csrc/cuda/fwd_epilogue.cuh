@@ -18,23 +18,21 @@ MLXA_D float load_padded(const float* __restrict__ yb, int L, int src, int mode)
     return __ldg(yb + src);
 }
 
-MLXA_D float spectral_power(float2 X, int mode, float power) {
+template <int PW>
+MLXA_D float spectral_power(float2 X, float power) {
     const float sq = fmaf(X.x, X.x, X.y * X.y);
-    if (mode == POW_SQUARE) return sq;
+    if constexpr (PW == POW_SQUARE) return sq;
     const float a = sqrtf(sq);
-    if (mode == POW_ABS) return a;
+    if constexpr (PW == POW_ABS) return a;
     return powf(a, power);
 }
 
+// EP_STFT / EP_GL: one bin straight to global memory
 template <int EP>
-MLXA_D void epilogue_bin(const FwdParams& p, int b, int t, int f_local, int k, float2 X,
-                         float* s_ep, int ep_stride) {
+MLXA_D void epilogue_bin_global(const FwdParams& p, long long o, float2 X) {
     if constexpr (EP == EP_STFT) {
-        p.spec[((long long)b * p.T + t) * p.F + k] = X;
-    } else if constexpr (EP == EP_MEL) {
-        s_ep[k * ep_stride + f_local] = spectral_power(X, p.power_mode, p.power);
+        p.spec[o] = X;
     } else {
-        const long long o = ((long long)b * p.T + t) * p.F + k;
         const float m = __ldg(p.mag + o);
         const float n2 = fmaf(X.x, X.x, X.y * X.y);
         float2 nw;
@@ -54,33 +52,80 @@ MLXA_D void epilogue_bin(const FwdParams& p, int b, int t, int f_local, int k, f
     }
 }
 
+// ---- band-sparse filterbank staged in shared memory ------------------------------------------
+// Row m: bins [start, start + 4*n4) with weights zero-padded to a multiple of four so the
+// projection loop reads them as float4.  Layout in smem (floats): [w4 ... | start | n4 | off4].
+struct MelSmem {
+    float4* w4;
+    int* start;
+    int* n4;
+    int* off4;
+};
+MLXA_HD size_t mel_smem_floats(int n_bands, long long n_weights) {
+    return size_t((n_weights + 3LL * n_bands + 3) & ~3LL) + 3 * size_t(n_bands) + 4;
+}
+MLXA_D MelSmem mel_smem_carve(float* base, int n_bands, long long n_weights) {
+    MelSmem m;
+    m.w4 = reinterpret_cast<float4*>(base);
+    int* ip = reinterpret_cast<int*>(base + ((n_weights + 3LL * n_bands + 3) & ~3LL));
+    m.start = ip;
+    m.n4 = ip + n_bands;
+    m.off4 = ip + 2 * n_bands;
+    return m;
+}
+// all threads; ends with __syncthreads()
+template <int THREADS>
+MLXA_D void mel_smem_fill(const FwdParams& p, MelSmem ms) {
+    if (threadIdx.x == 0) {
+        int o = 0;
+        for (int m = 0; m < p.n_bands; ++m) {
+            const int n4 = (__ldg(p.band_len + m) + 3) >> 2;
+            ms.off4[m] = o;
+            ms.n4[m] = n4;
+            ms.start[m] = __ldg(p.band_start + m);
+            o += n4;
+        }
+    }
+    __syncthreads();
+    float* w = reinterpret_cast<float*>(ms.w4);
+    for (int m = threadIdx.x >> 5; m < p.n_bands; m += THREADS / 32) {
+        const int len = __ldg(p.band_len + m), o = ms.off4[m] * 4, go = __ldg(p.band_off + m);
+        for (int j = threadIdx.x & 31; j < ms.n4[m] * 4; j += 32) w[o + j] = (j < len) ? __ldg(p.band_w + go + j) : 0.f;
+    }
+    __syncthreads();
+}
+
 // Band-sparse projection of the |X|^p tile: lanes run along the frames of the tile (coalesced
 // (B, n_bands, T) stores), warps x sub-lanes run along the bands.  Each row of the filterbank
 // is its contiguous support only (1.5-2.4 % of the dense matmul of mel.py:344).
 template <int THREADS>
-MLXA_D void mel_phase(const FwdParams& p, int b, int t0, int nt, const float* s_ep, int TT,
+MLXA_D void mel_phase(const FwdParams& p, int b, int t0, int nt, const float* s_ep, int TT, const MelSmem ms,
                       float* s_red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int subs = 32 / TT;
     const int t = lane % TT, sub = lane / TT;
     const int stride = TT + 1;
     float vmax = 0.f;
+    const float db_ref = fmaxf(p.db_ref, p.db_amin);
+    float* outb = p.mel + (long long)b * p.n_bands * p.T + t0 + t;
     for (int m = warp * subs + sub; m < p.n_bands; m += (THREADS / 32) * subs) {
-        const int len = __ldg(p.band_len + m);
-        const float* w = p.band_w + __ldg(p.band_off + m);
-        const float* col = s_ep + __ldg(p.band_start + m) * stride + t;
-        float a0 = 0.f, a1 = 0.f;
-        int j = 0;
-        for (; j + 1 < len; j += 2) {
-            a0 = fmaf(__ldg(w + j), col[j * stride], a0);
-            a1 = fmaf(__ldg(w + j + 1), col[(j + 1) * stride], a1);
+        const int n4 = ms.n4[m];
+        const float4* w4 = ms.w4 + ms.off4[m];
+        const float* col = s_ep + ms.start[m] * stride + t;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int j = 0; j < n4; ++j) {
+            const float4 w = w4[j];
+            a0 = fmaf(w.x, col[0], a0);
+            a1 = fmaf(w.y, col[stride], a1);
+            a2 = fmaf(w.z, col[2 * stride], a2);
+            a3 = fmaf(w.w, col[3 * stride], a3);
+            col += 4 * stride;
         }
-        if (j < len) a0 = fmaf(__ldg(w + j), col[j * stride], a0);
-        float v = a0 + a1;
+        float v = (a0 + a1) + (a2 + a3);
         if (t < nt) {
             vmax = fmaxf(vmax, v);
-            if (p.db_mode) v = p.db_coef * log10f(fmaxf(v, p.db_amin) / fmaxf(p.db_ref, p.db_amin));
-            p.mel[((long long)b * p.n_bands + m) * p.T + t0 + t] = v;
+            if (p.db_mode) v = p.db_coef * log10f(fmaxf(v, p.db_amin) / db_ref);
+            outb[(long long)m * p.T] = v;
         }
     }
     if (p.gmax != nullptr) {

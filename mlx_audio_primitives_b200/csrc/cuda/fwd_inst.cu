@@ -2,11 +2,13 @@
 // (built once per size with -DMLXA_NFFT=<n_fft>).
 //
 // One CTA = one clip x one tile of consecutive frames.  The hop-overlapped span of samples the
-// tile needs, (tile-1)*hop + n_fft, is staged ONCE in shared memory (padding is index
-// arithmetic on the way in), so HBM sees each input sample ~once instead of n_fft/hop times
-// plus three inflated round trips (reference stft.py:118-130).  Groups of G lanes then run the
-// Stockham plan per frame (or per frame pair), exchange through a padded smem buffer with
-// __syncwarp only, unpack the real spectrum and hand every bin to the epilogue in registers.
+// tile needs, (tile-1)*hop + n_fft, is staged ONCE in shared memory -- by a single 1-D bulk
+// async copy (TMA, cp.async.bulk + mbarrier) for interior tiles, by index arithmetic (the
+// padding rules) for the first/last tiles of a clip -- so HBM sees each input sample ~once
+// instead of n_fft/hop times plus three inflated round trips (reference stft.py:118-130).
+// Groups of G lanes then run the Stockham plan per frame (or per frame pair), exchange through a
+// padded smem buffer with __syncwarp only, unpack the real spectrum and hand every bin to the
+// epilogue in registers.  Window, twiddles and the band-sparse filterbank are smem-resident.
 #include "fft_plans_list.cuh"
 #include "fwd_epilogue.cuh"
 
@@ -20,13 +22,32 @@ namespace {  // per-translation-unit kernels: every n_fft gets its own copy
 using PF = PlanFor<MLXA_NFFT>;
 using P = PF::Plan;
 constexpr int NFFT = MLXA_NFFT;
-constexpr int FPT = (PF::MODE == MODE_PAIR) ? 2 : 1;          // frames per transform
+constexpr bool PACK = (PF::MODE == MODE_PACK);
+constexpr int FPT = PACK ? 1 : 2;                              // frames per transform
 constexpr int THREADS = (P::E > 32) ? 128 : 256;              // register-heavy plans run fewer warps
 constexpr int NG = THREADS / P::G;                            // transforms in flight per CTA
+static_assert((NG * P::BUF) % 2 == 0 && NFFT % 4 == 0, "smem carve-up assumes 16-byte multiples");
+constexpr int NBINS = NFFT / 2 + 1;
+constexpr int NUNPACK = PACK ? P::N + 1 : 0;                   // exp(-i*pi*k/N) entries
+constexpr bool TW_SMEM = (P::TW + NUNPACK) * 8 <= 20 * 1024;   // twiddles staged in smem when small
 
 constexpr int round_up4(int v) { return (v + 3) & ~3; }
 
-template <int EP>
+struct SmemLayout {
+    int in_floats, tw_f2, ep_floats, mel_floats;
+    size_t bytes;
+};
+__host__ __device__ inline SmemLayout smem_layout(int ep, int hop, int TT, int n_bands, long long n_weights) {
+    SmemLayout s;
+    s.in_floats = round_up4((TT - 1) * hop + NFFT + 8);  // +8: room for a 16-byte alignment lead + tail
+    s.tw_f2 = TW_SMEM ? ((P::TW + NUNPACK + 1) & ~1) : 0;  // even count keeps 16-byte alignment behind it
+    s.ep_floats = (ep == EP_MEL) ? round_up4((NBINS + 3) * (TT + 1)) : 0;
+    s.mel_floats = (ep == EP_MEL) ? round_up4((int)mel_smem_floats(n_bands, n_weights)) : 0;
+    s.bytes = size_t(s.in_floats + NFFT + s.ep_floats + s.mel_floats) * 4 + size_t(s.tw_f2 + NG * P::BUF) * 8 + 16;
+    return s;
+}
+
+template <int EP, int PW>
 __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TT = p.tile_frames;
@@ -34,27 +55,60 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
     const int t0 = blockIdx.x * TT;
     const int nt = min(TT, p.T - t0);
     const int tile_len = (nt - 1) * p.hop + NFFT;
+    const SmemLayout lay = smem_layout(EP, p.hop, TT, p.n_bands, p.n_weights);
 
     float* s_in = reinterpret_cast<float*>(smem_raw);
-    float* s_win = s_in + round_up4((TT - 1) * p.hop + NFFT);
-    float2* s_buf = reinterpret_cast<float2*>(s_win + NFFT);
+    float* s_win = s_in + lay.in_floats;
+    float2* s_tw = reinterpret_cast<float2*>(s_win + NFFT);
+    float2* s_buf = s_tw + lay.tw_f2;
     float* s_ep = reinterpret_cast<float*>(s_buf + NG * P::BUF);
+    float* s_mel = s_ep + lay.ep_floats;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mel + lay.mel_floats);
     __shared__ float s_red[THREADS / 32];
 
-    // ---- stage the tile's samples and the window --------------------------------------
-    {
-        const float* yb = p.y + (long long)b * p.ldy;
-        const int src0 = t0 * p.hop - p.pad;
+    // ---- stage the tile's samples --------------------------------------------------------
+    const float* yb = p.y + (long long)b * p.ldy;
+    const int src0 = t0 * p.hop - p.pad;
+    // interior tile: every sample exists -> one bulk async copy from the 16-byte aligned address
+    // at or below the first sample ("lead" extra floats in front)
+    const int lead = int((reinterpret_cast<uintptr_t>(yb + src0) & 15) >> 2);
+    const int n_bulk = round_up4(lead + tile_len);
+    const bool bulk = (src0 - lead >= 0) && (src0 - lead + n_bulk <= p.L) && ((reinterpret_cast<uintptr_t>(yb) & 3) == 0);
+    const int in_off = bulk ? lead : 0;
+    if (bulk) {
+        if (threadIdx.x == 0) mbar_init(s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(s_bar, n_bulk * 4);
+            bulk_copy_g2s(s_in, yb + src0 - lead, n_bulk * 4, s_bar);
+        }
+    } else {
         for (int i = threadIdx.x; i < tile_len; i += THREADS)
             s_in[i] = load_padded(yb, p.L, src0 + i, p.pad_mode);
-        for (int i = threadIdx.x; i < NFFT; i += THREADS) s_win[i] = __ldg(p.window + i);
     }
-    __syncthreads();
+    // ---- constants: window, twiddles, filterbank (overlaps the bulk copy) -----------------
+    for (int i = threadIdx.x; i < NFFT; i += THREADS) s_win[i] = __ldg(p.window + i);
+    if constexpr (TW_SMEM) {
+        for (int i = threadIdx.x; i < P::TW; i += THREADS) s_tw[i] = __ldg(p.tw_plan + i);
+        for (int i = threadIdx.x; i < NUNPACK; i += THREADS) s_tw[P::TW + i] = __ldg(p.tw_unpack + i);
+    }
+    const float2* tw_plan = TW_SMEM ? s_tw : p.tw_plan;
+    const float2* tw_unpack = TW_SMEM ? s_tw + P::TW : p.tw_unpack;
+    MelSmem ms{};
+    const int ep_stride = TT + 1;
+    if constexpr (EP == EP_MEL) {
+        ms = mel_smem_carve(s_mel, p.n_bands, p.n_weights);
+        for (int i = threadIdx.x; i < 3 * ep_stride; i += THREADS) s_ep[NBINS * ep_stride + i] = 0.f;  // pad rows
+        mel_smem_fill<THREADS>(p, ms);  // ends with __syncthreads()
+    } else {
+        __syncthreads();
+    }
+    if (bulk) mbar_wait(s_bar, 0);
 
     const int gi = threadIdx.x / P::G, g = threadIdx.x % P::G;
     float2* buf = s_buf + gi * P::BUF;
-    const int ep_stride = TT + 1;
-    const bool hop_even = (p.hop & 1) == 0;
+    const bool even_off = (((p.hop | in_off) & 1) == 0);
+    const float* tile = s_in + in_off;
 
     for (int base = 0; base < nt; base += NG * FPT) {
         const int f0 = base + gi * FPT;
@@ -62,9 +116,9 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
         float2 v[P::E];
 
         // ---- pass 0: windowed samples straight from the staged tile --------------------
-        if constexpr (PF::MODE == MODE_PACK) {
-            const float* src = s_in + (va ? f0 * p.hop : 0);
-            if (hop_even) {
+        if constexpr (PACK) {
+            const float* src = tile + (va ? f0 * p.hop : 0);
+            if (even_off) {
                 pass_load_fn<P, 0>(g, v, [&](int n) {
                     const float2 x = *reinterpret_cast<const float2*>(src + 2 * n);
                     const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
@@ -78,55 +132,71 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
             }
         } else {
             const bool vb = (f0 + 1 < nt) && (t0 + f0 + 1 < p.T_valid);
-            const float* sa = s_in + (va ? f0 * p.hop : 0);
-            const float* sb = s_in + (vb ? (f0 + 1) * p.hop : 0);
+            const float* sa = tile + (va ? f0 * p.hop : 0);
+            const float* sb = tile + (vb ? (f0 + 1) * p.hop : 0);
             pass_load_fn<P, 0>(g, v, [&](int n) {
                 const float w = s_win[n];
                 return make_float2(va ? sa[n] * w : 0.f, vb ? sb[n] * w : 0.f);
             });
         }
-        pass_compute<P, 0>(g, v, p.tw_plan);
+        pass_compute<P, 0>(g, v, tw_plan);
         pass_store_buf<P, 0>(g, v, buf);
         __syncwarp();
         pass_load_buf<P, 1>(g, v, buf);
         __syncwarp();
-        pass_compute<P, 1>(g, v, p.tw_plan);
-        pass_store_buf<P, 1>(g, v, buf);
-        __syncwarp();
+        pass_compute<P, 1>(g, v, tw_plan);
         if constexpr (P::NPASS == 3) {
+            pass_store_buf<P, 1>(g, v, buf);
+            __syncwarp();
             pass_load_buf<P, 2>(g, v, buf);
             __syncwarp();
-            pass_compute<P, 2>(g, v, p.tw_plan);
-            pass_store_buf<P, 2>(g, v, buf);
-            __syncwarp();
+            pass_compute<P, 2>(g, v, tw_plan);
         }
+        pass_store_natural<P, P::NPASS - 1>(g, v, buf);  // Z[k] at buf[k]
+        __syncwarp();
 
         // ---- unpack the real spectrum, feed the epilogue --------------------------------
-        if constexpr (PF::MODE == MODE_PACK) {
-            constexpr int N = P::N;  // n_fft / 2
-            if (f0 < nt) {
-                for (int k = g; k <= N; k += P::G) {
-                    const float2 zk = buf[P::phys(k == N ? 0 : k)];
-                    const float2 zm = buf[P::phys(k == 0 ? 0 : N - k)];
-                    const float2 w = __ldg(p.tw_unpack + k);
-                    const float ex = 0.5f * (zk.x + zm.x), ey = 0.5f * (zk.y - zm.y);
-                    const float ox = 0.5f * (zk.y + zm.y), oy = -0.5f * (zk.x - zm.x);
-                    const float2 X = make_float2(ex + fmaf(ox, w.x, -(oy * w.y)), ey + fmaf(ox, w.y, oy * w.x));
-                    epilogue_bin<EP>(p, b, t0 + f0, f0, k, X, s_ep, ep_stride);
-                }
-            }
-        } else {
-            constexpr int N = P::N;  // n_fft
-            if (f0 < nt) {
+        if (f0 < nt) {
+            constexpr int NQ = ceil_div(NBINS, P::G);
+            if constexpr (PACK) {
+                constexpr int N = P::N;  // n_fft / 2
+                const long long obase = ((long long)b * p.T + t0 + f0) * p.F;
+                static_for<NQ>([&](auto q) {
+                    constexpr int Q = decltype(q)::value;
+                    const int k = g + Q * P::G;
+                    if ((NQ * P::G == NBINS) || Q + 1 < NQ || k <= N) {
+                        const float2 zk = buf[(Q + 1 == NQ && k == N) ? 0 : k];
+                        const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
+                        const float2 w = tw_unpack[k];
+                        const float ex = 0.5f * (zk.x + zm.x), ey = 0.5f * (zk.y - zm.y);
+                        const float ox = 0.5f * (zk.y + zm.y), oy = -0.5f * (zk.x - zm.x);
+                        const float2 X = make_float2(ex + fmaf(ox, w.x, -(oy * w.y)), ey + fmaf(ox, w.y, oy * w.x));
+                        if constexpr (EP == EP_MEL) s_ep[k * ep_stride + f0] = spectral_power<PW>(X, p.power);
+                        else epilogue_bin_global<EP>(p, obase + k, X);
+                    }
+                });
+            } else {
+                constexpr int N = P::N;  // n_fft
                 const bool fb = f0 + 1 < nt;
-                for (int k = g; k <= N / 2; k += P::G) {
-                    const float2 zk = buf[P::phys(k)];
-                    const float2 zm = buf[P::phys(k == 0 ? 0 : N - k)];
-                    const float2 Xa = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-                    const float2 Xb = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
-                    epilogue_bin<EP>(p, b, t0 + f0, f0, k, Xa, s_ep, ep_stride);
-                    if (fb) epilogue_bin<EP>(p, b, t0 + f0 + 1, f0 + 1, k, Xb, s_ep, ep_stride);
-                }
+                const long long obase = ((long long)b * p.T + t0 + f0) * p.F;
+                static_for<NQ>([&](auto q) {
+                    constexpr int Q = decltype(q)::value;
+                    const int k = g + Q * P::G;
+                    if ((NQ * P::G == NBINS) || Q + 1 < NQ || k <= N / 2) {
+                        const float2 zk = buf[k];
+                        const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
+                        const float2 Xa = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                        const float2 Xb = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+                        if constexpr (EP == EP_MEL) {
+                            float* pe = s_ep + k * ep_stride + f0;
+                            pe[0] = spectral_power<PW>(Xa, p.power);
+                            pe[1] = spectral_power<PW>(Xb, p.power);  // column f0+1 <= TT always exists in the tile
+                        } else {
+                            epilogue_bin_global<EP>(p, obase + k, Xa);
+                            if (fb) epilogue_bin_global<EP>(p, obase + p.F + k, Xb);
+                        }
+                    }
+                });
             }
         }
         __syncwarp();
@@ -134,14 +204,8 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
 
     if constexpr (EP == EP_MEL) {
         __syncthreads();
-        mel_phase<THREADS>(p, b, t0, nt, s_ep, TT, s_red);
+        mel_phase<THREADS>(p, b, t0, nt, s_ep, TT, ms, s_red);
     }
-}
-
-static size_t fwd_smem_bytes(int ep, int hop, int TT, int F) {
-    size_t s = size_t(round_up4((TT - 1) * hop + NFFT)) * 4 + size_t(NFFT) * 4 + size_t(NG) * P::BUF * 8;
-    if (ep == EP_MEL) s += size_t(F) * (TT + 1) * 4;
-    return s;
 }
 
 }  // namespace
@@ -151,30 +215,31 @@ static size_t fwd_smem_bytes(int ep, int hop, int TT, int F) {
 
 cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t s) {
     constexpr size_t kMaxSmem = 227 * 1024;
+    auto bytes = [&](int TT) { return smem_layout(ep, p.hop, TT, p.n_bands, p.n_weights).bytes; };
     int TT;
     if (ep == EP_MEL) {
         TT = 32;  // lanes run along the tile's frames in the projection phase
-        while (TT > 1 && fwd_smem_bytes(ep, p.hop, TT, p.F) > kMaxSmem) TT >>= 1;
+        while (TT > 2 && bytes(TT) > kMaxSmem) TT >>= 1;
         // prefer two CTAs per SM when that is possible with a tile of >= 16 frames
-        if (TT == 32 && fwd_smem_bytes(ep, p.hop, 32, p.F) > kMaxSmem / 2 &&
-            fwd_smem_bytes(ep, p.hop, 16, p.F) <= kMaxSmem / 2)
-            TT = 16;
+        if (TT == 32 && bytes(32) > kMaxSmem / 2 && bytes(16) <= kMaxSmem / 2) TT = 16;
     } else {
         TT = 2 * NG * FPT;  // two rounds of transforms per staged tile
-        while (TT > 1 && fwd_smem_bytes(ep, p.hop, TT, p.F) > kMaxSmem / 2) TT >>= 1;
+        while (TT > 2 && bytes(TT) > kMaxSmem / 2) TT >>= 1;
     }
-    if (fwd_smem_bytes(ep, p.hop, TT, p.F) > kMaxSmem) return cudaErrorInvalidConfiguration;
+    if (bytes(TT) > kMaxSmem) return cudaErrorInvalidConfiguration;
     p.tile_frames = TT;
-    const size_t smem = fwd_smem_bytes(ep, p.hop, TT, p.F);
+    const size_t smem = bytes(TT);
     dim3 grid((p.T + TT - 1) / TT, p.B);
     cudaError_t e;
-#define MLXA_LAUNCH(EPV)                                                                          \
-    e = cudaFuncSetAttribute(fwd_kernel<EPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                               \
-    fwd_kernel<EPV><<<grid, THREADS, smem, s>>>(p);
-    if (ep == EP_STFT) { MLXA_LAUNCH(EP_STFT) }
-    else if (ep == EP_MEL) { MLXA_LAUNCH(EP_MEL) }
-    else { MLXA_LAUNCH(EP_GL) }
+#define MLXA_LAUNCH(EPV, PWV)                                                                          \
+    e = cudaFuncSetAttribute(fwd_kernel<EPV, PWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                    \
+    fwd_kernel<EPV, PWV><<<grid, THREADS, smem, s>>>(p);
+    if (ep == EP_STFT) { MLXA_LAUNCH(EP_STFT, POW_SQUARE) }
+    else if (ep == EP_GL) { MLXA_LAUNCH(EP_GL, POW_SQUARE) }
+    else if (p.power_mode == POW_SQUARE) { MLXA_LAUNCH(EP_MEL, POW_SQUARE) }
+    else if (p.power_mode == POW_ABS) { MLXA_LAUNCH(EP_MEL, POW_ABS) }
+    else { MLXA_LAUNCH(EP_MEL, POW_GENERAL) }
 #undef MLXA_LAUNCH
     return cudaGetLastError();
 }
@@ -182,9 +247,9 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
 // host tables: plan twiddles and the real-unpack twiddle exp(-i*pi*k/N)
 void MLXA_CAT(plan_tables_, MLXA_NFFT)(float2* tw_plan_host, int* n_plan, float2* tw_unpack_host, int* n_unpack) {
     *n_plan = P::TW;
-    *n_unpack = (PF::MODE == MODE_PACK) ? P::N + 1 : 0;
+    *n_unpack = NUNPACK;
     if (tw_plan_host) fill_plan_twiddles<P>(tw_plan_host);
-    if (tw_unpack_host && PF::MODE == MODE_PACK)
+    if (tw_unpack_host && PACK)
         for (int k = 0; k <= P::N; ++k) {
             const double a = -kPi * double(k) / double(P::N);
             tw_unpack_host[k] = make_float2(float(__builtin_cos(a)), float(__builtin_sin(a)));

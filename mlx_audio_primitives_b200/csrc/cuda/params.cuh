@@ -32,6 +32,7 @@ struct FwdParams {
     const int* band_off;
     const float* band_w;
     int n_bands;
+    long long n_weights;  // total filterbank weights (sizes the smem copy)
     float* mel;   // (B, n_bands, T)
     float* gmax;  // optional running max
     int db_mode;

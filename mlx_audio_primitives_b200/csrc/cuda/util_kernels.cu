@@ -247,12 +247,21 @@ __global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p, int n
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TT = p.tile_frames, n_fft = p.n_fft;
     const int b = blockIdx.y, t0 = blockIdx.x * TT, nt = min(TT, p.T - t0);
-    float* s_x = reinterpret_cast<float*>(smem_raw);  // [nwarps][n_fft] windowed frames
-    float* s_ep = s_x + nwarps * n_fft;
+    float* s_x = reinterpret_cast<float*>(smem_raw);  // [nwarps][round_up4(n_fft)] windowed frames
+    const int xs = (n_fft + 3) & ~3;
+    float* s_ep = s_x + nwarps * xs;
+    const int ep_floats = (EP == EP_MEL) ? (((p.F + 3) * (TT + 1) + 3) & ~3) : 0;
+    float* s_mel = s_ep + ep_floats;
     __shared__ float s_red[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* yb = p.y + (long long)b * p.ldy;
-    float* xw = s_x + warp * n_fft;
+    float* xw = s_x + warp * xs;
+    MelSmem ms{};
+    if constexpr (EP == EP_MEL) {
+        ms = mel_smem_carve(s_mel, p.n_bands, p.n_weights);
+        for (int i = threadIdx.x; i < 3 * (TT + 1); i += 256) s_ep[p.F * (TT + 1) + i] = 0.f;
+        mel_smem_fill<256>(p, ms);
+    }
     if (warp < nwarps) {
         for (int f = warp; f < nt; f += nwarps) {
             const int t = t0 + f;
@@ -270,23 +279,34 @@ __global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p, int n
                     idx += k;
                     if (idx >= n_fft) idx -= n_fft;
                 }
-                epilogue_bin<EP>(p, b, t, f, k, make_float2(re, im), s_ep, TT + 1);
+                const float2 X = make_float2(re, im);
+                if constexpr (EP == EP_MEL) {
+                    float pw;
+                    if (p.power_mode == POW_SQUARE) pw = spectral_power<POW_SQUARE>(X, p.power);
+                    else if (p.power_mode == POW_ABS) pw = spectral_power<POW_ABS>(X, p.power);
+                    else pw = spectral_power<POW_GENERAL>(X, p.power);
+                    s_ep[k * (TT + 1) + f] = pw;
+                } else {
+                    epilogue_bin_global<EP>(p, ((long long)b * p.T + t) * p.F + k, X);
+                }
             }
             __syncwarp();
         }
     }
     if constexpr (EP == EP_MEL) {
         __syncthreads();
-        mel_phase<256>(p, b, t0, nt, s_ep, TT, s_red);
+        mel_phase<256>(p, b, t0, nt, s_ep, TT, ms, s_red);
     }
 }
 
 cudaError_t launch_fwd_naive(int ep, FwdParams& p, cudaStream_t s) {
     const int TT = 8;
-    const size_t ep_bytes = (ep == EP_MEL) ? size_t(p.F) * (TT + 1) * 4 : 0;
+    const size_t ep_bytes = (ep == EP_MEL)
+        ? size_t(((p.F + 3) * (TT + 1) + 3) & ~3) * 4 + ((mel_smem_floats(p.n_bands, p.n_weights) + 3) & ~size_t(3)) * 4 : 0;
+    const size_t xs = size_t((p.n_fft + 3) & ~3) * 4;
     int nwarps = 8;
-    while (nwarps > 1 && size_t(nwarps) * p.n_fft * 4 + ep_bytes > 200 * 1024) nwarps >>= 1;
-    const size_t smem = size_t(nwarps) * p.n_fft * 4 + ep_bytes;
+    while (nwarps > 1 && size_t(nwarps) * xs + ep_bytes > 200 * 1024) nwarps >>= 1;
+    const size_t smem = size_t(nwarps) * xs + ep_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     p.tile_frames = TT;
     dim3 grid((p.T + TT - 1) / TT, p.B);

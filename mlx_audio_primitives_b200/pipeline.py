@@ -63,7 +63,7 @@ class LogMelPlan:
         check(_ext.mlxa_melspec_f32(ptr(y), self.B, self.L, y.stride(0), ptr(self.win), self.n_fft, self.hop,
                                     int(self.center), self.mode, self.power, ptr(self.bank.start),
                                     ptr(self.bank.length), ptr(self.bank.offset), ptr(self.bank.weights),
-                                    self.n_mels, ptr(out), ptr(self.peak) if self.need_peak else None,
+                                    self.n_mels, self.bank.n_weights, ptr(out), ptr(self.peak) if self.need_peak else None,
                                     int(fuse), 10.0, self.amin, self.ref, s), "melspectrogram")
 
     def db(self, out: torch.Tensor) -> None:
