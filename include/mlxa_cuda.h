@@ -75,20 +75,31 @@ int mlxa_window_sumsquare_f32(const float* window, int n_fft, int hop, int64_t T
 int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window,
                   int n_fft, int hop, int center, int pad_mode, mlxa_c64* spec, void* stream);
 
+/* Packed band-sparse filterbank ("bank"): a 16-byte aligned array of 32-bit words
+ *     float   w[4*n_w4]        row m's weights start at w[4*off4[m]], zero-padded to 4*n4[m] values
+ *     int32   start[n_bands]   first frequency bin of row m's contiguous support
+ *     int32   n4[n_bands]      ceil(support length / 4)
+ *     int32   off4[n_bands]
+ * padded to mlxa_packed_bank_words(n_bands, n_w4) words (a multiple of 4).  Every kernel that
+ * projects a spectrum bulk-copies this blob into shared memory.  mlxa_pack_filterbank builds it on
+ * the HOST from a dense (n_bands, F) row-major matrix (rows must have contiguous support, which
+ * triangular mel / linear / Bark banks have); returns n_w4 through *n_w4_out.  Call it with
+ * packed_host == NULL to size the buffer. */
+int64_t mlxa_packed_bank_words(int n_bands, int64_t n_w4);
+int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, float* packed_host,
+                         int64_t capacity_words, int64_t* n_w4_out);
+
 /* STFT with the |X|^power + band-sparse filterbank epilogue (replaces mel.py:309-352 =
  * stft -> abs -> power -> dense matmul); the spectrum never reaches HBM.
- * Filterbank rows are given by their contiguous support: row m has band_len[m] weights
- * starting at bin band_start[m], stored at band_w[band_off[m] ...]; n_weights = total number of
- * stored weights (sum of band_len).
+ * bank: packed filterbank on the DEVICE (see above).
  * mel (B, n_bands, T).  gmax (optional, may be NULL): device float, atomically raised to
  * max(mel) -- the producer side of power_to_db(ref=max / top_db) (convert.py:42-58).
  * db_mode != 0 writes db_coef*log10(max(v, db_amin)/max(db_ref, db_amin)) instead of v
  * (the no-global-max form of convert.py:48-52). */
 int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window,
                      int n_fft, int hop, int center, int pad_mode, float power,
-                     const int32_t* band_start, const int32_t* band_len,
-                     const int32_t* band_off, const float* band_w, int n_bands,
-                     int64_t n_weights, float* mel, float* gmax, int db_mode, float db_coef, float db_amin,
+                     const float* bank, int n_bands, int64_t n_w4,
+                     float* mel, float* gmax, int db_mode, float db_coef, float db_amin,
                      float db_ref, void* stream);
 
 /* irFFT -> window -> gather overlap-add -> / max(sum w^2, 1e-8) -> trim in one kernel
@@ -152,14 +163,13 @@ int mlxa_mfcc_tail_f32(const float* mel, int64_t B, int n_mels, int64_t T, const
 
 /* ---- host-buffer convenience (the e2e path: pinned or pageable HOST pointers) ------------ */
 /* log-mel of host clips with chunked H2D / compute / D2H overlap on internal streams.
- * y_host (B, L), out_host (B, n_bands, T).  The dB step is power_to_db(ref, amin, top_db)
+ * y_host (B, L), out_host (B, n_bands, T), bank_host: packed filterbank in HOST memory.  The dB step is power_to_db(ref, amin, top_db)
  * with the max taken over the whole batch; ref_is_max != 0 means ref = max(mel).
  * Synchronous: returns when out_host is complete. */
 int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float* window_host,
                          int n_fft, int hop, int center, int pad_mode, float power,
-                         const int32_t* band_start_host, const int32_t* band_len_host,
-                         const int32_t* band_off_host, const float* band_w_host, int n_bands,
-                         int64_t n_weights, int apply_db, int ref_is_max, float ref, float amin,
+                         const float* bank_host, int n_bands, int64_t n_w4,
+                         int apply_db, int ref_is_max, float ref, float amin,
                          int use_top_db, float top_db, float* out_host);
 
 /* Measurement aid: launches blocks x threads threads, each running 8 independent chains of

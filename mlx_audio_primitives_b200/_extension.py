@@ -25,7 +25,8 @@ SIGNATURES = {
     "mlxa_overlap_add_f32": [_p, _p, _i64, _i64, _i32, _i32, _i64, _p, _p],
     "mlxa_window_sumsquare_f32": [_p, _i32, _i32, _i64, _i64, _p, _p],
     "mlxa_stft_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _p, _p],
-    "mlxa_melspec_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f32, _p, _p, _p, _p, _i32, _i64,
+    "mlxa_pack_filterbank": [_p, _i32, _i32, _p, _i64, _p],
+    "mlxa_melspec_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i64,
                          _p, _p, _i32, _f32, _f32, _f32, _p],
     "mlxa_istft_f32": [_p, _i64, _i64, _i32, _p, _p, _i32, _i32, _i64, _i64, _i64, _p, _i64, _p],
     "mlxa_griffinlim_project_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _i64, _i64, _p, _p, _p,
@@ -41,7 +42,7 @@ SIGNATURES = {
     "mlxa_from_db_f32": [_p, _i64, _f32, _f32, _p, _p],
     "mlxa_dct_f32": [_p, _i64, _i32, _p, _i32, _p, _p],
     "mlxa_mfcc_tail_f32": [_p, _i64, _i32, _i64, _p, _i32, _p, _i32, _f32, _f32, _i32, _f32, _p, _p, _p],
-    "mlxa_logmel_host_f32": [_p, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f32, _p, _p, _p, _p, _i32, _i64,
+    "mlxa_logmel_host_f32": [_p, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i64,
                              _i32, _i32, _f32, _f32, _i32, _f32, _p],
     "mlxa_ffma_probe": [_p, _i32, _i32, _i32, _p],
 }
@@ -64,6 +65,8 @@ def _load() -> C.CDLL:
         fn.restype = C.c_int
     lib.mlxa_last_error.argtypes = []
     lib.mlxa_last_error.restype = C.c_char_p
+    lib.mlxa_packed_bank_words.argtypes = [_i32, _i64]
+    lib.mlxa_packed_bank_words.restype = _i64
     if lib.mlxa_abi_version() != ABI_VERSION:
         raise ImportError(f"ABI mismatch: library {lib.mlxa_abi_version()} != host layer {ABI_VERSION}; rebuild")
     return lib

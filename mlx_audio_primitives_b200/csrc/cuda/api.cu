@@ -131,6 +131,7 @@ int fill_fwd_common(FwdParams& p, const float* y, int64_t B, int64_t L, int64_t 
     p.T = (int)T; p.T_valid = (int)T; p.F = n_fft / 2 + 1;
     p.n_fft = n_fft; p.hop = hop; p.pad = pad; p.pad_mode = pad_mode;
     p.window = window;
+    p.const_bulk = ((uintptr_t)window & 15) == 0;
     Tables t;
     CHECK_CUDA(get_tables(n_fft, &t), "twiddle tables");
     p.tw_plan = t.tw_plan; p.tw_unpack = t.tw_unpack;
@@ -201,22 +202,49 @@ int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float
     });
 }
 
+int64_t mlxa_packed_bank_words(int n_bands, int64_t n_w4) { return packed_bank_words(n_bands, n_w4); }
+
+int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, float* packed_host, int64_t capacity_words,
+                         int64_t* n_w4_out) {
+    CHECK_ARG(dense_host && n_w4_out && n_bands > 0 && F > 0, "bad argument");
+    std::vector<int> start(n_bands, 0), n4(n_bands, 0), off4(n_bands, 0);
+    int64_t total = 0;
+    for (int m = 0; m < n_bands; ++m) {
+        const float* row = dense_host + (int64_t)m * F;
+        int lo = -1, hi = -1;
+        for (int k = 0; k < F; ++k)
+            if (row[k] != 0.f) { if (lo < 0) lo = k; hi = k; }
+        off4[m] = (int)total;
+        if (lo >= 0) { start[m] = lo; n4[m] = (hi - lo + 1 + 3) / 4; }
+        total += n4[m];
+    }
+    *n_w4_out = total;
+    if (!packed_host) return 0;
+    CHECK_ARG(capacity_words >= packed_bank_words(n_bands, total), "packed buffer too small");
+    const int64_t words = packed_bank_words(n_bands, total);
+    std::memset(packed_host, 0, sizeof(float) * words);
+    for (int m = 0; m < n_bands; ++m) {
+        const float* row = dense_host + (int64_t)m * F;
+        for (int j = 0; j < 4 * n4[m] && start[m] + j < F; ++j) packed_host[4 * (int64_t)off4[m] + j] = row[start[m] + j];
+    }
+    int32_t* ip = reinterpret_cast<int32_t*>(packed_host + 4 * total);
+    for (int m = 0; m < n_bands; ++m) { ip[m] = start[m]; ip[n_bands + m] = n4[m]; ip[2 * n_bands + m] = off4[m]; }
+    return 0;
+}
+
 int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window, int n_fft, int hop,
-                     int center, int pad_mode, float power, const int32_t* band_start, const int32_t* band_len,
-                     const int32_t* band_off, const float* band_w, int n_bands, int64_t n_weights, float* mel,
-                     float* gmax, int db_mode,
-                     float db_coef, float db_amin, float db_ref, void* stream) {
-    CHECK_ARG(band_start && band_len && band_off && band_w && mel, "null pointer");
-    CHECK_ARG(n_bands > 0 && n_weights > 0 && n_weights < (1LL << 24), "bad filterbank size");
+                     int center, int pad_mode, float power, const float* bank, int n_bands, int64_t n_w4, float* mel,
+                     float* gmax, int db_mode, float db_coef, float db_amin, float db_ref, void* stream) {
+    CHECK_ARG(bank && mel, "null pointer");
+    CHECK_ARG(n_bands > 0 && n_w4 > 0 && n_w4 < (1LL << 22), "bad filterbank size");
     return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
         FwdParams p;
         int rc = fill_fwd_common(p, y + b0 * ldy, nb, L, ldy, window, n_fft, hop, center, pad_mode);
         if (rc) return rc;
         p.power = power;
         p.power_mode = (power == 2.0f) ? POW_SQUARE : (power == 1.0f ? POW_ABS : POW_GENERAL);
-        p.band_start = band_start; p.band_len = band_len; p.band_off = band_off; p.band_w = band_w;
-        p.n_bands = n_bands;
-        p.n_weights = n_weights;
+        p.bank = bank; p.n_bands = n_bands; p.n_w4 = n_w4;
+        p.const_bulk = (((uintptr_t)bank | (uintptr_t)window) & 15) == 0;
         p.mel = mel + b0 * (int64_t)n_bands * p.T;
         p.gmax = gmax;
         p.db_mode = db_mode; p.db_coef = db_coef; p.db_amin = db_amin; p.db_ref = db_ref;
@@ -364,9 +392,8 @@ struct HostWorkspace {
     cudaStream_t st[NS] = {};
     cudaEvent_t done[NS] = {};
     bool init = false;
-    float *d_y = nullptr, *d_mel = nullptr, *d_win = nullptr, *d_w = nullptr, *d_gmax = nullptr;
-    int32_t* d_bands = nullptr;
-    size_t cap_y = 0, cap_mel = 0, cap_win = 0, cap_w = 0, cap_bands = 0;
+    float *d_y = nullptr, *d_mel = nullptr, *d_win = nullptr, *d_bank = nullptr, *d_gmax = nullptr;
+    size_t cap_y = 0, cap_mel = 0, cap_win = 0, cap_bank = 0;
 };
 std::map<int, HostWorkspace> g_ws;
 std::mutex g_ws_mu;
@@ -384,13 +411,12 @@ cudaError_t grow(T** p, size_t* cap, size_t need) {
 extern "C" {
 
 int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float* window_host, int n_fft, int hop,
-                         int center, int pad_mode, float power, const int32_t* band_start_host,
-                         const int32_t* band_len_host, const int32_t* band_off_host, const float* band_w_host,
-                         int n_bands, int64_t n_weights, int apply_db, int ref_is_max, float ref, float amin,
-                         int use_top_db, float top_db, float* out_host) {
-    CHECK_ARG(y_host && window_host && out_host && band_start_host && band_len_host && band_off_host && band_w_host,
-              "null pointer");
-    CHECK_ARG(B > 0 && L > 0 && n_bands > 0 && n_weights > 0, "bad shape");
+                         int center, int pad_mode, float power, const float* bank_host, int n_bands, int64_t n_w4,
+                         int apply_db, int ref_is_max, float ref, float amin, int use_top_db, float top_db,
+                         float* out_host) {
+    CHECK_ARG(y_host && window_host && out_host && bank_host, "null pointer");
+    CHECK_ARG(B > 0 && L > 0 && n_bands > 0 && n_w4 > 0, "bad shape");
+    const int64_t bank_words = packed_bank_words(n_bands, n_w4);
     int pad = 0;
     int64_t T = 0;
     CHECK_ARG(n_fft >= 2 && hop >= 1 && hop <= n_fft, "bad n_fft / hop");
@@ -412,14 +438,10 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
     CHECK_CUDA(grow(&ws.d_y, &ws.cap_y, (size_t)B * L), "malloc clips");
     CHECK_CUDA(grow(&ws.d_mel, &ws.cap_mel, (size_t)B * n_bands * T), "malloc mel");
     CHECK_CUDA(grow(&ws.d_win, &ws.cap_win, (size_t)n_fft), "malloc window");
-    CHECK_CUDA(grow(&ws.d_w, &ws.cap_w, (size_t)n_weights), "malloc weights");
-    CHECK_CUDA(grow(&ws.d_bands, &ws.cap_bands, (size_t)3 * n_bands), "malloc bands");
+    CHECK_CUDA(grow(&ws.d_bank, &ws.cap_bank, (size_t)bank_words), "malloc bank");
     cudaStream_t s0 = ws.st[0];
     CHECK_CUDA(cudaMemcpyAsync(ws.d_win, window_host, sizeof(float) * n_fft, cudaMemcpyHostToDevice, s0), "copy window");
-    CHECK_CUDA(cudaMemcpyAsync(ws.d_w, band_w_host, sizeof(float) * n_weights, cudaMemcpyHostToDevice, s0), "copy weights");
-    CHECK_CUDA(cudaMemcpyAsync(ws.d_bands, band_start_host, sizeof(int32_t) * n_bands, cudaMemcpyHostToDevice, s0), "copy bands");
-    CHECK_CUDA(cudaMemcpyAsync(ws.d_bands + n_bands, band_len_host, sizeof(int32_t) * n_bands, cudaMemcpyHostToDevice, s0), "copy bands");
-    CHECK_CUDA(cudaMemcpyAsync(ws.d_bands + 2 * n_bands, band_off_host, sizeof(int32_t) * n_bands, cudaMemcpyHostToDevice, s0), "copy bands");
+    CHECK_CUDA(cudaMemcpyAsync(ws.d_bank, bank_host, sizeof(float) * bank_words, cudaMemcpyHostToDevice, s0), "copy bank");
     CHECK_CUDA(cudaMemsetAsync(ws.d_gmax, 0, sizeof(float), s0), "memset");
     CHECK_CUDA(cudaEventRecord(ws.done[0], s0), "event");
     for (int i = 1; i < NS; ++i) CHECK_CUDA(cudaStreamWaitEvent(ws.st[i], ws.done[0], 0), "wait");
@@ -431,9 +453,8 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
         const int64_t nb = std::min(chunk, B - b0);
         cudaStream_t s = ws.st[ci % NS];
         CHECK_CUDA(cudaMemcpyAsync(ws.d_y + b0 * L, y_host + b0 * L, sizeof(float) * (size_t)nb * L, cudaMemcpyHostToDevice, s), "h2d");
-        int rc = mlxa_melspec_f32(ws.d_y + b0 * L, nb, L, L, ws.d_win, n_fft, hop, center, pad_mode, power, ws.d_bands,
-                                  ws.d_bands + n_bands, ws.d_bands + 2 * n_bands, ws.d_w, n_bands, n_weights,
-                                  ws.d_mel + b0 * mel_per_clip, need_max ? ws.d_gmax : nullptr, fuse_db ? 1 : 0, 10.0f,
+        int rc = mlxa_melspec_f32(ws.d_y + b0 * L, nb, L, L, ws.d_win, n_fft, hop, center, pad_mode, power, ws.d_bank,
+                                  n_bands, n_w4, ws.d_mel + b0 * mel_per_clip, need_max ? ws.d_gmax : nullptr, fuse_db ? 1 : 0, 10.0f,
                                   amin, ref, s);
         if (rc) return rc;
         if (!need_max)

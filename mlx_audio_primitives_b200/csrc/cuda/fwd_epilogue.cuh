@@ -52,47 +52,24 @@ MLXA_D void epilogue_bin_global(const FwdParams& p, long long o, float2 X) {
     }
 }
 
-// ---- band-sparse filterbank staged in shared memory ------------------------------------------
-// Row m: bins [start, start + 4*n4) with weights zero-padded to a multiple of four so the
-// projection loop reads them as float4.  Layout in smem (floats): [w4 ... | start | n4 | off4].
+// ---- band-sparse filterbank, packed (include/mlxa_cuda.h "packed filterbank") -----------------
+// words: [w: 4*n_w4 floats][start: n_bands][n4: n_bands][off4: n_bands], padded to a multiple of 4.
+// Row m covers bins [start[m], start[m] + 4*n4[m]) with weights w[4*off4[m] ...] zero-padded to a
+// multiple of four so the projection loop reads them as float4.  The blob is bulk-copied to smem.
 struct MelSmem {
-    float4* w4;
-    int* start;
-    int* n4;
-    int* off4;
+    const float4* w4;
+    const int* start;
+    const int* n4;
+    const int* off4;
 };
-MLXA_HD size_t mel_smem_floats(int n_bands, long long n_weights) {
-    return size_t((n_weights + 3LL * n_bands + 3) & ~3LL) + 3 * size_t(n_bands) + 4;
-}
-MLXA_D MelSmem mel_smem_carve(float* base, int n_bands, long long n_weights) {
+MLXA_D MelSmem mel_smem_carve(const float* base, int n_bands, long long n_w4) {
     MelSmem m;
-    m.w4 = reinterpret_cast<float4*>(base);
-    int* ip = reinterpret_cast<int*>(base + ((n_weights + 3LL * n_bands + 3) & ~3LL));
+    m.w4 = reinterpret_cast<const float4*>(base);
+    const int* ip = reinterpret_cast<const int*>(base + 4 * n_w4);
     m.start = ip;
     m.n4 = ip + n_bands;
     m.off4 = ip + 2 * n_bands;
     return m;
-}
-// all threads; ends with __syncthreads()
-template <int THREADS>
-MLXA_D void mel_smem_fill(const FwdParams& p, MelSmem ms) {
-    if (threadIdx.x == 0) {
-        int o = 0;
-        for (int m = 0; m < p.n_bands; ++m) {
-            const int n4 = (__ldg(p.band_len + m) + 3) >> 2;
-            ms.off4[m] = o;
-            ms.n4[m] = n4;
-            ms.start[m] = __ldg(p.band_start + m);
-            o += n4;
-        }
-    }
-    __syncthreads();
-    float* w = reinterpret_cast<float*>(ms.w4);
-    for (int m = threadIdx.x >> 5; m < p.n_bands; m += THREADS / 32) {
-        const int len = __ldg(p.band_len + m), o = ms.off4[m] * 4, go = __ldg(p.band_off + m);
-        for (int j = threadIdx.x & 31; j < ms.n4[m] * 4; j += 32) w[o + j] = (j < len) ? __ldg(p.band_w + go + j) : 0.f;
-    }
-    __syncthreads();
 }
 
 // Band-sparse projection of the |X|^p tile: lanes run along the frames of the tile (coalesced
@@ -113,6 +90,7 @@ MLXA_D void mel_phase(const FwdParams& p, int b, int t0, int nt, const float* s_
         const float4* w4 = ms.w4 + ms.off4[m];
         const float* col = s_ep + ms.start[m] * stride + t;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 1
         for (int j = 0; j < n4; ++j) {
             const float4 w = w4[j];
             a0 = fmaf(w.x, col[0], a0);

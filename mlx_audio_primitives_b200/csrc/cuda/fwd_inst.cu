@@ -31,18 +31,20 @@ constexpr int NBINS = NFFT / 2 + 1;
 constexpr int NUNPACK = PACK ? P::N + 1 : 0;                   // exp(-i*pi*k/N) entries
 constexpr bool TW_SMEM = (P::TW + NUNPACK) * 8 <= 20 * 1024;   // twiddles staged in smem when small
 
+constexpr int TWP = (P::TW + 1) & ~1, TWU = (NUNPACK + 1) & ~1;  // table sizes as uploaded (even counts)
+
 constexpr int round_up4(int v) { return (v + 3) & ~3; }
 
 struct SmemLayout {
     int in_floats, tw_f2, ep_floats, mel_floats;
     size_t bytes;
 };
-__host__ __device__ inline SmemLayout smem_layout(int ep, int hop, int TT, int n_bands, long long n_weights) {
+__host__ __device__ inline SmemLayout smem_layout(int ep, int hop, int TT, int n_bands, long long n_w4) {
     SmemLayout s;
     s.in_floats = round_up4((TT - 1) * hop + NFFT + 8);  // +8: room for a 16-byte alignment lead + tail
-    s.tw_f2 = TW_SMEM ? ((P::TW + NUNPACK + 1) & ~1) : 0;  // even count keeps 16-byte alignment behind it
+    s.tw_f2 = TW_SMEM ? (TWP + TWU) : 0;  // both tables padded to even counts (16-byte multiples)
     s.ep_floats = (ep == EP_MEL) ? round_up4((NBINS + 3) * (TT + 1)) : 0;
-    s.mel_floats = (ep == EP_MEL) ? round_up4((int)mel_smem_floats(n_bands, n_weights)) : 0;
+    s.mel_floats = (ep == EP_MEL) ? (int)packed_bank_words(n_bands, n_w4) : 0;
     s.bytes = size_t(s.in_floats + NFFT + s.ep_floats + s.mel_floats) * 4 + size_t(s.tw_f2 + NG * P::BUF) * 8 + 16;
     return s;
 }
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
     const int t0 = blockIdx.x * TT;
     const int nt = min(TT, p.T - t0);
     const int tile_len = (nt - 1) * p.hop + NFFT;
-    const SmemLayout lay = smem_layout(EP, p.hop, TT, p.n_bands, p.n_weights);
+    const SmemLayout lay = smem_layout(EP, p.hop, TT, p.n_bands, p.n_w4);
 
     float* s_in = reinterpret_cast<float*>(smem_raw);
     float* s_win = s_in + lay.in_floats;
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mel + lay.mel_floats);
     __shared__ float s_red[THREADS / 32];
 
-    // ---- stage the tile's samples --------------------------------------------------------
+    // ---- stage the tile's samples and the constants ------------------------------------------
     const float* yb = p.y + (long long)b * p.ldy;
     const int src0 = t0 * p.hop - p.pad;
     // interior tile: every sample exists -> one bulk async copy from the 16-byte aligned address
@@ -75,35 +77,42 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
     const int n_bulk = round_up4(lead + tile_len);
     const bool bulk = (src0 - lead >= 0) && (src0 - lead + n_bulk <= p.L) && ((reinterpret_cast<uintptr_t>(yb) & 3) == 0);
     const int in_off = bulk ? lead : 0;
-    if (bulk) {
-        if (threadIdx.x == 0) mbar_init(s_bar, 1);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(s_bar, n_bulk * 4);
-            bulk_copy_g2s(s_in, yb + src0 - lead, n_bulk * 4, s_bar);
+    const bool cbulk = p.const_bulk != 0;
+    const uint32_t mel_bytes = (EP == EP_MEL) ? uint32_t(lay.mel_floats) * 4u : 0u;
+    if (threadIdx.x == 0) mbar_init(s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tx = (bulk ? n_bulk * 4 : 0) + (TW_SMEM ? (TWP + TWU) * 8 : 0) + (cbulk ? NFFT * 4 + mel_bytes : 0);
+        mbar_arrive_expect_tx(s_bar, tx);
+        if (bulk) bulk_copy_g2s(s_in, yb + src0 - lead, n_bulk * 4, s_bar);
+        if constexpr (TW_SMEM) {
+            if (TWP) bulk_copy_g2s(s_tw, p.tw_plan, TWP * 8, s_bar);
+            if (TWU) bulk_copy_g2s(s_tw + TWP, p.tw_unpack, TWU * 8, s_bar);
         }
-    } else {
+        if (cbulk) {
+            bulk_copy_g2s(s_win, p.window, NFFT * 4, s_bar);
+            if (EP == EP_MEL) bulk_copy_g2s(s_mel, p.bank, mel_bytes, s_bar);
+        }
+    }
+    if (!bulk) {
         for (int i = threadIdx.x; i < tile_len; i += THREADS)
             s_in[i] = load_padded(yb, p.L, src0 + i, p.pad_mode);
     }
-    // ---- constants: window, twiddles, filterbank (overlaps the bulk copy) -----------------
-    for (int i = threadIdx.x; i < NFFT; i += THREADS) s_win[i] = __ldg(p.window + i);
-    if constexpr (TW_SMEM) {
-        for (int i = threadIdx.x; i < P::TW; i += THREADS) s_tw[i] = __ldg(p.tw_plan + i);
-        for (int i = threadIdx.x; i < NUNPACK; i += THREADS) s_tw[P::TW + i] = __ldg(p.tw_unpack + i);
+    if (!cbulk) {
+        for (int i = threadIdx.x; i < NFFT; i += THREADS) s_win[i] = __ldg(p.window + i);
+        if (EP == EP_MEL)
+            for (int i = threadIdx.x; i < lay.mel_floats; i += THREADS) s_mel[i] = __ldg(p.bank + i);
     }
     const float2* tw_plan = TW_SMEM ? s_tw : p.tw_plan;
-    const float2* tw_unpack = TW_SMEM ? s_tw + P::TW : p.tw_unpack;
+    const float2* tw_unpack = TW_SMEM ? s_tw + TWP : p.tw_unpack;
     MelSmem ms{};
     const int ep_stride = TT + 1;
     if constexpr (EP == EP_MEL) {
-        ms = mel_smem_carve(s_mel, p.n_bands, p.n_weights);
+        ms = mel_smem_carve(s_mel, p.n_bands, p.n_w4);
         for (int i = threadIdx.x; i < 3 * ep_stride; i += THREADS) s_ep[NBINS * ep_stride + i] = 0.f;  // pad rows
-        mel_smem_fill<THREADS>(p, ms);  // ends with __syncthreads()
-    } else {
-        __syncthreads();
     }
-    if (bulk) mbar_wait(s_bar, 0);
+    __syncthreads();
+    mbar_wait(s_bar, 0);
 
     const int gi = threadIdx.x / P::G, g = threadIdx.x % P::G;
     float2* buf = s_buf + gi * P::BUF;
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
 
 cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t s) {
     constexpr size_t kMaxSmem = 227 * 1024;
-    auto bytes = [&](int TT) { return smem_layout(ep, p.hop, TT, p.n_bands, p.n_weights).bytes; };
+    auto bytes = [&](int TT) { return smem_layout(ep, p.hop, TT, p.n_bands, p.n_w4).bytes; };
     int TT;
     if (ep == EP_MEL) {
         TT = 32;  // lanes run along the tile's frames in the projection phase
@@ -246,9 +255,13 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
 
 // host tables: plan twiddles and the real-unpack twiddle exp(-i*pi*k/N)
 void MLXA_CAT(plan_tables_, MLXA_NFFT)(float2* tw_plan_host, int* n_plan, float2* tw_unpack_host, int* n_unpack) {
-    *n_plan = P::TW;
-    *n_unpack = NUNPACK;
-    if (tw_plan_host) fill_plan_twiddles<P>(tw_plan_host);
+    *n_plan = TWP;       // even counts: the tables are bulk-copied in 16-byte units
+    *n_unpack = TWU;
+    if (tw_plan_host) {
+        for (int i = 0; i < TWP; ++i) tw_plan_host[i] = make_float2(0.f, 0.f);
+        fill_plan_twiddles<P>(tw_plan_host);
+    }
+    if (tw_unpack_host) for (int i = 0; i < TWU; ++i) tw_unpack_host[i] = make_float2(0.f, 0.f);
     if (tw_unpack_host && PACK)
         for (int k = 0; k <= P::N; ++k) {
             const double a = -kPi * double(k) / double(P::N);

@@ -27,12 +27,10 @@ struct FwdParams {
     // EP_MEL
     int power_mode;
     float power;
-    const int* band_start;
-    const int* band_len;
-    const int* band_off;
-    const float* band_w;
+    const float* bank;   // packed band-sparse filterbank (device), see fwd_epilogue.cuh
     int n_bands;
-    long long n_weights;  // total filterbank weights (sizes the smem copy)
+    long long n_w4;      // float4 weight groups in the packed bank
+    int const_bulk;      // window / bank pointers are 16-byte aligned -> bulk async copies
     float* mel;   // (B, n_bands, T)
     float* gmax;  // optional running max
     int db_mode;
@@ -43,6 +41,11 @@ struct FwdParams {
     float2* rebuilt;   // (B, T, F), out
     float momentum;
 };
+
+// 32-bit words of a packed band-sparse filterbank (layout: fwd_epilogue.cuh / mlxa_cuda.h)
+__host__ __device__ inline long long packed_bank_words(int n_bands, long long n_w4) {
+    return (4 * n_w4 + 3LL * n_bands + 3) & ~3LL;
+}
 
 struct InvParams {
     const float2* spec;  // (B, T, F_in)

@@ -258,9 +258,11 @@ __global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p, int n
     float* xw = s_x + warp * xs;
     MelSmem ms{};
     if constexpr (EP == EP_MEL) {
-        ms = mel_smem_carve(s_mel, p.n_bands, p.n_weights);
+        ms = mel_smem_carve(s_mel, p.n_bands, p.n_w4);
         for (int i = threadIdx.x; i < 3 * (TT + 1); i += 256) s_ep[p.F * (TT + 1) + i] = 0.f;
-        mel_smem_fill<256>(p, ms);
+        const int words = (int)packed_bank_words(p.n_bands, p.n_w4);
+        for (int i = threadIdx.x; i < words; i += 256) s_mel[i] = __ldg(p.bank + i);
+        __syncthreads();
     }
     if (warp < nwarps) {
         for (int f = warp; f < nt; f += nwarps) {
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p, int n
 cudaError_t launch_fwd_naive(int ep, FwdParams& p, cudaStream_t s) {
     const int TT = 8;
     const size_t ep_bytes = (ep == EP_MEL)
-        ? size_t(((p.F + 3) * (TT + 1) + 3) & ~3) * 4 + ((mel_smem_floats(p.n_bands, p.n_weights) + 3) & ~size_t(3)) * 4 : 0;
+        ? size_t(((p.F + 3) * (TT + 1) + 3) & ~3) * 4 + size_t(packed_bank_words(p.n_bands, p.n_w4)) * 4 : 0;
     const size_t xs = size_t((p.n_fft + 3) & ~3) * 4;
     int nwarps = 8;
     while (nwarps > 1 && size_t(nwarps) * xs + ep_bytes > 200 * 1024) nwarps >>= 1;

@@ -7,6 +7,7 @@ band-sparse rows (contiguous support per band) that the fused kernel consumes.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 import threading
 from dataclasses import dataclass
@@ -84,33 +85,35 @@ def mel_filterbank_host(sr, n_fft, n_mels, fmin, fmax, htk, norm) -> np.ndarray:
 
 @dataclass
 class SparseBank:
-    """Band-sparse rows of a filterbank on one device: row m covers bins
-    [start[m], start[m] + length[m]) with weights[offset[m] ...]."""
-    start: torch.Tensor
-    length: torch.Tensor
-    offset: torch.Tensor
-    weights: torch.Tensor
+    """A filterbank in the packed band-sparse form the kernels bulk-copy into shared memory
+    (layout: include/mlxa_cuda.h, "packed filterbank")."""
+    packed: torch.Tensor      # device, float32 words
     n_bands: int
-    n_weights: int
-    host: tuple  # (start, length, offset, weights) NumPy copies for the host-buffer entry point
+    n_w4: int
+    host: np.ndarray          # the same words on the host (for the host-buffer entry point)
 
 
 def sparse_rows_host(bank: np.ndarray):
-    n_bands = bank.shape[0]
-    start = np.zeros(n_bands, np.int32)
-    length = np.zeros(n_bands, np.int32)
-    offset = np.zeros(n_bands, np.int32)
-    chunks = []
-    pos = 0
-    for m in range(n_bands):
-        nz = np.flatnonzero(bank[m])
-        if nz.size:
-            start[m], length[m] = nz[0], nz[-1] - nz[0] + 1
-            chunks.append(bank[m, nz[0]:nz[-1] + 1])
-        offset[m] = pos
-        pos += int(length[m])
-    weights = np.concatenate(chunks).astype(np.float32) if chunks else np.zeros(1, np.float32)
-    return start, length, offset, weights
+    """(start, length, weights-per-row) of each row's contiguous support -- used by the tests to
+    show that the packed form reproduces the dense matrix exactly."""
+    out = []
+    for row in bank:
+        nz = np.flatnonzero(row)
+        out.append((int(nz[0]), int(nz[-1] - nz[0] + 1), row[nz[0]:nz[-1] + 1].copy()) if nz.size else (0, 0, row[:0]))
+    return out
+
+
+def pack_bank_host(bank: np.ndarray):
+    """dense (n_bands, F) float32 -> (packed words, n_w4) via the library's own packer."""
+    bank = np.ascontiguousarray(bank, dtype=np.float32)
+    n_bands, F = bank.shape
+    n_w4 = C.c_int64(0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(_ext.mlxa_pack_filterbank(vp(bank), n_bands, F, None, 0, C.byref(n_w4)), "pack_filterbank")
+    words = int(_ext.mlxa_packed_bank_words(n_bands, n_w4.value))
+    packed = np.zeros(words, dtype=np.float32)
+    check(_ext.mlxa_pack_filterbank(vp(bank), n_bands, F, vp(packed), words, C.byref(n_w4)), "pack_filterbank")
+    return packed, int(n_w4.value)
 
 
 _lock = threading.RLock()
@@ -135,9 +138,9 @@ def sparse_bank_device(key: tuple, host_fn) -> SparseBank:
     with _lock:
         sb = _sparse_cache.get(k)
         if sb is None:
-            rows = sparse_rows_host(np.asarray(host_fn()))
-            dev = [torch.from_numpy(a).cuda() for a in rows]
-            sb = SparseBank(*dev, n_bands=rows[0].shape[0], n_weights=int(rows[3].shape[0]), host=rows)
+            dense = np.asarray(host_fn())
+            packed, n_w4 = pack_bank_host(dense)
+            sb = SparseBank(torch.from_numpy(packed).cuda(), dense.shape[0], n_w4, packed)
             _sparse_cache[k] = sb
         return sb
 
@@ -204,8 +207,7 @@ def _melspec_from_bank(y, bank: SparseBank, n_fft, hop, win_length, window, cent
     peak = torch.zeros(1, dtype=torch.float32, device=y.device) if want_peak else None
     db = fused_db or (0, 10.0, 1e-10, 1.0)
     check(_ext.mlxa_melspec_f32(ptr(y), B, L, y.stride(0), ptr(win), n_fft, hop, int(center), mode, float(power),
-                                ptr(bank.start), ptr(bank.length), ptr(bank.offset), ptr(bank.weights),
-                                bank.n_bands, bank.n_weights, ptr(out), ptr(peak), int(db[0]), float(db[1]), float(db[2]),
+                                ptr(bank.packed), bank.n_bands, bank.n_w4, ptr(out), ptr(peak), int(db[0]), float(db[1]), float(db[2]),
                                 float(db[3]), stream_ptr(y)), "melspectrogram")
     res = out[0] if one_d else out
     if want_peak:

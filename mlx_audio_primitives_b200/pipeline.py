@@ -61,9 +61,8 @@ class LogMelPlan:
             check(_ext.mlxa_fill_f32(ptr(self.peak), 1, 0.0, s), "fill")
         fuse = self.to_db and not self.need_peak
         check(_ext.mlxa_melspec_f32(ptr(y), self.B, self.L, y.stride(0), ptr(self.win), self.n_fft, self.hop,
-                                    int(self.center), self.mode, self.power, ptr(self.bank.start),
-                                    ptr(self.bank.length), ptr(self.bank.offset), ptr(self.bank.weights),
-                                    self.n_mels, self.bank.n_weights, ptr(out), ptr(self.peak) if self.need_peak else None,
+                                    int(self.center), self.mode, self.power, ptr(self.bank.packed),
+                                    self.n_mels, self.bank.n_w4, ptr(out), ptr(self.peak) if self.need_peak else None,
                                     int(fuse), 10.0, self.amin, self.ref, s), "melspectrogram")
 
     def db(self, out: torch.Tensor) -> None:
@@ -92,12 +91,11 @@ class LogMelPlan:
             raise ValueError("run_host takes contiguous CPU tensors")
         if tuple(y_host.shape) != (self.B, self.L) or tuple(out_host.shape) != (self.B, self.n_mels, self.T):
             raise ValueError("shape mismatch with the plan")
-        st, ln, of, w = self.bank.host
         vp = lambda a: a.ctypes.data_as(C.c_void_p).value
         with torch.cuda.device(self.device):
             check(_ext.mlxa_logmel_host_f32(y_host.data_ptr(), self.B, self.L, vp(self._win_host), self.n_fft, self.hop,
-                                            int(self.center), self.mode, self.power, vp(st), vp(ln), vp(of), vp(w),
-                                            self.n_mels, int(w.shape[0]), int(self.to_db), int(self.ref_is_max),
+                                            int(self.center), self.mode, self.power, vp(self.bank.host),
+                                            self.n_mels, self.bank.n_w4, int(self.to_db), int(self.ref_is_max),
                                             self.ref, self.amin, int(self.top_db is not None),
                                             float(self.top_db or 0.0), out_host.data_ptr()), "logmel_host")
         return out_host

@@ -21,7 +21,7 @@ def test_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(ext.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in mlxa_cuda.h but not exported"
-    assert declared - {"mlxa_last_error"} == set(ext.SIGNATURES), "host-layer signature table out of sync"
+    assert declared - {"mlxa_last_error", "mlxa_packed_bank_words"} == set(ext.SIGNATURES), "host-layer signature table out of sync"
     assert ext._ext.mlxa_abi_version() == ext.ABI_VERSION
     assert ext._ext.mlxa_has_fast_plan(400) == 1 and ext._ext.mlxa_has_fast_plan(2048) == 1
     assert ext._ext.mlxa_has_fast_plan(600) == 0
@@ -34,7 +34,7 @@ def test_abi_exports_every_declared_symbol():
 
 def test_host_constants_match_reference_fixtures(golden):
     from mlx_audio_primitives_b200.windows import window_host
-    from mlx_audio_primitives_b200.mel import mel_filterbank_host, sparse_rows_host, hz_to_mel, mel_to_hz
+    from mlx_audio_primitives_b200.mel import mel_filterbank_host, pack_bank_host, hz_to_mel, mel_to_hz
     from mlx_audio_primitives_b200.mfcc import dct_matrix_host
     from mlx_audio_primitives_b200.filterbanks import _linear_host
     for key in golden.files:
@@ -47,12 +47,14 @@ def test_host_constants_match_reference_fixtures(golden):
             norm = None if parts[7] == "None" else parts[7]
             fb = mel_filterbank_host(sr, n_fft, n_mels, fmin, fmax, bool(int(parts[6])), norm)
             assert np.array_equal(fb, golden[key]), key
-            # the band-sparse rows reproduce the dense matrix exactly
-            start, length, offset, w = sparse_rows_host(fb)
-            dense = np.zeros_like(fb)
+            # the packed band-sparse form (what the kernels consume) reproduces the dense matrix exactly
+            packed, n_w4 = pack_bank_host(fb)
+            ints = packed[4 * n_w4:].view(np.int32)
+            start, n4, off4 = ints[:n_mels], ints[n_mels:2 * n_mels], ints[2 * n_mels:3 * n_mels]
+            dense = np.zeros((n_mels, fb.shape[1] + 3), np.float32)
             for m in range(n_mels):
-                dense[m, start[m]:start[m] + length[m]] = w[offset[m]:offset[m] + length[m]]
-            assert np.array_equal(dense, fb)
+                dense[m, start[m]:start[m] + 4 * n4[m]] = packed[4 * off4[m]:4 * (off4[m] + n4[m])]
+            assert np.array_equal(dense[:, :fb.shape[1]], fb) and not dense[:, fb.shape[1]:].any()
         elif parts[0] == "dctmat":
             norm = None if parts[3] == "None" else parts[3]
             assert np.array_equal(dct_matrix_host(int(parts[1]), int(parts[2]), norm), golden[key]), key

@@ -28,15 +28,21 @@ class _StubLib:
             assert len(args) == len(argtypes), f"{name}: {len(args)} args, ABI declares {len(argtypes)}"
             for a, t in zip(args, argtypes):
                 if t is ctypes.c_void_p:
-                    assert a is None or isinstance(a, int), f"{name}: pointer argument got {type(a)}"
+                    assert a is None or isinstance(a, (int, ctypes.c_void_p)) or hasattr(a, "_obj"), \
+                        f"{name}: pointer argument got {type(a)}"
                 else:
                     t(a)  # raises TypeError on a wrong Python type
             self.calls.append(name)
+            if name == "mlxa_pack_filterbank":  # out-parameter: report one float4 group per band
+                args[5]._obj.value = args[1]
             return 0
         return fn
 
     def mlxa_last_error(self):
         return b""
+
+    def mlxa_packed_bank_words(self, n_bands, n_w4):
+        return (4 * n_w4 + 3 * n_bands + 3) & ~3
 
 
 @pytest.fixture
