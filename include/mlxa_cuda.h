@@ -76,9 +76,9 @@ int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float
                   int n_fft, int hop, int center, int pad_mode, mlxa_c64* spec, void* stream);
 
 /* Packed band-sparse filterbank ("bank"): a 16-byte aligned array of 32-bit words
- *     float   w[4*n_w4]        row m's weights start at w[4*off4[m]], zero-padded to 4*n4[m] values
+ *     float   w[4*n_w4]        row m's weights start at w[4*off4[m]] (16-byte aligned, zero-padded)
  *     int32   start[n_bands]   first frequency bin of row m's contiguous support
- *     int32   n4[n_bands]      ceil(support length / 4)
+ *     int32   len[n_bands]     support length in bins
  *     int32   off4[n_bands]
  * padded to mlxa_packed_bank_words(n_bands, n_w4) words (a multiple of 4).  Every kernel that
  * projects a spectrum bulk-copies this blob into shared memory.  mlxa_pack_filterbank builds it on

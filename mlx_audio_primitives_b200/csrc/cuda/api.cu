@@ -207,7 +207,7 @@ int64_t mlxa_packed_bank_words(int n_bands, int64_t n_w4) { return packed_bank_w
 int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, float* packed_host, int64_t capacity_words,
                          int64_t* n_w4_out) {
     CHECK_ARG(dense_host && n_w4_out && n_bands > 0 && F > 0, "bad argument");
-    std::vector<int> start(n_bands, 0), n4(n_bands, 0), off4(n_bands, 0);
+    std::vector<int> start(n_bands, 0), len(n_bands, 0), off4(n_bands, 0);
     int64_t total = 0;
     for (int m = 0; m < n_bands; ++m) {
         const float* row = dense_host + (int64_t)m * F;
@@ -215,8 +215,8 @@ int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, float* pac
         for (int k = 0; k < F; ++k)
             if (row[k] != 0.f) { if (lo < 0) lo = k; hi = k; }
         off4[m] = (int)total;
-        if (lo >= 0) { start[m] = lo; n4[m] = (hi - lo + 1 + 3) / 4; }
-        total += n4[m];
+        if (lo >= 0) { start[m] = lo; len[m] = hi - lo + 1; }
+        total += (len[m] + 3) / 4;
     }
     *n_w4_out = total;
     if (!packed_host) return 0;
@@ -225,10 +225,10 @@ int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, float* pac
     std::memset(packed_host, 0, sizeof(float) * words);
     for (int m = 0; m < n_bands; ++m) {
         const float* row = dense_host + (int64_t)m * F;
-        for (int j = 0; j < 4 * n4[m] && start[m] + j < F; ++j) packed_host[4 * (int64_t)off4[m] + j] = row[start[m] + j];
+        for (int j = 0; j < len[m]; ++j) packed_host[4 * (int64_t)off4[m] + j] = row[start[m] + j];
     }
     int32_t* ip = reinterpret_cast<int32_t*>(packed_host + 4 * total);
-    for (int m = 0; m < n_bands; ++m) { ip[m] = start[m]; ip[n_bands + m] = n4[m]; ip[2 * n_bands + m] = off4[m]; }
+    for (int m = 0; m < n_bands; ++m) { ip[m] = start[m]; ip[n_bands + m] = len[m]; ip[2 * n_bands + m] = off4[m]; }
     return 0;
 }
 

@@ -53,54 +53,75 @@ MLXA_D void epilogue_bin_global(const FwdParams& p, long long o, float2 X) {
 }
 
 // ---- band-sparse filterbank, packed (include/mlxa_cuda.h "packed filterbank") -----------------
-// words: [w: 4*n_w4 floats][start: n_bands][n4: n_bands][off4: n_bands], padded to a multiple of 4.
-// Row m covers bins [start[m], start[m] + 4*n4[m]) with weights w[4*off4[m] ...] zero-padded to a
-// multiple of four so the projection loop reads them as float4.  The blob is bulk-copied to smem.
+// words: [w: 4*n_w4 floats][start: n_bands][len: n_bands][off4: n_bands], padded to a multiple of 4.
+// Row m covers bins [start[m], start[m] + len[m]) with weights w[4*off4[m] ...] (each row starts on
+// a 16-byte boundary, zero-padded).  The blob is bulk-copied to shared memory once per CTA.
 struct MelSmem {
-    const float4* w4;
+    const float* w;
     const int* start;
-    const int* n4;
+    const int* len;
     const int* off4;
 };
 MLXA_D MelSmem mel_smem_carve(const float* base, int n_bands, long long n_w4) {
     MelSmem m;
-    m.w4 = reinterpret_cast<const float4*>(base);
+    m.w = base;
     const int* ip = reinterpret_cast<const int*>(base + 4 * n_w4);
     m.start = ip;
-    m.n4 = ip + n_bands;
+    m.len = ip + n_bands;
     m.off4 = ip + 2 * n_bands;
     return m;
 }
 
-// Band-sparse projection of the |X|^p tile: lanes run along the frames of the tile (coalesced
-// (B, n_bands, T) stores), warps x sub-lanes run along the bands.  Each row of the filterbank
-// is its contiguous support only (1.5-2.4 % of the dense matmul of mel.py:344).
+// Band-sparse projection done by the SAME lane group that produced the spectrum, straight from
+// the |X|^p values it just parked in its exchange buffer: lanes run along the bands (row m of
+// the filterbank is its contiguous support only -- 1.5-2.4 % of the dense matmul of mel.py:344),
+// NF frames (1 for a packed transform, 2 for a frame pair) share every weight load.  Results go
+// to the [n_bands][tile+1] staging tile s_out, column f0 (+1).
+template <int G, int NF>
+MLXA_D void mel_project_group(const MelSmem ms, int n_bands, int g, const float* pw, float* s_out, int ostride, int f0) {
+    for (int m = g; m < n_bands; m += G) {
+        const int n = ms.len[m];
+        const float* w = ms.w + 4 * ms.off4[m];
+        if constexpr (NF == 2) {
+            const float2* p2 = reinterpret_cast<const float2*>(pw) + ms.start[m];
+            float a = 0.f, b = 0.f;
+#pragma unroll 2
+            for (int i = 0; i < n; ++i) {
+                const float2 pp = p2[i];
+                const float ww = w[i];
+                a = fmaf(ww, pp.x, a);
+                b = fmaf(ww, pp.y, b);
+            }
+            s_out[m * ostride + f0] = a;
+            s_out[m * ostride + f0 + 1] = b;
+        } else {
+            const float* p1 = pw + ms.start[m];
+            float a = 0.f, b = 0.f;
+            int i = 0;
+            for (; i + 1 < n; i += 2) {
+                a = fmaf(w[i], p1[i], a);
+                b = fmaf(w[i + 1], p1[i + 1], b);
+            }
+            if (i < n) a = fmaf(w[i], p1[i], a);
+            s_out[m * ostride + f0] = a + b;
+        }
+    }
+}
+
+// Tile store: s_out [n_bands][TT+1] -> mel (B, n_bands, T), lanes along the frames (coalesced),
+// with the optional fused dB and the running max for power_to_db(ref=max / top_db).
 template <int THREADS>
-MLXA_D void mel_phase(const FwdParams& p, int b, int t0, int nt, const float* s_ep, int TT, const MelSmem ms,
-                      float* s_red) {
+MLXA_D void mel_store_tile(const FwdParams& p, int b, int t0, int nt, const float* s_out, int TT, float* s_red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int subs = 32 / TT;
+    const int subs = 32 / TT;  // TT is a power of two <= 32
     const int t = lane % TT, sub = lane / TT;
-    const int stride = TT + 1;
+    const int ostride = TT + 1;
     float vmax = 0.f;
     const float db_ref = fmaxf(p.db_ref, p.db_amin);
     float* outb = p.mel + (long long)b * p.n_bands * p.T + t0 + t;
-    for (int m = warp * subs + sub; m < p.n_bands; m += (THREADS / 32) * subs) {
-        const int n4 = ms.n4[m];
-        const float4* w4 = ms.w4 + ms.off4[m];
-        const float* col = s_ep + ms.start[m] * stride + t;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 1
-        for (int j = 0; j < n4; ++j) {
-            const float4 w = w4[j];
-            a0 = fmaf(w.x, col[0], a0);
-            a1 = fmaf(w.y, col[stride], a1);
-            a2 = fmaf(w.z, col[2 * stride], a2);
-            a3 = fmaf(w.w, col[3 * stride], a3);
-            col += 4 * stride;
-        }
-        float v = (a0 + a1) + (a2 + a3);
-        if (t < nt) {
+    if (t < nt) {
+        for (int m = warp * subs + sub; m < p.n_bands; m += (THREADS / 32) * subs) {
+            float v = s_out[m * ostride + t];
             vmax = fmaxf(vmax, v);
             if (p.db_mode) v = p.db_coef * log10f(fmaxf(v, p.db_amin) / db_ref);
             outb[(long long)m * p.T] = v;

@@ -43,7 +43,7 @@ __host__ __device__ inline SmemLayout smem_layout(int ep, int hop, int TT, int n
     SmemLayout s;
     s.in_floats = round_up4((TT - 1) * hop + NFFT + 8);  // +8: room for a 16-byte alignment lead + tail
     s.tw_f2 = TW_SMEM ? (TWP + TWU) : 0;  // both tables padded to even counts (16-byte multiples)
-    s.ep_floats = (ep == EP_MEL) ? round_up4((NBINS + 3) * (TT + 1)) : 0;
+    s.ep_floats = (ep == EP_MEL) ? round_up4(n_bands * (TT + 1)) : 0;  // mel staging tile [n_bands][TT+1]
     s.mel_floats = (ep == EP_MEL) ? (int)packed_bank_words(n_bands, n_w4) : 0;
     s.bytes = size_t(s.in_floats + NFFT + s.ep_floats + s.mel_floats) * 4 + size_t(s.tw_f2 + NG * P::BUF) * 8 + 16;
     return s;
@@ -109,7 +109,6 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
     const int ep_stride = TT + 1;
     if constexpr (EP == EP_MEL) {
         ms = mel_smem_carve(s_mel, p.n_bands, p.n_w4);
-        for (int i = threadIdx.x; i < 3 * ep_stride; i += THREADS) s_ep[NBINS * ep_stride + i] = 0.f;  // pad rows
     }
     __syncthreads();
     mbar_wait(s_bar, 0);
@@ -165,45 +164,73 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
         __syncwarp();
 
         // ---- unpack the real spectrum, feed the epilogue --------------------------------
-        if (f0 < nt) {
-            constexpr int NQ = ceil_div(NBINS, P::G);
-            if constexpr (PACK) {
-                constexpr int N = P::N;  // n_fft / 2
-                const long long obase = ((long long)b * p.T + t0 + f0) * p.F;
-                static_for<NQ>([&](auto q) {
-                    constexpr int Q = decltype(q)::value;
-                    const int k = g + Q * P::G;
-                    if ((NQ * P::G == NBINS) || Q + 1 < NQ || k <= N) {
+        constexpr int NQ = ceil_div(NBINS, P::G);
+        if constexpr (EP == EP_MEL) {
+            // |X|^p of every bin into registers, then parked in the group's own exchange buffer
+            // (Z is dead by then) where the band-sparse projection reads it.
+            float pw[NQ * FPT];
+            static_for<NQ>([&](auto q) {
+                constexpr int Q = decltype(q)::value;
+                const int k = g + Q * P::G;
+                if (Q + 1 < NQ || k < NBINS) {
+                    if constexpr (PACK) {
+                        constexpr int N = P::N;
                         const float2 zk = buf[(Q + 1 == NQ && k == N) ? 0 : k];
                         const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
                         const float2 w = tw_unpack[k];
                         const float ex = 0.5f * (zk.x + zm.x), ey = 0.5f * (zk.y - zm.y);
                         const float ox = 0.5f * (zk.y + zm.y), oy = -0.5f * (zk.x - zm.x);
                         const float2 X = make_float2(ex + fmaf(ox, w.x, -(oy * w.y)), ey + fmaf(ox, w.y, oy * w.x));
-                        if constexpr (EP == EP_MEL) s_ep[k * ep_stride + f0] = spectral_power<PW>(X, p.power);
-                        else epilogue_bin_global<EP>(p, obase + k, X);
+                        pw[Q] = spectral_power<PW>(X, p.power);
+                    } else {
+                        constexpr int N = P::N;
+                        const float2 zk = buf[k];
+                        const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
+                        pw[2 * Q] = spectral_power<PW>(make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y)), p.power);
+                        pw[2 * Q + 1] = spectral_power<PW>(make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x)), p.power);
+                    }
+                }
+            });
+            __syncwarp();
+            float* pbuf = reinterpret_cast<float*>(buf);
+            static_for<NQ>([&](auto q) {
+                constexpr int Q = decltype(q)::value;
+                const int k = g + Q * P::G;
+                if (Q + 1 < NQ || k < NBINS) {
+                    if constexpr (PACK) pbuf[k] = pw[Q];
+                    else reinterpret_cast<float2*>(pbuf)[k] = make_float2(pw[2 * Q], pw[2 * Q + 1]);
+                }
+            });
+            __syncwarp();
+            if (f0 < nt) mel_project_group<P::G, FPT>(ms, p.n_bands, g, pbuf, s_ep, ep_stride, f0);
+        } else if (f0 < nt) {
+            const long long obase = ((long long)b * p.T + t0 + f0) * p.F;
+            if constexpr (PACK) {
+                constexpr int N = P::N;  // n_fft / 2
+                static_for<NQ>([&](auto q) {
+                    constexpr int Q = decltype(q)::value;
+                    const int k = g + Q * P::G;
+                    if (Q + 1 < NQ || k <= N) {
+                        const float2 zk = buf[(Q + 1 == NQ && k == N) ? 0 : k];
+                        const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
+                        const float2 w = tw_unpack[k];
+                        const float ex = 0.5f * (zk.x + zm.x), ey = 0.5f * (zk.y - zm.y);
+                        const float ox = 0.5f * (zk.y + zm.y), oy = -0.5f * (zk.x - zm.x);
+                        const float2 X = make_float2(ex + fmaf(ox, w.x, -(oy * w.y)), ey + fmaf(ox, w.y, oy * w.x));
+                        epilogue_bin_global<EP>(p, obase + k, X);
                     }
                 });
             } else {
                 constexpr int N = P::N;  // n_fft
                 const bool fb = f0 + 1 < nt;
-                const long long obase = ((long long)b * p.T + t0 + f0) * p.F;
                 static_for<NQ>([&](auto q) {
                     constexpr int Q = decltype(q)::value;
                     const int k = g + Q * P::G;
-                    if ((NQ * P::G == NBINS) || Q + 1 < NQ || k <= N / 2) {
+                    if (Q + 1 < NQ || k <= N / 2) {
                         const float2 zk = buf[k];
                         const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
-                        const float2 Xa = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-                        const float2 Xb = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
-                        if constexpr (EP == EP_MEL) {
-                            float* pe = s_ep + k * ep_stride + f0;
-                            pe[0] = spectral_power<PW>(Xa, p.power);
-                            pe[1] = spectral_power<PW>(Xb, p.power);  // column f0+1 <= TT always exists in the tile
-                        } else {
-                            epilogue_bin_global<EP>(p, obase + k, Xa);
-                            if (fb) epilogue_bin_global<EP>(p, obase + p.F + k, Xb);
-                        }
+                        epilogue_bin_global<EP>(p, obase + k, make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y)));
+                        if (fb) epilogue_bin_global<EP>(p, obase + p.F + k, make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x)));
                     }
                 });
             }
@@ -213,7 +240,7 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
 
     if constexpr (EP == EP_MEL) {
         __syncthreads();
-        mel_phase<THREADS>(p, b, t0, nt, s_ep, TT, ms, s_red);
+        mel_store_tile<THREADS>(p, b, t0, nt, s_ep, TT, s_red);
     }
 }
 

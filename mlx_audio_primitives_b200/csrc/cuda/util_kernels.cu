@@ -247,11 +247,12 @@ __global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p, int n
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TT = p.tile_frames, n_fft = p.n_fft;
     const int b = blockIdx.y, t0 = blockIdx.x * TT, nt = min(TT, p.T - t0);
-    float* s_x = reinterpret_cast<float*>(smem_raw);  // [nwarps][round_up4(n_fft)] windowed frames
-    const int xs = (n_fft + 3) & ~3;
-    float* s_ep = s_x + nwarps * xs;
-    const int ep_floats = (EP == EP_MEL) ? (((p.F + 3) * (TT + 1) + 3) & ~3) : 0;
-    float* s_mel = s_ep + ep_floats;
+    const int xs = (n_fft + 3) & ~3, ps = (p.F + 3) & ~3;
+    float* s_x = reinterpret_cast<float*>(smem_raw);  // [nwarps][xs] windowed frames
+    float* s_p = s_x + nwarps * xs;                    // [nwarps][ps] |X|^p of the warp's frame (EP_MEL)
+    float* s_out = s_p + (EP == EP_MEL ? nwarps * ps : 0);
+    const int out_floats = (EP == EP_MEL) ? ((p.n_bands * (TT + 1) + 3) & ~3) : 0;
+    float* s_mel = s_out + out_floats;
     __shared__ float s_red[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* yb = p.y + (long long)b * p.ldy;
@@ -259,7 +260,6 @@ __global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p, int n
     MelSmem ms{};
     if constexpr (EP == EP_MEL) {
         ms = mel_smem_carve(s_mel, p.n_bands, p.n_w4);
-        for (int i = threadIdx.x; i < 3 * (TT + 1); i += 256) s_ep[p.F * (TT + 1) + i] = 0.f;
         const int words = (int)packed_bank_words(p.n_bands, p.n_w4);
         for (int i = threadIdx.x; i < words; i += 256) s_mel[i] = __ldg(p.bank + i);
         __syncthreads();
@@ -287,28 +287,32 @@ __global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p, int n
                     if (p.power_mode == POW_SQUARE) pw = spectral_power<POW_SQUARE>(X, p.power);
                     else if (p.power_mode == POW_ABS) pw = spectral_power<POW_ABS>(X, p.power);
                     else pw = spectral_power<POW_GENERAL>(X, p.power);
-                    s_ep[k * (TT + 1) + f] = pw;
+                    s_p[warp * ps + k] = pw;
                 } else {
                     epilogue_bin_global<EP>(p, ((long long)b * p.T + t) * p.F + k, X);
                 }
             }
             __syncwarp();
+            if constexpr (EP == EP_MEL) {
+                mel_project_group<32, 1>(ms, p.n_bands, lane, s_p + warp * ps, s_out, TT + 1, f);
+                __syncwarp();
+            }
         }
     }
     if constexpr (EP == EP_MEL) {
         __syncthreads();
-        mel_phase<256>(p, b, t0, nt, s_ep, TT, ms, s_red);
+        mel_store_tile<256>(p, b, t0, nt, s_out, TT, s_red);
     }
 }
 
 cudaError_t launch_fwd_naive(int ep, FwdParams& p, cudaStream_t s) {
     const int TT = 8;
-    const size_t ep_bytes = (ep == EP_MEL)
-        ? size_t(((p.F + 3) * (TT + 1) + 3) & ~3) * 4 + size_t(packed_bank_words(p.n_bands, p.n_w4)) * 4 : 0;
-    const size_t xs = size_t((p.n_fft + 3) & ~3) * 4;
+    const size_t xs = size_t((p.n_fft + 3) & ~3) * 4, ps = (ep == EP_MEL) ? size_t((p.F + 3) & ~3) * 4 : 0;
+    const size_t fixed = (ep == EP_MEL)
+        ? size_t((p.n_bands * (TT + 1) + 3) & ~3) * 4 + size_t(packed_bank_words(p.n_bands, p.n_w4)) * 4 : 0;
     int nwarps = 8;
-    while (nwarps > 1 && size_t(nwarps) * xs + ep_bytes > 200 * 1024) nwarps >>= 1;
-    const size_t smem = size_t(nwarps) * xs + ep_bytes;
+    while (nwarps > 1 && size_t(nwarps) * (xs + ps) + fixed > 200 * 1024) nwarps >>= 1;
+    const size_t smem = size_t(nwarps) * (xs + ps) + fixed;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     p.tile_frames = TT;
     dim3 grid((p.T + TT - 1) / TT, p.B);
