@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Time all five BASELINE.json configs through the public API on one GPU (secondary to bench.py,
+which is the contract benchmark for configs[1]).  Prints one JSON line per config with
+audio-seconds/second and the fraction of the SURVEY 8(d) roofline (max of algorithmic bytes at the
+measured HBM peak and algorithmic flops at the FP32 peak).
+
+    python tools/bench_configs.py [--configs c1,c2,c3,c4,c5] [--iters 20] [--clips-scale 1.0]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+import mlx_audio_primitives_b200 as ap
+
+HBM_GBS = 6449.7
+FP32_TFLOPS = 74.4
+try:
+    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+        HBM_GBS = json.load(f).get("hbm_gbs", HBM_GBS)
+except Exception:
+    pass
+
+
+def fft_flops(N):
+    return 2.5 * N * math.log2(N)
+
+
+def clips(B, L, sr, seed=0):
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    t = torch.arange(L, device="cuda", dtype=torch.float64) / sr
+    base = torch.sin(2 * np.pi * (100 + 1000 * t) * t).to(torch.float32)
+    return base[None] + 0.1 * torch.randn((B, L), generator=g, device="cuda")
+
+
+def timed(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def report(name, label, audio_s, ms, bytes_, flops, extra=None):
+    t_roof = max(bytes_ / (HBM_GBS * 1e9), flops / (FP32_TFLOPS * 1e12)) * 1e3
+    line = {"config": name, "workload": label, "ms": ms, "audio_s_per_s": audio_s / (ms * 1e-3),
+            "alg_bytes": bytes_, "alg_flops": flops, "t_roof_ms": t_roof, "frac_of_roofline": t_roof / ms,
+            "bound": "hbm" if bytes_ / (HBM_GBS * 1e9) >= flops / (FP32_TFLOPS * 1e12) else "fp32",
+            "achieved_GBs": bytes_ / (ms * 1e-3) / 1e9, "achieved_TFLOPs": flops / (ms * 1e-3) / 1e12}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = argparse.ArgumentParser()
+    a.add_argument("--configs", default="c1,c2,c3,c4,c5")
+    a.add_argument("--iters", type=int, default=20)
+    a.add_argument("--clips-scale", type=float, default=1.0, help="scale the batch (e.g. 0.125 = one of 8 GPUs' share)")
+    args = a.parse_args()
+    want = args.configs.split(",")
+    sc = args.clips_scale
+
+    if "c1" in want:  # stft + istft round trip, 1 x 10 s @ 22.05 kHz, 2048/512
+        L, N, hop = 220500, 2048, 512
+        y = clips(1, L, 22050)
+        T, F = 1 + L // hop, N // 2 + 1
+        S = ap.stft(y, N, hop)
+        ms_f = timed(lambda: ap.stft(y, N, hop), args.iters * 5)
+        ms_i = timed(lambda: ap.istft(S, hop, length=L), args.iters * 5)
+        r = ap.istft(S, hop, length=L)
+        err = float((r[:, 1:] - y[:, 1:]).abs().max())
+        by = (4 * L + 8 * F * T) * 2
+        fl = T * (2 * fft_flops(N) + N + 4 * N)
+        report("c1", "stft+istft 2048/512 hann 1x10 s @22.05k", 10.0, ms_f + ms_i, by, fl,
+               {"ms_stft": ms_f, "ms_istft": ms_i, "round_trip_max_err": err})
+    if "c2" in want:
+        B, L = max(1, int(64 * sc)), 480000
+        y = clips(B, L, 16000)
+        fn = lambda: ap.power_to_db(ap.melspectrogram(y, sr=16000, n_fft=400, hop_length=160, n_mels=80))
+        ms = timed(fn, args.iters * 5)
+        T, F = 1 + L // 160, 201
+        report("c2", f"log-mel 16k 400/160 80 mels {B}x30 s", B * 30.0, ms, B * (4 * L + 4 * 80 * T),
+               B * T * (fft_flops(400) + 400 + 7 * F + 3 * 80))
+    if "c3" in want:
+        B, L = max(1, int(1024 * sc * 0.125)), 661500  # one GPU's share of the 8-GPU batch by default
+        y = clips(B, L, 22050)
+        fn = lambda: ap.power_to_db(ap.melspectrogram(y, sr=22050, n_fft=2048, hop_length=512, n_mels=128), ref=torch.max)
+        ms = timed(fn, args.iters)
+        T, F = 1 + L // 512, 1025
+        report("c3", f"mel+power_to_db(ref=max) 22.05k 2048/512 128 mels {B}x30 s", B * 30.0, ms,
+               B * (4 * L + 4 * 128 * T), B * T * (fft_flops(2048) + 2048 + 7 * F + 3 * 128))
+    if "c4" in want:
+        B, L = max(1, int(256 * sc * 0.25)), 2646000  # 64 clips by default (0.68 GB input)
+        y = clips(B, L, 44100)
+        fn = lambda: ap.mfcc(y, sr=44100, n_mfcc=40, n_fft=4096, hop_length=1024)
+        ms = timed(fn, args.iters)
+        T, F = 1 + L // 1024, 2049
+        report("c4", f"MFCC-40 44.1k 4096/1024 128 mels {B}x60 s", B * 60.0, ms, B * (4 * L + 4 * 40 * T),
+               B * T * (fft_flops(4096) + 4096 + 7 * F + 3 * 128 + 2 * 128 * 40))
+    if "c5" in want:
+        B, L, N, hop, iters = max(1, int(128 * sc)), 220500, 1024, 256, 32
+        y = clips(B, L, 22050)
+        S = ap.magnitude(ap.stft(y, N, hop))
+        fn = lambda: ap.griffinlim(S, n_iter=iters, hop_length=hop, random_state=0)
+        ms = timed(fn, max(2, args.iters // 5), warm=1)
+        T, F = S.shape[-1], N // 2 + 1
+        per_it = 8 * F * T + 4 * L + 4 * L + 4 * F * T + 8 * F * T + 16 * F * T
+        by = B * (iters * per_it + 8 * F * T + 4 * L)
+        fl = B * T * (iters * (2 * fft_flops(N) + N + 4 * N + 40 * F) + fft_flops(N) + 4 * N)
+        report("c5", f"Griffin-Lim 32 it 1024/256 {B}x10 s @22.05k (incl. host RNG init + upload)", B * 10.0, ms, by, fl)
+
+
+if __name__ == "__main__":
+    main()
