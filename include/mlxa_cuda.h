@@ -126,6 +126,13 @@ int mlxa_griffinlim_project_f32(const float* y, int64_t B, int64_t L, int64_t ld
 /* rebuilt = mag * exp(i*angles) elementwise over n values (griffinlim.py:123) */
 int mlxa_polar_f32(const float* mag, const float* angles, int64_t n, mlxa_c64* out, void* stream);
 
+/* out[i] = float32(low + (high - low) * u_i), u_i the i-th double of NumPy's PCG64 stream whose
+ * 128-bit state / increment are given as two 64-bit halves each -- bit-identical to
+ * np.random.Generator(PCG64).uniform(low, high, n).astype(float32).  Replaces the host-side draw of
+ * the Griffin-Lim phase init (griffinlim.py:112-115) while keeping seeds reproducible. */
+int mlxa_pcg64_uniform_f32(uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo,
+                           double low, double high, int64_t n, float* out, void* stream);
+
 /* |z| and atan2(im, re) over n complex values (stft.py:347-379) */
 int mlxa_magnitude_f32(const mlxa_c64* z, int64_t n, float* out, void* stream);
 int mlxa_phase_f32(const mlxa_c64* z, int64_t n, float* out, void* stream);

@@ -318,6 +318,12 @@ int mlxa_polar_f32(const float* mag, const float* angles, int64_t n, mlxa_c64* o
     CHECK_CUDA(run_polar(mag, angles, n, reinterpret_cast<float2*>(out), (cudaStream_t)stream), "polar");
     return 0;
 }
+int mlxa_pcg64_uniform_f32(uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo, double low,
+                           double high, int64_t n, float* out, void* stream) {
+    CHECK_ARG(out && n > 0, "bad argument");
+    CHECK_CUDA(run_pcg64_uniform(state_hi, state_lo, inc_hi, inc_lo, low, high - low, n, out, (cudaStream_t)stream), "pcg64_uniform");
+    return 0;
+}
 int mlxa_magnitude_f32(const mlxa_c64* z, int64_t n, float* out, void* stream) {
     CHECK_ARG(z && out && n > 0, "bad argument");
     CHECK_CUDA(run_magnitude(reinterpret_cast<const float2*>(z), n, out, (cudaStream_t)stream), "magnitude");

@@ -2,6 +2,7 @@
 // overlap-add entry points, the dB family with its global-max reduction, the MFCC tail,
 // elementwise complex helpers and the O(n^2) DFT used for n_fft values without a compiled plan.
 #include "fwd_epilogue.cuh"
+#include "pcg64.cuh"
 #include "util_kernels.cuh"
 
 namespace mlxa {
@@ -359,6 +360,25 @@ cudaError_t launch_irdft_naive(const float2* spec, long long rows, int F_in, int
                                float* frames, cudaStream_t s) {
     const size_t smem = size_t(n_fft / 2 + 1) * 8;
     irdft_naive_kernel<<<(unsigned)rows, 256, smem, s>>>(spec, rows, F_in, n_fft, tw_full, frames);
+    return cudaGetLastError();
+}
+
+// ---- NumPy-compatible uniform stream (pcg64.cuh): each thread jumps to its chunk ---------------
+constexpr int kPcgChunk = 32;
+__global__ void pcg64_uniform_kernel(unsigned long long s_hi, unsigned long long s_lo, unsigned long long i_hi,
+                                     unsigned long long i_lo, double low, double range, long long n, float* __restrict__ out) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long i0 = c * kPcgChunk;
+    if (i0 >= n) return;
+    const u128 inc = ((u128)i_hi << 64) | i_lo;
+    u128 st = pcg_advance(((u128)s_hi << 64) | s_lo, inc, (unsigned long long)i0);
+    const int m = (int)min((long long)kPcgChunk, n - i0);
+    for (int j = 0; j < m; ++j) out[i0 + j] = pcg_uniform_f32(st, inc, low, range);
+}
+cudaError_t run_pcg64_uniform(unsigned long long s_hi, unsigned long long s_lo, unsigned long long i_hi,
+                              unsigned long long i_lo, double low, double range, long long n, float* out, cudaStream_t s) {
+    const long long chunks = (n + kPcgChunk - 1) / kPcgChunk;
+    pcg64_uniform_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, s>>>(s_hi, s_lo, i_hi, i_lo, low, range, n, out);
     return cudaGetLastError();
 }
 

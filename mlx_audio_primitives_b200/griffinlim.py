@@ -25,6 +25,23 @@ def _to_physical_f32(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _uniform_phase(rng: np.random.Generator, shape, device) -> torch.Tensor:
+    """rng.uniform(-pi, pi, shape).astype(float32) in C order (reference griffinlim.py:112-115), drawn
+    ON THE DEVICE: NumPy's PCG64 stream is reproduced bit for bit by a jump-ahead kernel, so seeds give
+    the reference's phases without a host draw + upload of the whole spectrogram."""
+    n = int(np.prod(shape))
+    st = rng.bit_generator.state
+    if n == 0 or st.get("bit_generator") != "PCG64":
+        return torch.from_numpy(rng.uniform(-np.pi, np.pi, shape).astype(np.float32)).to(device)
+    state, inc = int(st["state"]["state"]), int(st["state"]["inc"])
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    m64 = (1 << 64) - 1
+    check(_ext.mlxa_pcg64_uniform_f32(state >> 64, state & m64, inc >> 64, inc & m64, -np.pi, np.pi, n, ptr(out),
+                                      torch.cuda.current_stream(device).cuda_stream), "pcg64_uniform")
+    rng.bit_generator.advance(n)  # keep a caller-supplied Generator in step with what was consumed
+    return out
+
+
 def griffinlim(S, n_iter: int = 32, hop_length: int | None = None, win_length: int | None = None,
                n_fft: int | None = None, window="hann", center: bool = True, length: int | None = None,
                pad_mode: str = "constant", momentum: float = 0.99, init: str = "random", random_state=None):
@@ -49,8 +66,7 @@ def griffinlim(S, n_iter: int = 32, hop_length: int | None = None, win_length: i
     mode = pad_mode_code(pad_mode)
     rng = np.random.default_rng(random_state)
     if init == "random":
-        angles_host = rng.uniform(-np.pi, np.pi, (B, F, T)).astype(np.float32)
-        angles = torch.from_numpy(angles_host).to(S.device)
+        angles = _uniform_phase(rng, (B, F, T), S.device)
     elif init == "zeros":
         angles = torch.zeros((B, F, T), dtype=torch.float32, device=S.device)
     else:

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <vector>
 #include "fft_plans_list.cuh"
+#include "pcg64.cuh"
 
 using namespace mlxa;
 
@@ -42,6 +43,15 @@ static void run_radix(const float2* in, float2* out) {
 }
 
 extern "C" {
+// the same __host__ __device__ PCG64 code the device kernel runs, including the per-chunk jump-ahead
+void emul_pcg64_uniform(unsigned long long s_hi, unsigned long long s_lo, unsigned long long i_hi, unsigned long long i_lo,
+                        double low, double high, long long n, int chunk, float* out) {
+    const u128 inc = ((u128)i_hi << 64) | i_lo, s0 = ((u128)s_hi << 64) | s_lo;
+    for (long long i0 = 0; i0 < n; i0 += chunk) {
+        u128 st = pcg_advance(s0, inc, (unsigned long long)i0);
+        for (long long j = i0; j < n && j < i0 + chunk; ++j) out[j] = pcg_uniform_f32(st, inc, low, high - low);
+    }
+}
 int emul_plan_length(int n_fft) {
     switch (n_fft) {
 #define X(NF) case NF: return PlanFor<NF>::Plan::N;

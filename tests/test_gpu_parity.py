@@ -369,6 +369,20 @@ def test_griffinlim_matches_reference_code(ap, golden):
     assert np.array_equal(a, b)  # deterministic kernels: same seed -> same bits
 
 
+def test_device_rng_is_numpy_pcg64(ap):
+    """The on-device phase init reproduces np.random.default_rng(seed).uniform(-pi, pi) bit for bit."""
+    from mlx_audio_primitives_b200.griffinlim import _uniform_phase
+    for seed, shape in [(0, (2, 257, 33)), (123, (1, 513, 7)), (7, (3, 5, 1000))]:
+        got = H(_uniform_phase(np.random.default_rng(seed), shape, torch.device("cuda")))
+        want = np.random.default_rng(seed).uniform(-np.pi, np.pi, shape).astype(np.float32)
+        assert np.array_equal(got, want)
+    g = np.random.default_rng(5)
+    a = H(_uniform_phase(g, (1000,), torch.device("cuda")))
+    b = g.uniform(-np.pi, np.pi, 10)  # the caller's generator was advanced past what the device consumed
+    ref = np.random.default_rng(5).uniform(-np.pi, np.pi, 1010)
+    assert np.array_equal(a, ref[:1000].astype(np.float32)) and np.array_equal(b, ref[1000:])
+
+
 def test_griffinlim_quality_and_errors(ap):
     """reference tests/test_griffinlim.py:31,100-121: spectral MSE thresholds per iteration count"""
     t = np.arange(22050) / 22050.0  # chirp + noise, the reference's benchmark signal (benchmarks/utils.py:92-115)

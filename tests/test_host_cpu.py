@@ -133,6 +133,22 @@ def test_plan_fft_emulated(emul, n_fft):
     assert np.abs(out - ref).max() <= 5e-7 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("seed", [0, 1, 42, 2**40 + 7])
+def test_pcg64_stream_matches_numpy(emul, seed):
+    """Device RNG for the Griffin-Lim init (same __host__ __device__ code, run on the host): bit-identical
+    to np.random.default_rng(seed).uniform(-pi, pi, n).astype(float32), with per-chunk jump-ahead."""
+    n = 10007
+    st = np.random.default_rng(seed).bit_generator.state["state"]
+    m64 = (1 << 64) - 1
+    out = np.zeros(n, np.float32)
+    emul.emul_pcg64_uniform.argtypes = [ctypes.c_uint64] * 4 + [ctypes.c_double, ctypes.c_double, ctypes.c_longlong,
+                                                                ctypes.c_int, ctypes.c_void_p]
+    emul.emul_pcg64_uniform.restype = None
+    emul.emul_pcg64_uniform(st["state"] >> 64, st["state"] & m64, st["inc"] >> 64, st["inc"] & m64, -np.pi, np.pi, n, 32, _c(out))
+    want = np.random.default_rng(seed).uniform(-np.pi, np.pi, n).astype(np.float32)
+    assert np.array_equal(out, want)
+
+
 def test_shard_bounds():
     from mlx_audio_primitives_b200.distributed import shard_bounds
     for n, w in [(1024, 8), (64, 8), (10, 4), (3, 8), (1, 2)]:
