@@ -112,16 +112,23 @@ int mlxa_istft_f32(const mlxa_c64* spec, int64_t B, int64_t T, int F_in, const f
                    const float* wss, int n_fft, int hop, int64_t ola_len, int64_t trim,
                    int64_t out_len, float* y, int64_t ldy, void* stream);
 
-/* One Griffin-Lim projection (griffinlim.py:143-178) fused into the STFT epilogue:
- *   X = stft(y); new = mag * X/|X| (mag + 0j where X == 0, i.e. angle 0);
- *   rebuilt = new + momentum*(new - tprev); tprev = new.
- * mag, tprev, rebuilt are (B, T, F); frames t >= T_valid see X = 0 (zero-padded frames,
- * griffinlim.py:159-165).  tprev is updated in place. */
+/* Same kernel with the Griffin-Lim extrapolation (griffinlim.py:176-178) fused into its loader: the
+ * spectrum that is inverted is spec + momentum*(spec - spec_prev).  spec_prev may be NULL when
+ * momentum == 0.  Needs a compiled plan for n_fft (mlxa_has_fast_plan). */
+int mlxa_istft_extrap_f32(const mlxa_c64* spec, const mlxa_c64* spec_prev, float momentum,
+                          int64_t B, int64_t T, int F_in, const float* window, const float* wss,
+                          int n_fft, int hop, int64_t ola_len, int64_t trim, int64_t out_len,
+                          float* y, int64_t ldy, void* stream);
+
+/* One Griffin-Lim projection (griffinlim.py:143-169) fused into the STFT epilogue:
+ *   X = stft(y); projected = mag * X/|X|  (mag + 0j where X == 0, i.e. angle 0).
+ * mag and projected are (B, T, F); frames t >= T_valid see X = 0 (zero-padded frames,
+ * griffinlim.py:159-165).  The momentum step rebuilt = new + m*(new - prev) is NOT materialised:
+ * feed (projected, previous projected, m) to mlxa_istft_extrap_f32. */
 int mlxa_griffinlim_project_f32(const float* y, int64_t B, int64_t L, int64_t ldy,
                                 const float* window, int n_fft, int hop, int center,
                                 int pad_mode, int64_t T, int64_t T_valid, const float* mag,
-                                mlxa_c64* tprev, mlxa_c64* rebuilt, float momentum,
-                                void* stream);
+                                mlxa_c64* projected, void* stream);
 
 /* rebuilt = mag * exp(i*angles) elementwise over n values (griffinlim.py:123) */
 int mlxa_polar_f32(const float* mag, const float* angles, int64_t n, mlxa_c64* out, void* stream);

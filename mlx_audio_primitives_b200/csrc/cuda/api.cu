@@ -255,8 +255,8 @@ int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const fl
 
 int mlxa_griffinlim_project_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window, int n_fft,
                                 int hop, int center, int pad_mode, int64_t T, int64_t T_valid, const float* mag,
-                                mlxa_c64* tprev, mlxa_c64* rebuilt, float momentum, void* stream) {
-    CHECK_ARG(mag && rebuilt && (tprev || momentum <= 0.f), "null pointer");
+                                mlxa_c64* projected, void* stream) {
+    CHECK_ARG(mag && projected, "null pointer");
     CHECK_ARG(T > 0 && T_valid >= 0 && T_valid <= T, "bad frame counts");
     return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
         FwdParams p;
@@ -266,17 +266,34 @@ int mlxa_griffinlim_project_f32(const float* y, int64_t B, int64_t L, int64_t ld
         p.T = (int)T; p.T_valid = (int)T_valid;
         const int64_t off = b0 * T * p.F;
         p.mag = mag + off;
-        p.tprev = tprev ? reinterpret_cast<float2*>(tprev) + off : nullptr;
-        p.rebuilt = reinterpret_cast<float2*>(rebuilt) + off;
-        p.momentum = momentum;
+        p.rebuilt = reinterpret_cast<float2*>(projected) + off;
         CHECK_CUDA(dispatch_fwd(EP_GL, p, (cudaStream_t)stream), "griffinlim_project");
         return 0;
     });
 }
 
+static int istft_impl(const mlxa_c64* spec, const mlxa_c64* spec_prev, float momentum, int64_t B, int64_t T, int F_in,
+                      const float* window, const float* wss, int n_fft, int hop, int64_t ola_len, int64_t trim,
+                      int64_t out_len, float* y, int64_t ldy, void* stream);
+
 int mlxa_istft_f32(const mlxa_c64* spec, int64_t B, int64_t T, int F_in, const float* window, const float* wss,
                    int n_fft, int hop, int64_t ola_len, int64_t trim, int64_t out_len, float* y, int64_t ldy,
                    void* stream) {
+    return istft_impl(spec, nullptr, 0.f, B, T, F_in, window, wss, n_fft, hop, ola_len, trim, out_len, y, ldy, stream);
+}
+
+int mlxa_istft_extrap_f32(const mlxa_c64* spec, const mlxa_c64* spec_prev, float momentum, int64_t B, int64_t T,
+                          int F_in, const float* window, const float* wss, int n_fft, int hop, int64_t ola_len,
+                          int64_t trim, int64_t out_len, float* y, int64_t ldy, void* stream) {
+    CHECK_ARG(spec_prev || momentum == 0.f, "spec_prev required when momentum != 0");
+    return istft_impl(spec, spec_prev, momentum, B, T, F_in, window, wss, n_fft, hop, ola_len, trim, out_len, y, ldy, stream);
+}
+
+}  // extern "C"
+
+static int istft_impl(const mlxa_c64* spec, const mlxa_c64* spec_prev, float momentum, int64_t B, int64_t T, int F_in,
+                      const float* window, const float* wss, int n_fft, int hop, int64_t ola_len, int64_t trim,
+                      int64_t out_len, float* y, int64_t ldy, void* stream) {
     CHECK_ARG(spec && window && wss && y, "null pointer");
     CHECK_ARG(B > 0 && T > 0 && F_in > 0 && n_fft >= 2 && hop >= 1, "bad shape");
     CHECK_ARG(ola_len > 0 && trim >= 0 && out_len > 0 && ldy >= out_len, "bad output geometry");
@@ -289,6 +306,9 @@ int mlxa_istft_f32(const mlxa_c64* spec, int64_t B, int64_t T, int F_in, const f
             InvParams p;
             std::memset(&p, 0, sizeof(p));
             p.spec = reinterpret_cast<const float2*>(spec) + b0 * T * F_in;
+            p.spec_prev = (spec_prev && momentum != 0.f) ? reinterpret_cast<const float2*>(spec_prev) + b0 * T * F_in : nullptr;
+            p.momentum = momentum;
+            p.const_bulk = ((uintptr_t)window & 15) == 0;
             p.B = (int)nb; p.T = (int)T; p.F_in = F_in; p.n_fft = n_fft; p.hop = hop;
             p.window = window; p.wss = wss; p.tw_plan = t.tw_plan; p.tw_unpack = t.tw_unpack;
             p.ola_len = ola_len; p.trim = trim; p.out_len = out_len; p.ldy = ldy;
@@ -304,6 +324,7 @@ int mlxa_istft_f32(const mlxa_c64* spec, int64_t B, int64_t T, int F_in, const f
         });
     }
     // no compiled plan: O(n^2) inverse DFT into stream-ordered scratch, then the gather OLA
+    CHECK_ARG(!(spec_prev && momentum != 0.f), "fused extrapolation needs a compiled plan; combine the spectra first");
     float* frames = nullptr;
     CHECK_CUDA(cudaMallocAsync(&frames, sizeof(float) * (size_t)B * T * n_fft, s), "istft scratch");
     cudaError_t e = launch_irdft_naive(reinterpret_cast<const float2*>(spec), B * T, F_in, n_fft, t.tw_plan, frames, s);
@@ -312,6 +333,8 @@ int mlxa_istft_f32(const mlxa_c64* spec, int64_t B, int64_t T, int F_in, const f
     CHECK_CUDA(e, "istft (dft fallback)");
     return 0;
 }
+
+extern "C" {
 
 int mlxa_polar_f32(const float* mag, const float* angles, int64_t n, mlxa_c64* out, void* stream) {
     CHECK_ARG(mag && angles && out && n > 0, "bad argument");

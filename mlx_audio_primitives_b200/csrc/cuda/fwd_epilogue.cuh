@@ -42,13 +42,7 @@ MLXA_D void epilogue_bin_global(const FwdParams& p, long long o, float2 X) {
         } else {
             nw = make_float2(m, 0.f);  // angle(0) = 0 -> mag * exp(0)
         }
-        if (p.momentum > 0.f) {
-            const float2 tp = p.tprev[o];
-            p.rebuilt[o] = make_float2(fmaf(p.momentum, nw.x - tp.x, nw.x), fmaf(p.momentum, nw.y - tp.y, nw.y));
-            p.tprev[o] = nw;
-        } else {
-            p.rebuilt[o] = nw;
-        }
+        p.rebuilt[o] = nw;  // the momentum extrapolation is fused into the next inverse transform's loader
     }
 }
 

@@ -9,6 +9,10 @@
 // overlap, so the adds run in r barrier-separated phases and the summation order is fixed
 // (deterministic results).  The (B, T, n_fft) frame tensor of the reference
 // (stft.py:295 -> overlap_add.metal:16) never exists.
+//
+// Optionally the spectrum is formed on the fly as spec + momentum*(spec - spec_prev): the
+// Griffin-Lim extrapolation (griffinlim.py:176-178) fused into the loader, so the chain keeps
+// only the projected spectra in HBM.
 #include "fft_plans_list.cuh"
 #include "params.cuh"
 
@@ -22,33 +26,71 @@ namespace {  // per-translation-unit kernels: every n_fft gets its own copy
 using PF = PlanFor<MLXA_NFFT>;
 using P = PF::Plan;
 constexpr int NFFT = MLXA_NFFT;
-constexpr int FPT = (PF::MODE == MODE_PAIR) ? 2 : 1;
+constexpr bool PACK = (PF::MODE == MODE_PACK);
+constexpr int FPT = PACK ? 1 : 2;
 constexpr int THREADS = (P::E > 32) ? 128 : 256;
 constexpr int NG = THREADS / P::G;
+constexpr int NUNPACK = PACK ? P::N + 1 : 0;
+constexpr int TWP = (P::TW + 1) & ~1, TWU = (NUNPACK + 1) & ~1;
+constexpr bool TW_SMEM = (TWP + TWU) * 8 <= 20 * 1024;
 
+constexpr int round_up4(int v) { return (v + 3) & ~3; }
+
+template <bool EXTRAP>
+MLXA_D float2 load_bin(const float2* __restrict__ X, const float2* __restrict__ Xp, int k, bool ok, float m) {
+    float2 a = make_float2(0.f, 0.f);
+    if (ok) {
+        a = __ldg(X + k);
+        if constexpr (EXTRAP) {
+            const float2 c = __ldg(Xp + k);
+            a = make_float2(fmaf(m, a.x - c.x, a.x), fmaf(m, a.y - c.y, a.y));
+        }
+    }
+    return a;
+}
+
+template <bool EXTRAP>
 __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TS = p.tile_hops * p.hop;
     float* s_acc = reinterpret_cast<float*>(smem_raw);
-    float* s_win = s_acc + ((TS + 3) & ~3);
-    float2* s_buf = reinterpret_cast<float2*>(s_win + NFFT);
+    float* s_win = s_acc + round_up4(TS);
+    float2* s_tw = reinterpret_cast<float2*>(s_win + NFFT);
+    float2* s_buf = s_tw + (TW_SMEM ? TWP + TWU : 0);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_buf + NG * P::BUF);
 
     const int b = blockIdx.y;
     const long long o0 = (long long)blockIdx.x * TS;
+    const bool cbulk = p.const_bulk != 0;
+    if (threadIdx.x == 0) mbar_init(s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(s_bar, (TW_SMEM ? (TWP + TWU) * 8 : 0) + (cbulk ? NFFT * 4 : 0));
+        if constexpr (TW_SMEM) {
+            if (TWP) bulk_copy_g2s(s_tw, p.tw_plan, TWP * 8, s_bar);
+            if (TWU) bulk_copy_g2s(s_tw + TWP, p.tw_unpack, TWU * 8, s_bar);
+        }
+        if (cbulk) bulk_copy_g2s(s_win, p.window, NFFT * 4, s_bar);
+    }
     for (int i = threadIdx.x; i < TS; i += THREADS) s_acc[i] = 0.f;
-    for (int i = threadIdx.x; i < NFFT; i += THREADS) s_win[i] = __ldg(p.window + i);
+    if (!cbulk)
+        for (int i = threadIdx.x; i < NFFT; i += THREADS) s_win[i] = __ldg(p.window + i);
+    const float2* tw_plan = TW_SMEM ? s_tw : p.tw_plan;
+    const float2* tw_unpack = TW_SMEM ? s_tw + TWP : p.tw_unpack;
 
     // frames touching [o0, min(o0 + TS, ola_len))
     const long long o_end = min(o0 + (long long)TS, p.ola_len);
     const int r = (NFFT + p.hop - 1) / p.hop;
-    int f_lo = (o0 < NFFT) ? 0 : int((o0 - NFFT) / p.hop) + 1;
-    int f_hi = (o_end > o0) ? int(min((long long)(p.T - 1), (o_end - 1) / p.hop)) : -1;
+    const int f_lo = (o0 < NFFT) ? 0 : int((o0 - NFFT) / p.hop) + 1;
+    const int f_hi = (o_end > o0) ? int(min((long long)(p.T - 1), (o_end - 1) / p.hop)) : -1;
     __syncthreads();
+    mbar_wait(s_bar, 0);
 
     const int gi = threadIdx.x / P::G, g = threadIdx.x % P::G;
     float2* buf = s_buf + gi * P::BUF;
-    const float2* specb = p.spec + (long long)b * p.T * p.F_in;
+    const long long clip = (long long)b * p.T * p.F_in;
     const float inv_n = 1.0f / float(P::N);
+    const bool hop_even = (p.hop & 1) == 0;
 
     for (int base = f_lo; base <= f_hi; base += NG * FPT) {
         const int fa = base + gi * FPT;
@@ -56,76 +98,99 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
         float2 v[P::E];
 
         // ---- spectrum -> packed complex input (swapped: inverse = swap . forward . swap) ---
-        if constexpr (PF::MODE == MODE_PACK) {
+        if constexpr (PACK) {
             constexpr int N = P::N;
-            const float2* X = specb + (long long)(va ? fa : 0) * p.F_in;
-            for (int k = g; k < N; k += P::G) {
-                float2 xk = make_float2(0.f, 0.f), xm = make_float2(0.f, 0.f);
-                if (va && k < p.F_in) xk = __ldg(X + k);
-                if (va && N - k < p.F_in) xm = __ldg(X + N - k);
-                if (k == 0) { xk.y = 0.f; xm.y = 0.f; }  // c2r ignores imag of DC / Nyquist
-                const float2 w = __ldg(p.tw_unpack + k);
-                const float ex = 0.5f * (xk.x + xm.x), ey = 0.5f * (xk.y - xm.y);
-                const float2 d = make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y + xm.y));
-                const float2 o = cmul_conj(d, w);
-                buf[k] = make_float2(ey + o.x, ex - o.y);  // swap(E + i*O)
-            }
+            constexpr int NQ = ceil_div(N, P::G);
+            const long long fo = clip + (long long)(va ? fa : 0) * p.F_in;
+            const float2* X = p.spec + fo;
+            const float2* Xp = EXTRAP ? p.spec_prev + fo : nullptr;
+            static_for<NQ>([&](auto q) {
+                constexpr int Q = decltype(q)::value;
+                const int k = g + Q * P::G;
+                if ((N % P::G == 0) || Q + 1 < NQ || k < N) {
+                    float2 xk = load_bin<EXTRAP>(X, Xp, k, va && k < p.F_in, p.momentum);
+                    float2 xm = load_bin<EXTRAP>(X, Xp, N - k, va && N - k < p.F_in, p.momentum);
+                    if (Q == 0 && k == 0) { xk.y = 0.f; xm.y = 0.f; }  // c2r ignores imag of DC / Nyquist
+                    const float2 w = tw_unpack[k];
+                    const float ex = 0.5f * (xk.x + xm.x), ey = 0.5f * (xk.y - xm.y);
+                    const float2 d = make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y + xm.y));
+                    const float2 o = cmul_conj(d, w);
+                    buf[k] = make_float2(ey + o.x, ex - o.y);  // swap(E + i*O)
+                }
+            });
         } else {
             constexpr int N = P::N;
+            constexpr int NQ = ceil_div(N / 2 + 1, P::G);
             const bool vb = fa + 1 <= f_hi;
-            const float2* Xa = specb + (long long)(va ? fa : 0) * p.F_in;
-            const float2* Xb = specb + (long long)(vb ? fa + 1 : 0) * p.F_in;
-            for (int k = g; k <= N / 2; k += P::G) {
-                float2 a = make_float2(0.f, 0.f), c = make_float2(0.f, 0.f);
-                if (va && k < p.F_in) a = __ldg(Xa + k);
-                if (vb && k < p.F_in) c = __ldg(Xb + k);
-                if (k == 0 || 2 * k == N) { a.y = 0.f; c.y = 0.f; }
-                buf[k] = make_float2(a.y + c.x, a.x - c.y);  // swap(Xa + i*Xb)
-                if (k > 0 && 2 * k < N) buf[N - k] = make_float2(c.x - a.y, a.x + c.y);  // swap(conj Xa + i*conj Xb)
-            }
+            const long long foa = clip + (long long)(va ? fa : 0) * p.F_in, fob = clip + (long long)(vb ? fa + 1 : 0) * p.F_in;
+            const float2 *Xa = p.spec + foa, *Xb = p.spec + fob;
+            const float2 *Xpa = EXTRAP ? p.spec_prev + foa : nullptr, *Xpb = EXTRAP ? p.spec_prev + fob : nullptr;
+            static_for<NQ>([&](auto q) {
+                constexpr int Q = decltype(q)::value;
+                const int k = g + Q * P::G;
+                if (Q + 1 < NQ || k <= N / 2) {
+                    float2 a = load_bin<EXTRAP>(Xa, Xpa, k, va && k < p.F_in, p.momentum);
+                    float2 c = load_bin<EXTRAP>(Xb, Xpb, k, vb && k < p.F_in, p.momentum);
+                    if ((Q == 0 && k == 0) || 2 * k == N) { a.y = 0.f; c.y = 0.f; }
+                    buf[k] = make_float2(a.y + c.x, a.x - c.y);  // swap(Xa + i*Xb)
+                    if (!(Q == 0 && k == 0) && 2 * k < N) buf[N - k] = make_float2(c.x - a.y, a.x + c.y);  // swap(conj Xa + i*conj Xb)
+                }
+            });
         }
         __syncwarp();
         pass_load_fn<P, 0>(g, v, [&](int n) { return buf[n]; });
         __syncwarp();
-        pass_compute<P, 0>(g, v, p.tw_plan);
+        pass_compute<P, 0>(g, v, tw_plan);
         pass_store_buf<P, 0>(g, v, buf);
         __syncwarp();
         pass_load_buf<P, 1>(g, v, buf);
         __syncwarp();
-        pass_compute<P, 1>(g, v, p.tw_plan);
+        pass_compute<P, 1>(g, v, tw_plan);
         if constexpr (P::NPASS == 3) {
             pass_store_buf<P, 1>(g, v, buf);
             __syncwarp();
             pass_load_buf<P, 2>(g, v, buf);
             __syncwarp();
-            pass_compute<P, 2>(g, v, p.tw_plan);
+            pass_compute<P, 2>(g, v, tw_plan);
         }
 
         // ---- windowed overlap-add into the tile accumulator, r conflict-free phases -------
+        // lane-private part of each frame: last pass leaves element n = b + k*NS in v[], i.e. samples 2n, 2n+1
         for (int ph = 0; ph < r; ++ph) {
-            if constexpr (PF::MODE == MODE_PACK) {
+            if constexpr (PACK) {
                 if (va && ((fa - f_lo) % r) == ph) {
-                    const long long off = (long long)fa * p.hop - o0;
-                    pass_store_fn<P, P::NPASS - 1>(g, v, [&](int n, float2 val) {
-                        const long long q = off + 2 * n;
-                        if (q >= 0 && q < TS) s_acc[q] = fmaf(s_win[2 * n], val.y * inv_n, s_acc[q]);
-                        if (q + 1 >= 0 && q + 1 < TS) s_acc[q + 1] = fmaf(s_win[2 * n + 1], val.x * inv_n, s_acc[q + 1]);
-                    });
+                    const int off = int((long long)fa * p.hop - o0);  // tile-local start of the frame
+                    if (off >= 0 && off + NFFT <= TS && hop_even) {  // frame fully inside the tile
+                        float2* acc2 = reinterpret_cast<float2*>(s_acc + off);
+                        const float2* w2 = reinterpret_cast<const float2*>(s_win);
+                        pass_store_fn<P, P::NPASS - 1>(g, v, [&](int n, float2 val) {
+                            float2 a = acc2[n];
+                            const float2 w = w2[n];
+                            a.x = fmaf(w.x, val.y * inv_n, a.x);
+                            a.y = fmaf(w.y, val.x * inv_n, a.y);
+                            acc2[n] = a;
+                        });
+                    } else {
+                        pass_store_fn<P, P::NPASS - 1>(g, v, [&](int n, float2 val) {
+                            const int q = off + 2 * n;
+                            if (q >= 0 && q < TS) s_acc[q] = fmaf(s_win[2 * n], val.y * inv_n, s_acc[q]);
+                            if (q + 1 >= 0 && q + 1 < TS) s_acc[q + 1] = fmaf(s_win[2 * n + 1], val.x * inv_n, s_acc[q + 1]);
+                        });
+                    }
                 }
             } else {
-                if (va && ((fa - f_lo) % r) == ph) {
-                    const long long off = (long long)fa * p.hop - o0;
-                    pass_store_fn<P, P::NPASS - 1>(g, v, [&](int n, float2 val) {
-                        const long long q = off + n;
-                        if (q >= 0 && q < TS) s_acc[q] = fmaf(s_win[n], val.y * inv_n, s_acc[q]);
-                    });
-                }
-                if ((fa + 1 <= f_hi) && ((fa + 1 - f_lo) % r) == ph) {
-                    const long long off = (long long)(fa + 1) * p.hop - o0;
-                    pass_store_fn<P, P::NPASS - 1>(g, v, [&](int n, float2 val) {
-                        const long long q = off + n;
-                        if (q >= 0 && q < TS) s_acc[q] = fmaf(s_win[n], val.x * inv_n, s_acc[q]);
-                    });
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {
+                    const int f = fa + which;
+                    if (f <= f_hi && ((f - f_lo) % r) == ph) {
+                        const int off = int((long long)f * p.hop - o0);
+                        const bool inside = off >= 0 && off + NFFT <= TS;
+                        pass_store_fn<P, P::NPASS - 1>(g, v, [&](int n, float2 val) {
+                            const int q = off + n;
+                            if (inside || (q >= 0 && q < TS))
+                                s_acc[q] = fmaf(s_win[n], (which ? val.x : val.y) * inv_n, s_acc[q]);
+                        });
+                    }
                 }
             }
             __syncthreads();
@@ -133,20 +198,33 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
     }
     __syncthreads();
 
-    // ---- normalise, trim, store ---------------------------------------------------------
+    // ---- normalise, trim, store: the window-sum envelope of the tile is bulk-copied into the
+    // (now idle) exchange buffers when it is 16-byte aligned ----------------------------------
+    float* s_wss = reinterpret_cast<float*>(s_buf);
+    const long long n_w = max(0LL, min((long long)TS, p.ola_len - o0));
+    const bool wbulk = ((reinterpret_cast<uintptr_t>(p.wss + o0) & 15) == 0) && (n_w % 4 == 0) && n_w > 0 &&
+                       (size_t)n_w * 4 <= size_t(NG) * P::BUF * 8;
+    if (wbulk) {
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(s_bar, (uint32_t)n_w * 4);
+            bulk_copy_g2s(s_wss, p.wss + o0, (uint32_t)n_w * 4, s_bar);
+        }
+        mbar_wait(s_bar, 1);
+    }
     float* yb = p.y + (long long)b * p.ldy;
     for (int i = threadIdx.x; i < TS; i += THREADS) {
         const long long o = o0 + i;
         const long long j = o - p.trim;
         if (j < 0 || j >= p.out_len) continue;
         float val = 0.f;
-        if (o < p.ola_len) val = s_acc[i] / fmaxf(__ldg(p.wss + o), 1e-8f);
+        if (o < p.ola_len) val = s_acc[i] / fmaxf(wbulk ? s_wss[i] : __ldg(p.wss + o), 1e-8f);
         yb[j] = val;
     }
 }
 
 static size_t inv_smem_bytes(int hop, int TH) {
-    return size_t((TH * hop + 3) & ~3) * 4 + size_t(NFFT) * 4 + size_t(NG) * P::BUF * 8;
+    return size_t(round_up4(TH * hop)) * 4 + size_t(NFFT) * 4 + size_t(TW_SMEM ? TWP + TWU : 0) * 8 +
+           size_t(NG) * P::BUF * 8 + 16;
 }
 
 }  // namespace
@@ -168,9 +246,16 @@ cudaError_t MLXA_CAT(launch_inv_, MLXA_NFFT)(InvParams& p, cudaStream_t s) {
     const size_t smem = inv_smem_bytes(p.hop, TH);
     const long long TS = (long long)TH * p.hop;
     dim3 grid((unsigned)((span + TS - 1) / TS), p.B);
-    cudaError_t e = cudaFuncSetAttribute(inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    inv_kernel<<<grid, THREADS, smem, s>>>(p);
+    cudaError_t e;
+    if (p.spec_prev != nullptr && p.momentum != 0.f) {
+        e = cudaFuncSetAttribute(inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        inv_kernel<true><<<grid, THREADS, smem, s>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(inv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        inv_kernel<false><<<grid, THREADS, smem, s>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -37,9 +37,7 @@ struct FwdParams {
     float db_coef, db_amin, db_ref;
     // EP_GL
     const float* mag;  // (B, T, F)
-    float2* tprev;     // (B, T, F), in/out
-    float2* rebuilt;   // (B, T, F), out
-    float momentum;
+    float2* rebuilt;   // (B, T, F), out: mag * X/|X|
 };
 
 // 32-bit words of a packed band-sparse filterbank (layout: fwd_epilogue.cuh / mlxa_cuda.h)
@@ -48,7 +46,10 @@ __host__ __device__ inline long long packed_bank_words(int n_bands, long long n_
 }
 
 struct InvParams {
-    const float2* spec;  // (B, T, F_in)
+    const float2* spec;       // (B, T, F_in)
+    const float2* spec_prev;  // optional (B, T, F_in): the transform input is spec + momentum*(spec - spec_prev)
+    float momentum;
+    int const_bulk;           // window pointer is 16-byte aligned -> bulk async copy
     int B, T, F_in;
     int n_fft, hop;
     int tile_hops;       // output tile = tile_hops * hop samples

@@ -74,20 +74,28 @@ def griffinlim(S, n_iter: int = 32, hop_length: int | None = None, win_length: i
     win = padded_window(window, win_length, n_fft)
     mag = _to_physical_f32(S)                 # (B, T, F)
     ang = _to_physical_f32(angles)
-    rebuilt = torch.empty((B, T, F, 2), dtype=torch.float32, device=S.device)
-    check(_ext.mlxa_polar_f32(ptr(mag), ptr(ang), mag.numel(), ptr(rebuilt), stream_ptr(S)), "polar")
+    # Only the PROJECTED spectra live in HBM (two ping-pong buffers); the momentum extrapolation
+    # rebuilt = new + m*(new - prev) is formed inside the inverse transform's loader.
+    cur = torch.empty((B, T, F, 2), dtype=torch.float32, device=S.device)
+    check(_ext.mlxa_polar_f32(ptr(mag), ptr(ang), mag.numel(), ptr(cur), stream_ptr(S)), "polar")
     del ang, angles
-    tprev = rebuilt.clone() if momentum > 0 else None
-    rebuilt_c = torch.view_as_complex(rebuilt)
+    prev = cur  # tprev = rebuilt at the start (reference griffinlim.py:126)
     y = None
     for _ in range(n_iter):
-        y = _istft_physical(rebuilt_c, n_fft, hop_length, win, center, length, out=y)
+        y = _istft_physical(torch.view_as_complex(cur), n_fft, hop_length, win, center, length, out=y,
+                            prev=torch.view_as_complex(prev) if prev is not cur else None, momentum=momentum)
         L = y.shape[1]
         T_new = frames_or_raise(L, n_fft, hop_length, center, pad_mode)
+        if momentum > 0:  # the older projection is dead once the inverse transform has consumed it
+            dst = prev if prev is not cur else torch.empty_like(cur)
+        else:
+            dst = cur
         check(_ext.mlxa_griffinlim_project_f32(ptr(y), B, L, y.stride(0), ptr(win), n_fft, hop_length, int(center),
-                                               mode, T, min(T, T_new), ptr(mag), ptr(tprev), ptr(rebuilt),
-                                               float(momentum), stream_ptr(S)), "griffinlim")
-    y = _istft_physical(rebuilt_c, n_fft, hop_length, win, center, length, out=y)
+                                               mode, T, min(T, T_new), ptr(mag), ptr(dst), stream_ptr(S)),
+              "griffinlim")
+        prev, cur = (cur, dst) if momentum > 0 else (cur, cur)
+    y = _istft_physical(torch.view_as_complex(cur), n_fft, hop_length, win, center, length, out=y,
+                        prev=torch.view_as_complex(prev) if prev is not cur else None, momentum=momentum)
     return y if batched else y[0]
 
 
