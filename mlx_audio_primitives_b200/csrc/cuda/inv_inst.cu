@@ -99,23 +99,35 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
 
         // ---- spectrum -> packed complex input (swapped: inverse = swap . forward . swap) ---
         if constexpr (PACK) {
+            // 1) every bin X[0..N] is read from HBM exactly once (coalesced) and parked in buf[k];
+            // 2) the lane that owns the pair (k, N-k) turns it into Z[k], Z[N-k] in place:
+            //    Z[k] = E + iO, Z[N-k] = conj(E) + i*conj(O), E = (X[k] + conj X[N-k])/2,
+            //    O = conj(w^k) (X[k] - conj X[N-k])/2.
             constexpr int N = P::N;
-            constexpr int NQ = ceil_div(N, P::G);
+            constexpr int NQ1 = ceil_div(N + 1, P::G), NQ2 = ceil_div(N / 2 + 1, P::G);
+            static_assert(P::BUF >= N + 1, "exchange buffer must hold the Nyquist bin");
             const long long fo = clip + (long long)(va ? fa : 0) * p.F_in;
             const float2* X = p.spec + fo;
             const float2* Xp = EXTRAP ? p.spec_prev + fo : nullptr;
-            static_for<NQ>([&](auto q) {
+            const int kmax = va ? min(p.F_in, N + 1) : 0;
+            static_for<NQ1>([&](auto q) {
                 constexpr int Q = decltype(q)::value;
                 const int k = g + Q * P::G;
-                if ((N % P::G == 0) || Q + 1 < NQ || k < N) {
-                    float2 xk = load_bin<EXTRAP>(X, Xp, k, va && k < p.F_in, p.momentum);
-                    float2 xm = load_bin<EXTRAP>(X, Xp, N - k, va && N - k < p.F_in, p.momentum);
+                if (Q + 1 < NQ1 || k <= N) buf[k] = load_bin<EXTRAP>(X, Xp, k, k < kmax, p.momentum);
+            });
+            __syncwarp();
+            static_for<NQ2>([&](auto q) {
+                constexpr int Q = decltype(q)::value;
+                const int k = g + Q * P::G;
+                if (Q + 1 < NQ2 || k <= N / 2) {
+                    float2 xk = buf[k], xm = buf[N - k];
                     if (Q == 0 && k == 0) { xk.y = 0.f; xm.y = 0.f; }  // c2r ignores imag of DC / Nyquist
                     const float2 w = tw_unpack[k];
                     const float ex = 0.5f * (xk.x + xm.x), ey = 0.5f * (xk.y - xm.y);
                     const float2 d = make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y + xm.y));
                     const float2 o = cmul_conj(d, w);
-                    buf[k] = make_float2(ey + o.x, ex - o.y);  // swap(E + i*O)
+                    buf[k] = make_float2(ey + o.x, ex - o.y);                                   // swap(E + iO)
+                    if (!(Q == 0 && k == 0)) buf[N - k] = make_float2(o.x - ey, ex + o.y);      // swap(conj E + i conj O)
                 }
             });
         } else {
