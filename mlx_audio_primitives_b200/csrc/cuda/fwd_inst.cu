@@ -24,7 +24,9 @@ using P = PF::Plan;
 constexpr int NFFT = MLXA_NFFT;
 constexpr bool PACK = (PF::MODE == MODE_PACK);
 constexpr int FPT = PACK ? 1 : 2;                              // frames per transform
-constexpr int THREADS = (P::E > 32) ? 128 : 256;              // register-heavy plans run fewer warps
+// warps per CTA: sized so that the exchange buffers of all resident transforms fill the SM's shared memory
+// (n_fft 2048: 16 warps x 8.4 KB; n_fft 4096: 8 warps x 16.6 KB with 64 complex values per lane)
+constexpr int THREADS = (P::E > 32) ? 256 : ((P::G == 32) ? 512 : 256);
 constexpr int NG = THREADS / P::G;                            // transforms in flight per CTA
 static_assert((NG * P::BUF) % 2 == 0 && NFFT % 4 == 0, "smem carve-up assumes 16-byte multiples");
 constexpr int NBINS = NFFT / 2 + 1;

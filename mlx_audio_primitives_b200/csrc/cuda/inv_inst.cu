@@ -28,7 +28,9 @@ using P = PF::Plan;
 constexpr int NFFT = MLXA_NFFT;
 constexpr bool PACK = (PF::MODE == MODE_PACK);
 constexpr int FPT = PACK ? 1 : 2;
-constexpr int THREADS = (P::E > 32) ? 128 : 256;
+// warps per CTA: sized so that the exchange buffers of all resident transforms fill the SM's shared memory
+// (n_fft 2048: 16 warps x 8.4 KB; n_fft 4096: 8 warps x 16.6 KB with 64 complex values per lane)
+constexpr int THREADS = (P::E > 32) ? 256 : ((P::G == 32) ? 512 : 256);
 constexpr int NG = THREADS / P::G;
 constexpr int NUNPACK = PACK ? P::N + 1 : 0;
 constexpr int TWP = (P::TW + 1) & ~1, TWU = (NUNPACK + 1) & ~1;
