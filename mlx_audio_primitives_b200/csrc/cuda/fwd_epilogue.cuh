@@ -103,34 +103,37 @@ MLXA_D void mel_project_group(const MelSmem ms, int n_bands, int g, const float*
 }
 
 // Tile store: s_out [n_bands][TT+1] -> mel (B, n_bands, T), lanes along the frames (coalesced),
-// with the optional fused dB and the running max for power_to_db(ref=max / top_db).
+// with the optional fused dB.  TT is a power of two.  Returns the thread's running max of the raw
+// values it stored (for power_to_db(ref=max / top_db)); the caller reduces it once per CTA.
 template <int THREADS>
-MLXA_D void mel_store_tile(const FwdParams& p, int b, int t0, int nt, const float* s_out, int TT, float* s_red) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int subs = 32 / TT;  // TT is a power of two <= 32
-    const int t = lane % TT, sub = lane / TT;
+MLXA_D float mel_store_tile(const FwdParams& p, int b, int t0, int nt, const float* s_out, int TT, int log2TT, float vmax) {
     const int ostride = TT + 1;
-    float vmax = 0.f;
     const float db_ref = fmaxf(p.db_ref, p.db_amin);
-    float* outb = p.mel + (long long)b * p.n_bands * p.T + t0 + t;
-    if (t < nt) {
-        for (int m = warp * subs + sub; m < p.n_bands; m += (THREADS / 32) * subs) {
+    float* outb = p.mel + (long long)b * p.n_bands * p.T + t0;
+    const int n = p.n_bands << log2TT;
+    for (int idx = threadIdx.x; idx < n; idx += THREADS) {
+        const int m = idx >> log2TT, t = idx & (TT - 1);
+        if (t < nt) {
             float v = s_out[m * ostride + t];
             vmax = fmaxf(vmax, v);
             if (p.db_mode) v = p.db_coef * log10f(fmaxf(v, p.db_amin) / db_ref);
-            outb[(long long)m * p.T] = v;
+            outb[(long long)m * p.T + t] = v;
         }
     }
-    if (p.gmax != nullptr) {
+    return vmax;
+}
+
+// one atomicMax per CTA (mel >= 0, so the int ordering of the bit patterns is the float ordering)
+template <int THREADS>
+MLXA_D void block_max_to_global(float vmax, float* gmax, float* s_red) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        if (lane == 0) s_red[warp] = vmax;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float mx = 0.f;
-            for (int i = 0; i < THREADS / 32; ++i) mx = fmaxf(mx, s_red[i]);
-            atomicMax(reinterpret_cast<int*>(p.gmax), __float_as_int(mx));  // mel >= 0
-        }
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = vmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mx = 0.f;
+        for (int i = 0; i < THREADS / 32; ++i) mx = fmaxf(mx, s_red[i]);
+        atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(mx));
     }
 }
 

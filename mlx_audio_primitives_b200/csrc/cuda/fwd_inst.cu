@@ -1,14 +1,16 @@
 // Fused pad -> frame -> window -> real FFT (+ epilogue) kernel for one compiled n_fft
 // (built once per size with -DMLXA_NFFT=<n_fft>).
 //
-// One CTA = one clip x one tile of consecutive frames.  The hop-overlapped span of samples the
-// tile needs, (tile-1)*hop + n_fft, is staged ONCE in shared memory -- by a single 1-D bulk
-// async copy (TMA, cp.async.bulk + mbarrier) for interior tiles, by index arithmetic (the
-// padding rules) for the first/last tiles of a clip -- so HBM sees each input sample ~once
-// instead of n_fft/hop times plus three inflated round trips (reference stft.py:118-130).
-// Groups of G lanes then run the Stockham plan per frame (or per frame pair), exchange through a
-// padded smem buffer with __syncwarp only, unpack the real spectrum and hand every bin to the
-// epilogue in registers.  Window, twiddles and the band-sparse filterbank are smem-resident.
+// PERSISTENT: the grid is one CTA per resident slot (SM count x occupancy); each CTA loops over
+// (clip, frame-tile) work items.  Window, twiddles and the packed filterbank are bulk-copied into
+// shared memory once per CTA.  A tile's hop-overlapped span of samples, (tile-1)*hop + n_fft, is
+// staged by ONE 1-D bulk async copy (TMA: cp.async.bulk + mbarrier) -- with two staging buffers
+// the copy of the next tile is in flight while the current tile is transformed; the first/last
+// tiles of a clip (where the padding rules apply) are staged by index arithmetic instead.  HBM
+// therefore sees each input sample ~once instead of n_fft/hop times plus three inflated round
+// trips (reference stft.py:118-130).  Groups of G lanes run the Stockham plan per frame (or per
+// frame pair), exchange through a padded smem buffer with __syncwarp only, unpack the real
+// spectrum and hand every bin to the epilogue in registers.
 #include "fft_plans_list.cuh"
 #include "fwd_epilogue.cuh"
 
@@ -25,14 +27,14 @@ constexpr int NFFT = MLXA_NFFT;
 constexpr bool PACK = (PF::MODE == MODE_PACK);
 constexpr int FPT = PACK ? 1 : 2;                              // frames per transform
 // warps per CTA: sized so that the exchange buffers of all resident transforms fill the SM's shared memory
-// (n_fft 2048: 16 warps x 8.4 KB; n_fft 4096: 8 warps x 16.6 KB with 64 complex values per lane)
-constexpr int THREADS = (P::E > 32) ? 256 : ((P::G == 32) ? 512 : 256);
+// (n_fft 2048: 16 warps x 8.4 KB; n_fft 4096: 8 warps x 16.6 KB with 64 complex values per lane;
+//  n_fft 400: one 16-warp CTA per SM with double-buffered staging)
+constexpr int THREADS = (P::E > 32) ? 256 : (P::N >= 400 ? 512 : 256);
 constexpr int NG = THREADS / P::G;                            // transforms in flight per CTA
 static_assert((NG * P::BUF) % 2 == 0 && NFFT % 4 == 0, "smem carve-up assumes 16-byte multiples");
 constexpr int NBINS = NFFT / 2 + 1;
-constexpr int NUNPACK = PACK ? P::N + 1 : 0;                   // exp(-i*pi*k/N) entries
+constexpr int NUNPACK = PACK ? P::N + 1 : 0;                   // 0.5*exp(-i*pi*k/N) entries
 constexpr bool TW_SMEM = (P::TW + NUNPACK) * 8 <= 20 * 1024;   // twiddles staged in smem when small
-
 constexpr int TWP = (P::TW + 1) & ~1, TWU = (NUNPACK + 1) & ~1;  // table sizes as uploaded (even counts)
 
 constexpr int round_up4(int v) { return (v + 3) & ~3; }
@@ -41,64 +43,84 @@ struct SmemLayout {
     int in_floats, tw_f2, ep_floats, mel_floats;
     size_t bytes;
 };
-__host__ __device__ inline SmemLayout smem_layout(int ep, int hop, int TT, int n_bands, long long n_w4) {
+__host__ __device__ inline SmemLayout smem_layout(int ep, int hop, int TT, int n_in_buf, int n_bands, long long n_w4) {
     SmemLayout s;
     s.in_floats = round_up4((TT - 1) * hop + NFFT + 8);  // +8: room for a 16-byte alignment lead + tail
     s.tw_f2 = TW_SMEM ? (TWP + TWU) : 0;  // both tables padded to even counts (16-byte multiples)
     s.ep_floats = (ep == EP_MEL) ? round_up4(n_bands * (TT + 1)) : 0;  // mel staging tile [n_bands][TT+1]
     s.mel_floats = (ep == EP_MEL) ? (int)packed_bank_words(n_bands, n_w4) : 0;
-    s.bytes = size_t(s.in_floats + NFFT + s.ep_floats + s.mel_floats) * 4 + size_t(s.tw_f2 + NG * P::BUF) * 8 + 16;
+    s.bytes = size_t(n_in_buf * s.in_floats + NFFT + s.ep_floats + s.mel_floats) * 4 +
+              size_t(s.tw_f2 + NG * P::BUF) * 8 + 32;
     return s;
+}
+
+// geometry of one work item
+struct Tile {
+    int b, t0, nt, tile_len, src0, lead, n_bulk;
+    bool bulk;
+    const float* yb;
+};
+MLXA_D Tile tile_info(const FwdParams& p, int TT, int tiles_per_clip, long long id) {
+    Tile t;
+    t.b = int(id / tiles_per_clip);
+    t.t0 = int(id - (long long)t.b * tiles_per_clip) * TT;
+    t.nt = min(TT, p.T - t.t0);
+    t.tile_len = (t.nt - 1) * p.hop + NFFT;
+    t.yb = p.y + (long long)t.b * p.ldy;
+    t.src0 = t.t0 * p.hop - p.pad;
+    // interior tile: every sample exists -> one bulk async copy from the 16-byte aligned address at
+    // or below the first sample ("lead" extra floats in front)
+    t.lead = int((reinterpret_cast<uintptr_t>(t.yb + t.src0) & 15) >> 2);
+    t.n_bulk = round_up4(t.lead + t.tile_len);
+    t.bulk = (t.src0 - t.lead >= 0) && (t.src0 - t.lead + t.n_bulk <= p.L) && ((reinterpret_cast<uintptr_t>(t.yb) & 3) == 0);
+    return t;
 }
 
 template <int EP, int PW>
 __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TT = p.tile_frames;
-    const int b = blockIdx.y;
-    const int t0 = blockIdx.x * TT;
-    const int nt = min(TT, p.T - t0);
-    const int tile_len = (nt - 1) * p.hop + NFFT;
-    const SmemLayout lay = smem_layout(EP, p.hop, TT, p.n_bands, p.n_w4);
+    const int nbuf = p.n_in_buf;
+    const SmemLayout lay = smem_layout(EP, p.hop, TT, nbuf, p.n_bands, p.n_w4);
 
-    float* s_in = reinterpret_cast<float*>(smem_raw);
-    float* s_win = s_in + lay.in_floats;
+    float* s_in0 = reinterpret_cast<float*>(smem_raw);
+    float* s_win = s_in0 + nbuf * lay.in_floats;
     float2* s_tw = reinterpret_cast<float2*>(s_win + NFFT);
     float2* s_buf = s_tw + lay.tw_f2;
     float* s_ep = reinterpret_cast<float*>(s_buf + NG * P::BUF);
     float* s_mel = s_ep + lay.ep_floats;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mel + lay.mel_floats);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mel + lay.mel_floats);  // [0],[1]: tile buffers, [2]: constants
     __shared__ float s_red[THREADS / 32];
 
-    // ---- stage the tile's samples and the constants ------------------------------------------
-    const float* yb = p.y + (long long)b * p.ldy;
-    const int src0 = t0 * p.hop - p.pad;
-    // interior tile: every sample exists -> one bulk async copy from the 16-byte aligned address
-    // at or below the first sample ("lead" extra floats in front)
-    const int lead = int((reinterpret_cast<uintptr_t>(yb + src0) & 15) >> 2);
-    const int n_bulk = round_up4(lead + tile_len);
-    const bool bulk = (src0 - lead >= 0) && (src0 - lead + n_bulk <= p.L) && ((reinterpret_cast<uintptr_t>(yb) & 3) == 0);
-    const int in_off = bulk ? lead : 0;
+    const int tiles_per_clip = (p.T + TT - 1) / TT;
+    const long long total = (long long)p.B * tiles_per_clip;
+    long long id = blockIdx.x;
+    if (id >= total) return;
+
+    // ---- once per CTA: barriers, constants, first tile -----------------------------------------
     const bool cbulk = p.const_bulk != 0;
     const uint32_t mel_bytes = (EP == EP_MEL) ? uint32_t(lay.mel_floats) * 4u : 0u;
-    if (threadIdx.x == 0) mbar_init(s_bar, 1);
+    if (threadIdx.x == 0) {
+        mbar_init(s_bar + 0, 1);
+        mbar_init(s_bar + 1, 1);
+        mbar_init(s_bar + 2, 1);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t tx = (bulk ? n_bulk * 4 : 0) + (TW_SMEM ? (TWP + TWU) * 8 : 0) + (cbulk ? NFFT * 4 + mel_bytes : 0);
-        mbar_arrive_expect_tx(s_bar, tx);
-        if (bulk) bulk_copy_g2s(s_in, yb + src0 - lead, n_bulk * 4, s_bar);
+        mbar_arrive_expect_tx(s_bar + 2, (TW_SMEM ? (TWP + TWU) * 8 : 0) + (cbulk ? NFFT * 4 + mel_bytes : 0));
         if constexpr (TW_SMEM) {
-            if (TWP) bulk_copy_g2s(s_tw, p.tw_plan, TWP * 8, s_bar);
-            if (TWU) bulk_copy_g2s(s_tw + TWP, p.tw_unpack, TWU * 8, s_bar);
+            if (TWP) bulk_copy_g2s(s_tw, p.tw_plan, TWP * 8, s_bar + 2);
+            if (TWU) bulk_copy_g2s(s_tw + TWP, p.tw_unpack, TWU * 8, s_bar + 2);
         }
         if (cbulk) {
-            bulk_copy_g2s(s_win, p.window, NFFT * 4, s_bar);
-            if (EP == EP_MEL) bulk_copy_g2s(s_mel, p.bank, mel_bytes, s_bar);
+            bulk_copy_g2s(s_win, p.window, NFFT * 4, s_bar + 2);
+            if (EP == EP_MEL) bulk_copy_g2s(s_mel, p.bank, mel_bytes, s_bar + 2);
         }
-    }
-    if (!bulk) {
-        for (int i = threadIdx.x; i < tile_len; i += THREADS)
-            s_in[i] = load_padded(yb, p.L, src0 + i, p.pad_mode);
+        const Tile t = tile_info(p, TT, tiles_per_clip, id);
+        if (t.bulk) {
+            mbar_arrive_expect_tx(s_bar + 0, t.n_bulk * 4);
+            bulk_copy_g2s(s_in0, t.yb + t.src0 - t.lead, t.n_bulk * 4, s_bar + 0);
+        }
     }
     if (!cbulk) {
         for (int i = threadIdx.x; i < NFFT; i += THREADS) s_win[i] = __ldg(p.window + i);
@@ -108,142 +130,199 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
     const float2* tw_plan = TW_SMEM ? s_tw : p.tw_plan;
     const float2* tw_unpack = TW_SMEM ? s_tw + TWP : p.tw_unpack;
     MelSmem ms{};
-    const int ep_stride = TT + 1;
-    if constexpr (EP == EP_MEL) {
-        ms = mel_smem_carve(s_mel, p.n_bands, p.n_w4);
-    }
+    if constexpr (EP == EP_MEL) ms = mel_smem_carve(s_mel, p.n_bands, p.n_w4);
     __syncthreads();
-    mbar_wait(s_bar, 0);
+    mbar_wait(s_bar + 2, 0);
 
     const int gi = threadIdx.x / P::G, g = threadIdx.x % P::G;
     float2* buf = s_buf + gi * P::BUF;
-    const bool even_off = (((p.hop | in_off) & 1) == 0);
-    const float* tile = s_in + in_off;
+    const int ep_stride = TT + 1;
+    uint32_t ph0 = 0u, ph1 = 0u;  // parity of the next completion on each staging barrier
+    float vmax = 0.f;
 
-    for (int base = 0; base < nt; base += NG * FPT) {
-        const int f0 = base + gi * FPT;
-        const bool va = (f0 < nt) && (t0 + f0 < p.T_valid);
-        float2 v[P::E];
+    for (int it = 0; id < total; ++it, id += gridDim.x) {
+        const int c = (nbuf == 2) ? (it & 1) : 0;
+        float* s_in = s_in0 + c * lay.in_floats;
+        const Tile ti = tile_info(p, TT, tiles_per_clip, id);
 
-        // ---- pass 0: windowed samples straight from the staged tile --------------------
-        if constexpr (PACK) {
-            const float* src = tile + (va ? f0 * p.hop : 0);
-            if (even_off) {
-                pass_load_fn<P, 0>(g, v, [&](int n) {
-                    const float2 x = *reinterpret_cast<const float2*>(src + 2 * n);
-                    const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
-                    return va ? make_float2(x.x * w.x, x.y * w.y) : make_float2(0.f, 0.f);
-                });
-            } else {
-                pass_load_fn<P, 0>(g, v, [&](int n) {
-                    const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
-                    return va ? make_float2(src[2 * n] * w.x, src[2 * n + 1] * w.y) : make_float2(0.f, 0.f);
-                });
+        // ---- stage: prefetch the next tile (two buffers) / fetch this one (one buffer) -------
+        if (threadIdx.x == 0) {
+            if (nbuf == 2) {
+                const long long nid = id + gridDim.x;
+                if (nid < total) {
+                    const Tile tn = tile_info(p, TT, tiles_per_clip, nid);
+                    if (tn.bulk) {
+                        mbar_arrive_expect_tx(s_bar + (c ^ 1), tn.n_bulk * 4);
+                        bulk_copy_g2s(s_in0 + (c ^ 1) * lay.in_floats, tn.yb + tn.src0 - tn.lead, tn.n_bulk * 4, s_bar + (c ^ 1));
+                    }
+                }
+            } else if (it > 0 && ti.bulk) {
+                mbar_arrive_expect_tx(s_bar + 0, ti.n_bulk * 4);
+                bulk_copy_g2s(s_in0, ti.yb + ti.src0 - ti.lead, ti.n_bulk * 4, s_bar + 0);
             }
+        }
+        if (ti.bulk) {
+            mbar_wait(s_bar + c, c ? ph1 : ph0);
+            if (c) ph1 ^= 1u; else ph0 ^= 1u;
         } else {
-            const bool vb = (f0 + 1 < nt) && (t0 + f0 + 1 < p.T_valid);
-            const float* sa = tile + (va ? f0 * p.hop : 0);
-            const float* sb = tile + (vb ? (f0 + 1) * p.hop : 0);
-            pass_load_fn<P, 0>(g, v, [&](int n) {
-                const float w = s_win[n];
-                return make_float2(va ? sa[n] * w : 0.f, vb ? sb[n] * w : 0.f);
-            });
+            for (int i = threadIdx.x; i < ti.tile_len; i += THREADS)
+                s_in[i] = load_padded(ti.yb, p.L, ti.src0 + i, p.pad_mode);
+            __syncthreads();
         }
-        pass_compute<P, 0>(g, v, tw_plan);
-        pass_store_buf<P, 0>(g, v, buf);
-        __syncwarp();
-        pass_load_buf<P, 1>(g, v, buf);
-        __syncwarp();
-        pass_compute<P, 1>(g, v, tw_plan);
-        if constexpr (P::NPASS == 3) {
-            pass_store_buf<P, 1>(g, v, buf);
-            __syncwarp();
-            pass_load_buf<P, 2>(g, v, buf);
-            __syncwarp();
-            pass_compute<P, 2>(g, v, tw_plan);
-        }
-        pass_store_natural<P, P::NPASS - 1>(g, v, buf);  // Z[k] at buf[k]
-        __syncwarp();
+        const int in_off = ti.bulk ? ti.lead : 0;
+        const bool even_off = (((p.hop | in_off) & 1) == 0);
+        const float* tile = s_in + in_off;
+        const int b = ti.b, t0 = ti.t0, nt = ti.nt;
 
-        // ---- unpack the real spectrum, feed the epilogue --------------------------------
-        constexpr int NQ = ceil_div(NBINS, P::G);
-        if constexpr (EP == EP_MEL) {
-            // |X|^p of every bin into registers, then parked in the group's own exchange buffer
-            // (Z is dead by then) where the band-sparse projection reads it.
-            float pw[NQ * FPT];
-            static_for<NQ>([&](auto q) {
-                constexpr int Q = decltype(q)::value;
-                const int k = g + Q * P::G;
-                if (Q + 1 < NQ || k < NBINS) {
-                    if constexpr (PACK) {
-                        constexpr int N = P::N;
-                        const float2 zk = buf[(Q + 1 == NQ && k == N) ? 0 : k];
-                        const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
-                        const float2 w = tw_unpack[k];
-                        const float ex = 0.5f * (zk.x + zm.x), ey = 0.5f * (zk.y - zm.y);
-                        const float ox = 0.5f * (zk.y + zm.y), oy = -0.5f * (zk.x - zm.x);
-                        const float2 X = make_float2(ex + fmaf(ox, w.x, -(oy * w.y)), ey + fmaf(ox, w.y, oy * w.x));
-                        pw[Q] = spectral_power<PW>(X, p.power);
-                    } else {
-                        constexpr int N = P::N;
-                        const float2 zk = buf[k];
-                        const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
-                        pw[2 * Q] = spectral_power<PW>(make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y)), p.power);
-                        pw[2 * Q + 1] = spectral_power<PW>(make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x)), p.power);
-                    }
-                }
-            });
-            __syncwarp();
-            float* pbuf = reinterpret_cast<float*>(buf);
-            static_for<NQ>([&](auto q) {
-                constexpr int Q = decltype(q)::value;
-                const int k = g + Q * P::G;
-                if (Q + 1 < NQ || k < NBINS) {
-                    if constexpr (PACK) pbuf[k] = pw[Q];
-                    else reinterpret_cast<float2*>(pbuf)[k] = make_float2(pw[2 * Q], pw[2 * Q + 1]);
-                }
-            });
-            __syncwarp();
-            if (f0 < nt) mel_project_group<P::G, FPT>(ms, p.n_bands, g, pbuf, s_ep, ep_stride, f0);
-        } else if (f0 < nt) {
-            const long long obase = ((long long)b * p.T + t0 + f0) * p.F;
+        for (int base = 0; base < nt; base += NG * FPT) {
+            const int f0 = base + gi * FPT;
+            const bool va = f0 < nt;  // frames beyond the tile: finite dummy input, results unused
+            float2 v[P::E];
+
+            // ---- pass 0: windowed samples straight from the staged tile --------------------
             if constexpr (PACK) {
-                constexpr int N = P::N;  // n_fft / 2
-                static_for<NQ>([&](auto q) {
-                    constexpr int Q = decltype(q)::value;
-                    const int k = g + Q * P::G;
-                    if (Q + 1 < NQ || k <= N) {
-                        const float2 zk = buf[(Q + 1 == NQ && k == N) ? 0 : k];
-                        const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
-                        const float2 w = tw_unpack[k];
-                        const float ex = 0.5f * (zk.x + zm.x), ey = 0.5f * (zk.y - zm.y);
-                        const float ox = 0.5f * (zk.y + zm.y), oy = -0.5f * (zk.x - zm.x);
-                        const float2 X = make_float2(ex + fmaf(ox, w.x, -(oy * w.y)), ey + fmaf(ox, w.y, oy * w.x));
-                        epilogue_bin_global<EP>(p, obase + k, X);
-                    }
-                });
+                const float* src = tile + (va ? f0 * p.hop : 0);
+                const bool zero = (EP == EP_GL) && (t0 + f0 >= p.T_valid);  // Griffin-Lim frame padding
+                if (even_off) {
+                    pass_load_fn<P, 0>(g, v, [&](int n) {
+                        const float2 x = *reinterpret_cast<const float2*>(src + 2 * n);
+                        const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
+                        if constexpr (EP == EP_GL) return zero ? make_float2(0.f, 0.f) : make_float2(x.x * w.x, x.y * w.y);
+                        else return make_float2(x.x * w.x, x.y * w.y);
+                    });
+                } else {
+                    pass_load_fn<P, 0>(g, v, [&](int n) {
+                        const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
+                        if constexpr (EP == EP_GL) return zero ? make_float2(0.f, 0.f) : make_float2(src[2 * n] * w.x, src[2 * n + 1] * w.y);
+                        else return make_float2(src[2 * n] * w.x, src[2 * n + 1] * w.y);
+                    });
+                }
             } else {
-                constexpr int N = P::N;  // n_fft
-                const bool fb = f0 + 1 < nt;
-                static_for<NQ>([&](auto q) {
-                    constexpr int Q = decltype(q)::value;
-                    const int k = g + Q * P::G;
-                    if (Q + 1 < NQ || k <= N / 2) {
-                        const float2 zk = buf[k];
-                        const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
-                        epilogue_bin_global<EP>(p, obase + k, make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y)));
-                        if (fb) epilogue_bin_global<EP>(p, obase + p.F + k, make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x)));
-                    }
+                // an absent second frame rides as a copy of the first: finite, and never stored
+                const bool vb = f0 + 1 < nt;
+                const float* sa = tile + (va ? f0 * p.hop : 0);
+                const float* sb = tile + (vb ? (f0 + 1) * p.hop : (va ? f0 * p.hop : 0));
+                const bool za = (EP == EP_GL) && (t0 + f0 >= p.T_valid), zb = (EP == EP_GL) && (t0 + f0 + 1 >= p.T_valid);
+                pass_load_fn<P, 0>(g, v, [&](int n) {
+                    const float w = s_win[n];
+                    if constexpr (EP == EP_GL) return make_float2(za ? 0.f : sa[n] * w, zb ? 0.f : sb[n] * w);
+                    else return make_float2(sa[n] * w, sb[n] * w);
                 });
             }
-        }
-        __syncwarp();
-    }
+            pass_compute<P, 0>(g, v, tw_plan);
+            pass_store_buf<P, 0>(g, v, buf);
+            __syncwarp();
+            pass_load_buf<P, 1>(g, v, buf);
+            __syncwarp();
+            pass_compute<P, 1>(g, v, tw_plan);
+            if constexpr (P::NPASS == 3) {
+                pass_store_buf<P, 1>(g, v, buf);
+                __syncwarp();
+                pass_load_buf<P, 2>(g, v, buf);
+                __syncwarp();
+                pass_compute<P, 2>(g, v, tw_plan);
+            }
+            pass_store_natural<P, P::NPASS - 1>(g, v, buf);  // Z[k] at buf[k]
+            __syncwarp();
 
-    if constexpr (EP == EP_MEL) {
-        __syncthreads();
-        mel_store_tile<THREADS>(p, b, t0, nt, s_ep, TT, s_red);
+            // ---- unpack the real spectrum, feed the epilogue --------------------------------
+            // packed: X[k] = 0.5*(E + w^k O), E = Z[k] + conj Z[N-k], O = -i (Z[k] - conj Z[N-k]);
+            //         the table holds 0.5*w^k.   pair: Xa = (Z[k] + conj Z[N-k])/2, Xb = -i (Z[k] - conj Z[N-k])/2.
+            constexpr int NQ = ceil_div(NBINS, P::G);
+            auto bin = [&](auto q, int k) {
+                constexpr int Q = decltype(q)::value;
+                if constexpr (PACK) {
+                    constexpr int N = P::N;
+                    const float2 zk = buf[(Q + 1 == NQ && k == N) ? 0 : k];
+                    const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
+                    const float2 w = tw_unpack[k];
+                    const float ex = zk.x + zm.x, ey = zk.y - zm.y, ox = zk.y + zm.y, oy = zm.x - zk.x;
+                    return make_float2(fmaf(0.5f, ex, fmaf(ox, w.x, -(oy * w.y))), fmaf(0.5f, ey, fmaf(ox, w.y, oy * w.x)));
+                } else {
+                    return make_float2(0.f, 0.f);
+                }
+            };
+            if constexpr (EP == EP_MEL) {
+                // |X|^p of every bin into registers, then parked in the group's own exchange buffer
+                // (Z is dead by then) where the band-sparse projection reads it.
+                float pw[NQ * FPT];
+                static_for<NQ>([&](auto q) {
+                    constexpr int Q = decltype(q)::value;
+                    const int k = g + Q * P::G;
+                    if (Q + 1 < NQ || k < NBINS) {
+                        if constexpr (PACK) {
+                            pw[Q] = spectral_power<PW>(bin(q, k), p.power);
+                        } else {
+                            constexpr int N = P::N;
+                            const float2 zk = buf[k];
+                            const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
+                            pw[2 * Q] = spectral_power<PW>(make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y)), p.power);
+                            pw[2 * Q + 1] = spectral_power<PW>(make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x)), p.power);
+                        }
+                    }
+                });
+                __syncwarp();
+                float* pbuf = reinterpret_cast<float*>(buf);
+                static_for<NQ>([&](auto q) {
+                    constexpr int Q = decltype(q)::value;
+                    const int k = g + Q * P::G;
+                    if (Q + 1 < NQ || k < NBINS) {
+                        if constexpr (PACK) pbuf[k] = pw[Q];
+                        else reinterpret_cast<float2*>(pbuf)[k] = make_float2(pw[2 * Q], pw[2 * Q + 1]);
+                    }
+                });
+                __syncwarp();
+                if (va) mel_project_group<P::G, FPT>(ms, p.n_bands, g, pbuf, s_ep, ep_stride, f0);
+            } else if (va) {
+                const long long obase = ((long long)b * p.T + t0 + f0) * p.F;
+                if constexpr (PACK) {
+                    static_for<NQ>([&](auto q) {
+                        constexpr int Q = decltype(q)::value;
+                        const int k = g + Q * P::G;
+                        if (Q + 1 < NQ || k < NBINS) epilogue_bin_global<EP>(p, obase + k, bin(q, k));
+                    });
+                } else {
+                    constexpr int N = P::N;  // n_fft
+                    const bool fb = f0 + 1 < nt;
+                    static_for<NQ>([&](auto q) {
+                        constexpr int Q = decltype(q)::value;
+                        const int k = g + Q * P::G;
+                        if (Q + 1 < NQ || k < NBINS) {
+                            const float2 zk = buf[k];
+                            const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
+                            epilogue_bin_global<EP>(p, obase + k, make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y)));
+                            if (fb) epilogue_bin_global<EP>(p, obase + p.F + k, make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x)));
+                        }
+                    });
+                }
+            }
+            __syncwarp();
+        }
+
+        if constexpr (EP == EP_MEL) {
+            __syncthreads();
+            vmax = mel_store_tile<THREADS>(p, b, t0, nt, s_ep, TT, p.log2_tile, vmax);
+        }
+        __syncthreads();  // tile done: its staging buffer and the mel tile may be overwritten
     }
+    if constexpr (EP == EP_MEL) {
+        if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red);
+    }
+}
+
+template <int EP, int PW>
+cudaError_t launch_one(FwdParams& p, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(fwd_kernel<EP, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, n_sm = 0, per_sm = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fwd_kernel<EP, PW>, THREADS, smem)) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    const long long total = (long long)p.B * ((p.T + p.tile_frames - 1) / p.tile_frames);
+    const long long slots = (long long)n_sm * per_sm;
+    fwd_kernel<EP, PW><<<(unsigned)(total < slots ? total : slots), THREADS, smem, s>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -253,36 +332,31 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
 
 cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t s) {
     constexpr size_t kMaxSmem = 227 * 1024;
-    auto bytes = [&](int TT) { return smem_layout(ep, p.hop, TT, p.n_bands, p.n_w4).bytes; };
-    int TT;
-    if (ep == EP_MEL) {
-        TT = 32;  // lanes run along the tile's frames in the projection phase
-        while (TT > 2 && bytes(TT) > kMaxSmem) TT >>= 1;
-        // prefer two CTAs per SM when that is possible with a tile of >= 16 frames
-        if (TT == 32 && bytes(32) > kMaxSmem / 2 && bytes(16) <= kMaxSmem / 2) TT = 16;
-    } else {
-        TT = 2 * NG * FPT;  // two rounds of transforms per staged tile
-        while (TT > 2 && bytes(TT) > kMaxSmem / 2) TT >>= 1;
-    }
-    if (bytes(TT) > kMaxSmem) return cudaErrorInvalidConfiguration;
+    auto bytes = [&](int TT, int nb) { return smem_layout(ep, p.hop, TT, nb, p.n_bands, p.n_w4).bytes; };
+    // one round of transforms per tile for the mel epilogue (its staging tile is [n_bands][TT+1]),
+    // two rounds for the store-through epilogues
+    int TT = NG * FPT * (ep == EP_MEL ? 1 : 2);
+    while (TT > NG * FPT && bytes(TT, 1) > kMaxSmem) TT >>= 1;
+    if (bytes(TT, 1) > kMaxSmem) return cudaErrorInvalidConfiguration;
+    // double-buffer the staging when it does not cost a resident CTA
+    const int ctas1 = (int)(kMaxSmem / bytes(TT, 1));
+    const int want = ctas1 > 2 ? 2 : ctas1;
+    const int nbuf = (bytes(TT, 2) <= kMaxSmem && (int)(kMaxSmem / bytes(TT, 2)) >= want) ? 2 : 1;
     p.tile_frames = TT;
-    const size_t smem = bytes(TT);
-    dim3 grid((p.T + TT - 1) / TT, p.B);
-    cudaError_t e;
-#define MLXA_LAUNCH(EPV, PWV)                                                                          \
-    e = cudaFuncSetAttribute(fwd_kernel<EPV, PWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                    \
-    fwd_kernel<EPV, PWV><<<grid, THREADS, smem, s>>>(p);
-    if (ep == EP_STFT) { MLXA_LAUNCH(EP_STFT, POW_SQUARE) }
-    else if (ep == EP_GL) { MLXA_LAUNCH(EP_GL, POW_SQUARE) }
-    else if (p.power_mode == POW_SQUARE) { MLXA_LAUNCH(EP_MEL, POW_SQUARE) }
-    else if (p.power_mode == POW_ABS) { MLXA_LAUNCH(EP_MEL, POW_ABS) }
-    else { MLXA_LAUNCH(EP_MEL, POW_GENERAL) }
-#undef MLXA_LAUNCH
-    return cudaGetLastError();
+    p.n_in_buf = nbuf;
+    int lg = 0;
+    while ((1 << lg) < TT) ++lg;
+    p.log2_tile = lg;
+    if (ep == EP_MEL && (1 << lg) != TT) return cudaErrorInvalidConfiguration;
+    const size_t smem = bytes(TT, nbuf);
+    if (ep == EP_STFT) return launch_one<EP_STFT, POW_SQUARE>(p, smem, s);
+    if (ep == EP_GL) return launch_one<EP_GL, POW_SQUARE>(p, smem, s);
+    if (p.power_mode == POW_SQUARE) return launch_one<EP_MEL, POW_SQUARE>(p, smem, s);
+    if (p.power_mode == POW_ABS) return launch_one<EP_MEL, POW_ABS>(p, smem, s);
+    return launch_one<EP_MEL, POW_GENERAL>(p, smem, s);
 }
 
-// host tables: plan twiddles and the real-unpack twiddle exp(-i*pi*k/N)
+// host tables: plan twiddles and the real-unpack twiddle 0.5*exp(-i*pi*k/N)
 void MLXA_CAT(plan_tables_, MLXA_NFFT)(float2* tw_plan_host, int* n_plan, float2* tw_unpack_host, int* n_unpack) {
     *n_plan = TWP;       // even counts: the tables are bulk-copied in 16-byte units
     *n_unpack = TWU;
@@ -294,7 +368,7 @@ void MLXA_CAT(plan_tables_, MLXA_NFFT)(float2* tw_plan_host, int* n_plan, float2
     if (tw_unpack_host && PACK)
         for (int k = 0; k <= P::N; ++k) {
             const double a = -kPi * double(k) / double(P::N);
-            tw_unpack_host[k] = make_float2(float(__builtin_cos(a)), float(__builtin_sin(a)));
+            tw_unpack_host[k] = make_float2(float(0.5 * __builtin_cos(a)), float(0.5 * __builtin_sin(a)));
         }
 }
 

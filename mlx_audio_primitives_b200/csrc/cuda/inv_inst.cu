@@ -124,9 +124,9 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
                 if (Q + 1 < NQ2 || k <= N / 2) {
                     float2 xk = buf[k], xm = buf[N - k];
                     if (Q == 0 && k == 0) { xk.y = 0.f; xm.y = 0.f; }  // c2r ignores imag of DC / Nyquist
-                    const float2 w = tw_unpack[k];
+                    const float2 w = tw_unpack[k];  // 0.5 * exp(-i*pi*k/N): the 1/2 of O is in the table
                     const float ex = 0.5f * (xk.x + xm.x), ey = 0.5f * (xk.y - xm.y);
-                    const float2 d = make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y + xm.y));
+                    const float2 d = make_float2(xk.x - xm.x, xk.y + xm.y);
                     const float2 o = cmul_conj(d, w);
                     buf[k] = make_float2(ey + o.x, ex - o.y);                                   // swap(E + iO)
                     if (!(Q == 0 && k == 0)) buf[N - k] = make_float2(o.x - ey, ex + o.y);      // swap(conj E + i conj O)

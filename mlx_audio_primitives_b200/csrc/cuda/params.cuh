@@ -18,7 +18,9 @@ struct FwdParams {
     int T_valid;  // frames >= T_valid see all-zero input (Griffin-Lim frame padding)
     int F;        // n_fft/2 + 1
     int n_fft, hop, pad, pad_mode;
-    int tile_frames;  // frames per CTA
+    int tile_frames;  // frames per tile (a power of two for the mel epilogue)
+    int log2_tile;    // log2(tile_frames) when it is a power of two
+    int n_in_buf;     // 1 or 2 staging buffers for the tile samples (2 = next tile prefetched by TMA)
     const float* window;      // n_fft
     const float2* tw_plan;    // inter-pass twiddles of the plan (or the full table for the naive DFT)
     const float2* tw_unpack;  // exp(-i*pi*k/N), k in [0, N]  (packed real transform)

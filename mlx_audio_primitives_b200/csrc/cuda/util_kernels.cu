@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p, int n
     }
     if constexpr (EP == EP_MEL) {
         __syncthreads();
-        mel_store_tile<256>(p, b, t0, nt, s_out, TT, s_red);
+        const float vmax = mel_store_tile<256>(p, b, t0, nt, s_out, TT, 3, 0.f);  // TT = 8
+        if (p.gmax != nullptr) block_max_to_global<256>(vmax, p.gmax, s_red);
     }
 }
 
