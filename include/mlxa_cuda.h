@@ -75,30 +75,36 @@ int mlxa_window_sumsquare_f32(const float* window, int n_fft, int hop, int64_t T
 int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window,
                   int n_fft, int hop, int center, int pad_mode, mlxa_c64* spec, void* stream);
 
-/* Packed band-sparse filterbank ("bank"): a 16-byte aligned array of 32-bit words
- *     float   w[4*n_w4]        row m's weights start at w[4*off4[m]] (16-byte aligned, zero-padded)
- *     int32   start[n_bands]   first frequency bin of row m's contiguous support
- *     int32   len[n_bands]     support length in bins
- *     int32   off4[n_bands]
- * padded to mlxa_packed_bank_words(n_bands, n_w4) words (a multiple of 4).  Every kernel that
- * projects a spectrum bulk-copies this blob into shared memory.  mlxa_pack_filterbank builds it on
- * the HOST from a dense (n_bands, F) row-major matrix (rows must have contiguous support, which
- * triangular mel / linear / Bark banks have); returns n_w4 through *n_w4_out.  Call it with
+/* Lanes per transform of the kernels that serve n_fft (32 for sizes without a compiled plan). */
+int mlxa_plan_group(int n_fft);
+
+/* Packed band-sparse filterbank ("bank") for a lane group of `group` = mlxa_plan_group(n_fft):
+ * a 16-byte aligned array of 32-bit words
+ *     float   wt[n_wt]          bands are taken `group` at a time; inside group j the weights are
+ *                               transposed: wt[goff[j] + i*group + g] = weight of band j*group + g
+ *                               at bin start[band] + i, zero-padded to glen[j] rows
+ *     int32   start[n_bands]    first frequency bin of each row's contiguous support
+ *     int32   len[n_bands]      support length in bins
+ *     int32   goff[n_groups], glen[n_groups]      n_groups = ceil(n_bands / group)
+ * padded to mlxa_packed_bank_words(n_bands, n_wt, group) words (a multiple of 4).  The kernels
+ * bulk-copy this blob into shared memory once per CTA.  mlxa_pack_filterbank builds it on the
+ * HOST from a dense (n_bands, F) row-major matrix (rows must have contiguous support, which
+ * triangular mel / linear / Bark banks have); returns n_wt through *n_wt_out.  Call it with
  * packed_host == NULL to size the buffer. */
-int64_t mlxa_packed_bank_words(int n_bands, int64_t n_w4);
-int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, float* packed_host,
-                         int64_t capacity_words, int64_t* n_w4_out);
+int64_t mlxa_packed_bank_words(int n_bands, int64_t n_wt, int group);
+int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, int group, float* packed_host,
+                         int64_t capacity_words, int64_t* n_wt_out);
 
 /* STFT with the |X|^power + band-sparse filterbank epilogue (replaces mel.py:309-352 =
  * stft -> abs -> power -> dense matmul); the spectrum never reaches HBM.
- * bank: packed filterbank on the DEVICE (see above).
+ * bank: packed filterbank on the DEVICE, packed for mlxa_plan_group(n_fft); n_wt as returned by the packer.
  * mel (B, n_bands, T).  gmax (optional, may be NULL): device float, atomically raised to
  * max(mel) -- the producer side of power_to_db(ref=max / top_db) (convert.py:42-58).
  * db_mode != 0 writes db_coef*log10(max(v, db_amin)/max(db_ref, db_amin)) instead of v
  * (the no-global-max form of convert.py:48-52). */
 int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window,
                      int n_fft, int hop, int center, int pad_mode, float power,
-                     const float* bank, int n_bands, int64_t n_w4,
+                     const float* bank, int n_bands, int64_t n_wt,
                      float* mel, float* gmax, int db_mode, float db_coef, float db_amin,
                      float db_ref, void* stream);
 
@@ -182,7 +188,7 @@ int mlxa_mfcc_tail_f32(const float* mel, int64_t B, int n_mels, int64_t T, const
  * Synchronous: returns when out_host is complete. */
 int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float* window_host,
                          int n_fft, int hop, int center, int pad_mode, float power,
-                         const float* bank_host, int n_bands, int64_t n_w4,
+                         const float* bank_host, int n_bands, int64_t n_wt,
                          int apply_db, int ref_is_max, float ref, float amin,
                          int use_top_db, float top_db, float* out_host);
 

@@ -25,7 +25,8 @@ SIGNATURES = {
     "mlxa_overlap_add_f32": [_p, _p, _i64, _i64, _i32, _i32, _i64, _p, _p],
     "mlxa_window_sumsquare_f32": [_p, _i32, _i32, _i64, _i64, _p, _p],
     "mlxa_stft_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _p, _p],
-    "mlxa_pack_filterbank": [_p, _i32, _i32, _p, _i64, _p],
+    "mlxa_plan_group": [_i32],
+    "mlxa_pack_filterbank": [_p, _i32, _i32, _i32, _p, _i64, _p],
     "mlxa_melspec_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i64,
                          _p, _p, _i32, _f32, _f32, _f32, _p],
     "mlxa_istft_f32": [_p, _i64, _i64, _i32, _p, _p, _i32, _i32, _i64, _i64, _i64, _p, _i64, _p],
@@ -66,7 +67,7 @@ def _load() -> C.CDLL:
         fn.restype = C.c_int
     lib.mlxa_last_error.argtypes = []
     lib.mlxa_last_error.restype = C.c_char_p
-    lib.mlxa_packed_bank_words.argtypes = [_i32, _i64]
+    lib.mlxa_packed_bank_words.argtypes = [_i32, _i64, _i32]
     lib.mlxa_packed_bank_words.restype = _i64
     if lib.mlxa_abi_version() != ABI_VERSION:
         raise ImportError(f"ABI mismatch: library {lib.mlxa_abi_version()} != host layer {ABI_VERSION}; rebuild")

@@ -202,33 +202,46 @@ int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float
     });
 }
 
-int64_t mlxa_packed_bank_words(int n_bands, int64_t n_w4) { return packed_bank_words(n_bands, n_w4); }
+int mlxa_plan_group(int n_fft) {
+    switch (n_fft) {
+#define X(NF) case NF: return plan_group_##NF();
+        X(64) X(128) X(256) X(400) X(512) X(1024) X(2048) X(4096)
+#undef X
+    }
+    return 32;  // O(n^2) DFT kernels: one warp per frame
+}
 
-int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, float* packed_host, int64_t capacity_words,
-                         int64_t* n_w4_out) {
-    CHECK_ARG(dense_host && n_w4_out && n_bands > 0 && F > 0, "bad argument");
-    std::vector<int> start(n_bands, 0), len(n_bands, 0), off4(n_bands, 0);
-    int64_t total = 0;
+int64_t mlxa_packed_bank_words(int n_bands, int64_t n_wt, int group) { return packed_bank_words(n_bands, n_wt, group); }
+
+int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, int group, float* packed_host,
+                         int64_t capacity_words, int64_t* n_wt_out) {
+    CHECK_ARG(dense_host && n_wt_out && n_bands > 0 && F > 0, "bad argument");
+    CHECK_ARG(group == 4 || group == 8 || group == 16 || group == 32, "group must be 4, 8, 16 or 32");
+    const int n_groups = (n_bands + group - 1) / group;
+    std::vector<int> start(n_bands, 0), len(n_bands, 0), goff(n_groups, 0), glen(n_groups, 0);
     for (int m = 0; m < n_bands; ++m) {
         const float* row = dense_host + (int64_t)m * F;
         int lo = -1, hi = -1;
         for (int k = 0; k < F; ++k)
             if (row[k] != 0.f) { if (lo < 0) lo = k; hi = k; }
-        off4[m] = (int)total;
         if (lo >= 0) { start[m] = lo; len[m] = hi - lo + 1; }
-        total += (len[m] + 3) / 4;
+        glen[m / group] = std::max(glen[m / group], len[m]);
     }
-    *n_w4_out = total;
+    int64_t total = 0;
+    for (int j = 0; j < n_groups; ++j) { goff[j] = (int)total; total += (int64_t)glen[j] * group; }
+    *n_wt_out = total;
     if (!packed_host) return 0;
-    CHECK_ARG(capacity_words >= packed_bank_words(n_bands, total), "packed buffer too small");
-    const int64_t words = packed_bank_words(n_bands, total);
+    const int64_t words = packed_bank_words(n_bands, total, group);
+    CHECK_ARG(capacity_words >= words, "packed buffer too small");
     std::memset(packed_host, 0, sizeof(float) * words);
     for (int m = 0; m < n_bands; ++m) {
         const float* row = dense_host + (int64_t)m * F;
-        for (int j = 0; j < len[m]; ++j) packed_host[4 * (int64_t)off4[m] + j] = row[start[m] + j];
+        float* wt = packed_host + goff[m / group] + (m % group);
+        for (int i = 0; i < len[m]; ++i) wt[(int64_t)i * group] = row[start[m] + i];
     }
-    int32_t* ip = reinterpret_cast<int32_t*>(packed_host + 4 * total);
-    for (int m = 0; m < n_bands; ++m) { ip[m] = start[m]; ip[n_bands + m] = len[m]; ip[2 * n_bands + m] = off4[m]; }
+    int32_t* ip = reinterpret_cast<int32_t*>(packed_host + total);
+    for (int m = 0; m < n_bands; ++m) { ip[m] = start[m]; ip[n_bands + m] = len[m]; }
+    for (int j = 0; j < n_groups; ++j) { ip[2 * n_bands + j] = goff[j]; ip[2 * n_bands + n_groups + j] = glen[j]; }
     return 0;
 }
 
@@ -236,7 +249,7 @@ int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const fl
                      int center, int pad_mode, float power, const float* bank, int n_bands, int64_t n_w4, float* mel,
                      float* gmax, int db_mode, float db_coef, float db_amin, float db_ref, void* stream) {
     CHECK_ARG(bank && mel, "null pointer");
-    CHECK_ARG(n_bands > 0 && n_w4 > 0 && n_w4 < (1LL << 22), "bad filterbank size");
+    CHECK_ARG(n_bands > 0 && n_w4 > 0 && n_w4 < (1LL << 22), "bad filterbank size");  // n_w4 = n_wt words
     return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
         FwdParams p;
         int rc = fill_fwd_common(p, y + b0 * ldy, nb, L, ldy, window, n_fft, hop, center, pad_mode);
@@ -445,7 +458,7 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
                          float* out_host) {
     CHECK_ARG(y_host && window_host && out_host && bank_host, "null pointer");
     CHECK_ARG(B > 0 && L > 0 && n_bands > 0 && n_w4 > 0, "bad shape");
-    const int64_t bank_words = packed_bank_words(n_bands, n_w4);
+    const int64_t bank_words = packed_bank_words(n_bands, n_w4, mlxa_plan_group(n_fft));
     int pad = 0;
     int64_t T = 0;
     CHECK_ARG(n_fft >= 2 && hop >= 1 && hop <= n_fft, "bad n_fft / hop");

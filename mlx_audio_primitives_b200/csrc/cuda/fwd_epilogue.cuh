@@ -46,23 +46,28 @@ MLXA_D void epilogue_bin_global(const FwdParams& p, long long o, float2 X) {
     }
 }
 
-// ---- band-sparse filterbank, packed (include/mlxa_cuda.h "packed filterbank") -----------------
-// words: [w: 4*n_w4 floats][start: n_bands][len: n_bands][off4: n_bands], padded to a multiple of 4.
-// Row m covers bins [start[m], start[m] + len[m]) with weights w[4*off4[m] ...] (each row starts on
-// a 16-byte boundary, zero-padded).  The blob is bulk-copied to shared memory once per CTA.
+// ---- band-sparse filterbank, packed for a lane group of G (include/mlxa_cuda.h) ---------------
+// words: [wt: n_wt floats][start: n_bands][len: n_bands][goff: n_groups][glen: n_groups], padded to
+// a multiple of 4, n_groups = ceil(n_bands / G).  Bands are taken G at a time (band j*G + g belongs
+// to lane g); inside group j the weights are TRANSPOSED, wt[goff[j] + i*G + g] = weight of band
+// j*G + g at bin start + i, zero-padded to glen[j] = the longest support in the group, so that the
+// G lanes read consecutive words (no bank conflicts) and share one loop bound.
 struct MelSmem {
-    const float* w;
+    const float* wt;
     const int* start;
-    const int* len;
-    const int* off4;
+    const int* goff;
+    const int* glen;
+    int n_groups;
 };
-MLXA_D MelSmem mel_smem_carve(const float* base, int n_bands, long long n_w4) {
+template <int G>
+MLXA_D MelSmem mel_smem_carve(const float* base, int n_bands, long long n_wt) {
     MelSmem m;
-    m.w = base;
-    const int* ip = reinterpret_cast<const int*>(base + 4 * n_w4);
+    m.n_groups = (n_bands + G - 1) / G;
+    m.wt = base;
+    const int* ip = reinterpret_cast<const int*>(base + n_wt);
     m.start = ip;
-    m.len = ip + n_bands;
-    m.off4 = ip + 2 * n_bands;
+    m.goff = ip + 2 * n_bands;
+    m.glen = m.goff + m.n_groups;
     return m;
 }
 
@@ -70,34 +75,39 @@ MLXA_D MelSmem mel_smem_carve(const float* base, int n_bands, long long n_w4) {
 // the |X|^p values it just parked in its exchange buffer: lanes run along the bands (row m of
 // the filterbank is its contiguous support only -- 1.5-2.4 % of the dense matmul of mel.py:344),
 // NF frames (1 for a packed transform, 2 for a frame pair) share every weight load.  Results go
-// to the [n_bands][tile+1] staging tile s_out, column f0 (+1).
+// to the [n_bands][tile+1] staging tile s_out, column f0 (+1).  Reads past a band's own support
+// hit zero weights (the values there are finite: stale transform output).
 template <int G, int NF>
 MLXA_D void mel_project_group(const MelSmem ms, int n_bands, int g, const float* pw, float* s_out, int ostride, int f0) {
-    for (int m = g; m < n_bands; m += G) {
-        const int n = ms.len[m];
-        const float* w = ms.w + 4 * ms.off4[m];
+    for (int j = 0; j < ms.n_groups; ++j) {
+        const int m = j * G + g;
+        const int n = ms.glen[j];
+        const float* w = ms.wt + ms.goff[j] + g;
+        const int st = (m < n_bands) ? ms.start[m] : 0;
         if constexpr (NF == 2) {
-            const float2* p2 = reinterpret_cast<const float2*>(pw) + ms.start[m];
+            const float2* p2 = reinterpret_cast<const float2*>(pw) + st;
             float a = 0.f, b = 0.f;
 #pragma unroll 2
             for (int i = 0; i < n; ++i) {
                 const float2 pp = p2[i];
-                const float ww = w[i];
+                const float ww = w[i * G];
                 a = fmaf(ww, pp.x, a);
                 b = fmaf(ww, pp.y, b);
             }
-            s_out[m * ostride + f0] = a;
-            s_out[m * ostride + f0 + 1] = b;
+            if (m < n_bands) {
+                s_out[m * ostride + f0] = a;
+                s_out[m * ostride + f0 + 1] = b;
+            }
         } else {
-            const float* p1 = pw + ms.start[m];
+            const float* p1 = pw + st;
             float a = 0.f, b = 0.f;
             int i = 0;
             for (; i + 1 < n; i += 2) {
-                a = fmaf(w[i], p1[i], a);
-                b = fmaf(w[i + 1], p1[i + 1], b);
+                a = fmaf(w[i * G], p1[i], a);
+                b = fmaf(w[(i + 1) * G], p1[i + 1], b);
             }
-            if (i < n) a = fmaf(w[i], p1[i], a);
-            s_out[m * ostride + f0] = a + b;
+            if (i < n) a = fmaf(w[i * G], p1[i], a);
+            if (m < n_bands) s_out[m * ostride + f0] = a + b;
         }
     }
 }

@@ -48,7 +48,7 @@ __host__ __device__ inline SmemLayout smem_layout(int ep, int hop, int TT, int n
     s.in_floats = round_up4((TT - 1) * hop + NFFT + 8);  // +8: room for a 16-byte alignment lead + tail
     s.tw_f2 = TW_SMEM ? (TWP + TWU) : 0;  // both tables padded to even counts (16-byte multiples)
     s.ep_floats = (ep == EP_MEL) ? round_up4(n_bands * (TT + 1)) : 0;  // mel staging tile [n_bands][TT+1]
-    s.mel_floats = (ep == EP_MEL) ? (int)packed_bank_words(n_bands, n_w4) : 0;
+    s.mel_floats = (ep == EP_MEL) ? (int)packed_bank_words(n_bands, n_w4, P::G) : 0;
     s.bytes = size_t(n_in_buf * s.in_floats + NFFT + s.ep_floats + s.mel_floats) * 4 +
               size_t(s.tw_f2 + NG * P::BUF) * 8 + 32;
     return s;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
     const float2* tw_plan = TW_SMEM ? s_tw : p.tw_plan;
     const float2* tw_unpack = TW_SMEM ? s_tw + TWP : p.tw_unpack;
     MelSmem ms{};
-    if constexpr (EP == EP_MEL) ms = mel_smem_carve(s_mel, p.n_bands, p.n_w4);
+    if constexpr (EP == EP_MEL) ms = mel_smem_carve<P::G>(s_mel, p.n_bands, p.n_w4);
     __syncthreads();
     mbar_wait(s_bar + 2, 0);
 
@@ -357,6 +357,8 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
 }
 
 // host tables: plan twiddles and the real-unpack twiddle 0.5*exp(-i*pi*k/N)
+int MLXA_CAT(plan_group_, MLXA_NFFT)() { return P::G; }
+
 void MLXA_CAT(plan_tables_, MLXA_NFFT)(float2* tw_plan_host, int* n_plan, float2* tw_unpack_host, int* n_unpack) {
     *n_plan = TWP;       // even counts: the tables are bulk-copied in 16-byte units
     *n_unpack = TWU;

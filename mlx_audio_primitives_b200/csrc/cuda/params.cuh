@@ -31,7 +31,7 @@ struct FwdParams {
     float power;
     const float* bank;   // packed band-sparse filterbank (device), see fwd_epilogue.cuh
     int n_bands;
-    long long n_w4;      // float4 weight groups in the packed bank
+    long long n_w4;      // transposed weight words (n_wt) in the packed bank
     int const_bulk;      // window / bank pointers are 16-byte aligned -> bulk async copies
     float* mel;   // (B, n_bands, T)
     float* gmax;  // optional running max
@@ -43,8 +43,8 @@ struct FwdParams {
 };
 
 // 32-bit words of a packed band-sparse filterbank (layout: fwd_epilogue.cuh / mlxa_cuda.h)
-__host__ __device__ inline long long packed_bank_words(int n_bands, long long n_w4) {
-    return (4 * n_w4 + 3LL * n_bands + 3) & ~3LL;
+__host__ __device__ inline long long packed_bank_words(int n_bands, long long n_wt, int group) {
+    return (n_wt + 2LL * n_bands + 2LL * ((n_bands + group - 1) / group) + 3) & ~3LL;
 }
 
 struct InvParams {
@@ -67,6 +67,7 @@ struct InvParams {
 #define MLXA_DECL_LAUNCHERS(NF)                                                            \
     cudaError_t launch_fwd_##NF(int ep, FwdParams& p, cudaStream_t s);                     \
     cudaError_t launch_inv_##NF(InvParams& p, cudaStream_t s);                             \
+    int plan_group_##NF();                                                                  \
     void plan_tables_##NF(float2* tw_plan_host, int* n_plan, float2* tw_unpack_host, int* n_unpack);
 
 // naive O(n^2) DFT fallback for any other n_fft

@@ -260,8 +260,8 @@ __global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p, int n
     float* xw = s_x + warp * xs;
     MelSmem ms{};
     if constexpr (EP == EP_MEL) {
-        ms = mel_smem_carve(s_mel, p.n_bands, p.n_w4);
-        const int words = (int)packed_bank_words(p.n_bands, p.n_w4);
+        ms = mel_smem_carve<32>(s_mel, p.n_bands, p.n_w4);
+        const int words = (int)packed_bank_words(p.n_bands, p.n_w4, 32);
         for (int i = threadIdx.x; i < words; i += 256) s_mel[i] = __ldg(p.bank + i);
         __syncthreads();
     }
@@ -311,7 +311,7 @@ cudaError_t launch_fwd_naive(int ep, FwdParams& p, cudaStream_t s) {
     const int TT = 8;
     const size_t xs = size_t((p.n_fft + 3) & ~3) * 4, ps = (ep == EP_MEL) ? size_t((p.F + 3) & ~3) * 4 : 0;
     const size_t fixed = (ep == EP_MEL)
-        ? size_t((p.n_bands * (TT + 1) + 3) & ~3) * 4 + size_t(packed_bank_words(p.n_bands, p.n_w4)) * 4 : 0;
+        ? size_t((p.n_bands * (TT + 1) + 3) & ~3) * 4 + size_t(packed_bank_words(p.n_bands, p.n_w4, 32)) * 4 : 0;
     int nwarps = 8;
     while (nwarps > 1 && size_t(nwarps) * (xs + ps) + fixed > 200 * 1024) nwarps >>= 1;
     const size_t smem = size_t(nwarps) * (xs + ps) + fixed;

@@ -103,17 +103,18 @@ def sparse_rows_host(bank: np.ndarray):
     return out
 
 
-def pack_bank_host(bank: np.ndarray):
-    """dense (n_bands, F) float32 -> (packed words, n_w4) via the library's own packer."""
+def pack_bank_host(bank: np.ndarray, group: int):
+    """dense (n_bands, F) float32 -> (packed words, n_wt) via the library's own packer; ``group`` is the
+    lane-group width of the kernels serving this n_fft (``mlxa_plan_group``)."""
     bank = np.ascontiguousarray(bank, dtype=np.float32)
     n_bands, F = bank.shape
-    n_w4 = C.c_int64(0)
+    n_wt = C.c_int64(0)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    check(_ext.mlxa_pack_filterbank(vp(bank), n_bands, F, None, 0, C.byref(n_w4)), "pack_filterbank")
-    words = int(_ext.mlxa_packed_bank_words(n_bands, n_w4.value))
+    check(_ext.mlxa_pack_filterbank(vp(bank), n_bands, F, group, None, 0, C.byref(n_wt)), "pack_filterbank")
+    words = int(_ext.mlxa_packed_bank_words(n_bands, n_wt.value, group))
     packed = np.zeros(words, dtype=np.float32)
-    check(_ext.mlxa_pack_filterbank(vp(bank), n_bands, F, vp(packed), words, C.byref(n_w4)), "pack_filterbank")
-    return packed, int(n_w4.value)
+    check(_ext.mlxa_pack_filterbank(vp(bank), n_bands, F, group, vp(packed), words, C.byref(n_wt)), "pack_filterbank")
+    return packed, int(n_wt.value)
 
 
 _lock = threading.RLock()
@@ -139,7 +140,8 @@ def sparse_bank_device(key: tuple, host_fn) -> SparseBank:
         sb = _sparse_cache.get(k)
         if sb is None:
             dense = np.asarray(host_fn())
-            packed, n_w4 = pack_bank_host(dense)
+            n_fft = 2 * (dense.shape[1] - 1)
+            packed, n_w4 = pack_bank_host(dense, int(_ext.mlxa_plan_group(n_fft)))
             sb = SparseBank(torch.from_numpy(packed).cuda(), dense.shape[0], n_w4, packed)
             _sparse_cache[k] = sb
         return sb

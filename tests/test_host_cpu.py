@@ -22,6 +22,7 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in mlxa_cuda.h but not exported"
     assert declared - {"mlxa_last_error", "mlxa_packed_bank_words"} == set(ext.SIGNATURES), "host-layer signature table out of sync"
+    assert ext._ext.mlxa_plan_group(400) == 16 and ext._ext.mlxa_plan_group(2048) == 32 and ext._ext.mlxa_plan_group(777) == 32
     assert ext._ext.mlxa_abi_version() == ext.ABI_VERSION
     assert ext._ext.mlxa_has_fast_plan(400) == 1 and ext._ext.mlxa_has_fast_plan(2048) == 1
     assert ext._ext.mlxa_has_fast_plan(600) == 0
@@ -48,13 +49,19 @@ def test_host_constants_match_reference_fixtures(golden):
             fb = mel_filterbank_host(sr, n_fft, n_mels, fmin, fmax, bool(int(parts[6])), norm)
             assert np.array_equal(fb, golden[key]), key
             # the packed band-sparse form (what the kernels consume) reproduces the dense matrix exactly
-            packed, n_w4 = pack_bank_host(fb)
-            ints = packed[4 * n_w4:].view(np.int32)
-            start, ln, off4 = ints[:n_mels], ints[n_mels:2 * n_mels], ints[2 * n_mels:3 * n_mels]
-            dense = np.zeros_like(fb)
-            for m in range(n_mels):
-                dense[m, start[m]:start[m] + ln[m]] = packed[4 * off4[m]:4 * off4[m] + ln[m]]
-            assert np.array_equal(dense, fb) and np.all(off4 * 4 % 4 == 0)
+            for group in (16, 32):
+                packed, n_wt = pack_bank_host(fb, group)
+                n_groups = -(-n_mels // group)
+                ints = packed[n_wt:].view(np.int32)
+                start, ln = ints[:n_mels], ints[n_mels:2 * n_mels]
+                goff, glen = ints[2 * n_mels:2 * n_mels + n_groups], ints[2 * n_mels + n_groups:2 * n_mels + 2 * n_groups]
+                dense = np.zeros_like(fb)
+                for m in range(n_mels):
+                    j_, g_ = divmod(m, group)
+                    col = packed[goff[j_] + g_: goff[j_] + glen[j_] * group: group]
+                    assert ln[m] <= glen[j_] and not col[ln[m]:].any()
+                    dense[m, start[m]:start[m] + ln[m]] = col[:ln[m]]
+                assert np.array_equal(dense, fb)
         elif parts[0] == "dctmat":
             norm = None if parts[3] == "None" else parts[3]
             assert np.array_equal(dct_matrix_host(int(parts[1]), int(parts[2]), norm), golden[key]), key

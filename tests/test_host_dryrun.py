@@ -33,16 +33,18 @@ class _StubLib:
                 else:
                     t(a)  # raises TypeError on a wrong Python type
             self.calls.append(name)
-            if name == "mlxa_pack_filterbank":  # out-parameter: report one float4 group per band
-                args[5]._obj.value = args[1]
+            if name == "mlxa_pack_filterbank":  # out-parameter: pretend every band has 4 weights
+                args[6]._obj.value = 4 * args[1]
+            if name == "mlxa_plan_group":
+                return 16
             return 0
         return fn
 
     def mlxa_last_error(self):
         return b""
 
-    def mlxa_packed_bank_words(self, n_bands, n_w4):
-        return (4 * n_w4 + 3 * n_bands + 3) & ~3
+    def mlxa_packed_bank_words(self, n_bands, n_wt, group):
+        return (n_wt + 2 * n_bands + 2 * (-(-n_bands // group)) + 3) & ~3
 
 
 @pytest.fixture
