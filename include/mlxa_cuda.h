@@ -161,10 +161,12 @@ int mlxa_fill_f32(float* x, int64_t n, float value, void* stream);
 /* convert.py:14-60.  out = coef*log10(max(x, amin)/max(ref, amin)); ref is *ref_dev when
  * ref_dev != NULL (a device scalar, e.g. the fused max for ref=max) else ref_host.
  * use_top_db: clamp at coef*log10(max(*gmax_dev, amin)/max(ref, amin)) - top_db, the global
- * max of the output by monotonicity.  In-place (out == x) is allowed. */
+ * max of the output by monotonicity.  In-place (out == x) is allowed.  reset_next (optional): a
+ * device float set to 0 by this launch -- the peak slot the NEXT producer call will atomically raise,
+ * so a pipeline alternating two slots needs no separate fill launch. */
 int mlxa_to_db_f32(const float* x, int64_t n, float coef, float amin, float ref_host,
                    const float* ref_dev, int use_top_db, float top_db, const float* gmax_dev,
-                   float* out, void* stream);
+                   float* out, float* reset_next, void* stream);
 /* convert.py:100-129,169-198: out = ref * 10^(x/div) */
 int mlxa_from_db_f32(const float* x, int64_t n, float ref, float div, float* out, void* stream);
 

@@ -40,7 +40,7 @@ SIGNATURES = {
     "mlxa_transpose_c64": [_p, _i64, _i64, _i64, _p, _p],
     "mlxa_max_f32": [_p, _i64, _p, _p],
     "mlxa_fill_f32": [_p, _i64, _f32, _p],
-    "mlxa_to_db_f32": [_p, _i64, _f32, _f32, _f32, _p, _i32, _f32, _p, _p, _p],
+    "mlxa_to_db_f32": [_p, _i64, _f32, _f32, _f32, _p, _i32, _f32, _p, _p, _p, _p],
     "mlxa_from_db_f32": [_p, _i64, _f32, _f32, _p, _p],
     "mlxa_dct_f32": [_p, _i64, _i32, _p, _i32, _p, _p],
     "mlxa_mfcc_tail_f32": [_p, _i64, _i32, _i64, _p, _i32, _p, _i32, _f32, _f32, _i32, _f32, _p, _p, _p],

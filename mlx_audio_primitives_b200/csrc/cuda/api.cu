@@ -392,10 +392,10 @@ int mlxa_fill_f32(float* x, int64_t n, float value, void* stream) {
     return 0;
 }
 int mlxa_to_db_f32(const float* x, int64_t n, float coef, float amin, float ref_host, const float* ref_dev,
-                   int use_top_db, float top_db, const float* gmax_dev, float* out, void* stream) {
+                   int use_top_db, float top_db, const float* gmax_dev, float* out, float* reset_next, void* stream) {
     CHECK_ARG(x && out && n > 0, "bad argument");
     CHECK_ARG(!use_top_db || (gmax_dev && top_db > 0), "top_db needs a positive value and the global max");
-    CHECK_CUDA(run_to_db(x, n, coef, amin, ref_host, ref_dev, use_top_db, top_db, gmax_dev, out, (cudaStream_t)stream), "to_db");
+    CHECK_CUDA(run_to_db(x, n, coef, amin, ref_host, ref_dev, use_top_db, top_db, gmax_dev, out, reset_next, (cudaStream_t)stream), "to_db");
     return 0;
 }
 int mlxa_from_db_f32(const float* x, int64_t n, float ref, float div, float* out, void* stream) {
@@ -514,7 +514,7 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
             cudaStream_t s = ws.st[ci % NS];
             float* m = ws.d_mel + b0 * mel_per_clip;
             int rc = mlxa_to_db_f32(m, nb * mel_per_clip, 10.0f, amin, ref, ref_is_max ? ws.d_gmax : nullptr, use_top_db,
-                                    top_db, ws.d_gmax, m, s);
+                                    top_db, ws.d_gmax, m, nullptr, s);
             if (rc) return rc;
             CHECK_CUDA(cudaMemcpyAsync(out_host + b0 * mel_per_clip, m, sizeof(float) * (size_t)nb * mel_per_clip,
                                        cudaMemcpyDeviceToHost, s), "d2h");

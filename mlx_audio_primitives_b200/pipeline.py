@@ -44,12 +44,13 @@ class LogMelPlan:
             self.bank = sparse_bank_device(key, lambda: mel_filterbank_host(sr, n_fft, n_mels, float(fmin),
                                                                             float(fmax), bool(htk), norm))
             self.win = padded_window(window, self.win_length, self.n_fft)
-            self.peak = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self.peaks = torch.zeros(2, dtype=torch.float32, device=self.device)  # two slots, alternated per call
+            self._slot = 0
         self._win_host = np.zeros(self.n_fft, np.float32)
         left = (self.n_fft - self.win_length) // 2
         self._win_host[left:left + self.win_length] = window_host(window, self.win_length, True)
         self.need_peak = self.to_db and (self.ref_is_max or self.top_db is not None)
-        self.kernel_launches_per_call = 1 + (2 if self.need_peak else 0)
+        self.kernel_launches_per_call = 1 + (1 if self.need_peak else 0)
 
     def empty_output(self) -> torch.Tensor:
         return torch.empty((self.B, self.n_mels, self.T), dtype=torch.float32, device=self.device)
@@ -57,22 +58,26 @@ class LogMelPlan:
     # -- the two launches, separately callable so a benchmark can time the dominant kernel ----
     def mel(self, y: torch.Tensor, out: torch.Tensor) -> None:
         s = torch.cuda.current_stream(self.device).cuda_stream
-        if self.need_peak:
-            check(_ext.mlxa_fill_f32(ptr(self.peak), 1, 0.0, s), "fill")
-        fuse = self.to_db and not self.need_peak
+        fuse = self.to_db and not self.need_peak  # the peak slot was zeroed by the previous call's dB kernel
         check(_ext.mlxa_melspec_f32(ptr(y), self.B, self.L, y.stride(0), ptr(self.win), self.n_fft, self.hop,
                                     int(self.center), self.mode, self.power, ptr(self.bank.packed),
-                                    self.n_mels, self.bank.n_w4, ptr(out), ptr(self.peak) if self.need_peak else None,
+                                    self.n_mels, self.bank.n_w4, ptr(out), self._peak_ptr() if self.need_peak else None,
                                     int(fuse), 10.0, self.amin, self.ref, s), "melspectrogram")
+
+    def _peak_ptr(self, other: bool = False) -> int:
+        return self.peaks.data_ptr() + 4 * (self._slot ^ int(other))
 
     def db(self, out: torch.Tensor) -> None:
         if not self.need_peak:
             return
-        distributed.all_reduce_max_(self.peak)
+        peak = self.peaks[self._slot:self._slot + 1]
+        distributed.all_reduce_max_(peak)
         s = torch.cuda.current_stream(self.device).cuda_stream
         check(_ext.mlxa_to_db_f32(ptr(out), out.numel(), 10.0, self.amin, self.ref,
-                                  ptr(self.peak) if self.ref_is_max else None, int(self.top_db is not None),
-                                  float(self.top_db or 0.0), ptr(self.peak), ptr(out), s), "to_db")
+                                  self._peak_ptr() if self.ref_is_max else None, int(self.top_db is not None),
+                                  float(self.top_db or 0.0), self._peak_ptr(), ptr(out), self._peak_ptr(other=True), s),
+              "to_db")
+        self._slot ^= 1
 
     def __call__(self, y: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         if y.shape != (self.B, self.L) or y.dtype != torch.float32 or not y.is_cuda or y.stride(1) != 1:
