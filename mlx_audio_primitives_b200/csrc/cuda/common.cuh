@@ -121,6 +121,14 @@ MLXA_D void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// Ampere-style per-thread async copies (LDGSTS), 8 bytes each; used to prefetch a spectrum frame
+MLXA_D void cp_async8(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+MLXA_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+MLXA_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+MLXA_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 MLXA_D bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(

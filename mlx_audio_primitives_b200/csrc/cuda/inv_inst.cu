@@ -94,6 +94,36 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
     const float inv_n = 1.0f / float(P::N);
     const bool hop_even = (p.hop & 1) == 0;
 
+    // PACK plans: the spectrum of a group's NEXT frame is fetched by per-lane async copies
+    // (cp.async, 8 bytes) straight into the group's exchange buffer as soon as the last pass has
+    // read it, so the HBM latency of round r+1 hides behind the butterflies and the overlap-add of
+    // round r; the previous-projection lines of the Griffin-Lim extrapolation are pulled into L2.
+    constexpr int NSPEC = PACK ? P::N + 1 : 0;
+    [[maybe_unused]] const int kmax_c = min(p.F_in, NSPEC);
+    [[maybe_unused]] auto prefetch_frame = [&](int f) {
+        if constexpr (PACK) {
+            constexpr int NQ1 = ceil_div(NSPEC, P::G);
+            const long long fo = clip + (long long)f * p.F_in;
+            const float2* X = p.spec + fo;
+            static_for<NQ1>([&](auto q) {
+                constexpr int Q = decltype(q)::value;
+                const int k = g + Q * P::G;
+                if (Q + 1 < NQ1 || k < NSPEC) {
+                    if (k < kmax_c) cp_async8(buf + k, X + k);
+                    else buf[k] = make_float2(0.f, 0.f);
+                }
+            });
+            cp_async_commit();
+            if constexpr (EXTRAP) {
+                const char* lp = reinterpret_cast<const char*>(p.spec_prev + fo);
+                for (int off = g * 128; off < kmax_c * 8 + 128; off += P::G * 128) prefetch_l2(lp + off);
+            }
+        }
+    };
+    if constexpr (PACK) {
+        if (f_lo + gi * FPT <= f_hi) prefetch_frame(f_lo + gi * FPT);
+    }
+
     for (int base = f_lo; base <= f_hi; base += NG * FPT) {
         const int fa = base + gi * FPT;
         const bool va = fa <= f_hi;
@@ -101,22 +131,27 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
 
         // ---- spectrum -> packed complex input (swapped: inverse = swap . forward . swap) ---
         if constexpr (PACK) {
-            // 1) every bin X[0..N] is read from HBM exactly once (coalesced) and parked in buf[k];
+            // 1) every bin X[0..N] is read from HBM exactly once and parked in buf[k] (prefetched);
             // 2) the lane that owns the pair (k, N-k) turns it into Z[k], Z[N-k] in place:
             //    Z[k] = E + iO, Z[N-k] = conj(E) + i*conj(O), E = (X[k] + conj X[N-k])/2,
             //    O = conj(w^k) (X[k] - conj X[N-k])/2.
             constexpr int N = P::N;
             constexpr int NQ1 = ceil_div(N + 1, P::G), NQ2 = ceil_div(N / 2 + 1, P::G);
             static_assert(P::BUF >= N + 1, "exchange buffer must hold the Nyquist bin");
-            const long long fo = clip + (long long)(va ? fa : 0) * p.F_in;
-            const float2* X = p.spec + fo;
-            const float2* Xp = EXTRAP ? p.spec_prev + fo : nullptr;
-            const int kmax = va ? min(p.F_in, N + 1) : 0;
-            static_for<NQ1>([&](auto q) {
-                constexpr int Q = decltype(q)::value;
-                const int k = g + Q * P::G;
-                if (Q + 1 < NQ1 || k <= N) buf[k] = load_bin<EXTRAP>(X, Xp, k, k < kmax, p.momentum);
-            });
+            cp_async_wait_all();
+            if constexpr (EXTRAP) {
+                if (va) {  // lane-owned bins: X + m*(X - X_prev) in place
+                    const float2* Xp = p.spec_prev + clip + (long long)fa * p.F_in;
+                    static_for<NQ1>([&](auto q) {
+                        constexpr int Q = decltype(q)::value;
+                        const int k = g + Q * P::G;
+                        if ((Q + 1 < NQ1 || k <= N) && k < kmax_c) {
+                            const float2 a = buf[k], c = __ldg(Xp + k);
+                            buf[k] = make_float2(fmaf(p.momentum, a.x - c.x, a.x), fmaf(p.momentum, a.y - c.y, a.y));
+                        }
+                    });
+                }
+            }
             __syncwarp();
             static_for<NQ2>([&](auto q) {
                 constexpr int Q = decltype(q)::value;
@@ -159,12 +194,18 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
         __syncwarp();
         pass_load_buf<P, 1>(g, v, buf);
         __syncwarp();
+        if constexpr (PACK && P::NPASS == 2) {
+            if (fa + NG * FPT <= f_hi) prefetch_frame(fa + NG * FPT);  // buffer is free: fetch the next round's frame
+        }
         pass_compute<P, 1>(g, v, tw_plan);
         if constexpr (P::NPASS == 3) {
             pass_store_buf<P, 1>(g, v, buf);
             __syncwarp();
             pass_load_buf<P, 2>(g, v, buf);
             __syncwarp();
+            if constexpr (PACK) {
+                if (fa + NG * FPT <= f_hi) prefetch_frame(fa + NG * FPT);
+            }
             pass_compute<P, 2>(g, v, tw_plan);
         }
 
