@@ -26,12 +26,16 @@ using P = PF::Plan;
 constexpr int NFFT = MLXA_NFFT;
 constexpr bool PACK = (PF::MODE == MODE_PACK);
 constexpr int FPT = PACK ? 1 : 2;                              // frames per transform
-// warps per CTA: sized so that the exchange buffers of all resident transforms fill the SM's shared memory
-// (n_fft 2048: 16 warps x 8.4 KB; n_fft 4096: 8 warps x 16.6 KB with 64 complex values per lane;
-//  n_fft 400: one 16-warp CTA per SM with double-buffered staging)
-constexpr int THREADS = (P::E > 32) ? 256 : (P::N >= 400 ? 512 : 256);
-constexpr int NG = THREADS / P::G;                            // transforms in flight per CTA
-static_assert((NG * P::BUF) % 2 == 0 && NFFT % 4 == 0, "smem carve-up assumes 16-byte multiples");
+// Threads per CTA, sized so that the exchange buffers of the resident transforms fill the SM's shared
+// memory: the mel epilogue runs ONE 16-warp CTA per SM for the mid-size plans (its staging tile and the
+// double-buffered input want the whole SM); the store-through epilogues (STFT, Griffin-Lim) run two
+// 8-warp CTAs per SM so one CTA's global stores overlap the other's butterflies.  n_fft 2048 needs 16
+// warps in one CTA either way (8.4 KB of exchange buffer per warp), n_fft 4096 runs 8 warps (64 complex
+// values per lane).
+constexpr int threads_for(int ep) {
+    return (P::E > 32) ? 256 : ((P::G == 32 && P::E == 32) ? 512 : ((ep == EP_MEL && P::N >= 400) ? 512 : 256));
+}
+static_assert(P::BUF % 2 == 0 && NFFT % 4 == 0, "smem carve-up assumes 16-byte multiples");
 constexpr int NBINS = NFFT / 2 + 1;
 constexpr int NUNPACK = PACK ? P::N + 1 : 0;                   // 0.5*exp(-i*pi*k/N) entries
 constexpr bool TW_SMEM = (P::TW + NUNPACK) * 8 <= 20 * 1024;   // twiddles staged in smem when small
@@ -43,7 +47,7 @@ struct SmemLayout {
     int in_floats, tw_f2, ep_floats, mel_floats;
     size_t bytes;
 };
-__host__ __device__ inline SmemLayout smem_layout(int ep, int hop, int TT, int n_in_buf, int n_bands, long long n_w4) {
+__host__ __device__ inline SmemLayout smem_layout(int ep, int NG, int hop, int TT, int n_in_buf, int n_bands, long long n_w4) {
     SmemLayout s;
     s.in_floats = round_up4((TT - 1) * hop + NFFT + 8);  // +8: room for a 16-byte alignment lead + tail
     s.tw_f2 = TW_SMEM ? (TWP + TWU) : 0;  // both tables padded to even counts (16-byte multiples)
@@ -77,11 +81,13 @@ MLXA_D Tile tile_info(const FwdParams& p, int TT, int tiles_per_clip, long long 
 }
 
 template <int EP, int PW>
-__global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p) {
+    constexpr int THREADS = threads_for(EP);
+    constexpr int NG = THREADS / P::G;  // transforms in flight per CTA
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TT = p.tile_frames;
     const int nbuf = p.n_in_buf;
-    const SmemLayout lay = smem_layout(EP, p.hop, TT, nbuf, p.n_bands, p.n_w4);
+    const SmemLayout lay = smem_layout(EP, NG, p.hop, TT, nbuf, p.n_bands, p.n_w4);
 
     float* s_in0 = reinterpret_cast<float*>(smem_raw);
     float* s_win = s_in0 + nbuf * lay.in_floats;
@@ -312,6 +318,7 @@ __global__ void __launch_bounds__(THREADS) fwd_kernel(const FwdParams p) {
 
 template <int EP, int PW>
 cudaError_t launch_one(FwdParams& p, size_t smem, cudaStream_t s) {
+    constexpr int THREADS = threads_for(EP);
     cudaError_t e = cudaFuncSetAttribute(fwd_kernel<EP, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, n_sm = 0, per_sm = 0;
@@ -332,7 +339,8 @@ cudaError_t launch_one(FwdParams& p, size_t smem, cudaStream_t s) {
 
 cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t s) {
     constexpr size_t kMaxSmem = 227 * 1024;
-    auto bytes = [&](int TT, int nb) { return smem_layout(ep, p.hop, TT, nb, p.n_bands, p.n_w4).bytes; };
+    const int NG = threads_for(ep) / P::G;
+    auto bytes = [&](int TT, int nb) { return smem_layout(ep, NG, p.hop, TT, nb, p.n_bands, p.n_w4).bytes; };
     // one round of transforms per tile for the mel epilogue (its staging tile is [n_bands][TT+1]),
     // two rounds for the store-through epilogues
     int TT = NG * FPT * (ep == EP_MEL ? 1 : 2);

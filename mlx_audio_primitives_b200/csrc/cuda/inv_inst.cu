@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
         const long long j = o - p.trim;
         if (j < 0 || j >= p.out_len) continue;
         float val = 0.f;
-        if (o < p.ola_len) val = s_acc[i] / fmaxf(wbulk ? s_wss[i] : __ldg(p.wss + o), 1e-8f);
+        if (o < p.ola_len) val = __fdividef(s_acc[i], fmaxf(wbulk ? s_wss[i] : __ldg(p.wss + o), 1e-8f));
         yb[j] = val;
     }
 }
@@ -291,11 +291,23 @@ cudaError_t MLXA_CAT(launch_inv_, MLXA_NFFT)(InvParams& p, cudaStream_t s) {
     constexpr size_t kMaxSmem = 227 * 1024;
     const int r = (NFFT + p.hop - 1) / p.hop;
     const long long span = (p.ola_len > p.out_len + p.trim) ? p.ola_len : p.out_len + p.trim;
-    // tile of TH hops: as large as fits two CTAs per SM, but at least 4 halos long
-    int TH = 1;
-    while (inv_smem_bytes(p.hop, TH * 2) <= kMaxSmem / 2) TH *= 2;
-    while (TH < 4 * r && inv_smem_bytes(p.hop, TH * 2) <= kMaxSmem) TH *= 2;
-    while ((long long)(TH / 2) * p.hop >= span && TH > 1) TH /= 2;  // short clips
+    // A tile of TH hops needs the TH + r - 1 frames that touch it.  Frames are transformed in rounds of
+    // NG*FPT, so TH is chosen as m*NG*FPT - (r - 1): every round is full (no idle transform slots) and
+    // the halo recompute is (r - 1) frames per m rounds.  m grows while two CTAs still fit per SM.
+    const int per_round = NG * FPT;
+    auto th_for = [&](int m) { return m * per_round - (r - 1); };
+    int m = 1;
+    while (th_for(m) < 1) ++m;
+    while (inv_smem_bytes(p.hop, th_for(m + 1)) <= kMaxSmem / 2) ++m;
+    if (inv_smem_bytes(p.hop, th_for(m)) > kMaxSmem / 2) {  // not even one round fits twice: go for one CTA per SM
+        while (inv_smem_bytes(p.hop, th_for(m + 1)) <= kMaxSmem && m < 4) ++m;
+    }
+    int TH = th_for(m);
+    while (m > 1 && (long long)th_for(m - 1) * p.hop >= span) TH = th_for(--m);  // short clips
+    if ((long long)TH * p.hop > span) {  // very short clip: one tile that just covers it
+        TH = (int)((span + p.hop - 1) / p.hop);
+        if (TH < 1) TH = 1;
+    }
     if (inv_smem_bytes(p.hop, TH) > kMaxSmem) return cudaErrorInvalidConfiguration;
     p.tile_hops = TH;
     const size_t smem = inv_smem_bytes(p.hop, TH);
