@@ -47,12 +47,12 @@ struct SmemLayout {
     int in_floats, tw_f2, ep_floats, mel_floats;
     size_t bytes;
 };
-__host__ __device__ inline SmemLayout smem_layout(int ep, int NG, int hop, int TT, int n_in_buf, int n_bands, long long n_w4) {
+__host__ __device__ inline SmemLayout smem_layout(int ep, int NG, int hop, int TT, int n_in_buf, int n_bands, long long n_w4, int bank_in_smem) {
     SmemLayout s;
     s.in_floats = round_up4((TT - 1) * hop + NFFT + 8);  // +8: room for a 16-byte alignment lead + tail
     s.tw_f2 = TW_SMEM ? (TWP + TWU) : 0;  // both tables padded to even counts (16-byte multiples)
     s.ep_floats = (ep == EP_MEL) ? round_up4(n_bands * (TT + 1)) : 0;  // mel staging tile [n_bands][TT+1]
-    s.mel_floats = (ep == EP_MEL) ? (int)packed_bank_words(n_bands, n_w4, P::G) : 0;
+    s.mel_floats = (ep == EP_MEL && bank_in_smem) ? (int)packed_bank_words(n_bands, n_w4, P::G) : 0;
     s.bytes = size_t(n_in_buf * s.in_floats + NFFT + s.ep_floats + s.mel_floats) * 4 +
               size_t(s.tw_f2 + NG * P::BUF) * 8 + 32;
     return s;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TT = p.tile_frames;
     const int nbuf = p.n_in_buf;
-    const SmemLayout lay = smem_layout(EP, NG, p.hop, TT, nbuf, p.n_bands, p.n_w4);
+    const SmemLayout lay = smem_layout(EP, NG, p.hop, TT, nbuf, p.n_bands, p.n_w4, p.bank_in_smem);
 
     float* s_in0 = reinterpret_cast<float*>(smem_raw);
     float* s_win = s_in0 + nbuf * lay.in_floats;
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
         }
         if (cbulk) {
             bulk_copy_g2s(s_win, p.window, NFFT * 4, s_bar + 2);
-            if (EP == EP_MEL) bulk_copy_g2s(s_mel, p.bank, mel_bytes, s_bar + 2);
+            if (EP == EP_MEL && mel_bytes) bulk_copy_g2s(s_mel, p.bank, mel_bytes, s_bar + 2);
         }
         const Tile t = tile_info(p, TT, tiles_per_clip, id);
         if (t.bulk) {
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
     const float2* tw_plan = TW_SMEM ? s_tw : p.tw_plan;
     const float2* tw_unpack = TW_SMEM ? s_tw + TWP : p.tw_unpack;
     MelSmem ms{};
-    if constexpr (EP == EP_MEL) ms = mel_smem_carve<P::G>(s_mel, p.n_bands, p.n_w4);
+    if constexpr (EP == EP_MEL) ms = mel_smem_carve<P::G>(p.bank_in_smem ? s_mel : p.bank, p.n_bands, p.n_w4);
     __syncthreads();
     mbar_wait(s_bar + 2, 0);
 
@@ -338,13 +338,15 @@ cudaError_t launch_one(FwdParams& p, size_t smem, cudaStream_t s) {
 #define MLXA_CAT(a, b) MLXA_CAT2(a, b)
 
 cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t s) {
-    constexpr size_t kMaxSmem = 227 * 1024;
+    constexpr size_t kMaxSmem = 227 * 1024 - 256;  // opt-in maximum minus the kernel's static shared memory
     const int NG = threads_for(ep) / P::G;
-    auto bytes = [&](int TT, int nb) { return smem_layout(ep, NG, p.hop, TT, nb, p.n_bands, p.n_w4).bytes; };
+    p.bank_in_smem = 1;
+    if (ep == EP_MEL && smem_layout(ep, NG, p.hop, 1, 1, p.n_bands, p.n_w4, 1).bytes > kMaxSmem) p.bank_in_smem = 0;
+    auto bytes = [&](int TT, int nb) { return smem_layout(ep, NG, p.hop, TT, nb, p.n_bands, p.n_w4, p.bank_in_smem).bytes; };
     // one round of transforms per tile for the mel epilogue (its staging tile is [n_bands][TT+1]),
     // two rounds for the store-through epilogues
     int TT = NG * FPT * (ep == EP_MEL ? 1 : 2);
-    while (TT > NG * FPT && bytes(TT, 1) > kMaxSmem) TT >>= 1;
+    while (TT > 1 && bytes(TT, 1) > kMaxSmem) TT >>= 1;  // huge hops: fewer frames per tile than transform slots
     if (bytes(TT, 1) > kMaxSmem) return cudaErrorInvalidConfiguration;
     // double-buffer the staging when it does not cost a resident CTA
     const int ctas1 = (int)(kMaxSmem / bytes(TT, 1));

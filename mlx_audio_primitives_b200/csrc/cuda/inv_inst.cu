@@ -308,6 +308,7 @@ cudaError_t MLXA_CAT(launch_inv_, MLXA_NFFT)(InvParams& p, cudaStream_t s) {
         TH = (int)((span + p.hop - 1) / p.hop);
         if (TH < 1) TH = 1;
     }
+    while (TH > 1 && inv_smem_bytes(p.hop, TH) > kMaxSmem) TH = (TH + 1) / 2;  // huge hops: partial rounds
     if (inv_smem_bytes(p.hop, TH) > kMaxSmem) return cudaErrorInvalidConfiguration;
     p.tile_hops = TH;
     const size_t smem = inv_smem_bytes(p.hop, TH);

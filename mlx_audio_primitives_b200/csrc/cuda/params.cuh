@@ -33,6 +33,7 @@ struct FwdParams {
     int n_bands;
     long long n_w4;      // transposed weight words (n_wt) in the packed bank
     int const_bulk;      // window / bank pointers are 16-byte aligned -> bulk async copies
+    int bank_in_smem;    // 0: the packed bank is too large for shared memory and is read from global
     float* mel;   // (B, n_bands, T)
     float* gmax;  // optional running max
     int db_mode;
