@@ -75,7 +75,8 @@ int mlxa_window_sumsquare_f32(const float* window, int n_fft, int hop, int64_t T
 int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window,
                   int n_fft, int hop, int center, int pad_mode, mlxa_c64* spec, void* stream);
 
-/* Lanes per transform of the kernels that serve n_fft (32 for sizes without a compiled plan). */
+/* How the mel kernel that serves n_fft wants its filterbank packed: the lanes per transform (4..32;
+ * 32 for sizes without a compiled plan), or 1 = ROW format (n_fft = 400). */
 int mlxa_plan_group(int n_fft);
 
 /* Packed band-sparse filterbank ("bank") for a lane group of `group` = mlxa_plan_group(n_fft):
@@ -86,7 +87,13 @@ int mlxa_plan_group(int n_fft);
  *     int32   start[n_bands]    first frequency bin of each row's contiguous support
  *     int32   len[n_bands]      support length in bins
  *     int32   goff[n_groups], glen[n_groups]      n_groups = ceil(n_bands / group)
- * padded to mlxa_packed_bank_words(n_bands, n_wt, group) words (a multiple of 4).  The kernels
+ * padded to mlxa_packed_bank_words(n_bands, n_wt, group) words (a multiple of 4).
+ * ROW format (group == 1; the projection runs with lanes along frames, weights are warp-uniform):
+ *     float   wt[n_wt]          every band's contiguous run, zero-padded to whole quads (16-byte units)
+ *     int32   start[n_bands]    first frequency bin of the run
+ *     int32   n4[n_bands]       quads in the run
+ *     int32   off4[n_bands]     first quad of the run (wt + 4*off4)
+ * The kernels
  * bulk-copy this blob into shared memory once per CTA.  mlxa_pack_filterbank builds it on the
  * HOST from a dense (n_bands, F) row-major matrix (rows must have contiguous support, which
  * triangular mel / linear / Bark banks have); returns n_wt through *n_wt_out.  Call it with

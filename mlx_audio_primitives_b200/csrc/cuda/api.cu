@@ -216,17 +216,33 @@ int64_t mlxa_packed_bank_words(int n_bands, int64_t n_wt, int group) { return pa
 int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, int group, float* packed_host,
                          int64_t capacity_words, int64_t* n_wt_out) {
     CHECK_ARG(dense_host && n_wt_out && n_bands > 0 && F > 0, "bad argument");
-    CHECK_ARG(group == 4 || group == 8 || group == 16 || group == 32, "group must be 4, 8, 16 or 32");
-    const int n_groups = (n_bands + group - 1) / group;
-    std::vector<int> start(n_bands, 0), len(n_bands, 0), goff(n_groups, 0), glen(n_groups, 0);
+    CHECK_ARG(group == 1 || group == 4 || group == 8 || group == 16 || group == 32, "group must be 1 (row format), 4, 8, 16 or 32");
+    std::vector<int> start(n_bands, 0), len(n_bands, 0);
     for (int m = 0; m < n_bands; ++m) {
         const float* row = dense_host + (int64_t)m * F;
         int lo = -1, hi = -1;
         for (int k = 0; k < F; ++k)
             if (row[k] != 0.f) { if (lo < 0) lo = k; hi = k; }
         if (lo >= 0) { start[m] = lo; len[m] = hi - lo + 1; }
-        glen[m / group] = std::max(glen[m / group], len[m]);
     }
+    if (group == 1) {  // row format: every band's run zero-padded to whole quads
+        std::vector<int> off4(n_bands, 0);
+        int64_t total = 0;
+        for (int m = 0; m < n_bands; ++m) { off4[m] = (int)(total / 4); total += (int64_t)((len[m] + 3) / 4) * 4; }
+        *n_wt_out = total;
+        if (!packed_host) return 0;
+        const int64_t words = packed_bank_words(n_bands, total, 1);
+        CHECK_ARG(capacity_words >= words, "packed buffer too small");
+        std::memset(packed_host, 0, sizeof(float) * words);
+        for (int m = 0; m < n_bands; ++m)
+            std::memcpy(packed_host + 4 * (int64_t)off4[m], dense_host + (int64_t)m * F + start[m], sizeof(float) * len[m]);
+        int32_t* ip = reinterpret_cast<int32_t*>(packed_host + total);
+        for (int m = 0; m < n_bands; ++m) { ip[m] = start[m]; ip[n_bands + m] = (len[m] + 3) / 4; ip[2 * n_bands + m] = off4[m]; }
+        return 0;
+    }
+    const int n_groups = (n_bands + group - 1) / group;
+    std::vector<int> goff(n_groups, 0), glen(n_groups, 0);
+    for (int m = 0; m < n_bands; ++m) glen[m / group] = std::max(glen[m / group], len[m]);
     int64_t total = 0;
     for (int j = 0; j < n_groups; ++j) { goff[j] = (int)total; total += (int64_t)glen[j] * group; }
     *n_wt_out = total;
@@ -249,7 +265,7 @@ int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const fl
                      int center, int pad_mode, float power, const float* bank, int n_bands, int64_t n_w4, float* mel,
                      float* gmax, int db_mode, float db_coef, float db_amin, float db_ref, void* stream) {
     CHECK_ARG(bank && mel, "null pointer");
-    CHECK_ARG(n_bands > 0 && n_w4 > 0 && n_w4 < (1LL << 22), "bad filterbank size");  // n_w4 = n_wt words
+    CHECK_ARG(n_bands > 0 && n_w4 >= 0 && n_w4 < (1LL << 22), "bad filterbank size");  // n_w4 = n_wt words
     return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
         FwdParams p;
         int rc = fill_fwd_common(p, y + b0 * ldy, nb, L, ldy, window, n_fft, hop, center, pad_mode);

@@ -13,6 +13,7 @@
 // spectrum and hand every bin to the epilogue in registers.
 #include "fft_plans_list.cuh"
 #include "fwd_epilogue.cuh"
+#include "fft_mirror.cuh"
 
 #ifndef MLXA_NFFT
 #error "compile with -DMLXA_NFFT=<n_fft>"
@@ -64,10 +65,10 @@ struct Tile {
     bool bulk;
     const float* yb;
 };
-MLXA_D Tile tile_info(const FwdParams& p, int TT, int tiles_per_clip, long long id) {
+MLXA_D Tile tile_at(const FwdParams& p, int TT, int b, int tile) {
     Tile t;
-    t.b = int(id / tiles_per_clip);
-    t.t0 = int(id - (long long)t.b * tiles_per_clip) * TT;
+    t.b = b;
+    t.t0 = tile * TT;
     t.nt = min(TT, p.T - t.t0);
     t.tile_len = (t.nt - 1) * p.hop + NFFT;
     t.yb = p.y + (long long)t.b * p.ldy;
@@ -79,6 +80,24 @@ MLXA_D Tile tile_info(const FwdParams& p, int TT, int tiles_per_clip, long long 
     t.bulk = (t.src0 - t.lead >= 0) && (t.src0 - t.lead + t.n_bulk <= p.L) && ((reinterpret_cast<uintptr_t>(t.yb) & 3) == 0);
     return t;
 }
+// A persistent CTA's walk over the (clip, tile) items blockIdx.x, blockIdx.x + gridDim.x, ...: one
+// 32-bit division per kernel, then add-and-carry per step.
+struct TileWalk {
+    int b, tile, dq, dr, tpc;
+    MLXA_D TileWalk(int tiles_per_clip) : tpc(tiles_per_clip) {
+        b = int(blockIdx.x / unsigned(tpc));
+        tile = int(blockIdx.x - unsigned(b) * unsigned(tpc));
+        dq = int(gridDim.x / unsigned(tpc));
+        dr = int(gridDim.x - unsigned(dq) * unsigned(tpc));
+    }
+    MLXA_D void advance() {
+        b += dq;
+        tile += dr;
+        if (tile >= tpc) { tile -= tpc; ++b; }
+    }
+};
+
+#include "fwd_mel_rows.cuh"
 
 template <int EP, int PW>
 __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p) {
@@ -99,9 +118,8 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
     __shared__ float s_red[THREADS / 32];
 
     const int tiles_per_clip = (p.T + TT - 1) / TT;
-    const long long total = (long long)p.B * tiles_per_clip;
-    long long id = blockIdx.x;
-    if (id >= total) return;
+    TileWalk cur(tiles_per_clip);
+    if (cur.b >= p.B) return;
 
     // ---- once per CTA: barriers, constants, first tile -----------------------------------------
     const bool cbulk = p.const_bulk != 0;
@@ -122,7 +140,7 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
             bulk_copy_g2s(s_win, p.window, NFFT * 4, s_bar + 2);
             if (EP == EP_MEL && mel_bytes) bulk_copy_g2s(s_mel, p.bank, mel_bytes, s_bar + 2);
         }
-        const Tile t = tile_info(p, TT, tiles_per_clip, id);
+        const Tile t = tile_at(p, TT, cur.b, cur.tile);
         if (t.bulk) {
             mbar_arrive_expect_tx(s_bar + 0, t.n_bulk * 4);
             bulk_copy_g2s(s_in0, t.yb + t.src0 - t.lead, t.n_bulk * 4, s_bar + 0);
@@ -146,17 +164,18 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
     uint32_t ph0 = 0u, ph1 = 0u;  // parity of the next completion on each staging barrier
     float vmax = 0.f;
 
-    for (int it = 0; id < total; ++it, id += gridDim.x) {
+    for (int it = 0; cur.b < p.B; ++it, cur.advance()) {
         const int c = (nbuf == 2) ? (it & 1) : 0;
         float* s_in = s_in0 + c * lay.in_floats;
-        const Tile ti = tile_info(p, TT, tiles_per_clip, id);
+        const Tile ti = tile_at(p, TT, cur.b, cur.tile);
 
         // ---- stage: prefetch the next tile (two buffers) / fetch this one (one buffer) -------
         if (threadIdx.x == 0) {
             if (nbuf == 2) {
-                const long long nid = id + gridDim.x;
-                if (nid < total) {
-                    const Tile tn = tile_info(p, TT, tiles_per_clip, nid);
+                TileWalk nxt = cur;
+                nxt.advance();
+                if (nxt.b < p.B) {
+                    const Tile tn = tile_at(p, TT, nxt.b, nxt.tile);
                     if (tn.bulk) {
                         mbar_arrive_expect_tx(s_bar + (c ^ 1), tn.n_bulk * 4);
                         bulk_copy_g2s(s_in0 + (c ^ 1) * lay.in_floats, tn.yb + tn.src0 - tn.lead, tn.n_bulk * 4, s_bar + (c ^ 1));
@@ -332,6 +351,45 @@ cudaError_t launch_one(FwdParams& p, size_t smem, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// mel epilogue of PAIR-mode plans: the mirror-paired kernel of fwd_mel_rows.cuh (row-format bank)
+template <class PL, bool PAIR>
+struct MelRowsLaunch {
+    static cudaError_t run(FwdParams&, cudaStream_t) { return cudaErrorInvalidConfiguration; }
+};
+template <class PL>
+struct MelRowsLaunch<PL, true> {
+    template <int PW>
+    static cudaError_t go(FwdParams& p, size_t smem, cudaStream_t s) {
+        return p.bank_in_smem ? go2<PW, true>(p, smem, s) : go2<PW, false>(p, smem, s);
+    }
+    template <int PW, bool BS>
+    static cudaError_t go2(FwdParams& p, size_t smem, cudaStream_t s) {
+        using C = MelRows<PL>;
+        cudaError_t e = cudaFuncSetAttribute(mel_rows_kernel<PL, PW, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int dev = 0, n_sm = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        const long long total = (long long)p.B * ((p.T + C::TT - 1) / C::TT);
+        mel_rows_kernel<PL, PW, BS><<<(unsigned)(total < n_sm ? total : n_sm), C::THREADS, smem, s>>>(p);
+        return cudaGetLastError();
+    }
+    static cudaError_t run(FwdParams& p, cudaStream_t s) {
+        using C = MelRows<PL>;
+        constexpr size_t kMaxSmem = 227 * 1024 - 256;
+        long long bw = packed_bank_words(p.n_bands, p.n_w4, 1);
+        p.bank_in_smem = 1;
+        if (C::smem_bytes(p.hop, 1, bw) > kMaxSmem) { p.bank_in_smem = 0; bw = 0; }
+        if (C::smem_bytes(p.hop, 1, bw) > kMaxSmem) return cudaErrorInvalidConfiguration;
+        p.n_in_buf = (C::smem_bytes(p.hop, 2, bw) <= kMaxSmem) ? 2 : 1;
+        p.tile_frames = C::TT;
+        const size_t smem = C::smem_bytes(p.hop, p.n_in_buf, bw);
+        if (p.power_mode == POW_SQUARE) return go<POW_SQUARE>(p, smem, s);
+        if (p.power_mode == POW_ABS) return go<POW_ABS>(p, smem, s);
+        return go<POW_GENERAL>(p, smem, s);
+    }
+};
+
 }  // namespace
 
 #define MLXA_CAT2(a, b) a##b
@@ -339,6 +397,7 @@ cudaError_t launch_one(FwdParams& p, size_t smem, cudaStream_t s) {
 
 cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t s) {
     constexpr size_t kMaxSmem = 227 * 1024 - 256;  // opt-in maximum minus the kernel's static shared memory
+    if (!PACK && ep == EP_MEL) return MelRowsLaunch<P, !PACK>::run(p, s);
     const int NG = threads_for(ep) / P::G;
     p.bank_in_smem = 1;
     if (ep == EP_MEL && smem_layout(ep, NG, p.hop, 1, 1, p.n_bands, p.n_w4, 1).bytes > kMaxSmem) p.bank_in_smem = 0;
@@ -367,7 +426,8 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
 }
 
 // host tables: plan twiddles and the real-unpack twiddle 0.5*exp(-i*pi*k/N)
-int MLXA_CAT(plan_group_, MLXA_NFFT)() { return P::G; }
+// how the mel kernel of this n_fft wants its filterbank packed: lanes per transform, or 1 = row format
+int MLXA_CAT(plan_group_, MLXA_NFFT)() { return PACK ? P::G : 1; }
 
 void MLXA_CAT(plan_tables_, MLXA_NFFT)(float2* tw_plan_host, int* n_plan, float2* tw_unpack_host, int* n_unpack) {
     *n_plan = TWP;       // even counts: the tables are bulk-copied in 16-byte units

@@ -1,0 +1,223 @@
+// Mel-spectrogram kernel for PAIR-mode plans (n_fft = 400 = 25 x 16): two real frames ride one
+// N-point complex transform, and -- because only |X|^p is wanted -- the real-spectrum unpack never
+// touches shared memory:
+//
+//   * pass 0 (radix R0, one butterfly per lane) reads the windowed samples from the staged tile.  The
+//     second lane group of a warp reads its frames cyclically rotated by 16 samples: a rotation only
+//     multiplies the spectrum by a unit-modulus ramp, |X| is unchanged, and the two groups then hit
+//     disjoint halves of the 32 banks (every frame starts on the same bank when hop % 32 == 0).
+//   * last pass (radix R1 over NB = R0 butterflies): lane g runs butterfly g AND its mirror R0 - g.
+//     Output leg k of butterfly g is Z[g + R0*k]; its Hermitian partner Z[N - g - R0*k] is leg
+//     R1-1-k of the mirror butterfly, so both members of every (k, N-k) pair sit in the same lane.
+//     The mirror's twiddles are conj(t) * W_R1^r; the W_R1^r factor is a one-leg rotation of the DFT
+//     output (free register renaming), so one table read serves both butterflies.
+//   * |Z[k] +- conj Z[N-k]|^2 = 4 |Xa[k]|^2, 4 |Xb[k]|^2: the 1/4 rides on the projected sums.
+//   * the powers of a whole 64-frame tile are laid out [bin][frame] over the (dead) exchange buffers;
+//     the band-sparse projection then runs with lanes along FRAMES: conflict-free 64-bit reads,
+//     warp-uniform weights fetched four at a time, no padding to a lane group's longest band, and the
+//     (band, 64 frames) row goes straight to global memory (coalesced), with the running max and the
+//     optional dB fused.  (Replaces reference mel.py:309-352.)
+//
+// Included by fwd_inst.cu INSIDE its per-translation-unit namespace, after Tile / tile_info.
+
+// bank packed in ROW format (mlxa_plan_group == 1, see include/mlxa_cuda.h)
+struct RowBank {
+    const float4* wt4;
+    const int* start;
+    const int* n4;
+    const int* off4;
+};
+MLXA_D RowBank row_bank_carve(const float* base, int n_bands, long long n_wt) {
+    RowBank r;
+    r.wt4 = reinterpret_cast<const float4*>(base);
+    const int* ip = reinterpret_cast<const int*>(base + n_wt);
+    r.start = ip;
+    r.n4 = ip + n_bands;
+    r.off4 = ip + 2 * n_bands;
+    return r;
+}
+
+template <class P>
+struct MelRows {
+    static constexpr int N = P::N, G = P::G, R0 = P::R0, R1 = P::R1;
+    static_assert(G == 16 && Mirror<P>::OWNERS + 1 <= G, "two groups per warp; one idle lane zeroes the pad rows");
+    static constexpr int THREADS = 512, NG = THREADS / G, TT = 2 * NG;  // 64 frames per tile
+    static constexpr int NBINS = N / 2 + 1;
+    static constexpr int PS = TT + 2;        // floats per row of the power tile (stride == 2 mod 32: conflict-free)
+    static constexpr int PROWS = NBINS + 3;  // + rows the zero-padded weight quads may touch
+    static constexpr int TWP = (P::TW + 1) & ~1;
+    static constexpr int XCH_BYTES = (NG * P::BUF * 8 > PROWS * PS * 4) ? NG * P::BUF * 8 : PROWS * PS * 4;
+    static constexpr int in_floats(int hop) { return ((TT - 1) * hop + N + 8 + 3) & ~3; }
+    static constexpr size_t smem_bytes(int hop, int nbuf, long long bank_words) {
+        return size_t(nbuf) * in_floats(hop) * 4 + size_t(N) * 4 + size_t(TWP) * 8 + size_t(XCH_BYTES) + size_t(bank_words) * 4 + 32;
+    }
+};
+
+template <class P, int PW, bool BANK_SMEM>
+__global__ void __launch_bounds__(512, 1) mel_rows_kernel(const FwdParams p) {
+    using C = MelRows<P>;
+    constexpr int THREADS = C::THREADS, G = C::G, TT = C::TT, N = C::N, R0 = C::R0, R1 = C::R1, PS = C::PS;
+    constexpr int NBINS = C::NBINS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nbuf = p.n_in_buf;
+    const int in_floats = C::in_floats(p.hop);
+    const long long bank_words = BANK_SMEM ? packed_bank_words(p.n_bands, p.n_w4, 1) : 0;
+
+    float* s_in0 = reinterpret_cast<float*>(smem_raw);
+    float* s_win = s_in0 + nbuf * in_floats;
+    float2* s_tw = reinterpret_cast<float2*>(s_win + N);
+    unsigned char* s_x = reinterpret_cast<unsigned char*>(s_tw + C::TWP);
+    float* s_bank = reinterpret_cast<float*>(s_x + C::XCH_BYTES);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bank + bank_words);
+    float* s_pw = reinterpret_cast<float*>(s_x);  // power tile [PROWS][PS], aliases the exchange buffers
+    __shared__ float s_red[THREADS / 32];
+
+    const int tiles_per_clip = (p.T + TT - 1) / TT;
+    TileWalk cur(tiles_per_clip);
+    if (cur.b >= p.B) return;
+
+    const bool cbulk = p.const_bulk != 0;
+    if (threadIdx.x == 0) {
+        mbar_init(s_bar + 0, 1);
+        mbar_init(s_bar + 1, 1);
+        mbar_init(s_bar + 2, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(s_bar + 2, C::TWP * 8 + (cbulk ? N * 4 + uint32_t(bank_words) * 4u : 0u));
+        bulk_copy_g2s(s_tw, p.tw_plan, C::TWP * 8, s_bar + 2);
+        if (cbulk) {
+            bulk_copy_g2s(s_win, p.window, N * 4, s_bar + 2);
+            if (bank_words) bulk_copy_g2s(s_bank, p.bank, uint32_t(bank_words) * 4u, s_bar + 2);
+        }
+        const Tile t = tile_at(p, TT, cur.b, cur.tile);
+        if (t.bulk) {
+            mbar_arrive_expect_tx(s_bar + 0, t.n_bulk * 4);
+            bulk_copy_g2s(s_in0, t.yb + t.src0 - t.lead, t.n_bulk * 4, s_bar + 0);
+        }
+    }
+    if (!cbulk) {
+        for (int i = threadIdx.x; i < N; i += THREADS) s_win[i] = __ldg(p.window + i);
+        for (int i = threadIdx.x; i < (int)bank_words; i += THREADS) s_bank[i] = __ldg(p.bank + i);
+    }
+    const RowBank rb = row_bank_carve(BANK_SMEM ? s_bank : p.bank, p.n_bands, p.n_w4);
+    __syncthreads();
+    mbar_wait(s_bar + 2, 0);
+
+    const int gi = threadIdx.x / G, g = threadIdx.x % G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* buf = reinterpret_cast<float2*>(s_x) + gi * P::BUF;
+    // pass-0 sample offsets: lane g reads element g + 16*r (+16, cyclically, in the odd group of a warp)
+    const int sh = (gi & 1) ? G : 0;
+    const int o_last = (gi & 1) ? -G : G * (R0 - 1);
+    const float pscale = (PW == POW_SQUARE) ? 0.25f : (PW == POW_ABS ? 0.5f : exp2f(-p.power));
+    const float db_ref = fmaxf(p.db_ref, p.db_amin);
+    uint32_t ph0 = 0u, ph1 = 0u;
+    float vmax = 0.f;
+
+    for (int it = 0; cur.b < p.B; ++it, cur.advance()) {
+        const int c = (nbuf == 2) ? (it & 1) : 0;
+        float* s_in = s_in0 + c * in_floats;
+        const Tile ti = tile_at(p, TT, cur.b, cur.tile);
+
+        if (threadIdx.x == 0) {
+            if (nbuf == 2) {
+                TileWalk nxt = cur;
+                nxt.advance();
+                if (nxt.b < p.B) {
+                    const Tile tn = tile_at(p, TT, nxt.b, nxt.tile);
+                    if (tn.bulk) {
+                        mbar_arrive_expect_tx(s_bar + (c ^ 1), tn.n_bulk * 4);
+                        bulk_copy_g2s(s_in0 + (c ^ 1) * in_floats, tn.yb + tn.src0 - tn.lead, tn.n_bulk * 4, s_bar + (c ^ 1));
+                    }
+                }
+            } else if (it > 0 && ti.bulk) {
+                mbar_arrive_expect_tx(s_bar + 0, ti.n_bulk * 4);
+                bulk_copy_g2s(s_in0, ti.yb + ti.src0 - ti.lead, ti.n_bulk * 4, s_bar + 0);
+            }
+        }
+        if (ti.bulk) {
+            mbar_wait(s_bar + c, c ? ph1 : ph0);
+            if (c) ph1 ^= 1u; else ph0 ^= 1u;
+        } else {
+            for (int i = threadIdx.x; i < ti.tile_len; i += THREADS)
+                s_in[i] = load_padded(ti.yb, p.L, ti.src0 + i, p.pad_mode);
+            __syncthreads();
+        }
+        const float* tile = s_in + (ti.bulk ? ti.lead : 0);
+        const int nt = ti.nt;
+
+        // ---- transform of the group's frame pair (f0, f0 + 1) ------------------------------------
+        float2 pp[R1];  // (|.|^p of frame f0, of frame f0 + 1) for the lane's R1 bins, times 1/pscale
+        {
+            const int f0 = 2 * gi;
+            const bool va = f0 < nt, vb = f0 + 1 < nt;  // absent frames ride as copies: finite, never stored
+            const float* sa = tile + (va ? f0 * p.hop : 0) + g + sh;
+            const float* sb = tile + (vb ? (f0 + 1) * p.hop : (va ? f0 * p.hop : 0)) + g + sh;
+            const float* wp = s_win + g + sh;
+            mirror_pass0<P>(g, [&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                const int o = (r == R0 - 1) ? o_last : G * r;
+                const float w = wp[o];
+                return make_float2(sa[o] * w, sb[o] * w);
+            }, buf);
+        }
+        __syncwarp();
+        mirror_last_pass_powers<P, PW>(g, buf, s_tw, p.power, pp);
+        __syncthreads();  // every exchange buffer is dead: the power tile may overwrite them
+
+        // ---- powers -> tile [bin][frame]; bin of leg k: g + R0*k (k < R1/2) or its mirror ---------
+        if (g <= R0 / 2) {
+            float2* lo = reinterpret_cast<float2*>(s_pw) + g * (PS / 2) + gi;
+            float2* hi = reinterpret_cast<float2*>(s_pw) + (R0 - g) * (PS / 2) + gi;
+            static_for<R1>([&](auto k_) {
+                constexpr int k = decltype(k_)::value;
+                if constexpr (k < R1 / 2) lo[R0 * k * (PS / 2)] = pp[k];
+                else hi[R0 * (R1 - 1 - k) * (PS / 2)] = pp[k];
+            });
+        } else if (g == R0 / 2 + 1) {
+            float2* z = reinterpret_cast<float2*>(s_pw) + NBINS * (PS / 2) + gi;
+            z[0] = z[PS / 2] = z[2 * (PS / 2)] = make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+
+        // ---- band-sparse projection, lanes along frames (2 per lane), warps along bands -------------
+        {
+            const int t = 2 * lane;
+            float* outb = p.mel + (long long)ti.b * p.n_bands * p.T + ti.t0 + t;
+            for (int j = 0; j * 16 < p.n_bands; ++j) {
+                const int m = j * 16 + ((j & 1) ? 15 - warp : warp);  // boustrophedon: long and short bands mix
+                if (m >= p.n_bands) continue;
+                const int n4 = rb.n4[m];
+                const float4* w4 = rb.wt4 + rb.off4[m];
+                const float2* q = reinterpret_cast<const float2*>(s_pw) + rb.start[m] * (PS / 2) + lane;
+                float a0 = 0.f, a1 = 0.f;
+                for (int i = 0; i < n4; ++i, q += 4 * (PS / 2)) {
+                    const float4 w = w4[i];
+                    const float2 q0 = q[0], q1 = q[PS / 2], q2 = q[2 * (PS / 2)], q3 = q[3 * (PS / 2)];
+                    a0 = fmaf(w.x, q0.x, a0); a1 = fmaf(w.x, q0.y, a1);
+                    a0 = fmaf(w.y, q1.x, a0); a1 = fmaf(w.y, q1.y, a1);
+                    a0 = fmaf(w.z, q2.x, a0); a1 = fmaf(w.z, q2.y, a1);
+                    a0 = fmaf(w.w, q3.x, a0); a1 = fmaf(w.w, q3.y, a1);
+                }
+                a0 *= pscale;
+                a1 *= pscale;
+                if (t < nt) vmax = fmaxf(vmax, a0);
+                if (t + 1 < nt) vmax = fmaxf(vmax, a1);
+                if (p.db_mode) {
+                    a0 = p.db_coef * log10f(fmaxf(a0, p.db_amin) / db_ref);
+                    a1 = p.db_coef * log10f(fmaxf(a1, p.db_amin) / db_ref);
+                }
+                float* o = outb + (long long)m * p.T;
+                if (t + 1 < nt && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+                    *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
+                } else {
+                    if (t < nt) o[0] = a0;
+                    if (t + 1 < nt) o[1] = a1;
+                }
+            }
+        }
+        __syncthreads();  // power tile consumed: the next tile's transforms may reuse the buffers
+    }
+    if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red);
+}

@@ -1,0 +1,137 @@
+"""CPU oracle for the 'next' rows of SURVEY section 8(f): spectral features and the time-domain
+frame statistics that sit either side of the spectral hot path (TEST INFRASTRUCTURE ONLY).
+
+NumPy restatement of reference ``features.py`` (centroid :57, bandwidth :137, rolloff :274,
+flatness :363, zero_crossing_rate :625) and ``framing.py`` (rms :81, preemphasis :154-295).
+Pinned by tests/golden/reference_features.npz (the reference's own code run on the MLX stand-in).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import spectral as sp
+
+
+def fft_frequencies(sr, n_fft):
+    """features.py:19-21 : linspace(0, sr/2, n_fft//2 + 1) in float32."""
+    return np.linspace(0, sr / 2.0, n_fft // 2 + 1).astype(np.float32)
+
+
+def _spectrogram(y, S, n_fft, hop_length, win_length, window, center, pad_mode, power=1.0, dtype=np.float32):
+    """features.py:24-54 : magnitude STFT (to the given power) unless S is supplied."""
+    if S is not None:
+        return np.asarray(S).astype(dtype)
+    if y is None:
+        raise ValueError("Either y (audio) or S (spectrogram) must be provided")
+    mag = np.abs(sp.stft(y, n_fft, hop_length, win_length, window, center, pad_mode, dtype)).astype(dtype)
+    return np.power(mag, dtype(power)) if power != 1.0 else mag
+
+
+def _batched(S):
+    return (S, True) if S.ndim == 3 else (S[None], False)
+
+
+def spectral_centroid(y=None, sr=22050, S=None, n_fft=2048, hop_length=512, win_length=None, window="hann",
+                      center=True, pad_mode="constant", freq=None, dtype=np.float32):
+    """sum_k f_k S[k] / (sum_k S[k] + 1e-10) per frame (features.py:120-134)."""
+    S, batched = _batched(_spectrogram(y, S, n_fft, hop_length, win_length, window, center, pad_mode, dtype=dtype))
+    f = (fft_frequencies(sr, n_fft) if freq is None else np.asarray(freq)).astype(dtype)
+    out = (f[None, :, None] * S).sum(1, keepdims=True) / (S.sum(1, keepdims=True) + dtype(1e-10))
+    return out if batched else out[0]
+
+
+def spectral_bandwidth(y=None, sr=22050, S=None, n_fft=2048, hop_length=512, win_length=None, window="hann",
+                       center=True, pad_mode="constant", freq=None, centroid=None, p=2.0, norm=True, dtype=np.float32):
+    """(sum S |f - centroid|^p / (sum S + 1e-10))^(1/p) (features.py:226-271)."""
+    S, batched = _batched(_spectrogram(y, S, n_fft, hop_length, win_length, window, center, pad_mode, dtype=dtype))
+    f = (fft_frequencies(sr, n_fft) if freq is None else np.asarray(freq)).astype(dtype)
+    if centroid is None:
+        centroid = spectral_centroid(S=S, sr=sr, n_fft=n_fft, freq=f, dtype=dtype)
+    centroid = np.asarray(centroid).astype(dtype)
+    if centroid.ndim == 2:
+        centroid = centroid[None]
+    dev = np.abs(f[None, :, None] - centroid)
+    w = (S * np.power(dev, dtype(p))).sum(1, keepdims=True)
+    out = np.power(w / (S.sum(1, keepdims=True) + dtype(1e-10)), dtype(1.0 / p)) if norm else np.power(w, dtype(1.0 / p))
+    return out if batched else out[0]
+
+
+def spectral_rolloff(y=None, sr=22050, S=None, n_fft=2048, hop_length=512, win_length=None, window="hann",
+                     center=True, pad_mode="constant", freq=None, roll_percent=0.85, dtype=np.float32):
+    """first bin whose cumulative sum reaches roll_percent of the total (features.py:274-360)."""
+    if not 0.0 <= roll_percent <= 1.0:
+        raise ValueError(f"roll_percent must be >= 0.0, got {roll_percent}" if roll_percent < 0 else
+                         f"roll_percent must be <= 1.0, got {roll_percent}")
+    S, batched = _batched(_spectrogram(y, S, n_fft, hop_length, win_length, window, center, pad_mode, dtype=dtype))
+    f = (fft_frequencies(sr, n_fft) if freq is None else np.asarray(freq)).astype(np.float32)
+    cs = np.cumsum(S, axis=1, dtype=dtype)
+    thr = dtype(roll_percent) * cs[:, -1:, :]
+    idx = np.minimum((cs < thr).sum(1), S.shape[1] - 1)  # searchsorted(side='left') on a non-decreasing sequence
+    out = f[idx][:, None, :].astype(np.float32)
+    return out if batched else out[0]
+
+
+def spectral_flatness(y=None, S=None, n_fft=2048, hop_length=512, win_length=None, window="hann", center=True,
+                      pad_mode="constant", power=2.0, amin=1e-10, dtype=np.float32):
+    """exp(mean log max(S, amin)) / (mean max(S, amin) + 1e-10), S = |X|^power (features.py:430-442)."""
+    S, batched = _batched(_spectrogram(y, S, n_fft, hop_length, win_length, window, center, pad_mode, power, dtype))
+    S = np.maximum(S, dtype(amin))
+    out = np.exp(np.log(S).mean(1, keepdims=True)) / (S.mean(1, keepdims=True) + dtype(1e-10))
+    return out.astype(dtype) if batched else out[0].astype(dtype)
+
+
+def _padded_frames(y, frame_length, hop_length, center, pad_mode):
+    if frame_length <= 0:
+        raise ValueError(f"frame_length must be positive, got {frame_length}")
+    if hop_length <= 0:
+        raise ValueError(f"hop_length must be positive, got {hop_length}")
+    y = np.asarray(y, dtype=np.float32)
+    one_d = y.ndim == 1
+    if one_d:
+        y = y[None]
+    if center:
+        if pad_mode not in ("constant", "edge"):
+            raise ValueError(f"Unknown pad_mode: '{pad_mode}'. Supported: 'constant', 'edge'")
+        y = sp.pad_signal(y, frame_length // 2, pad_mode)
+    return sp.frame_signal(y, frame_length, hop_length), one_d
+
+
+def rms(y, frame_length=2048, hop_length=512, center=True, pad_mode="constant"):
+    """sqrt(mean(frame^2)) -> (B, 1, T) (framing.py:81-151)."""
+    fr, one_d = _padded_frames(y, frame_length, hop_length, center, pad_mode)
+    out = np.sqrt((fr.astype(np.float32) ** 2).mean(-1))[:, None, :].astype(np.float32)
+    return out[0] if one_d else out
+
+
+def zero_crossing_rate(y, frame_length=2048, hop_length=512, center=True, pad_mode="edge"):
+    """mean over the frame of sign(x[i]) != sign(x[i-1]) with sign = (x >= 0); the first sample of a
+    frame never counts (features.py:594-720)."""
+    fr, one_d = _padded_frames(y, frame_length, hop_length, center, pad_mode)
+    s = fr >= 0
+    cross = np.concatenate([np.zeros_like(s[..., :1]), s[..., 1:] != s[..., :-1]], axis=-1)
+    out = cross.astype(np.float32).mean(-1)[:, None, :].astype(np.float32)
+    return out[0] if one_d else out
+
+
+def preemphasis(y, coef=0.97, zi=None, return_zf=False):
+    """y[n] - coef*y[n-1]; first sample y[0] + zi with zi = 2 y[0] - y[1] by default; zf = y[-1]
+    (framing.py:154-295, the default ``use_mlx`` path)."""
+    if not 0.0 <= coef <= 1.0:
+        raise ValueError(f"coef must be in [0, 1], got {coef}")
+    y = np.asarray(y, dtype=np.float32)
+    one_d = y.ndim == 1
+    if one_d:
+        y = y[None]
+    B = y.shape[0]
+    if zi is None:
+        z = 2 * y[:, 0:1] - y[:, 1:2]
+    else:
+        z = np.asarray(zi, dtype=np.float32)
+        z = np.broadcast_to(z.reshape(-1, 1) if z.ndim == 1 and z.shape[0] == B else z.reshape(1, -1)[:, :1], (B, 1))
+    out = y.copy()
+    out[:, 1:] = y[:, 1:] - np.float32(coef) * y[:, :-1]
+    out[:, 0:1] = y[:, 0:1] + z
+    zf = y[:, -1:]
+    if one_d:
+        out, zf = out[0], zf[0]
+    return (out, zf) if return_zf else out

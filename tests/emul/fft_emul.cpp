@@ -4,6 +4,7 @@
 #include <cmath>
 #include <vector>
 #include "fft_plans_list.cuh"
+#include "fft_mirror.cuh"
 #include "pcg64.cuh"
 
 using namespace mlxa;
@@ -42,7 +43,30 @@ static void run_radix(const float2* in, float2* out) {
     for (int i = 0; i < R; ++i) out[dft_perm(R, i)] = v[i];
 }
 
+// mirror-paired power spectra of a frame pair (fft_mirror.cuh), lanes run one after another; rot != 0
+// feeds the frames cyclically rotated by G samples, as the odd lane group of a warp does
+template <class P>
+static void run_mirror(const float* fa, const float* fb, const float* win, int rot, float* pa, float* pb) {
+    using M = Mirror<P>;
+    std::vector<float2> buf(P::BUF, make_float2(0.f, 0.f)), tw(P::TW);
+    fill_plan_twiddles<P>(tw.data());
+    for (int g = 0; g < P::G; ++g)
+        mirror_pass0<P>(g, [&](auto r_) {
+            const int n = (g + P::G * (decltype(r_)::value + (rot ? 1 : 0))) % P::N;
+            return make_float2(fa[n] * win[n], fb[n] * win[n]);
+        }, buf.data());
+    for (int g = 0; g < M::OWNERS; ++g) {
+        float2 pp[P::R1];
+        mirror_last_pass_powers<P, POW_SQUARE>(g, buf.data(), tw.data(), 2.f, pp);
+        for (int k = 0; k < P::R1; ++k) { pa[M::row(g, k)] = pp[k].x; pb[M::row(g, k)] = pp[k].y; }
+    }
+}
+
 extern "C" {
+int emul_mirror_powers_400(const float* fa, const float* fb, const float* win, int rot, float* pa, float* pb) {
+    run_mirror<PlanFor<400>::Plan>(fa, fb, win, rot, pa, pb);
+    return 0;
+}
 // the same __host__ __device__ PCG64 code the device kernel runs, including the per-chunk jump-ahead
 void emul_pcg64_uniform(unsigned long long s_hi, unsigned long long s_lo, unsigned long long i_hi, unsigned long long i_lo,
                         double low, double high, long long n, int chunk, float* out) {

@@ -1,0 +1,47 @@
+"""Golden vectors for the section-8(f) rows (spectral features, rms, zcr, preemphasis): the reference's
+own Python code executed on the MLX stand-in (see generate_golden.py).  Build container only."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "mlx_shim"))
+sys.path.insert(0, "/root/reference")
+import mlx.core as mx  # noqa: E402
+import mlx_audio_primitives as ref  # noqa: E402
+
+A = np.asarray
+g = np.load(os.path.join(HERE, "reference_outputs.npz"))
+y2 = g["stft/input"]  # (2, 6000)
+out = {}
+cases = [dict(n_fft=2048, hop_length=512), dict(n_fft=1024, hop_length=256), dict(n_fft=400, hop_length=160, sr=16000),
+         dict(n_fft=600, hop_length=150)]
+for i, kw in enumerate(cases):
+    sr = kw.get("sr", 22050)
+    k2 = {k: v for k, v in kw.items() if k != "sr"}
+    out[f"centroid/{i}"] = A(ref.spectral_centroid(mx.array(y2), sr=sr, **k2))
+    out[f"bandwidth/{i}"] = A(ref.spectral_bandwidth(mx.array(y2), sr=sr, **k2))
+    out[f"bandwidth_p3/{i}"] = A(ref.spectral_bandwidth(mx.array(y2), sr=sr, p=3.0, norm=False, **k2))
+    out[f"rolloff/{i}"] = A(ref.spectral_rolloff(mx.array(y2), sr=sr, **k2))
+    out[f"rolloff50/{i}"] = A(ref.spectral_rolloff(mx.array(y2), sr=sr, roll_percent=0.5, **k2))
+    out[f"flatness/{i}"] = A(ref.spectral_flatness(mx.array(y2), **k2))
+    out[f"flatness_p1/{i}"] = A(ref.spectral_flatness(mx.array(y2), power=1.0, amin=1e-6, **k2))
+out["ncases"] = np.array(len(cases))
+S = ref.magnitude(ref.stft(mx.array(y2[0]), n_fft=512, hop_length=128))
+out["S1d"] = A(S)
+out["centroid_S1d"] = A(ref.spectral_centroid(S=S, sr=22050, n_fft=512))
+out["rolloff_S1d"] = A(ref.spectral_rolloff(S=S, sr=22050, n_fft=512))
+for (fl, hop, center, mode) in [(2048, 512, True, "constant"), (400, 160, True, "edge"), (256, 64, False, "constant")]:
+    out[f"rms/{fl}/{hop}/{int(center)}/{mode}"] = A(ref.rms(mx.array(y2), fl, hop, center=center, pad_mode=mode))
+    zm = "edge" if mode == "edge" else "constant"
+    out[f"zcr/{fl}/{hop}/{int(center)}/{zm}"] = A(ref.zero_crossing_rate(mx.array(y2), fl, hop, center=center, pad_mode=zm))
+out["rms1d"] = A(ref.rms(mx.array(y2[1]), 1024, 256))
+out["pre/default"] = A(ref.preemphasis(mx.array(y2)))
+o2, zf = ref.preemphasis(mx.array(y2), coef=0.9, zi=mx.array(np.array([0.5, -0.25], np.float32)), return_zf=True)
+out["pre/zi"], out["pre/zf"] = A(o2), A(zf)
+out["pre/1d"] = A(ref.preemphasis(mx.array(y2[0]), coef=0.5))
+np.savez_compressed(os.path.join(HERE, "reference_features.npz"), **out)
+import json  # noqa: E402
+json.dump(cases, open(os.path.join(HERE, "feature_cases.json"), "w"))
+print("wrote", len(out), "arrays")

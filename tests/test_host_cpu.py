@@ -22,7 +22,7 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in mlxa_cuda.h but not exported"
     assert declared - {"mlxa_last_error", "mlxa_packed_bank_words"} == set(ext.SIGNATURES), "host-layer signature table out of sync"
-    assert ext._ext.mlxa_plan_group(400) == 16 and ext._ext.mlxa_plan_group(2048) == 32 and ext._ext.mlxa_plan_group(777) == 32
+    assert ext._ext.mlxa_plan_group(400) == 1 and ext._ext.mlxa_plan_group(2048) == 32 and ext._ext.mlxa_plan_group(777) == 32
     assert ext._ext.mlxa_abi_version() == ext.ABI_VERSION
     assert ext._ext.mlxa_has_fast_plan(400) == 1 and ext._ext.mlxa_has_fast_plan(2048) == 1
     assert ext._ext.mlxa_has_fast_plan(600) == 0
@@ -48,7 +48,14 @@ def test_host_constants_match_reference_fixtures(golden):
             norm = None if parts[7] == "None" else parts[7]
             fb = mel_filterbank_host(sr, n_fft, n_mels, fmin, fmax, bool(int(parts[6])), norm)
             assert np.array_equal(fb, golden[key]), key
-            # the packed band-sparse form (what the kernels consume) reproduces the dense matrix exactly
+            # the packed band-sparse forms (what the kernels consume) reproduce the dense matrix exactly
+            packed, n_wt = pack_bank_host(fb, 1)  # row format: quad-padded runs
+            ints = packed[n_wt:].view(np.int32)
+            start, n4, off4 = ints[:n_mels], ints[n_mels:2 * n_mels], ints[2 * n_mels:3 * n_mels]
+            dense = np.zeros((n_mels, fb.shape[1] + 3), np.float32)
+            for m in range(n_mels):
+                dense[m, start[m]:start[m] + 4 * n4[m]] = packed[4 * off4[m]:4 * (off4[m] + n4[m])]
+            assert n_wt % 4 == 0 and np.array_equal(dense[:, :fb.shape[1]], fb) and not dense[:, fb.shape[1]:].any()
             for group in (16, 32):
                 packed, n_wt = pack_bank_host(fb, group)
                 n_groups = -(-n_mels // group)
@@ -138,6 +145,22 @@ def test_plan_fft_emulated(emul, n_fft):
     assert emul.emul_plan_fft(n_fft, _c(x), _c(out)) == 0
     ref = np.fft.fft(x.astype(np.complex128))
     assert np.abs(out - ref).max() <= 5e-7 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("rot", [0, 1])
+def test_mirror_paired_powers_emulated(emul, rot):
+    """fft_mirror.cuh (the n_fft = 400 mel kernel's transform): both members of every Hermitian pair come
+    out of one lane's registers, so |Xa|^2, |Xb|^2 of a frame pair need no unpack; with the frames fed
+    cyclically rotated (odd lane group) the powers are unchanged."""
+    rng = np.random.default_rng(400 + rot)
+    fa, fb = rng.standard_normal((2, 400)).astype(np.float32)
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(400) / 400)).astype(np.float32)
+    pa, pb = np.full(201, np.nan, np.float32), np.full(201, np.nan, np.float32)
+    assert emul.emul_mirror_powers_400(_c(fa), _c(fb), _c(win), rot, _c(pa), _c(pb)) == 0
+    for got, fr in ((pa, fa), (pb, fb)):
+        ref = 4.0 * np.abs(np.fft.rfft(fr.astype(np.float64) * win)) ** 2
+        assert np.isfinite(got).all()  # every bin 0..200 was produced by some lane
+        assert np.abs(got - ref).max() <= 2e-6 * ref.max()
 
 
 @pytest.mark.parametrize("seed", [0, 1, 42, 2**40 + 7])
