@@ -90,9 +90,8 @@ int mlxa_plan_group(int n_fft);
  * padded to mlxa_packed_bank_words(n_bands, n_wt, group) words (a multiple of 4).
  * ROW format (group == 1; the projection runs with lanes along frames, weights are warp-uniform):
  *     float   wt[n_wt]          every band's contiguous run, zero-padded to whole quads (16-byte units)
- *     int32   start[n_bands]    first frequency bin of the run
- *     int32   n4[n_bands]       quads in the run
- *     int32   off4[n_bands]     first quad of the run (wt + 4*off4)
+ *     int32   desc[n_bands][4]  {first frequency bin of the run, quads in the run, first quad of the
+ *                               run (wt + 4*off4), support length in bins}
  * The kernels
  * bulk-copy this blob into shared memory once per CTA.  mlxa_pack_filterbank builds it on the
  * HOST from a dense (n_bands, F) row-major matrix (rows must have contiguous support, which

@@ -237,7 +237,7 @@ int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, int group,
         for (int m = 0; m < n_bands; ++m)
             std::memcpy(packed_host + 4 * (int64_t)off4[m], dense_host + (int64_t)m * F + start[m], sizeof(float) * len[m]);
         int32_t* ip = reinterpret_cast<int32_t*>(packed_host + total);
-        for (int m = 0; m < n_bands; ++m) { ip[m] = start[m]; ip[n_bands + m] = (len[m] + 3) / 4; ip[2 * n_bands + m] = off4[m]; }
+        for (int m = 0; m < n_bands; ++m) { ip[4 * m] = start[m]; ip[4 * m + 1] = (len[m] + 3) / 4; ip[4 * m + 2] = off4[m]; ip[4 * m + 3] = len[m]; }
         return 0;
     }
     const int n_groups = (n_bands + group - 1) / group;

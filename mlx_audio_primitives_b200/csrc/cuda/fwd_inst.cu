@@ -59,10 +59,14 @@ __host__ __device__ inline SmemLayout smem_layout(int ep, int NG, int hop, int T
     return s;
 }
 
-// geometry of one work item
+// Geometry of one work item.  The tile's samples src0 .. src0 + tile_len (clip coordinates; negative or
+// >= L where the centre padding applies) sit in a staging buffer at [lead, lead + tile_len), lead chosen
+// so that smem and global addresses agree mod 16 bytes.  The part of the tile that exists in the clip is
+// fetched by ONE bulk async copy (16-byte units: it may start up to 3 samples before the tile and end up
+// to 3 after); only the nl leading / nr trailing samples outside it -- the padding of a clip's first and
+// last tiles -- are filled by index arithmetic.
 struct Tile {
-    int b, t0, nt, tile_len, src0, lead, n_bulk;
-    bool bulk;
+    int b, t0, nt, tile_len, src0, lead, bulk_lo, n_bulk, nl, nr;
     const float* yb;
 };
 MLXA_D Tile tile_at(const FwdParams& p, int TT, int b, int tile) {
@@ -73,13 +77,40 @@ MLXA_D Tile tile_at(const FwdParams& p, int TT, int b, int tile) {
     t.tile_len = (t.nt - 1) * p.hop + NFFT;
     t.yb = p.y + (long long)t.b * p.ldy;
     t.src0 = t.t0 * p.hop - p.pad;
-    // interior tile: every sample exists -> one bulk async copy from the 16-byte aligned address at
-    // or below the first sample ("lead" extra floats in front)
-    t.lead = int((reinterpret_cast<uintptr_t>(t.yb + t.src0) & 15) >> 2);
-    t.n_bulk = round_up4(t.lead + t.tile_len);
-    t.bulk = (t.src0 - t.lead >= 0) && (t.src0 - t.lead + t.n_bulk <= p.L) && ((reinterpret_cast<uintptr_t>(t.yb) & 3) == 0);
+    const int a0 = int((reinterpret_cast<uintptr_t>(t.yb) >> 2) & 3);
+    t.lead = (a0 + t.src0) & 3;
+    const int e = t.src0 + t.tile_len;
+    int lo = t.src0 - t.lead;                    // aligned at or below the first sample ...
+    if (lo < 0) lo = (-a0) & 3;                  // ... or the first aligned sample of the clip
+    int hi = e + ((-(a0 + e)) & 3);              // aligned at or above the end ...
+    if (hi > p.L) hi = p.L - ((a0 + p.L) & 3);   // ... or the last aligned position inside the clip
+    if (hi <= lo || (reinterpret_cast<uintptr_t>(t.yb) & 3)) {
+        t.n_bulk = 0; t.bulk_lo = 0; t.nl = t.tile_len; t.nr = 0;
+    } else {
+        t.n_bulk = hi - lo;
+        t.bulk_lo = lo - t.src0;
+        t.nl = max(0, lo - t.src0);
+        t.nr = max(0, e - hi);
+    }
     return t;
 }
+// one thread: start the tile's bulk copy into staging buffer s_in
+MLXA_D void tile_issue_bulk(const Tile& t, float* s_in, uint64_t* bar) {
+    if (t.n_bulk > 0) {
+        mbar_arrive_expect_tx(bar, t.n_bulk * 4);
+        bulk_copy_g2s(s_in + t.lead + t.bulk_lo, t.yb + t.src0 + t.bulk_lo, t.n_bulk * 4, bar);
+    }
+}
+// all threads: the samples the bulk copy does not cover (padding rules of pad_signal.metal:11-92)
+template <int THREADS>
+MLXA_D void tile_fill_edges(const FwdParams& p, const Tile& t, float* s_in) {
+    const int n = t.nl + t.nr;
+    for (int i = threadIdx.x; i < n; i += THREADS) {
+        const int s = (i < t.nl) ? i : t.tile_len - t.nr + (i - t.nl);
+        s_in[t.lead + s] = load_padded(t.yb, p.L, t.src0 + s, p.pad_mode);
+    }
+}
+
 // A persistent CTA's walk over the (clip, tile) items blockIdx.x, blockIdx.x + gridDim.x, ...: one
 // 32-bit division per kernel, then add-and-carry per step.
 struct TileWalk {
@@ -140,11 +171,7 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
             bulk_copy_g2s(s_win, p.window, NFFT * 4, s_bar + 2);
             if (EP == EP_MEL && mel_bytes) bulk_copy_g2s(s_mel, p.bank, mel_bytes, s_bar + 2);
         }
-        const Tile t = tile_at(p, TT, cur.b, cur.tile);
-        if (t.bulk) {
-            mbar_arrive_expect_tx(s_bar + 0, t.n_bulk * 4);
-            bulk_copy_g2s(s_in0, t.yb + t.src0 - t.lead, t.n_bulk * 4, s_bar + 0);
-        }
+        tile_issue_bulk(tile_at(p, TT, cur.b, cur.tile), s_in0, s_bar + 0);
     }
     if (!cbulk) {
         for (int i = threadIdx.x; i < NFFT; i += THREADS) s_win[i] = __ldg(p.window + i);
@@ -174,27 +201,20 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
             if (nbuf == 2) {
                 TileWalk nxt = cur;
                 nxt.advance();
-                if (nxt.b < p.B) {
-                    const Tile tn = tile_at(p, TT, nxt.b, nxt.tile);
-                    if (tn.bulk) {
-                        mbar_arrive_expect_tx(s_bar + (c ^ 1), tn.n_bulk * 4);
-                        bulk_copy_g2s(s_in0 + (c ^ 1) * lay.in_floats, tn.yb + tn.src0 - tn.lead, tn.n_bulk * 4, s_bar + (c ^ 1));
-                    }
-                }
-            } else if (it > 0 && ti.bulk) {
-                mbar_arrive_expect_tx(s_bar + 0, ti.n_bulk * 4);
-                bulk_copy_g2s(s_in0, ti.yb + ti.src0 - ti.lead, ti.n_bulk * 4, s_bar + 0);
+                if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0 + (c ^ 1) * lay.in_floats, s_bar + (c ^ 1));
+            } else if (it > 0) {
+                tile_issue_bulk(ti, s_in0, s_bar + 0);
             }
         }
-        if (ti.bulk) {
-            mbar_wait(s_bar + c, c ? ph1 : ph0);
-            if (c) ph1 ^= 1u; else ph0 ^= 1u;
-        } else {
-            for (int i = threadIdx.x; i < ti.tile_len; i += THREADS)
-                s_in[i] = load_padded(ti.yb, p.L, ti.src0 + i, p.pad_mode);
+        if (ti.nl + ti.nr) {  // CTA-uniform: a clip's first / last tile
+            tile_fill_edges<THREADS>(p, ti, s_in);
             __syncthreads();
         }
-        const int in_off = ti.bulk ? ti.lead : 0;
+        if (ti.n_bulk > 0) {
+            mbar_wait(s_bar + c, c ? ph1 : ph0);
+            if (c) ph1 ^= 1u; else ph0 ^= 1u;
+        }
+        const int in_off = ti.lead;
         const bool even_off = (((p.hop | in_off) & 1) == 0);
         const float* tile = s_in + in_off;
         const int b = ti.b, t0 = ti.t0, nt = ti.nt;

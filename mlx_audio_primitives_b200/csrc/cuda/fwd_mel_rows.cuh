@@ -20,20 +20,16 @@
 //
 // Included by fwd_inst.cu INSIDE its per-translation-unit namespace, after Tile / tile_info.
 
-// bank packed in ROW format (mlxa_plan_group == 1, see include/mlxa_cuda.h)
+// bank packed in ROW format (mlxa_plan_group == 1, see include/mlxa_cuda.h): quad-padded weight runs, then
+// one int4 {start, n4, off4, len} per band
 struct RowBank {
     const float4* wt4;
-    const int* start;
-    const int* n4;
-    const int* off4;
+    const int4* desc;
 };
-MLXA_D RowBank row_bank_carve(const float* base, int n_bands, long long n_wt) {
+MLXA_D RowBank row_bank_carve(const float* base, long long n_wt) {
     RowBank r;
     r.wt4 = reinterpret_cast<const float4*>(base);
-    const int* ip = reinterpret_cast<const int*>(base + n_wt);
-    r.start = ip;
-    r.n4 = ip + n_bands;
-    r.off4 = ip + 2 * n_bands;
+    r.desc = reinterpret_cast<const int4*>(base + n_wt);
     return r;
 }
 
@@ -90,17 +86,13 @@ __global__ void __launch_bounds__(512, 1) mel_rows_kernel(const FwdParams p) {
             bulk_copy_g2s(s_win, p.window, N * 4, s_bar + 2);
             if (bank_words) bulk_copy_g2s(s_bank, p.bank, uint32_t(bank_words) * 4u, s_bar + 2);
         }
-        const Tile t = tile_at(p, TT, cur.b, cur.tile);
-        if (t.bulk) {
-            mbar_arrive_expect_tx(s_bar + 0, t.n_bulk * 4);
-            bulk_copy_g2s(s_in0, t.yb + t.src0 - t.lead, t.n_bulk * 4, s_bar + 0);
-        }
+        tile_issue_bulk(tile_at(p, TT, cur.b, cur.tile), s_in0, s_bar + 0);
     }
     if (!cbulk) {
         for (int i = threadIdx.x; i < N; i += THREADS) s_win[i] = __ldg(p.window + i);
         for (int i = threadIdx.x; i < (int)bank_words; i += THREADS) s_bank[i] = __ldg(p.bank + i);
     }
-    const RowBank rb = row_bank_carve(BANK_SMEM ? s_bank : p.bank, p.n_bands, p.n_w4);
+    const RowBank rb = row_bank_carve(BANK_SMEM ? s_bank : p.bank, p.n_w4);
     __syncthreads();
     mbar_wait(s_bar + 2, 0);
 
@@ -124,27 +116,20 @@ __global__ void __launch_bounds__(512, 1) mel_rows_kernel(const FwdParams p) {
             if (nbuf == 2) {
                 TileWalk nxt = cur;
                 nxt.advance();
-                if (nxt.b < p.B) {
-                    const Tile tn = tile_at(p, TT, nxt.b, nxt.tile);
-                    if (tn.bulk) {
-                        mbar_arrive_expect_tx(s_bar + (c ^ 1), tn.n_bulk * 4);
-                        bulk_copy_g2s(s_in0 + (c ^ 1) * in_floats, tn.yb + tn.src0 - tn.lead, tn.n_bulk * 4, s_bar + (c ^ 1));
-                    }
-                }
-            } else if (it > 0 && ti.bulk) {
-                mbar_arrive_expect_tx(s_bar + 0, ti.n_bulk * 4);
-                bulk_copy_g2s(s_in0, ti.yb + ti.src0 - ti.lead, ti.n_bulk * 4, s_bar + 0);
+                if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0 + (c ^ 1) * in_floats, s_bar + (c ^ 1));
+            } else if (it > 0) {
+                tile_issue_bulk(ti, s_in0, s_bar + 0);
             }
         }
-        if (ti.bulk) {
-            mbar_wait(s_bar + c, c ? ph1 : ph0);
-            if (c) ph1 ^= 1u; else ph0 ^= 1u;
-        } else {
-            for (int i = threadIdx.x; i < ti.tile_len; i += THREADS)
-                s_in[i] = load_padded(ti.yb, p.L, ti.src0 + i, p.pad_mode);
+        if (ti.nl + ti.nr) {  // CTA-uniform: a clip's first / last tile
+            tile_fill_edges<THREADS>(p, ti, s_in);
             __syncthreads();
         }
-        const float* tile = s_in + (ti.bulk ? ti.lead : 0);
+        if (ti.n_bulk > 0) {
+            mbar_wait(s_bar + c, c ? ph1 : ph0);
+            if (c) ph1 ^= 1u; else ph0 ^= 1u;
+        }
+        const float* tile = s_in + ti.lead;
         const int nt = ti.nt;
 
         // ---- transform of the group's frame pair (f0, f0 + 1) ------------------------------------
@@ -184,36 +169,42 @@ __global__ void __launch_bounds__(512, 1) mel_rows_kernel(const FwdParams p) {
         // ---- band-sparse projection, lanes along frames (2 per lane), warps along bands -------------
         {
             const int t = 2 * lane;
+            const bool ok0 = t < nt, ok1 = t + 1 < nt;
             float* outb = p.mel + (long long)ti.b * p.n_bands * p.T + ti.t0 + t;
+            const float2* q_lane = reinterpret_cast<const float2*>(s_pw) + lane;
+#pragma unroll 1
             for (int j = 0; j * 16 < p.n_bands; ++j) {
                 const int m = j * 16 + ((j & 1) ? 15 - warp : warp);  // boustrophedon: long and short bands mix
-                if (m >= p.n_bands) continue;
-                const int n4 = rb.n4[m];
-                const float4* w4 = rb.wt4 + rb.off4[m];
-                const float2* q = reinterpret_cast<const float2*>(s_pw) + rb.start[m] * (PS / 2) + lane;
-                float a0 = 0.f, a1 = 0.f;
-                for (int i = 0; i < n4; ++i, q += 4 * (PS / 2)) {
-                    const float4 w = w4[i];
-                    const float2 q0 = q[0], q1 = q[PS / 2], q2 = q[2 * (PS / 2)], q3 = q[3 * (PS / 2)];
-                    a0 = fmaf(w.x, q0.x, a0); a1 = fmaf(w.x, q0.y, a1);
-                    a0 = fmaf(w.y, q1.x, a0); a1 = fmaf(w.y, q1.y, a1);
-                    a0 = fmaf(w.z, q2.x, a0); a1 = fmaf(w.z, q2.y, a1);
-                    a0 = fmaf(w.w, q3.x, a0); a1 = fmaf(w.w, q3.y, a1);
-                }
-                a0 *= pscale;
-                a1 *= pscale;
-                if (t < nt) vmax = fmaxf(vmax, a0);
-                if (t + 1 < nt) vmax = fmaxf(vmax, a1);
-                if (p.db_mode) {
-                    a0 = p.db_coef * log10f(fmaxf(a0, p.db_amin) / db_ref);
-                    a1 = p.db_coef * log10f(fmaxf(a1, p.db_amin) / db_ref);
-                }
-                float* o = outb + (long long)m * p.T;
-                if (t + 1 < nt && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
-                    *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
-                } else {
-                    if (t < nt) o[0] = a0;
-                    if (t + 1 < nt) o[1] = a1;
+                if (m < p.n_bands) {
+                    const int4 d = rb.desc[m];  // start, quads, first quad
+                    const float4* w4 = rb.wt4 + d.z;
+                    const float2* q = q_lane + d.x * (PS / 2);
+                    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 1
+                    for (int i = 0; i < d.y; ++i, q += 4 * (PS / 2)) {
+                        const float4 w = w4[i];
+                        const float2 q0 = q[0], q1 = q[PS / 2], q2 = q[2 * (PS / 2)], q3 = q[3 * (PS / 2)];
+                        a0 = fmaf(w.x, q0.x, a0); a1 = fmaf(w.x, q0.y, a1);
+                        a0 = fmaf(w.y, q1.x, a0); a1 = fmaf(w.y, q1.y, a1);
+                        a0 = fmaf(w.z, q2.x, a0); a1 = fmaf(w.z, q2.y, a1);
+                        a0 = fmaf(w.w, q3.x, a0); a1 = fmaf(w.w, q3.y, a1);
+                    }
+                    a0 *= pscale;
+                    a1 *= pscale;
+                    if (ok0) vmax = fmaxf(vmax, a0);
+                    if (ok1) vmax = fmaxf(vmax, a1);
+                    if (p.db_mode) {
+                        a0 = p.db_coef * log10f(fmaxf(a0, p.db_amin) / db_ref);
+                        a1 = p.db_coef * log10f(fmaxf(a1, p.db_amin) / db_ref);
+                    }
+                    float* o = outb + (long long)m * p.T;
+                    if ((reinterpret_cast<uintptr_t>(o) & 7) == 0) {  // warp-uniform
+                        if (ok1) *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
+                        else if (ok0) o[0] = a0;
+                    } else {
+                        if (ok0) o[0] = a0;
+                        if (ok1) o[1] = a1;
+                    }
                 }
             }
         }

@@ -44,9 +44,9 @@ struct FwdParams {
 };
 
 // 32-bit words of a packed band-sparse filterbank (layout: fwd_epilogue.cuh / mlxa_cuda.h)
-// group == 1 is the ROW format (fwd_mel_rows.cuh): [wt][start][n4][off4]
+// group == 1 is the ROW format (fwd_mel_rows.cuh): [wt][int4 {start, n4, off4, len} per band]
 __host__ __device__ inline long long packed_bank_words(int n_bands, long long n_wt, int group) {
-    if (group == 1) return (n_wt + 3LL * n_bands + 3) & ~3LL;
+    if (group == 1) return n_wt + 4LL * n_bands;
     return (n_wt + 2LL * n_bands + 2LL * ((n_bands + group - 1) / group) + 3) & ~3LL;
 }
 

@@ -50,8 +50,8 @@ def test_host_constants_match_reference_fixtures(golden):
             assert np.array_equal(fb, golden[key]), key
             # the packed band-sparse forms (what the kernels consume) reproduce the dense matrix exactly
             packed, n_wt = pack_bank_host(fb, 1)  # row format: quad-padded runs
-            ints = packed[n_wt:].view(np.int32)
-            start, n4, off4 = ints[:n_mels], ints[n_mels:2 * n_mels], ints[2 * n_mels:3 * n_mels]
+            start, n4, off4, ln = packed[n_wt:].view(np.int32).reshape(n_mels, 4).T
+            assert packed.size == n_wt + 4 * n_mels and np.array_equal(n4, (ln + 3) // 4)
             dense = np.zeros((n_mels, fb.shape[1] + 3), np.float32)
             for m in range(n_mels):
                 dense[m, start[m]:start[m] + 4 * n4[m]] = packed[4 * off4[m]:4 * (off4[m] + n4[m])]
