@@ -327,7 +327,7 @@ def main():
     achieved = bytes_clip * B / (k_ms * 1e-3) / 1e9
     fl_ach = flops_clip * B / (k_ms * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": f"fwd_kernel<EP_MEL> n_fft={w['n_fft']}", "kernel_ms": k_ms,
+                "traffic": None, "kernel": ("mel_rows_kernel" if w["n_fft"] == 400 else "fwd_kernel<EP_MEL>") + f" n_fft={w['n_fft']}", "kernel_ms": k_ms,
                 "kernel_ms_min": min(kern_ms), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_clip * B, "algorithmic_flops_per_launch": flops_clip * B,
                 "fp32": {"achieved_tflops": fl_ach, "peak_measured_tflops": fp32_measured,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MLXA_ABI_VERSION 1
+#define MLXA_ABI_VERSION 2
 
 #define MLXA_E_INVALID (-1)   /* bad size / null pointer / unknown mode            */
 #define MLXA_E_UNSUPPORTED (-2)
@@ -107,12 +107,16 @@ int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, int group,
  * mel (B, n_bands, T).  gmax (optional, may be NULL): device float, atomically raised to
  * max(mel) -- the producer side of power_to_db(ref=max / top_db) (convert.py:42-58).
  * db_mode != 0 writes db_coef*log10(max(v, db_amin)/max(db_ref, db_amin)) instead of v
- * (the no-global-max form of convert.py:48-52). */
+ * (the no-global-max form of convert.py:48-52).
+ * block_min (optional, may be NULL): (B, ceil(T / MLXA_MIN_BLOCK_FRAMES)) device floats the caller
+ * initialised to +inf; each slot is atomically lowered to the smallest raw mel value of that 64-frame
+ * block of the clip -- what mlxa_db_floor_blocks_f32 needs to skip blocks the top_db floor cannot touch. */
+#define MLXA_MIN_BLOCK_FRAMES 64
 int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window,
                      int n_fft, int hop, int center, int pad_mode, float power,
                      const float* bank, int n_bands, int64_t n_wt,
                      float* mel, float* gmax, int db_mode, float db_coef, float db_amin,
-                     float db_ref, void* stream);
+                     float db_ref, float* block_min, void* stream);
 
 /* irFFT -> window -> gather overlap-add -> / max(sum w^2, 1e-8) -> trim in one kernel
  * (replaces stft.py:292-338 = mx.fft.irfft -> _ext.overlap_add -> slices).
@@ -173,6 +177,21 @@ int mlxa_fill_f32(float* x, int64_t n, float value, void* stream);
 int mlxa_to_db_f32(const float* x, int64_t n, float coef, float amin, float ref_host,
                    const float* ref_dev, int use_top_db, float top_db, const float* gmax_dev,
                    float* out, float* reset_next, void* stream);
+/* Second half of a fused log-mel (convert.py:55-58 alone): x_db already holds coef*log10(max(S, amin)/
+ * max(ref, amin)) -- mlxa_melspec_f32 with db_mode != 0 and gmax -- and is raised in place to
+ * max(x_db) - top_db, max(x_db) derived from the peak *gmax_dev of S.  Read-mostly: only values below the
+ * floor are written.  Bit-identical to mlxa_to_db_f32 on the raw mel values.  reset_next as above. */
+int mlxa_db_floor_f32(float* x_db, int64_t n, float coef, float amin, float ref, float top_db,
+                      const float* gmax_dev, float* reset_next, void* stream);
+/* The same floor, block-wise: x_db (B, n_bands, T) with the producer's block_min.  A 64-frame block of a
+ * clip whose minimum already clears the floor is skipped entirely, so the pass costs B*ceil(T/64) reads
+ * unless the material really spans top_db of dynamic range.  Consumed block_min slots are reset to +inf.
+ * raised (optional, 1 + B*ceil(T/64) device int32, raised[0] zeroed by the caller): raised[0] counts the
+ * rewritten blocks, raised[1..] lists them as b*ceil(T/64) + block (any order).  Same bits as
+ * mlxa_to_db_f32 / mlxa_db_floor_f32. */
+int mlxa_db_floor_blocks_f32(float* x_db, int64_t B, int n_bands, int64_t T, float coef, float amin,
+                             float ref, float top_db, const float* gmax_dev, float* block_min,
+                             float* reset_next, int32_t* raised, void* stream);
 /* convert.py:100-129,169-198: out = ref * 10^(x/div) */
 int mlxa_from_db_f32(const float* x, int64_t n, float ref, float div, float* out, void* stream);
 

@@ -263,7 +263,8 @@ int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, int group,
 
 int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window, int n_fft, int hop,
                      int center, int pad_mode, float power, const float* bank, int n_bands, int64_t n_w4, float* mel,
-                     float* gmax, int db_mode, float db_coef, float db_amin, float db_ref, void* stream) {
+                     float* gmax, int db_mode, float db_coef, float db_amin, float db_ref, float* block_min,
+                     void* stream) {
     CHECK_ARG(bank && mel, "null pointer");
     CHECK_ARG(n_bands > 0 && n_w4 >= 0 && n_w4 < (1LL << 22), "bad filterbank size");  // n_w4 = n_wt words
     return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
@@ -276,6 +277,8 @@ int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const fl
         p.const_bulk = (((uintptr_t)bank | (uintptr_t)window) & 15) == 0;
         p.mel = mel + b0 * (int64_t)n_bands * p.T;
         p.gmax = gmax;
+        p.blocks_per_clip = (int)((p.T + MLXA_MIN_BLOCK_FRAMES - 1) / MLXA_MIN_BLOCK_FRAMES);
+        p.block_min = block_min ? block_min + b0 * p.blocks_per_clip : nullptr;
         p.db_mode = db_mode; p.db_coef = db_coef; p.db_amin = db_amin; p.db_ref = db_ref;
         CHECK_CUDA(dispatch_fwd(EP_MEL, p, (cudaStream_t)stream), "melspec");
         return 0;
@@ -414,6 +417,20 @@ int mlxa_to_db_f32(const float* x, int64_t n, float coef, float amin, float ref_
     CHECK_CUDA(run_to_db(x, n, coef, amin, ref_host, ref_dev, use_top_db, top_db, gmax_dev, out, reset_next, (cudaStream_t)stream), "to_db");
     return 0;
 }
+int mlxa_db_floor_f32(float* x_db, int64_t n, float coef, float amin, float ref, float top_db, const float* gmax_dev,
+                      float* reset_next, void* stream) {
+    CHECK_ARG(x_db && gmax_dev && n > 0 && top_db > 0, "bad argument");
+    CHECK_CUDA(run_db_floor(x_db, n, coef, amin, ref, top_db, gmax_dev, reset_next, (cudaStream_t)stream), "db_floor");
+    return 0;
+}
+int mlxa_db_floor_blocks_f32(float* x_db, int64_t B, int n_bands, int64_t T, float coef, float amin, float ref,
+                             float top_db, const float* gmax_dev, float* block_min, float* reset_next, int32_t* n_raised,
+                             void* stream) {
+    CHECK_ARG(x_db && gmax_dev && block_min && B > 0 && B <= 65535 && n_bands > 0 && T > 0 && top_db > 0, "bad argument");
+    CHECK_CUDA(run_db_floor_blocks(x_db, B, n_bands, T, coef, amin, ref, top_db, gmax_dev, block_min, reset_next, n_raised,
+                                   (cudaStream_t)stream), "db_floor_blocks");
+    return 0;
+}
 int mlxa_from_db_f32(const float* x, int64_t n, float ref, float div, float* out, void* stream) {
     CHECK_ARG(x && out && n > 0 && div != 0.f, "bad argument");
     CHECK_CUDA(run_from_db(x, n, ref, div, out, (cudaStream_t)stream), "from_db");
@@ -450,8 +467,9 @@ struct HostWorkspace {
     cudaStream_t st[NS] = {};
     cudaEvent_t done[NS] = {};
     bool init = false;
-    float *d_y = nullptr, *d_mel = nullptr, *d_win = nullptr, *d_bank = nullptr, *d_gmax = nullptr;
-    size_t cap_y = 0, cap_mel = 0, cap_win = 0, cap_bank = 0;
+    float *d_y = nullptr, *d_mel = nullptr, *d_win = nullptr, *d_bank = nullptr, *d_gmax = nullptr, *d_bmin = nullptr;
+    int *d_raised = nullptr, *h_raised = nullptr;  // count + list of the blocks the top_db floor had to rewrite
+    size_t cap_y = 0, cap_mel = 0, cap_win = 0, cap_bank = 0, cap_bmin = 0, cap_raised = 0;
 };
 std::map<int, HostWorkspace> g_ws;
 std::mutex g_ws_mu;
@@ -497,15 +515,38 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
     CHECK_CUDA(grow(&ws.d_mel, &ws.cap_mel, (size_t)B * n_bands * T), "malloc mel");
     CHECK_CUDA(grow(&ws.d_win, &ws.cap_win, (size_t)n_fft), "malloc window");
     CHECK_CUDA(grow(&ws.d_bank, &ws.cap_bank, (size_t)bank_words), "malloc bank");
+    // ref a constant: the mel kernel writes dB itself.  With top_db the result is then final except where
+    // a value lies more than top_db below the batch peak -- rare -- so every chunk is copied back
+    // speculatively right behind its kernel (D2H overlaps the remaining H2D), the block-wise floor pass runs
+    // once the peak is known, and only chunks in which it had to rewrite something are copied again.
+    const bool fuse_db = apply_db && !ref_is_max;
+    const bool speculate = fuse_db && use_top_db;
+    const int64_t nblk = (T + MLXA_MIN_BLOCK_FRAMES - 1) / MLXA_MIN_BLOCK_FRAMES;
+    if (speculate) {
+        CHECK_CUDA(grow(&ws.d_bmin, &ws.cap_bmin, (size_t)B * nblk), "malloc block minima");
+        if ((size_t)(1 + B * nblk) > ws.cap_raised) {
+            if (ws.h_raised) cudaFreeHost(ws.h_raised);
+            ws.h_raised = nullptr;
+            CHECK_CUDA(cudaHostAlloc(&ws.h_raised, sizeof(int) * (size_t)(1 + B * nblk), cudaHostAllocDefault), "host list");
+        }
+        CHECK_CUDA(grow(&ws.d_raised, &ws.cap_raised, (size_t)(1 + B * nblk)), "malloc list");
+    }
     cudaStream_t s0 = ws.st[0];
     CHECK_CUDA(cudaMemcpyAsync(ws.d_win, window_host, sizeof(float) * n_fft, cudaMemcpyHostToDevice, s0), "copy window");
     CHECK_CUDA(cudaMemcpyAsync(ws.d_bank, bank_host, sizeof(float) * bank_words, cudaMemcpyHostToDevice, s0), "copy bank");
     CHECK_CUDA(cudaMemsetAsync(ws.d_gmax, 0, sizeof(float), s0), "memset");
+    if (speculate) {
+        CHECK_CUDA(cudaMemsetAsync(ws.d_raised, 0, sizeof(int), s0), "memset");
+        CHECK_CUDA(run_fill(ws.d_bmin, B * nblk, INFINITY, s0), "fill block minima");
+    }
     CHECK_CUDA(cudaEventRecord(ws.done[0], s0), "event");
     for (int i = 1; i < NS; ++i) CHECK_CUDA(cudaStreamWaitEvent(ws.st[i], ws.done[0], 0), "wait");
     const int64_t chunk = std::max<int64_t>(1, (B + 7) / 8);
-    const bool fuse_db = apply_db && !need_max;
     const int64_t mel_per_clip = (int64_t)n_bands * T;
+    auto d2h = [&](int64_t b0, int64_t nb, cudaStream_t s) {
+        return cudaMemcpyAsync(out_host + b0 * mel_per_clip, ws.d_mel + b0 * mel_per_clip,
+                               sizeof(float) * (size_t)nb * mel_per_clip, cudaMemcpyDeviceToHost, s);
+    };
     int ci = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk, ++ci) {
         const int64_t nb = std::min(chunk, B - b0);
@@ -513,11 +554,9 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
         CHECK_CUDA(cudaMemcpyAsync(ws.d_y + b0 * L, y_host + b0 * L, sizeof(float) * (size_t)nb * L, cudaMemcpyHostToDevice, s), "h2d");
         int rc = mlxa_melspec_f32(ws.d_y + b0 * L, nb, L, L, ws.d_win, n_fft, hop, center, pad_mode, power, ws.d_bank,
                                   n_bands, n_w4, ws.d_mel + b0 * mel_per_clip, need_max ? ws.d_gmax : nullptr, fuse_db ? 1 : 0, 10.0f,
-                                  amin, ref, s);
+                                  amin, ref, speculate ? ws.d_bmin + b0 * nblk : nullptr, s);
         if (rc) return rc;
-        if (!need_max)
-            CHECK_CUDA(cudaMemcpyAsync(out_host + b0 * mel_per_clip, ws.d_mel + b0 * mel_per_clip,
-                                       sizeof(float) * (size_t)nb * mel_per_clip, cudaMemcpyDeviceToHost, s), "d2h");
+        if (!need_max || speculate) CHECK_CUDA(d2h(b0, nb, s), "d2h");
     }
     if (need_max) {
         for (int i = 0; i < NS; ++i) CHECK_CUDA(cudaEventRecord(ws.done[i], ws.st[i]), "event");
@@ -525,15 +564,42 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
             for (int j = 0; j < NS; ++j)
                 if (i != j) CHECK_CUDA(cudaStreamWaitEvent(ws.st[i], ws.done[j], 0), "wait");
         ci = 0;
-        for (int64_t b0 = 0; b0 < B; b0 += chunk, ++ci) {
+        for (int64_t b0 = 0; b0 < B && !speculate; b0 += chunk, ++ci) {
             const int64_t nb = std::min(chunk, B - b0);
             cudaStream_t s = ws.st[ci % NS];
             float* m = ws.d_mel + b0 * mel_per_clip;
             int rc = mlxa_to_db_f32(m, nb * mel_per_clip, 10.0f, amin, ref, ref_is_max ? ws.d_gmax : nullptr, use_top_db,
                                     top_db, ws.d_gmax, m, nullptr, s);
             if (rc) return rc;
-            CHECK_CUDA(cudaMemcpyAsync(out_host + b0 * mel_per_clip, m, sizeof(float) * (size_t)nb * mel_per_clip,
-                                       cudaMemcpyDeviceToHost, s), "d2h");
+            CHECK_CUDA(d2h(b0, nb, s), "d2h");
+        }
+        if (speculate) {
+            int rc = mlxa_db_floor_blocks_f32(ws.d_mel, B, n_bands, T, 10.0f, amin, ref, top_db, ws.d_gmax, ws.d_bmin, nullptr,
+                                              ws.d_raised, s0);
+            if (rc) return rc;
+            CHECK_CUDA(cudaMemcpyAsync(ws.h_raised, ws.d_raised, sizeof(int) * (size_t)(1 + B * nblk), cudaMemcpyDeviceToHost, s0), "d2h list");
+            for (int i = 0; i < NS; ++i) CHECK_CUDA(cudaStreamSynchronize(ws.st[i]), "sync");
+            const int n_raised = ws.h_raised[0];
+            if (n_raised > B * nblk / 4) {  // the floor bit widely: whole clips again, in runs
+                std::vector<char> hit((size_t)B, 0);
+                for (int i = 0; i < n_raised; ++i) hit[ws.h_raised[1 + i] / nblk] = 1;
+                ci = 0;
+                for (int64_t b0 = 0; b0 < B; ++ci) {
+                    if (!hit[b0]) { ++b0; continue; }
+                    int64_t b1 = b0;
+                    while (b1 < B && hit[b1]) ++b1;
+                    CHECK_CUDA(d2h(b0, b1 - b0, ws.st[ci % NS]), "d2h again");
+                    b0 = b1;
+                }
+            } else {  // a few blocks: strided copies of just those (n_bands rows of <= 64 frames)
+                for (int i = 0; i < n_raised; ++i) {
+                    const int64_t slot = ws.h_raised[1 + i], b = slot / nblk, t0 = (slot - b * nblk) * MLXA_MIN_BLOCK_FRAMES;
+                    const int64_t off = b * mel_per_clip + t0;
+                    const size_t width = sizeof(float) * (size_t)std::min<int64_t>(MLXA_MIN_BLOCK_FRAMES, T - t0);
+                    CHECK_CUDA(cudaMemcpy2DAsync(out_host + off, sizeof(float) * T, ws.d_mel + off, sizeof(float) * T, width,
+                                                 (size_t)n_bands, cudaMemcpyDeviceToHost, ws.st[i % NS]), "d2h block");
+                }
+            }
         }
     }
     for (int i = 0; i < NS; ++i) CHECK_CUDA(cudaStreamSynchronize(ws.st[i]), "sync");

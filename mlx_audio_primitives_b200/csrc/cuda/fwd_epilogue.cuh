@@ -27,6 +27,13 @@ MLXA_D float spectral_power(float2 X, float power) {
     return powf(a, power);
 }
 
+// coef * log10(max(x, amin) / refc): divide first, then log, like convert.py:52.  The quotient and the
+// logarithm use the SFU (MUFU.RCP / MUFU.LG2): absolute error of lg2 is 2^-22, i.e. < 1e-5 dB, far inside
+// the 1e-3 dB parity bound, and the kernel stops being bound by the 20-instruction log10f expansion.
+MLXA_D float to_db_one(float x, float coef, float amin, float refc) {
+    return (coef * 0.30102999566398120f) * __log2f(__fdividef(fmaxf(x, amin), refc));
+}
+
 // EP_STFT / EP_GL: one bin straight to global memory
 template <int EP>
 MLXA_D void epilogue_bin_global(const FwdParams& p, long long o, float2 X) {
@@ -112,6 +119,17 @@ MLXA_D void mel_project_group(const MelSmem ms, int n_bands, int g, const float*
     }
 }
 
+// min of the raw values of a tile into its 64-frame block's slot (tiles never straddle blocks: the tile
+// size is a power of two <= 64).  Values are >= 0, so the int ordering of the bit patterns is the float
+// ordering; one atomic per warp.
+constexpr int kMinBlockFrames = 64;
+MLXA_D void block_min_to_global(const FwdParams& p, int b, int t0, float vmin) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    if ((threadIdx.x & 31) == 0)
+        atomicMin(reinterpret_cast<int*>(p.block_min) + (long long)b * p.blocks_per_clip + t0 / kMinBlockFrames, __float_as_int(vmin));
+}
+
 // Tile store: s_out [n_bands][TT+1] -> mel (B, n_bands, T), lanes along the frames (coalesced),
 // with the optional fused dB.  TT is a power of two.  Returns the thread's running max of the raw
 // values it stored (for power_to_db(ref=max / top_db)); the caller reduces it once per CTA.
@@ -121,15 +139,18 @@ MLXA_D float mel_store_tile(const FwdParams& p, int b, int t0, int nt, const flo
     const float db_ref = fmaxf(p.db_ref, p.db_amin);
     float* outb = p.mel + (long long)b * p.n_bands * p.T + t0;
     const int n = p.n_bands << log2TT;
+    float vmin = INFINITY;
     for (int idx = threadIdx.x; idx < n; idx += THREADS) {
         const int m = idx >> log2TT, t = idx & (TT - 1);
         if (t < nt) {
             float v = s_out[m * ostride + t];
             vmax = fmaxf(vmax, v);
-            if (p.db_mode) v = p.db_coef * log10f(fmaxf(v, p.db_amin) / db_ref);
+            vmin = fminf(vmin, v);
+            if (p.db_mode) v = to_db_one(v, p.db_coef, p.db_amin, db_ref);
             outb[(long long)m * p.T + t] = v;
         }
     }
+    if (p.block_min != nullptr) block_min_to_global(p, b, t0, vmin);
     return vmax;
 }
 

@@ -36,7 +36,7 @@ MLXA_D RowBank row_bank_carve(const float* base, long long n_wt) {
 template <class P>
 struct MelRows {
     static constexpr int N = P::N, G = P::G, R0 = P::R0, R1 = P::R1;
-    static_assert(G == 16 && Mirror<P>::OWNERS + 1 <= G, "two groups per warp; one idle lane zeroes the pad rows");
+    static_assert(2 * (512 / G) == kMinBlockFrames && G == 16 && Mirror<P>::OWNERS + 1 <= G, "two groups per warp; one idle lane zeroes the pad rows");
     static constexpr int THREADS = 512, NG = THREADS / G, TT = 2 * NG;  // 64 frames per tile
     static constexpr int NBINS = N / 2 + 1;
     static constexpr int PS = TT + 2;        // floats per row of the power tile (stride == 2 mod 32: conflict-free)
@@ -93,8 +93,13 @@ __global__ void __launch_bounds__(512, 1) mel_rows_kernel(const FwdParams p) {
         for (int i = threadIdx.x; i < (int)bank_words; i += THREADS) s_bank[i] = __ldg(p.bank + i);
     }
     const RowBank rb = row_bank_carve(BANK_SMEM ? s_bank : p.bank, p.n_w4);
+    const float pscale = (PW == POW_SQUARE) ? 0.25f : (PW == POW_ABS ? 0.5f : exp2f(-p.power));
     __syncthreads();
     mbar_wait(s_bar + 2, 0);
+    if constexpr (BANK_SMEM) {  // the 1/4 (1/2, 2^-p) of the pair transform rides on the staged weights
+        for (int i = threadIdx.x; i < (int)p.n_w4; i += THREADS) s_bank[i] *= pscale;
+        __syncthreads();
+    }
 
     const int gi = threadIdx.x / G, g = threadIdx.x % G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -102,7 +107,6 @@ __global__ void __launch_bounds__(512, 1) mel_rows_kernel(const FwdParams p) {
     // pass-0 sample offsets: lane g reads element g + 16*r (+16, cyclically, in the odd group of a warp)
     const int sh = (gi & 1) ? G : 0;
     const int o_last = (gi & 1) ? -G : G * (R0 - 1);
-    const float pscale = (PW == POW_SQUARE) ? 0.25f : (PW == POW_ABS ? 0.5f : exp2f(-p.power));
     const float db_ref = fmaxf(p.db_ref, p.db_amin);
     uint32_t ph0 = 0u, ph1 = 0u;
     float vmax = 0.f;
@@ -168,45 +172,60 @@ __global__ void __launch_bounds__(512, 1) mel_rows_kernel(const FwdParams p) {
 
         // ---- band-sparse projection, lanes along frames (2 per lane), warps along bands -------------
         {
-            const int t = 2 * lane;
-            const bool ok0 = t < nt, ok1 = t + 1 < nt;
-            float* outb = p.mel + (long long)ti.b * p.n_bands * p.T + ti.t0 + t;
+            char* ob = reinterpret_cast<char*>(p.mel + (long long)ti.b * p.n_bands * p.T + ti.t0 + 2 * lane);
             const float2* q_lane = reinterpret_cast<const float2*>(s_pw) + lane;
+            const unsigned row_bytes = unsigned(p.T) * 4u;
+            // band m -> the lane's frames 2*lane, 2*lane + 1 of row m; FULL: every frame of the tile exists
+            float tmin = INFINITY;
+            auto band = [&](auto full_, int m) {
+                constexpr bool FULL = decltype(full_)::value;
+                if (m >= p.n_bands) return;
+                const int4 d = rb.desc[m];  // start, quads, first quad
+                const float4* w4 = rb.wt4 + d.z;
+                const float4* w4e = w4 + d.y;
+                const float2* q = q_lane + d.x * (PS / 2);
+                float a0 = 0.f, a1 = 0.f;
 #pragma unroll 1
-            for (int j = 0; j * 16 < p.n_bands; ++j) {
-                const int m = j * 16 + ((j & 1) ? 15 - warp : warp);  // boustrophedon: long and short bands mix
-                if (m < p.n_bands) {
-                    const int4 d = rb.desc[m];  // start, quads, first quad
-                    const float4* w4 = rb.wt4 + d.z;
-                    const float2* q = q_lane + d.x * (PS / 2);
-                    float a0 = 0.f, a1 = 0.f;
+                for (; w4 != w4e; ++w4, q += 4 * (PS / 2)) {
+                    const float4 w = *w4;
+                    const float2 q0 = q[0], q1 = q[PS / 2], q2 = q[2 * (PS / 2)], q3 = q[3 * (PS / 2)];
+                    a0 = fmaf(w.x, q0.x, a0); a1 = fmaf(w.x, q0.y, a1);
+                    a0 = fmaf(w.y, q1.x, a0); a1 = fmaf(w.y, q1.y, a1);
+                    a0 = fmaf(w.z, q2.x, a0); a1 = fmaf(w.z, q2.y, a1);
+                    a0 = fmaf(w.w, q3.x, a0); a1 = fmaf(w.w, q3.y, a1);
+                }
+                if constexpr (!BANK_SMEM) { a0 *= pscale; a1 *= pscale; }  // (folded into the staged weights otherwise)
+                const bool ok0 = FULL || 2 * lane < nt, ok1 = FULL || 2 * lane + 1 < nt;
+                if (ok0) { vmax = fmaxf(vmax, a0); tmin = fminf(tmin, a0); }
+                if (ok1) { vmax = fmaxf(vmax, a1); tmin = fminf(tmin, a1); }
+                if (p.db_mode) {
+                    a0 = to_db_one(a0, p.db_coef, p.db_amin, db_ref);
+                    a1 = to_db_one(a1, p.db_coef, p.db_amin, db_ref);
+                }
+                float* o = reinterpret_cast<float*>(ob + (unsigned long long)unsigned(m) * row_bytes);
+                if ((reinterpret_cast<uintptr_t>(o) & 7) == 0) {  // warp-uniform
+                    if (ok1) *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
+                    else if (ok0) o[0] = a0;
+                } else {
+                    if (ok0) o[0] = a0;
+                    if (ok1) o[1] = a1;
+                }
+            };
+            // boustrophedon over the 16 warps: long and short bands mix
+            if (nt == TT) {
 #pragma unroll 1
-                    for (int i = 0; i < d.y; ++i, q += 4 * (PS / 2)) {
-                        const float4 w = w4[i];
-                        const float2 q0 = q[0], q1 = q[PS / 2], q2 = q[2 * (PS / 2)], q3 = q[3 * (PS / 2)];
-                        a0 = fmaf(w.x, q0.x, a0); a1 = fmaf(w.x, q0.y, a1);
-                        a0 = fmaf(w.y, q1.x, a0); a1 = fmaf(w.y, q1.y, a1);
-                        a0 = fmaf(w.z, q2.x, a0); a1 = fmaf(w.z, q2.y, a1);
-                        a0 = fmaf(w.w, q3.x, a0); a1 = fmaf(w.w, q3.y, a1);
-                    }
-                    a0 *= pscale;
-                    a1 *= pscale;
-                    if (ok0) vmax = fmaxf(vmax, a0);
-                    if (ok1) vmax = fmaxf(vmax, a1);
-                    if (p.db_mode) {
-                        a0 = p.db_coef * log10f(fmaxf(a0, p.db_amin) / db_ref);
-                        a1 = p.db_coef * log10f(fmaxf(a1, p.db_amin) / db_ref);
-                    }
-                    float* o = outb + (long long)m * p.T;
-                    if ((reinterpret_cast<uintptr_t>(o) & 7) == 0) {  // warp-uniform
-                        if (ok1) *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
-                        else if (ok0) o[0] = a0;
-                    } else {
-                        if (ok0) o[0] = a0;
-                        if (ok1) o[1] = a1;
-                    }
+                for (int m0 = 0; m0 < p.n_bands; m0 += 32) {
+                    band(std::true_type{}, m0 + warp);
+                    band(std::true_type{}, m0 + 31 - warp);
+                }
+            } else {
+#pragma unroll 1
+                for (int m0 = 0; m0 < p.n_bands; m0 += 32) {
+                    band(std::false_type{}, m0 + warp);
+                    band(std::false_type{}, m0 + 31 - warp);
                 }
             }
+            if (p.block_min != nullptr) block_min_to_global(p, ti.b, ti.t0, tmin);
         }
         __syncthreads();  // power tile consumed: the next tile's transforms may reuse the buffers
     }

@@ -36,6 +36,8 @@ struct FwdParams {
     int bank_in_smem;    // 0: the packed bank is too large for shared memory and is read from global
     float* mel;   // (B, n_bands, T)
     float* gmax;  // optional running max
+    float* block_min;     // optional (B, blocks_per_clip): min of the raw values per 64-frame block of a clip
+    int blocks_per_clip;  // ceil(T / 64)
     int db_mode;
     float db_coef, db_amin, db_ref;
     // EP_GL

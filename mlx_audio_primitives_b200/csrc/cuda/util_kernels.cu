@@ -1,6 +1,7 @@
 // Small kernels around the fused transforms: the reference-granularity pad / frame /
 // overlap-add entry points, the dB family with its global-max reduction, the MFCC tail,
 // elementwise complex helpers and the O(n^2) DFT used for n_fft values without a compiled plan.
+#include <algorithm>
 #include "fwd_epilogue.cuh"
 #include "pcg64.cuh"
 #include "util_kernels.cuh"
@@ -155,12 +156,6 @@ __global__ void max_kernel(const float* __restrict__ x, long long n, float* gmax
 }
 
 // ---- dB family (convert.py:14-60) ---------------------------------------------------------
-// coef * log10(max(x, amin) / refc): divide first, then log, like convert.py:52.  The quotient and the
-// logarithm use the SFU (MUFU.RCP / MUFU.LG2): absolute error of lg2 is 2^-22, i.e. < 1e-5 dB, far inside
-// the 1e-3 dB parity bound, and the kernel stops being bound by the 20-instruction log10f expansion.
-__device__ __forceinline__ float to_db_one(float x, float coef, float amin, float refc) {
-    return (coef * 0.30102999566398120f) * __log2f(__fdividef(fmaxf(x, amin), refc));
-}
 __global__ void to_db_kernel(const float* __restrict__ x, long long n, float coef, float amin, float ref_host,
                              const float* __restrict__ ref_dev, int use_top, float top_db,
                              const float* __restrict__ gmax, float* __restrict__ out, float* reset_next) {
@@ -183,6 +178,83 @@ __global__ void to_db_kernel(const float* __restrict__ x, long long n, float coe
     }
     for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = fmaxf(to_db_one(x[i], coef, amin, refc), floor_db);
+}
+// Second half of a fused log-mel: x already holds coef*log10(max(S, amin)/refc) (written by the mel
+// kernel's epilogue); raise everything below max(x) - top_db to that floor.  max(x) follows from the peak
+// of S by monotonicity.  Only vectors that change are written back, so the pass is read-mostly and, right
+// behind its producer, served from L2.
+__global__ void db_floor_kernel(float* __restrict__ x, long long n, float coef, float amin, float ref, float top_db,
+                                const float* __restrict__ gmax, float* reset_next) {
+    if (reset_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *reset_next = 0.f;
+    const float floor_db = to_db_one(__ldg(gmax), coef, amin, fmaxf(ref, amin)) - top_db;
+    const long long n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
+    float4* x4 = reinterpret_cast<float4*>(x);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = x4[i];
+        if (fminf(fminf(v.x, v.y), fminf(v.z, v.w)) < floor_db) {
+            v.x = fmaxf(v.x, floor_db); v.y = fmaxf(v.y, floor_db); v.z = fmaxf(v.z, floor_db); v.w = fmaxf(v.w, floor_db);
+            x4[i] = v;
+        }
+    }
+    for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        if (x[i] < floor_db) x[i] = floor_db;
+}
+// The same floor with the producer's per-block minima (mlxa_melspec_f32 block_min): a 64-frame block of a
+// clip whose smallest value is already at or above the floor is not touched at all, so on material without
+// 80 dB of dynamic range the pass reads B*ceil(T/64) floats.  Consumed slots are re-armed to +inf.
+// A CTA looks at kSlotsPerCta (clip, block) slots at once -- one thread each, one barrier -- and then
+// rewrites the flagged ones with all of its warps (a CTA per slot costs ~16 us in launch + barrier latency
+// for the 3008 slots of a 64 x 30 s batch even when nothing is flagged; tools/probes/floor_probe.cu).
+constexpr int kSlotsPerCta = 8, kFloorThreads = 512;
+__global__ void __launch_bounds__(kFloorThreads)
+db_floor_blocks_kernel(float* __restrict__ x, long long n_slots, int n_bands, long long T, float coef, float amin, float ref,
+                       float top_db, const float* __restrict__ gmax, float* __restrict__ block_min, float* reset_next,
+                       int* n_raised) {
+    if (reset_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *reset_next = 0.f;
+    const float refc = fmaxf(ref, amin);
+    const float floor_db = to_db_one(__ldg(gmax), coef, amin, refc) - top_db;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = kFloorThreads / 32, U = 5;
+    const long long nblk = (T + kMinBlockFrames - 1) / kMinBlockFrames;
+    __shared__ unsigned s_flags;
+    const long long slot0 = (long long)blockIdx.x * kSlotsPerCta;
+    if (threadIdx.x < 32) {
+        bool f = false;
+        if (lane < kSlotsPerCta && slot0 + lane < n_slots) {
+            const float m = block_min[slot0 + lane];
+            block_min[slot0 + lane] = INFINITY;
+            f = to_db_one(m, coef, amin, refc) < floor_db;
+        }
+        const unsigned fl = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_flags = fl;
+    }
+    __syncthreads();
+    unsigned fl = s_flags;
+    while (fl) {
+        const int i = __ffs(fl) - 1;
+        fl &= fl - 1;
+        const long long slot = slot0 + i, b = slot / nblk, blk = slot - b * nblk;
+        if (threadIdx.x == 0 && n_raised != nullptr) n_raised[1 + atomicAdd(n_raised, 1)] = (int)slot;
+        // a warp per band row: 64 frames = two coalesced 128-byte accesses; U rows in flight per warp
+        const long long t0 = blk * kMinBlockFrames;
+        float* xb = x + b * n_bands * T + t0 + lane;
+        const bool ok0 = t0 + lane < T, ok1 = t0 + lane + 32 < T;
+        for (int m0 = warp; m0 < n_bands; m0 += U * NW) {
+            float v0[U], v1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int m = m0 + u * NW;
+                v0[u] = (m < n_bands && ok0) ? xb[(long long)m * T] : INFINITY;
+                v1[u] = (m < n_bands && ok1) ? xb[(long long)m * T + 32] : INFINITY;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int m = m0 + u * NW;
+                if (v0[u] < floor_db) xb[(long long)m * T] = floor_db;
+                if (v1[u] < floor_db) xb[(long long)m * T + 32] = floor_db;
+            }
+        }
+    }
 }
 __global__ void from_db_kernel(const float* __restrict__ x, long long n, float ref, float div, float* __restrict__ out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -438,6 +510,21 @@ cudaError_t run_max(const float* x, long long n, float* gmax, cudaStream_t s) {
 cudaError_t run_to_db(const float* x, long long n, float coef, float amin, float ref_host, const float* ref_dev,
                       int use_top, float top_db, const float* gmax, float* out, float* reset_next, cudaStream_t s) {
     to_db_kernel<<<grid_for(n, kThreads * 8, 148u * 16u), kThreads, 0, s>>>(x, n, coef, amin, ref_host, ref_dev, use_top, top_db, gmax, out, reset_next);
+    return cudaGetLastError();
+}
+cudaError_t run_db_floor(float* x, long long n, float coef, float amin, float ref, float top_db, const float* gmax,
+                         float* reset_next, cudaStream_t s) {
+    db_floor_kernel<<<grid_for(n, kThreads * 8, 148u * 16u), kThreads, 0, s>>>(x, n, coef, amin, ref, top_db, gmax, reset_next);
+    return cudaGetLastError();
+}
+cudaError_t run_db_floor_blocks(float* x, long long B, int n_bands, long long T, float coef, float amin, float ref,
+                                float top_db, const float* gmax, float* block_min, float* reset_next, int* n_raised,
+                                cudaStream_t s) {
+    const long long n_slots = B * ((T + kMinBlockFrames - 1) / kMinBlockFrames);
+    const long long grid = (n_slots + kSlotsPerCta - 1) / kSlotsPerCta;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    db_floor_blocks_kernel<<<(unsigned)grid, kFloorThreads, 0, s>>>(x, n_slots, n_bands, T, coef, amin, ref, top_db, gmax,
+                                                                     block_min, reset_next, n_raised);
     return cudaGetLastError();
 }
 cudaError_t run_from_db(const float* x, long long n, float ref, float div, float* out, cudaStream_t s) {

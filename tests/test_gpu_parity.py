@@ -337,6 +337,36 @@ def test_db_family(ap, golden):
         ap.power_to_db(x, top_db=0)
 
 
+@pytest.mark.parametrize("n_fft,hop,n_mels,sr", [(400, 160, 80, 16000), (1024, 256, 64, 22050), (600, 150, 40, 16000)])
+@pytest.mark.parametrize("ref", [1.0, 0.37, "max"])
+def test_logmel_plan_floor_paths_same_bits(ap, n_fft, hop, n_mels, sr, ref):
+    """LogMelPlan fuses dB into the mel kernel and applies top_db block-wise (only 64-frame blocks whose
+    minimum is below the floor are rewritten); the host-buffer entry copies results back speculatively and
+    re-copies rewritten chunks.  Both must give the bits of melspectrogram -> power_to_db, on material
+    where the floor bites in some blocks (silence, fades) and not in others."""
+    rng = np.random.default_rng(n_fft + n_mels)
+    B, L = 11, 9 * 64 * hop + 123
+    y = rng.standard_normal((B, L)).astype(np.float32)
+    y[0, : L // 2] = 0.0                      # digital silence: amin-clamped, far below the floor
+    y[3] *= np.linspace(1.0, 1e-6, L, dtype=np.float32)  # fade: the floor bites only in the tail blocks
+    y[5] = 0.0
+    y[7] *= 1e-5
+    y[9, 2000:2000 + 64 * hop] = 0.0
+    yt = torch.from_numpy(y).cuda()
+    kw = dict(sr=sr, n_fft=n_fft, hop_length=hop, n_mels=n_mels)
+    for top_db in (80.0, 25.0, None):
+        want = ap.power_to_db(ap.melspectrogram(yt, **kw), ref=(torch.max if ref == "max" else ref), top_db=top_db)
+        plan = ap.LogMelPlan(B, L, ref=ref, top_db=top_db, **kw)
+        for _ in range(2):  # twice: the peak slots and block minima must re-arm themselves
+            assert torch.equal(plan(yt), want)
+        out_h = torch.empty(tuple(want.shape), dtype=torch.float32).pin_memory()
+        plan.run_host(torch.from_numpy(y).pin_memory(), out_h)
+        assert torch.equal(out_h, want.cpu())
+        if top_db is not None:
+            assert float(want.max()) - float(want.min()) <= top_db + 1e-3
+            assert float((want == want.min()).float().mean()) > 0.05  # the floor really bit
+
+
 def test_dct(ap, golden):
     x = golden["dct/input"]
     np.testing.assert_allclose(H(ap.dct(x)), golden["dct/ortho"], atol=1e-4)
