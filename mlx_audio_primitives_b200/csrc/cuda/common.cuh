@@ -56,14 +56,60 @@ constexpr double cos_units8(long long m, long long d) {
 constexpr double cos_turn(long long num, long long den) { return cos_units8(8 * num, den); }
 constexpr double sin_turn(long long num, long long den) { return cos_units8(8 * num - 2 * den, den); }
 
-// ---- tiny complex helpers on float2 -----------------------------------------------------
-MLXA_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-MLXA_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-MLXA_HD float2 cmul(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
+// ---- complex helpers on float2 ---------------------------------------------------------------
+// On the device every helper is ONE or TWO packed FP32 instructions (sm_100 FADD2 / FMUL2 / FFMA2 on an
+// aligned register pair {re, im}; PTX add/mul/fma.rn.f32x2).  ptxas folds the component swaps and
+// per-half sign changes written below as pack(...) arguments into operand modifiers (.LO_HI, .NP), so a
+// complex add or a multiplication by -i costs one issue slot instead of two.  A packed instruction
+// occupies the FMA pipe for two passes -- the flop rate is unchanged (tools/probes/f32x2_probe.cu) --
+// but the transform kernels are issue-bound, not pipe-bound.  The host versions (CPU emulation of the
+// kernels, tests/emul) perform the same roundings in the same order.
+#if defined(__CUDA_ARCH__)
+typedef unsigned long long mlxa_u64;
+MLXA_D mlxa_u64 pk2(float a, float b) { mlxa_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+MLXA_D mlxa_u64 pk2(float2 a) { return pk2(a.x, a.y); }
+MLXA_D float2 up2(mlxa_u64 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+MLXA_D mlxa_u64 add2(mlxa_u64 a, mlxa_u64 b) { mlxa_u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+MLXA_D mlxa_u64 mul2(mlxa_u64 a, mlxa_u64 b) { mlxa_u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+MLXA_D mlxa_u64 fma2(mlxa_u64 a, mlxa_u64 b, mlxa_u64 c) { mlxa_u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+#endif
+
+// (a.x + b.x, a.y + b.y) with the second operand's halves optionally swapped / negated
+MLXA_HD float2 padd(float2 a, float bx, float by) {
+#if defined(__CUDA_ARCH__)
+    return up2(add2(pk2(a), pk2(bx, by)));
+#else
+    return make_float2(a.x + bx, a.y + by);
+#endif
 }
-MLXA_HD float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
-    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -(a.x * b.y)));
+MLXA_HD float2 cadd(float2 a, float2 b) { return padd(a, b.x, b.y); }
+MLXA_HD float2 csub(float2 a, float2 b) { return padd(a, -b.x, -b.y); }
+MLXA_HD float2 cadd_rot(float2 a, float2 b) { return padd(a, b.y, -b.x); }    // a + (-i) b
+MLXA_HD float2 csub_rot(float2 a, float2 b) { return padd(a, -b.y, b.x); }    // a - (-i) b
+MLXA_HD float2 cadd_conj(float2 a, float2 b) { return padd(a, b.x, -b.y); }   // a + conj b
+MLXA_HD float2 csub_conj(float2 a, float2 b) { return padd(a, -b.x, b.y); }   // a - conj b
+// (a.x * s.x, a.y * s.y) and (a.x * s.x + c.x, a.y * s.y + c.y)
+MLXA_HD float2 pmul(float2 a, float sx, float sy) {
+#if defined(__CUDA_ARCH__)
+    return up2(mul2(pk2(a), pk2(sx, sy)));
+#else
+    return make_float2(a.x * sx, a.y * sy);
+#endif
+}
+MLXA_HD float2 pfma(float ax, float ay, float sx, float sy, float2 c) {
+#if defined(__CUDA_ARCH__)
+    return up2(fma2(pk2(ax, ay), pk2(sx, sy), pk2(c)));
+#else
+    return make_float2(fmaf(ax, sx, c.x), fmaf(ay, sy, c.y));
+#endif
+}
+MLXA_HD float2 cscale(float2 a, float s) { return pmul(a, s, s); }                       // s * a
+MLXA_HD float2 caxpy(float s, float2 a, float2 c) { return pfma(a.x, a.y, s, s, c); }    // c + s * a
+MLXA_HD float2 cmul(float2 a, float2 b) {  // a.x * (b.x, b.y) + a.y * (-b.y, b.x)
+    return pfma(a.y, a.y, -b.y, b.x, pmul(make_float2(a.x, a.x), b.x, b.y));
+}
+MLXA_HD float2 cmul_conj(float2 a, float2 b) {  // a * conj(b) = a.x * (b.x, -b.y) + a.y * (b.y, b.x)
+    return pfma(a.y, a.y, b.y, b.x, pmul(make_float2(a.x, a.x), b.x, -b.y));
 }
 MLXA_HD float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 MLXA_HD float2 mul_pos_i(float2 a) { return make_float2(-a.y, a.x); }  // a * (+i)
@@ -73,6 +119,7 @@ MLXA_HD float2 cswap(float2 a) { return make_float2(a.y, a.x); }
 template <int NUM, int DEN>
 MLXA_HD float2 mul_tw(float2 v) {
     constexpr int n = ((NUM % DEN) + DEN) % DEN;
+    constexpr float h = 0.70710678118654752440f;
     if constexpr (n == 0) {
         return v;
     } else if constexpr (4 * n == DEN) {
@@ -81,23 +128,19 @@ MLXA_HD float2 mul_tw(float2 v) {
         return make_float2(-v.x, -v.y);
     } else if constexpr (4 * n == 3 * DEN) {
         return mul_pos_i(v);
-    } else if constexpr (8 * n == DEN) {  // (1 - i)/sqrt2
-        constexpr float h = 0.70710678118654752440f;
-        return make_float2(h * (v.x + v.y), h * (v.y - v.x));
-    } else if constexpr (8 * n == 3 * DEN) {  // (-1 - i)/sqrt2
-        constexpr float h = 0.70710678118654752440f;
-        return make_float2(h * (v.y - v.x), -h * (v.x + v.y));
-    } else if constexpr (8 * n == 5 * DEN) {  // (-1 + i)/sqrt2
-        constexpr float h = 0.70710678118654752440f;
-        return make_float2(-h * (v.x + v.y), h * (v.x - v.y));
-    } else if constexpr (8 * n == 7 * DEN) {  // (1 + i)/sqrt2
-        constexpr float h = 0.70710678118654752440f;
-        return make_float2(h * (v.x - v.y), h * (v.x + v.y));
+    } else if constexpr (8 * n == DEN) {  // (1 - i)/sqrt2: h * (x + y, y - x)
+        return cscale(padd(v, v.y, -v.x), h);
+    } else if constexpr (8 * n == 3 * DEN) {  // (-1 - i)/sqrt2: h * (y - x, -(x + y))
+        return cscale(padd(make_float2(-v.x, -v.y), v.y, -v.x), h);
+    } else if constexpr (8 * n == 5 * DEN) {  // (-1 + i)/sqrt2: h * (-(x + y), x - y)
+        return cscale(padd(make_float2(-v.x, -v.y), -v.y, v.x), h);
+    } else if constexpr (8 * n == 7 * DEN) {  // (1 + i)/sqrt2: h * (x - y, x + y)
+        return cscale(padd(v, -v.y, v.x), h);
     } else {
         constexpr float c = float(cos_turn(n, DEN));
         constexpr float s = float(sin_turn(n, DEN));
         // (x + iy)(c - is) = (xc + ys) + i(yc - xs)
-        return make_float2(fmaf(v.x, c, v.y * s), fmaf(v.y, c, -(v.x * s)));
+        return pfma(v.x, v.y, c, c, pmul(make_float2(v.y, v.x), s, -s));
     }
 }
 

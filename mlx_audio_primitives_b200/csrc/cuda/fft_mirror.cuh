@@ -70,8 +70,8 @@ MLXA_HD void mirror_last_pass_powers(int g, const float2* buf, const float2* __r
     static_for<R1>([&](auto k_) {
         constexpr int k = decltype(k_)::value;
         const float2 z1 = a[dft_pos(R1, k)], z2 = m[dft_pos(R1, (R1 - k) % R1)];
-        const float sx = z1.x + z2.x, sy = z1.y - z2.y, dx = z1.x - z2.x, dy = z1.y + z2.y;
-        float qa = fmaf(sx, sx, sy * sy), qb = fmaf(dx, dx, dy * dy);
+        const float2 s = cadd_conj(z1, z2), d = csub_conj(z1, z2);  // 2 A[bin], 2i B[bin]
+        float qa = fmaf(s.x, s.x, s.y * s.y), qb = fmaf(d.x, d.x, d.y * d.y);
         if constexpr (PW != POW_SQUARE) { qa = sqrtf(qa); qb = sqrtf(qb); }
         if constexpr (PW == POW_GENERAL) { qa = powf(qa, power); qb = powf(qb, power); }
         pp[k] = make_float2(qa, qb);

@@ -42,11 +42,11 @@ struct DftInplace<4, S, OFF> {
     static MLXA_HD void run(float2* v) {
         const float2 a0 = v[OFF], a1 = v[OFF + S], a2 = v[OFF + 2 * S], a3 = v[OFF + 3 * S];
         const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2);
-        const float2 t2 = cadd(a1, a3), t3 = mul_neg_i(csub(a1, a3));
+        const float2 t2 = cadd(a1, a3), d = csub(a1, a3);
         v[OFF] = cadd(t0, t2);
-        v[OFF + S] = cadd(t1, t3);
+        v[OFF + S] = cadd_rot(t1, d);      // t1 + (-i) d
         v[OFF + 2 * S] = csub(t0, t2);
-        v[OFF + 3 * S] = csub(t1, t3);
+        v[OFF + 3 * S] = csub_rot(t1, d);  // t1 - (-i) d
     }
 };
 
@@ -55,12 +55,11 @@ struct DftInplace<3, S, OFF> {
     static MLXA_HD void run(float2* v) {
         constexpr float s3 = 0.86602540378443864676f;
         const float2 a0 = v[OFF], a1 = v[OFF + S], a2 = v[OFF + 2 * S];
-        const float2 t = cadd(a1, a2), d = csub(a1, a2);
-        const float2 m = make_float2(fmaf(-0.5f, t.x, a0.x), fmaf(-0.5f, t.y, a0.y));
-        const float2 q = make_float2(s3 * d.y, -s3 * d.x);  // (-i*s3)*d
+        const float2 t = cadd(a1, a2), d = cscale(csub(a1, a2), s3);
+        const float2 m = caxpy(-0.5f, t, a0);
         v[OFF] = cadd(a0, t);
-        v[OFF + S] = cadd(m, q);
-        v[OFF + 2 * S] = csub(m, q);
+        v[OFF + S] = cadd_rot(m, d);      // m + (-i*s3)*(a1 - a2)
+        v[OFF + 2 * S] = csub_rot(m, d);
     }
 };
 
@@ -72,16 +71,15 @@ struct DftInplace<5, S, OFF> {
         const float2 a0 = v[OFF], a1 = v[OFF + S], a2 = v[OFF + 2 * S], a3 = v[OFF + 3 * S],
                      a4 = v[OFF + 4 * S];
         const float2 t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
-        const float2 m1 = make_float2(fmaf(c2, t2.x, fmaf(c1, t1.x, a0.x)), fmaf(c2, t2.y, fmaf(c1, t1.y, a0.y)));
-        const float2 m2 = make_float2(fmaf(c1, t2.x, fmaf(c2, t1.x, a0.x)), fmaf(c1, t2.y, fmaf(c2, t1.y, a0.y)));
-        const float2 n1 = make_float2(fmaf(s2, t4.x, s1 * t3.x), fmaf(s2, t4.y, s1 * t3.y));
-        const float2 n2 = make_float2(fmaf(-s1, t4.x, s2 * t3.x), fmaf(-s1, t4.y, s2 * t3.y));
-        const float2 q1 = mul_neg_i(n1), q2 = mul_neg_i(n2);
-        v[OFF] = make_float2(a0.x + t1.x + t2.x, a0.y + t1.y + t2.y);
-        v[OFF + S] = cadd(m1, q1);
-        v[OFF + 4 * S] = csub(m1, q1);
-        v[OFF + 2 * S] = cadd(m2, q2);
-        v[OFF + 3 * S] = csub(m2, q2);
+        const float2 m1 = caxpy(c2, t2, caxpy(c1, t1, a0));
+        const float2 m2 = caxpy(c1, t2, caxpy(c2, t1, a0));
+        const float2 n1 = caxpy(s2, t4, cscale(t3, s1));
+        const float2 n2 = caxpy(-s1, t4, cscale(t3, s2));
+        v[OFF] = cadd(cadd(a0, t1), t2);
+        v[OFF + S] = cadd_rot(m1, n1);      // m1 + (-i) n1
+        v[OFF + 4 * S] = csub_rot(m1, n1);
+        v[OFF + 2 * S] = cadd_rot(m2, n2);
+        v[OFF + 3 * S] = csub_rot(m2, n2);
     }
 };
 

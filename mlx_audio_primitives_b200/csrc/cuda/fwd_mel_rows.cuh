@@ -147,8 +147,7 @@ __global__ void __launch_bounds__(512, 1) mel_rows_kernel(const FwdParams p) {
             mirror_pass0<P>(g, [&](auto r_) {
                 constexpr int r = decltype(r_)::value;
                 const int o = (r == R0 - 1) ? o_last : G * r;
-                const float w = wp[o];
-                return make_float2(sa[o] * w, sb[o] * w);
+                return cscale(make_float2(sa[o], sb[o]), wp[o]);
             }, buf);
         }
         __syncwarp();
@@ -184,16 +183,14 @@ __global__ void __launch_bounds__(512, 1) mel_rows_kernel(const FwdParams p) {
                 const float4* w4 = rb.wt4 + d.z;
                 const float4* w4e = w4 + d.y;
                 const float2* q = q_lane + d.x * (PS / 2);
-                float a0 = 0.f, a1 = 0.f;
+                float2 acc = make_float2(0.f, 0.f);
 #pragma unroll 1
                 for (; w4 != w4e; ++w4, q += 4 * (PS / 2)) {
                     const float4 w = *w4;
                     const float2 q0 = q[0], q1 = q[PS / 2], q2 = q[2 * (PS / 2)], q3 = q[3 * (PS / 2)];
-                    a0 = fmaf(w.x, q0.x, a0); a1 = fmaf(w.x, q0.y, a1);
-                    a0 = fmaf(w.y, q1.x, a0); a1 = fmaf(w.y, q1.y, a1);
-                    a0 = fmaf(w.z, q2.x, a0); a1 = fmaf(w.z, q2.y, a1);
-                    a0 = fmaf(w.w, q3.x, a0); a1 = fmaf(w.w, q3.y, a1);
+                    acc = caxpy(w.w, q3, caxpy(w.z, q2, caxpy(w.y, q1, caxpy(w.x, q0, acc))));
                 }
+                float a0 = acc.x, a1 = acc.y;
                 if constexpr (!BANK_SMEM) { a0 *= pscale; a1 *= pscale; }  // (folded into the staged weights otherwise)
                 const bool ok0 = FULL || 2 * lane < nt, ok1 = FULL || 2 * lane + 1 < nt;
                 if (ok0) { vmax = fmaxf(vmax, a0); tmin = fminf(tmin, a0); }
