@@ -11,6 +11,7 @@
 // trips (reference stft.py:118-130).  Groups of G lanes run the Stockham plan per frame (or per
 // frame pair), exchange through a padded smem buffer with __syncwarp only, unpack the real
 // spectrum and hand every bin to the epilogue in registers.
+#include <cstdlib>
 #include "fft_plans_list.cuh"
 #include "fwd_epilogue.cuh"
 #include "fft_mirror.cuh"
@@ -376,37 +377,55 @@ template <class PL, bool PAIR>
 struct MelRowsLaunch {
     static cudaError_t run(FwdParams&, cudaStream_t) { return cudaErrorInvalidConfiguration; }
 };
-template <class PL>
-struct MelRowsLaunch<PL, true> {
+template <class PL, int THREADS>
+struct MelRowsVariant {
+    using C = MelRows<PL, THREADS>;
     template <int PW>
     static cudaError_t go(FwdParams& p, size_t smem, cudaStream_t s) {
         return p.bank_in_smem ? go2<PW, true>(p, smem, s) : go2<PW, false>(p, smem, s);
     }
     template <int PW, bool BS>
     static cudaError_t go2(FwdParams& p, size_t smem, cudaStream_t s) {
-        using C = MelRows<PL>;
-        cudaError_t e = cudaFuncSetAttribute(mel_rows_kernel<PL, PW, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kern = mel_rows_kernel<PL, C::THREADS, PW, BS>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int dev = 0, n_sm = 0;
+        int dev = 0, n_sm = 0, per_sm = 0;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        const long long total = (long long)p.B * ((p.T + C::TT - 1) / C::TT);
-        mel_rows_kernel<PL, PW, BS><<<(unsigned)(total < n_sm ? total : n_sm), C::THREADS, smem, s>>>(p);
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem)) != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        const long long total = (long long)p.B * ((p.T + C::TT - 1) / C::TT), slots = (long long)n_sm * per_sm;
+        kern<<<(unsigned)(total < slots ? total : slots), C::THREADS, smem, s>>>(p);
         return cudaGetLastError();
     }
     static cudaError_t run(FwdParams& p, cudaStream_t s) {
-        using C = MelRows<PL>;
         constexpr size_t kMaxSmem = 227 * 1024 - 256;
+        constexpr size_t kShare = (228 * 1024) / C::CTAS_PER_SM - 1024 - 64;  // an SM's shared memory split over the resident CTAs
         long long bw = packed_bank_words(p.n_bands, p.n_w4, 1);
         p.bank_in_smem = 1;
         if (C::smem_bytes(p.hop, 1, bw) > kMaxSmem) { p.bank_in_smem = 0; bw = 0; }
         if (C::smem_bytes(p.hop, 1, bw) > kMaxSmem) return cudaErrorInvalidConfiguration;
-        p.n_in_buf = (C::smem_bytes(p.hop, 2, bw) <= kMaxSmem) ? 2 : 1;
+        // double-buffer the staging when it does not cost a resident CTA
+        const bool fits1 = C::smem_bytes(p.hop, 1, bw) <= kShare;
+        const size_t lim = fits1 ? kShare : kMaxSmem;
+        p.n_in_buf = (C::smem_bytes(p.hop, 2, bw) <= lim) ? 2 : 1;
         p.tile_frames = C::TT;
         const size_t smem = C::smem_bytes(p.hop, p.n_in_buf, bw);
         if (p.power_mode == POW_SQUARE) return go<POW_SQUARE>(p, smem, s);
         if (p.power_mode == POW_ABS) return go<POW_ABS>(p, smem, s);
         return go<POW_GENERAL>(p, smem, s);
+    }
+};
+// Default: two 8-warp CTAs (32-frame tiles) per SM, so one CTA's projection / barrier phases overlap the
+// other's transforms; MLXA_MEL_ROWS_THREADS=512 selects one 16-warp CTA with 64-frame tiles (A/B runs).
+template <class PL>
+struct MelRowsLaunch<PL, true> {
+    static cudaError_t run(FwdParams& p, cudaStream_t s) {
+        static const int threads = [] {
+            const char* e = getenv("MLXA_MEL_ROWS_THREADS");
+            return (e && atoi(e) == 512) ? 512 : 256;
+        }();
+        return threads == 512 ? MelRowsVariant<PL, 512>::run(p, s) : MelRowsVariant<PL, 256>::run(p, s);
     }
 };
 

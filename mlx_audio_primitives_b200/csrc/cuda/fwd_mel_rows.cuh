@@ -33,11 +33,13 @@ MLXA_D RowBank row_bank_carve(const float* base, long long n_wt) {
     return r;
 }
 
-template <class P>
+template <class P, int THREADS_>
 struct MelRows {
     static constexpr int N = P::N, G = P::G, R0 = P::R0, R1 = P::R1;
-    static_assert(2 * (512 / G) == kMinBlockFrames && G == 16 && Mirror<P>::OWNERS + 1 <= G, "two groups per warp; one idle lane zeroes the pad rows");
-    static constexpr int THREADS = 512, NG = THREADS / G, TT = 2 * NG;  // 64 frames per tile
+    static_assert(G == 16 && Mirror<P>::OWNERS + 1 <= G, "two groups per warp; one idle lane zeroes the pad rows");
+    static constexpr int THREADS = THREADS_, NG = THREADS / G, TT = 2 * NG;  // frames per tile: 64 (512 threads) or 32
+    static_assert(kMinBlockFrames % TT == 0 && TT >= 16, "tiles never straddle a block of minima");
+    static constexpr int CTAS_PER_SM = 512 / THREADS;  // 16 warps per SM either way (the register file allows no more)
     static constexpr int NBINS = N / 2 + 1;
     static constexpr int PS = TT + 2;        // floats per row of the power tile (stride == 2 mod 32: conflict-free)
     static constexpr int PROWS = NBINS + 3;  // + rows the zero-padded weight quads may touch
@@ -49,9 +51,9 @@ struct MelRows {
     }
 };
 
-template <class P, int PW, bool BANK_SMEM>
-__global__ void __launch_bounds__(512, 1) mel_rows_kernel(const FwdParams p) {
-    using C = MelRows<P>;
+template <class P, int THREADS_, int PW, bool BANK_SMEM>
+__global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(const FwdParams p) {
+    using C = MelRows<P, THREADS_>;
     constexpr int THREADS = C::THREADS, G = C::G, TT = C::TT, N = C::N, R0 = C::R0, R1 = C::R1, PS = C::PS;
     constexpr int NBINS = C::NBINS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -169,58 +171,69 @@ __global__ void __launch_bounds__(512, 1) mel_rows_kernel(const FwdParams p) {
         }
         __syncthreads();
 
-        // ---- band-sparse projection, lanes along frames (2 per lane), warps along bands -------------
+        // ---- band-sparse projection: LB lanes along a band row's frame pairs, 32/LB bands per warp -----
         {
-            char* ob = reinterpret_cast<char*>(p.mel + (long long)ti.b * p.n_bands * p.T + ti.t0 + 2 * lane);
-            const float2* q_lane = reinterpret_cast<const float2*>(s_pw) + lane;
+            constexpr int LB = TT / 2, SLOTS = (THREADS / 32) * (32 / LB);  // band slots of the CTA per step
+            static_assert(SLOTS == 16, "the boustrophedon below walks the bands 32 at a time");
+            const int fl = lane % LB, slot = warp * (32 / LB) + lane / LB;
+            char* ob = reinterpret_cast<char*>(p.mel + (long long)ti.b * p.n_bands * p.T + ti.t0 + 2 * fl);
+            const float2* q_lane = reinterpret_cast<const float2*>(s_pw) + fl;
             const unsigned row_bytes = unsigned(p.T) * 4u;
-            // band m -> the lane's frames 2*lane, 2*lane + 1 of row m; FULL: every frame of the tile exists
+            // Bands are taken two at a time per lane (two independent accumulation chains and epilogues in
+            // flight: the phase is latency-bound otherwise); band m -> the lane's frames 2*fl, 2*fl + 1 of
+            // row m.  FULL: every frame of the tile exists.
             float tmin = INFINITY;
-            auto band = [&](auto full_, int m) {
-                constexpr bool FULL = decltype(full_)::value;
-                if (m >= p.n_bands) return;
-                const int4 d = rb.desc[m];  // start, quads, first quad
-                const float4* w4 = rb.wt4 + d.z;
-                const float4* w4e = w4 + d.y;
-                const float2* q = q_lane + d.x * (PS / 2);
-                float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 1
-                for (; w4 != w4e; ++w4, q += 4 * (PS / 2)) {
-                    const float4 w = *w4;
-                    const float2 q0 = q[0], q1 = q[PS / 2], q2 = q[2 * (PS / 2)], q3 = q[3 * (PS / 2)];
-                    acc = caxpy(w.w, q3, caxpy(w.z, q2, caxpy(w.y, q1, caxpy(w.x, q0, acc))));
-                }
-                float a0 = acc.x, a1 = acc.y;
-                if constexpr (!BANK_SMEM) { a0 *= pscale; a1 *= pscale; }  // (folded into the staged weights otherwise)
-                const bool ok0 = FULL || 2 * lane < nt, ok1 = FULL || 2 * lane + 1 < nt;
-                if (ok0) { vmax = fmaxf(vmax, a0); tmin = fminf(tmin, a0); }
-                if (ok1) { vmax = fmaxf(vmax, a1); tmin = fminf(tmin, a1); }
-                if (p.db_mode) {
-                    a0 = to_db_one(a0, p.db_coef, p.db_amin, db_ref);
-                    a1 = to_db_one(a1, p.db_coef, p.db_amin, db_ref);
-                }
-                float* o = reinterpret_cast<float*>(ob + (unsigned long long)unsigned(m) * row_bytes);
-                if ((reinterpret_cast<uintptr_t>(o) & 7) == 0) {  // warp-uniform
-                    if (ok1) *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
-                    else if (ok0) o[0] = a0;
-                } else {
-                    if (ok0) o[0] = a0;
-                    if (ok1) o[1] = a1;
-                }
+            auto quad = [&](const float4* w4, const float2* q, float2 acc) {
+                const float4 w = *w4;
+                const float2 q0 = q[0], q1 = q[PS / 2], q2 = q[2 * (PS / 2)], q3 = q[3 * (PS / 2)];
+                return caxpy(w.w, q3, caxpy(w.z, q2, caxpy(w.y, q1, caxpy(w.x, q0, acc))));
             };
-            // boustrophedon over the 16 warps: long and short bands mix
+            auto band_pair = [&](auto full_, int mA, int mB) {
+                constexpr bool FULL = decltype(full_)::value;
+                const bool hasA = mA < p.n_bands, hasB = mB < p.n_bands;
+                const int4 dA = hasA ? rb.desc[mA] : make_int4(0, 0, 0, 0);  // start, quads, first quad
+                const int4 dB = hasB ? rb.desc[mB] : make_int4(0, 0, 0, 0);
+                const float4 *wA = rb.wt4 + dA.z, *wB = rb.wt4 + dB.z;
+                const float2 *qA = q_lane + dA.x * (PS / 2), *qB = q_lane + dB.x * (PS / 2);
+                float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
+                int nA = dA.y, nB = dB.y;
+#pragma unroll 1
+                for (; nA > 0 && nB > 0; --nA, --nB, ++wA, ++wB, qA += 4 * (PS / 2), qB += 4 * (PS / 2)) {
+                    accA = quad(wA, qA, accA);
+                    accB = quad(wB, qB, accB);
+                }
+#pragma unroll 1
+                for (; nA > 0; --nA, ++wA, qA += 4 * (PS / 2)) accA = quad(wA, qA, accA);
+#pragma unroll 1
+                for (; nB > 0; --nB, ++wB, qB += 4 * (PS / 2)) accB = quad(wB, qB, accB);
+                float v[4] = {accA.x, accA.y, accB.x, accB.y};
+                if constexpr (!BANK_SMEM) {  // (folded into the staged weights otherwise)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] *= pscale;
+                }
+                const bool ok0 = FULL || 2 * fl < nt, ok1 = FULL || 2 * fl + 1 < nt;
+                const bool st[4] = {ok0 && hasA, ok1 && hasA, ok0 && hasB, ok1 && hasB};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (st[i]) { vmax = fmaxf(vmax, v[i]); tmin = fminf(tmin, v[i]); }
+                if (p.db_mode) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = to_db_one(v[i], p.db_coef, p.db_amin, db_ref);
+                }
+                float* oA = reinterpret_cast<float*>(ob + (unsigned long long)unsigned(mA) * row_bytes);
+                float* oB = reinterpret_cast<float*>(ob + (unsigned long long)unsigned(mB) * row_bytes);
+                if (st[0]) oA[0] = v[0];
+                if (st[1]) oA[1] = v[1];
+                if (st[2]) oB[0] = v[2];
+                if (st[3]) oB[1] = v[3];
+            };
+            // boustrophedon over the CTA's 16 band slots: long and short bands mix
             if (nt == TT) {
 #pragma unroll 1
-                for (int m0 = 0; m0 < p.n_bands; m0 += 32) {
-                    band(std::true_type{}, m0 + warp);
-                    band(std::true_type{}, m0 + 31 - warp);
-                }
+                for (int m0 = 0; m0 < p.n_bands; m0 += 32) band_pair(std::true_type{}, m0 + slot, m0 + 31 - slot);
             } else {
 #pragma unroll 1
-                for (int m0 = 0; m0 < p.n_bands; m0 += 32) {
-                    band(std::false_type{}, m0 + warp);
-                    band(std::false_type{}, m0 + 31 - warp);
-                }
+                for (int m0 = 0; m0 < p.n_bands; m0 += 32) band_pair(std::false_type{}, m0 + slot, m0 + 31 - slot);
             }
             if (p.block_min != nullptr) block_min_to_global(p, ti.b, ti.t0, tmin);
         }
