@@ -27,11 +27,12 @@ MLXA_D float spectral_power(float2 X, float power) {
     return powf(a, power);
 }
 
-// coef * log10(max(x, amin) / refc): divide first, then log, like convert.py:52.  The quotient and the
-// logarithm use the SFU (MUFU.RCP / MUFU.LG2): absolute error of lg2 is 2^-22, i.e. < 1e-5 dB, far inside
-// the 1e-3 dB parity bound, and the kernel stops being bound by the 20-instruction log10f expansion.
+// coef * log10(max(x, amin) / refc): scale first, then log, like convert.py:52.  The quotient is a
+// multiplication by the (loop-invariant, correctly rounded) reciprocal of refc and the logarithm runs on the
+// SFU (MUFU.LG2): absolute error of lg2 is 2^-22, i.e. < 1e-5 dB, far inside the 1e-3 dB parity bound.
+// Every kernel that converts to dB uses this one function, so fused and two-pass paths give the same bits.
 MLXA_D float to_db_one(float x, float coef, float amin, float refc) {
-    return (coef * 0.30102999566398120f) * __log2f(__fdividef(fmaxf(x, amin), refc));
+    return (coef * 0.30102999566398120f) * __log2f(fmaxf(x, amin) * (1.0f / refc));
 }
 
 // EP_STFT / EP_GL: one bin straight to global memory
