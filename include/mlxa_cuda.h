@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MLXA_ABI_VERSION 2
+#define MLXA_ABI_VERSION 3
 
 #define MLXA_E_INVALID (-1)   /* bad size / null pointer / unknown mode            */
 #define MLXA_E_UNSUPPORTED (-2)
@@ -37,6 +37,22 @@ extern "C" {
 #define MLXA_PAD_EDGE 2
 
 typedef struct { float re, im; } mlxa_c64;
+
+/* One-float MAX exchange over peer memory (NVLink / NVSwitch) for a batch sharded over `world` GPUs: what the
+ * reference gets from taking ref=max / top_db over the whole batch (convert.py:42-58).  peer_slots is a
+ * DEVICE array of `world` pointers, entry r the base of rank r's slot buffer of 2*world uint64 (zeroed once,
+ * peer-mapped on every rank, e.g. torch symmetric memory); ticket a zeroed device uint32 owned by this rank;
+ * epoch a counter the caller raises by one per producer launch, identical on all ranks, starting at 1.  The
+ * last CTA of the producer (mlxa_melspec_f32) stores (epoch, peak) into slot [epoch & 1][rank] of every rank;
+ * consumers given the same descriptor (mlxa_to_db_f32, mlxa_db_floor_blocks_f32) spin on their own slots
+ * until all ranks have published this epoch and use the maximum in place of *gmax_dev (and of a ref_dev that
+ * aliases gmax_dev).  Pass NULL for single-GPU use. */
+typedef struct {
+    uint64_t* const* peer_slots;
+    int32_t rank, world;
+    uint32_t epoch;
+    uint32_t* ticket;
+} mlxa_peak_exchange;
 
 int mlxa_abi_version(void);
 const char* mlxa_last_error(void);
@@ -116,7 +132,7 @@ int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const fl
                      int n_fft, int hop, int center, int pad_mode, float power,
                      const float* bank, int n_bands, int64_t n_wt,
                      float* mel, float* gmax, int db_mode, float db_coef, float db_amin,
-                     float db_ref, float* block_min, void* stream);
+                     float db_ref, float* block_min, const mlxa_peak_exchange* xchg, void* stream);
 
 /* irFFT -> window -> gather overlap-add -> / max(sum w^2, 1e-8) -> trim in one kernel
  * (replaces stft.py:292-338 = mx.fft.irfft -> _ext.overlap_add -> slices).
@@ -176,7 +192,7 @@ int mlxa_fill_f32(float* x, int64_t n, float value, void* stream);
  * so a pipeline alternating two slots needs no separate fill launch. */
 int mlxa_to_db_f32(const float* x, int64_t n, float coef, float amin, float ref_host,
                    const float* ref_dev, int use_top_db, float top_db, const float* gmax_dev,
-                   float* out, float* reset_next, void* stream);
+                   float* out, float* reset_next, const mlxa_peak_exchange* xchg, void* stream);
 /* Second half of a fused log-mel (convert.py:55-58 alone): x_db already holds coef*log10(max(S, amin)/
  * max(ref, amin)) -- mlxa_melspec_f32 with db_mode != 0 and gmax -- and is raised in place to
  * max(x_db) - top_db, max(x_db) derived from the peak *gmax_dev of S.  Read-mostly: only values below the
@@ -191,7 +207,7 @@ int mlxa_db_floor_f32(float* x_db, int64_t n, float coef, float amin, float ref,
  * mlxa_to_db_f32 / mlxa_db_floor_f32. */
 int mlxa_db_floor_blocks_f32(float* x_db, int64_t B, int n_bands, int64_t T, float coef, float amin,
                              float ref, float top_db, const float* gmax_dev, float* block_min,
-                             float* reset_next, int32_t* raised, void* stream);
+                             float* reset_next, int32_t* raised, const mlxa_peak_exchange* xchg, void* stream);
 /* convert.py:100-129,169-198: out = ref * 10^(x/div) */
 int mlxa_from_db_f32(const float* x, int64_t n, float ref, float div, float* out, void* stream);
 

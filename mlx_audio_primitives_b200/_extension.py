@@ -12,7 +12,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MLXA_CUDA_LIB", os.path.join(_HERE, "_lib", "libmlxaudio_cuda.so"))
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _i64, _i32, _f32, _p = C.c_int64, C.c_int, C.c_float, C.c_void_p
 
@@ -28,7 +28,7 @@ SIGNATURES = {
     "mlxa_plan_group": [_i32],
     "mlxa_pack_filterbank": [_p, _i32, _i32, _i32, _p, _i64, _p],
     "mlxa_melspec_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i64,
-                         _p, _p, _i32, _f32, _f32, _f32, _p, _p],
+                         _p, _p, _i32, _f32, _f32, _f32, _p, _p, _p],
     "mlxa_istft_f32": [_p, _i64, _i64, _i32, _p, _p, _i32, _i32, _i64, _i64, _i64, _p, _i64, _p],
     "mlxa_istft_extrap_f32": [_p, _p, _f32, _i64, _i64, _i32, _p, _p, _i32, _i32, _i64, _i64, _i64, _p, _i64, _p],
     "mlxa_griffinlim_project_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _i64, _i64, _p, _p, _p],
@@ -40,9 +40,9 @@ SIGNATURES = {
     "mlxa_transpose_c64": [_p, _i64, _i64, _i64, _p, _p],
     "mlxa_max_f32": [_p, _i64, _p, _p],
     "mlxa_fill_f32": [_p, _i64, _f32, _p],
-    "mlxa_to_db_f32": [_p, _i64, _f32, _f32, _f32, _p, _i32, _f32, _p, _p, _p, _p],
+    "mlxa_to_db_f32": [_p, _i64, _f32, _f32, _f32, _p, _i32, _f32, _p, _p, _p, _p, _p],
     "mlxa_db_floor_f32": [_p, _i64, _f32, _f32, _f32, _f32, _p, _p, _p],
-    "mlxa_db_floor_blocks_f32": [_p, _i64, _i32, _i64, _f32, _f32, _f32, _f32, _p, _p, _p, _p, _p],
+    "mlxa_db_floor_blocks_f32": [_p, _i64, _i32, _i64, _f32, _f32, _f32, _f32, _p, _p, _p, _p, _p, _p],
     "mlxa_from_db_f32": [_p, _i64, _f32, _f32, _p, _p],
     "mlxa_dct_f32": [_p, _i64, _i32, _p, _i32, _p, _p],
     "mlxa_mfcc_tail_f32": [_p, _i64, _i32, _i64, _p, _i32, _p, _i32, _f32, _f32, _i32, _f32, _p, _p, _p],

@@ -51,7 +51,7 @@ def _to_db(S, ref, coefficient: float, amin: float, top_db):
     if top_db is not None and peak is None:
         peak = _global_peak(S)
     check(_ext.mlxa_to_db_f32(ptr(S), S.numel(), float(coefficient), float(amin), ref_host, ptr(ref_dev),
-                              int(top_db is not None), float(top_db or 0.0), ptr(peak), ptr(out), None, stream_ptr(S)),
+                              int(top_db is not None), float(top_db or 0.0), ptr(peak), ptr(out), None, None, stream_ptr(S)),
           "to_db")
     return out
 

@@ -32,6 +32,14 @@ int cuda_fail(cudaError_t e, const char* where) {
     g_err = std::string(where) + ": " + cudaGetErrorString(e);
     return (int)e;
 }
+PeakExchange to_xchg(const mlxa_peak_exchange* x) {
+    PeakExchange r{};
+    if (x != nullptr && x->peer_slots != nullptr && x->world > 1) {
+        r.peer_slots = reinterpret_cast<unsigned long long* const*>(x->peer_slots);
+        r.rank = x->rank; r.world = x->world; r.epoch = x->epoch; r.ticket = x->ticket;
+    }
+    return r;
+}
 #define CHECK_ARG(cond, msg) \
     if (!(cond)) return fail(MLXA_E_INVALID, msg)
 #define CHECK_CUDA(expr, where)                      \
@@ -264,8 +272,10 @@ int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, int group,
 int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window, int n_fft, int hop,
                      int center, int pad_mode, float power, const float* bank, int n_bands, int64_t n_w4, float* mel,
                      float* gmax, int db_mode, float db_coef, float db_amin, float db_ref, float* block_min,
-                     void* stream) {
+                     const mlxa_peak_exchange* xchg, void* stream) {
     CHECK_ARG(bank && mel, "null pointer");
+    CHECK_ARG(xchg == nullptr || (gmax && B <= 65535 && xchg->rank >= 0 && xchg->rank < xchg->world && xchg->ticket),
+              "a peak exchange needs gmax, a ticket counter and a single launch (B <= 65535)");
     CHECK_ARG(n_bands > 0 && n_w4 >= 0 && n_w4 < (1LL << 22), "bad filterbank size");  // n_w4 = n_wt words
     return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
         FwdParams p;
@@ -277,6 +287,7 @@ int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const fl
         p.const_bulk = (((uintptr_t)bank | (uintptr_t)window) & 15) == 0;
         p.mel = mel + b0 * (int64_t)n_bands * p.T;
         p.gmax = gmax;
+        p.xchg = to_xchg(xchg);
         p.blocks_per_clip = (int)((p.T + MLXA_MIN_BLOCK_FRAMES - 1) / MLXA_MIN_BLOCK_FRAMES);
         p.block_min = block_min ? block_min + b0 * p.blocks_per_clip : nullptr;
         p.db_mode = db_mode; p.db_coef = db_coef; p.db_amin = db_amin; p.db_ref = db_ref;
@@ -411,10 +422,12 @@ int mlxa_fill_f32(float* x, int64_t n, float value, void* stream) {
     return 0;
 }
 int mlxa_to_db_f32(const float* x, int64_t n, float coef, float amin, float ref_host, const float* ref_dev,
-                   int use_top_db, float top_db, const float* gmax_dev, float* out, float* reset_next, void* stream) {
+                   int use_top_db, float top_db, const float* gmax_dev, float* out, float* reset_next,
+                   const mlxa_peak_exchange* xchg, void* stream) {
     CHECK_ARG(x && out && n > 0, "bad argument");
     CHECK_ARG(!use_top_db || (gmax_dev && top_db > 0), "top_db needs a positive value and the global max");
-    CHECK_CUDA(run_to_db(x, n, coef, amin, ref_host, ref_dev, use_top_db, top_db, gmax_dev, out, reset_next, (cudaStream_t)stream), "to_db");
+    CHECK_CUDA(run_to_db(x, n, coef, amin, ref_host, ref_dev, use_top_db, top_db, gmax_dev, out, reset_next, to_xchg(xchg),
+                         (cudaStream_t)stream), "to_db");
     return 0;
 }
 int mlxa_db_floor_f32(float* x_db, int64_t n, float coef, float amin, float ref, float top_db, const float* gmax_dev,
@@ -425,10 +438,10 @@ int mlxa_db_floor_f32(float* x_db, int64_t n, float coef, float amin, float ref,
 }
 int mlxa_db_floor_blocks_f32(float* x_db, int64_t B, int n_bands, int64_t T, float coef, float amin, float ref,
                              float top_db, const float* gmax_dev, float* block_min, float* reset_next, int32_t* n_raised,
-                             void* stream) {
+                             const mlxa_peak_exchange* xchg, void* stream) {
     CHECK_ARG(x_db && gmax_dev && block_min && B > 0 && B <= 65535 && n_bands > 0 && T > 0 && top_db > 0, "bad argument");
     CHECK_CUDA(run_db_floor_blocks(x_db, B, n_bands, T, coef, amin, ref, top_db, gmax_dev, block_min, reset_next, n_raised,
-                                   (cudaStream_t)stream), "db_floor_blocks");
+                                   to_xchg(xchg), (cudaStream_t)stream), "db_floor_blocks");
     return 0;
 }
 int mlxa_from_db_f32(const float* x, int64_t n, float ref, float div, float* out, void* stream) {
@@ -554,7 +567,7 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
         CHECK_CUDA(cudaMemcpyAsync(ws.d_y + b0 * L, y_host + b0 * L, sizeof(float) * (size_t)nb * L, cudaMemcpyHostToDevice, s), "h2d");
         int rc = mlxa_melspec_f32(ws.d_y + b0 * L, nb, L, L, ws.d_win, n_fft, hop, center, pad_mode, power, ws.d_bank,
                                   n_bands, n_w4, ws.d_mel + b0 * mel_per_clip, need_max ? ws.d_gmax : nullptr, fuse_db ? 1 : 0, 10.0f,
-                                  amin, ref, speculate ? ws.d_bmin + b0 * nblk : nullptr, s);
+                                  amin, ref, speculate ? ws.d_bmin + b0 * nblk : nullptr, nullptr, s);
         if (rc) return rc;
         if (!need_max || speculate) CHECK_CUDA(d2h(b0, nb, s), "d2h");
     }
@@ -569,13 +582,13 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
             cudaStream_t s = ws.st[ci % NS];
             float* m = ws.d_mel + b0 * mel_per_clip;
             int rc = mlxa_to_db_f32(m, nb * mel_per_clip, 10.0f, amin, ref, ref_is_max ? ws.d_gmax : nullptr, use_top_db,
-                                    top_db, ws.d_gmax, m, nullptr, s);
+                                    top_db, ws.d_gmax, m, nullptr, nullptr, s);
             if (rc) return rc;
             CHECK_CUDA(d2h(b0, nb, s), "d2h");
         }
         if (speculate) {
             int rc = mlxa_db_floor_blocks_f32(ws.d_mel, B, n_bands, T, 10.0f, amin, ref, top_db, ws.d_gmax, ws.d_bmin, nullptr,
-                                              ws.d_raised, s0);
+                                              ws.d_raised, nullptr, s0);
             if (rc) return rc;
             CHECK_CUDA(cudaMemcpyAsync(ws.h_raised, ws.d_raised, sizeof(int) * (size_t)(1 + B * nblk), cudaMemcpyDeviceToHost, s0), "d2h list");
             for (int i = 0; i < NS; ++i) CHECK_CUDA(cudaStreamSynchronize(ws.st[i]), "sync");

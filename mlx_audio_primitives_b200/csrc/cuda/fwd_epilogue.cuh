@@ -155,9 +155,55 @@ MLXA_D float mel_store_tile(const FwdParams& p, int b, int t0, int nt, const flo
     return vmax;
 }
 
-// one atomicMax per CTA (mel >= 0, so the int ordering of the bit patterns is the float ordering)
+// ---- peak exchange over peer memory (params.cuh: PeakExchange) ------------------------------------
+MLXA_D void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+MLXA_D unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// one thread of the last CTA of a producer kernel: this rank's final peak to every rank's slot set
+MLXA_D void peak_publish(const PeakExchange& x, float* gmax, unsigned n_ctas) {
+    __threadfence();
+    if (atomicAdd(x.ticket, 1u) != n_ctas - 1) return;
+    *x.ticket = 0u;
+    __threadfence();
+    const float peak = __int_as_float(atomicMax(reinterpret_cast<int*>(gmax), 0));  // coherent read (values >= 0)
+    const unsigned long long v = ((unsigned long long)x.epoch << 32) | (unsigned)__float_as_int(peak);
+    for (int r = 0; r < x.world; ++r) st_release_sys_u64(x.peer_slots[r] + (x.epoch & 1u) * x.world + x.rank, v);
+}
+// any thread of a consumer kernel: the maximum over all ranks (spins until every rank has published this
+// epoch; a rank that never arrives traps instead of hanging the GPU)
+MLXA_D float peak_collect(const PeakExchange& x, const unsigned long long* my_slots) {
+    float m = 0.f;
+    for (int r = 0; r < x.world; ++r) {
+        const unsigned long long* s = my_slots + (x.epoch & 1u) * x.world + r;
+        unsigned long long v = ld_acquire_sys_u64(s);
+        for (unsigned spins = 0; (unsigned)(v >> 32) != x.epoch; ++spins) {
+            if (spins > (1u << 26)) __trap();
+            __nanosleep(64);
+            v = ld_acquire_sys_u64(s);
+        }
+        m = fmaxf(m, __int_as_float((int)(unsigned)v));
+    }
+    return m;
+}
+
+// all threads of a consumer CTA: the batch-global peak -- the local *gmax, or with an exchange the maximum
+// over the ranks (thread 0 collects, one barrier)
+MLXA_D float resolve_peak(const float* gmax, const PeakExchange& x, float* s_slot) {
+    if (x.peer_slots == nullptr) return gmax ? __ldg(gmax) : 0.f;
+    if (threadIdx.x == 0) *s_slot = peak_collect(x, x.peer_slots[x.rank]);
+    __syncthreads();
+    return *s_slot;
+}
+
+// one atomicMax per CTA (mel >= 0, so the int ordering of the bit patterns is the float ordering); with a
+// peak exchange the last CTA to get here also publishes the final value to the peers
 template <int THREADS>
-MLXA_D void block_max_to_global(float vmax, float* gmax, float* s_red) {
+MLXA_D void block_max_to_global(float vmax, float* gmax, float* s_red, const PeakExchange& xchg) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = vmax;
@@ -166,6 +212,7 @@ MLXA_D void block_max_to_global(float vmax, float* gmax, float* s_red) {
         float mx = 0.f;
         for (int i = 0; i < THREADS / 32; ++i) mx = fmaxf(mx, s_red[i]);
         atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(mx));
+        if (xchg.peer_slots != nullptr) peak_publish(xchg, gmax, gridDim.x * gridDim.y);
     }
 }
 

@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
         __syncthreads();  // tile done: its staging buffer and the mel tile may be overwritten
     }
     if constexpr (EP == EP_MEL) {
-        if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red);
+        if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red, p.xchg);
     }
 }
 

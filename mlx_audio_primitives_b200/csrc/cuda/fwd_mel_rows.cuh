@@ -239,5 +239,5 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
         }
         __syncthreads();  // power tile consumed: the next tile's transforms may reuse the buffers
     }
-    if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red);
+    if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red, p.xchg);
 }

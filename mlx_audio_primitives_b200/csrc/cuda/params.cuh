@@ -8,6 +8,19 @@ namespace mlxa {
 enum : int { EP_STFT = 0, EP_MEL = 1, EP_GL = 2 };
 enum : int { POW_SQUARE = 0, POW_ABS = 1, POW_GENERAL = 2 };
 
+// One-float MAX exchange over peer memory (NVLink / NVSwitch), replacing the all-reduce between the mel
+// kernel and the dB kernel when clips are sharded over GPUs.  Every rank owns `2 * world` 64-bit slots in a
+// peer-mapped buffer: slot [epoch & 1][r] holds (epoch << 32 | float bits of rank r's peak).  The LAST CTA of
+// the producer kernel (ticket counter) stores this rank's peak into its slot on every peer; consumers spin
+// on their own, local slots until all `world` entries carry the current epoch.  Alternating the two slot
+// sets by epoch parity keeps a fast rank from overwriting a value a slow rank has not read yet.
+struct PeakExchange {
+    unsigned long long* const* peer_slots;  // device array: base of every rank's slots (nullptr: disabled)
+    int rank, world;
+    unsigned epoch;
+    unsigned* ticket;  // local counter of finished CTAs, left at 0
+};
+
 struct FwdParams {
     // input clips
     const float* y;
@@ -36,6 +49,7 @@ struct FwdParams {
     int bank_in_smem;    // 0: the packed bank is too large for shared memory and is read from global
     float* mel;   // (B, n_bands, T)
     float* gmax;  // optional running max
+    PeakExchange xchg;    // optional: publish the final gmax to every peer
     float* block_min;     // optional (B, blocks_per_clip): min of the raw values per 64-frame block of a clip
     int blocks_per_clip;  // ceil(T / 64)
     int db_mode;

@@ -158,12 +158,16 @@ __global__ void max_kernel(const float* __restrict__ x, long long n, float* gmax
 // ---- dB family (convert.py:14-60) ---------------------------------------------------------
 __global__ void to_db_kernel(const float* __restrict__ x, long long n, float coef, float amin, float ref_host,
                              const float* __restrict__ ref_dev, int use_top, float top_db,
-                             const float* __restrict__ gmax, float* __restrict__ out, float* reset_next) {
+                             const float* __restrict__ gmax, float* __restrict__ out, float* reset_next,
+                             PeakExchange xchg) {
     if (reset_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *reset_next = 0.f;  // peak slot of the NEXT call
-    const float ref = ref_dev ? __ldg(ref_dev) : ref_host;
+    __shared__ float s_peak;
+    // with an exchange, gmax (and a ref_dev that aliases it, i.e. ref = max) mean the maximum over all ranks
+    const float peak = (use_top || xchg.peer_slots != nullptr) ? resolve_peak(gmax, xchg, &s_peak) : 0.f;
+    const float ref = ref_dev ? ((xchg.peer_slots != nullptr && ref_dev == gmax) ? peak : __ldg(ref_dev)) : ref_host;
     const float refc = fmaxf(ref, amin);
     float floor_db = -INFINITY;
-    if (use_top) floor_db = to_db_one(__ldg(gmax), coef, amin, refc) - top_db;
+    if (use_top) floor_db = to_db_one(peak, coef, amin, refc) - top_db;
     const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     const long long n4 = al ? n / 4 : 0;
     const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -209,10 +213,11 @@ constexpr int kSlotsPerCta = 8, kFloorThreads = 512;
 __global__ void __launch_bounds__(kFloorThreads)
 db_floor_blocks_kernel(float* __restrict__ x, long long n_slots, int n_bands, long long T, float coef, float amin, float ref,
                        float top_db, const float* __restrict__ gmax, float* __restrict__ block_min, float* reset_next,
-                       int* n_raised) {
+                       int* n_raised, PeakExchange xchg) {
     if (reset_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *reset_next = 0.f;
+    __shared__ float s_peak;
     const float refc = fmaxf(ref, amin);
-    const float floor_db = to_db_one(__ldg(gmax), coef, amin, refc) - top_db;
+    const float floor_db = to_db_one(resolve_peak(gmax, xchg, &s_peak), coef, amin, refc) - top_db;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = kFloorThreads / 32, U = 5;
     const long long nblk = (T + kMinBlockFrames - 1) / kMinBlockFrames;
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p, int n
     if constexpr (EP == EP_MEL) {
         __syncthreads();
         const float vmax = mel_store_tile<256>(p, b, t0, nt, s_out, TT, 3, 0.f);  // TT = 8
-        if (p.gmax != nullptr) block_max_to_global<256>(vmax, p.gmax, s_red);
+        if (p.gmax != nullptr) block_max_to_global<256>(vmax, p.gmax, s_red, p.xchg);
     }
 }
 
@@ -508,8 +513,9 @@ cudaError_t run_max(const float* x, long long n, float* gmax, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t run_to_db(const float* x, long long n, float coef, float amin, float ref_host, const float* ref_dev,
-                      int use_top, float top_db, const float* gmax, float* out, float* reset_next, cudaStream_t s) {
-    to_db_kernel<<<grid_for(n, kThreads * 8, 148u * 16u), kThreads, 0, s>>>(x, n, coef, amin, ref_host, ref_dev, use_top, top_db, gmax, out, reset_next);
+                      int use_top, float top_db, const float* gmax, float* out, float* reset_next, const PeakExchange& xchg,
+                      cudaStream_t s) {
+    to_db_kernel<<<grid_for(n, kThreads * 8, 148u * 16u), kThreads, 0, s>>>(x, n, coef, amin, ref_host, ref_dev, use_top, top_db, gmax, out, reset_next, xchg);
     return cudaGetLastError();
 }
 cudaError_t run_db_floor(float* x, long long n, float coef, float amin, float ref, float top_db, const float* gmax,
@@ -519,12 +525,12 @@ cudaError_t run_db_floor(float* x, long long n, float coef, float amin, float re
 }
 cudaError_t run_db_floor_blocks(float* x, long long B, int n_bands, long long T, float coef, float amin, float ref,
                                 float top_db, const float* gmax, float* block_min, float* reset_next, int* n_raised,
-                                cudaStream_t s) {
+                                const PeakExchange& xchg, cudaStream_t s) {
     const long long n_slots = B * ((T + kMinBlockFrames - 1) / kMinBlockFrames);
     const long long grid = (n_slots + kSlotsPerCta - 1) / kSlotsPerCta;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     db_floor_blocks_kernel<<<(unsigned)grid, kFloorThreads, 0, s>>>(x, n_slots, n_bands, T, coef, amin, ref, top_db, gmax,
-                                                                     block_min, reset_next, n_raised);
+                                                                     block_min, reset_next, n_raised, xchg);
     return cudaGetLastError();
 }
 cudaError_t run_from_db(const float* x, long long n, float ref, float div, float* out, cudaStream_t s) {

@@ -210,7 +210,7 @@ def _melspec_from_bank(y, bank: SparseBank, n_fft, hop, win_length, window, cent
     db = fused_db or (0, 10.0, 1e-10, 1.0)
     check(_ext.mlxa_melspec_f32(ptr(y), B, L, y.stride(0), ptr(win), n_fft, hop, int(center), mode, float(power),
                                 ptr(bank.packed), bank.n_bands, bank.n_w4, ptr(out), ptr(peak), int(db[0]), float(db[1]), float(db[2]),
-                                float(db[3]), None, stream_ptr(y)), "melspectrogram")
+                                float(db[3]), None, None, stream_ptr(y)), "melspectrogram")
     res = out[0] if one_d else out
     if want_peak:
         _peaks.remember(res, peak)

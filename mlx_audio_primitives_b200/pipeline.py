@@ -52,6 +52,8 @@ class LogMelPlan:
         left = (self.n_fft - self.win_length) // 2
         self._win_host[left:left + self.win_length] = window_host(window, self.win_length, True)
         self.need_peak = self.to_db and (self.ref_is_max or self.top_db is not None)
+        # sharded batch: the peak crosses GPUs through peer memory inside the two kernels (NCCL if unavailable)
+        self.xchg = distributed.PeakExchange.create(self.device) if (self.to_db and (self.ref_is_max or self.top_db is not None)) else None
         # ref a constant: the mel kernel's epilogue writes dB itself and top_db is a read-mostly floor pass
         self.fused_db = self.to_db and not self.ref_is_max
         self.kernel_launches_per_call = 1 + (1 if self.need_peak else 0)
@@ -63,11 +65,14 @@ class LogMelPlan:
     def mel(self, y: torch.Tensor, out: torch.Tensor) -> None:
         s = torch.cuda.current_stream(self.device).cuda_stream
         fuse = self.fused_db  # the peak slot was zeroed by the previous call's dB / floor kernel
+        if self.xchg is not None:
+            self.xchg.next_epoch()
         check(_ext.mlxa_melspec_f32(ptr(y), self.B, self.L, y.stride(0), ptr(self.win), self.n_fft, self.hop,
                                     int(self.center), self.mode, self.power, ptr(self.bank.packed),
                                     self.n_mels, self.bank.n_w4, ptr(out), self._peak_ptr() if self.need_peak else None,
                                     int(fuse), 10.0, self.amin, self.ref,
-                                    ptr(self.block_min) if (fuse and self.need_peak) else None, s), "melspectrogram")
+                                    ptr(self.block_min) if (fuse and self.need_peak) else None,
+                                    self.xchg.ref if self.xchg is not None else None, s), "melspectrogram")
 
     def _peak_ptr(self, other: bool = False) -> int:
         return self.peaks.data_ptr() + 4 * (self._slot ^ int(other))
@@ -75,18 +80,19 @@ class LogMelPlan:
     def db(self, out: torch.Tensor) -> None:
         if not self.need_peak:
             return
-        peak = self.peaks[self._slot:self._slot + 1]
-        distributed.all_reduce_max_(peak)
+        xr = self.xchg.ref if self.xchg is not None else None
+        if xr is None:
+            distributed.all_reduce_max_(self.peaks[self._slot:self._slot + 1])
         s = torch.cuda.current_stream(self.device).cuda_stream
         if self.fused_db:
             check(_ext.mlxa_db_floor_blocks_f32(ptr(out), self.B, self.n_mels, self.T, 10.0, self.amin, self.ref,
                                                 float(self.top_db), self._peak_ptr(), ptr(self.block_min),
-                                                self._peak_ptr(other=True), None, s), "db_floor_blocks")
+                                                self._peak_ptr(other=True), None, xr, s), "db_floor_blocks")
             self._slot ^= 1
             return
         check(_ext.mlxa_to_db_f32(ptr(out), out.numel(), 10.0, self.amin, self.ref,
                                   self._peak_ptr() if self.ref_is_max else None, int(self.top_db is not None),
-                                  float(self.top_db or 0.0), self._peak_ptr(), ptr(out), self._peak_ptr(other=True), s),
+                                  float(self.top_db or 0.0), self._peak_ptr(), ptr(out), self._peak_ptr(other=True), xr, s),
               "to_db")
         self._slot ^= 1
 
