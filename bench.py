@@ -120,7 +120,7 @@ def run_reference_arm(args, w):
                              "sample": f"{clips} clips x {w['seconds']:.0f} s per step (bounded sample of the "
                                        f"{w['clips']}-clip batch), float32 restatement of the reference CPU path"},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -182,7 +182,24 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # anything a library prints to fd 1 (NCCL's version banner under torchrun) must not pollute the JSON line
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--gpus", type=int, default=1)
     ap_.add_argument("--steps", type=int, default=2000)
@@ -357,7 +374,7 @@ def main():
             "clocks": sampler.summary(t_start, t_end) if sampler else None}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(w, os.cpu_count() or 1, min(B, 64))
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -156,12 +156,14 @@ MLXA_D float mel_store_tile(const FwdParams& p, int b, int t0, int nt, const flo
 }
 
 // ---- peak exchange over peer memory (params.cuh: PeakExchange) ------------------------------------
-MLXA_D void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// The (epoch, peak) word is self-contained -- nothing else has to become visible with it -- so relaxed
+// system-scope accesses suffice (a release store made the producer wait ~5 us for its own output writes).
+MLXA_D void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-MLXA_D unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+MLXA_D unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 // one thread of the last CTA of a producer kernel: this rank's final peak to every rank's slot set
@@ -172,7 +174,7 @@ MLXA_D void peak_publish(const PeakExchange& x, float* gmax, unsigned n_ctas) {
     __threadfence();
     const float peak = __int_as_float(atomicMax(reinterpret_cast<int*>(gmax), 0));  // coherent read (values >= 0)
     const unsigned long long v = ((unsigned long long)x.epoch << 32) | (unsigned)__float_as_int(peak);
-    for (int r = 0; r < x.world; ++r) st_release_sys_u64(x.peer_slots[r] + (x.epoch & 1u) * x.world + x.rank, v);
+    for (int r = 0; r < x.world; ++r) st_relaxed_sys_u64(x.peer_slots[r] + (x.epoch & 1u) * x.world + x.rank, v);
 }
 // any thread of a consumer kernel: the maximum over all ranks (spins until every rank has published this
 // epoch; a rank that never arrives traps instead of hanging the GPU)
@@ -180,11 +182,11 @@ MLXA_D float peak_collect(const PeakExchange& x, const unsigned long long* my_sl
     float m = 0.f;
     for (int r = 0; r < x.world; ++r) {
         const unsigned long long* s = my_slots + (x.epoch & 1u) * x.world + r;
-        unsigned long long v = ld_acquire_sys_u64(s);
+        unsigned long long v = ld_relaxed_sys_u64(s);
         for (unsigned spins = 0; (unsigned)(v >> 32) != x.epoch; ++spins) {
             if (spins > (1u << 26)) __trap();
             __nanosleep(64);
-            v = ld_acquire_sys_u64(s);
+            v = ld_relaxed_sys_u64(s);
         }
         m = fmaxf(m, __int_as_float((int)(unsigned)v));
     }

@@ -56,7 +56,8 @@ class PeakExchange:
 
     @classmethod
     def create(cls, device) -> "PeakExchange | None":
-        if not _enabled:
+        import os
+        if not _enabled or os.environ.get("MLXA_NO_PEER_EXCHANGE"):
             return None
         import torch.distributed as dist
         group = _group if _group is not None else dist.group.WORLD
