@@ -15,6 +15,7 @@
 #include "fft_plans_list.cuh"
 #include "fwd_epilogue.cuh"
 #include "fft_mirror.cuh"
+#include "mel_project.cuh"
 
 #ifndef MLXA_NFFT
 #error "compile with -DMLXA_NFFT=<n_fft>"
@@ -46,17 +47,19 @@ constexpr int TWP = (P::TW + 1) & ~1, TWU = (NUNPACK + 1) & ~1;  // table sizes 
 constexpr int round_up4(int v) { return (v + 3) & ~3; }
 
 struct SmemLayout {
-    int in_floats, tw_f2, ep_floats, mel_floats;
+    int in_floats, tw_f2, xch_bytes, mel_floats;
     size_t bytes;
 };
+// EP_MEL: the tile's power spectra are laid out [bin][frame] over the (then dead) exchange buffers and
+// projected with lanes along frames (mel_project.cuh); the bank is in ROW format.
 __host__ __device__ inline SmemLayout smem_layout(int ep, int NG, int hop, int TT, int n_in_buf, int n_bands, long long n_w4, int bank_in_smem) {
     SmemLayout s;
     s.in_floats = round_up4((TT - 1) * hop + NFFT + 8);  // +8: room for a 16-byte alignment lead + tail
     s.tw_f2 = TW_SMEM ? (TWP + TWU) : 0;  // both tables padded to even counts (16-byte multiples)
-    s.ep_floats = (ep == EP_MEL) ? round_up4(n_bands * (TT + 1)) : 0;  // mel staging tile [n_bands][TT+1]
-    s.mel_floats = (ep == EP_MEL && bank_in_smem) ? (int)packed_bank_words(n_bands, n_w4, P::G) : 0;
-    s.bytes = size_t(n_in_buf * s.in_floats + NFFT + s.ep_floats + s.mel_floats) * 4 +
-              size_t(s.tw_f2 + NG * P::BUF) * 8 + 32;
+    const int pt_bytes = (ep == EP_MEL) ? power_tile_rows(NBINS) * power_tile_stride(TT) * 4 : 0;
+    s.xch_bytes = (NG * P::BUF * 8 > pt_bytes) ? NG * P::BUF * 8 : ((pt_bytes + 15) & ~15);
+    s.mel_floats = (ep == EP_MEL && bank_in_smem) ? (int)packed_bank_words(n_bands, n_w4, 1) : 0;
+    s.bytes = size_t(n_in_buf * s.in_floats + NFFT + s.mel_floats) * 4 + size_t(s.tw_f2) * 8 + size_t(s.xch_bytes) + 32;
     return s;
 }
 
@@ -144,8 +147,8 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
     float* s_win = s_in0 + nbuf * lay.in_floats;
     float2* s_tw = reinterpret_cast<float2*>(s_win + NFFT);
     float2* s_buf = s_tw + lay.tw_f2;
-    float* s_ep = reinterpret_cast<float*>(s_buf + NG * P::BUF);
-    float* s_mel = s_ep + lay.ep_floats;
+    float* s_pw = reinterpret_cast<float*>(s_buf);  // EP_MEL: power tile [bins + 3][TT + 2] over the exchange buffers
+    float* s_mel = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_buf) + lay.xch_bytes);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mel + lay.mel_floats);  // [0],[1]: tile buffers, [2]: constants
     __shared__ float s_red[THREADS / 32];
 
@@ -181,14 +184,14 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
     }
     const float2* tw_plan = TW_SMEM ? s_tw : p.tw_plan;
     const float2* tw_unpack = TW_SMEM ? s_tw + TWP : p.tw_unpack;
-    MelSmem ms{};
-    if constexpr (EP == EP_MEL) ms = mel_smem_carve<P::G>(p.bank_in_smem ? s_mel : p.bank, p.n_bands, p.n_w4);
+    RowBank rb{};
+    if constexpr (EP == EP_MEL) rb = row_bank_carve(p.bank_in_smem ? s_mel : p.bank, p.n_w4);
     __syncthreads();
     mbar_wait(s_bar + 2, 0);
 
     const int gi = threadIdx.x / P::G, g = threadIdx.x % P::G;
     float2* buf = s_buf + gi * P::BUF;
-    const int ep_stride = TT + 1;
+    const int PS = power_tile_stride(TT);
     uint32_t ph0 = 0u, ph1 = 0u;  // parity of the next completion on each staging barrier
     float vmax = 0.f;
 
@@ -307,18 +310,22 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
                         }
                     }
                 });
-                __syncwarp();
-                float* pbuf = reinterpret_cast<float*>(buf);
-                static_for<NQ>([&](auto q) {
-                    constexpr int Q = decltype(q)::value;
-                    const int k = g + Q * P::G;
-                    if (Q + 1 < NQ || k < NBINS) {
-                        if constexpr (PACK) pbuf[k] = pw[Q];
-                        else reinterpret_cast<float2*>(pbuf)[k] = make_float2(pw[2 * Q], pw[2 * Q + 1]);
-                    }
-                });
-                __syncwarp();
-                if (va) mel_project_group<P::G, FPT>(ms, p.n_bands, g, pbuf, s_ep, ep_stride, f0);
+                // every group is past its unpack reads: the power tile may overwrite the exchange buffers
+                __syncthreads();
+                if (va) {
+                    float* col = s_pw + f0;
+                    static_for<NQ>([&](auto q) {
+                        constexpr int Q = decltype(q)::value;
+                        const int k = g + Q * P::G;
+                        if (Q + 1 < NQ || k < NBINS) {
+                            if constexpr (PACK) col[k * PS] = pw[Q];
+                            else *reinterpret_cast<float2*>(col + k * PS) = make_float2(pw[2 * Q], pw[2 * Q + 1]);
+                        }
+                    });
+                }
+                for (int i = threadIdx.x; i < 3 * PS; i += THREADS) s_pw[NBINS * PS + i] = 0.f;  // rows padded quads touch
+                __syncthreads();
+                project_power_tile<THREADS, 0, false>(p, rb, s_pw, TT, b, t0, nt, 1.f, vmax);
             } else if (va) {
                 const long long obase = ((long long)b * p.T + t0 + f0) * p.F;
                 if constexpr (PACK) {
@@ -345,11 +352,7 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
             __syncwarp();
         }
 
-        if constexpr (EP == EP_MEL) {
-            __syncthreads();
-            vmax = mel_store_tile<THREADS>(p, b, t0, nt, s_ep, TT, p.log2_tile, vmax);
-        }
-        __syncthreads();  // tile done: its staging buffer and the mel tile may be overwritten
+        __syncthreads();  // tile done: its staging buffer and the power tile may be overwritten
     }
     if constexpr (EP == EP_MEL) {
         if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red, p.xchg);
@@ -455,7 +458,7 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
     int lg = 0;
     while ((1 << lg) < TT) ++lg;
     p.log2_tile = lg;
-    if (ep == EP_MEL && (1 << lg) != TT) return cudaErrorInvalidConfiguration;
+    if (ep == EP_MEL && ((1 << lg) != TT || TT < 2 || TT > kMinBlockFrames)) return cudaErrorInvalidConfiguration;
     const size_t smem = bytes(TT, nbuf);
     if (ep == EP_STFT) return launch_one<EP_STFT, POW_SQUARE>(p, smem, s);
     if (ep == EP_GL) return launch_one<EP_GL, POW_SQUARE>(p, smem, s);
@@ -465,8 +468,8 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
 }
 
 // host tables: plan twiddles and the real-unpack twiddle 0.5*exp(-i*pi*k/N)
-// how the mel kernel of this n_fft wants its filterbank packed: lanes per transform, or 1 = row format
-int MLXA_CAT(plan_group_, MLXA_NFFT)() { return PACK ? P::G : 1; }
+// how the mel kernel of this n_fft wants its filterbank packed: 1 = row format (every planned size)
+int MLXA_CAT(plan_group_, MLXA_NFFT)() { return 1; }
 
 void MLXA_CAT(plan_tables_, MLXA_NFFT)(float2* tw_plan_host, int* n_plan, float2* tw_unpack_host, int* n_unpack) {
     *n_plan = TWP;       // even counts: the tables are bulk-copied in 16-byte units

@@ -20,19 +20,6 @@
 //
 // Included by fwd_inst.cu INSIDE its per-translation-unit namespace, after Tile / tile_info.
 
-// bank packed in ROW format (mlxa_plan_group == 1, see include/mlxa_cuda.h): quad-padded weight runs, then
-// one int4 {start, n4, off4, len} per band
-struct RowBank {
-    const float4* wt4;
-    const int4* desc;
-};
-MLXA_D RowBank row_bank_carve(const float* base, long long n_wt) {
-    RowBank r;
-    r.wt4 = reinterpret_cast<const float4*>(base);
-    r.desc = reinterpret_cast<const int4*>(base + n_wt);
-    return r;
-}
-
 template <class P, int THREADS_>
 struct MelRows {
     static constexpr int N = P::N, G = P::G, R0 = P::R0, R1 = P::R1;
@@ -41,8 +28,7 @@ struct MelRows {
     static_assert(kMinBlockFrames % TT == 0 && TT >= 16, "tiles never straddle a block of minima");
     static constexpr int CTAS_PER_SM = 512 / THREADS;  // 16 warps per SM either way (the register file allows no more)
     static constexpr int NBINS = N / 2 + 1;
-    static constexpr int PS = TT + 2;        // floats per row of the power tile (stride == 2 mod 32: conflict-free)
-    static constexpr int PROWS = NBINS + 3;  // + rows the zero-padded weight quads may touch
+    static constexpr int PS = power_tile_stride(TT), PROWS = power_tile_rows(NBINS);
     static constexpr int TWP = (P::TW + 1) & ~1;
     static constexpr int XCH_BYTES = (NG * P::BUF * 8 > PROWS * PS * 4) ? NG * P::BUF * 8 : PROWS * PS * 4;
     static constexpr int in_floats(int hop) { return ((TT - 1) * hop + N + 8 + 3) & ~3; }
@@ -109,7 +95,6 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
     // pass-0 sample offsets: lane g reads element g + 16*r (+16, cyclically, in the odd group of a warp)
     const int sh = (gi & 1) ? G : 0;
     const int o_last = (gi & 1) ? -G : G * (R0 - 1);
-    const float db_ref = fmaxf(p.db_ref, p.db_amin);
     uint32_t ph0 = 0u, ph1 = 0u;
     float vmax = 0.f;
 
@@ -171,72 +156,8 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
         }
         __syncthreads();
 
-        // ---- band-sparse projection: LB lanes along a band row's frame pairs, 32/LB bands per warp -----
-        {
-            constexpr int LB = TT / 2, SLOTS = (THREADS / 32) * (32 / LB);  // band slots of the CTA per step
-            static_assert(SLOTS == 16, "the boustrophedon below walks the bands 32 at a time");
-            const int fl = lane % LB, slot = warp * (32 / LB) + lane / LB;
-            char* ob = reinterpret_cast<char*>(p.mel + (long long)ti.b * p.n_bands * p.T + ti.t0 + 2 * fl);
-            const float2* q_lane = reinterpret_cast<const float2*>(s_pw) + fl;
-            const unsigned row_bytes = unsigned(p.T) * 4u;
-            // Bands are taken two at a time per lane (two independent accumulation chains and epilogues in
-            // flight: the phase is latency-bound otherwise); band m -> the lane's frames 2*fl, 2*fl + 1 of
-            // row m.  FULL: every frame of the tile exists.
-            float tmin = INFINITY;
-            auto quad = [&](const float4* w4, const float2* q, float2 acc) {
-                const float4 w = *w4;
-                const float2 q0 = q[0], q1 = q[PS / 2], q2 = q[2 * (PS / 2)], q3 = q[3 * (PS / 2)];
-                return caxpy(w.w, q3, caxpy(w.z, q2, caxpy(w.y, q1, caxpy(w.x, q0, acc))));
-            };
-            auto band_pair = [&](auto full_, int mA, int mB) {
-                constexpr bool FULL = decltype(full_)::value;
-                const bool hasA = mA < p.n_bands, hasB = mB < p.n_bands;
-                const int4 dA = hasA ? rb.desc[mA] : make_int4(0, 0, 0, 0);  // start, quads, first quad
-                const int4 dB = hasB ? rb.desc[mB] : make_int4(0, 0, 0, 0);
-                const float4 *wA = rb.wt4 + dA.z, *wB = rb.wt4 + dB.z;
-                const float2 *qA = q_lane + dA.x * (PS / 2), *qB = q_lane + dB.x * (PS / 2);
-                float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
-                int nA = dA.y, nB = dB.y;
-#pragma unroll 1
-                for (; nA > 0 && nB > 0; --nA, --nB, ++wA, ++wB, qA += 4 * (PS / 2), qB += 4 * (PS / 2)) {
-                    accA = quad(wA, qA, accA);
-                    accB = quad(wB, qB, accB);
-                }
-#pragma unroll 1
-                for (; nA > 0; --nA, ++wA, qA += 4 * (PS / 2)) accA = quad(wA, qA, accA);
-#pragma unroll 1
-                for (; nB > 0; --nB, ++wB, qB += 4 * (PS / 2)) accB = quad(wB, qB, accB);
-                float v[4] = {accA.x, accA.y, accB.x, accB.y};
-                if constexpr (!BANK_SMEM) {  // (folded into the staged weights otherwise)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] *= pscale;
-                }
-                const bool ok0 = FULL || 2 * fl < nt, ok1 = FULL || 2 * fl + 1 < nt;
-                const bool st[4] = {ok0 && hasA, ok1 && hasA, ok0 && hasB, ok1 && hasB};
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (st[i]) { vmax = fmaxf(vmax, v[i]); tmin = fminf(tmin, v[i]); }
-                if (p.db_mode) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] = to_db_one(v[i], p.db_coef, p.db_amin, db_ref);
-                }
-                float* oA = reinterpret_cast<float*>(ob + (unsigned long long)unsigned(mA) * row_bytes);
-                float* oB = reinterpret_cast<float*>(ob + (unsigned long long)unsigned(mB) * row_bytes);
-                if (st[0]) oA[0] = v[0];
-                if (st[1]) oA[1] = v[1];
-                if (st[2]) oB[0] = v[2];
-                if (st[3]) oB[1] = v[3];
-            };
-            // boustrophedon over the CTA's 16 band slots: long and short bands mix
-            if (nt == TT) {
-#pragma unroll 1
-                for (int m0 = 0; m0 < p.n_bands; m0 += 32) band_pair(std::true_type{}, m0 + slot, m0 + 31 - slot);
-            } else {
-#pragma unroll 1
-                for (int m0 = 0; m0 < p.n_bands; m0 += 32) band_pair(std::false_type{}, m0 + slot, m0 + 31 - slot);
-            }
-            if (p.block_min != nullptr) block_min_to_global(p, ti.b, ti.t0, tmin);
-        }
+        // ---- band-sparse projection, lanes along frames (mel_project.cuh) -----------------------------
+        project_power_tile<THREADS, TT, !BANK_SMEM>(p, rb, s_pw, TT, ti.b, ti.t0, nt, pscale, vmax);
         __syncthreads();  // power tile consumed: the next tile's transforms may reuse the buffers
     }
     if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red, p.xchg);

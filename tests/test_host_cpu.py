@@ -22,7 +22,7 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in mlxa_cuda.h but not exported"
     assert declared - {"mlxa_last_error", "mlxa_packed_bank_words"} == set(ext.SIGNATURES), "host-layer signature table out of sync"
-    assert ext._ext.mlxa_plan_group(400) == 1 and ext._ext.mlxa_plan_group(2048) == 32 and ext._ext.mlxa_plan_group(777) == 32
+    assert ext._ext.mlxa_plan_group(400) == 1 and ext._ext.mlxa_plan_group(2048) == 1 and ext._ext.mlxa_plan_group(777) == 32
     assert ext._ext.mlxa_abi_version() == ext.ABI_VERSION
     assert ext._ext.mlxa_has_fast_plan(400) == 1 and ext._ext.mlxa_has_fast_plan(2048) == 1
     assert ext._ext.mlxa_has_fast_plan(600) == 0
