@@ -236,14 +236,14 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
                     pass_load_fn<P, 0>(g, v, [&](int n) {
                         const float2 x = *reinterpret_cast<const float2*>(src + 2 * n);
                         const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
-                        if constexpr (EP == EP_GL) return zero ? make_float2(0.f, 0.f) : make_float2(x.x * w.x, x.y * w.y);
-                        else return make_float2(x.x * w.x, x.y * w.y);
+                        if constexpr (EP == EP_GL) return zero ? make_float2(0.f, 0.f) : pmul(x, w.x, w.y);
+                        else return pmul(x, w.x, w.y);
                     });
                 } else {
                     pass_load_fn<P, 0>(g, v, [&](int n) {
                         const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
-                        if constexpr (EP == EP_GL) return zero ? make_float2(0.f, 0.f) : make_float2(src[2 * n] * w.x, src[2 * n + 1] * w.y);
-                        else return make_float2(src[2 * n] * w.x, src[2 * n + 1] * w.y);
+                        if constexpr (EP == EP_GL) return zero ? make_float2(0.f, 0.f) : pmul(make_float2(src[2 * n], src[2 * n + 1]), w.x, w.y);
+                        else return pmul(make_float2(src[2 * n], src[2 * n + 1]), w.x, w.y);
                     });
                 }
             } else {
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
                 pass_load_fn<P, 0>(g, v, [&](int n) {
                     const float w = s_win[n];
                     if constexpr (EP == EP_GL) return make_float2(za ? 0.f : sa[n] * w, zb ? 0.f : sb[n] * w);
-                    else return make_float2(sa[n] * w, sb[n] * w);
+                    else return cscale(make_float2(sa[n], sb[n]), w);
                 });
             }
             pass_compute<P, 0>(g, v, tw_plan);
@@ -285,8 +285,8 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
                     const float2 zk = buf[(Q + 1 == NQ && k == N) ? 0 : k];
                     const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
                     const float2 w = tw_unpack[k];
-                    const float ex = zk.x + zm.x, ey = zk.y - zm.y, ox = zk.y + zm.y, oy = zm.x - zk.x;
-                    return make_float2(fmaf(0.5f, ex, fmaf(ox, w.x, -(oy * w.y))), fmaf(0.5f, ey, fmaf(ox, w.y, oy * w.x)));
+                    const float2 E = cadd_conj(zk, zm), D = csub_conj(zk, zm);  // O = -i D
+                    return caxpy(0.5f, E, cmul(mul_neg_i(D), w));
                 } else {
                     return make_float2(0.f, 0.f);
                 }
