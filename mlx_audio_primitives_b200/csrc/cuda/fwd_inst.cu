@@ -135,7 +135,8 @@ struct TileWalk {
 #include "fwd_mel_rows.cuh"
 
 template <int EP, int PW>
-__global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p) {
+// 16 warps per SM (register cap 128), except the 64-values-per-lane plan: one 8-warp CTA, 255 registers
+__global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threads_for(EP)) fwd_kernel(const FwdParams p) {
     constexpr int THREADS = threads_for(EP);
     constexpr int NG = THREADS / P::G;  // transforms in flight per CTA
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -271,16 +272,47 @@ __global__ void __launch_bounds__(threads_for(EP)) fwd_kernel(const FwdParams p)
                 __syncwarp();
                 pass_compute<P, 2>(g, v, tw_plan);
             }
-            pass_store_natural<P, P::NPASS - 1>(g, v, buf);  // Z[k] at buf[k]
-            __syncwarp();
-
             // ---- unpack the real spectrum, feed the epilogue --------------------------------
             // packed: X[k] = 0.5*(E + w^k O), E = Z[k] + conj Z[N-k], O = -i (Z[k] - conj Z[N-k]);
             //         the table holds 0.5*w^k.   pair: Xa = (Z[k] + conj Z[N-k])/2, Xb = -i (Z[k] - conj Z[N-k])/2.
+            // REG_UNPACK (two-pass packed plans): Z never goes back to shared memory.  After the last pass
+            // (radix R1 over NB = R0 butterflies, lane g runs b = g + G*rd) register [rd][pos(kk)] holds
+            // Z[b + R0*kk]; its Hermitian partner Z[N - b - R0*kk] is leg R1-1-kk of butterfly R0 - b, i.e. of
+            // lane G - g, round RD-1-rd: one warp shuffle per component instead of a natural-order store and
+            // two loads (a shuffle costs one shared-memory wavefront, tools/probes/shfl_probe.cu; the round
+            // trip cost 4 + conflicts).  Lane 0 is its own mirror (leg (R1-kk)%R1 in round 0, R1-1-kk after).
+            // Only the mel epilogue takes this path: it is bound by shared-memory wavefronts; the store-through
+            // epilogues are bound by their global stores and lose more to the longer register lifetimes
+            // (Griffin-Lim c5: 23.6 ms -> 26.0 ms with it).
+            constexpr bool REG_UNPACK = (EP == EP_MEL) && PACK && P::NPASS == 2 && (P::nb(P::NPASS - 1) % P::G == 0);
+            if constexpr (!REG_UNPACK) {
+                pass_store_natural<P, P::NPASS - 1>(g, v, buf);  // Z[k] at buf[k]
+                __syncwarp();
+            }
             constexpr int NQ = ceil_div(NBINS, P::G);
+            const unsigned gmask = (P::G == 32) ? 0xffffffffu : (((1u << (P::G & 31)) - 1u) << (threadIdx.x & 31 & ~(P::G - 1)));
             auto bin = [&](auto q, int k) {
                 constexpr int Q = decltype(q)::value;
-                if constexpr (PACK) {
+                if constexpr (REG_UNPACK) {
+                    constexpr int RD = P::rounds(1), R1 = P::radix(1), N = P::N;
+                    static_assert(RD <= 2, "the self-mirror rule of lane 0 covers one or two rounds");
+                    float2 zk, zm;
+                    if constexpr (Q * P::G >= N) {  // the Nyquist slot k = N (lane 0 only): Z[N] = Z[0]
+                        zk = zm = v[dft_pos(R1, 0)];
+                    } else {
+                        constexpr int rd = Q % RD, kk = Q / RD;
+                        zk = v[rd * R1 + dft_pos(R1, kk)];
+                        const float2 vs = v[(RD - 1 - rd) * R1 + dft_pos(R1, R1 - 1 - kk)];
+                        const int src = (P::G - g) & (P::G - 1);
+                        zm.x = __shfl_sync(gmask, vs.x, src, P::G);
+                        zm.y = __shfl_sync(gmask, vs.y, src, P::G);
+                        const float2 own = v[rd * R1 + dft_pos(R1, rd == 0 ? (R1 - kk) % R1 : R1 - 1 - kk)];
+                        if (g == 0) zm = own;
+                    }
+                    const float2 w = tw_unpack[k];
+                    const float2 E = cadd_conj(zk, zm), D = csub_conj(zk, zm);  // O = -i D
+                    return caxpy(0.5f, E, cmul(mul_neg_i(D), w));
+                } else if constexpr (PACK) {
                     constexpr int N = P::N;
                     const float2 zk = buf[(Q + 1 == NQ && k == N) ? 0 : k];
                     const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
