@@ -363,7 +363,9 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["label"], "clips_per_gpu": B, "samples_per_clip": L, "frames_per_clip": T,
                        "power_to_db": "ref=1.0 amin=1e-10 top_db=80 (batch-global max)",
-                       "parallelism": f"clips sharded x{world}, 1-float all-reduce(MAX)" if world > 1 else "single GPU",
+                       "parallelism": (f"clips sharded x{world}, one-float MAX exchange " +
+                                       ("over peer memory inside the mel / floor kernels" if plan.xchg is not None
+                                        else "by NCCL all-reduce")) if world > 1 else "single GPU",
                        "l2": f"{NBUF} distinct input batches rotated ({NBUF * in_bytes / 1e6:.0f} MB > 126 MB L2)"},
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": in_bytes,
