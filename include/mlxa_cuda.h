@@ -224,6 +224,25 @@ int mlxa_mfcc_tail_f32(const float* mel, int64_t B, int n_mels, int64_t T, const
                        int use_top_db, float top_db, const float* gmax_dev, float* out,
                        void* stream);
 
+/* ---- the callers either side of the path (reference features.py / framing.py) ----------- */
+/* Per-frame spectral statistics over the F bins of each of the B*T frames (reference features.py:57-442; native
+ * twins csrc/primitives/spectral.cpp:8-257).  S is the PHYSICAL (B, T, F) array -- complex64 as written by
+ * mlxa_stft_f32 (is_complex != 0: |X| is formed on load) or float32.  freq: F bin frequencies.  kind:
+ * 0 centroid; 1 bandwidth (p1 = p, norm, optional centroid_in (B*T)); 2 rolloff (p1 = roll_percent);
+ * 3 flatness (p1 = power applied to |X| / S, p2 = amin).  out (B*T). */
+int mlxa_spectral_stats_f32(const void* S, int is_complex, int64_t B, int64_t T, int F, const float* freq,
+                            int kind, float p1, float p2, int norm, const float* centroid_in, float* out,
+                            void* stream);
+/* Per-frame time-domain statistics with the framing done by index arithmetic (centre padding constant or
+ * edge): kind 0 RMS (framing.py:81-151), kind 1 zero-crossing rate (features.py:594-720).
+ * out (B, T), T = 1 + (L + 2*pad - frame_length) / hop. */
+int mlxa_frame_stats_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int frame_length, int hop,
+                         int center, int pad_mode, int kind, float* out, void* stream);
+/* y[n] - coef*y[n-1] with out[0] = y[0] + zi[b] (zi NULL: 2 y[0] - y[1]); zf (optional, B) = y[L-1]
+ * (framing.py:154-295). */
+int mlxa_preemphasis_f32(const float* y, int64_t B, int64_t L, int64_t ldy, float coef, const float* zi,
+                         float* out, float* zf, void* stream);
+
 /* ---- host-buffer convenience (the e2e path: pinned or pageable HOST pointers) ------------ */
 /* log-mel of host clips with chunked H2D / compute / D2H overlap on internal streams.
  * y_host (B, L), out_host (B, n_bands, T), bank_host: packed filterbank in HOST memory.  The dB step is power_to_db(ref, amin, top_db)

@@ -9,7 +9,9 @@ hand-written CUDA kernels behind the C ABI of ``include/mlxa_cuda.h``; there is 
 from ._extension import HAS_CPP_EXT as _HAS_CPP_EXT  # noqa: F401  (loads the CUDA library or raises)
 from .convert import amplitude_to_db, db_to_amplitude, db_to_power, power_to_db
 from .filterbanks import bark_filterbank, bark_to_hz, hz_to_bark, linear_filterbank
-from .framing import frame
+from .features import (spectral_bandwidth, spectral_centroid, spectral_flatness, spectral_rolloff,
+                       zero_crossing_rate)
+from .framing import frame, preemphasis, rms
 from .griffinlim import griffinlim, griffinlim_iter
 from .mel import hz_to_mel, mel_filterbank, mel_to_hz, melspectrogram
 from .mfcc import dct, dct_matrix, mfcc
@@ -27,4 +29,6 @@ __all__ = [
     "dct", "dct_matrix", "mfcc", "griffinlim", "griffinlim_iter", "frame",
     "linear_filterbank", "bark_filterbank", "hz_to_bark", "bark_to_hz",
     "pad_signal", "overlap_add", "distributed", "LogMelPlan",
+    "spectral_centroid", "spectral_bandwidth", "spectral_rolloff", "spectral_flatness",
+    "zero_crossing_rate", "rms", "preemphasis",
 ]

@@ -444,6 +444,34 @@ int mlxa_db_floor_blocks_f32(float* x_db, int64_t B, int n_bands, int64_t T, flo
                                    to_xchg(xchg), (cudaStream_t)stream), "db_floor_blocks");
     return 0;
 }
+int mlxa_spectral_stats_f32(const void* S, int is_complex, int64_t B, int64_t T, int F, const float* freq, int kind, float p1,
+                            float p2, int norm, const float* centroid_in, float* out, void* stream) {
+    CHECK_ARG(S && freq && out && B > 0 && T > 0 && F > 0, "bad argument");
+    CHECK_ARG(kind >= 0 && kind <= 3, "unknown statistic");
+    CHECK_ARG(kind != 1 || p1 > 0.f, "bandwidth needs p > 0");
+    CHECK_ARG(kind != 2 || (p1 >= 0.f && p1 <= 1.f), "roll_percent must be in [0, 1]");
+    CHECK_CUDA(run_spectral_stats(S, is_complex, B * T, F, freq, kind, p1, p2, norm, centroid_in, out, (cudaStream_t)stream),
+               "spectral_stats");
+    return 0;
+}
+int mlxa_frame_stats_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int frame_length, int hop, int center, int pad_mode,
+                         int kind, float* out, void* stream) {
+    CHECK_ARG(y && out && B > 0 && L > 0 && ldy >= L && L < (1LL << 30), "bad argument");
+    CHECK_ARG(frame_length > 0 && hop > 0 && (kind == 0 || kind == 1), "bad frame geometry / statistic");
+    CHECK_ARG(pad_mode == MLXA_PAD_CONSTANT || pad_mode == MLXA_PAD_EDGE, "frame statistics pad with constant or edge");
+    const int pad = center ? frame_length / 2 : 0;
+    const int64_t Lp = L + 2 * (int64_t)pad;
+    CHECK_ARG(Lp >= frame_length, "signal shorter than frame_length");
+    const int64_t T = 1 + (Lp - frame_length) / hop;
+    CHECK_CUDA(run_frame_stats(y, B, (int)L, ldy, frame_length, hop, pad, pad_mode, T, kind, out, (cudaStream_t)stream), "frame_stats");
+    return 0;
+}
+int mlxa_preemphasis_f32(const float* y, int64_t B, int64_t L, int64_t ldy, float coef, const float* zi, float* out, float* zf,
+                         void* stream) {
+    CHECK_ARG(y && out && B > 0 && L > 0 && ldy >= L, "bad argument");
+    CHECK_CUDA(run_preemphasis(y, B, L, ldy, coef, zi, out, zf, (cudaStream_t)stream), "preemphasis");
+    return 0;
+}
 int mlxa_from_db_f32(const float* x, int64_t n, float ref, float div, float* out, void* stream) {
     CHECK_ARG(x && out && n > 0 && div != 0.f, "bad argument");
     CHECK_CUDA(run_from_db(x, n, ref, div, out, (cudaStream_t)stream), "from_db");

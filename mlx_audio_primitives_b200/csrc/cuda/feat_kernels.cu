@@ -1,0 +1,183 @@
+// Per-frame reductions either side of the spectral hot path: spectral
+// centroid / bandwidth / rolloff / flatness over the F bins of every frame (reference features.py:57-442),
+// RMS and zero-crossing rate over the samples of every frame (framing.py:81, features.py:594-720), and
+// pre-emphasis (framing.py:154-295).  One warp per frame; the spectral kernel reads the PHYSICAL (B, T, F)
+// rows the fused STFT produces (complex: |X| is formed on load, so no magnitude pass and no transposed copy)
+// or a real (B, T, F) array.
+#include <cmath>
+#include "fwd_epilogue.cuh"
+#include "util_kernels.cuh"
+
+namespace mlxa {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+// inclusive prefix sum over the 32 lanes
+__device__ __forceinline__ float warp_scan(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+enum : int { STAT_CENTROID = 0, STAT_BANDWIDTH = 1, STAT_ROLLOFF = 2, STAT_FLATNESS = 3 };
+
+// S[row][k]: |X|^power of bin k (power applied only for flatness-from-audio; 1 elsewhere)
+template <bool CPLX>
+__device__ __forceinline__ float spec_value(const void* base, long long row, int F, int k, float power) {
+    float m;
+    if constexpr (CPLX) {
+        const float2 z = __ldg(reinterpret_cast<const float2*>(base) + row * F + k);
+        if (power == 2.0f) return fmaf(z.x, z.x, z.y * z.y);
+        m = sqrtf(fmaf(z.x, z.x, z.y * z.y));
+    } else {
+        m = __ldg(reinterpret_cast<const float*>(base) + row * F + k);
+        if (power == 2.0f) return m * m;
+    }
+    return power == 1.0f ? m : powf(m, power);
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256) spectral_stats_kernel(const void* __restrict__ S, long long rows, int F,
+                                                             const float* __restrict__ freq, int kind, float p1, float p2,
+                                                             int norm, const float* __restrict__ centroid_in,
+                                                             float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+        float res = 0.f;
+        if (kind == STAT_CENTROID || kind == STAT_BANDWIDTH) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int k = lane; k < F; k += 32) {
+                const float v = spec_value<CPLX>(S, row, F, k, 1.0f);
+                s0 += v;
+                s1 = fmaf(__ldg(freq + k), v, s1);
+            }
+            s0 = warp_sum(s0);
+            s1 = warp_sum(s1);
+            const float c = s1 / (s0 + 1e-10f);  // features.py:120-134
+            if (kind == STAT_CENTROID) {
+                res = c;
+            } else {  // features.py:226-271: (sum S |f - c|^p / (sum S + 1e-10))^(1/p), or without the division
+                const float cc = centroid_in ? __ldg(centroid_in + row) : c;
+                float s2 = 0.f;
+                for (int k = lane; k < F; k += 32) {
+                    const float v = spec_value<CPLX>(S, row, F, k, 1.0f);
+                    const float d = fabsf(__ldg(freq + k) - cc);
+                    s2 = fmaf(v, (p1 == 2.0f) ? d * d : powf(d, p1), s2);
+                }
+                s2 = warp_sum(s2);
+                const float q = norm ? s2 / (s0 + 1e-10f) : s2;
+                res = (p1 == 2.0f) ? sqrtf(q) : powf(q, 1.0f / p1);
+            }
+        } else if (kind == STAT_ROLLOFF) {  // features.py:242-271: first bin whose cumulative sum reaches p1 * total
+            float carry = 0.f;
+            for (int k0 = 0; k0 < F; k0 += 32) {
+                const int k = k0 + lane;
+                const float cs = warp_scan(k < F ? spec_value<CPLX>(S, row, F, k, 1.0f) : 0.f, lane);
+                carry += __shfl_sync(kFull, cs, 31);
+            }
+            const float thr = p1 * carry;  // the same blocked scan below reaches exactly `carry`
+            int idx = F - 1;
+            carry = 0.f;
+            for (int k0 = 0; k0 < F; k0 += 32) {
+                const int k = k0 + lane;
+                const float cs = carry + warp_scan(k < F ? spec_value<CPLX>(S, row, F, k, 1.0f) : 0.f, lane);
+                const unsigned hit = __ballot_sync(kFull, k < F && !(cs < thr));
+                if (hit) { idx = k0 + __ffs(hit) - 1; break; }
+                carry = __shfl_sync(kFull, cs, 31);
+            }
+            res = __ldg(freq + idx);
+        } else {  // STAT_FLATNESS, features.py:430-442: exp(mean log max(S, amin)) / (mean max(S, amin) + 1e-10)
+            float sl = 0.f, sa = 0.f;
+            for (int k = lane; k < F; k += 32) {
+                const float v = fmaxf(spec_value<CPLX>(S, row, F, k, p1), p2);
+                sl += logf(v);
+                sa += v;
+            }
+            sl = warp_sum(sl);
+            sa = warp_sum(sa);
+            res = expf(sl / float(F)) / (sa / float(F) + 1e-10f);
+        }
+        if (lane == 0) out[row] = res;
+    }
+}
+
+// kind 0: sqrt(mean x^2) (framing.py:81-151); kind 1: mean of sign changes, the first sample of a frame never
+// counts, sign = (x >= 0) (features.py:594-720).  Frames by index arithmetic on the centre-padded clip.
+__global__ void __launch_bounds__(256) frame_stats_kernel(const float* __restrict__ y, long long B, int L, long long ldy,
+                                                          int frame_length, int hop, int pad, int pad_mode, long long T,
+                                                          int kind, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5), rows = B * T;
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+        const long long b = row / T, t = row - b * T;
+        const float* yb = y + b * ldy;
+        const int s0 = int(t * hop) - pad;
+        float acc = 0.f;
+        if (kind == 0) {
+            for (int i = lane; i < frame_length; i += 32) {
+                const float x = load_padded(yb, L, s0 + i, pad_mode);
+                acc = fmaf(x, x, acc);
+            }
+            acc = sqrtf(warp_sum(acc) / float(frame_length));
+        } else {
+            for (int i = lane + 1; i < frame_length; i += 32) {
+                const bool a = load_padded(yb, L, s0 + i, pad_mode) >= 0.f, c = load_padded(yb, L, s0 + i - 1, pad_mode) >= 0.f;
+                acc += (a != c) ? 1.f : 0.f;
+            }
+            acc = warp_sum(acc) / float(frame_length);
+        }
+        if (lane == 0) out[row] = acc;
+    }
+}
+
+// out[n] = y[n] - coef*y[n-1]; out[0] = y[0] + zi (zi = 2 y[0] - y[1] by default); zf = y[L-1]
+__global__ void preemphasis_kernel(const float* __restrict__ y, long long B, long long L, long long ldy, float coef,
+                                   const float* __restrict__ zi, float* __restrict__ out, float* __restrict__ zf) {
+    const long long n = B * L;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / L, j = i - b * L;
+        const float* yb = y + b * ldy;
+        float v;
+        if (j == 0) v = yb[0] + (zi ? __ldg(zi + b) : (L > 1 ? __fsub_rn(__fmul_rn(2.f, yb[0]), yb[1]) : yb[0]));
+        else v = __fsub_rn(yb[j], __fmul_rn(coef, yb[j - 1]));  // product rounded first, like the reference (bit-exact)
+        out[i] = v;
+        if (zf != nullptr && j == L - 1) zf[b] = yb[j];
+    }
+}
+
+unsigned grid_for_rows(long long rows, int per_cta) {
+    const long long g = (rows + per_cta - 1) / per_cta;
+    return (unsigned)(g < 1 ? 1 : (g > 148LL * 32 ? 148LL * 32 : g));
+}
+}  // namespace
+
+cudaError_t run_spectral_stats(const void* S, int is_complex, long long rows, int F, const float* freq, int kind, float p1,
+                               float p2, int norm, const float* centroid_in, float* out, cudaStream_t s) {
+    const unsigned grid = grid_for_rows(rows, 8);
+    if (is_complex) spectral_stats_kernel<true><<<grid, 256, 0, s>>>(S, rows, F, freq, kind, p1, p2, norm, centroid_in, out);
+    else spectral_stats_kernel<false><<<grid, 256, 0, s>>>(S, rows, F, freq, kind, p1, p2, norm, centroid_in, out);
+    return cudaGetLastError();
+}
+cudaError_t run_frame_stats(const float* y, long long B, int L, long long ldy, int frame_length, int hop, int pad, int pad_mode,
+                            long long T, int kind, float* out, cudaStream_t s) {
+    frame_stats_kernel<<<grid_for_rows(B * T, 8), 256, 0, s>>>(y, B, L, ldy, frame_length, hop, pad, pad_mode, T, kind, out);
+    return cudaGetLastError();
+}
+cudaError_t run_preemphasis(const float* y, long long B, long long L, long long ldy, float coef, const float* zi, float* out,
+                            float* zf, cudaStream_t s) {
+    const long long n = B * L;
+    const long long g = (n + 255) / 256;
+    preemphasis_kernel<<<(unsigned)(g > 148LL * 64 ? 148LL * 64 : g), 256, 0, s>>>(y, B, L, ldy, coef, zi, out, zf);
+    return cudaGetLastError();
+}
+
+}  // namespace mlxa

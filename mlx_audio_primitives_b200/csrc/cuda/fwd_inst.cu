@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             const int f0 = base + gi * FPT;
             const bool va = f0 < nt;  // frames beyond the tile: finite dummy input, results unused
             float2 v[P::E];
+            [[maybe_unused]] bool pair_zero_a = false, pair_zero_b = false;
 
             // ---- pass 0: windowed samples straight from the staged tile --------------------
             if constexpr (PACK) {
@@ -258,6 +259,18 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                     if constexpr (EP == EP_GL) return make_float2(za ? 0.f : sa[n] * w, zb ? 0.f : sb[n] * w);
                     else return cscale(make_float2(sa[n], sb[n]), w);
                 });
+                // A silent frame riding with a loud one would pick up ~1e-7 of its partner's spectrum through
+                // the pair unpack; its true spectrum is exactly zero (as the reference returns), so remember
+                // which of the two frames is all-zero after windowing and store zeros for it.
+                unsigned ora = 0u, orb = 0u;
+                static_for<P::regs(0)>([&](auto i) {
+                    constexpr int I = decltype(i)::value;
+                    ora |= __float_as_uint(v[I].x);
+                    orb |= __float_as_uint(v[I].y);
+                });
+                const unsigned gm = (P::G == 32) ? 0xffffffffu : (((1u << (P::G & 31)) - 1u) << (threadIdx.x & 31 & ~(P::G - 1)));
+                pair_zero_a = __all_sync(gm, (ora << 1) == 0u);
+                pair_zero_b = __all_sync(gm, (orb << 1) == 0u);
             }
             pass_compute<P, 0>(g, v, tw_plan);
             pass_store_buf<P, 0>(g, v, buf);
@@ -375,8 +388,9 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                         if (Q + 1 < NQ || k < NBINS) {
                             const float2 zk = buf[k];
                             const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
-                            epilogue_bin_global<EP>(p, obase + k, make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y)));
-                            if (fb) epilogue_bin_global<EP>(p, obase + p.F + k, make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x)));
+                            const float2 zero = make_float2(0.f, 0.f);
+                            epilogue_bin_global<EP>(p, obase + k, pair_zero_a ? zero : make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y)));
+                            if (fb) epilogue_bin_global<EP>(p, obase + p.F + k, pair_zero_b ? zero : make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x)));
                         }
                     });
                 }

@@ -1,10 +1,10 @@
-"""Framing (reference ``framing.py:16-78`` + ``_frame_impl.py:18-82``)."""
+"""Framing, RMS and pre-emphasis (reference ``framing.py:16-295`` + ``_frame_impl.py:18-82``)."""
 from __future__ import annotations
 
 import torch
 
 from ._extension import _ext, check
-from ._tensor import f32c, ptr, stream_ptr
+from ._tensor import f32c, ptr, stream_ptr, to_tensor
 from ._validation import validate_positive
 
 
@@ -38,3 +38,37 @@ def frame(y, frame_length: int, hop_length: int, axis: int = -1) -> torch.Tensor
         y = y[None, :]
     frames = frame_signal_batched(y, frame_length, hop_length)
     return frames[0] if one_d else frames
+
+
+def rms(y, frame_length: int = 2048, hop_length: int = 512, center: bool = True, pad_mode: str = "constant") -> torch.Tensor:
+    """sqrt(mean(frame^2)) per frame -> (1, T) / (B, 1, T) (reference framing.py:81-151); one kernel, the
+    frames are formed by index arithmetic on the centre-padded clip."""
+    from .features import _frame_stat
+    return _frame_stat(y, frame_length, hop_length, center, pad_mode, 0, ("constant", "edge"))
+
+
+def preemphasis(y, coef: float = 0.97, zi=None, return_zf: bool = False, use_mlx: bool = True):
+    """y[n] - coef*y[n-1]; the first sample is y[0] + zi with zi = 2 y[0] - y[1] by default; zf = y[-1]
+    (reference framing.py:194-295).  ``use_mlx`` is accepted for signature compatibility."""
+    if not 0.0 <= coef <= 1.0:
+        raise ValueError(f"coef must be in [0, 1], got {coef}")
+    y = f32c(y)
+    one_d = y.ndim == 1
+    if one_d:
+        y = y[None, :]
+    if y.ndim != 2:
+        raise ValueError(f"y must be 1D or 2D, got {y.ndim}D")
+    B, L = y.shape
+    z = None
+    if zi is not None:
+        z = to_tensor(zi, torch.float32, y.device).reshape(-1)
+        z = (z if z.numel() == B else z[:1].expand(B)).contiguous()
+    out = torch.empty_like(y)
+    zf = torch.empty((B, 1), dtype=torch.float32, device=y.device) if return_zf else None
+    if B * L:
+        check(_ext.mlxa_preemphasis_f32(ptr(y), B, L, y.stride(0), float(coef), ptr(z), ptr(out), ptr(zf), stream_ptr(y)),
+              "preemphasis")
+    if one_d:
+        out = out[0]
+        zf = zf[0] if zf is not None else None
+    return (out, zf) if return_zf else out

@@ -1,0 +1,132 @@
+"""GPU parity for the section-8(f) rows: spectral centroid / bandwidth / rolloff / flatness, RMS, zero-crossing
+rate and pre-emphasis -- the CUDA path (Python host layer -> C ABI) against oracle/features.py (float64) and
+the committed outputs of the reference's own code (tests/golden/reference_features.npz).  Tolerances follow
+the reference's feature tests (rtol 1e-4 .. 1e-5 against librosa)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import features as of
+from oracle import spectral as o
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ap():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import mlx_audio_primitives_b200 as ap
+    return ap
+
+
+def H(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, b, rtol):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.abs(a - b).max() <= rtol * max(np.abs(b).max(), 1e-30), (np.abs(a - b).max(), np.abs(b).max())
+
+
+def rolloff_close(got, ref, freq_step):
+    """Rolloff is an index decision on a cumulative sum: at most one bin away, and only where the threshold falls
+    within rounding of a cumulative value (a handful of frames)."""
+    assert got.shape == ref.shape
+    d = np.abs(got - ref)
+    assert d.max() <= freq_step * 1.001 and (d > 0).mean() <= 0.01, (d.max(), (d > 0).mean())
+
+
+def test_features_match_reference_fixtures(ap):
+    g = np.load(os.path.join(GOLDEN, "reference_features.npz"))
+    y2 = np.load(os.path.join(GOLDEN, "reference_outputs.npz"))["stft/input"]
+    cases = json.load(open(os.path.join(GOLDEN, "feature_cases.json")))
+    for i, kw in enumerate(cases):
+        sr = kw.get("sr", 22050)
+        k2 = {k: v for k, v in kw.items() if k != "sr"}
+        step = sr / 2.0 / (kw["n_fft"] // 2)
+        close(H(ap.spectral_centroid(y2, sr=sr, **k2)), g[f"centroid/{i}"], 2e-5)
+        close(H(ap.spectral_bandwidth(y2, sr=sr, **k2)), g[f"bandwidth/{i}"], 2e-5)
+        close(H(ap.spectral_bandwidth(y2, sr=sr, p=3.0, norm=False, **k2)), g[f"bandwidth_p3/{i}"], 1e-4)
+        rolloff_close(H(ap.spectral_rolloff(y2, sr=sr, **k2)), g[f"rolloff/{i}"], step)
+        rolloff_close(H(ap.spectral_rolloff(y2, sr=sr, roll_percent=0.5, **k2)), g[f"rolloff50/{i}"], step)
+        close(H(ap.spectral_flatness(y2, **k2)), g[f"flatness/{i}"], 1e-4)
+        close(H(ap.spectral_flatness(y2, power=1.0, amin=1e-6, **k2)), g[f"flatness_p1/{i}"], 1e-4)
+    close(H(ap.spectral_centroid(S=g["S1d"], sr=22050, n_fft=512)), g["centroid_S1d"], 2e-5)
+    rolloff_close(H(ap.spectral_rolloff(S=g["S1d"], sr=22050, n_fft=512)), g["rolloff_S1d"], 22050 / 2 / 256)
+    for key in g.files:
+        parts = key.split("/")
+        if parts[0] in ("rms", "zcr") and len(parts) == 5:
+            fl, hop, center, mode = int(parts[1]), int(parts[2]), bool(int(parts[3])), parts[4]
+            fn = ap.rms if parts[0] == "rms" else ap.zero_crossing_rate
+            close(H(fn(y2, fl, hop, center=center, pad_mode=mode)), g[key], 2e-6 if parts[0] == "rms" else 1e-7)
+    close(H(ap.rms(y2[1], 1024, 256)), g["rms1d"], 2e-6)
+    assert np.array_equal(H(ap.preemphasis(y2)), g["pre/default"])
+    o2, zf = ap.preemphasis(y2, coef=0.9, zi=np.array([0.5, -0.25], np.float32), return_zf=True)
+    assert np.array_equal(H(o2), g["pre/zi"]) and np.array_equal(H(zf), g["pre/zf"])
+    assert np.array_equal(H(ap.preemphasis(y2[0], coef=0.5)), g["pre/1d"])
+
+
+@pytest.mark.parametrize("n_fft,hop,sr", [(2048, 512, 22050), (400, 160, 16000), (1024, 256, 44100), (96, 24, 8000)])
+def test_features_match_float64_oracle(ap, n_fft, hop, sr):
+    rng = np.random.default_rng(n_fft)
+    B, L = 5, 20000 + n_fft
+    t = np.arange(L) / sr
+    y = (np.sin(2 * np.pi * (200 + 3000 * t) * t)[None] * rng.uniform(0.1, 2.0, (B, 1)) + 0.05 * rng.standard_normal((B, L))).astype(np.float32)
+    y[3, : L // 2] = 0.0  # silent frames: the 1e-10 guards decide the value
+    kw = dict(n_fft=n_fft, hop_length=hop)
+    f64 = np.float64
+    close(H(ap.spectral_centroid(y, sr=sr, **kw)), of.spectral_centroid(y, sr=sr, dtype=f64, **kw), 1e-5)
+    close(H(ap.spectral_bandwidth(y, sr=sr, **kw)), of.spectral_bandwidth(y, sr=sr, dtype=f64, **kw), 1e-5)
+    close(H(ap.spectral_bandwidth(y, sr=sr, p=1.5, **kw)), of.spectral_bandwidth(y, sr=sr, p=1.5, dtype=f64, **kw), 1e-4)
+    step = sr / 2.0 / (n_fft // 2)
+    for rp in (0.85, 0.1, 1.0, 0.0):
+        ref = of.spectral_rolloff(y, sr=sr, roll_percent=rp, dtype=f64, **kw)
+        got = H(ap.spectral_rolloff(y, sr=sr, roll_percent=rp, **kw))
+        live = np.abs(o.stft(y, n_fft, hop)).sum(1, keepdims=True) > 0  # all-zero frames: every bin ties
+        rolloff_close(np.where(live, got, 0), np.where(live, ref, 0).astype(np.float32), step)
+    close(H(ap.spectral_flatness(y, **kw)), of.spectral_flatness(y, dtype=f64, **kw), 1e-4)
+    close(H(ap.spectral_flatness(y, power=1.0, amin=1e-6, **kw)), of.spectral_flatness(y, power=1.0, amin=1e-6, dtype=f64, **kw), 1e-4)
+    # a pre-computed spectrogram, in both layouts a caller can hand over
+    S = ap.magnitude(ap.stft(y, **kw))                      # (B, F, T) view of the physical (B, T, F) buffer
+    for Sx in (S, S.contiguous(), S[1]):
+        ref = of.spectral_centroid(S=H(Sx), sr=sr, n_fft=n_fft, dtype=f64)
+        close(H(ap.spectral_centroid(S=Sx, sr=sr, n_fft=n_fft)), ref, 1e-5)
+    cen = ap.spectral_centroid(S=S, sr=sr, n_fft=n_fft)
+    close(H(ap.spectral_bandwidth(S=S, sr=sr, n_fft=n_fft, centroid=cen * 0 + 1000.0)),
+          of.spectral_bandwidth(S=H(S), sr=sr, n_fft=n_fft, centroid=np.full(H(cen).shape, 1000.0), dtype=f64), 1e-5)
+    close(H(ap.spectral_flatness(S=S ** 2)), of.spectral_flatness(S=H(S) ** 2, dtype=f64), 1e-4)
+
+
+@pytest.mark.parametrize("fl,hop,center,mode", [(2048, 512, True, "constant"), (400, 160, True, "edge"), (256, 64, False, "constant"),
+                                                (33, 7, True, "edge")])
+def test_rms_zcr_preemphasis_match_oracle(ap, fl, hop, center, mode):
+    rng = np.random.default_rng(fl)
+    y = rng.standard_normal((3, 9000)).astype(np.float32)
+    y[1, 100:400] = 0.0
+    close(H(ap.rms(y, fl, hop, center=center, pad_mode=mode)), of.rms(y, fl, hop, center=center, pad_mode=mode), 2e-6)
+    assert np.array_equal(H(ap.zero_crossing_rate(y, fl, hop, center=center, pad_mode=mode)),
+                          of.zero_crossing_rate(y, fl, hop, center=center, pad_mode=mode))
+    for coef in (0.97, 0.0, 1.0):
+        assert np.array_equal(H(ap.preemphasis(y, coef=coef)), of.preemphasis(y, coef=coef))
+
+
+def test_feature_errors(ap):
+    y = np.zeros(4000, np.float32)
+    with pytest.raises(ValueError, match="Either y"):
+        ap.spectral_centroid()
+    with pytest.raises(ValueError, match="roll_percent must be <= 1.0"):
+        ap.spectral_rolloff(y, roll_percent=1.5)
+    with pytest.raises(ValueError, match="roll_percent must be >= 0.0"):
+        ap.spectral_rolloff(y, roll_percent=-0.1)
+    with pytest.raises(ValueError, match="coef must be in"):
+        ap.preemphasis(y, coef=1.5)
+    with pytest.raises(ValueError, match="frame_length must be positive"):
+        ap.rms(y, 0, 10)
+    with pytest.raises(ValueError, match="Unknown pad_mode"):
+        ap.zero_crossing_rate(y, pad_mode="reflect")
+    assert tuple(ap.spectral_centroid(y).shape) == (1, 8) and float(ap.spectral_centroid(y).abs().max()) == 0.0

@@ -5,10 +5,14 @@
   3. the libraries the reference's tests use as oracle that exist here
      (torch.stft / istft, torchaudio mel, scipy windows and DCT) at the reference's tolerances.
 """
+import os
+
 import numpy as np
 import pytest
 
 from oracle import spectral as o
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 # ---- 1. reference golden vectors -------------------------------------------
@@ -195,3 +199,48 @@ def test_error_messages():
         o.dct(np.ones(4, np.float32), type=3)
     with pytest.raises(ValueError, match="Unknown init"):
         o.griffinlim(np.ones((5, 3), np.float32), init="ones")
+
+
+# ---------------------------------------------------------------- section 8(f): features, rms, zcr, preemphasis
+def test_feature_oracle_matches_reference_code():
+    """oracle/features.py against the reference's own features.py / framing.py run on the MLX stand-in
+    (tests/golden/generate_golden_features.py -> reference_features.npz)."""
+    import json
+    from oracle import features as of
+    g = np.load(os.path.join(GOLDEN, "reference_features.npz"))
+    y2 = np.load(os.path.join(GOLDEN, "reference_outputs.npz"))["stft/input"]
+    cases = json.load(open(os.path.join(GOLDEN, "feature_cases.json")))
+    assert int(g["ncases"]) == len(cases)
+
+    def close(a, b, rtol):
+        assert a.shape == b.shape, (a.shape, b.shape)
+        assert np.abs(a - b).max() <= rtol * max(np.abs(b).max(), 1e-30), np.abs(a - b).max()
+
+    for i, kw in enumerate(cases):
+        sr = kw.get("sr", 22050)
+        k2 = {k: v for k, v in kw.items() if k != "sr"}
+        close(of.spectral_centroid(y2, sr=sr, **k2), g[f"centroid/{i}"], 2e-6)
+        close(of.spectral_bandwidth(y2, sr=sr, **k2), g[f"bandwidth/{i}"], 5e-6)
+        close(of.spectral_bandwidth(y2, sr=sr, p=3.0, norm=False, **k2), g[f"bandwidth_p3/{i}"], 2e-5)
+        for key, rp in (("rolloff", 0.85), ("rolloff50", 0.5)):
+            got, ref = of.spectral_rolloff(y2, sr=sr, roll_percent=rp, **k2), g[f"{key}/{i}"]
+            assert got.shape == ref.shape and (got != ref).mean() <= 0.01  # a float32 cumsum tie may move one bin
+        close(of.spectral_flatness(y2, **k2), g[f"flatness/{i}"], 2e-5)
+        close(of.spectral_flatness(y2, power=1.0, amin=1e-6, **k2), g[f"flatness_p1/{i}"], 2e-5)
+    close(of.spectral_centroid(S=g["S1d"], sr=22050, n_fft=512), g["centroid_S1d"], 2e-6)
+    assert np.array_equal(of.spectral_rolloff(S=g["S1d"], sr=22050, n_fft=512), g["rolloff_S1d"])
+    for key in g.files:
+        parts = key.split("/")
+        if parts[0] in ("rms", "zcr") and len(parts) == 5:
+            fl, hop, center, mode = int(parts[1]), int(parts[2]), bool(int(parts[3])), parts[4]
+            fn = of.rms if parts[0] == "rms" else of.zero_crossing_rate
+            close(fn(y2, fl, hop, center=center, pad_mode=mode), g[key], 2e-6)
+    close(of.rms(y2[1], 1024, 256), g["rms1d"], 2e-6)
+    assert np.array_equal(of.preemphasis(y2), g["pre/default"])
+    o2, zf = of.preemphasis(y2, coef=0.9, zi=np.array([0.5, -0.25], np.float32), return_zf=True)
+    assert np.array_equal(o2, g["pre/zi"]) and np.array_equal(zf, g["pre/zf"])
+    assert np.array_equal(of.preemphasis(y2[0], coef=0.5), g["pre/1d"])
+    with pytest.raises(ValueError, match="roll_percent must be <= 1.0"):
+        of.spectral_rolloff(y2, roll_percent=1.5)
+    with pytest.raises(ValueError, match="Either y"):
+        of.spectral_centroid()
