@@ -68,7 +68,7 @@ def report(name, label, audio_s, ms, bytes_, flops, extra=None):
 
 def main():
     a = argparse.ArgumentParser()
-    a.add_argument("--configs", default="c1,c2,c3,c4,c5")
+    a.add_argument("--configs", default="c1,c2,c3,c4,c5,f1,f2")
     a.add_argument("--iters", type=int, default=20)
     a.add_argument("--clips-scale", type=float, default=1.0, help="scale the batch (e.g. 0.125 = one of 8 GPUs' share)")
     args = a.parse_args()
@@ -123,6 +123,31 @@ def main():
         by = B * (iters * per_it + 8 * F * T + 4 * L)
         fl = B * T * (iters * (2 * fft_flops(N) + N + 4 * N + 40 * F) + fft_flops(N) + 4 * N)
         report("c5", f"Griffin-Lim 32 it 1024/256 {B}x10 s @22.05k (incl. host RNG init + upload)", B * 10.0, ms, by, fl)
+    if "f1" in want:  # section 8(f) rank 1: the four spectral features of a music batch (C3's shape), from audio
+        B, L, N, hop = max(1, int(1024 * sc * 0.125)), 661500, 2048, 512
+        y = clips(B, L, 22050)
+        T, F = 1 + L // hop, N // 2 + 1
+        kw = dict(sr=22050, n_fft=N, hop_length=hop)
+
+        def feats():
+            ap.spectral_centroid(y, **kw); ap.spectral_bandwidth(y, **kw); ap.spectral_rolloff(y, **kw)
+            ap.spectral_flatness(y, n_fft=N, hop_length=hop)
+        ms = timed(feats, args.iters)
+        # algorithmic: every feature reads the clip once and writes T floats; the current two-launch form also
+        # writes and re-reads the (B, T, F) complex spectrum (8FT + passes x 8FT bytes)
+        report("f1", f"spectral centroid+bandwidth+rolloff+flatness 22.05k 2048/512 {B}x30 s (4 calls from audio)", B * 30.0, ms,
+               4 * B * (4 * L + 4 * T), 4 * B * T * (fft_flops(N) + N + 8 * F),
+               {"moved_bytes_two_launch_form": B * (4 * (4 * L + 8 * F * T) + (1 + 2 + 2 + 1) * 8 * F * T + 4 * 4 * T)})
+    if "f2" in want:  # section 8(f) rank 2: rms + zero-crossing rate + pre-emphasis of the same batch
+        B, L = max(1, int(1024 * sc * 0.125)), 661500
+        y = clips(B, L, 22050)
+        T = 1 + L // 512
+
+        def tdom():
+            ap.rms(y, 2048, 512); ap.zero_crossing_rate(y, 2048, 512); ap.preemphasis(y)
+        ms = timed(tdom, args.iters)
+        report("f2", f"rms+zcr (2048/512)+preemphasis 22.05k {B}x30 s (3 calls)", B * 30.0, ms,
+               B * (2 * (4 * L + 4 * T) + 8 * L), B * (2 * 2 * 2048 * T + 2 * L))
 
 
 if __name__ == "__main__":
