@@ -2,6 +2,7 @@
 // checks, per-device constant tables (twiddles), dispatch to the per-n_fft kernels.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -582,7 +583,12 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
     }
     CHECK_CUDA(cudaEventRecord(ws.done[0], s0), "event");
     for (int i = 1; i < NS; ++i) CHECK_CUDA(cudaStreamWaitEvent(ws.st[i], ws.done[0], 0), "wait");
-    const int64_t chunk = std::max<int64_t>(1, (B + 7) / 8);
+    static const int n_chunks = [] {  // copy / compute overlap granularity (MLXA_HOST_CHUNKS overrides for experiments)
+        const char* e = getenv("MLXA_HOST_CHUNKS");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 1 && v <= 256) ? v : 16;
+    }();
+    const int64_t chunk = std::max<int64_t>(1, (B + n_chunks - 1) / n_chunks);
     const int64_t mel_per_clip = (int64_t)n_bands * T;
     auto d2h = [&](int64_t b0, int64_t nb, cudaStream_t s) {
         return cudaMemcpyAsync(out_host + b0 * mel_per_clip, ws.d_mel + b0 * mel_per_clip,
