@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 TileWalk nxt = cur;
                 nxt.advance();
                 if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0 + (c ^ 1) * lay.in_floats, s_bar + (c ^ 1));
-            } else if (it > 0) {
-                tile_issue_bulk(ti, s_in0, s_bar + 0);
+            } else if (it > 0 && EP != EP_MEL) {
+                tile_issue_bulk(ti, s_in0, s_bar + 0);  // (EP_MEL: already in flight, see below)
             }
         }
         if (ti.nl + ti.nr) {  // CTA-uniform: a clip's first / last tile
@@ -357,6 +357,13 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 });
                 // every group is past its unpack reads: the power tile may overwrite the exchange buffers
                 __syncthreads();
+                // ... and past its reads of the staged samples: with a single staging buffer the next tile's
+                // bulk copy starts now and lands under the projection instead of stalling the next transforms
+                if (nbuf == 1 && threadIdx.x == 0) {
+                    TileWalk nxt = cur;
+                    nxt.advance();
+                    if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0, s_bar + 0);
+                }
                 if (va) {
                     float* col = s_pw + f0;
                     static_for<NQ>([&](auto q) {
