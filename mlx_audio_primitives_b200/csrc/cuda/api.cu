@@ -455,6 +455,26 @@ int mlxa_spectral_stats_f32(const void* S, int is_complex, int64_t B, int64_t T,
                "spectral_stats");
     return 0;
 }
+int mlxa_spectral_feature_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window, int n_fft, int hop,
+                              int center, int pad_mode, const float* freq, int kind, float p1, float p2, int norm,
+                              const float* centroid_in, float* out, void* stream) {
+    CHECK_ARG(freq && out, "null pointer");
+    CHECK_ARG(has_plan(n_fft), "the fused feature kernel needs a compiled plan (mlxa_has_fast_plan)");
+    CHECK_ARG(kind >= 0 && kind <= 3, "unknown statistic");
+    CHECK_ARG(kind != 1 || p1 > 0.f, "bandwidth needs p > 0");
+    CHECK_ARG(kind != 2 || (p1 >= 0.f && p1 <= 1.f), "roll_percent must be in [0, 1]");
+    return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
+        FwdParams p;
+        int rc = fill_fwd_common(p, y + b0 * ldy, nb, L, ldy, window, n_fft, hop, center, pad_mode);
+        if (rc) return rc;
+        p.feat_kind = kind; p.feat_norm = norm; p.feat_p1 = p1; p.feat_p2 = p2;
+        p.feat_freq = freq;
+        p.feat_centroid = centroid_in ? centroid_in + b0 * (int64_t)p.T : nullptr;
+        p.feat_out = out + b0 * (int64_t)p.T;
+        CHECK_CUDA(dispatch_fwd(EP_FEAT, p, (cudaStream_t)stream), "spectral_feature");
+        return 0;
+    });
+}
 int mlxa_frame_stats_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int frame_length, int hop, int center, int pad_mode,
                          int kind, float* out, void* stream) {
     CHECK_ARG(y && out && B > 0 && L > 0 && ldy >= L && L < (1LL << 30), "bad argument");

@@ -27,7 +27,6 @@ __device__ __forceinline__ float warp_scan(float v, int lane) {
     return v;
 }
 
-enum : int { STAT_CENTROID = 0, STAT_BANDWIDTH = 1, STAT_ROLLOFF = 2, STAT_FLATNESS = 3 };
 
 // S[row][k]: |X|^power of bin k (power applied only for flatness-from-audio; 1 elsewhere)
 template <bool CPLX>

@@ -155,6 +155,82 @@ MLXA_D float mel_store_tile(const FwdParams& p, int b, int t0, int nt, const flo
     return vmax;
 }
 
+// ---- EP_FEAT: per-frame spectral statistics by the lane group that produced the spectrum ------------------
+// The lane owns bins k = g + q*G (q < NQ) of one frame in sv[q*STRIDE] (0 beyond the last bin): |X| -- or
+// |X|^power for flatness.  Reductions are shuffles inside the group (gmask); every lane returns the result.
+// Same formulas and guards as feat_kernels.cu / reference features.py:120-442.
+template <int G, int NQ, int STRIDE>
+MLXA_D float group_spectral_stat(const FwdParams& p, const float* sv, int g, unsigned gmask, int n_bins, long long frame) {
+    auto gsum = [&](float v) {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o, G);
+        return v;
+    };
+    const float* fq = p.feat_freq + g;
+    if (p.feat_kind == STAT_FLATNESS) {
+        float sl = 0.f, sa = 0.f;
+        static_for<NQ>([&](auto q) {
+            constexpr int Q = decltype(q)::value;
+            if (g + Q * G < n_bins) {
+                const float v = fmaxf(sv[Q * STRIDE], p.feat_p2);
+                sl += logf(v);
+                sa += v;
+            }
+        });
+        sl = gsum(sl);
+        sa = gsum(sa);
+        return expf(sl / float(n_bins)) / (sa / float(n_bins) + 1e-10f);
+    }
+    if (p.feat_kind == STAT_ROLLOFF) {
+        auto gscan = [&](float v) {
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) {
+                const float t = __shfl_up_sync(gmask, v, o, G);
+                if (g >= o) v += t;
+            }
+            return v;
+        };
+        float total = 0.f;
+        static_for<NQ>([&](auto q) { total += __shfl_sync(gmask, gscan(sv[decltype(q)::value * STRIDE]), G - 1, G); });
+        const float thr = p.feat_p1 * total;  // the same blocked scan below reaches exactly `total`
+        const int base = (threadIdx.x & 31) & ~(G - 1);
+        float carry = 0.f;
+        int idx = -1;
+        static_for<NQ>([&](auto q) {
+            constexpr int Q = decltype(q)::value;
+            const float cs = carry + gscan(sv[Q * STRIDE]);
+            const unsigned hit = (__ballot_sync(gmask, g + Q * G < n_bins && !(cs < thr)) >> base) & (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u));
+            if (idx < 0 && hit) idx = Q * G + __ffs(hit) - 1;
+            carry = __shfl_sync(gmask, cs, G - 1, G);
+        });
+        return __ldg(p.feat_freq + (idx < 0 ? n_bins - 1 : idx));
+    }
+    float s0 = 0.f, s1 = 0.f;
+    static_for<NQ>([&](auto q) {
+        constexpr int Q = decltype(q)::value;
+        if (g + Q * G < n_bins) {
+            s0 += sv[Q * STRIDE];
+            s1 = fmaf(__ldg(fq + Q * G), sv[Q * STRIDE], s1);
+        }
+    });
+    s0 = gsum(s0);
+    s1 = gsum(s1);
+    const float c = s1 / (s0 + 1e-10f);
+    if (p.feat_kind == STAT_CENTROID) return c;
+    const float cc = p.feat_centroid ? __ldg(p.feat_centroid + frame) : c;
+    float s2 = 0.f;
+    static_for<NQ>([&](auto q) {
+        constexpr int Q = decltype(q)::value;
+        if (g + Q * G < n_bins) {
+            const float d = fabsf(__ldg(fq + Q * G) - cc);
+            s2 = fmaf(sv[Q * STRIDE], (p.feat_p1 == 2.0f) ? d * d : powf(d, p.feat_p1), s2);
+        }
+    });
+    s2 = gsum(s2);
+    const float qv = p.feat_norm ? s2 / (s0 + 1e-10f) : s2;
+    return (p.feat_p1 == 2.0f) ? sqrtf(qv) : powf(qv, 1.0f / p.feat_p1);
+}
+
 // ---- peak exchange over peer memory (params.cuh: PeakExchange) ------------------------------------
 // The (epoch, peak) word is self-contained -- nothing else has to become visible with it -- so relaxed
 // system-scope accesses suffice (a release store made the producer wait ~5 us for its own output writes).

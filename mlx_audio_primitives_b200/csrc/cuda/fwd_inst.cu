@@ -207,9 +207,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 TileWalk nxt = cur;
                 nxt.advance();
                 if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0 + (c ^ 1) * lay.in_floats, s_bar + (c ^ 1));
-            } else if (it > 0 && EP != EP_MEL) {
-                tile_issue_bulk(ti, s_in0, s_bar + 0);  // (EP_MEL: already in flight, see below)
-            }
+            }  // one buffer: the copy was started as soon as the previous tile's samples had been read (below)
         }
         if (ti.nl + ti.nr) {  // CTA-uniform: a clip's first / last tile
             tile_fill_edges<THREADS>(p, ti, s_in);
@@ -274,7 +272,19 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             }
             pass_compute<P, 0>(g, v, tw_plan);
             pass_store_buf<P, 0>(g, v, buf);
-            __syncwarp();
+            if (nbuf == 1 && EP != EP_MEL && base + NG * FPT >= nt) {
+                // One staging buffer, last round of the tile: every transform has read its samples, so the next
+                // tile's bulk copy starts now and lands under the rest of this round instead of stalling the
+                // next tile (EP_MEL does the same at its first CTA barrier).
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    TileWalk nxt = cur;
+                    nxt.advance();
+                    if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0, s_bar + 0);
+                }
+            } else {
+                __syncwarp();
+            }
             pass_load_buf<P, 1>(g, v, buf);
             __syncwarp();
             pass_compute<P, 1>(g, v, tw_plan);
@@ -297,7 +307,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             // Only the mel epilogue takes this path: it is bound by shared-memory wavefronts; the store-through
             // epilogues are bound by their global stores and lose more to the longer register lifetimes
             // (Griffin-Lim c5: 23.6 ms -> 26.0 ms with it).
-            constexpr bool REG_UNPACK = (EP == EP_MEL) && PACK && P::NPASS == 2 && (P::nb(P::NPASS - 1) % P::G == 0);
+            constexpr bool REG_UNPACK = (EP == EP_MEL || EP == EP_FEAT) && PACK && P::NPASS == 2 && (P::nb(P::NPASS - 1) % P::G == 0);
             if constexpr (!REG_UNPACK) {
                 pass_store_natural<P, P::NPASS - 1>(g, v, buf);  // Z[k] at buf[k]
                 __syncwarp();
@@ -378,6 +388,37 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 for (int i = threadIdx.x; i < 3 * PS; i += THREADS) s_pw[NBINS * PS + i] = 0.f;  // rows padded quads touch
                 __syncthreads();
                 project_power_tile<THREADS, 0, false>(p, rb, s_pw, TT, b, t0, nt, 1.f, vmax);
+            } else if constexpr (EP == EP_FEAT) {
+                // |X| (|X|^power for flatness) of the lane's bins stays in registers; the statistic of the frame
+                // is reduced inside the lane group and one float per frame is written
+                const bool flat = p.feat_kind == STAT_FLATNESS;
+                auto value = [&](float2 X) {
+                    const float sq = fmaf(X.x, X.x, X.y * X.y);
+                    if (flat && p.feat_p1 == 2.0f) return sq;
+                    const float m = sqrtf(sq);
+                    return (flat && p.feat_p1 != 1.0f) ? powf(m, p.feat_p1) : m;
+                };
+                float sv[NQ * FPT];
+                static_for<NQ>([&](auto q) {
+                    constexpr int Q = decltype(q)::value;
+                    const int k = g + Q * P::G;
+                    const bool ok = (Q + 1 < NQ || k < NBINS);
+                    if constexpr (PACK) {
+                        sv[Q] = ok ? value(bin(q, ok ? k : 0)) : 0.f;
+                    } else {
+                        constexpr int N = P::N;
+                        const float2 zk = buf[ok ? k : 0];
+                        const float2 zm = buf[(!ok || k == 0) ? 0 : N - k];
+                        sv[2 * Q] = (ok && !pair_zero_a) ? value(make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y))) : 0.f;
+                        sv[2 * Q + 1] = (ok && !pair_zero_b) ? value(make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x))) : 0.f;
+                    }
+                });
+                static_for<FPT>([&](auto j) {
+                    constexpr int J = decltype(j)::value;
+                    const long long frame = (long long)b * p.T + t0 + f0 + J;
+                    const float r = group_spectral_stat<P::G, NQ, FPT>(p, sv + J, g, gmask, NBINS, (f0 + J < nt) ? frame : 0);
+                    if (g == 0 && f0 + J < nt) p.feat_out[frame] = r;
+                });
             } else if (va) {
                 const long long obase = ((long long)b * p.T + t0 + f0) * p.F;
                 if constexpr (PACK) {
@@ -515,6 +556,7 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
     const size_t smem = bytes(TT, nbuf);
     if (ep == EP_STFT) return launch_one<EP_STFT, POW_SQUARE>(p, smem, s);
     if (ep == EP_GL) return launch_one<EP_GL, POW_SQUARE>(p, smem, s);
+    if (ep == EP_FEAT) return launch_one<EP_FEAT, POW_SQUARE>(p, smem, s);
     if (p.power_mode == POW_SQUARE) return launch_one<EP_MEL, POW_SQUARE>(p, smem, s);
     if (p.power_mode == POW_ABS) return launch_one<EP_MEL, POW_ABS>(p, smem, s);
     return launch_one<EP_MEL, POW_GENERAL>(p, smem, s);

@@ -5,7 +5,8 @@
 
 namespace mlxa {
 
-enum : int { EP_STFT = 0, EP_MEL = 1, EP_GL = 2 };
+enum : int { EP_STFT = 0, EP_MEL = 1, EP_GL = 2, EP_FEAT = 3 };
+enum : int { STAT_CENTROID = 0, STAT_BANDWIDTH = 1, STAT_ROLLOFF = 2, STAT_FLATNESS = 3 };
 enum : int { POW_SQUARE = 0, POW_ABS = 1, POW_GENERAL = 2 };
 
 // One-float MAX exchange over peer memory (NVLink / NVSwitch), replacing the all-reduce between the mel
@@ -54,6 +55,12 @@ struct FwdParams {
     int blocks_per_clip;  // ceil(T / 64)
     int db_mode;
     float db_coef, db_amin, db_ref;
+    // EP_FEAT: one per-frame spectral statistic (STAT_*), the spectrum never leaves the SM
+    int feat_kind, feat_norm;
+    float feat_p1, feat_p2;        // p | roll_percent | power, amin
+    const float* feat_freq;        // F bin frequencies
+    const float* feat_centroid;    // optional (B, T): bandwidth around a given centroid
+    float* feat_out;               // (B, T)
     // EP_GL
     const float* mag;  // (B, T, F)
     float2* rebuilt;   // (B, T, F), out: mag * X/|X|

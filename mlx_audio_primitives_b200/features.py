@@ -1,8 +1,9 @@
 """Spectral features and zero-crossing rate (reference ``features.py``).
 
-From audio, a feature is two launches -- the fused STFT kernel and one per-frame reduction kernel that reads
-the PHYSICAL (B, T, F) complex spectrum directly (|X| is formed on load: no magnitude pass, no transposed
-copy).  From a pre-computed spectrogram ``S`` (logical (B, F, T), as the reference takes it) the same kernel
+From audio, a feature is ONE kernel for every n_fft with a compiled plan: the fused STFT with a reduction
+epilogue -- |X| stays in the registers of the lane group that produced it and only the (B, T) statistic is
+written.  Other sizes take two launches (STFT + a per-frame reduction kernel that reads the PHYSICAL (B, T, F)
+complex spectrum directly: |X| is formed on load, no magnitude pass, no transposed copy).  From a pre-computed spectrogram ``S`` (logical (B, F, T), as the reference takes it) the same kernel
 runs on its (B, T, F) layout -- zero-copy when ``S`` came from ``magnitude(stft(...))``.  Results have the
 reference's shapes: (1, T) for 1-D input, (B, 1, T) for batches.  ``spectral_contrast`` is not built yet.
 """
@@ -15,7 +16,7 @@ import torch
 
 from ._extension import _ext, check
 from ._tensor import f32c, ptr, require_cuda, stream_ptr, to_tensor
-from .mel import _resolve_stft_args, pad_mode_code
+from .mel import _resolve_stft_args, frames_or_raise, pad_mode_code
 from .stft import _stft_physical
 from .windows import padded_window
 
@@ -69,6 +70,39 @@ def _frames_bins(y, S, n_fft, hop_length, win_length, window, center, pad_mode):
     return X, True, batched
 
 
+def _fused_from_audio(y, S, n_fft, hop_length, win_length, window, center, pad_mode, sr, freq, kind, p1=0.0, p2=0.0,
+                      norm=True, centroid=None):
+    """From audio with a compiled plan for n_fft: ONE kernel (fused STFT + per-frame reduction in the lane group
+    that produced the spectrum; nothing but the (B, T) result is written).  Returns None when the two-launch
+    form has to be used (a spectrogram was supplied, or n_fft has no compiled plan)."""
+    if S is not None or y is None or not _ext.mlxa_has_fast_plan(int(n_fft)):
+        return None
+    hop, win_length = _resolve_stft_args(n_fft, hop_length, win_length)
+    y = f32c(y)
+    batched = y.ndim == 2
+    if not batched:
+        if y.ndim != 1:
+            raise ValueError(f"y must be 1D or 2D, got {y.ndim}D")
+        y = y[None, :]
+    B, L = y.shape
+    T = frames_or_raise(L, n_fft, hop, center, pad_mode)
+    F = n_fft // 2 + 1
+    f = _freq(freq, sr, n_fft, y.device)
+    if f.numel() != F:
+        raise ValueError(f"freq has {f.numel()} entries, the spectrogram has {F} bins")
+    c = None
+    if centroid is not None:
+        c = to_tensor(centroid, torch.float32, y.device).contiguous()
+        if c.numel() != B * T:
+            raise ValueError(f"centroid has {c.numel()} entries for {B * T} frames")
+    win = padded_window(window, win_length, n_fft)
+    out = torch.empty((B, 1, T), dtype=torch.float32, device=y.device)
+    check(_ext.mlxa_spectral_feature_f32(ptr(y), B, L, y.stride(0), ptr(win), n_fft, hop, int(center), pad_mode_code(pad_mode),
+                                         ptr(f), kind, float(p1), float(p2), int(norm), ptr(c), ptr(out), stream_ptr(y)),
+          "spectral_feature")
+    return out if batched else out[0]
+
+
 def _stat(data, is_complex, batched, freq, kind, p1=0.0, p2=0.0, norm=True, centroid=None):
     B, T, F = data.shape
     if freq.numel() != F:
@@ -90,6 +124,9 @@ def spectral_centroid(y=None, sr: int = 22050, S=None, n_fft: int = 2048, hop_le
                       win_length: int | None = None, window="hann", center: bool = True, pad_mode: str = "constant",
                       freq=None) -> torch.Tensor:
     """sum_k f_k S[k] / (sum_k S[k] + 1e-10) per frame (reference features.py:57-134)."""
+    r = _fused_from_audio(y, S, n_fft, hop_length, win_length, window, center, pad_mode, sr, freq, _CENTROID)
+    if r is not None:
+        return r
     data, cplx, batched = _frames_bins(y, S, n_fft, hop_length, win_length, window, center, pad_mode)
     return _stat(data, cplx, batched, _freq(freq, sr, 2 * (data.shape[2] - 1) if S is not None else n_fft, data.device), _CENTROID)
 
@@ -100,6 +137,10 @@ def spectral_bandwidth(y=None, sr: int = 22050, S=None, n_fft: int = 2048, hop_l
     """(sum S |f - centroid|^p / (sum S + 1e-10))^(1/p) (reference features.py:137-271)."""
     if p <= 0:
         raise ValueError(f"p must be positive, got {p}")
+    r = _fused_from_audio(y, S, n_fft, hop_length, win_length, window, center, pad_mode, sr, freq, _BANDWIDTH, p1=p, norm=norm,
+                          centroid=centroid)
+    if r is not None:
+        return r
     data, cplx, batched = _frames_bins(y, S, n_fft, hop_length, win_length, window, center, pad_mode)
     B, T, _ = data.shape
     c = None
@@ -120,6 +161,9 @@ def spectral_rolloff(y=None, sr: int = 22050, S=None, n_fft: int = 2048, hop_len
         raise ValueError(f"roll_percent must be >= 0.0, got {roll_percent}")
     if roll_percent > 1.0:
         raise ValueError(f"roll_percent must be <= 1.0, got {roll_percent}")
+    r = _fused_from_audio(y, S, n_fft, hop_length, win_length, window, center, pad_mode, sr, freq, _ROLLOFF, p1=roll_percent)
+    if r is not None:
+        return r
     data, cplx, batched = _frames_bins(y, S, n_fft, hop_length, win_length, window, center, pad_mode)
     return _stat(data, cplx, batched, _freq(freq, sr, 2 * (data.shape[2] - 1) if S is not None else n_fft, data.device),
                  _ROLLOFF, p1=roll_percent)
@@ -130,6 +174,9 @@ def spectral_flatness(y=None, S=None, n_fft: int = 2048, hop_length: int = 512, 
                       amin: float = 1e-10) -> torch.Tensor:
     """exp(mean log max(S, amin)) / (mean max(S, amin) + 1e-10) with S = |X|^power when computed from audio; a
     supplied S is used as it is (reference features.py:363-442)."""
+    r = _fused_from_audio(y, S, n_fft, hop_length, win_length, window, center, pad_mode, 1, None, _FLATNESS, p1=power, p2=amin)
+    if r is not None:
+        return r
     data, cplx, batched = _frames_bins(y, S, n_fft, hop_length, win_length, window, center, pad_mode)
     f = fft_frequencies_device(1, 2 * (data.shape[2] - 1))  # unused by this statistic; only its length is checked
     return _stat(data, cplx, batched, f, _FLATNESS, p1=(power if S is None else 1.0), p2=amin)
