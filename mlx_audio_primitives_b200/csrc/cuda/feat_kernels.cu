@@ -121,16 +121,43 @@ __global__ void __launch_bounds__(256) frame_stats_kernel(const float* __restric
         const float* yb = y + b * ldy;
         const int s0 = int(t * hop) - pad;
         float acc = 0.f;
+        const bool inside = s0 >= 1 && (long long)s0 + frame_length <= L;  // no padding rule applies (and x[s0 - 1] exists)
         if (kind == 0) {
-            for (int i = lane; i < frame_length; i += 32) {
-                const float x = load_padded(yb, L, s0 + i, pad_mode);
-                acc = fmaf(x, x, acc);
+            if (inside) {  // interior frame: plain coalesced loads, four independent partial sums
+                const float* x = yb + s0;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                int i = lane;
+                for (; i + 96 < frame_length; i += 128) {
+                    const float x0 = __ldg(x + i), x1 = __ldg(x + i + 32), x2 = __ldg(x + i + 64), x3 = __ldg(x + i + 96);
+                    a0 = fmaf(x0, x0, a0); a1 = fmaf(x1, x1, a1); a2 = fmaf(x2, x2, a2); a3 = fmaf(x3, x3, a3);
+                }
+                for (; i < frame_length; i += 32) {
+                    const float x0 = __ldg(x + i);
+                    a0 = fmaf(x0, x0, a0);
+                }
+                acc = (a0 + a1) + (a2 + a3);
+            } else {
+                for (int i = lane; i < frame_length; i += 32) {
+                    const float x = load_padded(yb, L, s0 + i, pad_mode);
+                    acc = fmaf(x, x, acc);
+                }
             }
             acc = sqrtf(warp_sum(acc) / float(frame_length));
         } else {
-            for (int i = lane + 1; i < frame_length; i += 32) {
-                const bool a = load_padded(yb, L, s0 + i, pad_mode) >= 0.f, c = load_padded(yb, L, s0 + i - 1, pad_mode) >= 0.f;
-                acc += (a != c) ? 1.f : 0.f;
+            if (inside) {
+                const float* x = yb + s0;
+                int i = lane + 1;
+                for (; i + 32 < frame_length; i += 64) {
+                    const float c0 = __ldg(x + i), p0 = __ldg(x + i - 1), c1 = __ldg(x + i + 32), p1 = __ldg(x + i + 31);
+                    acc += ((c0 >= 0.f) != (p0 >= 0.f)) ? 1.f : 0.f;
+                    acc += ((c1 >= 0.f) != (p1 >= 0.f)) ? 1.f : 0.f;
+                }
+                for (; i < frame_length; i += 32) acc += ((__ldg(x + i) >= 0.f) != (__ldg(x + i - 1) >= 0.f)) ? 1.f : 0.f;
+            } else {
+                for (int i = lane + 1; i < frame_length; i += 32) {
+                    const bool a = load_padded(yb, L, s0 + i, pad_mode) >= 0.f, c = load_padded(yb, L, s0 + i - 1, pad_mode) >= 0.f;
+                    acc += (a != c) ? 1.f : 0.f;
+                }
             }
             acc = warp_sum(acc) / float(frame_length);
         }
@@ -141,6 +168,24 @@ __global__ void __launch_bounds__(256) frame_stats_kernel(const float* __restric
 // out[n] = y[n] - coef*y[n-1]; out[0] = y[0] + zi (zi = 2 y[0] - y[1] by default); zf = y[L-1]
 __global__ void preemphasis_kernel(const float* __restrict__ y, long long B, long long L, long long ldy, float coef,
                                    const float* __restrict__ zi, float* __restrict__ out, float* __restrict__ zf) {
+    // four samples per thread where the row layout allows 16-byte accesses (product rounded first, then the
+    // subtraction, like the reference: bit-exact)
+    const bool vec = (L % 4 == 0) && (ldy % 4 == 0) && (((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+    const long long L4 = vec ? L / 4 : 0, n4 = B * L4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / L4, j = (i - b * L4) * 4;
+        const float* yb = y + b * ldy;
+        const float4 c = __ldg(reinterpret_cast<const float4*>(yb + j));
+        float4 o;
+        if (j == 0) o.x = c.x + (zi ? __ldg(zi + b) : __fsub_rn(__fmul_rn(2.f, c.x), c.y));
+        else o.x = __fsub_rn(c.x, __fmul_rn(coef, __ldg(yb + j - 1)));
+        o.y = __fsub_rn(c.y, __fmul_rn(coef, c.x));
+        o.z = __fsub_rn(c.z, __fmul_rn(coef, c.y));
+        o.w = __fsub_rn(c.w, __fmul_rn(coef, c.z));
+        *reinterpret_cast<float4*>(out + b * L + j) = o;
+        if (zf != nullptr && j + 4 == L) zf[b] = c.w;
+    }
+    if (vec) return;
     const long long n = B * L;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const long long b = i / L, j = i - b * L;
