@@ -442,7 +442,7 @@ int mlxa_db_floor_blocks_f32(float* x_db, int64_t B, int n_bands, int64_t T, flo
                              const mlxa_peak_exchange* xchg, void* stream) {
     CHECK_ARG(x_db && gmax_dev && block_min && B > 0 && B <= 65535 && n_bands > 0 && T > 0 && top_db > 0, "bad argument");
     CHECK_CUDA(run_db_floor_blocks(x_db, B, n_bands, T, coef, amin, ref, top_db, gmax_dev, block_min, reset_next, n_raised,
-                                   to_xchg(xchg), (cudaStream_t)stream), "db_floor_blocks");
+                                   to_xchg(xchg), nullptr, (cudaStream_t)stream), "db_floor_blocks");
     return 0;
 }
 int mlxa_spectral_stats_f32(const void* S, int is_complex, int64_t B, int64_t T, int F, const float* freq, int kind, float p1,
@@ -641,30 +641,39 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
             CHECK_CUDA(d2h(b0, nb, s), "d2h");
         }
         if (speculate) {
-            int rc = mlxa_db_floor_blocks_f32(ws.d_mel, B, n_bands, T, 10.0f, amin, ref, top_db, ws.d_gmax, ws.d_bmin, nullptr,
-                                              ws.d_raised, nullptr, s0);
-            if (rc) return rc;
-            CHECK_CUDA(cudaMemcpyAsync(ws.h_raised, ws.d_raised, sizeof(int) * (size_t)(1 + B * nblk), cudaMemcpyDeviceToHost, s0), "d2h list");
-            for (int i = 0; i < NS; ++i) CHECK_CUDA(cudaStreamSynchronize(ws.st[i]), "sync");
-            const int n_raised = ws.h_raised[0];
-            if (n_raised > B * nblk / 4) {  // the floor bit widely: whole clips again, in runs
-                std::vector<char> hit((size_t)B, 0);
-                for (int i = 0; i < n_raised; ++i) hit[ws.h_raised[1 + i] / nblk] = 1;
-                ci = 0;
-                for (int64_t b0 = 0; b0 < B; ++ci) {
-                    if (!hit[b0]) { ++b0; continue; }
-                    int64_t b1 = b0;
-                    while (b1 < B && hit[b1]) ++b1;
-                    CHECK_CUDA(d2h(b0, b1 - b0, ws.st[ci % NS]), "d2h again");
-                    b0 = b1;
-                }
-            } else {  // a few blocks: strided copies of just those (n_bands rows of <= 64 frames)
-                for (int i = 0; i < n_raised; ++i) {
-                    const int64_t slot = ws.h_raised[1 + i], b = slot / nblk, t0 = (slot - b * nblk) * MLXA_MIN_BLOCK_FRAMES;
-                    const int64_t off = b * mel_per_clip + t0;
-                    const size_t width = sizeof(float) * (size_t)std::min<int64_t>(MLXA_MIN_BLOCK_FRAMES, T - t0);
-                    CHECK_CUDA(cudaMemcpy2DAsync(out_host + off, sizeof(float) * T, ws.d_mel + off, sizeof(float) * T, width,
-                                                 (size_t)n_bands, cudaMemcpyDeviceToHost, ws.st[i % NS]), "d2h block");
+            // Pinned result buffer: the floor kernel patches the few raised values straight into it over PCIe
+            // (it already holds the speculative copy); otherwise the rewritten blocks are listed and re-copied.
+            float* mirror = nullptr;
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, out_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+                mirror = static_cast<float*>(pa.devicePointer);
+            else
+                (void)cudaGetLastError();
+            CHECK_CUDA(run_db_floor_blocks(ws.d_mel, B, n_bands, T, 10.0f, amin, ref, top_db, ws.d_gmax, ws.d_bmin, nullptr,
+                                           mirror ? nullptr : ws.d_raised, PeakExchange{}, mirror, s0), "db_floor_blocks");
+            if (!mirror) {
+                CHECK_CUDA(cudaMemcpyAsync(ws.h_raised, ws.d_raised, sizeof(int) * (size_t)(1 + B * nblk), cudaMemcpyDeviceToHost, s0), "d2h list");
+                for (int i = 0; i < NS; ++i) CHECK_CUDA(cudaStreamSynchronize(ws.st[i]), "sync");
+                const int n_raised = ws.h_raised[0];
+                if (n_raised > B * nblk / 4) {  // the floor bit widely: whole clips again, in runs
+                    std::vector<char> hit((size_t)B, 0);
+                    for (int i = 0; i < n_raised; ++i) hit[ws.h_raised[1 + i] / nblk] = 1;
+                    ci = 0;
+                    for (int64_t b0 = 0; b0 < B; ++ci) {
+                        if (!hit[b0]) { ++b0; continue; }
+                        int64_t b1 = b0;
+                        while (b1 < B && hit[b1]) ++b1;
+                        CHECK_CUDA(d2h(b0, b1 - b0, ws.st[ci % NS]), "d2h again");
+                        b0 = b1;
+                    }
+                } else {  // a few blocks: strided copies of just those (n_bands rows of <= 64 frames)
+                    for (int i = 0; i < n_raised; ++i) {
+                        const int64_t slot = ws.h_raised[1 + i], b = slot / nblk, t0 = (slot - b * nblk) * MLXA_MIN_BLOCK_FRAMES;
+                        const int64_t off = b * mel_per_clip + t0;
+                        const size_t width = sizeof(float) * (size_t)std::min<int64_t>(MLXA_MIN_BLOCK_FRAMES, T - t0);
+                        CHECK_CUDA(cudaMemcpy2DAsync(out_host + off, sizeof(float) * T, ws.d_mel + off, sizeof(float) * T, width,
+                                                     (size_t)n_bands, cudaMemcpyDeviceToHost, ws.st[i % NS]), "d2h block");
+                    }
                 }
             }
         }

@@ -206,6 +206,8 @@ __global__ void db_floor_kernel(float* __restrict__ x, long long n, float coef, 
 // The same floor with the producer's per-block minima (mlxa_melspec_f32 block_min): a 64-frame block of a
 // clip whose smallest value is already at or above the floor is not touched at all, so on material without
 // 80 dB of dynamic range the pass reads B*ceil(T/64) floats.  Consumed slots are re-armed to +inf.
+// host_mirror (optional): a device-accessible alias of a pinned HOST copy of x that already holds the values
+// from before the floor (the host path's speculative copy-back); raised values are patched into it directly.
 // A CTA looks at kSlotsPerCta (clip, block) slots at once -- one thread each, one barrier -- and then
 // rewrites the flagged ones with all of its warps (a CTA per slot costs ~16 us in launch + barrier latency
 // for the 3008 slots of a 64 x 30 s batch even when nothing is flagged; tools/probes/floor_probe.cu).
@@ -213,7 +215,7 @@ constexpr int kSlotsPerCta = 8, kFloorThreads = 512;
 __global__ void __launch_bounds__(kFloorThreads)
 db_floor_blocks_kernel(float* __restrict__ x, long long n_slots, int n_bands, long long T, float coef, float amin, float ref,
                        float top_db, const float* __restrict__ gmax, float* __restrict__ block_min, float* reset_next,
-                       int* n_raised, PeakExchange xchg) {
+                       int* n_raised, PeakExchange xchg, float* __restrict__ host_mirror) {
     if (reset_next != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *reset_next = 0.f;
     __shared__ float s_peak;
     const float refc = fmaxf(ref, amin);
@@ -255,8 +257,14 @@ db_floor_blocks_kernel(float* __restrict__ x, long long n_slots, int n_bands, lo
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int m = m0 + u * NW;
-                if (v0[u] < floor_db) xb[(long long)m * T] = floor_db;
-                if (v1[u] < floor_db) xb[(long long)m * T + 32] = floor_db;
+                if (v0[u] < floor_db) {
+                    xb[(long long)m * T] = floor_db;
+                    if (host_mirror != nullptr) host_mirror[(xb - x) + (long long)m * T] = floor_db;
+                }
+                if (v1[u] < floor_db) {
+                    xb[(long long)m * T + 32] = floor_db;
+                    if (host_mirror != nullptr) host_mirror[(xb - x) + (long long)m * T + 32] = floor_db;
+                }
             }
         }
     }
@@ -525,12 +533,12 @@ cudaError_t run_db_floor(float* x, long long n, float coef, float amin, float re
 }
 cudaError_t run_db_floor_blocks(float* x, long long B, int n_bands, long long T, float coef, float amin, float ref,
                                 float top_db, const float* gmax, float* block_min, float* reset_next, int* n_raised,
-                                const PeakExchange& xchg, cudaStream_t s) {
+                                const PeakExchange& xchg, float* host_mirror, cudaStream_t s) {
     const long long n_slots = B * ((T + kMinBlockFrames - 1) / kMinBlockFrames);
     const long long grid = (n_slots + kSlotsPerCta - 1) / kSlotsPerCta;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     db_floor_blocks_kernel<<<(unsigned)grid, kFloorThreads, 0, s>>>(x, n_slots, n_bands, T, coef, amin, ref, top_db, gmax,
-                                                                     block_min, reset_next, n_raised, xchg);
+                                                                     block_min, reset_next, n_raised, xchg, host_mirror);
     return cudaGetLastError();
 }
 cudaError_t run_from_db(const float* x, long long n, float ref, float div, float* out, cudaStream_t s) {

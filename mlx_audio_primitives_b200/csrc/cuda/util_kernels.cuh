@@ -22,7 +22,7 @@ cudaError_t run_db_floor(float* x, long long n, float coef, float amin, float re
                          float* reset_next, cudaStream_t s);
 cudaError_t run_db_floor_blocks(float* x, long long B, int n_bands, long long T, float coef, float amin, float ref,
                                 float top_db, const float* gmax, float* block_min, float* reset_next, int* n_raised,
-                                const PeakExchange& xchg, cudaStream_t s);
+                                const PeakExchange& xchg, float* host_mirror, cudaStream_t s);
 cudaError_t run_from_db(const float* x, long long n, float ref, float div, float* out, cudaStream_t s);
 cudaError_t run_dct(const float* x, long long rows, int n_in, const float* D, int n_out, float* out, cudaStream_t s);
 cudaError_t run_mfcc_tail(const float* mel, long long B, int n_mels, long long T, const float* D, int n_mfcc,
