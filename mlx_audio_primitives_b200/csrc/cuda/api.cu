@@ -601,8 +601,8 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
         CHECK_CUDA(cudaMemsetAsync(ws.d_raised, 0, sizeof(int), s0), "memset");
         CHECK_CUDA(run_fill(ws.d_bmin, B * nblk, INFINITY, s0), "fill block minima");
     }
-    CHECK_CUDA(cudaEventRecord(ws.done[0], s0), "event");
-    for (int i = 1; i < NS; ++i) CHECK_CUDA(cudaStreamWaitEvent(ws.st[i], ws.done[0], 0), "wait");
+    CHECK_CUDA(cudaEventRecord(ws.done[0], s0), "event");  // constants ready: awaited by each stream before its first KERNEL,
+    bool waited[NS] = {true};                                 // so the first clips are already crossing PCIe meanwhile
     static const int n_chunks = [] {  // copy / compute overlap granularity (MLXA_HOST_CHUNKS overrides for experiments)
         const char* e = getenv("MLXA_HOST_CHUNKS");
         const int v = e ? atoi(e) : 0;
@@ -617,8 +617,13 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
     int ci = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk, ++ci) {
         const int64_t nb = std::min(chunk, B - b0);
-        cudaStream_t s = ws.st[ci % NS];
+        const int si = (ci + 1) % NS;  // the first chunks go to streams that are not busy with the constants
+        cudaStream_t s = ws.st[si];
         CHECK_CUDA(cudaMemcpyAsync(ws.d_y + b0 * L, y_host + b0 * L, sizeof(float) * (size_t)nb * L, cudaMemcpyHostToDevice, s), "h2d");
+        if (!waited[si]) {
+            CHECK_CUDA(cudaStreamWaitEvent(s, ws.done[0], 0), "wait");
+            waited[si] = true;
+        }
         int rc = mlxa_melspec_f32(ws.d_y + b0 * L, nb, L, L, ws.d_win, n_fft, hop, center, pad_mode, power, ws.d_bank,
                                   n_bands, n_w4, ws.d_mel + b0 * mel_per_clip, need_max ? ws.d_gmax : nullptr, fuse_db ? 1 : 0, 10.0f,
                                   amin, ref, speculate ? ws.d_bmin + b0 * nblk : nullptr, nullptr, s);
