@@ -236,11 +236,13 @@ int mlxa_spectral_stats_f32(const void* S, int is_complex, int64_t B, int64_t T,
 /* The same statistics FROM AUDIO in one kernel: pad -> frame -> window -> rFFT as mlxa_stft_f32, |X| kept in the
  * registers of the lane group that produced it, the statistic reduced by shuffles inside the group -- the
  * spectrum is never written.  n_fft must have a compiled plan (mlxa_has_fast_plan); other sizes use
- * mlxa_stft_f32 + mlxa_spectral_stats_f32.  out (B, T). */
+ * mlxa_stft_f32 + mlxa_spectral_stats_f32.  freq_step > 0 declares freq[k] == k * freq_step (the default
+ * linspace(0, sr/2, F)): centroid / bandwidth then skip the table reads (rolloff always reads its one entry).
+ * out (B, T). */
 int mlxa_spectral_feature_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window,
-                              int n_fft, int hop, int center, int pad_mode, const float* freq, int kind,
-                              float p1, float p2, int norm, const float* centroid_in, float* out,
-                              void* stream);
+                              int n_fft, int hop, int center, int pad_mode, const float* freq,
+                              float freq_step, int kind, float p1, float p2, int norm,
+                              const float* centroid_in, float* out, void* stream);
 /* Per-frame time-domain statistics with the framing done by index arithmetic (centre padding constant or
  * edge): kind 0 RMS (framing.py:81-151), kind 1 zero-crossing rate (features.py:594-720).
  * out (B, T), T = 1 + (L + 2*pad - frame_length) / hop. */

@@ -456,8 +456,8 @@ int mlxa_spectral_stats_f32(const void* S, int is_complex, int64_t B, int64_t T,
     return 0;
 }
 int mlxa_spectral_feature_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window, int n_fft, int hop,
-                              int center, int pad_mode, const float* freq, int kind, float p1, float p2, int norm,
-                              const float* centroid_in, float* out, void* stream) {
+                              int center, int pad_mode, const float* freq, float freq_step, int kind, float p1, float p2,
+                              int norm, const float* centroid_in, float* out, void* stream) {
     CHECK_ARG(freq && out, "null pointer");
     CHECK_ARG(has_plan(n_fft), "the fused feature kernel needs a compiled plan (mlxa_has_fast_plan)");
     CHECK_ARG(kind >= 0 && kind <= 3, "unknown statistic");
@@ -469,6 +469,7 @@ int mlxa_spectral_feature_f32(const float* y, int64_t B, int64_t L, int64_t ldy,
         if (rc) return rc;
         p.feat_kind = kind; p.feat_norm = norm; p.feat_p1 = p1; p.feat_p2 = p2;
         p.feat_freq = freq;
+        p.feat_freq_step = freq_step;
         p.feat_centroid = centroid_in ? centroid_in + b0 * (int64_t)p.T : nullptr;
         p.feat_out = out + b0 * (int64_t)p.T;
         CHECK_CUDA(dispatch_fwd(EP_FEAT, p, (cudaStream_t)stream), "spectral_feature");

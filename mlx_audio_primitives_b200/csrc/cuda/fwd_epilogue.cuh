@@ -167,6 +167,8 @@ MLXA_D float group_spectral_stat(const FwdParams& p, const float* sv, int g, uns
         return v;
     };
     const float* fq = p.feat_freq + g;
+    const float step = p.feat_freq_step;
+    auto freq_at = [&](int q_times_g) { return step > 0.f ? float(g + q_times_g) * step : __ldg(fq + q_times_g); };
     if (p.feat_kind == STAT_FLATNESS) {
         float sl = 0.f, sa = 0.f;
         static_for<NQ>([&](auto q) {
@@ -210,7 +212,7 @@ MLXA_D float group_spectral_stat(const FwdParams& p, const float* sv, int g, uns
         constexpr int Q = decltype(q)::value;
         if (g + Q * G < n_bins) {
             s0 += sv[Q * STRIDE];
-            s1 = fmaf(__ldg(fq + Q * G), sv[Q * STRIDE], s1);
+            s1 = fmaf(freq_at(Q * G), sv[Q * STRIDE], s1);
         }
     });
     s0 = gsum(s0);
@@ -222,7 +224,7 @@ MLXA_D float group_spectral_stat(const FwdParams& p, const float* sv, int g, uns
     static_for<NQ>([&](auto q) {
         constexpr int Q = decltype(q)::value;
         if (g + Q * G < n_bins) {
-            const float d = fabsf(__ldg(fq + Q * G) - cc);
+            const float d = fabsf(freq_at(Q * G) - cc);
             s2 = fmaf(sv[Q * STRIDE], (p.feat_p1 == 2.0f) ? d * d : powf(d, p.feat_p1), s2);
         }
     });

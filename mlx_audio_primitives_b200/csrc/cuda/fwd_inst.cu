@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 auto value = [&](float2 X) {
                     const float sq = fmaf(X.x, X.x, X.y * X.y);
                     if (flat && p.feat_p1 == 2.0f) return sq;
-                    const float m = sqrtf(sq);
+                    const float m = sq > 0.f ? sq * rsqrtf(sq) : 0.f;  // |X| to 2 ulp on the SFU (sqrtf is ~8 instructions per bin)
                     return (flat && p.feat_p1 != 1.0f) ? powf(m, p.feat_p1) : m;
                 };
                 float sv[NQ * FPT];

@@ -59,6 +59,7 @@ struct FwdParams {
     int feat_kind, feat_norm;
     float feat_p1, feat_p2;        // p | roll_percent | power, amin
     const float* feat_freq;        // F bin frequencies
+    float feat_freq_step;          // > 0: the frequencies are k * step (default linspace): no table reads
     const float* feat_centroid;    // optional (B, T): bandwidth around a given centroid
     float* feat_out;               // (B, T)
     // EP_GL

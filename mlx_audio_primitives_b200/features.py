@@ -98,7 +98,8 @@ def _fused_from_audio(y, S, n_fft, hop_length, win_length, window, center, pad_m
     win = padded_window(window, win_length, n_fft)
     out = torch.empty((B, 1, T), dtype=torch.float32, device=y.device)
     check(_ext.mlxa_spectral_feature_f32(ptr(y), B, L, y.stride(0), ptr(win), n_fft, hop, int(center), pad_mode_code(pad_mode),
-                                         ptr(f), kind, float(p1), float(p2), int(norm), ptr(c), ptr(out), stream_ptr(y)),
+                                         ptr(f), (float(sr) / 2.0 / (F - 1)) if freq is None else 0.0, kind, float(p1), float(p2),
+                                         int(norm), ptr(c), ptr(out), stream_ptr(y)),
           "spectral_feature")
     return out if batched else out[0]
 
