@@ -91,6 +91,9 @@ int mlxa_window_sumsquare_f32(const float* window, int n_fft, int hop, int64_t T
 int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window,
                   int n_fft, int hop, int center, int pad_mode, mlxa_c64* spec, void* stream);
 
+/* 1 when mlxa_spectral_feature_f32 serves n_fft (a compiled plan whose lane groups fit one warp). */
+int mlxa_has_fused_feature(int n_fft);
+
 /* How the mel kernel that serves n_fft wants its filterbank packed: the lanes per transform (4..32;
  * 32 for sizes without a compiled plan), or 1 = ROW format (n_fft = 400). */
 int mlxa_plan_group(int n_fft);
@@ -235,7 +238,7 @@ int mlxa_spectral_stats_f32(const void* S, int is_complex, int64_t B, int64_t T,
                             void* stream);
 /* The same statistics FROM AUDIO in one kernel: pad -> frame -> window -> rFFT as mlxa_stft_f32, |X| kept in the
  * registers of the lane group that produced it, the statistic reduced by shuffles inside the group -- the
- * spectrum is never written.  n_fft must have a compiled plan (mlxa_has_fast_plan); other sizes use
+ * spectrum is never written.  n_fft must satisfy mlxa_has_fused_feature; other sizes use
  * mlxa_stft_f32 + mlxa_spectral_stats_f32.  freq_step > 0 declares freq[k] == k * freq_step (the default
  * linspace(0, sr/2, F)): centroid / bandwidth then skip the table reads (rolloff always reads its one entry).
  * out (B, T). */

@@ -20,6 +20,7 @@ _i64, _i32, _f32, _p = C.c_int64, C.c_int, C.c_float, C.c_void_p
 SIGNATURES = {
     "mlxa_abi_version": [],
     "mlxa_has_fast_plan": [_i32],
+    "mlxa_has_fused_feature": [_i32],
     "mlxa_pad_signal_f32": [_p, _i64, _i64, _i64, _i32, _p, _p],
     "mlxa_frame_signal_f32": [_p, _i64, _i64, _i32, _i32, _p, _p],
     "mlxa_overlap_add_f32": [_p, _p, _i64, _i64, _i32, _i32, _i64, _p, _p],

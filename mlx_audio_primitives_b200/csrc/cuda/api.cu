@@ -220,6 +220,15 @@ int mlxa_plan_group(int n_fft) {
     return 32;  // O(n^2) DFT kernels: one warp per frame
 }
 
+int mlxa_has_fused_feature(int n_fft) {
+    switch (n_fft) {
+#define X(NF) case NF: return plan_fused_feature_##NF();
+        X(64) X(128) X(256) X(400) X(512) X(1024) X(2048) X(4096)
+#undef X
+    }
+    return 0;
+}
+
 int64_t mlxa_packed_bank_words(int n_bands, int64_t n_wt, int group) { return packed_bank_words(n_bands, n_wt, group); }
 
 int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, int group, float* packed_host,
@@ -459,7 +468,7 @@ int mlxa_spectral_feature_f32(const float* y, int64_t B, int64_t L, int64_t ldy,
                               int center, int pad_mode, const float* freq, float freq_step, int kind, float p1, float p2,
                               int norm, const float* centroid_in, float* out, void* stream) {
     CHECK_ARG(freq && out, "null pointer");
-    CHECK_ARG(has_plan(n_fft), "the fused feature kernel needs a compiled plan (mlxa_has_fast_plan)");
+    CHECK_ARG(mlxa_has_fused_feature(n_fft), "no fused feature kernel for this n_fft (mlxa_has_fused_feature)");
     CHECK_ARG(kind >= 0 && kind <= 3, "unknown statistic");
     CHECK_ARG(kind != 1 || p1 > 0.f, "bandwidth needs p > 0");
     CHECK_ARG(kind != 2 || (p1 >= 0.f && p1 <= 1.f), "roll_percent must be in [0, 1]");

@@ -172,6 +172,17 @@ MLXA_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memor
 MLXA_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 MLXA_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Synchronise the G lanes that share a transform: a (sub-)warp for G <= 32, the two warps of a 64-lane group
+// through named barrier 1 + group index otherwise (barrier 0 is __syncthreads; at most 15 groups per CTA).
+template <int G>
+MLXA_D void group_sync(int group_in_cta) {
+    if constexpr (G <= 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(group_in_cta + 1), "n"(G) : "memory");
+    }
+}
+
 MLXA_D bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(

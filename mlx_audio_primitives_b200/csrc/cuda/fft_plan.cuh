@@ -19,7 +19,7 @@ struct FftPlan {
     static constexpr int N = N_, G = G_, R0 = R0_, R1 = R1_, R2 = R2_;
     static constexpr int NPASS = (R2_ > 1) ? 3 : 2;
     static_assert(R0_ * R1_ * R2_ == N_, "radices must multiply to N");
-    static_assert(32 % G_ == 0, "group must divide a warp");
+    static_assert(32 % G_ == 0 || G_ == 64, "a group is a divisor of a warp, or two warps (exchange through a named barrier)");
     static constexpr int radix(int p) { return p == 0 ? R0 : (p == 1 ? R1 : R2); }
     static constexpr int ns(int p) { return p == 0 ? 1 : (p == 1 ? R0 : R0 * R1); }
     static constexpr int nb(int p) { return N / radix(p); }

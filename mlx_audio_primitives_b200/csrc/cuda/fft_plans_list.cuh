@@ -23,7 +23,14 @@ MLXA_PLAN(400, MODE_PAIR, 400, 16, 25, 16)
 MLXA_PLAN(512, MODE_PACK, 256, 16, 16, 16)
 MLXA_PLAN(1024, MODE_PACK, 512, 16, 32, 16)
 MLXA_PLAN(2048, MODE_PACK, 1024, 32, 32, 32)
-MLXA_PLAN(4096, MODE_PACK, 2048, 32, 64, 32)
+#ifndef MLXA_PLAN_4096_TWO_WARPS
+MLXA_PLAN(4096, MODE_PACK, 2048, 32, 64, 32)     // one warp, 64 values per lane: 255 registers, 8 warps per SM
+#else
+// Two warps per transform (group_sync = named barrier), 32 values per lane, 16 warps per SM.  Parity-green but
+// slower (MFCC c4 1.93 ms vs 1.80 ms): three passes and an unpack through shared memory cost more wavefronts
+// than the doubled occupancy hides.  Kept for experiments (-DMLXA_PLAN_4096_TWO_WARPS).
+MLXA_PLAN(4096, MODE_PACK, 2048, 64, 32, 8, 8)
+#endif
 #undef MLXA_PLAN
 
 // X(macro) over every planned n_fft

@@ -36,7 +36,7 @@ constexpr int FPT = PACK ? 1 : 2;                              // frames per tra
 // warps in one CTA either way (8.4 KB of exchange buffer per warp), n_fft 4096 runs 8 warps (64 complex
 // values per lane).
 constexpr int threads_for(int ep) {
-    return (P::E > 32) ? 256 : ((P::G == 32 && P::E == 32) ? 512 : ((ep == EP_MEL && P::N >= 400) ? 512 : 256));
+    return (P::E > 32) ? 256 : ((P::G >= 32 && P::E == 32) ? 512 : ((ep == EP_MEL && P::N >= 400) ? 512 : 256));
 }
 static_assert(P::BUF % 2 == 0 && NFFT % 4 == 0, "smem carve-up assumes 16-byte multiples");
 constexpr int NBINS = NFFT / 2 + 1;
@@ -283,16 +283,16 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                     if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0, s_bar + 0);
                 }
             } else {
-                __syncwarp();
+                group_sync<P::G>(gi);
             }
             pass_load_buf<P, 1>(g, v, buf);
-            __syncwarp();
+            group_sync<P::G>(gi);
             pass_compute<P, 1>(g, v, tw_plan);
             if constexpr (P::NPASS == 3) {
                 pass_store_buf<P, 1>(g, v, buf);
-                __syncwarp();
+                group_sync<P::G>(gi);
                 pass_load_buf<P, 2>(g, v, buf);
-                __syncwarp();
+                group_sync<P::G>(gi);
                 pass_compute<P, 2>(g, v, tw_plan);
             }
             // ---- unpack the real spectrum, feed the epilogue --------------------------------
@@ -307,10 +307,11 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             // Only the mel epilogue takes this path: it is bound by shared-memory wavefronts; the store-through
             // epilogues are bound by their global stores and lose more to the longer register lifetimes
             // (Griffin-Lim c5: 23.6 ms -> 26.0 ms with it).
-            constexpr bool REG_UNPACK = (EP == EP_MEL || EP == EP_FEAT) && PACK && P::NPASS == 2 && (P::nb(P::NPASS - 1) % P::G == 0);
+            constexpr bool REG_UNPACK = (EP == EP_MEL || EP == EP_FEAT) && PACK && P::NPASS == 2 && P::G <= 32 &&
+                                        (P::nb(P::NPASS - 1) % P::G == 0) && P::rounds(1) <= 2;  // (lane 0's self-mirror rule covers <= 2 rounds)
             if constexpr (!REG_UNPACK) {
                 pass_store_natural<P, P::NPASS - 1>(g, v, buf);  // Z[k] at buf[k]
-                __syncwarp();
+                group_sync<P::G>(gi);
             }
             constexpr int NQ = ceil_div(NBINS, P::G);
             const unsigned gmask = (P::G == 32) ? 0xffffffffu : (((1u << (P::G & 31)) - 1u) << (threadIdx.x & 31 & ~(P::G - 1)));
@@ -318,7 +319,6 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 constexpr int Q = decltype(q)::value;
                 if constexpr (REG_UNPACK) {
                     constexpr int RD = P::rounds(1), R1 = P::radix(1), N = P::N;
-                    static_assert(RD <= 2, "the self-mirror rule of lane 0 covers one or two rounds");
                     float2 zk, zm;
                     if constexpr (Q * P::G >= N) {  // the Nyquist slot k = N (lane 0 only): Z[N] = Z[0]
                         zk = zm = v[dft_pos(R1, 0)];
@@ -388,6 +388,8 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 for (int i = threadIdx.x; i < 3 * PS; i += THREADS) s_pw[NBINS * PS + i] = 0.f;  // rows padded quads touch
                 __syncthreads();
                 project_power_tile<THREADS, 0, false>(p, rb, s_pw, TT, b, t0, nt, 1.f, vmax);
+            } else if constexpr (EP == EP_FEAT && P::G > 32) {
+                // (not reachable: the launcher refuses EP_FEAT for two-warp groups -- the reductions are warp shuffles)
             } else if constexpr (EP == EP_FEAT) {
                 // |X| (|X|^power for flatness) of the lane's bins stays in registers; the statistic of the frame
                 // is reduced inside the lane group and one float per frame is written
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                     });
                 }
             }
-            __syncwarp();
+            group_sync<P::G>(gi);
         }
 
         __syncthreads();  // tile done: its staging buffer and the power tile may be overwritten
@@ -556,7 +558,7 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
     const size_t smem = bytes(TT, nbuf);
     if (ep == EP_STFT) return launch_one<EP_STFT, POW_SQUARE>(p, smem, s);
     if (ep == EP_GL) return launch_one<EP_GL, POW_SQUARE>(p, smem, s);
-    if (ep == EP_FEAT) return launch_one<EP_FEAT, POW_SQUARE>(p, smem, s);
+    if (ep == EP_FEAT) return (P::G <= 32) ? launch_one<EP_FEAT, POW_SQUARE>(p, smem, s) : cudaErrorNotSupported;
     if (p.power_mode == POW_SQUARE) return launch_one<EP_MEL, POW_SQUARE>(p, smem, s);
     if (p.power_mode == POW_ABS) return launch_one<EP_MEL, POW_ABS>(p, smem, s);
     return launch_one<EP_MEL, POW_GENERAL>(p, smem, s);
@@ -565,6 +567,8 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
 // host tables: plan twiddles and the real-unpack twiddle 0.5*exp(-i*pi*k/N)
 // how the mel kernel of this n_fft wants its filterbank packed: 1 = row format (every planned size)
 int MLXA_CAT(plan_group_, MLXA_NFFT)() { return 1; }
+// the fused per-frame statistics reduce with warp shuffles: plans whose groups fit a warp
+int MLXA_CAT(plan_fused_feature_, MLXA_NFFT)() { return P::G <= 32 ? 1 : 0; }
 
 void MLXA_CAT(plan_tables_, MLXA_NFFT)(float2* tw_plan_host, int* n_plan, float2* tw_unpack_host, int* n_unpack) {
     *n_plan = TWP;       // even counts: the tables are bulk-copied in 16-byte units

@@ -30,7 +30,7 @@ constexpr bool PACK = (PF::MODE == MODE_PACK);
 constexpr int FPT = PACK ? 1 : 2;
 // warps per CTA: sized so that the exchange buffers of all resident transforms fill the SM's shared memory
 // (n_fft 2048: 16 warps x 8.4 KB; n_fft 4096: 8 warps x 16.6 KB with 64 complex values per lane)
-constexpr int THREADS = (P::E > 32) ? 256 : ((P::G == 32) ? 512 : 256);
+constexpr int THREADS = (P::E > 32) ? 256 : ((P::G >= 32) ? 512 : 256);
 constexpr int NG = THREADS / P::G;
 constexpr int NUNPACK = PACK ? P::N + 1 : 0;
 constexpr int TWP = (P::TW + 1) & ~1, TWU = (NUNPACK + 1) & ~1;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
                     });
                 }
             }
-            __syncwarp();
+            group_sync<P::G>(gi);
             static_for<NQ2>([&](auto q) {
                 constexpr int Q = decltype(q)::value;
                 const int k = g + Q * P::G;
@@ -186,23 +186,23 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
                 }
             });
         }
-        __syncwarp();
+        group_sync<P::G>(gi);
         pass_load_fn<P, 0>(g, v, [&](int n) { return buf[n]; });
-        __syncwarp();
+        group_sync<P::G>(gi);
         pass_compute<P, 0>(g, v, tw_plan);
         pass_store_buf<P, 0>(g, v, buf);
-        __syncwarp();
+        group_sync<P::G>(gi);
         pass_load_buf<P, 1>(g, v, buf);
-        __syncwarp();
+        group_sync<P::G>(gi);
         if constexpr (PACK && P::NPASS == 2) {
             if (fa + NG * FPT <= f_hi) prefetch_frame(fa + NG * FPT);  // buffer is free: fetch the next round's frame
         }
         pass_compute<P, 1>(g, v, tw_plan);
         if constexpr (P::NPASS == 3) {
             pass_store_buf<P, 1>(g, v, buf);
-            __syncwarp();
+            group_sync<P::G>(gi);
             pass_load_buf<P, 2>(g, v, buf);
-            __syncwarp();
+            group_sync<P::G>(gi);
             if constexpr (PACK) {
                 if (fa + NG * FPT <= f_hi) prefetch_frame(fa + NG * FPT);
             }

@@ -95,6 +95,7 @@ struct InvParams {
     cudaError_t launch_fwd_##NF(int ep, FwdParams& p, cudaStream_t s);                     \
     cudaError_t launch_inv_##NF(InvParams& p, cudaStream_t s);                             \
     int plan_group_##NF();                                                                  \
+    int plan_fused_feature_##NF();                                                          \
     void plan_tables_##NF(float2* tw_plan_host, int* n_plan, float2* tw_unpack_host, int* n_unpack);
 
 // naive O(n^2) DFT fallback for any other n_fft

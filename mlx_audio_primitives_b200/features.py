@@ -75,7 +75,7 @@ def _fused_from_audio(y, S, n_fft, hop_length, win_length, window, center, pad_m
     """From audio with a compiled plan for n_fft: ONE kernel (fused STFT + per-frame reduction in the lane group
     that produced the spectrum; nothing but the (B, T) result is written).  Returns None when the two-launch
     form has to be used (a spectrogram was supplied, or n_fft has no compiled plan)."""
-    if S is not None or y is None or not _ext.mlxa_has_fast_plan(int(n_fft)):
+    if S is not None or y is None or not _ext.mlxa_has_fused_feature(int(n_fft)):
         return None
     hop, win_length = _resolve_stft_args(n_fft, hop_length, win_length)
     y = f32c(y)
