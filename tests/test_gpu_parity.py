@@ -337,7 +337,8 @@ def test_db_family(ap, golden):
         ap.power_to_db(x, top_db=0)
 
 
-@pytest.mark.parametrize("n_fft,hop,n_mels,sr", [(400, 160, 80, 16000), (1024, 256, 64, 22050), (600, 150, 40, 16000)])
+@pytest.mark.parametrize("n_fft,hop,n_mels,sr", [(400, 160, 80, 16000), (1024, 256, 64, 22050), (600, 150, 40, 16000),
+                                                 (2048, 512, 128, 22050), (4096, 1024, 96, 44100), (64, 16, 12, 8000), (256, 64, 33, 8000)])
 @pytest.mark.parametrize("ref", [1.0, 0.37, "max"])
 def test_logmel_plan_floor_paths_same_bits(ap, n_fft, hop, n_mels, sr, ref):
     """LogMelPlan fuses dB into the mel kernel and applies top_db block-wise (only 64-frame blocks whose
