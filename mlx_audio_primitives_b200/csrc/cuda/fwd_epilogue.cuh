@@ -159,7 +159,7 @@ MLXA_D float mel_store_tile(const FwdParams& p, int b, int t0, int nt, const flo
 // The lane owns bins k = g + q*G (q < NQ) of one frame in sv[q*STRIDE] (0 beyond the last bin): |X| -- or
 // |X|^power for flatness.  Reductions are shuffles inside the group (gmask); every lane returns the result.
 // Same formulas and guards as feat_kernels.cu / reference features.py:120-442.
-template <int G, int NQ, int STRIDE>
+template <int KIND, int G, int NQ, int STRIDE>
 MLXA_D float group_spectral_stat(const FwdParams& p, const float* sv, int g, unsigned gmask, int n_bins, long long frame) {
     auto gsum = [&](float v) {
 #pragma unroll
@@ -169,7 +169,7 @@ MLXA_D float group_spectral_stat(const FwdParams& p, const float* sv, int g, uns
     const float* fq = p.feat_freq + g;
     const float step = p.feat_freq_step;
     auto freq_at = [&](int q_times_g) { return step > 0.f ? float(g + q_times_g) * step : __ldg(fq + q_times_g); };
-    if (p.feat_kind == STAT_FLATNESS) {
+    if constexpr (KIND == STAT_FLATNESS) {
         float sl = 0.f, sa = 0.f;
         static_for<NQ>([&](auto q) {
             constexpr int Q = decltype(q)::value;
@@ -183,7 +183,7 @@ MLXA_D float group_spectral_stat(const FwdParams& p, const float* sv, int g, uns
         sa = gsum(sa);
         return expf(sl / float(n_bins)) / (sa / float(n_bins) + 1e-10f);
     }
-    if (p.feat_kind == STAT_ROLLOFF) {
+    if constexpr (KIND == STAT_ROLLOFF) {
         auto gscan = [&](float v) {
 #pragma unroll
             for (int o = 1; o < G; o <<= 1) {
@@ -207,30 +207,37 @@ MLXA_D float group_spectral_stat(const FwdParams& p, const float* sv, int g, uns
         });
         return __ldg(p.feat_freq + (idx < 0 ? n_bins - 1 : idx));
     }
-    float s0 = 0.f, s1 = 0.f;
-    static_for<NQ>([&](auto q) {
-        constexpr int Q = decltype(q)::value;
-        if (g + Q * G < n_bins) {
-            s0 += sv[Q * STRIDE];
-            s1 = fmaf(freq_at(Q * G), sv[Q * STRIDE], s1);
+    if constexpr (KIND == STAT_CENTROID || KIND == STAT_BANDWIDTH) {
+        float s0 = 0.f, s1 = 0.f;
+        static_for<NQ>([&](auto q) {
+            constexpr int Q = decltype(q)::value;
+            if (g + Q * G < n_bins) {
+                s0 += sv[Q * STRIDE];
+                s1 = fmaf(freq_at(Q * G), sv[Q * STRIDE], s1);
+            }
+        });
+        s0 = gsum(s0);
+        s1 = gsum(s1);
+        const float c = s1 / (s0 + 1e-10f);
+        if constexpr (KIND == STAT_CENTROID) {
+            return c;
+        } else {
+            const float cc = p.feat_centroid ? __ldg(p.feat_centroid + frame) : c;
+            const bool square = p.feat_p1 == 2.0f;
+            float s2 = 0.f;
+            static_for<NQ>([&](auto q) {
+                constexpr int Q = decltype(q)::value;
+                if (g + Q * G < n_bins) {
+                    const float d = fabsf(freq_at(Q * G) - cc);
+                    s2 = fmaf(sv[Q * STRIDE], square ? d * d : powf(d, p.feat_p1), s2);
+                }
+            });
+            s2 = gsum(s2);
+            const float qv = p.feat_norm ? s2 / (s0 + 1e-10f) : s2;
+            return square ? sqrtf(qv) : powf(qv, 1.0f / p.feat_p1);
         }
-    });
-    s0 = gsum(s0);
-    s1 = gsum(s1);
-    const float c = s1 / (s0 + 1e-10f);
-    if (p.feat_kind == STAT_CENTROID) return c;
-    const float cc = p.feat_centroid ? __ldg(p.feat_centroid + frame) : c;
-    float s2 = 0.f;
-    static_for<NQ>([&](auto q) {
-        constexpr int Q = decltype(q)::value;
-        if (g + Q * G < n_bins) {
-            const float d = fabsf(freq_at(Q * G) - cc);
-            s2 = fmaf(sv[Q * STRIDE], (p.feat_p1 == 2.0f) ? d * d : powf(d, p.feat_p1), s2);
-        }
-    });
-    s2 = gsum(s2);
-    const float qv = p.feat_norm ? s2 / (s0 + 1e-10f) : s2;
-    return (p.feat_p1 == 2.0f) ? sqrtf(qv) : powf(qv, 1.0f / p.feat_p1);
+    }
+    return 0.f;
 }
 
 // ---- peak exchange over peer memory (params.cuh: PeakExchange) ------------------------------------

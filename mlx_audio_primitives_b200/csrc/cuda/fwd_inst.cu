@@ -393,12 +393,17 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             } else if constexpr (EP == EP_FEAT) {
                 // |X| (|X|^power for flatness) of the lane's bins stays in registers; the statistic of the frame
                 // is reduced inside the lane group and one float per frame is written
-                const bool flat = p.feat_kind == STAT_FLATNESS;
+                constexpr int KIND = PW;  // EP_FEAT instantiates the kernel per statistic (the PW slot carries STAT_*)
+                constexpr bool flat = KIND == STAT_FLATNESS;
+                const bool flat_sq = p.feat_p1 == 2.0f, flat_abs = p.feat_p1 == 1.0f;
                 auto value = [&](float2 X) {
                     const float sq = fmaf(X.x, X.x, X.y * X.y);
-                    if (flat && p.feat_p1 == 2.0f) return sq;
+                    if constexpr (flat) {
+                        if (flat_sq) return sq;
+                    }
                     const float m = sq > 0.f ? sq * rsqrtf(sq) : 0.f;  // |X| to 2 ulp on the SFU (sqrtf is ~8 instructions per bin)
-                    return (flat && p.feat_p1 != 1.0f) ? powf(m, p.feat_p1) : m;
+                    if constexpr (flat) return flat_abs ? m : powf(m, p.feat_p1);
+                    else return m;
                 };
                 float sv[NQ * FPT];
                 static_for<NQ>([&](auto q) {
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 static_for<FPT>([&](auto j) {
                     constexpr int J = decltype(j)::value;
                     const long long frame = (long long)b * p.T + t0 + f0 + J;
-                    const float r = group_spectral_stat<P::G, NQ, FPT>(p, sv + J, g, gmask, NBINS, (f0 + J < nt) ? frame : 0);
+                    const float r = group_spectral_stat<KIND, P::G, NQ, FPT>(p, sv + J, g, gmask, NBINS, (f0 + J < nt) ? frame : 0);
                     if (g == 0 && f0 + J < nt) p.feat_out[frame] = r;
                 });
             } else if (va) {
@@ -558,7 +563,15 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
     const size_t smem = bytes(TT, nbuf);
     if (ep == EP_STFT) return launch_one<EP_STFT, POW_SQUARE>(p, smem, s);
     if (ep == EP_GL) return launch_one<EP_GL, POW_SQUARE>(p, smem, s);
-    if (ep == EP_FEAT) return (P::G <= 32) ? launch_one<EP_FEAT, POW_SQUARE>(p, smem, s) : cudaErrorNotSupported;
+    if (ep == EP_FEAT) {
+        if (P::G > 32) return cudaErrorNotSupported;
+        switch (p.feat_kind) {
+            case STAT_CENTROID: return launch_one<EP_FEAT, STAT_CENTROID>(p, smem, s);
+            case STAT_BANDWIDTH: return launch_one<EP_FEAT, STAT_BANDWIDTH>(p, smem, s);
+            case STAT_ROLLOFF: return launch_one<EP_FEAT, STAT_ROLLOFF>(p, smem, s);
+            default: return launch_one<EP_FEAT, STAT_FLATNESS>(p, smem, s);
+        }
+    }
     if (p.power_mode == POW_SQUARE) return launch_one<EP_MEL, POW_SQUARE>(p, smem, s);
     if (p.power_mode == POW_ABS) return launch_one<EP_MEL, POW_ABS>(p, smem, s);
     return launch_one<EP_MEL, POW_GENERAL>(p, smem, s);
