@@ -236,6 +236,13 @@ int mlxa_mfcc_tail_f32(const float* mel, int64_t B, int n_mels, int64_t T, const
 int mlxa_spectral_stats_f32(const void* S, int is_complex, int64_t B, int64_t T, int F, const float* freq,
                             int kind, float p1, float p2, int norm, const float* centroid_in, float* out,
                             void* stream);
+/* Spectral contrast (features.py:445-592; host NumPy in the reference): per frame and band, mean of the nq
+ * largest minus mean of the nq smallest magnitudes of the band's bins, as a difference of 10*log10 values
+ * (linear == 0) or plainly.  S as for mlxa_spectral_stats_f32; bands: n_out DEVICE triples {first bin, bin
+ * count, nq} produced on the host by the reference's band-edge rules (a band with count 0 yields 0);
+ * out (B, n_out, T). */
+int mlxa_spectral_contrast_f32(const void* S, int is_complex, int64_t B, int64_t T, int F,
+                               const int32_t* bands, int n_out, int linear, float* out, void* stream);
 /* The same statistics FROM AUDIO in one kernel: pad -> frame -> window -> rFFT as mlxa_stft_f32, |X| kept in the
  * registers of the lane group that produced it, the statistic reduced by shuffles inside the group -- the
  * spectrum is never written.  n_fft must satisfy mlxa_has_fused_feature; other sizes use

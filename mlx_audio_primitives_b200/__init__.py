@@ -9,7 +9,7 @@ hand-written CUDA kernels behind the C ABI of ``include/mlxa_cuda.h``; there is 
 from ._extension import HAS_CPP_EXT as _HAS_CPP_EXT  # noqa: F401  (loads the CUDA library or raises)
 from .convert import amplitude_to_db, db_to_amplitude, db_to_power, power_to_db
 from .filterbanks import bark_filterbank, bark_to_hz, hz_to_bark, linear_filterbank
-from .features import (spectral_bandwidth, spectral_centroid, spectral_flatness, spectral_rolloff,
+from .features import (spectral_bandwidth, spectral_centroid, spectral_contrast, spectral_flatness, spectral_rolloff,
                        zero_crossing_rate)
 from .framing import frame, preemphasis, rms
 from .griffinlim import griffinlim, griffinlim_iter
@@ -29,6 +29,6 @@ __all__ = [
     "dct", "dct_matrix", "mfcc", "griffinlim", "griffinlim_iter", "frame",
     "linear_filterbank", "bark_filterbank", "hz_to_bark", "bark_to_hz",
     "pad_signal", "overlap_add", "distributed", "LogMelPlan",
-    "spectral_centroid", "spectral_bandwidth", "spectral_rolloff", "spectral_flatness",
+    "spectral_centroid", "spectral_bandwidth", "spectral_rolloff", "spectral_flatness", "spectral_contrast",
     "zero_crossing_rate", "rms", "preemphasis",
 ]

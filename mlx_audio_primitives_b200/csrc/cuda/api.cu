@@ -464,6 +464,12 @@ int mlxa_spectral_stats_f32(const void* S, int is_complex, int64_t B, int64_t T,
                "spectral_stats");
     return 0;
 }
+int mlxa_spectral_contrast_f32(const void* S, int is_complex, int64_t B, int64_t T, int F, const int32_t* bands, int n_out,
+                               int linear, float* out, void* stream) {
+    CHECK_ARG(S && bands && out && B > 0 && T > 0 && F > 0 && n_out > 0, "bad argument");
+    CHECK_CUDA(run_spectral_contrast(S, is_complex, B, T, F, bands, n_out, linear, out, (cudaStream_t)stream), "spectral_contrast");
+    return 0;
+}
 int mlxa_spectral_feature_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float* window, int n_fft, int hop,
                               int center, int pad_mode, const float* freq, float freq_step, int kind, float p1, float p2,
                               int norm, const float* centroid_in, float* out, void* stream) {

@@ -109,6 +109,68 @@ __global__ void __launch_bounds__(256) spectral_stats_kernel(const void* __restr
     }
 }
 
+// Spectral contrast (features.py:445-592, host NumPy in the reference): per frame and octave band, the mean of the
+// nq smallest ("valley") and of the nq largest ("peak") magnitudes of the band's bins.  One warp per frame: the
+// frame's magnitudes are parked in the warp's shared-memory slice once, then each band is scanned nq-at-most
+// times -- round j extracts the next distinct value beyond the last one taken, together with its multiplicity
+// (ties count like in a sort), so no sort and no per-lane arrays are needed and any band width works.
+// bands: (lo, n, nq) triples as computed on the host by the reference's edge rules.
+template <bool CPLX>
+__global__ void __launch_bounds__(256) spectral_contrast_kernel(const void* __restrict__ S, long long B, long long T, int F,
+                                                                const int* __restrict__ bands, int n_out, int linear,
+                                                                float* __restrict__ out) {
+    extern __shared__ float s_mag[];  // [warps][F]
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    float* m = s_mag + (size_t)wi * F;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5), rows = B * T;
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wi; row < rows; row += warps) {
+        __syncwarp();
+        for (int k = lane; k < F; k += 32) m[k] = spec_value<CPLX>(S, row, F, k, 1.0f);
+        __syncwarp();
+        const long long b = row / T, t = row - b * T;
+        for (int band = 0; band < n_out; ++band) {
+            const int lo = __ldg(bands + 3 * band), n = __ldg(bands + 3 * band + 1), nq = __ldg(bands + 3 * band + 2);
+            float res[2] = {0.f, 0.f};  // valley, peak
+            if (n > 0) {
+#pragma unroll
+                for (int top = 0; top < 2; ++top) {
+                    float last = top ? INFINITY : -INFINITY, sum = 0.f;
+                    int taken = 0;
+                    while (taken < nq) {  // warp-uniform
+                        float best = top ? -INFINITY : INFINITY;
+                        int cnt = 0;
+                        for (int i = lane; i < n; i += 32) {
+                            const float v = m[lo + i];
+                            const bool beyond = top ? (v < last) : (v > last);
+                            if (beyond) {
+                                if (top ? (v > best) : (v < best)) { best = v; cnt = 1; }
+                                else if (v == best) ++cnt;
+                            }
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float ob = __shfl_xor_sync(kFull, best, o);
+                            const int oc = __shfl_xor_sync(kFull, cnt, o);
+                            if (top ? (ob > best) : (ob < best)) { best = ob; cnt = oc; }
+                            else if (ob == best) cnt += oc;
+                        }
+                        if (cnt == 0) break;  // fewer than nq values (NaNs): stop with what there is
+                        const int take = min(cnt, nq - taken);
+                        sum = fmaf(float(take), best, sum);
+                        taken += take;
+                        last = best;
+                    }
+                    res[top] = sum / float(nq);
+                }
+            }
+            float r;
+            if (linear) r = res[1] - res[0];
+            else r = 10.0f * log10f(fmaxf(res[1], 1e-10f)) - 10.0f * log10f(fmaxf(res[0], 1e-10f));
+            if (lane == 0) out[(b * n_out + band) * T + t] = r;
+        }
+    }
+}
+
 // kind 0: sqrt(mean x^2) (framing.py:81-151); kind 1: mean of sign changes, the first sample of a frame never
 // counts, sign = (x >= 0) (features.py:594-720).  Frames by index arithmetic on the centre-padded clip.
 __global__ void __launch_bounds__(256) frame_stats_kernel(const float* __restrict__ y, long long B, int L, long long ldy,
@@ -209,6 +271,25 @@ cudaError_t run_spectral_stats(const void* S, int is_complex, long long rows, in
     const unsigned grid = grid_for_rows(rows, 8);
     if (is_complex) spectral_stats_kernel<true><<<grid, 256, 0, s>>>(S, rows, F, freq, kind, p1, p2, norm, centroid_in, out);
     else spectral_stats_kernel<false><<<grid, 256, 0, s>>>(S, rows, F, freq, kind, p1, p2, norm, centroid_in, out);
+    return cudaGetLastError();
+}
+cudaError_t run_spectral_contrast(const void* S, int is_complex, long long B, long long T, int F, const int* bands, int n_out,
+                                  int linear, float* out, cudaStream_t s) {
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * F * 4 > 96 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * F * 4;
+    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+    const unsigned grid = grid_for_rows(B * T, warps);
+    cudaError_t e;
+    if (is_complex) {
+        e = cudaFuncSetAttribute(spectral_contrast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        spectral_contrast_kernel<true><<<grid, warps * 32, smem, s>>>(S, B, T, F, bands, n_out, linear, out);
+    } else {
+        e = cudaFuncSetAttribute(spectral_contrast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        spectral_contrast_kernel<false><<<grid, warps * 32, smem, s>>>(S, B, T, F, bands, n_out, linear, out);
+    }
     return cudaGetLastError();
 }
 cudaError_t run_frame_stats(const float* y, long long B, int L, long long ldy, int frame_length, int hop, int pad, int pad_mode,

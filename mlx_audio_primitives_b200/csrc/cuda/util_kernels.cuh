@@ -33,6 +33,8 @@ cudaError_t run_pcg64_uniform(unsigned long long s_hi, unsigned long long s_lo, 
 // feat_kernels.cu
 cudaError_t run_spectral_stats(const void* S, int is_complex, long long rows, int F, const float* freq, int kind, float p1,
                                float p2, int norm, const float* centroid_in, float* out, cudaStream_t s);
+cudaError_t run_spectral_contrast(const void* S, int is_complex, long long B, long long T, int F, const int* bands, int n_out,
+                                  int linear, float* out, cudaStream_t s);
 cudaError_t run_frame_stats(const float* y, long long B, int L, long long ldy, int frame_length, int hop, int pad, int pad_mode,
                             long long T, int kind, float* out, cudaStream_t s);
 cudaError_t run_preemphasis(const float* y, long long B, long long L, long long ldy, float coef, const float* zi, float* out,

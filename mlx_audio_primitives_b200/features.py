@@ -5,7 +5,8 @@ epilogue -- |X| stays in the registers of the lane group that produced it and on
 written.  Other sizes take two launches (STFT + a per-frame reduction kernel that reads the PHYSICAL (B, T, F)
 complex spectrum directly: |X| is formed on load, no magnitude pass, no transposed copy).  From a pre-computed spectrogram ``S`` (logical (B, F, T), as the reference takes it) the same kernel
 runs on its (B, T, F) layout -- zero-copy when ``S`` came from ``magnitude(stft(...))``.  Results have the
-reference's shapes: (1, T) for 1-D input, (B, 1, T) for batches.  ``spectral_contrast`` is not built yet.
+reference's shapes: (1, T) for 1-D input, (B, 1, T) for batches ((n_bands + 1, T) / (B, n_bands + 1, T) for
+``spectral_contrast``).
 """
 from __future__ import annotations
 
@@ -181,6 +182,57 @@ def spectral_flatness(y=None, S=None, n_fft: int = 2048, hop_length: int = 512, 
     data, cplx, batched = _frames_bins(y, S, n_fft, hop_length, win_length, window, center, pad_mode)
     f = fft_frequencies_device(1, 2 * (data.shape[2] - 1))  # unused by this statistic; only its length is checked
     return _stat(data, cplx, batched, f, _FLATNESS, p1=(power if S is None else 1.0), p2=amin)
+
+
+def contrast_bands_host(freq: np.ndarray, fmin: float, n_bands: int, quantile: float) -> np.ndarray:
+    """(n_bands + 1, 3) int32 {first bin, bin count, n_quantile} per octave band by the reference's edge rules
+    (features.py:536-565): bins with f_low <= f <= f_high, the neighbour bin below for every band but the first,
+    the last band extended to Nyquist, n_quantile from the count before the last bin is dropped."""
+    freq = np.asarray(freq, dtype=np.float64)
+    octa = np.zeros(n_bands + 2)
+    octa[1:] = fmin * (2.0 ** np.arange(0, n_bands + 1))
+    rows = []
+    for k in range(n_bands + 1):
+        inside = np.flatnonzero((freq >= octa[k]) & (freq <= octa[k + 1]))
+        if inside.size == 0:
+            rows.append((0, 0, 0))
+            continue
+        lo, hi = int(inside[0]), int(inside[-1])
+        if k > 0 and lo > 0:
+            lo -= 1
+        if k == n_bands:
+            hi = len(freq) - 1
+        n = hi - lo + 1
+        nq = int(max(np.rint(quantile * n), 1))
+        if k < n_bands and n > 1:
+            n -= 1
+        rows.append((lo, n, nq))
+    return np.asarray(rows, dtype=np.int32)
+
+
+def spectral_contrast(y=None, sr: int = 22050, S=None, n_fft: int = 2048, hop_length: int = 512,
+                      win_length: int | None = None, window="hann", center: bool = True, pad_mode: str = "constant",
+                      freq=None, fmin: float = 200.0, n_bands: int = 6, quantile: float = 0.02,
+                      linear: bool = False) -> torch.Tensor:
+    """Octave-band peak/valley contrast, (n_bands + 1, T) / (B, n_bands + 1, T) (reference features.py:445-592,
+    which does this on the host in NumPy): mean of the top quantile against mean of the bottom quantile of each
+    band's magnitudes, as a difference of 10*log10 values or linearly.  One kernel over the physical (B, T, F)
+    spectrum; the band edges follow the reference's (librosa's) rules on the host."""
+    if n_bands <= 0:
+        raise ValueError(f"n_bands must be positive, got {n_bands}")
+    if not 0.0 <= quantile <= 1.0:
+        raise ValueError(f"quantile must be in [0, 1], got {quantile}" if quantile < 0 else f"quantile must be <= 1.0, got {quantile}")
+    data, cplx, batched = _frames_bins(y, S, n_fft, hop_length, win_length, window, center, pad_mode)
+    B, T, F = data.shape
+    f = _freq(freq, sr, 2 * (F - 1) if S is not None else n_fft, data.device)
+    if f.numel() != F:
+        raise ValueError(f"freq has {f.numel()} entries, the spectrogram has {F} bins")
+    bands = torch.from_numpy(contrast_bands_host(f.cpu().numpy(), float(fmin), int(n_bands), float(quantile))).to(data.device)
+    out = torch.empty((B, n_bands + 1, T), dtype=torch.float32, device=data.device)
+    if B * T:
+        check(_ext.mlxa_spectral_contrast_f32(ptr(data), int(cplx), B, T, F, ptr(bands), n_bands + 1, int(linear), ptr(out),
+                                              stream_ptr(data)), "spectral_contrast")
+    return out if batched else out[0]
 
 
 def _frame_stat(y, frame_length, hop_length, center, pad_mode, kind, modes):

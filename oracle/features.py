@@ -80,6 +80,64 @@ def spectral_flatness(y=None, S=None, n_fft=2048, hop_length=512, win_length=Non
     return out.astype(dtype) if batched else out[0].astype(dtype)
 
 
+def contrast_bands(freq, fmin, n_bands, quantile):
+    """Per octave band k = 0..n_bands: (first bin, bin count after the edge rules, n_quantile) exactly as
+    features.py:536-565 (librosa's rules): bins with f_low <= f <= f_high, plus the neighbour below for k > 0,
+    the last band extended to Nyquist, n_quantile from the count BEFORE the last bin is dropped (all bands but
+    the last drop it when they have more than one bin).  Bands without bins are (0, 0, 0)."""
+    freq = np.asarray(freq, dtype=np.float64)
+    octa = np.zeros(n_bands + 2)
+    octa[1:] = fmin * (2.0 ** np.arange(0, n_bands + 1))
+    out = []
+    for k, (f_low, f_high) in enumerate(zip(octa[:-1], octa[1:])):
+        band = np.logical_and(freq >= f_low, freq <= f_high)
+        idx = np.flatnonzero(band)
+        if len(idx) == 0:
+            out.append((0, 0, 0))
+            continue
+        if k > 0 and idx[0] > 0:
+            band[idx[0] - 1] = True
+        if k == n_bands and idx[-1] + 1 < len(band):
+            band[idx[-1] + 1:] = True
+        n = int(band.sum())
+        nq = int(np.maximum(np.rint(quantile * n), 1))
+        lo = int(np.flatnonzero(band)[0])
+        if k < n_bands and n > 1:
+            n -= 1
+        out.append((lo, n, nq))
+    return out
+
+
+def spectral_contrast(y=None, sr=22050, S=None, n_fft=2048, hop_length=512, win_length=None, window="hann", center=True,
+                      pad_mode="constant", freq=None, fmin=200.0, n_bands=6, quantile=0.02, linear=False, dtype=np.float32,
+                      parts=False):
+    """peak (mean of the top quantile) against valley (mean of the bottom quantile) of every octave band, as a
+    difference of 10*log10 values or linearly (features.py:445-592)."""
+    if n_bands <= 0:
+        raise ValueError(f"n_bands must be positive, got {n_bands}")
+    if not 0.0 <= quantile <= 1.0:
+        raise ValueError(f"quantile must be in [0, 1], got {quantile}")
+    S, batched = _batched(_spectrogram(y, S, n_fft, hop_length, win_length, window, center, pad_mode, dtype=dtype))
+    f = fft_frequencies(sr, n_fft) if freq is None else np.asarray(freq)
+    B, F, T = S.shape
+    valley = np.zeros((B, n_bands + 1, T), dtype=np.float32)
+    peak = np.zeros_like(valley)
+    for k, (lo, n, nq) in enumerate(contrast_bands(f, fmin, n_bands, quantile)):
+        if n == 0:
+            continue
+        srt = np.sort(S[:, lo:lo + n, :], axis=1)
+        valley[:, k, :] = srt[:, :nq, :].mean(1)
+        peak[:, k, :] = srt[:, -nq:, :].mean(1)
+    if linear:
+        out = peak - valley
+    else:
+        out = 10.0 * np.log10(np.maximum(peak, 1e-10)) - 10.0 * np.log10(np.maximum(valley, 1e-10))
+    out = out.astype(np.float32)
+    if parts:  # (contrast, peak, valley, largest magnitude per frame): lets a test judge the conditioning of the dB values
+        return out, peak, valley, S.max(1, keepdims=True)
+    return out if batched else out[0]
+
+
 def _padded_frames(y, frame_length, hop_length, center, pad_mode):
     if frame_length <= 0:
         raise ValueError(f"frame_length must be positive, got {frame_length}")

@@ -27,11 +27,14 @@ for i, kw in enumerate(cases):
     out[f"rolloff50/{i}"] = A(ref.spectral_rolloff(mx.array(y2), sr=sr, roll_percent=0.5, **k2))
     out[f"flatness/{i}"] = A(ref.spectral_flatness(mx.array(y2), **k2))
     out[f"flatness_p1/{i}"] = A(ref.spectral_flatness(mx.array(y2), power=1.0, amin=1e-6, **k2))
+    out[f"contrast/{i}"] = A(ref.spectral_contrast(mx.array(y2), sr=sr, **k2))
+    out[f"contrast_lin/{i}"] = A(ref.spectral_contrast(mx.array(y2), sr=sr, n_bands=4, fmin=150.0, quantile=0.1, linear=True, **k2))
 out["ncases"] = np.array(len(cases))
 S = ref.magnitude(ref.stft(mx.array(y2[0]), n_fft=512, hop_length=128))
 out["S1d"] = A(S)
 out["centroid_S1d"] = A(ref.spectral_centroid(S=S, sr=22050, n_fft=512))
 out["rolloff_S1d"] = A(ref.spectral_rolloff(S=S, sr=22050, n_fft=512))
+out["contrast_S1d"] = A(ref.spectral_contrast(S=S, sr=22050, n_fft=512))
 for (fl, hop, center, mode) in [(2048, 512, True, "constant"), (400, 160, True, "edge"), (256, 64, False, "constant")]:
     out[f"rms/{fl}/{hop}/{int(center)}/{mode}"] = A(ref.rms(mx.array(y2), fl, hop, center=center, pad_mode=mode))
     zm = "edge" if mode == "edge" else "constant"

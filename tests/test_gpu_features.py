@@ -56,6 +56,11 @@ def test_features_match_reference_fixtures(ap):
         rolloff_close(H(ap.spectral_rolloff(y2, sr=sr, roll_percent=0.5, **k2)), g[f"rolloff50/{i}"], step)
         close(H(ap.spectral_flatness(y2, **k2)), g[f"flatness/{i}"], 1e-4)
         close(H(ap.spectral_flatness(y2, power=1.0, amin=1e-6, **k2)), g[f"flatness_p1/{i}"], 1e-4)
+        # dB of a mean of the SMALLEST magnitudes: a float32 FFT's absolute error (1e-7 of the peak) is a relative
+        # error of up to ~1e-3 on those bins in either implementation, i.e. a few 1e-3 dB between two of them
+        assert np.abs(H(ap.spectral_contrast(y2, sr=sr, **k2)) - g[f"contrast/{i}"]).max() <= 5e-3
+        close(H(ap.spectral_contrast(y2, sr=sr, n_bands=4, fmin=150.0, quantile=0.1, linear=True, **k2)), g[f"contrast_lin/{i}"], 1e-5)
+    assert np.abs(H(ap.spectral_contrast(S=g["S1d"], sr=22050, n_fft=512)) - g["contrast_S1d"]).max() <= 1e-4  # same S: selection is exact
     close(H(ap.spectral_centroid(S=g["S1d"], sr=22050, n_fft=512)), g["centroid_S1d"], 2e-5)
     rolloff_close(H(ap.spectral_rolloff(S=g["S1d"], sr=22050, n_fft=512)), g["rolloff_S1d"], 22050 / 2 / 256)
     for key in g.files:
@@ -91,6 +96,23 @@ def test_features_match_float64_oracle(ap, n_fft, hop, sr):
         rolloff_close(np.where(live, got, 0), np.where(live, ref, 0).astype(np.float32), step)
     close(H(ap.spectral_flatness(y, **kw)), of.spectral_flatness(y, dtype=f64, **kw), 1e-4)
     close(H(ap.spectral_flatness(y, power=1.0, amin=1e-6, **kw)), of.spectral_flatness(y, power=1.0, amin=1e-6, dtype=f64, **kw), 1e-4)
+    # contrast: peaks / valleys are means of order statistics -- exact selection, so only the magnitudes' rounding
+    # shows (silent frames give 0 dB in every band: peak == valley == amin-clamped)
+    for ckw in (dict(), dict(n_bands=4, fmin=100.0, quantile=0.25, linear=True), dict(n_bands=3, quantile=1.0), dict(quantile=0.0)):
+        if n_fft < 256 and ckw.get("n_bands", 6) > 4:
+            ckw = dict(ckw, fmin=sr / 2.0 / 64)  # keep the octave ladder inside Nyquist for the small transforms
+        ref, _, valley, smax = of.spectral_contrast(y, sr=sr, dtype=f64, parts=True, **kw, **ckw)
+        got = H(ap.spectral_contrast(y, sr=sr, **kw, **ckw))
+        assert got.shape == ref.shape
+        if ckw.get("linear"):
+            close(got, ref, 1e-5)
+        else:
+            # dB of a valley is only as good as the valley's RELATIVE accuracy: a float32 transform is exact to
+            # ~1e-7 of the frame's largest magnitude, so entries whose valley is above 1e-4 of it must agree to
+            # 5e-3 dB; the rest (bins at the float32 noise floor) to the reference's own test tolerance, 0.5 dB
+            well = (valley >= 1e-4 * smax) | (valley == 0)
+            assert np.abs(got - ref)[well].max() <= 5e-3, np.abs(got - ref)[well].max()
+            assert (np.abs(got - ref) <= 0.5).mean() >= 0.999
     # a pre-computed spectrogram, in both layouts a caller can hand over
     S = ap.magnitude(ap.stft(y, **kw))                      # (B, F, T) view of the physical (B, T, F) buffer
     for Sx in (S, S.contiguous(), S[1]):
@@ -129,4 +151,9 @@ def test_feature_errors(ap):
         ap.rms(y, 0, 10)
     with pytest.raises(ValueError, match="Unknown pad_mode"):
         ap.zero_crossing_rate(y, pad_mode="reflect")
+    with pytest.raises(ValueError, match="n_bands must be positive"):
+        ap.spectral_contrast(y, n_bands=0)
+    with pytest.raises(ValueError, match="quantile"):
+        ap.spectral_contrast(y, quantile=1.5)
+    assert tuple(ap.spectral_contrast(y).shape) == (7, 8)
     assert tuple(ap.spectral_centroid(y).shape) == (1, 8) and float(ap.spectral_centroid(y).abs().max()) == 0.0

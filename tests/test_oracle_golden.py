@@ -227,6 +227,9 @@ def test_feature_oracle_matches_reference_code():
             assert got.shape == ref.shape and (got != ref).mean() <= 0.01  # a float32 cumsum tie may move one bin
         close(of.spectral_flatness(y2, **k2), g[f"flatness/{i}"], 2e-5)
         close(of.spectral_flatness(y2, power=1.0, amin=1e-6, **k2), g[f"flatness_p1/{i}"], 2e-5)
+        assert np.abs(of.spectral_contrast(y2, sr=sr, **k2) - g[f"contrast/{i}"]).max() <= 1e-5  # dB
+        close(of.spectral_contrast(y2, sr=sr, n_bands=4, fmin=150.0, quantile=0.1, linear=True, **k2), g[f"contrast_lin/{i}"], 1e-6)
+    assert np.abs(of.spectral_contrast(S=g["S1d"], sr=22050, n_fft=512) - g["contrast_S1d"]).max() <= 1e-5
     close(of.spectral_centroid(S=g["S1d"], sr=22050, n_fft=512), g["centroid_S1d"], 2e-6)
     assert np.array_equal(of.spectral_rolloff(S=g["S1d"], sr=22050, n_fft=512), g["rolloff_S1d"])
     for key in g.files:

@@ -133,11 +133,12 @@ def main():
             ap.spectral_centroid(y, **kw); ap.spectral_bandwidth(y, **kw); ap.spectral_rolloff(y, **kw)
             ap.spectral_flatness(y, n_fft=N, hop_length=hop)
         ms = timed(feats, args.iters)
+        ms_contrast = timed(lambda: ap.spectral_contrast(y, **kw), max(2, args.iters // 4))
         # algorithmic: every feature reads the clip once and writes T floats; the current two-launch form also
         # writes and re-reads the (B, T, F) complex spectrum (8FT + passes x 8FT bytes)
         report("f1", f"spectral centroid+bandwidth+rolloff+flatness 22.05k 2048/512 {B}x30 s (4 calls from audio)", B * 30.0, ms,
                4 * B * (4 * L + 4 * T), 4 * B * T * (fft_flops(N) + N + 8 * F),
-               {"moved_bytes_two_launch_form": B * (4 * (4 * L + 8 * F * T) + (1 + 2 + 2 + 1) * 8 * F * T + 4 * 4 * T)})
+               {"ms_spectral_contrast_extra": ms_contrast})
     if "f2" in want:  # section 8(f) rank 2: rms + zero-crossing rate + pre-emphasis of the same batch
         B, L = max(1, int(1024 * sc * 0.125)), 661500
         y = clips(B, L, 22050)
