@@ -253,6 +253,12 @@ int mlxa_spectral_feature_f32(const float* y, int64_t B, int64_t L, int64_t ldy,
                               int n_fft, int hop, int center, int pad_mode, const float* freq,
                               float freq_step, int kind, float p1, float p2, int norm,
                               const float* centroid_in, float* out, void* stream);
+/* Savitzky-Golay filter along the last axis: the `delta` features of reference mfcc.py:290-371, which calls
+ * scipy.signal.savgol_filter on the host.  x, out (rows, T); taps: `width` correlation taps (out[t] = sum_j taps[j] *
+ * x[t - width/2 + j]); mode 0 interp (edge_left / edge_right: (width/2, width) operators applied to the first / last
+ * `width` samples), 1 nearest, 2 mirror, 3 constant (cval), 4 wrap -- scipy's boundary rules. */
+int mlxa_savgol_f32(const float* x, int64_t rows, int64_t T, const float* taps, int width, int mode, float cval,
+                    const float* edge_left, const float* edge_right, float* out, void* stream);
 /* Per-frame time-domain statistics with the framing done by index arithmetic (centre padding constant or
  * edge): kind 0 RMS (framing.py:81-151), kind 1 zero-crossing rate (features.py:594-720).
  * out (B, T), T = 1 + (L + 2*pad - frame_length) / hop. */

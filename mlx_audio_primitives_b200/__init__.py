@@ -14,7 +14,7 @@ from .features import (spectral_bandwidth, spectral_centroid, spectral_contrast,
 from .framing import frame, preemphasis, rms
 from .griffinlim import griffinlim, griffinlim_iter
 from .mel import hz_to_mel, mel_filterbank, mel_to_hz, melspectrogram
-from .mfcc import dct, dct_matrix, mfcc
+from .mfcc import dct, dct_matrix, delta, mfcc
 from .stft import check_nola, istft, magnitude, overlap_add, pad_signal, phase, stft
 from .windows import get_window
 from .pipeline import LogMelPlan
@@ -30,5 +30,5 @@ __all__ = [
     "linear_filterbank", "bark_filterbank", "hz_to_bark", "bark_to_hz",
     "pad_signal", "overlap_add", "distributed", "LogMelPlan",
     "spectral_centroid", "spectral_bandwidth", "spectral_rolloff", "spectral_flatness", "spectral_contrast",
-    "zero_crossing_rate", "rms", "preemphasis",
+    "zero_crossing_rate", "rms", "preemphasis", "delta",
 ]

@@ -464,6 +464,14 @@ int mlxa_spectral_stats_f32(const void* S, int is_complex, int64_t B, int64_t T,
                "spectral_stats");
     return 0;
 }
+int mlxa_savgol_f32(const float* x, int64_t rows, int64_t T, const float* taps, int width, int mode, float cval,
+                    const float* edge_left, const float* edge_right, float* out, void* stream) {
+    CHECK_ARG(x && taps && out && rows > 0 && T > 0, "bad argument");
+    CHECK_ARG(width >= 1 && (width & 1) && width <= 8191 && mode >= 0 && mode <= 4, "width must be odd; unknown mode");
+    CHECK_ARG(mode != 0 || (edge_left && edge_right && width <= T), "mode interp needs the edge operators and width <= T");
+    CHECK_CUDA(run_savgol(x, rows, T, taps, width, mode, cval, edge_left, edge_right, out, (cudaStream_t)stream), "savgol");
+    return 0;
+}
 int mlxa_spectral_contrast_f32(const void* S, int is_complex, int64_t B, int64_t T, int F, const int32_t* bands, int n_out,
                                int linear, float* out, void* stream) {
     CHECK_ARG(S && bands && out && B > 0 && T > 0 && F > 0 && n_out > 0, "bad argument");

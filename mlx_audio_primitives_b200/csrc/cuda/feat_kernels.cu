@@ -260,6 +260,59 @@ __global__ void preemphasis_kernel(const float* __restrict__ y, long long B, lon
     }
 }
 
+// Savitzky-Golay filter along the last axis (reference mfcc.py:290-371 = scipy.signal.savgol_filter on the host):
+// out[r, t] = sum_j taps[j] * x[r, t - h + j] with the boundary rule of `mode`; in mode 0 ("interp") the first and
+// last h outputs come from the polynomial fitted to the first / last `width` samples, i.e. from the (h, width)
+// operators edge_left / edge_right.  taps / operators are computed on the host in float64.
+enum : int { SG_INTERP = 0, SG_NEAREST = 1, SG_MIRROR = 2, SG_CONSTANT = 3, SG_WRAP = 4 };
+__global__ void savgol_kernel(const float* __restrict__ x, long long rows, long long T, const float* __restrict__ taps,
+                              int width, int mode, float cval, const float* __restrict__ edge_left,
+                              const float* __restrict__ edge_right, float* __restrict__ out) {
+    extern __shared__ float s_taps[];
+    for (int i = threadIdx.x; i < width; i += blockDim.x) s_taps[i] = __ldg(taps + i);
+    __syncthreads();
+    const int h = width / 2;
+    const long long n = rows * T;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / T, t = i - r * T;
+        const float* xr = x + r * T;
+        float acc = 0.f;
+        if (mode == SG_INTERP && (t < h || t >= T - h)) {
+            const bool left = t < h;
+            const float* op = left ? edge_left + t * width : edge_right + (t - (T - h)) * width;
+            const float* seg = left ? xr : xr + (T - width);
+            for (int j = 0; j < width; ++j) acc = fmaf(__ldg(op + j), seg[j], acc);
+        } else if (t >= h && t < T - h) {
+            const float* seg = xr + (t - h);
+            for (int j = 0; j < width; ++j) acc = fmaf(s_taps[j], seg[j], acc);
+        } else {
+            for (int j = 0; j < width; ++j) {
+                long long q = t - h + j;
+                float v;
+                if (q >= 0 && q < T) {
+                    v = xr[q];
+                } else if (mode == SG_CONSTANT) {
+                    v = cval;
+                } else {
+                    if (mode == SG_NEAREST) q = q < 0 ? 0 : T - 1;
+                    else if (mode == SG_WRAP) { q %= T; if (q < 0) q += T; }
+                    else {  // mirror: d c b | a b c d | c b a (period 2T - 2, the edge sample is not repeated)
+                        if (T == 1) q = 0;
+                        else {
+                            const long long per = 2 * T - 2;
+                            q %= per; if (q < 0) q += per;
+                            if (q >= T) q = per - q;
+                        }
+                    }
+                    v = xr[q];
+                }
+                acc = fmaf(s_taps[j], v, acc);
+            }
+        }
+        out[i] = acc;
+    }
+}
+
 unsigned grid_for_rows(long long rows, int per_cta) {
     const long long g = (rows + per_cta - 1) / per_cta;
     return (unsigned)(g < 1 ? 1 : (g > 148LL * 32 ? 148LL * 32 : g));
@@ -290,6 +343,13 @@ cudaError_t run_spectral_contrast(const void* S, int is_complex, long long B, lo
         if (e != cudaSuccess) return e;
         spectral_contrast_kernel<false><<<grid, warps * 32, smem, s>>>(S, B, T, F, bands, n_out, linear, out);
     }
+    return cudaGetLastError();
+}
+cudaError_t run_savgol(const float* x, long long rows, long long T, const float* taps, int width, int mode, float cval,
+                       const float* edge_left, const float* edge_right, float* out, cudaStream_t s) {
+    const long long n = rows * T, g = (n + 255) / 256;
+    savgol_kernel<<<(unsigned)(g < 1 ? 1 : (g > 148LL * 64 ? 148LL * 64 : g)), 256, (size_t)width * 4, s>>>(
+        x, rows, T, taps, width, mode, cval, edge_left, edge_right, out);
     return cudaGetLastError();
 }
 cudaError_t run_frame_stats(const float* y, long long B, int L, long long ldy, int frame_length, int hop, int pad, int pad_mode,

@@ -35,6 +35,8 @@ cudaError_t run_spectral_stats(const void* S, int is_complex, long long rows, in
                                float p2, int norm, const float* centroid_in, float* out, cudaStream_t s);
 cudaError_t run_spectral_contrast(const void* S, int is_complex, long long B, long long T, int F, const int* bands, int n_out,
                                   int linear, float* out, cudaStream_t s);
+cudaError_t run_savgol(const float* x, long long rows, long long T, const float* taps, int width, int mode, float cval,
+                       const float* edge_left, const float* edge_right, float* out, cudaStream_t s);
 cudaError_t run_frame_stats(const float* y, long long B, int L, long long ldy, int frame_length, int hop, int pad, int pad_mode,
                             long long T, int kind, float* out, cudaStream_t s);
 cudaError_t run_preemphasis(const float* y, long long B, long long L, long long ldy, float coef, const float* zi, float* out,

@@ -108,3 +108,77 @@ def mfcc(y=None, sr: int = 22050, S=None, n_mfcc: int = 20, dct_type: int = 2, n
         check(_ext.mlxa_mfcc_tail_f32(ptr(M[b0:]), nb, n_in, T, ptr(D), n_mfcc, ptr(lift), apply_db, 1e-10, 1.0,
                                       apply_db, 80.0, ptr(peak), ptr(out[b0:]), stream_ptr(M)), "mfcc")
     return out if batched else out[0]
+
+
+# ---------------------------------------------------------------- delta features (reference mfcc.py:290-371)
+_SG_MODES = {"interp": 0, "nearest": 1, "mirror": 2, "constant": 3, "wrap": 4}
+
+
+@lru_cache(maxsize=64)
+def savgol_operators_host(width: int, polyorder: int, deriv: int, delta: float):
+    """Savitzky-Golay taps (correlation order) and the (width//2, width) edge operators of mode 'interp', float64 ->
+    float32.  Restates scipy.signal.savgol_coeffs / _fit_edges_polyfit (the reference's host dependency,
+    scipy >= 1.10): least-squares polynomial of degree `polyorder` through `width` samples, its `deriv`-th
+    derivative at the centre (interior) or at the first / last width//2 positions of the edge windows."""
+    from math import factorial
+    if polyorder >= width:
+        raise ValueError("polyorder must be less than window_length.")
+    if deriv > polyorder:
+        taps = np.zeros(width)
+    else:
+        h = width // 2
+        x = np.arange(-h, width - h, dtype=np.float64)[::-1]
+        A = x[None, :] ** np.arange(polyorder + 1)[:, None]
+        y = np.zeros(polyorder + 1)
+        y[deriv] = factorial(deriv) / (delta ** deriv)
+        taps = np.linalg.lstsq(A, y, rcond=None)[0][::-1]  # 'conv' coefficients reversed = correlation taps
+    h = width // 2
+    t = np.arange(width, dtype=np.float64)
+    P = np.linalg.pinv(t[:, None] ** np.arange(polyorder + 1)[None, :])  # polynomial coefficients = P @ samples
+
+    def deriv_rows(pos):
+        D = np.zeros((len(pos), polyorder + 1))
+        for k in range(deriv, polyorder + 1):
+            D[:, k] = factorial(k) / factorial(k - deriv) * pos ** (k - deriv)
+        return D / (delta ** deriv)
+    left = deriv_rows(np.arange(0, h, dtype=np.float64)) @ P
+    right = deriv_rows(np.arange(width - h, width, dtype=np.float64)) @ P
+    return (np.ascontiguousarray(taps, np.float32), np.ascontiguousarray(left, np.float32),
+            np.ascontiguousarray(right, np.float32))
+
+
+def delta(data, width: int = 9, order: int = 1, axis: int = -1, mode: str = "interp", **kwargs) -> torch.Tensor:
+    """Delta (derivative) features by Savitzky-Golay filtering along ``axis`` (reference mfcc.py:290-371, which
+    bounces to scipy.signal.savgol_filter on the host): one kernel on the device, taps and edge operators computed
+    once per (width, order) on the host.  ``polyorder`` (default ``order``), ``delta`` and ``cval`` are honoured."""
+    validate_positive(width, "width")
+    validate_positive(order, "order")
+    if width < 3:
+        raise ValueError(f"width must be >= 3, got {width}")
+    if width % 2 == 0:
+        raise ValueError(f"width must be odd, got {width}")
+    if mode not in _SG_MODES:
+        raise ValueError("mode must be 'mirror', 'constant', 'nearest' 'wrap' or 'interp'.")
+    x = to_tensor(data, torch.float32)
+    if x.ndim == 0:
+        x = x.reshape(1)
+    n = x.shape[axis]
+    if mode == "interp" and width > n:
+        raise ValueError(f"when mode='interp', width={width} cannot exceed data.shape[axis]={n}")
+    kwargs.pop("deriv", None)
+    polyorder = int(kwargs.pop("polyorder", order))
+    spacing = float(kwargs.pop("delta", 1.0))
+    cval = float(kwargs.pop("cval", 0.0))
+    if kwargs:
+        raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
+    taps, left, right = savgol_operators_host(int(width), polyorder, int(order), spacing)
+    moved = x.movedim(axis, -1)
+    xc = moved.contiguous()
+    rows = xc.numel() // n if n else 0
+    out = torch.empty_like(xc)
+    if rows and n:
+        dev = xc.device
+        t_d, l_d, r_d = (torch.from_numpy(a).to(dev) for a in (taps, left, right))
+        check(_ext.mlxa_savgol_f32(ptr(xc), rows, n, ptr(t_d), int(width), _SG_MODES[mode], cval, ptr(l_d), ptr(r_d), ptr(out),
+                                   stream_ptr(xc)), "savgol")
+    return out.movedim(-1, axis)

@@ -193,3 +193,24 @@ def preemphasis(y, coef=0.97, zi=None, return_zf=False):
     if one_d:
         out, zf = out[0], zf[0]
     return (out, zf) if return_zf else out
+
+
+def delta(data, width=9, order=1, axis=-1, mode="interp", **kwargs):
+    """mfcc.py:290-371: the reference validates, then calls scipy.signal.savgol_filter (scipy >= 1.10; 1.18.1 here)
+    with deriv = order and polyorder defaulting to order, and casts to float32.  The filter is the third-party
+    algorithm itself, so the oracle calls it too (on float64 when a yardstick is wanted)."""
+    from scipy.signal import savgol_filter
+    if width <= 0:
+        raise ValueError(f"width must be positive, got {width}")
+    if order <= 0:
+        raise ValueError(f"order must be positive, got {order}")
+    if width < 3:
+        raise ValueError(f"width must be >= 3, got {width}")
+    if width % 2 == 0:
+        raise ValueError(f"width must be odd, got {width}")
+    x = np.atleast_1d(np.asarray(data))
+    if mode == "interp" and width > x.shape[axis]:
+        raise ValueError(f"when mode='interp', width={width} cannot exceed data.shape[axis]={x.shape[axis]}")
+    kwargs.pop("deriv", None)
+    kwargs.setdefault("polyorder", order)
+    return savgol_filter(x, width, deriv=order, axis=axis, mode=mode, **kwargs).astype(np.float32)

@@ -44,6 +44,14 @@ out["pre/default"] = A(ref.preemphasis(mx.array(y2)))
 o2, zf = ref.preemphasis(mx.array(y2), coef=0.9, zi=mx.array(np.array([0.5, -0.25], np.float32)), return_zf=True)
 out["pre/zi"], out["pre/zf"] = A(o2), A(zf)
 out["pre/1d"] = A(ref.preemphasis(mx.array(y2[0]), coef=0.5))
+M = np.asarray(g["mfcc/0"]) if "mfcc/0" in g.files else np.random.default_rng(5).standard_normal((2, 13, 40)).astype(np.float32)
+out["delta/input"] = M.astype(np.float32)
+out["delta/w9o1"] = A(ref.delta(mx.array(M)))
+out["delta/w9o2"] = A(ref.delta(mx.array(M), order=2))
+out["delta/w5o1_mirror"] = A(ref.delta(mx.array(M), width=5, mode="mirror"))
+out["delta/w7o1_nearest_axis1"] = A(ref.delta(mx.array(M), width=7, mode="nearest", axis=1))
+out["delta/w3o1_wrap"] = A(ref.delta(mx.array(M), width=3, mode="wrap"))
+out["delta/w9o1_constant"] = A(ref.delta(mx.array(M), mode="constant"))
 np.savez_compressed(os.path.join(HERE, "reference_features.npz"), **out)
 import json  # noqa: E402
 json.dump(cases, open(os.path.join(HERE, "feature_cases.json"), "w"))

@@ -137,6 +137,31 @@ def test_rms_zcr_preemphasis_match_oracle(ap, fl, hop, center, mode):
         assert np.array_equal(H(ap.preemphasis(y, coef=coef)), of.preemphasis(y, coef=coef))
 
 
+def test_delta_matches_reference_and_scipy(ap):
+    """delta(): reference fixtures (its own code over scipy.signal.savgol_filter) and the float64 filter, every
+    boundary mode, both orders, odd shapes and a non-last axis."""
+    g = np.load(os.path.join(GOLDEN, "reference_features.npz"))
+    M = g["delta/input"]
+    for key, kw in (("w9o1", {}), ("w9o2", dict(order=2)), ("w5o1_mirror", dict(width=5, mode="mirror")),
+                    ("w7o1_nearest_axis1", dict(width=7, mode="nearest", axis=1)), ("w3o1_wrap", dict(width=3, mode="wrap")),
+                    ("w9o1_constant", dict(mode="constant"))):
+        close(H(ap.delta(M, **kw)), g["delta/" + key], 2e-6)
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((3, 40, 257)).astype(np.float32)
+    for kw in (dict(), dict(order=2), dict(width=21, order=2, polyorder=3), dict(width=3, mode="mirror"), dict(width=15, mode="wrap"),
+               dict(width=9, mode="constant", cval=2.5), dict(width=5, mode="nearest", axis=0), dict(width=11, axis=1), dict(delta=0.5)):
+        close(H(ap.delta(X, **kw)), of.delta(X.astype(np.float64), **kw), 5e-6)
+    close(H(ap.delta(X[0, 0])), of.delta(X[0, 0].astype(np.float64)), 5e-6)  # 1-D
+    short = X[:, :, :5]
+    close(H(ap.delta(short, width=9, mode="mirror")), of.delta(short.astype(np.float64), width=9, mode="mirror"), 5e-6)  # window > axis
+    with pytest.raises(ValueError, match="width must be odd"):
+        ap.delta(X, width=8)
+    with pytest.raises(ValueError, match="width must be >= 3"):
+        ap.delta(X, width=1)
+    with pytest.raises(ValueError, match="cannot exceed"):
+        ap.delta(short, width=9)
+
+
 def test_feature_errors(ap):
     y = np.zeros(4000, np.float32)
     with pytest.raises(ValueError, match="Either y"):

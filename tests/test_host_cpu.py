@@ -78,6 +78,23 @@ def test_host_constants_match_reference_fixtures(golden):
     assert np.array_equal(mel_to_hz(hz_to_mel(golden["hz"])), golden["mel_to_hz/slaney"])
 
 
+def test_savgol_operators_match_scipy():
+    """The host-side Savitzky-Golay taps / edge operators of delta() (NumPy least squares) against SciPy's own
+    coefficients and against savgol_filter(mode='interp') on random data."""
+    from scipy.signal import savgol_coeffs, savgol_filter
+    from mlx_audio_primitives_b200.mfcc import savgol_operators_host
+    rng = np.random.default_rng(0)
+    for width, polyorder, deriv, spacing in [(9, 1, 1, 1.0), (9, 2, 2, 1.0), (5, 1, 1, 1.0), (3, 1, 1, 1.0), (7, 3, 2, 0.5), (11, 2, 1, 2.0)]:
+        taps, left, right = savgol_operators_host(width, polyorder, deriv, spacing)
+        ref = savgol_coeffs(width, polyorder, deriv=deriv, delta=spacing)[::-1]
+        assert np.abs(taps - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-30)
+        x = rng.standard_normal((4, 40))
+        want = savgol_filter(x, width, polyorder, deriv=deriv, delta=spacing, mode="interp")
+        h = width // 2
+        assert np.abs(x[:, :width] @ left.T.astype(np.float64) - want[:, :h]).max() <= 2e-5 * np.abs(want).max()
+        assert np.abs(x[:, -width:] @ right.T.astype(np.float64) - want[:, -h:]).max() <= 2e-5 * np.abs(want).max()
+
+
 def test_host_validation_messages():
     from mlx_audio_primitives_b200.mel import _resolve_stft_args, check_band_args, frames_or_raise, pad_mode_code
     from mlx_audio_primitives_b200.windows import window_host

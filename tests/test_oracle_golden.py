@@ -243,6 +243,11 @@ def test_feature_oracle_matches_reference_code():
     o2, zf = of.preemphasis(y2, coef=0.9, zi=np.array([0.5, -0.25], np.float32), return_zf=True)
     assert np.array_equal(o2, g["pre/zi"]) and np.array_equal(zf, g["pre/zf"])
     assert np.array_equal(of.preemphasis(y2[0], coef=0.5), g["pre/1d"])
+    M = g["delta/input"]
+    for key, kw in (("w9o1", {}), ("w9o2", dict(order=2)), ("w5o1_mirror", dict(width=5, mode="mirror")),
+                    ("w7o1_nearest_axis1", dict(width=7, mode="nearest", axis=1)), ("w3o1_wrap", dict(width=3, mode="wrap")),
+                    ("w9o1_constant", dict(mode="constant"))):
+        assert np.array_equal(of.delta(M, **kw), g["delta/" + key]), key
     with pytest.raises(ValueError, match="roll_percent must be <= 1.0"):
         of.spectral_rolloff(y2, roll_percent=1.5)
     with pytest.raises(ValueError, match="Either y"):
