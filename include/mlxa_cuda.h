@@ -253,6 +253,13 @@ int mlxa_spectral_feature_f32(const float* y, int64_t B, int64_t L, int64_t ldy,
                               int n_fft, int hop, int center, int pad_mode, const float* freq,
                               float freq_step, int kind, float p1, float p2, int norm,
                               const float* centroid_in, float* out, void* stream);
+/* Autocorrelation pitch detector (pitch.py:118-260, a per-frame NumPy loop on the host in the reference), one kernel:
+ * per frame, r = irfft(|rfft(frame - mean, n_fft)|^2) / r[0] with n_fft the power of two >= 2*frame_length - 1
+ * (frame_length 33..2048), then f0 = sr / lag of the first local maximum above `threshold` in [int(sr/fmax),
+ * int(sr/fmin)], else of the range's global maximum if above it.  Centre padding is zeros.  f0 (B, T) float32,
+ * voiced (B, T) uint8, T = 1 + (L + 2*(frame_length/2 if center) - frame_length) / hop. */
+int mlxa_pitch_acf_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int frame_length, int hop, int center,
+                       float sr, float fmin, float fmax, float threshold, float* f0, uint8_t* voiced, void* stream);
 /* Savitzky-Golay filter along the last axis: the `delta` features of reference mfcc.py:290-371, which calls
  * scipy.signal.savgol_filter on the host.  x, out (rows, T); taps: `width` correlation taps (out[t] = sum_j taps[j] *
  * x[t - width/2 + j]); mode 0 interp (edge_left / edge_right: (width/2, width) operators applied to the first / last

@@ -49,6 +49,8 @@ def _units():
     for nf in PLANNED_NFFT:
         units.append((f"fwd_{nf}.o", "fwd_inst.cu", [f"-DMLXA_NFFT={nf}"]))
         units.append((f"inv_{nf}.o", "inv_inst.cu", [f"-DMLXA_NFFT={nf}"]))
+        if nf != 400:  # packed plans only
+            units.append((f"acf_{nf}.o", "acf_inst.cu", [f"-DMLXA_NFFT={nf}"]))
     return units
 
 

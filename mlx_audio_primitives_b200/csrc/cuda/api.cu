@@ -464,6 +464,36 @@ int mlxa_spectral_stats_f32(const void* S, int is_complex, int64_t B, int64_t T,
                "spectral_stats");
     return 0;
 }
+int mlxa_pitch_acf_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int frame_length, int hop, int center, float sr,
+                       float fmin, float fmax, float threshold, float* f0, uint8_t* voiced, void* stream) {
+    CHECK_ARG(y && f0 && voiced && B > 0 && L > 0 && ldy >= L && B < (1LL << 31) && L < (1LL << 30), "bad argument");
+    CHECK_ARG(frame_length >= 2 && hop >= 1 && sr > 0 && fmin > 0 && fmin < fmax, "bad frame geometry / frequency range");
+    int n_fft = 1;
+    while (n_fft < 2 * frame_length - 1) n_fft *= 2;
+    CHECK_ARG(n_fft >= 64 && n_fft <= 4096, "frame_length must be within 33..2048 (transform sizes 64..4096)");
+    const int pad = center ? frame_length / 2 : 0;
+    const int64_t Lp = L + 2 * (int64_t)pad;
+    CHECK_ARG(Lp >= frame_length, "signal shorter than frame_length");
+    AcfParams p{};
+    p.y = y; p.ldy = ldy; p.B = (int)B; p.L = (int)L;
+    p.T = 1 + (Lp - frame_length) / hop;
+    p.frame_length = frame_length; p.hop = hop; p.pad = pad;
+    p.min_lag = (int)(sr / fmax); p.max_lag = (int)(sr / fmin);  // int() truncation, as pitch.py:186-187
+    CHECK_ARG(p.max_lag + 1 <= n_fft / 2, "sr / fmin exceeds the lags the transform resolves");
+    p.threshold = threshold; p.sr = sr;
+    Tables t;
+    CHECK_CUDA(get_tables(n_fft, &t), "twiddle tables");
+    p.tw_plan = t.tw_plan; p.tw_unpack = t.tw_unpack;
+    p.f0 = f0; p.voiced = voiced;
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (n_fft) {
+#define X(NF) case NF: e = launch_acf_##NF(p, (cudaStream_t)stream); break;
+        X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
+#undef X
+    }
+    CHECK_CUDA(e, "pitch_acf");
+    return 0;
+}
 int mlxa_savgol_f32(const float* x, int64_t rows, int64_t T, const float* taps, int width, int mode, float cval,
                     const float* edge_left, const float* edge_right, float* out, void* stream) {
     CHECK_ARG(x && taps && out && rows > 0 && T > 0, "bad argument");

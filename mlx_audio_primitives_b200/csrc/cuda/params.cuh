@@ -90,10 +90,24 @@ struct InvParams {
     float* y;            // (B, out_len)
 };
 
+struct AcfParams {  // acf_inst.cu: autocorrelation pitch detector (pitch.py:118-260)
+    const float* y;
+    long long ldy, T;
+    int B, L;
+    int frame_length, hop, pad;
+    int min_lag, max_lag;
+    float threshold, sr;
+    const float2* tw_plan;
+    const float2* tw_unpack;
+    float* f0;             // (B, T)
+    unsigned char* voiced; // (B, T)
+};
+
 // one launcher per compiled n_fft (fwd_inst.cu / inv_inst.cu built with -DMLXA_NFFT=...)
 #define MLXA_DECL_LAUNCHERS(NF)                                                            \
     cudaError_t launch_fwd_##NF(int ep, FwdParams& p, cudaStream_t s);                     \
     cudaError_t launch_inv_##NF(InvParams& p, cudaStream_t s);                             \
+    cudaError_t launch_acf_##NF(const AcfParams& p, cudaStream_t s);                        \
     int plan_group_##NF();                                                                  \
     int plan_fused_feature_##NF();                                                          \
     void plan_tables_##NF(float2* tw_plan_host, int* n_plan, float2* tw_unpack_host, int* n_unpack);

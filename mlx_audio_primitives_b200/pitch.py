@@ -1,0 +1,45 @@
+"""Pitch detection by autocorrelation (reference ``pitch.py:118-260``).
+
+The reference loops over frames in NumPy on the host (rfft -> |Y|^2 -> irfft -> peak picking per frame); here
+one kernel does it for every frame of the batch with two passes through the shared-memory FFT engine and
+writes only (f0, voiced).  Frames up to 2048 samples (transform sizes up to 4096) are served; the whole-signal
+``autocorrelation`` (a single transform of up to 2^20 points) is not built."""
+from __future__ import annotations
+
+import torch
+
+from ._extension import _ext, check
+from ._tensor import f32c, ptr, stream_ptr
+from ._validation import validate_positive
+
+
+def pitch_detect_acf(y, sr: int = 22050, fmin: float = 50.0, fmax: float = 2000.0, frame_length: int = 2048,
+                     hop_length: int = 512, threshold: float = 0.1, center: bool = True):
+    """(f0, voiced_flag): fundamental frequency (Hz, 0 where unvoiced) and a bool mask per frame, (T,) or (B, T).
+    f0 = sr / lag of the first local maximum of the normalised autocorrelation above ``threshold`` inside
+    [int(sr / fmax), int(sr / fmin)], else of the range's global maximum if that is above the threshold."""
+    validate_positive(frame_length, "frame_length")
+    validate_positive(hop_length, "hop_length")
+    if fmin >= fmax:
+        raise ValueError(f"fmin ({fmin}) must be less than fmax ({fmax})")
+    if not 33 <= frame_length <= 2048:
+        raise ValueError(f"frame_length must be within 33..2048 on the device path, got {frame_length}")
+    y = f32c(y)
+    one_d = y.ndim == 1
+    if one_d:
+        y = y[None, :]
+    if y.ndim != 2:
+        raise ValueError(f"y must be 1D or 2D, got {y.ndim}D")
+    B, L = y.shape
+    Lp = L + (2 * (frame_length // 2) if center else 0)
+    if Lp < frame_length:
+        raise ValueError(f"Signal length ({Lp}) must be >= frame_length ({frame_length}). Consider padding the signal.")
+    if int(sr / fmin) + 1 > frame_length:
+        raise ValueError(f"sr / fmin = {int(sr / fmin)} lags exceed the frame ({frame_length} samples)")
+    T = 1 + (Lp - frame_length) // hop_length
+    f0 = torch.empty((B, T), dtype=torch.float32, device=y.device)
+    voiced = torch.empty((B, T), dtype=torch.uint8, device=y.device)
+    check(_ext.mlxa_pitch_acf_f32(ptr(y), B, L, y.stride(0), int(frame_length), int(hop_length), int(center), float(sr),
+                                  float(fmin), float(fmax), float(threshold), ptr(f0), ptr(voiced), stream_ptr(y)), "pitch_acf")
+    voiced = voiced.to(torch.bool)
+    return (f0[0], voiced[0]) if one_d else (f0, voiced)

@@ -214,3 +214,60 @@ def delta(data, width=9, order=1, axis=-1, mode="interp", **kwargs):
     kwargs.pop("deriv", None)
     kwargs.setdefault("polyorder", order)
     return savgol_filter(x, width, deriv=order, axis=axis, mode=mode, **kwargs).astype(np.float32)
+
+
+def pitch_detect_acf(y, sr=22050, fmin=50.0, fmax=2000.0, frame_length=2048, hop_length=512, threshold=0.1, center=True,
+                     dtype=np.float64, return_acf=False):
+    """pitch.py:118-260: per frame, r = irfft(|rfft(frame - mean, n_fft)|^2) with n_fft the power of two >= 2*frame_length - 1,
+    normalised by r[0] (frames with r[0] <= 1e-10 are unvoiced); f0 = sr / lag of the FIRST local maximum above
+    `threshold` in [sr/fmax, sr/fmin] (lags as int()), else of the global maximum of that range if above threshold.
+    -> (f0 float32, voiced bool), (T,) or (B, T).  return_acf adds the normalised r[:max_lag + 2] per frame."""
+    if frame_length <= 0:
+        raise ValueError(f"frame_length must be positive, got {frame_length}")
+    if hop_length <= 0:
+        raise ValueError(f"hop_length must be positive, got {hop_length}")
+    if fmin >= fmax:
+        raise ValueError(f"fmin ({fmin}) must be less than fmax ({fmax})")
+    min_lag, max_lag = int(sr / fmax), int(sr / fmin)
+    y = np.asarray(y, dtype=np.float32)
+    one_d = y.ndim == 1
+    if one_d:
+        y = y[None]
+    if center:
+        y = np.pad(y, [(0, 0), (frame_length // 2, frame_length // 2)])
+    B, Lp = y.shape
+    T = 1 + (Lp - frame_length) // hop_length
+    n_fft = 2 ** int(np.ceil(np.log2(2 * frame_length - 1)))
+    f0 = np.zeros((B, T), np.float32)
+    voiced = np.zeros((B, T), bool)
+    acf = np.zeros((B, T, max_lag + 2), dtype) if return_acf else None
+    for b in range(B):
+        for t in range(T):
+            fr = y[b, t * hop_length:t * hop_length + frame_length].astype(dtype)
+            fr = fr - fr.mean()
+            Y = np.fft.rfft(fr, n=n_fft)
+            r = np.fft.irfft(Y * np.conj(Y), n=n_fft)
+            if not r[0] > 1e-10:
+                continue
+            r = r / r[0]
+            if return_acf:
+                acf[b, t, :] = r[:max_lag + 2]
+            sr_ = r[min_lag:max_lag + 1]
+            if len(sr_) == 0:
+                continue
+            lag = -1
+            for i in range(1, len(sr_) - 1):
+                if sr_[i] > sr_[i - 1] and sr_[i] > sr_[i + 1] and sr_[i] > threshold:
+                    lag = min_lag + i
+                    break
+            if lag < 0:
+                i = int(np.argmax(sr_))
+                if sr_[i] > threshold:
+                    lag = min_lag + i
+            if lag > 0:
+                f0[b, t] = sr / lag
+                voiced[b, t] = True
+    if one_d:
+        f0, voiced = f0[0], voiced[0]
+        acf = acf[0] if return_acf else None
+    return (f0, voiced, acf) if return_acf else (f0, voiced)

@@ -44,6 +44,14 @@ out["pre/default"] = A(ref.preemphasis(mx.array(y2)))
 o2, zf = ref.preemphasis(mx.array(y2), coef=0.9, zi=mx.array(np.array([0.5, -0.25], np.float32)), return_zf=True)
 out["pre/zi"], out["pre/zf"] = A(o2), A(zf)
 out["pre/1d"] = A(ref.preemphasis(mx.array(y2[0]), coef=0.5))
+tt = np.arange(9000) / 22050.0
+yp = np.stack([np.sin(2 * np.pi * 220.0 * tt) + 0.3 * np.sin(2 * np.pi * 440.0 * tt),
+               np.sin(2 * np.pi * (150.0 + 400.0 * tt) * tt) * (tt < 0.3) + 0.01 * np.random.default_rng(3).standard_normal(9000)]).astype(np.float32)
+out["pitch/input"] = yp
+f0, vo = ref.pitch_detect_acf(mx.array(yp), sr=22050)
+out["pitch/f0"], out["pitch/voiced"] = A(f0), A(vo)
+f0, vo = ref.pitch_detect_acf(mx.array(yp[0]), sr=22050, fmin=80.0, fmax=800.0, frame_length=1024, hop_length=256, threshold=0.3, center=False)
+out["pitch/f0_b"], out["pitch/voiced_b"] = A(f0), A(vo)
 M = np.asarray(g["mfcc/0"]) if "mfcc/0" in g.files else np.random.default_rng(5).standard_normal((2, 13, 40)).astype(np.float32)
 out["delta/input"] = M.astype(np.float32)
 out["delta/w9o1"] = A(ref.delta(mx.array(M)))

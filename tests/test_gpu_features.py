@@ -162,6 +162,43 @@ def test_delta_matches_reference_and_scipy(ap):
         ap.delta(short, width=9)
 
 
+def test_pitch_detect_acf(ap):
+    """Fixtures of the reference's own code, then tones / chirps / noise / silence against the float64 oracle.  f0 is
+    sr / (an integer lag picked by comparisons on a float32 autocorrelation): identical lags are required on at
+    least 98 % of the frames, and on all frames of clean tones; a differing frame must be a neighbouring-peak
+    decision (never garbage): its autocorrelation value at our lag is within 1e-3 of the oracle's at its lag."""
+    g = np.load(os.path.join(GOLDEN, "reference_features.npz"))
+    yp = g["pitch/input"]
+    f0, vo = ap.pitch_detect_acf(yp, sr=22050)
+    assert np.array_equal(H(vo), g["pitch/voiced"]) and (H(f0) == g["pitch/f0"]).mean() >= 0.97
+    f0, vo = ap.pitch_detect_acf(yp[0], sr=22050, fmin=80.0, fmax=800.0, frame_length=1024, hop_length=256, threshold=0.3, center=False)
+    assert np.array_equal(H(vo), g["pitch/voiced_b"]) and (H(f0) == g["pitch/f0_b"]).mean() >= 0.97
+    sr = 16000
+    t = np.arange(3 * sr) / sr
+    rng = np.random.default_rng(12)
+    y = np.stack([np.sin(2 * np.pi * 200.0 * t), np.sin(2 * np.pi * 110.0 * t) + 0.5 * np.sin(2 * np.pi * 220.0 * t + 1.0),
+                  np.sin(2 * np.pi * (100.0 + 150.0 * t) * t), 0.3 * rng.standard_normal(t.size), np.zeros_like(t),
+                  np.sin(2 * np.pi * 440.0 * t) * (t > 1.0) + 1e-3 * rng.standard_normal(t.size)]).astype(np.float32)
+    for kw in (dict(), dict(frame_length=1024, hop_length=256, fmin=60.0, fmax=1000.0), dict(frame_length=512, hop_length=128, fmin=100.0, center=False),
+               dict(frame_length=700, hop_length=300, fmin=80.0, threshold=0.5)):
+        ref_f0, ref_vo, acf = of.pitch_detect_acf(y, sr=sr, return_acf=True, **kw)
+        f0, vo = ap.pitch_detect_acf(y, sr=sr, **kw)
+        f0, vo = H(f0), H(vo)
+        assert f0.shape == ref_f0.shape and vo.dtype == bool
+        assert (vo == ref_vo).mean() >= 0.99
+        assert np.array_equal(f0[:2], ref_f0[:2]) and not vo[4].any()  # clean tones exact, silence unvoiced
+        both = vo & ref_vo
+        assert (f0[both] == ref_f0[both]).mean() >= 0.98
+        bad = np.argwhere(both & (f0 != ref_f0))
+        for b, k in bad:
+            ours, theirs = int(round(sr / f0[b, k])), int(round(sr / ref_f0[b, k]))
+            assert abs(acf[b, k, ours] - acf[b, k, theirs]) <= 1e-3, (b, k, ours, theirs)
+    with pytest.raises(ValueError, match="must be less than fmax"):
+        ap.pitch_detect_acf(y, fmin=500.0, fmax=100.0)
+    with pytest.raises(ValueError, match="frame_length must be within"):
+        ap.pitch_detect_acf(y, frame_length=4096)
+
+
 def test_feature_errors(ap):
     y = np.zeros(4000, np.float32)
     with pytest.raises(ValueError, match="Either y"):

@@ -243,6 +243,11 @@ def test_feature_oracle_matches_reference_code():
     o2, zf = of.preemphasis(y2, coef=0.9, zi=np.array([0.5, -0.25], np.float32), return_zf=True)
     assert np.array_equal(o2, g["pre/zi"]) and np.array_equal(zf, g["pre/zf"])
     assert np.array_equal(of.preemphasis(y2[0], coef=0.5), g["pre/1d"])
+    f0, vo = of.pitch_detect_acf(g["pitch/input"], sr=22050)
+    assert np.array_equal(f0, g["pitch/f0"]) and np.array_equal(vo, g["pitch/voiced"])
+    f0, vo = of.pitch_detect_acf(g["pitch/input"][0], sr=22050, fmin=80.0, fmax=800.0, frame_length=1024, hop_length=256,
+                                 threshold=0.3, center=False)
+    assert np.array_equal(f0, g["pitch/f0_b"]) and np.array_equal(vo, g["pitch/voiced_b"])
     M = g["delta/input"]
     for key, kw in (("w9o1", {}), ("w9o2", dict(order=2)), ("w5o1_mirror", dict(width=5, mode="mirror")),
                     ("w7o1_nearest_axis1", dict(width=7, mode="nearest", axis=1)), ("w3o1_wrap", dict(width=3, mode="wrap")),

@@ -68,7 +68,7 @@ def report(name, label, audio_s, ms, bytes_, flops, extra=None):
 
 def main():
     a = argparse.ArgumentParser()
-    a.add_argument("--configs", default="c1,c2,c3,c4,c5,f1,f2")
+    a.add_argument("--configs", default="c1,c2,c3,c4,c5,f1,f2,f3")
     a.add_argument("--iters", type=int, default=20)
     a.add_argument("--clips-scale", type=float, default=1.0, help="scale the batch (e.g. 0.125 = one of 8 GPUs' share)")
     args = a.parse_args()
@@ -149,6 +149,16 @@ def main():
         ms = timed(tdom, args.iters)
         report("f2", f"rms+zcr (2048/512)+preemphasis 22.05k {B}x30 s (3 calls)", B * 30.0, ms,
                B * (2 * (4 * L + 4 * T) + 8 * L), B * (2 * 2 * 2048 * T + 2 * L))
+    if "f3" in want:  # section 8(f) rank 3 / 4: autocorrelation pitch detector and delta features
+        B, L = max(1, int(1024 * sc * 0.125)), 661500
+        y = clips(B, L, 22050)
+        T = 1 + L // 512
+        ms = timed(lambda: ap.pitch_detect_acf(y, sr=22050), args.iters)
+        report("f3", f"pitch_detect_acf 2048/512 (two 4096-point transforms per frame) 22.05k {B}x30 s", B * 30.0, ms,
+               B * (4 * L + 5 * T), B * T * (2 * fft_flops(4096) + 3 * 2049 + 2 * 2048))
+        M = torch.randn((B, 40, 2584), device="cuda")
+        ms_d = timed(lambda: ap.delta(M), args.iters)
+        report("f3b", f"delta width 9 on ({B}, 40, 2584) MFCCs", B * 60.0, ms_d, 2 * M.numel() * 4, 2 * 9 * M.numel())
 
 
 if __name__ == "__main__":
