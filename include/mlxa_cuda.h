@@ -260,6 +260,16 @@ int mlxa_spectral_feature_f32(const float* y, int64_t B, int64_t L, int64_t ldy,
  * voiced (B, T) uint8, T = 1 + (L + 2*(frame_length/2 if center) - frame_length) / hop. */
 int mlxa_pitch_acf_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int frame_length, int hop, int center,
                        float sr, float fmin, float fmax, float threshold, float* f0, uint8_t* voiced, void* stream);
+/* Rational resampling along the last axis (resample.py:215-300, scipy.signal.resample_poly on the host in the
+ * reference): out[r, j] = sum_i x[r, i] * h[(j + pre_remove)*down - i*up].  h (len_h, DEVICE) is the zero-padded Kaiser
+ * low-pass already multiplied by `up`, pre_remove / n_out as scipy derives them -- all computed on the host
+ * (mlx_audio_primitives_b200/resample.py restates the design).  x (rows, n_in) -> out (rows, n_out). */
+int mlxa_resample_poly_f32(const float* x, int64_t rows, int64_t n_in, const float* h, int len_h, int up, int down,
+                           int64_t pre_remove, int64_t n_out, float* out, void* stream);
+/* Linear-interpolation resampling (resample.py:142-212): positions linspace(0, n_in - 1, n_out), blend in float64 like
+ * NumPy, optional gain (scale=True), rounded to float32. */
+int mlxa_resample_linear_f32(const float* x, int64_t rows, int64_t n_in, int64_t n_out, double gain, int apply_gain,
+                             float* out, void* stream);
 /* Savitzky-Golay filter along the last axis: the `delta` features of reference mfcc.py:290-371, which calls
  * scipy.signal.savgol_filter on the host.  x, out (rows, T); taps: `width` correlation taps (out[t] = sum_j taps[j] *
  * x[t - width/2 + j]); mode 0 interp (edge_left / edge_right: (width/2, width) operators applied to the first / last

@@ -19,6 +19,7 @@ from .stft import check_nola, istft, magnitude, overlap_add, pad_signal, phase, 
 from .windows import get_window
 from .pipeline import LogMelPlan
 from .pitch import pitch_detect_acf
+from .resample import resample, resample_poly
 from . import distributed
 
 __version__ = "0.1.0"
@@ -31,5 +32,5 @@ __all__ = [
     "linear_filterbank", "bark_filterbank", "hz_to_bark", "bark_to_hz",
     "pad_signal", "overlap_add", "distributed", "LogMelPlan",
     "spectral_centroid", "spectral_bandwidth", "spectral_rolloff", "spectral_flatness", "spectral_contrast",
-    "zero_crossing_rate", "rms", "preemphasis", "delta", "pitch_detect_acf",
+    "zero_crossing_rate", "rms", "preemphasis", "delta", "pitch_detect_acf", "resample", "resample_poly",
 ]

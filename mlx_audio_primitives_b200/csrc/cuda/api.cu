@@ -494,6 +494,19 @@ int mlxa_pitch_acf_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int fr
     CHECK_CUDA(e, "pitch_acf");
     return 0;
 }
+int mlxa_resample_poly_f32(const float* x, int64_t rows, int64_t n_in, const float* h, int len_h, int up, int down,
+                           int64_t pre_remove, int64_t n_out, float* out, void* stream) {
+    CHECK_ARG(x && h && out && rows > 0 && n_in > 0 && n_out > 0 && len_h > 0 && up > 0 && down > 0 && pre_remove >= 0, "bad argument");
+    CHECK_CUDA(run_resample_poly(x, rows, n_in, h, len_h, up, down, pre_remove, n_out, out, (cudaStream_t)stream), "resample_poly");
+    return 0;
+}
+int mlxa_resample_linear_f32(const float* x, int64_t rows, int64_t n_in, int64_t n_out, double gain, int apply_gain, float* out,
+                             void* stream) {
+    CHECK_ARG(x && out && rows > 0 && n_in > 0 && n_out > 0, "bad argument");
+    const double step = n_out > 1 ? double(n_in - 1) / double(n_out - 1) : 0.0;  // np.linspace(0, n_in - 1, n_out)
+    CHECK_CUDA(run_resample_linear(x, rows, n_in, n_out, step, gain, apply_gain, out, (cudaStream_t)stream), "resample_linear");
+    return 0;
+}
 int mlxa_savgol_f32(const float* x, int64_t rows, int64_t T, const float* taps, int width, int mode, float cval,
                     const float* edge_left, const float* edge_right, float* out, void* stream) {
     CHECK_ARG(x && taps && out && rows > 0 && T > 0, "bad argument");

@@ -313,6 +313,44 @@ __global__ void savgol_kernel(const float* __restrict__ x, long long rows, long 
     }
 }
 
+// Polyphase rational resampling (reference resample.py:215-300 = scipy.signal.resample_poly on the host):
+// out[r, j] = sum_i x[r, i] * h[(j + pre_remove)*down - i*up], h the zero-padded, up-scaled Kaiser low-pass designed on
+// the host; one thread per output sample, the taps it meets are `up` apart.
+__global__ void resample_poly_kernel(const float* __restrict__ x, long long rows, long long n_in, const float* __restrict__ h,
+                                     int len_h, int up, int down, long long pre_remove, long long n_out,
+                                     float* __restrict__ out) {
+    const long long n = rows * n_out;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / n_out, j = idx - r * n_out;
+        const long long m = (j + pre_remove) * down;
+        long long i_hi = m / up;
+        if (i_hi > n_in - 1) i_hi = n_in - 1;
+        const long long lo_num = m - len_h + 1;
+        long long i_lo = lo_num <= 0 ? 0 : (lo_num + up - 1) / up;
+        const float* xr = x + r * n_in;
+        float acc = 0.f;
+        for (long long i = i_lo; i <= i_hi; ++i) acc = fmaf(xr[i], __ldg(h + (m - i * up)), acc);
+        out[idx] = acc;
+    }
+}
+// Linear-interpolation resampling (resample.py:142-212): positions linspace(0, n_in - 1, n_out) and the blend in
+// float64 like NumPy, the result rounded to float32 (and scaled by `gain` in float64 first when asked).
+__global__ void resample_linear_kernel(const float* __restrict__ x, long long rows, long long n_in, long long n_out, double step,
+                                       double gain, int apply_gain, float* __restrict__ out) {
+    const long long n = rows * n_out;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / n_out, j = idx - r * n_out;
+        const double t = (j == n_out - 1 && n_out > 1) ? double(n_in - 1) : double(j) * step;
+        const long long lo = (long long)floor(t);
+        const long long hi = lo + 1 < n_in ? lo + 1 : n_in - 1;
+        const double frac = t - double(lo);
+        const float* xr = x + r * n_in;
+        double v = (1.0 - frac) * double(xr[lo]) + frac * double(xr[hi]);
+        if (apply_gain) v *= gain;
+        out[idx] = float(v);
+    }
+}
+
 unsigned grid_for_rows(long long rows, int per_cta) {
     const long long g = (rows + per_cta - 1) / per_cta;
     return (unsigned)(g < 1 ? 1 : (g > 148LL * 32 ? 148LL * 32 : g));
@@ -350,6 +388,20 @@ cudaError_t run_savgol(const float* x, long long rows, long long T, const float*
     const long long n = rows * T, g = (n + 255) / 256;
     savgol_kernel<<<(unsigned)(g < 1 ? 1 : (g > 148LL * 64 ? 148LL * 64 : g)), 256, (size_t)width * 4, s>>>(
         x, rows, T, taps, width, mode, cval, edge_left, edge_right, out);
+    return cudaGetLastError();
+}
+cudaError_t run_resample_poly(const float* x, long long rows, long long n_in, const float* h, int len_h, int up, int down,
+                              long long pre_remove, long long n_out, float* out, cudaStream_t s) {
+    const long long n = rows * n_out, g = (n + 255) / 256;
+    resample_poly_kernel<<<(unsigned)(g < 1 ? 1 : (g > 148LL * 64 ? 148LL * 64 : g)), 256, 0, s>>>(x, rows, n_in, h, len_h, up, down,
+                                                                                                 pre_remove, n_out, out);
+    return cudaGetLastError();
+}
+cudaError_t run_resample_linear(const float* x, long long rows, long long n_in, long long n_out, double step, double gain,
+                                int apply_gain, float* out, cudaStream_t s) {
+    const long long n = rows * n_out, g = (n + 255) / 256;
+    resample_linear_kernel<<<(unsigned)(g < 1 ? 1 : (g > 148LL * 64 ? 148LL * 64 : g)), 256, 0, s>>>(x, rows, n_in, n_out, step, gain,
+                                                                                                   apply_gain, out);
     return cudaGetLastError();
 }
 cudaError_t run_frame_stats(const float* y, long long B, int L, long long ldy, int frame_length, int hop, int pad, int pad_mode,

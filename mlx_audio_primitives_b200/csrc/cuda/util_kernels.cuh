@@ -37,6 +37,10 @@ cudaError_t run_spectral_contrast(const void* S, int is_complex, long long B, lo
                                   int linear, float* out, cudaStream_t s);
 cudaError_t run_savgol(const float* x, long long rows, long long T, const float* taps, int width, int mode, float cval,
                        const float* edge_left, const float* edge_right, float* out, cudaStream_t s);
+cudaError_t run_resample_poly(const float* x, long long rows, long long n_in, const float* h, int len_h, int up, int down,
+                              long long pre_remove, long long n_out, float* out, cudaStream_t s);
+cudaError_t run_resample_linear(const float* x, long long rows, long long n_in, long long n_out, double step, double gain,
+                                int apply_gain, float* out, cudaStream_t s);
 cudaError_t run_frame_stats(const float* y, long long B, int L, long long ldy, int frame_length, int hop, int pad, int pad_mode,
                             long long T, int kind, float* out, cudaStream_t s);
 cudaError_t run_preemphasis(const float* y, long long B, long long L, long long ldy, float coef, const float* zi, float* out,

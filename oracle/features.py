@@ -271,3 +271,41 @@ def pitch_detect_acf(y, sr=22050, fmin=50.0, fmax=2000.0, frame_length=2048, hop
         f0, voiced = f0[0], voiced[0]
         acf = acf[0] if return_acf else None
     return (f0, voiced, acf) if return_acf else (f0, voiced)
+
+
+def resample_poly(y, up, down, axis=-1, padtype="constant"):
+    """resample.py:215-300: gcd reduction, then scipy.signal.resample_poly (the third-party algorithm itself) and a
+    float32 cast."""
+    import math
+    from scipy.signal import resample_poly as sp
+    if up <= 0:
+        raise ValueError(f"up must be positive, got {up}")
+    if down <= 0:
+        raise ValueError(f"down must be positive, got {down}")
+    g = math.gcd(up, down)
+    up, down = up // g, down // g
+    y = np.asarray(y)
+    if up == 1 and down == 1:
+        return y
+    return sp(y, up, down, axis=axis, padtype=padtype).astype(np.float32)
+
+
+def resample_linear(y, orig_sr, target_sr, fix=True, scale=False, axis=-1):
+    """resample.py:142-212 (res_type='linear'): positions linspace(0, n - 1, target), blend in float64, float32 cast."""
+    y = np.asarray(y, dtype=np.float32)
+    if orig_sr == target_sr:
+        return y
+    y = np.moveaxis(y, axis, -1)
+    n = y.shape[-1]
+    ratio = target_sr / orig_sr
+    m = int(np.round(n * ratio)) if fix else int(np.ceil(n * ratio))
+    if m == n:
+        return np.moveaxis(y, -1, axis)
+    t = np.linspace(0, n - 1, m)
+    lo = np.floor(t).astype(np.int32)
+    hi = np.minimum(lo + 1, n - 1)
+    fr = t - lo
+    out = (1 - fr) * y[..., lo] + fr * y[..., hi]
+    if scale:
+        out = out * ratio
+    return np.moveaxis(out.astype(np.float32), -1, axis)

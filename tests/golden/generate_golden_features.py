@@ -52,6 +52,11 @@ f0, vo = ref.pitch_detect_acf(mx.array(yp), sr=22050)
 out["pitch/f0"], out["pitch/voiced"] = A(f0), A(vo)
 f0, vo = ref.pitch_detect_acf(mx.array(yp[0]), sr=22050, fmin=80.0, fmax=800.0, frame_length=1024, hop_length=256, threshold=0.3, center=False)
 out["pitch/f0_b"], out["pitch/voiced_b"] = A(f0), A(vo)
+out["rs/poly_1_2"] = A(ref.resample_poly(mx.array(y2), 1, 2))
+out["rs/poly_3_2"] = A(ref.resample_poly(mx.array(y2[0]), 3, 2))
+out["rs/poly_160_147"] = A(ref.resample_poly(mx.array(y2[:, :2000]), 160, 147))
+out["rs/lin_down"] = A(ref.resample(mx.array(y2), 22050, 16000, res_type="linear"))
+out["rs/lin_up_scale"] = A(ref.resample(mx.array(y2[1]), 16000, 44100, res_type="linear", fix=False, scale=True))
 M = np.asarray(g["mfcc/0"]) if "mfcc/0" in g.files else np.random.default_rng(5).standard_normal((2, 13, 40)).astype(np.float32)
 out["delta/input"] = M.astype(np.float32)
 out["delta/w9o1"] = A(ref.delta(mx.array(M)))

@@ -199,6 +199,30 @@ def test_pitch_detect_acf(ap):
         ap.pitch_detect_acf(y, frame_length=4096)
 
 
+def test_resample(ap):
+    """resample_poly / resample(linear): reference fixtures, then SciPy / the NumPy restatement on odd shapes and axes."""
+    g = np.load(os.path.join(GOLDEN, "reference_features.npz"))
+    y2 = np.load(os.path.join(GOLDEN, "reference_outputs.npz"))["stft/input"]
+    close(H(ap.resample_poly(y2, 1, 2)), g["rs/poly_1_2"], 2e-6)
+    close(H(ap.resample_poly(y2[0], 3, 2)), g["rs/poly_3_2"], 2e-6)
+    close(H(ap.resample_poly(y2[:, :2000], 160, 147)), g["rs/poly_160_147"], 2e-6)
+    assert np.array_equal(H(ap.resample(y2, 22050, 16000, res_type="linear")), g["rs/lin_down"])
+    assert np.array_equal(H(ap.resample(y2[1], 16000, 44100, res_type="linear", fix=False, scale=True)), g["rs/lin_up_scale"])
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((3, 5, 1234)).astype(np.float32)
+    for up, down, axis in [(2, 1, -1), (4, 6, -1), (7, 3, 2), (1, 5, -1), (3, 2, 1), (147, 160, -1), (6, 6, -1)]:
+        close(H(ap.resample_poly(X, up, down, axis=axis)), of.resample_poly(X.astype(np.float64), up, down, axis=axis), 5e-6)
+    for a, b, kw in [(44100, 22050, {}), (16000, 22050, dict(fix=False)), (8000, 8001, dict(scale=True)), (48000, 16000, dict(axis=1))]:
+        assert np.array_equal(H(ap.resample(X, a, b, res_type="linear", **kw)), of.resample_linear(X, a, b, **kw))
+    assert ap.resample(X, 16000, 16000).shape == X.shape
+    with pytest.raises(NotImplementedError):
+        ap.resample(X, 16000, 8000)
+    with pytest.raises(ValueError, match="Unknown res_type"):
+        ap.resample(X, 16000, 8000, res_type="sinc")
+    with pytest.raises(ValueError, match="up must be positive"):
+        ap.resample_poly(X, 0, 2)
+
+
 def test_feature_errors(ap):
     y = np.zeros(4000, np.float32)
     with pytest.raises(ValueError, match="Either y"):

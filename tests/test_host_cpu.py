@@ -95,6 +95,25 @@ def test_savgol_operators_match_scipy():
         assert np.abs(x[:, -width:] @ right.T.astype(np.float64) - want[:, -h:]).max() <= 2e-5 * np.abs(want).max()
 
 
+def test_poly_filter_matches_scipy():
+    """The host-side design of resample_poly (Kaiser low-pass, padding, trimming) against SciPy: applying the taps by the
+    kernel's formula reproduces scipy.signal.resample_poly."""
+    from scipy.signal import resample_poly
+    from mlx_audio_primitives_b200.resample import poly_filter_host
+    x = np.random.default_rng(1).standard_normal((2, 157)).astype(np.float32)
+    for up, down in [(1, 2), (3, 1), (2, 3), (160, 147), (5, 4)]:
+        taps, pre, n_out = poly_filter_host(up, down, x.shape[1])
+        ref = resample_poly(x, up, down, axis=-1)
+        assert ref.shape == (2, n_out)
+        got = np.zeros((2, n_out))
+        for j in range(n_out):
+            m = (j + pre) * down
+            lo = max(0, -((-(m - taps.size + 1)) // up))
+            for i in range(lo, min(x.shape[1] - 1, m // up) + 1):
+                got[:, j] += x[:, i].astype(np.float64) * taps[m - i * up]
+        assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
 def test_host_validation_messages():
     from mlx_audio_primitives_b200.mel import _resolve_stft_args, check_band_args, frames_or_raise, pad_mode_code
     from mlx_audio_primitives_b200.windows import window_host

@@ -248,6 +248,10 @@ def test_feature_oracle_matches_reference_code():
     f0, vo = of.pitch_detect_acf(g["pitch/input"][0], sr=22050, fmin=80.0, fmax=800.0, frame_length=1024, hop_length=256,
                                  threshold=0.3, center=False)
     assert np.array_equal(f0, g["pitch/f0_b"]) and np.array_equal(vo, g["pitch/voiced_b"])
+    assert np.array_equal(of.resample_poly(y2, 1, 2), g["rs/poly_1_2"]) and np.array_equal(of.resample_poly(y2[0], 3, 2), g["rs/poly_3_2"])
+    assert np.array_equal(of.resample_poly(y2[:, :2000], 160, 147), g["rs/poly_160_147"])
+    assert np.array_equal(of.resample_linear(y2, 22050, 16000), g["rs/lin_down"])
+    assert np.array_equal(of.resample_linear(y2[1], 16000, 44100, fix=False, scale=True), g["rs/lin_up_scale"])
     M = g["delta/input"]
     for key, kw in (("w9o1", {}), ("w9o2", dict(order=2)), ("w5o1_mirror", dict(width=5, mode="mirror")),
                     ("w7o1_nearest_axis1", dict(width=7, mode="nearest", axis=1)), ("w3o1_wrap", dict(width=3, mode="wrap")),
