@@ -572,9 +572,13 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
             default: return launch_one<EP_FEAT, STAT_FLATNESS>(p, smem, s);
         }
     }
-    if (p.power_mode == POW_SQUARE) return launch_one<EP_MEL, POW_SQUARE>(p, smem, s);
-    if (p.power_mode == POW_ABS) return launch_one<EP_MEL, POW_ABS>(p, smem, s);
-    return launch_one<EP_MEL, POW_GENERAL>(p, smem, s);
+    if constexpr (PACK) {  // (pair-mode plans never get here: their mel epilogue is mel_rows_kernel)
+        if (p.power_mode == POW_SQUARE) return launch_one<EP_MEL, POW_SQUARE>(p, smem, s);
+        if (p.power_mode == POW_ABS) return launch_one<EP_MEL, POW_ABS>(p, smem, s);
+        return launch_one<EP_MEL, POW_GENERAL>(p, smem, s);
+    } else {
+        return cudaErrorInvalidConfiguration;
+    }
 }
 
 // host tables: plan twiddles and the real-unpack twiddle 0.5*exp(-i*pi*k/N)
