@@ -270,6 +270,12 @@ int mlxa_resample_poly_f32(const float* x, int64_t rows, int64_t n_in, const flo
  * NumPy, optional gain (scale=True), rounded to float32. */
 int mlxa_resample_linear_f32(const float* x, int64_t rows, int64_t n_in, int64_t n_out, double gain, int apply_gain,
                              float* out, void* stream);
+/* Whole-signal autocorrelation r[k] = sum_n y[n] y[n + k], k < max_lag <= n, of the (optionally mean-removed) clips,
+ * optionally divided by max(r[0], 1e-10) (pitch.py:16-116; the reference takes it from one zero-padded FFT of the entire
+ * signal).  Direct, deterministic sum, float32 inside 2048-sample chunks and float64 across them: O(n * max_lag).
+ * out (B, max_lag); scratch: 2*B device floats. */
+int mlxa_autocorrelation_f32(const float* y, int64_t B, int64_t n, int64_t ldy, int max_lag, int normalize, int center,
+                             float* out, float* scratch, void* stream);
 /* Savitzky-Golay filter along the last axis: the `delta` features of reference mfcc.py:290-371, which calls
  * scipy.signal.savgol_filter on the host.  x, out (rows, T); taps: `width` correlation taps (out[t] = sum_j taps[j] *
  * x[t - width/2 + j]); mode 0 interp (edge_left / edge_right: (width/2, width) operators applied to the first / last

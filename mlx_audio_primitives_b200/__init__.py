@@ -18,7 +18,7 @@ from .mfcc import dct, dct_matrix, delta, mfcc
 from .stft import check_nola, istft, magnitude, overlap_add, pad_signal, phase, stft
 from .windows import get_window
 from .pipeline import LogMelPlan
-from .pitch import pitch_detect_acf
+from .pitch import autocorrelation, pitch_detect_acf
 from .resample import resample, resample_poly
 from . import distributed
 
@@ -32,5 +32,5 @@ __all__ = [
     "linear_filterbank", "bark_filterbank", "hz_to_bark", "bark_to_hz",
     "pad_signal", "overlap_add", "distributed", "LogMelPlan",
     "spectral_centroid", "spectral_bandwidth", "spectral_rolloff", "spectral_flatness", "spectral_contrast",
-    "zero_crossing_rate", "rms", "preemphasis", "delta", "pitch_detect_acf", "resample", "resample_poly",
+    "zero_crossing_rate", "rms", "preemphasis", "delta", "pitch_detect_acf", "autocorrelation", "resample", "resample_poly",
 ]

@@ -48,6 +48,7 @@ SIGNATURES = {
     "mlxa_pitch_acf_f32": [_p, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _p, _p, _p],
     "mlxa_resample_poly_f32": [_p, _i64, _i64, _p, _i32, _i32, _i32, _i64, _i64, _p, _p],
     "mlxa_resample_linear_f32": [_p, _i64, _i64, _i64, C.c_double, _i32, _p, _p],
+    "mlxa_autocorrelation_f32": [_p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p],
     "mlxa_savgol_f32": [_p, _i64, _i64, _p, _i32, _i32, _f32, _p, _p, _p, _p],
     "mlxa_spectral_contrast_f32": [_p, _i32, _i64, _i64, _i32, _p, _i32, _i32, _p, _p],
     "mlxa_spectral_feature_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _p, _f32, _i32, _f32, _f32, _i32, _p, _p, _p],

@@ -507,6 +507,12 @@ int mlxa_resample_linear_f32(const float* x, int64_t rows, int64_t n_in, int64_t
     CHECK_CUDA(run_resample_linear(x, rows, n_in, n_out, step, gain, apply_gain, out, (cudaStream_t)stream), "resample_linear");
     return 0;
 }
+int mlxa_autocorrelation_f32(const float* y, int64_t B, int64_t n, int64_t ldy, int max_lag, int normalize, int center, float* out,
+                             float* scratch, void* stream) {
+    CHECK_ARG(y && out && scratch && B > 0 && B <= 65535 && n > 0 && ldy >= n && max_lag > 0 && max_lag <= n, "bad argument");
+    CHECK_CUDA(run_autocorrelation(y, B, n, ldy, max_lag, normalize, center, out, scratch, (cudaStream_t)stream), "autocorrelation");
+    return 0;
+}
 int mlxa_savgol_f32(const float* x, int64_t rows, int64_t T, const float* taps, int width, int mode, float cval,
                     const float* edge_left, const float* edge_right, float* out, void* stream) {
     CHECK_ARG(x && taps && out && rows > 0 && T > 0, "bad argument");

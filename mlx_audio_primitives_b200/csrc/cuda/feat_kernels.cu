@@ -351,6 +351,82 @@ __global__ void resample_linear_kernel(const float* __restrict__ x, long long ro
     }
 }
 
+// Whole-signal autocorrelation r[k] = sum_n y[n] y[n + k], k < max_lag (reference pitch.py:16-116 gets it from ONE
+// zero-padded FFT of the entire signal -- up to 2^20 points, not a shared-memory transform).  Here it is the direct sum:
+// a CTA owns 128 lags of a clip, stages the centred signal chunk by chunk in shared memory and accumulates every
+// chunk in float32 and the chunks in float64, in a fixed order (deterministic, and more accurate than a float32 FFT).
+// O(n * max_lag): meant for the lag ranges pitch analysis uses; max_lag = n is served but quadratic.
+constexpr int kAcLags = 128, kAcChunk = 2048;
+__global__ void __launch_bounds__(256) row_mean_kernel(const float* __restrict__ y, long long n, long long ldy, float* __restrict__ mean) {
+    __shared__ double s[256];
+    const float* yb = y + (long long)blockIdx.x * ldy;
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) acc += double(yb[i]);
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mean[blockIdx.x] = float(s[0] / double(n));
+}
+__global__ void __launch_bounds__(256) autocorr_kernel(const float* __restrict__ y, long long n, long long ldy, int max_lag,
+                                                       const float* __restrict__ mean, float* __restrict__ out,
+                                                       float* __restrict__ r0) {
+    __shared__ __align__(16) float s_y[kAcChunk], s_p[kAcChunk + kAcLags + 4];
+    __shared__ double s_part[8][kAcLags];
+    const long long b = blockIdx.y;
+    // a thread owns 4 consecutive lags and one eighth of every chunk: per 4 samples one broadcast 128-bit read of the
+    // chunk and one 128-bit read of the partners' window feed 16 FMAs (the window slides through registers)
+    const int k0 = blockIdx.x * kAcLags, kl = 4 * (threadIdx.x & 31), part_i = threadIdx.x >> 5;
+    const float* yb = y + b * ldy;
+    const float mu = mean ? __ldg(mean + b) : 0.f;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // lag k = k0 + kl + l pairs y[n] with y[n + k]: s_y holds the chunk, s_p the partners' window starting k0 later
+    for (long long n0 = 0; n0 + k0 < n; n0 += kAcChunk) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kAcChunk + kAcLags + 4; i += 256) {
+            const long long q = n0 + i, qp = q + k0;
+            if (i < kAcChunk) s_y[i] = (q < n) ? yb[q] - mu : 0.f;
+            s_p[i] = (qp < n) ? yb[qp] - mu : 0.f;
+        }
+        __syncthreads();
+        const int i_lo = part_i * (kAcChunk / 8);
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 pc = *reinterpret_cast<const float4*>(s_p + i_lo + kl);
+#pragma unroll 4
+        for (int i = i_lo; i < i_lo + kAcChunk / 8; i += 4) {
+            const float4 y4 = *reinterpret_cast<const float4*>(s_y + i);
+            const float4 pn = *reinterpret_cast<const float4*>(s_p + i + kl + 4);
+            const float P[8] = {pc.x, pc.y, pc.z, pc.w, pn.x, pn.y, pn.z, pn.w};
+            const float Y[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int l = 0; l < 4; ++l) part[l] = fmaf(Y[a], P[a + l], part[l]);
+            pc = pn;
+        }
+#pragma unroll
+        for (int l = 0; l < 4; ++l) acc[l] += double(part[l]);
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) s_part[part_i][kl + l] = acc[l];
+    __syncthreads();
+    if (threadIdx.x < kAcLags) {
+        const int k = k0 + threadIdx.x;
+        double r = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r += s_part[q][threadIdx.x];
+        if (k < max_lag) out[b * max_lag + k] = float(r);
+        if (k == 0) r0[b] = float(r);
+    }
+}
+__global__ void autocorr_normalize_kernel(float* __restrict__ out, long long B, int max_lag, const float* __restrict__ r0) {
+    const long long n = B * max_lag;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = out[i] / fmaxf(__ldg(r0 + i / max_lag), 1e-10f);
+}
+
 unsigned grid_for_rows(long long rows, int per_cta) {
     const long long g = (rows + per_cta - 1) / per_cta;
     return (unsigned)(g < 1 ? 1 : (g > 148LL * 32 ? 148LL * 32 : g));
@@ -402,6 +478,19 @@ cudaError_t run_resample_linear(const float* x, long long rows, long long n_in, 
     const long long n = rows * n_out, g = (n + 255) / 256;
     resample_linear_kernel<<<(unsigned)(g < 1 ? 1 : (g > 148LL * 64 ? 148LL * 64 : g)), 256, 0, s>>>(x, rows, n_in, n_out, step, gain,
                                                                                                    apply_gain, out);
+    return cudaGetLastError();
+}
+cudaError_t run_autocorrelation(const float* y, long long B, long long n, long long ldy, int max_lag, int normalize, int center,
+                                float* out, float* scratch, cudaStream_t s) {
+    float* mean = scratch;
+    float* r0 = scratch + B;
+    if (center) row_mean_kernel<<<(unsigned)B, 256, 0, s>>>(y, n, ldy, mean);
+    dim3 grid((unsigned)((max_lag + kAcLags - 1) / kAcLags), (unsigned)B);
+    autocorr_kernel<<<grid, 256, 0, s>>>(y, n, ldy, max_lag, center ? mean : nullptr, out, r0);
+    if (normalize) {
+        const long long tot = B * max_lag, g = (tot + 255) / 256;
+        autocorr_normalize_kernel<<<(unsigned)(g > 148LL * 32 ? 148LL * 32 : g), 256, 0, s>>>(out, B, max_lag, r0);
+    }
     return cudaGetLastError();
 }
 cudaError_t run_frame_stats(const float* y, long long B, int L, long long ldy, int frame_length, int hop, int pad, int pad_mode,

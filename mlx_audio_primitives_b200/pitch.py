@@ -2,8 +2,9 @@
 
 The reference loops over frames in NumPy on the host (rfft -> |Y|^2 -> irfft -> peak picking per frame); here
 one kernel does it for every frame of the batch with two passes through the shared-memory FFT engine and
-writes only (f0, voiced).  Frames up to 2048 samples (transform sizes up to 4096) are served; the whole-signal
-``autocorrelation`` (a single transform of up to 2^20 points) is not built."""
+writes only (f0, voiced).  Frames up to 2048 samples (transform sizes up to 4096) are served.  The whole-signal
+``autocorrelation`` (ONE zero-padded FFT of the entire signal in the reference -- not a shared-memory transform) is the
+direct, deterministic sum over the requested lags instead: O(n * max_lag), exact to float64 accumulation."""
 from __future__ import annotations
 
 import torch
@@ -11,6 +12,27 @@ import torch
 from ._extension import _ext, check
 from ._tensor import f32c, ptr, stream_ptr
 from ._validation import validate_positive
+
+
+def autocorrelation(y, max_lag: int | None = None, normalize: bool = True, center: bool = True) -> torch.Tensor:
+    """r[k] = sum_n y[n] y[n + k] for k < max_lag (default: the signal length), mean removed first when ``center``,
+    divided by max(r[0], 1e-10) when ``normalize``; (max_lag,) or (B, max_lag) (reference pitch.py:16-116)."""
+    y = f32c(y)
+    one_d = y.ndim == 1
+    if one_d:
+        y = y[None, :]
+    if y.ndim != 2:
+        raise ValueError("signal must be 1-dimensional (samples,) or 2-dimensional (batch, samples)")
+    B, n = y.shape
+    lag = n if (max_lag is None or max_lag <= 0) else min(int(max_lag), n)
+    out = torch.empty((B, lag), dtype=torch.float32, device=y.device)
+    if B and lag:
+        scratch = torch.empty(2 * B, dtype=torch.float32, device=y.device)
+        for b0 in range(0, B, 65535):
+            nb = min(65535, B - b0)
+            check(_ext.mlxa_autocorrelation_f32(ptr(y[b0:]), nb, n, y.stride(0), lag, int(bool(normalize)), int(bool(center)),
+                                                ptr(out[b0:]), ptr(scratch), stream_ptr(y)), "autocorrelation")
+    return out[0] if one_d else out
 
 
 def pitch_detect_acf(y, sr: int = 22050, fmin: float = 50.0, fmax: float = 2000.0, frame_length: int = 2048,

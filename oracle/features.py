@@ -309,3 +309,24 @@ def resample_linear(y, orig_sr, target_sr, fix=True, scale=False, axis=-1):
     if scale:
         out = out * ratio
     return np.moveaxis(out.astype(np.float32), -1, axis)
+
+
+def autocorrelation(y, max_lag=None, normalize=True, center=True, dtype=np.float64):
+    """pitch.py:16-116 (the Python path): r = irfft(|rfft(y - mean, n_fft)|^2)[:max_lag], n_fft the power of two >= 2n - 1,
+    divided by max(r[0], 1e-10) when normalize; float32 result."""
+    y = np.asarray(y, dtype=np.float32)
+    one_d = y.ndim == 1
+    if one_d:
+        y = y[None]
+    n = y.shape[1]
+    lag = n if max_lag is None else min(max_lag, n)
+    x = y.astype(dtype)
+    if center:
+        x = x - x.mean(-1, keepdims=True)
+    n_fft = 2 ** int(np.ceil(np.log2(2 * n - 1)))
+    Y = np.fft.rfft(x, n=n_fft, axis=-1)
+    r = np.fft.irfft(Y * np.conj(Y), n=n_fft, axis=-1)[:, :lag]
+    if normalize:
+        r = r / np.maximum(r[:, :1], 1e-10)
+    r = r.astype(np.float32)
+    return r[0] if one_d else r

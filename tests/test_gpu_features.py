@@ -243,3 +243,29 @@ def test_feature_errors(ap):
         ap.spectral_contrast(y, quantile=1.5)
     assert tuple(ap.spectral_contrast(y).shape) == (7, 8)
     assert tuple(ap.spectral_centroid(y).shape) == (1, 8) and float(ap.spectral_centroid(y).abs().max()) == 0.0
+
+
+def test_autocorrelation_matches_reference_and_oracle():
+    import mlx_audio_primitives_b200 as mb
+    from oracle import features as of
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_features.npz"))
+    yp = g["pitch/input"]
+    got = mb.autocorrelation(torch.from_numpy(yp).cuda(), max_lag=600).cpu().numpy()
+    assert got.shape == g["acf/default"].shape
+    assert np.abs(got - g["acf/default"]).max() < 1e-5          # normalised: |r| <= 1 (reference tolerance 1e-4)
+    raw = mb.autocorrelation(torch.from_numpy(yp[0, :3000]).cuda(), normalize=False, center=False).cpu().numpy()
+    assert raw.shape == (3000,)
+    assert np.abs(raw - g["acf/raw_1d"]).max() < 1e-5 * np.abs(g["acf/raw_1d"]).max()
+    rng = np.random.default_rng(5)
+    for B, n, lag in ((1, 1, None), (3, 129, None), (2, 5000, 257), (5, 70001, 1000)):
+        y = (rng.standard_normal((B, n)) + 0.3).astype(np.float32)
+        for normalize, center in ((True, True), (False, True), (True, False)):
+            if n == 1 and center:
+                continue                                       # r[0] = 0 -> 0 / 1e-10: nothing to compare
+            want = of.autocorrelation(y, max_lag=lag, normalize=normalize, center=center)
+            got = mb.autocorrelation(torch.from_numpy(y).cuda(), max_lag=lag, normalize=normalize, center=center).cpu().numpy()
+            assert got.shape == want.shape
+            assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max() + 1e-12, (B, n, lag, normalize, center)
+    # a strided view is a legal input; bits equal the contiguous call
+    big = torch.from_numpy(rng.standard_normal((4, 9000)).astype(np.float32)).cuda()
+    assert torch.equal(mb.autocorrelation(big[:, :8000], max_lag=300), mb.autocorrelation(big[:, :8000].contiguous(), max_lag=300))

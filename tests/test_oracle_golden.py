@@ -248,6 +248,9 @@ def test_feature_oracle_matches_reference_code():
     f0, vo = of.pitch_detect_acf(g["pitch/input"][0], sr=22050, fmin=80.0, fmax=800.0, frame_length=1024, hop_length=256,
                                  threshold=0.3, center=False)
     assert np.array_equal(f0, g["pitch/f0_b"]) and np.array_equal(vo, g["pitch/voiced_b"])
+    assert np.abs(of.autocorrelation(g["pitch/input"], max_lag=600) - g["acf/default"]).max() < 1e-6
+    raw = of.autocorrelation(g["pitch/input"][0, :3000], normalize=False, center=False)
+    assert np.abs(raw - g["acf/raw_1d"]).max() < 1e-6 * np.abs(raw).max()
     assert np.array_equal(of.resample_poly(y2, 1, 2), g["rs/poly_1_2"]) and np.array_equal(of.resample_poly(y2[0], 3, 2), g["rs/poly_3_2"])
     assert np.array_equal(of.resample_poly(y2[:, :2000], 160, 147), g["rs/poly_160_147"])
     assert np.array_equal(of.resample_linear(y2, 22050, 16000), g["rs/lin_down"])
