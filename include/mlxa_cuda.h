@@ -270,6 +270,16 @@ int mlxa_resample_poly_f32(const float* x, int64_t rows, int64_t n_in, const flo
  * NumPy, optional gain (scale=True), rounded to float32. */
 int mlxa_resample_linear_f32(const float* x, int64_t rows, int64_t n_in, int64_t n_out, double gain, int apply_gain,
                              float* out, void* stream);
+/* Periodicity per frame (pitch.py:267-383): max of r / r[0] over lags [int(sr/fmax), int(sr/fmin)] of the frame's
+ * autocorrelation (same engine passes as mlxa_pitch_acf_f32), 0 for silent frames or an empty range.  out (B, T). */
+int mlxa_periodicity_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int frame_length, int hop, int center, float sr,
+                         float fmin, float fmax, float* out, void* stream);
+/* De-emphasis out[n] = y[n] + coef * out[n-1] (framing.py:298-392; scipy.signal.lfilter on the host in the reference):
+ * a block-wise scan of the recurrence, float64 inside.  zi: (B) initial states added to out[0], or NULL for zero;
+ * librosa_zi != 0 ignores zi and applies the reference's default correction -corr * coef^n,
+ * corr = ((2 - coef) y[0] - y[1]) / (3 - coef).  zf: (B) final states as scipy reports them, or NULL.  out != y. */
+int mlxa_deemphasis_f32(const float* y, int64_t B, int64_t n, int64_t ldy, double coef, const float* zi, int librosa_zi,
+                        float* out, int64_t ldo, float* zf, void* stream);
 /* Whole-signal autocorrelation r[k] = sum_n y[n] y[n + k], k < max_lag <= n, of the (optionally mean-removed) clips,
  * optionally divided by max(r[0], 1e-10) (pitch.py:16-116; the reference takes it from one zero-padded FFT of the entire
  * signal).  Direct, deterministic sum, float32 inside 2048-sample chunks and float64 across them: O(n * max_lag).

@@ -11,14 +11,14 @@ from .convert import amplitude_to_db, db_to_amplitude, db_to_power, power_to_db
 from .filterbanks import bark_filterbank, bark_to_hz, hz_to_bark, linear_filterbank
 from .features import (spectral_bandwidth, spectral_centroid, spectral_contrast, spectral_flatness, spectral_rolloff,
                        zero_crossing_rate)
-from .framing import frame, preemphasis, rms
+from .framing import deemphasis, frame, preemphasis, rms
 from .griffinlim import griffinlim, griffinlim_iter
 from .mel import hz_to_mel, mel_filterbank, mel_to_hz, melspectrogram
 from .mfcc import dct, dct_matrix, delta, mfcc
 from .stft import check_nola, istft, magnitude, overlap_add, pad_signal, phase, stft
 from .windows import get_window
 from .pipeline import LogMelPlan
-from .pitch import autocorrelation, pitch_detect_acf
+from .pitch import autocorrelation, periodicity, pitch_detect_acf
 from .resample import resample, resample_poly
 from . import distributed
 
@@ -32,5 +32,5 @@ __all__ = [
     "linear_filterbank", "bark_filterbank", "hz_to_bark", "bark_to_hz",
     "pad_signal", "overlap_add", "distributed", "LogMelPlan",
     "spectral_centroid", "spectral_bandwidth", "spectral_rolloff", "spectral_flatness", "spectral_contrast",
-    "zero_crossing_rate", "rms", "preemphasis", "delta", "pitch_detect_acf", "autocorrelation", "resample", "resample_poly",
+    "zero_crossing_rate", "rms", "preemphasis", "delta", "pitch_detect_acf", "autocorrelation", "periodicity", "deemphasis", "resample", "resample_poly",
 ]

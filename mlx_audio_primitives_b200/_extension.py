@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MLXA_CUDA_LIB", os.path.join(_HERE, "_lib", "libmlxaudio_cuda.so"))
 ABI_VERSION = 3
 
-_i64, _i32, _f32, _p = C.c_int64, C.c_int, C.c_float, C.c_void_p
+_i64, _i32, _f32, _f64, _p = C.c_int64, C.c_int, C.c_float, C.c_double, C.c_void_p
 
 # name -> argtypes; mirrors include/mlxa_cuda.h one to one
 SIGNATURES = {
@@ -48,6 +48,8 @@ SIGNATURES = {
     "mlxa_pitch_acf_f32": [_p, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _p, _p, _p],
     "mlxa_resample_poly_f32": [_p, _i64, _i64, _p, _i32, _i32, _i32, _i64, _i64, _p, _p],
     "mlxa_resample_linear_f32": [_p, _i64, _i64, _i64, C.c_double, _i32, _p, _p],
+    "mlxa_periodicity_f32": [_p, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _p, _p],
+    "mlxa_deemphasis_f32": [_p, _i64, _i64, _i64, _f64, _p, _i32, _p, _i64, _p, _p],
     "mlxa_autocorrelation_f32": [_p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p],
     "mlxa_savgol_f32": [_p, _i64, _i64, _p, _i32, _i32, _f32, _p, _p, _p, _p],
     "mlxa_spectral_contrast_f32": [_p, _i32, _i64, _i64, _i32, _p, _i32, _i32, _p, _p],

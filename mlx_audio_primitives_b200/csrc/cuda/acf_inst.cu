@@ -121,6 +121,17 @@ __global__ void __launch_bounds__(THREADS) acf_pitch_kernel(const AcfParams p) {
     float f0 = 0.f;
     int voiced = 0;
     const int len = p.max_lag - p.min_lag + 1;  // search range r[min_lag .. max_lag]
+    if (p.voiced == nullptr) {  // periodicity (pitch.py:267-383): the maximum of r / r[0] over the range, 0 for silent frames
+        float best = 0.f;
+        if (r0 > 1e-10f && len > 0) {
+            best = -INFINITY;
+            for (int i = g; i < len; i += P::G) best = fmaxf(best, fb[p.min_lag + i] / r0);
+#pragma unroll
+            for (int o = P::G / 2; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(gmask, best, o, P::G));
+        }
+        if (live && g == 0) p.f0[frame] = best;
+        return;
+    }
     if (r0 > 1e-10f && len > 0) {  // (group-uniform)
         auto rn = [&](int lag) { return fb[lag] / r0; };
         int first = 0x7fffffff;

@@ -464,10 +464,8 @@ int mlxa_spectral_stats_f32(const void* S, int is_complex, int64_t B, int64_t T,
                "spectral_stats");
     return 0;
 }
-int mlxa_pitch_acf_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int frame_length, int hop, int center, float sr,
-                       float fmin, float fmax, float threshold, float* f0, uint8_t* voiced, void* stream) {
-    CHECK_ARG(y && f0 && voiced && B > 0 && L > 0 && ldy >= L && B < (1LL << 31) && L < (1LL << 30), "bad argument");
-    CHECK_ARG(frame_length >= 2 && hop >= 1 && sr > 0 && fmin > 0 && fmin < fmax, "bad frame geometry / frequency range");
+static int acf_frames(const float* y, int64_t B, int64_t L, int64_t ldy, int frame_length, int hop, int center, float sr, float fmin,
+                      float fmax, float threshold, float* f0, uint8_t* voiced, void* stream, const char* what) {
     int n_fft = 1;
     while (n_fft < 2 * frame_length - 1) n_fft *= 2;
     CHECK_ARG(n_fft >= 64 && n_fft <= 4096, "frame_length must be within 33..2048 (transform sizes 64..4096)");
@@ -478,7 +476,7 @@ int mlxa_pitch_acf_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int fr
     p.y = y; p.ldy = ldy; p.B = (int)B; p.L = (int)L;
     p.T = 1 + (Lp - frame_length) / hop;
     p.frame_length = frame_length; p.hop = hop; p.pad = pad;
-    p.min_lag = (int)(sr / fmax); p.max_lag = (int)(sr / fmin);  // int() truncation, as pitch.py:186-187
+    p.min_lag = (int)(sr / fmax); p.max_lag = (int)(sr / fmin);  // int() truncation, as pitch.py:186-187 / 318-319
     CHECK_ARG(p.max_lag + 1 <= n_fft / 2, "sr / fmin exceeds the lags the transform resolves");
     p.threshold = threshold; p.sr = sr;
     Tables t;
@@ -491,7 +489,27 @@ int mlxa_pitch_acf_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int fr
         X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
 #undef X
     }
-    CHECK_CUDA(e, "pitch_acf");
+    CHECK_CUDA(e, what);
+    return 0;
+}
+int mlxa_pitch_acf_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int frame_length, int hop, int center, float sr,
+                       float fmin, float fmax, float threshold, float* f0, uint8_t* voiced, void* stream) {
+    CHECK_ARG(y && f0 && voiced && B > 0 && L > 0 && ldy >= L && B < (1LL << 31) && L < (1LL << 30), "bad argument");
+    CHECK_ARG(frame_length >= 2 && hop >= 1 && sr > 0 && fmin > 0 && fmin < fmax, "bad frame geometry / frequency range");
+    return acf_frames(y, B, L, ldy, frame_length, hop, center, sr, fmin, fmax, threshold, f0, voiced, stream, "pitch_acf");
+}
+int mlxa_periodicity_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int frame_length, int hop, int center, float sr,
+                         float fmin, float fmax, float* out, void* stream) {
+    CHECK_ARG(y && out && B > 0 && L > 0 && ldy >= L && B < (1LL << 31) && L < (1LL << 30), "bad argument");
+    CHECK_ARG(frame_length >= 2 && hop >= 1 && sr > 0 && fmin > 0 && fmax > 0, "bad frame geometry / frequency range");
+    return acf_frames(y, B, L, ldy, frame_length, hop, center, sr, fmin, fmax, 0.f, out, nullptr, stream, "periodicity");
+}
+int mlxa_deemphasis_f32(const float* y, int64_t B, int64_t n, int64_t ldy, double coef, const float* zi, int librosa_zi, float* out,
+                        int64_t ldo, float* zf, void* stream) {
+    CHECK_ARG(y && out && y != out && B > 0 && B < (1LL << 31) && n > 0 && ldy >= n && ldo >= n, "bad argument");
+    CHECK_ARG(coef >= 0.0 && coef <= 1.0, "coef must be in [0, 1]");
+    CHECK_ARG(!librosa_zi || n >= 2, "the default initial state needs two samples");
+    CHECK_CUDA(run_deemphasis(y, B, n, ldy, coef, zi, librosa_zi, out, ldo, zf, (cudaStream_t)stream), "deemphasis");
     return 0;
 }
 int mlxa_resample_poly_f32(const float* x, int64_t rows, int64_t n_in, const float* h, int len_h, int up, int down,

@@ -427,6 +427,100 @@ __global__ void autocorr_normalize_kernel(float* __restrict__ out, long long B, 
         out[i] = out[i] / fmaxf(__ldg(r0 + i / max_lag), 1e-10f);
 }
 
+// De-emphasis out[n] = y[n] + coef * out[n-1] (framing.py:298-392; scipy.signal.lfilter on the host in the reference): a
+// first-order recurrence, so a scan of affine maps.  One CTA per clip walks the clip in blocks of 1024 x 8 samples: a
+// thread runs its 8 samples from a zero state, the states are combined by a shuffle scan (factor coef^(8 d) at distance d)
+// and the carried state z = coef * out[n-1] enters sample j of a segment as coef^j * z.  float64 inside, rounded once.
+constexpr int kDeSeg = 8, kDeThreads = 1024, kDeBlock = kDeSeg * kDeThreads;
+__global__ void __launch_bounds__(kDeThreads) deemphasis_kernel(const float* __restrict__ y, long long n, long long ldy, double coef,
+                                                                const float* __restrict__ zi, int librosa_zi,
+                                                                float* __restrict__ out, long long ldo, float* __restrict__ zf) {
+    __shared__ float s_v[kDeBlock + kDeBlock / 32];
+    __shared__ double s_w[32];
+    __shared__ double s_carry;
+    const long long b = blockIdx.x;
+    const float* yb = y + b * ldy;
+    float* ob = out + b * ldo;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    double cj[kDeSeg + 1];  // coef^j
+    cj[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j <= kDeSeg; ++j) cj[j] = cj[j - 1] * coef;
+    double cd[5], cw[5];  // coef^(8 d) for d = 1, 2, 4, 8, 16 lanes; coef^(256 d) for d warps
+    cd[0] = cj[kDeSeg];
+#pragma unroll
+    for (int i = 1; i < 5; ++i) cd[i] = cd[i - 1] * cd[i - 1];
+    cw[0] = cd[4] * cd[4];
+#pragma unroll
+    for (int i = 1; i < 5; ++i) cw[i] = cw[i - 1] * cw[i - 1];
+    // the state in front of sample 0: the caller's zi, or -corr for the reference's default (framing.py:368-381), which
+    // subtracts corr * coef^n with corr = ((2 - c) y[0] - y[1]) / (3 - c) evaluated in float32 like NumPy does
+    float corr = 0.f;
+    if (librosa_zi) {
+        corr = __fdiv_rn(__fsub_rn(__fmul_rn(float(2.0 - coef), yb[0]), yb[1]), float(3.0 - coef));
+    }
+    if (t == 0) s_carry = librosa_zi ? -double(corr) : (zi ? double(zi[b]) : 0.0);
+    auto pad = [](int i) { return i + (i >> 5); };
+    for (long long n0 = 0; n0 < n; n0 += kDeBlock) {
+        __syncthreads();
+        for (int i = t; i < kDeBlock; i += kDeThreads) s_v[pad(i)] = (n0 + i < n) ? yb[n0 + i] : 0.f;
+        __syncthreads();
+        double loc[kDeSeg];
+        double z = 0.0;
+#pragma unroll
+        for (int j = 0; j < kDeSeg; ++j) {
+            const double o = double(s_v[pad(t * kDeSeg + j)]) + z;
+            loc[j] = o;
+            z = coef * o;
+        }
+        // inclusive scan of the end states: Z_t = z_t + coef^8 Z_{t-1}
+        double inc = z;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const double up = __shfl_up_sync(0xffffffffu, inc, 1 << i);
+            if (lane >= (1 << i)) inc = fma(cd[i], up, inc);
+        }
+        if (lane == 31) s_w[warp] = inc;
+        const double carry_in = s_carry;
+        __syncthreads();
+        if (warp == 0) {
+            double w = s_w[lane];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const double up = __shfl_up_sync(0xffffffffu, w, 1 << i);
+                if (lane >= (1 << i)) w = fma(cw[i], up, w);
+            }
+            s_w[lane] = w;
+        }
+        __syncthreads();
+        // state in front of this thread's segment: the lane before, the warps before, the blocks before
+        double zin = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) zin = 0.0;
+        double cl = 1.0;  // coef^(8 lane)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) if (lane & (1 << i)) cl *= cd[i];
+        double cwp = 1.0;  // coef^(256 warp)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) if (warp & (1 << i)) cwp *= cw[i];
+        if (warp > 0) zin = fma(cl, s_w[warp - 1], zin);
+        zin = fma(cl * cwp, carry_in, zin);
+#pragma unroll
+        for (int j = 0; j < kDeSeg; ++j) s_v[pad(t * kDeSeg + j)] = float(fma(cj[j], zin, loc[j]));
+        __syncthreads();
+        for (int i = t; i < kDeBlock; i += kDeThreads) if (n0 + i < n) ob[n0 + i] = s_v[pad(i)];
+        if (t == kDeThreads - 1) s_carry = fma(cj[kDeSeg], zin, z);  // state after the block (zero samples past the end carry it on scaled)
+    }
+    __syncthreads();
+    if (t == 0 && zf != nullptr) {
+        // after the last REAL sample: the carried state was advanced over the zero tail of the last block -> undo by
+        // recomputing from the last output instead: z = coef * out[n-1]; the reference's default path reports the state
+        // of the uncorrected filter: add back corr * coef^n
+        double zl = coef * double(ob[n - 1]);
+        if (librosa_zi) zl += double(corr) * pow(coef, double(n));
+        zf[b] = float(zl);
+    }
+}
+
 unsigned grid_for_rows(long long rows, int per_cta) {
     const long long g = (rows + per_cta - 1) / per_cta;
     return (unsigned)(g < 1 ? 1 : (g > 148LL * 32 ? 148LL * 32 : g));
@@ -491,6 +585,11 @@ cudaError_t run_autocorrelation(const float* y, long long B, long long n, long l
         const long long tot = B * max_lag, g = (tot + 255) / 256;
         autocorr_normalize_kernel<<<(unsigned)(g > 148LL * 32 ? 148LL * 32 : g), 256, 0, s>>>(out, B, max_lag, r0);
     }
+    return cudaGetLastError();
+}
+cudaError_t run_deemphasis(const float* y, long long B, long long n, long long ldy, double coef, const float* zi, int librosa_zi,
+                           float* out, long long ldo, float* zf, cudaStream_t s) {
+    deemphasis_kernel<<<(unsigned)B, kDeThreads, 0, s>>>(y, n, ldy, coef, zi, librosa_zi, out, ldo, zf);
     return cudaGetLastError();
 }
 cudaError_t run_frame_stats(const float* y, long long B, int L, long long ldy, int frame_length, int hop, int pad, int pad_mode,

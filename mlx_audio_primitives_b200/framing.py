@@ -72,3 +72,32 @@ def preemphasis(y, coef: float = 0.97, zi=None, return_zf: bool = False, use_mlx
         out = out[0]
         zf = zf[0] if zf is not None else None
     return (out, zf) if return_zf else out
+
+
+def deemphasis(y, coef: float = 0.97, zi=None, return_zf: bool = False):
+    """out[n] = y[n] + coef * out[n-1], the inverse of ``preemphasis``; with zi=None the reference's correction
+    -corr * coef^n, corr = ((2 - coef) y[0] - y[1]) / (3 - coef), undoes preemphasis's default initial state; zf is the
+    final state scipy.signal.lfilter reports (reference framing.py:298-392, lfilter on the host there)."""
+    if not 0.0 <= coef <= 1.0:
+        raise ValueError(f"coef must be in [0, 1], got {coef}")
+    y = f32c(y)
+    one_d = y.ndim == 1
+    if one_d:
+        y = y[None, :]
+    if y.ndim != 2:
+        raise ValueError(f"y must be 1D or 2D, got {y.ndim}D")
+    B, L = y.shape
+    z = None
+    if zi is not None:
+        z = to_tensor(zi, torch.float32, y.device).reshape(-1)
+        z = (z if z.numel() == B else z[:1].expand(B)).contiguous()
+    elif L < 2:
+        raise ValueError("deemphasis with the default initial state needs at least two samples")
+    out = torch.empty_like(y)
+    zf = torch.empty((B, 1), dtype=torch.float32, device=y.device)
+    if B * L:
+        check(_ext.mlxa_deemphasis_f32(ptr(y), B, L, y.stride(0), float(coef), ptr(z), int(zi is None), ptr(out), out.stride(0),
+                                       ptr(zf), stream_ptr(y)), "deemphasis")
+    if one_d:
+        out, zf = out[0], zf[0]
+    return (out, zf) if return_zf else out

@@ -65,3 +65,30 @@ def pitch_detect_acf(y, sr: int = 22050, fmin: float = 50.0, fmax: float = 2000.
                                   float(fmin), float(fmax), float(threshold), ptr(f0), ptr(voiced), stream_ptr(y)), "pitch_acf")
     voiced = voiced.to(torch.bool)
     return (f0[0], voiced[0]) if one_d else (f0, voiced)
+
+
+def periodicity(y, sr: int = 22050, fmin: float = 50.0, fmax: float = 2000.0, frame_length: int = 2048, hop_length: int = 512,
+                center: bool = True) -> torch.Tensor:
+    """Autocorrelation strength per frame: the maximum of r / r[0] over lags [int(sr / fmax), int(sr / fmin)], 0 for silent
+    frames; (1, T) or (B, 1, T) (reference pitch.py:267-383, a per-frame NumPy loop on the host there)."""
+    validate_positive(frame_length, "frame_length")
+    validate_positive(hop_length, "hop_length")
+    if not 33 <= frame_length <= 2048:
+        raise ValueError(f"frame_length must be within 33..2048 on the device path, got {frame_length}")
+    y = f32c(y)
+    one_d = y.ndim == 1
+    if one_d:
+        y = y[None, :]
+    if y.ndim != 2:
+        raise ValueError(f"y must be 1D or 2D, got {y.ndim}D")
+    B, L = y.shape
+    Lp = L + (2 * (frame_length // 2) if center else 0)
+    if Lp < frame_length:
+        raise ValueError(f"Signal length ({Lp}) must be >= frame_length ({frame_length}). Consider padding the signal.")
+    if int(sr / fmin) + 1 > frame_length:
+        raise ValueError(f"sr / fmin = {int(sr / fmin)} lags exceed the frame ({frame_length} samples)")
+    T = 1 + (Lp - frame_length) // hop_length
+    out = torch.empty((B, 1, T), dtype=torch.float32, device=y.device)
+    check(_ext.mlxa_periodicity_f32(ptr(y), B, L, y.stride(0), int(frame_length), int(hop_length), int(center), float(sr),
+                                    float(fmin), float(fmax), ptr(out), stream_ptr(y)), "periodicity")
+    return out[0] if one_d else out

@@ -330,3 +330,52 @@ def autocorrelation(y, max_lag=None, normalize=True, center=True, dtype=np.float
         r = r / np.maximum(r[:, :1], 1e-10)
     r = r.astype(np.float32)
     return r[0] if one_d else r
+
+
+def deemphasis(y, coef=0.97, zi=None):
+    """framing.py:298-392: scipy.signal.lfilter([1], [1, -coef]) in float32 along the last axis; zi=None runs from a zero
+    state and subtracts corr * coef^n, corr = ((2 - coef) y[0] - y[1]) / (3 - coef).  Returns (out, zf)."""
+    from scipy import signal
+    y = np.asarray(y, dtype=np.float32)
+    one_d = y.ndim == 1
+    if one_d:
+        y = y[None]
+    B, L = y.shape
+    b = np.array([1.0], dtype=np.float32)
+    a = np.array([1.0, -coef], dtype=np.float32)
+    if zi is not None:
+        z = np.asarray(zi, dtype=np.float32).reshape(-1)
+        z = (z if z.size == B else np.broadcast_to(z[:1], (B,))).reshape(B, 1)
+        out, zf = signal.lfilter(b, a, y, zi=z, axis=-1)
+    else:
+        out, zf = signal.lfilter(b, a, y, zi=np.zeros((B, 1), dtype=np.float32), axis=-1)
+        corr = ((2 - coef) * y[:, 0:1] - y[:, 1:2]) / (3 - coef)
+        out = out - corr * (coef ** np.arange(L, dtype=np.float32))
+    out, zf = out.astype(np.float32), zf.astype(np.float32)
+    return (out[0], zf[0]) if one_d else (out, zf)
+
+
+def periodicity(y, sr=22050, fmin=50.0, fmax=2000.0, frame_length=2048, hop_length=512, center=True):
+    """pitch.py:267-383: per frame, max over lags [int(sr/fmax), int(sr/fmin)] of the normalised autocorrelation of the
+    mean-removed frame (one zero-padded FFT), 0 where r[0] <= 1e-10."""
+    y = np.asarray(y, dtype=np.float32)
+    one_d = y.ndim == 1
+    if one_d:
+        y = y[None]
+    lo, hi = int(sr / fmax), int(sr / fmin)
+    if center:
+        y = np.pad(y, [(0, 0), (frame_length // 2, frame_length // 2)])
+    T = 1 + (y.shape[1] - frame_length) // hop_length
+    n_fft = 2 ** int(np.ceil(np.log2(2 * frame_length - 1)))
+    out = np.zeros((y.shape[0], 1, T), dtype=np.float32)
+    for b in range(y.shape[0]):
+        for t in range(T):
+            fr = y[b, t * hop_length: t * hop_length + frame_length]
+            fr = fr - np.mean(fr)
+            Y = np.fft.rfft(fr, n=n_fft)
+            r = np.fft.irfft(Y * np.conj(Y), n=n_fft)
+            if r[0] > 1e-10:
+                rng = (r / r[0])[lo: hi + 1]
+                if len(rng):
+                    out[b, 0, t] = np.max(rng)
+    return out[0] if one_d else out

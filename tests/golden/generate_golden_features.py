@@ -54,6 +54,12 @@ f0, vo = ref.pitch_detect_acf(mx.array(yp[0]), sr=22050, fmin=80.0, fmax=800.0, 
 out["pitch/f0_b"], out["pitch/voiced_b"] = A(f0), A(vo)
 out["acf/default"] = A(ref.autocorrelation(mx.array(yp), max_lag=600))
 out["acf/raw_1d"] = A(ref.autocorrelation(mx.array(yp[0, :3000]), normalize=False, center=False))
+out["per/default"] = A(ref.periodicity(mx.array(yp), sr=22050))
+out["per/b"] = A(ref.periodicity(mx.array(yp[0]), sr=22050, fmin=80.0, fmax=800.0, frame_length=1024, hop_length=256, center=False))
+_de = ref.deemphasis(mx.array(y2), coef=0.97, return_zf=True)
+out["de/default"], out["de/default_zf"] = A(_de[0]), A(_de[1])
+_de = ref.deemphasis(mx.array(y2[0]), coef=0.9, zi=mx.array([0.25]), return_zf=True)
+out["de/zi"], out["de/zi_zf"] = A(_de[0]), A(_de[1])
 out["rs/poly_1_2"] = A(ref.resample_poly(mx.array(y2), 1, 2))
 out["rs/poly_3_2"] = A(ref.resample_poly(mx.array(y2[0]), 3, 2))
 out["rs/poly_160_147"] = A(ref.resample_poly(mx.array(y2[:, :2000]), 160, 147))

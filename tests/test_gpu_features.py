@@ -269,3 +269,59 @@ def test_autocorrelation_matches_reference_and_oracle():
     # a strided view is a legal input; bits equal the contiguous call
     big = torch.from_numpy(rng.standard_normal((4, 9000)).astype(np.float32)).cuda()
     assert torch.equal(mb.autocorrelation(big[:, :8000], max_lag=300), mb.autocorrelation(big[:, :8000].contiguous(), max_lag=300))
+
+
+def test_periodicity_matches_reference_and_oracle():
+    import mlx_audio_primitives_b200 as mb
+    g = np.load(os.path.join(GOLDEN, "reference_features.npz"))
+    yp = g["pitch/input"]
+    got = mb.periodicity(torch.from_numpy(yp).cuda(), sr=22050).cpu().numpy()
+    assert got.shape == g["per/default"].shape and np.abs(got - g["per/default"]).max() < 2e-5
+    got = mb.periodicity(torch.from_numpy(yp[0]).cuda(), sr=22050, fmin=80.0, fmax=800.0, frame_length=1024, hop_length=256,
+                         center=False).cpu().numpy()
+    assert got.shape == g["per/b"].shape and np.abs(got - g["per/b"]).max() < 2e-5
+    rng = np.random.default_rng(9)
+    y = rng.standard_normal((3, 20000)).astype(np.float32)
+    y[1, 4000:12000] = 0.0                                     # silent frames -> exactly 0
+    y[2] = np.sin(2 * np.pi * 220.0 * np.arange(20000) / 16000.0).astype(np.float32)
+    for fl, hop, center in ((512, 128, True), (2048, 512, True), (400, 160, False)):
+        want = of.periodicity(y, sr=16000, fmin=60.0, fmax=1000.0, frame_length=fl, hop_length=hop, center=center)
+        got = mb.periodicity(torch.from_numpy(y).cuda(), sr=16000, fmin=60.0, fmax=1000.0, frame_length=fl, hop_length=hop,
+                             center=center).cpu().numpy()
+        assert got.shape == want.shape and np.abs(got - want).max() < 5e-5, (fl, hop, center)
+        assert np.array_equal(got == 0, want == 0)
+    # an empty lag range is all zeros, as in the reference
+    assert not mb.periodicity(torch.from_numpy(y).cuda(), sr=16000, fmin=900.0, fmax=100.0, frame_length=512).any()
+    with pytest.raises(ValueError):
+        mb.periodicity(torch.from_numpy(y).cuda(), frame_length=4096)
+
+
+def test_deemphasis_matches_reference_and_inverts_preemphasis():
+    import mlx_audio_primitives_b200 as mb
+    g = np.load(os.path.join(GOLDEN, "reference_features.npz"))
+    y2 = np.load(os.path.join(GOLDEN, "reference_outputs.npz"))["stft/input"]
+    out, zf = mb.deemphasis(torch.from_numpy(y2).cuda(), coef=0.97, return_zf=True)
+    scale = np.abs(g["de/default"]).max()
+    assert np.abs(out.cpu().numpy() - g["de/default"]).max() < 2e-6 * scale
+    assert zf.shape == g["de/default_zf"].shape and np.abs(zf.cpu().numpy() - g["de/default_zf"]).max() < 2e-6 * scale
+    out, zf = mb.deemphasis(torch.from_numpy(y2[0]).cuda(), coef=0.9, zi=[0.25], return_zf=True)
+    assert out.shape == g["de/zi"].shape and np.abs(out.cpu().numpy() - g["de/zi"]).max() < 2e-6 * np.abs(g["de/zi"]).max()
+    assert zf.shape == g["de/zi_zf"].shape and np.abs(zf.cpu().numpy() - g["de/zi_zf"]).max() < 2e-6 * np.abs(g["de/zi"]).max()
+    rng = np.random.default_rng(10)
+    for B, L, coef in ((1, 2, 0.97), (3, 8191, 0.5), (2, 8192, 0.0), (2, 8193, 1.0), (4, 100001, 0.97), (1, 480000, 0.95)):
+        y = rng.standard_normal((B, L)).astype(np.float32)
+        for zi in (None, rng.standard_normal(B).astype(np.float32)):
+            want, want_zf = of.deemphasis(y, coef, zi=zi)
+            got, got_zf = mb.deemphasis(torch.from_numpy(y).cuda(), coef=coef, zi=zi, return_zf=True)
+            # float32 lfilter accumulates rounding along the recurrence (gain 1 / (1 - coef); a running sum at coef = 1)
+            tol = 3e-7 * np.abs(want).max() * (np.sqrt(L) if coef == 1.0 else 1.0 / (1.0 - coef))
+            assert np.abs(got.cpu().numpy() - want).max() <= tol, (B, L, coef, zi is None)
+            assert np.abs(got_zf.cpu().numpy() - want_zf).max() <= tol, (B, L, coef)
+    # round trip with preemphasis (the pair is exact in real arithmetic)
+    y = torch.from_numpy(rng.standard_normal((2, 50000)).astype(np.float32)).cuda()
+    back = mb.deemphasis(mb.preemphasis(y, 0.97), 0.97)
+    assert (back - y).abs().max().item() < 2e-5
+    with pytest.raises(ValueError):
+        mb.deemphasis(y, coef=1.5)
+    with pytest.raises(ValueError):
+        mb.deemphasis(y[:, :1])

@@ -251,6 +251,13 @@ def test_feature_oracle_matches_reference_code():
     assert np.abs(of.autocorrelation(g["pitch/input"], max_lag=600) - g["acf/default"]).max() < 1e-6
     raw = of.autocorrelation(g["pitch/input"][0, :3000], normalize=False, center=False)
     assert np.abs(raw - g["acf/raw_1d"]).max() < 1e-6 * np.abs(raw).max()
+    assert np.array_equal(of.periodicity(g["pitch/input"]), g["per/default"])
+    assert np.array_equal(of.periodicity(g["pitch/input"][0], fmin=80.0, fmax=800.0, frame_length=1024, hop_length=256, center=False),
+                          g["per/b"])
+    out, zf = of.deemphasis(y2, 0.97)
+    assert np.array_equal(out, g["de/default"]) and np.array_equal(zf, g["de/default_zf"])
+    out, zf = of.deemphasis(y2[0], 0.9, zi=[0.25])
+    assert np.array_equal(out, g["de/zi"]) and np.array_equal(zf, g["de/zi_zf"])
     assert np.array_equal(of.resample_poly(y2, 1, 2), g["rs/poly_1_2"]) and np.array_equal(of.resample_poly(y2[0], 3, 2), g["rs/poly_3_2"])
     assert np.array_equal(of.resample_poly(y2[:, :2000], 160, 147), g["rs/poly_160_147"])
     assert np.array_equal(of.resample_linear(y2, 22050, 16000), g["rs/lin_down"])
