@@ -260,6 +260,14 @@ int mlxa_spectral_feature_f32(const float* y, int64_t B, int64_t L, int64_t ldy,
  * voiced (B, T) uint8, T = 1 + (L + 2*(frame_length/2 if center) - frame_length) / hop. */
 int mlxa_pitch_acf_f32(const float* y, int64_t B, int64_t L, int64_t ldy, int frame_length, int hop, int center,
                        float sr, float fmin, float fmax, float threshold, float* f0, uint8_t* voiced, void* stream);
+/* Fourier-method resampling of whole signals to `num` samples (resample.py:84-139 -> scipy.signal.resample on the host
+ * in the reference): rfft, keep / zero-extend the spectrum (unpaired Nyquist bin doubled when shrinking, halved when
+ * growing), irfft, times num / n and `gain`.  Arbitrary lengths up to 2^24: both DFTs are Bluestein chirp transforms over
+ * power-of-two Stockham FFTs in global memory.  work: device scratch of mlxa_resample_fft_work_bytes(B, n, num) bytes.
+ * Chirps and their transforms are cached per length on the device (first call of a length builds them). */
+int64_t mlxa_resample_fft_work_bytes(int64_t B, int64_t n, int64_t num);
+int mlxa_resample_fft_f32(const float* x, int64_t B, int64_t n, int64_t ldx, int64_t num, float gain, float* out, int64_t ldo,
+                          void* work, int64_t work_bytes, void* stream);
 /* Rational resampling along the last axis (resample.py:215-300, scipy.signal.resample_poly on the host in the
  * reference): out[r, j] = sum_i x[r, i] * h[(j + pre_remove)*down - i*up].  h (len_h, DEVICE) is the zero-padded Kaiser
  * low-pass already multiplied by `up`, pre_remove / n_out as scipy derives them -- all computed on the host

@@ -45,7 +45,8 @@ def _newest_header() -> float:
 
 
 def _units():
-    units = [("api.o", "api.cu", []), ("util_kernels.o", "util_kernels.cu", []), ("feat_kernels.o", "feat_kernels.cu", [])]
+    units = [("api.o", "api.cu", []), ("util_kernels.o", "util_kernels.cu", []), ("feat_kernels.o", "feat_kernels.cu", []),
+             ("bigfft.o", "bigfft.cu", [])]
     for nf in PLANNED_NFFT:
         units.append((f"fwd_{nf}.o", "fwd_inst.cu", [f"-DMLXA_NFFT={nf}"]))
         units.append((f"inv_{nf}.o", "inv_inst.cu", [f"-DMLXA_NFFT={nf}"]))

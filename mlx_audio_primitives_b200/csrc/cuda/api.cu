@@ -512,6 +512,18 @@ int mlxa_deemphasis_f32(const float* y, int64_t B, int64_t n, int64_t ldy, doubl
     CHECK_CUDA(run_deemphasis(y, B, n, ldy, coef, zi, librosa_zi, out, ldo, zf, (cudaStream_t)stream), "deemphasis");
     return 0;
 }
+int64_t mlxa_resample_fft_work_bytes(int64_t B, int64_t n, int64_t num) {
+    if (B <= 0 || n <= 0 || num <= 0 || n > (1LL << 24) || num > (1LL << 24)) return -1;
+    return resample_fft_work_bytes(B, n, num);
+}
+int mlxa_resample_fft_f32(const float* x, int64_t B, int64_t n, int64_t ldx, int64_t num, float gain, float* out, int64_t ldo,
+                          void* work, int64_t work_bytes, void* stream) {
+    CHECK_ARG(x && out && work && B > 0 && B <= 65535 && n > 0 && num > 0 && ldx >= n && ldo >= num, "bad argument");
+    CHECK_ARG(n <= (1LL << 24) && num <= (1LL << 24), "signals of up to 2^24 samples are served");
+    CHECK_ARG(work_bytes >= resample_fft_work_bytes(B, n, num), "workspace too small (mlxa_resample_fft_work_bytes)");
+    CHECK_CUDA(run_resample_fft(x, B, n, ldx, num, gain, out, ldo, work, (cudaStream_t)stream), "resample_fft");
+    return 0;
+}
 int mlxa_resample_poly_f32(const float* x, int64_t rows, int64_t n_in, const float* h, int len_h, int up, int down,
                            int64_t pre_remove, int64_t n_out, float* out, void* stream) {
     CHECK_ARG(x && h && out && rows > 0 && n_in > 0 && n_out > 0 && len_h > 0 && up > 0 && down > 0 && pre_remove >= 0, "bad argument");

@@ -43,6 +43,9 @@ cudaError_t run_resample_linear(const float* x, long long rows, long long n_in, 
                                 int apply_gain, float* out, cudaStream_t s);
 cudaError_t run_autocorrelation(const float* y, long long B, long long n, long long ldy, int max_lag, int normalize, int center,
                                 float* out, float* scratch, cudaStream_t s);
+long long resample_fft_work_bytes(long long B, long long n, long long num);
+cudaError_t run_resample_fft(const float* x, long long B, long long n, long long ldx, long long num, float gain, float* out,
+                             long long ldo, void* work, cudaStream_t s);
 cudaError_t run_deemphasis(const float* y, long long B, long long n, long long ldy, double coef, const float* zi, int librosa_zi,
                            float* out, long long ldo, float* zf, cudaStream_t s);
 cudaError_t run_frame_stats(const float* y, long long B, int L, long long ldy, int frame_length, int hop, int pad, int pad_mode,

@@ -42,6 +42,9 @@ def poly_filter_host(up: int, down: int, n_in: int):
     return taps, int(n_pre_remove), int(n_out)
 
 
+_FFT_WORK_BYTES = 2 << 30  # scratch for the global-memory transforms of resample(res_type="fft"); clips go in slabs
+
+
 def resample_poly(y, up: int, down: int, axis: int = -1, padtype: str = "constant") -> torch.Tensor:
     """Polyphase resampling by the rational factor up/down (reference resample.py:215-300)."""
     validate_positive(up, "up")
@@ -67,16 +70,14 @@ def resample_poly(y, up: int, down: int, axis: int = -1, padtype: str = "constan
 
 def resample(y, orig_sr: int, target_sr: int, res_type: str = "fft", fix: bool = True, scale: bool = False,
              axis: int = -1) -> torch.Tensor:
-    """Resample to another rate (reference resample.py:21-212).  ``res_type="linear"`` runs on the device;
-    ``"fft"`` is not built (see the module docstring) -- use ``resample_poly`` for band-limited resampling."""
+    """Resample to another rate (reference resample.py:21-212).  ``res_type="fft"`` is the Fourier method of
+    scipy.signal.resample (two chirp-z transforms over global-memory FFTs, any length up to 2^24 samples);
+    ``"linear"`` blends neighbouring samples."""
     validate_positive(orig_sr, "orig_sr")
     validate_positive(target_sr, "target_sr")
     if orig_sr == target_sr:
         return to_tensor(y)
-    if res_type == "fft":
-        raise NotImplementedError("res_type='fft' needs one transform over the whole signal and is not built for the "
-                                  "device; use resample_poly(y, up, down) or res_type='linear'")
-    if res_type != "linear":
+    if res_type not in ("fft", "linear"):
         raise ValueError(f"Unknown res_type: '{res_type}'. Supported: 'fft', 'linear'")
     y = to_tensor(y, torch.float32)
     moved = y.movedim(axis, -1).contiguous()
@@ -87,6 +88,20 @@ def resample(y, orig_sr: int, target_sr: int, res_type: str = "fft", fix: bool =
         return y
     rows = moved.numel() // n_in if n_in else 0
     out = torch.empty(moved.shape[:-1] + (n_out,), dtype=torch.float32, device=moved.device)
+    if res_type == "fft":
+        if rows and n_out:
+            if max(n_in, n_out) > (1 << 24):
+                raise ValueError(f"res_type='fft' serves signals of up to 2^24 samples, got {max(n_in, n_out)}")
+            flat_in, flat_out = moved.reshape(rows, n_in), out.view(rows, n_out)
+            per_row = _ext.mlxa_resample_fft_work_bytes(1, n_in, n_out)
+            step = int(max(1, min(rows, 65535, _FFT_WORK_BYTES // per_row)))
+            work = torch.empty(per_row * step, dtype=torch.uint8, device=moved.device)
+            for r0 in range(0, rows, step):
+                nb = min(step, rows - r0)
+                check(_ext.mlxa_resample_fft_f32(ptr(flat_in[r0:]), nb, n_in, n_in, n_out, float(ratio) if scale else 1.0,
+                                                 ptr(flat_out[r0:]), n_out, ptr(work), work.numel(), stream_ptr(moved)),
+                      "resample_fft")
+        return out.movedim(-1, axis)
     if rows and n_out:
         check(_ext.mlxa_resample_linear_f32(ptr(moved), rows, n_in, n_out, float(ratio), int(bool(scale)), ptr(out),
                                             stream_ptr(moved)), "resample_linear")

@@ -379,3 +379,24 @@ def periodicity(y, sr=22050, fmin=50.0, fmax=2000.0, frame_length=2048, hop_leng
                 if len(rng):
                     out[b, 0, t] = np.max(rng)
     return out[0] if one_d else out
+
+
+def resample_fft(y, orig_sr, target_sr, fix=True, scale=False, dtype=np.float64):
+    """resample.py:84-139 -> scipy.signal.resample 1.18.1 (real input, no window), restated: X = rfft(x)[:m2] with
+    m = min(num, n), m2 = m // 2 + 1; the unpaired bin m / 2 (m even, num != n) doubled when shrinking, halved when growing;
+    irfft(X * num / n, num); times target_sr / orig_sr when scale."""
+    y = np.asarray(y, dtype=np.float32)
+    n = y.shape[-1]
+    ratio = target_sr / orig_sr
+    num = int(np.round(n * ratio)) if fix else int(np.ceil(n * ratio))
+    if num == n:
+        return y
+    X = np.fft.rfft(y.astype(dtype), axis=-1)
+    m = min(num, n)
+    X = X[..., : m // 2 + 1].copy()
+    if m % 2 == 0:
+        X[..., m // 2] *= 2 if num < n else 0.5
+    out = np.fft.irfft(X * (num / n), n=num, axis=-1)
+    if scale:
+        out = out * ratio
+    return out.astype(np.float32)

@@ -60,6 +60,9 @@ _de = ref.deemphasis(mx.array(y2), coef=0.97, return_zf=True)
 out["de/default"], out["de/default_zf"] = A(_de[0]), A(_de[1])
 _de = ref.deemphasis(mx.array(y2[0]), coef=0.9, zi=mx.array([0.25]), return_zf=True)
 out["de/zi"], out["de/zi_zf"] = A(_de[0]), A(_de[1])
+out["rs/fft_down"] = A(ref.resample(mx.array(y2), 22050, 16000))
+out["rs/fft_up"] = A(ref.resample(mx.array(y2[0, :4001]), 16000, 22050, scale=True))
+out["rs/fft_half"] = A(ref.resample(mx.array(y2[:, :5000]), 44100, 22050, fix=False))
 out["rs/poly_1_2"] = A(ref.resample_poly(mx.array(y2), 1, 2))
 out["rs/poly_3_2"] = A(ref.resample_poly(mx.array(y2[0]), 3, 2))
 out["rs/poly_160_147"] = A(ref.resample_poly(mx.array(y2[:, :2000]), 160, 147))

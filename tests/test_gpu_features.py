@@ -215,8 +215,7 @@ def test_resample(ap):
     for a, b, kw in [(44100, 22050, {}), (16000, 22050, dict(fix=False)), (8000, 8001, dict(scale=True)), (48000, 16000, dict(axis=1))]:
         assert np.array_equal(H(ap.resample(X, a, b, res_type="linear", **kw)), of.resample_linear(X, a, b, **kw))
     assert ap.resample(X, 16000, 16000).shape == X.shape
-    with pytest.raises(NotImplementedError):
-        ap.resample(X, 16000, 8000)
+    assert ap.resample(X, 16000, 8000).shape == (3, 5, 617)     # the default is the Fourier method (tested below)
     with pytest.raises(ValueError, match="Unknown res_type"):
         ap.resample(X, 16000, 8000, res_type="sinc")
     with pytest.raises(ValueError, match="up must be positive"):
@@ -325,3 +324,33 @@ def test_deemphasis_matches_reference_and_inverts_preemphasis():
         mb.deemphasis(y, coef=1.5)
     with pytest.raises(ValueError):
         mb.deemphasis(y[:, :1])
+
+
+def test_resample_fft_matches_reference_and_oracle():
+    import mlx_audio_primitives_b200 as mb
+    g = np.load(os.path.join(GOLDEN, "reference_features.npz"))
+    y2 = np.load(os.path.join(GOLDEN, "reference_outputs.npz"))["stft/input"]
+    for name, args, kw in (("rs/fft_down", (y2, 22050, 16000), {}), ("rs/fft_up", (y2[0, :4001], 16000, 22050), dict(scale=True)),
+                           ("rs/fft_half", (y2[:, :5000], 44100, 22050), dict(fix=False))):
+        got = mb.resample(torch.from_numpy(np.ascontiguousarray(args[0])).cuda(), args[1], args[2], **kw).cpu().numpy()
+        assert got.shape == g[name].shape, name
+        assert np.abs(got - g[name]).max() < 1e-5 * np.abs(g[name]).max(), name
+    rng = np.random.default_rng(21)
+    # odd / even / prime lengths, both directions, lengths that cross the transform sizes, a long clip
+    for B, n, a, b in ((1, 2, 1, 2), (3, 1000, 2, 1), (2, 1001, 3, 2), (2, 4099, 147, 160), (1, 65537, 1, 2), (2, 32768, 3, 1),
+                       (1, 480000, 16000, 22050), (4, 220500, 22050, 16000)):
+        y = rng.standard_normal((B, n)).astype(np.float32)
+        for scale in (False, True):
+            want = of.resample_fft(y, a, b, scale=scale)
+            got = mb.resample(torch.from_numpy(y).cuda(), a, b, scale=scale).cpu().numpy()
+            assert got.shape == want.shape, (B, n, a, b)
+            assert np.abs(got - want).max() < 2e-5 * np.abs(want).max(), (B, n, a, b, np.abs(got - want).max())
+    # same length -> the input itself; other axes; deterministic
+    y = torch.from_numpy(rng.standard_normal((3, 5, 700)).astype(np.float32)).cuda()
+    assert mb.resample(y, 8000, 8000) is y
+    r1 = mb.resample(y, 8000, 12000, axis=-1)
+    assert r1.shape == (3, 5, 1050) and torch.equal(r1, mb.resample(y, 8000, 12000))
+    r2 = mb.resample(y.transpose(1, 2), 8000, 12000, axis=1)
+    assert torch.equal(r2, r1.transpose(1, 2))
+    with pytest.raises(ValueError):
+        mb.resample(y, 8000, 12000, res_type="sinc")

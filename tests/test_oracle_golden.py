@@ -258,6 +258,10 @@ def test_feature_oracle_matches_reference_code():
     assert np.array_equal(out, g["de/default"]) and np.array_equal(zf, g["de/default_zf"])
     out, zf = of.deemphasis(y2[0], 0.9, zi=[0.25])
     assert np.array_equal(out, g["de/zi"]) and np.array_equal(zf, g["de/zi_zf"])
+    for name, args, kw in (("rs/fft_down", (y2, 22050, 16000), {}), ("rs/fft_up", (y2[0, :4001], 16000, 22050), dict(scale=True)),
+                           ("rs/fft_half", (y2[:, :5000], 44100, 22050), dict(fix=False))):
+        got = of.resample_fft(*args, **kw)                      # float64 restatement vs scipy's float32 transforms
+        assert got.shape == g[name].shape and np.abs(got - g[name]).max() < 2e-6 * np.abs(got).max(), name
     assert np.array_equal(of.resample_poly(y2, 1, 2), g["rs/poly_1_2"]) and np.array_equal(of.resample_poly(y2[0], 3, 2), g["rs/poly_3_2"])
     assert np.array_equal(of.resample_poly(y2[:, :2000], 160, 147), g["rs/poly_160_147"])
     assert np.array_equal(of.resample_linear(y2, 22050, 16000), g["rs/lin_down"])
