@@ -55,10 +55,24 @@ __global__ void chirp_wrap_kernel(const float2* __restrict__ w, long long n, lon
 }
 
 // One Stockham pass: thread j of M / R combines in[j + r M/R], r < R, twiddled by W_{Ns R}^{k r} (k = j mod Ns), into
-// out[(j - k) R + k + q Ns], q < R.
-template <int R>
+// out[(j - k) R + k + q Ns], q < R.  Twiddles: three table reads (powers 1, 4, 16 of the step) and at most two products
+// each -- a table read per leg would double the load traffic, powers above 3 of one rounded root would triple its phase
+// error.  MUL fuses the convolution's pointwise product into the transform's last pass: out = conj(out * bhat).
+struct PassIO {
+    const float* x = nullptr;          // IN_REAL: rows of n reals (stride ldx), multiplied by conj(chirp_in), zero up to M
+    long long n = 0, ldx = 0;
+    const float2* chirp_in = nullptr;
+    const float2* bhat = nullptr;      // OUT_MUL
+    float* y = nullptr;                // OUT_REAL: y[j] = Re(chirp_out[j] conj(result[j])) * gain for j < num (stride ldo)
+    long long num = 0, ldo = 0;
+    const float2* chirp_out = nullptr;
+    float gain = 0.f;
+};
+enum { IN_PLAIN = 0, IN_REAL = 1, OUT_PLAIN = 0, OUT_MUL = 1, OUT_REAL = 2 };
+
+template <int R, int IN, int OUT>
 __global__ void __launch_bounds__(256) bigfft_pass_kernel(const float2* __restrict__ in, float2* __restrict__ out, long long M,
-                                                          long long Ns, const float2* __restrict__ W) {
+                                                          long long Ns, const float2* __restrict__ W, const PassIO io) {
     const long long j = blockIdx.x * 256LL + threadIdx.x;
     const long long per = M / R;
     if (j >= per) return;
@@ -67,34 +81,112 @@ __global__ void __launch_bounds__(256) bigfft_pass_kernel(const float2* __restri
     const long long k = j & (Ns - 1);
     const long long tstep = k * (M / (Ns * R));
     float2 v[R];
+    if constexpr (IN == IN_REAL) {  // the chirp-premultiplied, zero-extended real signal: the padding is never read
+        const float* xr = io.x + blockIdx.y * io.ldx;
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = in[j + r * per];
+        for (int r = 0; r < R; ++r) {
+            const long long idx = j + r * per;
+            v[r] = make_float2(0.f, 0.f);
+            if (idx < io.n) {
+                const float xv = xr[idx];
+                const float2 c = __ldg(io.chirp_in + idx);
+                v[r] = make_float2(xv * c.x, -xv * c.y);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = in[j + r * per];
+    }
     if (Ns > 1) {
-#pragma unroll
-        for (int r = 1; r < R; ++r) v[r] = cmul(v[r], __ldg(W + tstep * r));
+        float2 p1[4], p4[4], p16[2];
+        p1[1] = __ldg(W + tstep);
+        p1[2] = cmul(p1[1], p1[1]);
+        p1[3] = cmul(p1[2], p1[1]);
+        if constexpr (R > 4) {
+            p4[1] = __ldg(W + 4 * tstep);
+            p4[2] = cmul(p4[1], p4[1]);
+            p4[3] = cmul(p4[2], p4[1]);
+        }
+        if constexpr (R > 16) p16[1] = __ldg(W + 16 * tstep);
+        static_for<R>([&](auto r_) {
+            constexpr int r = decltype(r_)::value;
+            constexpr int c = r & 3, b = (r >> 2) & 3, a = r >> 4;
+            if constexpr (r > 0) {
+                float2 t;
+                if constexpr (c > 0) {
+                    t = p1[c];
+                    if constexpr (b > 0) t = cmul(t, p4[b]);
+                    if constexpr (a > 0) t = cmul(t, p16[a]);
+                } else if constexpr (b > 0) {
+                    t = p4[b];
+                    if constexpr (a > 0) t = cmul(t, p16[a]);
+                } else {
+                    t = p16[a];
+                }
+                v[r] = cmul(v[r], t);
+            }
+        });
     }
     DftInplace<R, 1, 0>::run(v);
-    float2* o = out + (j - k) * R + k;
+    const long long o0 = (j - k) * R + k;
     static_for<R>([&](auto i_) {
         constexpr int i = decltype(i_)::value;
-        o[dft_perm(R, i) * Ns] = v[i];
+        const long long idx = o0 + dft_perm(R, i) * Ns;
+        float2 r = v[i];
+        if constexpr (OUT == OUT_REAL) {
+            if (idx < io.num) {
+                const float2 w = __ldg(io.chirp_out + idx);
+                io.y[blockIdx.y * io.ldo + idx] = (w.x * r.x + w.y * r.y) * io.gain;
+            }
+        } else {
+            if constexpr (OUT == OUT_MUL) {
+                r = cmul(r, __ldg(io.bhat + idx));
+                r.y = -r.y;
+            }
+            out[idx] = r;
+        }
     });
 }
 
-cudaError_t bigfft(float2* a, float2* tmp, long long M, long long B, const float2* W, cudaStream_t s, float2** result) {
-    // ping-pong a -> tmp -> a ...; *result is the buffer holding the transform
+template <int R>
+void bigfft_launch(dim3 grid, cudaStream_t s, const float2* src, float2* dst, long long M, long long Ns, const float2* W, int in_mode,
+                   int out_mode, const PassIO& io) {
+#define MLXA_PASS(I, O) bigfft_pass_kernel<R, I, O><<<grid, 256, 0, s>>>(src, dst, M, Ns, W, io)
+    if (in_mode == IN_REAL) {
+        if (out_mode == OUT_MUL) MLXA_PASS(IN_REAL, OUT_MUL);
+        else if (out_mode == OUT_REAL) MLXA_PASS(IN_REAL, OUT_REAL);
+        else MLXA_PASS(IN_REAL, OUT_PLAIN);
+    } else {
+        if (out_mode == OUT_MUL) MLXA_PASS(IN_PLAIN, OUT_MUL);
+        else if (out_mode == OUT_REAL) MLXA_PASS(IN_PLAIN, OUT_REAL);
+        else MLXA_PASS(IN_PLAIN, OUT_PLAIN);
+    }
+#undef MLXA_PASS
+}
+
+// FFT_M of B rows, ping-pong a -> tmp -> a ...; *result is the buffer holding the transform.  log2 M splits into
+// ceil(log2 M / 5) passes of near-equal radix (<= 32).  in_mode applies to the first pass (IN_REAL: `a` is not read),
+// out_mode to the last (OUT_MUL stores conj(result * bhat); OUT_REAL stores only the real output rows).
+cudaError_t bigfft(float2* a, float2* tmp, long long M, long long B, const float2* W, int in_mode, int out_mode, const PassIO& io,
+                   cudaStream_t s, float2** result) {
     float2* src = a;
     float2* dst = tmp;
+    int bits = 0;
+    while ((1LL << bits) < M) ++bits;
+    const int passes = bits == 0 ? 1 : (bits + 4) / 5;
     long long Ns = 1;
-    while (Ns < M) {
-        const long long left = M / Ns;
-        const int R = left >= 16 ? 16 : (int)left;
+    for (int p = 0; p < passes; ++p) {
+        const int rb = bits == 0 ? 0 : bits / passes + (p < bits % passes ? 1 : 0);
+        const int R = 1 << rb;
+        const int im = (p == 0) ? in_mode : IN_PLAIN, om = (p == passes - 1) ? out_mode : OUT_PLAIN;
         dim3 grid((unsigned)((M / R + 255) / 256), (unsigned)B);
         switch (R) {
-            case 16: bigfft_pass_kernel<16><<<grid, 256, 0, s>>>(src, dst, M, Ns, W); break;
-            case 8: bigfft_pass_kernel<8><<<grid, 256, 0, s>>>(src, dst, M, Ns, W); break;
-            case 4: bigfft_pass_kernel<4><<<grid, 256, 0, s>>>(src, dst, M, Ns, W); break;
-            default: bigfft_pass_kernel<2><<<grid, 256, 0, s>>>(src, dst, M, Ns, W); break;
+            case 32: bigfft_launch<32>(grid, s, src, dst, M, Ns, W, im, om, io); break;
+            case 16: bigfft_launch<16>(grid, s, src, dst, M, Ns, W, im, om, io); break;
+            case 8: bigfft_launch<8>(grid, s, src, dst, M, Ns, W, im, om, io); break;
+            case 4: bigfft_launch<4>(grid, s, src, dst, M, Ns, W, im, om, io); break;
+            case 2: bigfft_launch<2>(grid, s, src, dst, M, Ns, W, im, om, io); break;
+            default: bigfft_launch<1>(grid, s, src, dst, M, Ns, W, im, om, io); break;
         }
         Ns *= R;
         float2* t = src; src = dst; dst = t;
@@ -103,28 +195,6 @@ cudaError_t bigfft(float2* a, float2* tmp, long long M, long long B, const float
     return cudaGetLastError();
 }
 
-// a[j] = x[j] conj(w_n[j]) (j < n), 0 up to M
-__global__ void rs_chirp_in_kernel(const float* __restrict__ x, long long n, long long ldx, const float2* __restrict__ w,
-                                   long long M, float2* __restrict__ a) {
-    const long long j = blockIdx.x * 256LL + threadIdx.x;
-    if (j >= M) return;
-    const long long b = blockIdx.y;
-    float2 v = make_float2(0.f, 0.f);
-    if (j < n) {
-        const float xv = x[b * ldx + j];
-        const float2 c = __ldg(w + j);
-        v = make_float2(xv * c.x, -xv * c.y);
-    }
-    a[b * M + j] = v;
-}
-// a <- conj(a * bhat): the conjugate turns the following forward transform into the inverse one
-__global__ void rs_pointwise_kernel(float2* __restrict__ a, const float2* __restrict__ bhat, long long M) {
-    const long long j = blockIdx.x * 256LL + threadIdx.x;
-    if (j >= M) return;
-    float2* p = a + blockIdx.y * M + j;
-    const float2 v = cmul(*p, __ldg(bhat + j));
-    *p = make_float2(v.x, -v.y);
-}
 // c holds conj(M1 * convolution); X[k] = conj(w_n[k]) conv[k].  Build the Hermitian spectrum Z of the new length num
 // (scipy.signal.resample: bins below m2 = min(n, num) / 2 + 1 kept, the unpaired bin at m / 2 doubled when shrinking /
 // halved when growing, irfft semantics: imaginary parts of bin 0 and of the Nyquist bin dropped) and write the second
@@ -154,18 +224,6 @@ __global__ void rs_mid_kernel(const float2* __restrict__ c, long long M1, long l
     }
     a2[b * M2 + k] = v;
 }
-// c2 holds conj(M2 * convolution); y[j] = Re(w_num[j] conv[j]) / n (irfft's 1 / num times scipy's num / n), times scale
-__global__ void rs_out_kernel(const float2* __restrict__ c2, long long M2, long long num, const float2* __restrict__ wm, float gain,
-                              float* __restrict__ out, long long ldo) {
-    const long long j = blockIdx.x * 256LL + threadIdx.x;
-    if (j >= num) return;
-    const long long b = blockIdx.y;
-    const float2 cv = c2[b * M2 + j];
-    const float2 w = __ldg(wm + j);
-    // Re(w * conj(cv)) = w.x cv.x + w.y cv.y
-    out[b * ldo + j] = (w.x * cv.x + w.y * cv.y) * gain;
-}
-
 // ---- per-device caches: root tables per M, chirps and chirp transforms per length ---------------------------------------
 struct Key {
     int dev, kind;
@@ -204,7 +262,7 @@ cudaError_t cache_build(int kind, long long n, cudaStream_t s, float2** out) {
     if ((e = cudaMalloc(out, size_t(M) * 8)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&tmp, size_t(M) * 8)) != cudaSuccess) return e;
     chirp_wrap_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(w, n, M, kind == 3, *out);
-    if ((e = bigfft(*out, tmp, M, 1, W, s, &res)) != cudaSuccess) return e;
+    if ((e = bigfft(*out, tmp, M, 1, W, IN_PLAIN, OUT_PLAIN, PassIO{}, s, &res)) != cudaSuccess) return e;
     if (res != *out) e = cudaMemcpyAsync(*out, res, size_t(M) * 8, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     cudaFree(tmp);
@@ -257,21 +315,23 @@ cudaError_t run_resample_fft(const float* x, long long B, long long n, long long
     float2* r = nullptr;
     cudaError_t e;
     const unsigned by = (unsigned)B;
-    rs_chirp_in_kernel<<<dim3((unsigned)((M1 + 255) / 256), by), 256, 0, s>>>(x, n, ldx, wn, M1, a);
-    if ((e = bigfft(a, t, M1, B, W1, s, &r)) != cudaSuccess) return e;
-    float2* o = (r == a) ? t : a;
-    rs_pointwise_kernel<<<dim3((unsigned)((M1 + 255) / 256), by), 256, 0, s>>>(r, bh1, M1);
+    PassIO io;
+    io.x = x; io.n = n; io.ldx = ldx; io.chirp_in = wn; io.bhat = bh1;
+    // conj(FFT(x conj(chirp)) * FFT(chirp)), then the transform back: conj(M1 * convolution)
+    if ((e = bigfft(a, t, M1, B, W1, IN_REAL, OUT_MUL, io, s, &r)) != cudaSuccess) return e;
     float2* r2 = nullptr;
-    if ((e = bigfft(r, o, M1, B, W1, s, &r2)) != cudaSuccess) return e;
+    if ((e = bigfft(r, (r == a) ? t : a, M1, B, W1, IN_PLAIN, OUT_PLAIN, io, s, &r2)) != cudaSuccess) return e;
     float2* o2 = (r2 == a) ? t : a;
     rs_mid_kernel<<<dim3((unsigned)((M2 + 255) / 256), by), 256, 0, s>>>(r2, M1, n, wn, num, wm, M2, o2);
+    PassIO io2;
+    io2.bhat = bh2; io2.y = out; io2.num = num; io2.ldo = ldo; io2.chirp_out = wm;
+    // y[j] = Re(w_num[j] conv[j]) / n (irfft's 1 / num times scipy's num / n) times the caller's gain; the last transform
+    // holds conj(M2 conv)
+    io2.gain = gain / (float(M2) * float(n));
     float2* r3 = nullptr;
-    if ((e = bigfft(o2, r2, M2, B, W2, s, &r3)) != cudaSuccess) return e;
-    float2* o3 = (r3 == a) ? t : a;
-    rs_pointwise_kernel<<<dim3((unsigned)((M2 + 255) / 256), by), 256, 0, s>>>(r3, bh2, M2);
+    if ((e = bigfft(o2, r2, M2, B, W2, IN_PLAIN, OUT_MUL, io2, s, &r3)) != cudaSuccess) return e;
     float2* r4 = nullptr;
-    if ((e = bigfft(r3, o3, M2, B, W2, s, &r4)) != cudaSuccess) return e;
-    rs_out_kernel<<<dim3((unsigned)((num + 255) / 256), by), 256, 0, s>>>(r4, M2, num, wm, gain / (float(M2) * float(n)), out, ldo);
+    if ((e = bigfft(r3, (r3 == a) ? t : a, M2, B, W2, IN_PLAIN, OUT_REAL, io2, s, &r4)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

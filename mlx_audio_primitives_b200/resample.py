@@ -3,8 +3,9 @@
 ``resample_poly`` (scipy.signal.resample_poly on the host in the reference) and ``resample(res_type="linear")`` run
 on the device: the Kaiser low-pass of the polyphase resampler is designed on the host exactly as SciPy does
 (firwin, beta 5, 20*max(up, down) + 1 taps, cast to float32, scaled by ``up``) and applied by one kernel.
-``resample(res_type="fft")`` (scipy.signal.resample: ONE transform over the whole signal) is not built -- it is
-not a shared-memory FFT; it raises NotImplementedError instead of bouncing to the CPU."""
+``resample(res_type="fft")`` (scipy.signal.resample: rfft of the whole signal, spectrum kept / zero-extended, irfft) is
+two Bluestein chirp transforms over power-of-two Stockham FFTs in global memory (``bigfft.cu``): any length up to 2^24
+samples, chirps and their transforms cached per length on the device."""
 from __future__ import annotations
 
 import math
