@@ -294,6 +294,12 @@ int mlxa_deemphasis_f32(const float* y, int64_t B, int64_t n, int64_t ldy, doubl
  * out (B, max_lag); scratch: 2*B device floats. */
 int mlxa_autocorrelation_f32(const float* y, int64_t B, int64_t n, int64_t ldy, int max_lag, int normalize, int center,
                              float* out, float* scratch, void* stream);
+/* The same result through two global-memory transforms, r = FFT_M(|FFT_M(y - mean)|^2) / M with M the power of two
+ * >= 2n - 1 (what pitch.py:16-116 does in one FFT call): O(M log M), the choice for more than ~1000 lags.  float32
+ * transforms (error ~1e-6 of r[0]).  work: device scratch of mlxa_autocorrelation_fft_work_bytes(B, n) bytes. */
+int64_t mlxa_autocorrelation_fft_work_bytes(int64_t B, int64_t n);
+int mlxa_autocorrelation_fft_f32(const float* y, int64_t B, int64_t n, int64_t ldy, int max_lag, int normalize, int center,
+                                 float* out, float* scratch, void* work, int64_t work_bytes, void* stream);
 /* Savitzky-Golay filter along the last axis: the `delta` features of reference mfcc.py:290-371, which calls
  * scipy.signal.savgol_filter on the host.  x, out (rows, T); taps: `width` correlation taps (out[t] = sum_j taps[j] *
  * x[t - width/2 + j]); mode 0 interp (edge_left / edge_right: (width/2, width) operators applied to the first / last

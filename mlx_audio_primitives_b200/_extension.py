@@ -48,6 +48,8 @@ SIGNATURES = {
     "mlxa_pitch_acf_f32": [_p, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _p, _p, _p],
     "mlxa_resample_poly_f32": [_p, _i64, _i64, _p, _i32, _i32, _i32, _i64, _i64, _p, _p],
     "mlxa_resample_linear_f32": [_p, _i64, _i64, _i64, C.c_double, _i32, _p, _p],
+    "mlxa_autocorrelation_fft_work_bytes": [_i64, _i64],
+    "mlxa_autocorrelation_fft_f32": [_p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i64, _p],
     "mlxa_resample_fft_work_bytes": [_i64, _i64, _i64],
     "mlxa_resample_fft_f32": [_p, _i64, _i64, _i64, _i64, _f32, _p, _i64, _p, _i64, _p],
     "mlxa_periodicity_f32": [_p, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _p, _p],
@@ -87,6 +89,7 @@ def _load() -> C.CDLL:
     lib.mlxa_packed_bank_words.argtypes = [_i32, _i64, _i32]
     lib.mlxa_packed_bank_words.restype = _i64
     lib.mlxa_resample_fft_work_bytes.restype = _i64
+    lib.mlxa_autocorrelation_fft_work_bytes.restype = _i64
     if lib.mlxa_abi_version() != ABI_VERSION:
         raise ImportError(f"ABI mismatch: library {lib.mlxa_abi_version()} != host layer {ABI_VERSION}; rebuild")
     return lib

@@ -543,6 +543,21 @@ int mlxa_autocorrelation_f32(const float* y, int64_t B, int64_t n, int64_t ldy, 
     CHECK_CUDA(run_autocorrelation(y, B, n, ldy, max_lag, normalize, center, out, scratch, (cudaStream_t)stream), "autocorrelation");
     return 0;
 }
+int64_t mlxa_autocorrelation_fft_work_bytes(int64_t B, int64_t n) {
+    if (B <= 0 || n <= 0 || n > (1LL << 23)) return -1;
+    return autocorr_fft_work_bytes(B, n);
+}
+int mlxa_autocorrelation_fft_f32(const float* y, int64_t B, int64_t n, int64_t ldy, int max_lag, int normalize, int center, float* out,
+                                 float* scratch, void* work, int64_t work_bytes, void* stream) {
+    CHECK_ARG(y && out && scratch && work && B > 0 && B <= 65535 && n > 0 && ldy >= n && max_lag > 0 && max_lag <= n, "bad argument");
+    CHECK_ARG(n <= (1LL << 23), "signals of up to 2^23 samples are served");
+    CHECK_ARG(work_bytes >= autocorr_fft_work_bytes(B, n), "workspace too small (mlxa_autocorrelation_fft_work_bytes)");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (center) CHECK_CUDA(run_autocorr_prologue(y, B, n, ldy, scratch, s), "autocorrelation mean");
+    CHECK_CUDA(run_autocorr_fft(y, B, n, ldy, max_lag, center ? scratch : nullptr, out, work, s), "autocorrelation transforms");
+    if (normalize) CHECK_CUDA(run_autocorr_epilogue(out, B, max_lag, scratch + B, s), "autocorrelation normalise");
+    return 0;
+}
 int mlxa_savgol_f32(const float* x, int64_t rows, int64_t T, const float* taps, int width, int mode, float cval,
                     const float* edge_left, const float* edge_right, float* out, void* stream) {
     CHECK_ARG(x && taps && out && rows > 0 && T > 0, "bad argument");

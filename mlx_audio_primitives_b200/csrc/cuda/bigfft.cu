@@ -61,14 +61,15 @@ __global__ void chirp_wrap_kernel(const float2* __restrict__ w, long long n, lon
 struct PassIO {
     const float* x = nullptr;          // IN_REAL: rows of n reals (stride ldx), multiplied by conj(chirp_in), zero up to M
     long long n = 0, ldx = 0;
-    const float2* chirp_in = nullptr;
+    const float2* chirp_in = nullptr;  // (nullptr: the plain signal, minus mean[row] when mean is given)
+    const float* mean = nullptr;
     const float2* bhat = nullptr;      // OUT_MUL
     float* y = nullptr;                // OUT_REAL: y[j] = Re(chirp_out[j] conj(result[j])) * gain for j < num (stride ldo)
     long long num = 0, ldo = 0;
-    const float2* chirp_out = nullptr;
+    const float2* chirp_out = nullptr; // (nullptr: y[j] = Re(result[j]) * gain)
     float gain = 0.f;
 };
-enum { IN_PLAIN = 0, IN_REAL = 1, OUT_PLAIN = 0, OUT_MUL = 1, OUT_REAL = 2 };
+enum { IN_PLAIN = 0, IN_REAL = 1, OUT_PLAIN = 0, OUT_MUL = 1, OUT_REAL = 2, OUT_POWER = 3 };
 
 template <int R, int IN, int OUT>
 __global__ void __launch_bounds__(256) bigfft_pass_kernel(const float2* __restrict__ in, float2* __restrict__ out, long long M,
@@ -88,9 +89,13 @@ __global__ void __launch_bounds__(256) bigfft_pass_kernel(const float2* __restri
             const long long idx = j + r * per;
             v[r] = make_float2(0.f, 0.f);
             if (idx < io.n) {
-                const float xv = xr[idx];
-                const float2 c = __ldg(io.chirp_in + idx);
-                v[r] = make_float2(xv * c.x, -xv * c.y);
+                if (io.chirp_in != nullptr) {
+                    const float xv = xr[idx];
+                    const float2 c = __ldg(io.chirp_in + idx);
+                    v[r] = make_float2(xv * c.x, -xv * c.y);
+                } else {
+                    v[r].x = xr[idx] - (io.mean ? __ldg(io.mean + blockIdx.y) : 0.f);
+                }
             }
         }
     } else {
@@ -135,9 +140,15 @@ __global__ void __launch_bounds__(256) bigfft_pass_kernel(const float2* __restri
         float2 r = v[i];
         if constexpr (OUT == OUT_REAL) {
             if (idx < io.num) {
-                const float2 w = __ldg(io.chirp_out + idx);
-                io.y[blockIdx.y * io.ldo + idx] = (w.x * r.x + w.y * r.y) * io.gain;
+                float val = r.x;
+                if (io.chirp_out != nullptr) {
+                    const float2 w = __ldg(io.chirp_out + idx);
+                    val = w.x * r.x + w.y * r.y;
+                }
+                io.y[blockIdx.y * io.ldo + idx] = val * io.gain;
             }
+        } else if constexpr (OUT == OUT_POWER) {
+            out[idx] = make_float2(r.x * r.x + r.y * r.y, 0.f);
         } else {
             if constexpr (OUT == OUT_MUL) {
                 r = cmul(r, __ldg(io.bhat + idx));
@@ -155,10 +166,12 @@ void bigfft_launch(dim3 grid, cudaStream_t s, const float2* src, float2* dst, lo
     if (in_mode == IN_REAL) {
         if (out_mode == OUT_MUL) MLXA_PASS(IN_REAL, OUT_MUL);
         else if (out_mode == OUT_REAL) MLXA_PASS(IN_REAL, OUT_REAL);
+        else if (out_mode == OUT_POWER) MLXA_PASS(IN_REAL, OUT_POWER);
         else MLXA_PASS(IN_REAL, OUT_PLAIN);
     } else {
         if (out_mode == OUT_MUL) MLXA_PASS(IN_PLAIN, OUT_MUL);
         else if (out_mode == OUT_REAL) MLXA_PASS(IN_PLAIN, OUT_REAL);
+        else if (out_mode == OUT_POWER) MLXA_PASS(IN_PLAIN, OUT_POWER);
         else MLXA_PASS(IN_PLAIN, OUT_PLAIN);
     }
 #undef MLXA_PASS
@@ -333,6 +346,30 @@ cudaError_t run_resample_fft(const float* x, long long B, long long n, long long
     float2* r4 = nullptr;
     if ((e = bigfft(r3, (r3 == a) ? t : a, M2, B, W2, IN_PLAIN, OUT_REAL, io2, s, &r4)) != cudaSuccess) return e;
     return cudaGetLastError();
+}
+
+// Whole-signal autocorrelation through the transforms (pitch.py:16-116 is exactly this): r = FFT_M(|FFT_M(x - mean)|^2) / M
+// (the power spectrum is real and even, so the forward transform is its inverse up to 1 / M), M the power of two >= 2n - 1.
+long long autocorr_fft_work_bytes(long long B, long long n) { return 2 * B * pow2_at_least(2 * n - 1) * 8; }
+
+cudaError_t run_autocorr_fft(const float* y, long long B, long long n, long long ldy, long long max_lag, const float* mean, float* out,
+                             void* work, cudaStream_t s) {
+    const long long M = pow2_at_least(2 * n - 1);
+    float2* W;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        cudaError_t e;
+        if ((e = cache_get(0, M, s, &W)) != cudaSuccess) return e;
+    }
+    float2* a = static_cast<float2*>(work);
+    float2* t = a + B * M;
+    PassIO io;
+    io.x = y; io.n = n; io.ldx = ldy; io.mean = mean;
+    io.y = out; io.num = max_lag; io.ldo = max_lag; io.gain = 1.0f / float(M);
+    float2 *r = nullptr, *r2 = nullptr;
+    cudaError_t e;
+    if ((e = bigfft(a, t, M, B, W, IN_REAL, OUT_POWER, io, s, &r)) != cudaSuccess) return e;
+    return bigfft(r, (r == a) ? t : a, M, B, W, IN_PLAIN, OUT_REAL, io, s, &r2);
 }
 
 }  // namespace mlxa

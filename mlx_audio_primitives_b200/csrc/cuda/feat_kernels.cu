@@ -574,6 +574,20 @@ cudaError_t run_resample_linear(const float* x, long long rows, long long n_in, 
                                                                                                    apply_gain, out);
     return cudaGetLastError();
 }
+__global__ void autocorr_r0_kernel(const float* __restrict__ out, long long B, int max_lag, float* __restrict__ r0) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b < B) r0[b] = out[b * max_lag];
+}
+cudaError_t run_autocorr_prologue(const float* y, long long B, long long n, long long ldy, float* mean, cudaStream_t s) {
+    row_mean_kernel<<<(unsigned)B, 256, 0, s>>>(y, n, ldy, mean);
+    return cudaGetLastError();
+}
+cudaError_t run_autocorr_epilogue(float* out, long long B, int max_lag, float* r0, cudaStream_t s) {
+    autocorr_r0_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(out, B, max_lag, r0);
+    const long long tot = B * max_lag, g = (tot + 255) / 256;
+    autocorr_normalize_kernel<<<(unsigned)(g > 148LL * 32 ? 148LL * 32 : g), 256, 0, s>>>(out, B, max_lag, r0);
+    return cudaGetLastError();
+}
 cudaError_t run_autocorrelation(const float* y, long long B, long long n, long long ldy, int max_lag, int normalize, int center,
                                 float* out, float* scratch, cudaStream_t s) {
     float* mean = scratch;

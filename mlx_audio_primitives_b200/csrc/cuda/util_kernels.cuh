@@ -43,6 +43,11 @@ cudaError_t run_resample_linear(const float* x, long long rows, long long n_in, 
                                 int apply_gain, float* out, cudaStream_t s);
 cudaError_t run_autocorrelation(const float* y, long long B, long long n, long long ldy, int max_lag, int normalize, int center,
                                 float* out, float* scratch, cudaStream_t s);
+long long autocorr_fft_work_bytes(long long B, long long n);
+cudaError_t run_autocorr_fft(const float* y, long long B, long long n, long long ldy, long long max_lag, const float* mean, float* out,
+                             void* work, cudaStream_t s);
+cudaError_t run_autocorr_prologue(const float* y, long long B, long long n, long long ldy, float* mean, cudaStream_t s);
+cudaError_t run_autocorr_epilogue(float* out, long long B, int max_lag, float* r0, cudaStream_t s);
 long long resample_fft_work_bytes(long long B, long long n, long long num);
 cudaError_t run_resample_fft(const float* x, long long B, long long n, long long ldx, long long num, float gain, float* out,
                              long long ldo, void* work, cudaStream_t s);

@@ -14,9 +14,14 @@ from ._tensor import f32c, ptr, stream_ptr
 from ._validation import validate_positive
 
 
+_DIRECT_MAX_LAGS = 1024        # beyond this many lags two global-memory transforms beat the direct sum
+_FFT_WORK_BYTES = 2 << 30
+
+
 def autocorrelation(y, max_lag: int | None = None, normalize: bool = True, center: bool = True) -> torch.Tensor:
     """r[k] = sum_n y[n] y[n + k] for k < max_lag (default: the signal length), mean removed first when ``center``,
-    divided by max(r[0], 1e-10) when ``normalize``; (max_lag,) or (B, max_lag) (reference pitch.py:16-116)."""
+    divided by max(r[0], 1e-10) when ``normalize``; (max_lag,) or (B, max_lag) (reference pitch.py:16-116).
+    Up to 1024 lags: the direct sum (float64 across chunks); more: two power-of-two transforms in global memory."""
     y = f32c(y)
     one_d = y.ndim == 1
     if one_d:
@@ -27,11 +32,22 @@ def autocorrelation(y, max_lag: int | None = None, normalize: bool = True, cente
     lag = n if (max_lag is None or max_lag <= 0) else min(int(max_lag), n)
     out = torch.empty((B, lag), dtype=torch.float32, device=y.device)
     if B and lag:
-        scratch = torch.empty(2 * B, dtype=torch.float32, device=y.device)
-        for b0 in range(0, B, 65535):
-            nb = min(65535, B - b0)
-            check(_ext.mlxa_autocorrelation_f32(ptr(y[b0:]), nb, n, y.stride(0), lag, int(bool(normalize)), int(bool(center)),
-                                                ptr(out[b0:]), ptr(scratch), stream_ptr(y)), "autocorrelation")
+        if lag <= _DIRECT_MAX_LAGS or n > (1 << 23):
+            scratch = torch.empty(2 * B, dtype=torch.float32, device=y.device)
+            for b0 in range(0, B, 65535):
+                nb = min(65535, B - b0)
+                check(_ext.mlxa_autocorrelation_f32(ptr(y[b0:]), nb, n, y.stride(0), lag, int(bool(normalize)), int(bool(center)),
+                                                    ptr(out[b0:]), ptr(scratch), stream_ptr(y)), "autocorrelation")
+        else:
+            per_row = _ext.mlxa_autocorrelation_fft_work_bytes(1, n)
+            step = int(max(1, min(B, 65535, _FFT_WORK_BYTES // per_row)))
+            work = torch.empty(per_row * step, dtype=torch.uint8, device=y.device)
+            scratch = torch.empty(2 * step, dtype=torch.float32, device=y.device)
+            for b0 in range(0, B, step):
+                nb = min(step, B - b0)
+                check(_ext.mlxa_autocorrelation_fft_f32(ptr(y[b0:]), nb, n, y.stride(0), lag, int(bool(normalize)), int(bool(center)),
+                                                        ptr(out[b0:]), ptr(scratch), ptr(work), work.numel(), stream_ptr(y)),
+                      "autocorrelation")
     return out[0] if one_d else out
 
 

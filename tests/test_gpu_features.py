@@ -256,7 +256,8 @@ def test_autocorrelation_matches_reference_and_oracle():
     assert raw.shape == (3000,)
     assert np.abs(raw - g["acf/raw_1d"]).max() < 1e-5 * np.abs(g["acf/raw_1d"]).max()
     rng = np.random.default_rng(5)
-    for B, n, lag in ((1, 1, None), (3, 129, None), (2, 5000, 257), (5, 70001, 1000)):
+    for B, n, lag in ((1, 1, None), (3, 129, None), (2, 5000, 257), (5, 70001, 1000), (2, 5000, None), (3, 70001, 20000),
+                      (2, 300000, 2048)):
         y = (rng.standard_normal((B, n)) + 0.3).astype(np.float32)
         for normalize, center in ((True, True), (False, True), (True, False)):
             if n == 1 and center:
@@ -264,7 +265,9 @@ def test_autocorrelation_matches_reference_and_oracle():
             want = of.autocorrelation(y, max_lag=lag, normalize=normalize, center=center)
             got = mb.autocorrelation(torch.from_numpy(y).cuda(), max_lag=lag, normalize=normalize, center=center).cpu().numpy()
             assert got.shape == want.shape
-            assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max() + 1e-12, (B, n, lag, normalize, center)
+            # up to 1024 lags: the direct sum (float64 across chunks); beyond: two float32 transforms
+            tol = 2e-6 if got.shape[1] <= 1024 else 1e-5
+            assert np.abs(got - want).max() <= tol * np.abs(want).max() + 1e-12, (B, n, lag, normalize, center)
     # a strided view is a legal input; bits equal the contiguous call
     big = torch.from_numpy(rng.standard_normal((4, 9000)).astype(np.float32)).cuda()
     assert torch.equal(mb.autocorrelation(big[:, :8000], max_lag=300), mb.autocorrelation(big[:, :8000].contiguous(), max_lag=300))
