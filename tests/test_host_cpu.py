@@ -262,3 +262,28 @@ def test_global_peak_allreduce_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for p, out in zip(procs, outs):
         assert p.returncode == 0, out
+
+
+def test_public_signatures_match_the_reference():
+    """Every function the reference exports exists here with the same argument names, order and defaults
+    (tests/golden/reference_signatures.json, parsed from the reference's sources by generate_reference_signatures.py)."""
+    import ast
+    import glob
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    want = json.load(open(os.path.join(root, "tests", "golden", "reference_signatures.json")))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    from generate_reference_signatures import signatures
+    mine = signatures(glob.glob(os.path.join(root, "mlx_audio_primitives_b200", "*.py")))
+    exported = None
+    for n in ast.walk(ast.parse(open(os.path.join(root, "mlx_audio_primitives_b200", "__init__.py")).read())):
+        if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "__all__":
+            exported = {e.value for e in n.value.elts}
+    assert len(want) >= 37
+    norm = lambda v: None if v is None else v.replace('"', "'")
+    for name, sig in want.items():
+        assert name in exported and name in mine, name
+        got = mine[name]
+        assert [a for a, _ in got["args"]] == [a for a, _ in sig["args"]], name
+        assert [norm(d) for _, d in got["args"]] == [norm(d) for _, d in sig["args"]], name
+        assert [(a, norm(d)) for a, d in got["kwonly"]] == [(a, norm(d)) for a, d in sig["kwonly"]], name
