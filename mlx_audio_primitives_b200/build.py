@@ -49,7 +49,10 @@ def _units():
              ("bigfft.o", "bigfft.cu", [])]
     for nf in PLANNED_NFFT:
         units.append((f"fwd_{nf}.o", "fwd_inst.cu", [f"-DMLXA_NFFT={nf}"]))
-        units.append((f"inv_{nf}.o", "inv_inst.cu", [f"-DMLXA_NFFT={nf}"]))
+        inv_flags = [f"-DMLXA_NFFT={nf}"]
+        if os.environ.get(f"MLXA_INV_THREADS_{nf}"):  # experiments: threads per CTA of the inverse kernel
+            inv_flags.append(f"-DMLXA_INV_THREADS={os.environ[f'MLXA_INV_THREADS_{nf}']}")
+        units.append((f"inv_{nf}.o", "inv_inst.cu", inv_flags))
         if nf != 400:  # packed plans only
             units.append((f"acf_{nf}.o", "acf_inst.cu", [f"-DMLXA_NFFT={nf}"]))
     return units

@@ -5,8 +5,10 @@
 // frame that touches the tile (the r-1 = ceil(n_fft/hop)-1 frames before the tile are
 // recomputed as a halo), adds the windowed frames into a shared-memory accumulator and writes
 // each output sample once, already divided by max(sum w^2, 1e-8) and shifted by the centre
-// trim.  No atomics: within a round, frames whose index differs by a multiple of r cannot
-// overlap, so the adds run in r barrier-separated phases and the summation order is fixed
+// trim.  No atomics: frames whose index differs by a multiple of r cannot overlap.  When a tile
+// of NG*r hops fits (p.spaced), a round transforms NG frames that are r apart -- all groups add
+// at once and a round costs ONE CTA barrier; otherwise a round takes NG consecutive frames and
+// the adds run in r barrier-separated phases.  Either way the summation order is fixed
 // (deterministic results).  The (B, T, n_fft) frame tensor of the reference
 // (stft.py:295 -> overlap_add.metal:16) never exists.
 //
@@ -15,6 +17,8 @@
 // only the projected spectra in HBM.
 #include "fft_plans_list.cuh"
 #include "params.cuh"
+
+#include <cstdlib>
 
 #ifndef MLXA_NFFT
 #error "compile with -DMLXA_NFFT=<n_fft>"
@@ -30,7 +34,12 @@ constexpr bool PACK = (PF::MODE == MODE_PACK);
 constexpr int FPT = PACK ? 1 : 2;
 // warps per CTA: sized so that the exchange buffers of all resident transforms fill the SM's shared memory
 // (n_fft 2048: 16 warps x 8.4 KB; n_fft 4096: 8 warps x 16.6 KB with 64 complex values per lane)
-constexpr int THREADS = (P::E > 32) ? 256 : ((P::G >= 32) ? 512 : 256);
+#ifdef MLXA_INV_THREADS
+constexpr int THREADS = MLXA_INV_THREADS;
+#else
+// n_fft 1024 (16 lanes x 32 values): 12 groups, so that a tile of 12 * r hops (spaced rounds) fits twice per SM
+constexpr int THREADS = (P::E > 32) ? 256 : ((P::G >= 32) ? 512 : ((P::G == 16 && P::E == 32) ? 192 : 256));
+#endif
 constexpr int NG = THREADS / P::G;
 constexpr int NUNPACK = PACK ? P::N + 1 : 0;
 constexpr int TWP = (P::TW + 1) & ~1, TWU = (NUNPACK + 1) & ~1;
@@ -120,13 +129,23 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
             }
         }
     };
+    // frame of (round q, this group, slot `which` of a frame pair)
+    const int n_f = f_hi - f_lo + 1, per_super = NG * FPT * r;
+    const bool spaced = p.spaced != 0;
+    auto frame_of = [&](int q, int which) {
+        if (spaced) return f_lo + (q / r) * per_super + (which * NG + gi) * r + (q % r);
+        return f_lo + q * NG * FPT + gi * FPT + which;
+    };
+    const int n_rounds = n_f <= 0 ? 0 : (spaced ? ((n_f + per_super - 1) / per_super) * r : (n_f + NG * FPT - 1) / (NG * FPT));
+    const int n_phases = spaced ? 1 : r;
     if constexpr (PACK) {
-        if (f_lo + gi * FPT <= f_hi) prefetch_frame(f_lo + gi * FPT);
+        if (n_rounds > 0 && frame_of(0, 0) <= f_hi) prefetch_frame(frame_of(0, 0));
     }
 
-    for (int base = f_lo; base <= f_hi; base += NG * FPT) {
-        const int fa = base + gi * FPT;
+    for (int q = 0; q < n_rounds; ++q) {
+        const int fa = frame_of(q, 0);
         const bool va = fa <= f_hi;
+        [[maybe_unused]] const int f_next = (q + 1 < n_rounds) ? frame_of(q + 1, 0) : f_hi + 1;
         float2 v[P::E];
 
         // ---- spectrum -> packed complex input (swapped: inverse = swap . forward . swap) ---
@@ -170,8 +189,9 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
         } else {
             constexpr int N = P::N;
             constexpr int NQ = ceil_div(N / 2 + 1, P::G);
-            const bool vb = fa + 1 <= f_hi;
-            const long long foa = clip + (long long)(va ? fa : 0) * p.F_in, fob = clip + (long long)(vb ? fa + 1 : 0) * p.F_in;
+            const int fb = frame_of(q, 1);
+            const bool vb = fb <= f_hi;
+            const long long foa = clip + (long long)(va ? fa : 0) * p.F_in, fob = clip + (long long)(vb ? fb : 0) * p.F_in;
             const float2 *Xa = p.spec + foa, *Xb = p.spec + fob;
             const float2 *Xpa = EXTRAP ? p.spec_prev + foa : nullptr, *Xpb = EXTRAP ? p.spec_prev + fob : nullptr;
             static_for<NQ>([&](auto q) {
@@ -195,7 +215,7 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
         pass_load_buf<P, 1>(g, v, buf);
         group_sync<P::G>(gi);
         if constexpr (PACK && P::NPASS == 2) {
-            if (fa + NG * FPT <= f_hi) prefetch_frame(fa + NG * FPT);  // buffer is free: fetch the next round's frame
+            if (f_next <= f_hi) prefetch_frame(f_next);  // buffer is free: fetch the next round's frame
         }
         pass_compute<P, 1>(g, v, tw_plan);
         if constexpr (P::NPASS == 3) {
@@ -204,16 +224,16 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
             pass_load_buf<P, 2>(g, v, buf);
             group_sync<P::G>(gi);
             if constexpr (PACK) {
-                if (fa + NG * FPT <= f_hi) prefetch_frame(fa + NG * FPT);
+                if (f_next <= f_hi) prefetch_frame(f_next);
             }
             pass_compute<P, 2>(g, v, tw_plan);
         }
 
         // ---- windowed overlap-add into the tile accumulator, r conflict-free phases -------
         // lane-private part of each frame: last pass leaves element n = b + k*NS in v[], i.e. samples 2n, 2n+1
-        for (int ph = 0; ph < r; ++ph) {
+        for (int ph = 0; ph < n_phases; ++ph) {
             if constexpr (PACK) {
-                if (va && ((fa - f_lo) % r) == ph) {
+                if (va && (spaced || ((fa - f_lo) % r) == ph)) {
                     const int off = int((long long)fa * p.hop - o0);  // tile-local start of the frame
                     if (off >= 0 && off + NFFT <= TS && hop_even) {  // frame fully inside the tile
                         float2* acc2 = reinterpret_cast<float2*>(s_acc + off);
@@ -236,8 +256,8 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
             } else {
 #pragma unroll
                 for (int which = 0; which < 2; ++which) {
-                    const int f = fa + which;
-                    if (f <= f_hi && ((f - f_lo) % r) == ph) {
+                    const int f = frame_of(q, which);
+                    if (f <= f_hi && (spaced || ((f - f_lo) % r) == ph)) {
                         const int off = int((long long)f * p.hop - o0);
                         const bool inside = off >= 0 && off + NFFT <= TS;
                         pass_store_fn<P, P::NPASS - 1>(g, v, [&](int n, float2 val) {
@@ -295,6 +315,21 @@ cudaError_t MLXA_CAT(launch_inv_, MLXA_NFFT)(InvParams& p, cudaStream_t s) {
     // NG*FPT, so TH is chosen as m*NG*FPT - (r - 1): every round is full (no idle transform slots) and
     // the halo recompute is (r - 1) frames per m rounds.  m grows while two CTAs still fit per SM.
     const int per_round = NG * FPT;
+    p.spaced = 0;
+    // spaced rounds: a tile of m * per_round * r - (r - 1) hops keeps every slot of every round busy; taken when two
+    // such CTAs fit per SM and the clip is long enough to fill the tile
+    {
+        constexpr size_t kHalf = (228 * 1024) / 2 - 1024;
+        const int per_super = per_round * r;
+        auto th_sp = [&](int m) { return m * per_super - (r - 1); };
+        static const bool no_spaced = getenv("MLXA_INV_NO_SPACED") != nullptr;
+        if (!no_spaced && th_sp(1) >= 1 && inv_smem_bytes(p.hop, th_sp(1)) <= kHalf && (long long)th_sp(1) * p.hop <= span) {
+            int m = 1;
+            while (inv_smem_bytes(p.hop, th_sp(m + 1)) <= kHalf && (long long)th_sp(m + 1) * p.hop <= span) ++m;
+            p.spaced = 1;
+            p.tile_hops = th_sp(m);
+        }
+    }
     auto th_for = [&](int m) { return m * per_round - (r - 1); };
     int m = 1;
     while (th_for(m) < 1) ++m;
@@ -310,6 +345,7 @@ cudaError_t MLXA_CAT(launch_inv_, MLXA_NFFT)(InvParams& p, cudaStream_t s) {
     }
     while (TH > 1 && inv_smem_bytes(p.hop, TH) > kMaxSmem) TH = (TH + 1) / 2;  // huge hops: partial rounds
     if (inv_smem_bytes(p.hop, TH) > kMaxSmem) return cudaErrorInvalidConfiguration;
+    if (p.spaced) TH = p.tile_hops;
     p.tile_hops = TH;
     const size_t smem = inv_smem_bytes(p.hop, TH);
     const long long TS = (long long)TH * p.hop;

@@ -82,6 +82,7 @@ struct InvParams {
     int B, T, F_in;
     int n_fft, hop;
     int tile_hops;       // output tile = tile_hops * hop samples
+    int spaced;          // frames of a round are r = ceil(n_fft / hop) apart: they never overlap, one barrier per round
     const float* window; // n_fft
     const float* wss;    // ola_len
     const float2* tw_plan;
