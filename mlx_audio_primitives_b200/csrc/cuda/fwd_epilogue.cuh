@@ -36,12 +36,12 @@ MLXA_D float to_db_one(float x, float coef, float amin, float refc) {
 }
 
 // EP_STFT / EP_GL: one bin straight to global memory
+// (m: the target magnitude of the Griffin-Lim projection, loaded by the caller ahead of the bin loop)
 template <int EP>
-MLXA_D void epilogue_bin_global(const FwdParams& p, long long o, float2 X) {
+MLXA_D void epilogue_bin_global(const FwdParams& p, long long o, float2 X, float m) {
     if constexpr (EP == EP_STFT) {
         p.spec[o] = X;
     } else {
-        const float m = __ldg(p.mag + o);
         const float n2 = fmaf(X.x, X.x, X.y * X.y);
         float2 nw;
         if (n2 > 0.f) {
@@ -52,6 +52,10 @@ MLXA_D void epilogue_bin_global(const FwdParams& p, long long o, float2 X) {
         }
         p.rebuilt[o] = nw;  // the momentum extrapolation is fused into the next inverse transform's loader
     }
+}
+template <int EP>
+MLXA_D void epilogue_bin_global(const FwdParams& p, long long o, float2 X) {
+    epilogue_bin_global<EP>(p, o, X, EP == EP_GL ? __ldg(p.mag + o) : 0.f);
 }
 
 // ---- band-sparse filterbank, packed for a lane group of G (include/mlxa_cuda.h) ---------------

@@ -227,6 +227,12 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             const bool va = f0 < nt;  // frames beyond the tile: finite dummy input, results unused
             float2 v[P::E];
             [[maybe_unused]] bool pair_zero_a = false, pair_zero_b = false;
+            if constexpr (EP == EP_GL) {  // the projection's target magnitudes: pull the frame's row(s) towards the SM now
+                if (va) {
+                    const char* mp = reinterpret_cast<const char*>(p.mag + ((long long)b * p.T + t0 + f0) * p.F);
+                    for (int off = g * 128; off < FPT * p.F * 4 + 128; off += P::G * 128) prefetch_l2(mp + off);
+                }
+            }
 
             // ---- pass 0: windowed samples straight from the staged tile --------------------
             if constexpr (PACK) {
@@ -429,10 +435,18 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             } else if (va) {
                 const long long obase = ((long long)b * p.T + t0 + f0) * p.F;
                 if constexpr (PACK) {
+                    [[maybe_unused]] float mg[EP == EP_GL ? NQ : 1];
+                    if constexpr (EP == EP_GL) {  // all target magnitudes of the lane in flight before the first bin needs one
+                        static_for<NQ>([&](auto q) {
+                            constexpr int Q = decltype(q)::value;
+                            const int k = g + Q * P::G;
+                            mg[Q] = (Q + 1 < NQ || k < NBINS) ? __ldg(p.mag + obase + k) : 0.f;
+                        });
+                    }
                     static_for<NQ>([&](auto q) {
                         constexpr int Q = decltype(q)::value;
                         const int k = g + Q * P::G;
-                        if (Q + 1 < NQ || k < NBINS) epilogue_bin_global<EP>(p, obase + k, bin(q, k));
+                        if (Q + 1 < NQ || k < NBINS) epilogue_bin_global<EP>(p, obase + k, bin(q, k), EP == EP_GL ? mg[Q] : 0.f);
                     });
                 } else {
                     constexpr int N = P::N;  // n_fft
