@@ -36,30 +36,46 @@ def fft_flops(N):
 
 
 def clips(B, L, sr, seed=0):
-    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    g = torch.Generator(device="cuda"); g.manual_seed(seed + 1000 * RANK)
     t = torch.arange(L, device="cuda", dtype=torch.float64) / sr
     base = torch.sin(2 * np.pi * (100 + 1000 * t) * t).to(torch.float32)
     return base[None] + 0.1 * torch.randn((B, L), generator=g, device="cuda")
 
 
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+
+
 def timed(fn, iters, warm=3):
+    """ms per call on the device; under torchrun: barrier on both sides, max over ranks."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if WORLD > 1:
+        torch.distributed.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    ms = e0.elapsed_time(e1) / iters
+    if WORLD > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
 
 def report(name, label, audio_s, ms, bytes_, flops, extra=None):
-    t_roof = max(bytes_ / (HBM_GBS * 1e9), flops / (FP32_TFLOPS * 1e12)) * 1e3
+    # under torchrun every rank holds the same share (weak scaling): whole-job units over the slowest rank's time
+    audio_s, bytes_, flops = audio_s * WORLD, bytes_ * WORLD, flops * WORLD
+    if RANK != 0:
+        return
+    t_roof = max(bytes_ / (HBM_GBS * 1e9), flops / (FP32_TFLOPS * 1e12)) * 1e3 / WORLD
     line = {"config": name, "workload": label, "ms": ms, "audio_s_per_s": audio_s / (ms * 1e-3),
             "alg_bytes": bytes_, "alg_flops": flops, "t_roof_ms": t_roof, "frac_of_roofline": t_roof / ms,
-            "bound": "hbm" if bytes_ / (HBM_GBS * 1e9) >= flops / (FP32_TFLOPS * 1e12) else "fp32",
+            "n_gpus": WORLD, "bound": "hbm" if bytes_ / (HBM_GBS * 1e9) >= flops / (FP32_TFLOPS * 1e12) else "fp32",
             "achieved_GBs": bytes_ / (ms * 1e-3) / 1e9, "achieved_TFLOPs": flops / (ms * 1e-3) / 1e12}
     if extra:
         line.update(extra)
@@ -72,6 +88,10 @@ def main():
     a.add_argument("--iters", type=int, default=20)
     a.add_argument("--clips-scale", type=float, default=1.0, help="scale the batch (e.g. 0.125 = one of 8 GPUs' share)")
     args = a.parse_args()
+    if WORLD > 1:  # torchrun: one rank per GPU, clips sharded, the dB peak exchanged
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+        ap.distributed.enable()
     want = args.configs.split(",")
     sc = args.clips_scale
 
@@ -163,3 +183,5 @@ def main():
 
 if __name__ == "__main__":
     main()
+    if WORLD > 1:
+        torch.distributed.destroy_process_group()
