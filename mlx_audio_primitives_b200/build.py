@@ -48,7 +48,10 @@ def _units():
     units = [("api.o", "api.cu", []), ("util_kernels.o", "util_kernels.cu", []), ("feat_kernels.o", "feat_kernels.cu", []),
              ("bigfft.o", "bigfft.cu", [])]
     for nf in PLANNED_NFFT:
-        units.append((f"fwd_{nf}.o", "fwd_inst.cu", [f"-DMLXA_NFFT={nf}"]))
+        fwd_flags = [f"-DMLXA_NFFT={nf}"]
+        if os.environ.get("MLXA_TWIDDLE_POWERS"):  # experiment: rebuild pass twiddles from three table entries
+            fwd_flags.append("-DMLXA_TWIDDLE_POWERS")
+        units.append((f"fwd_{nf}.o", "fwd_inst.cu", fwd_flags))
         inv_flags = [f"-DMLXA_NFFT={nf}"]
         if os.environ.get(f"MLXA_INV_THREADS_{nf}"):  # experiments: threads per CTA of the inverse kernel
             inv_flags.append(f"-DMLXA_INV_THREADS={os.environ[f'MLXA_INV_THREADS_{nf}']}")

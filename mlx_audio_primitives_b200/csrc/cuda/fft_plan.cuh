@@ -76,6 +76,36 @@ MLXA_HD void pass_compute(int g, float2* v, const float2* __restrict__ tw) {
         if ((NB % P::G == 0) || b < NB) {
             if constexpr (PASS > 0) {
                 const float2* t = tw + P::tw_off(PASS) + (b % NS);
+#ifdef MLXA_TWIDDLE_POWERS
+                if constexpr (R >= 16) {
+                    // legs 1, 4, 16 from the table, the others as products of at most three of their powers (phase error
+                    // <= 3 roundings of a table entry): R - 4 fewer 64-bit shared-memory reads per butterfly
+                    float2 p1[4], p4[4], p16[2];
+                    p1[1] = t[0];
+                    p1[2] = cmul(p1[1], p1[1]);
+                    p1[3] = cmul(p1[2], p1[1]);
+                    p4[1] = t[3 * NS];
+                    p4[2] = cmul(p4[1], p4[1]);
+                    p4[3] = cmul(p4[2], p4[1]);
+                    if constexpr (R > 16) p16[1] = t[15 * NS];
+                    static_for<R - 1>([&](auto r1) {
+                        constexpr int r = decltype(r1)::value + 1;
+                        constexpr int c = r & 3, bb = (r >> 2) & 3, a = r >> 4;
+                        float2 w;
+                        if constexpr (c > 0) {
+                            w = p1[c];
+                            if constexpr (bb > 0) w = cmul(w, p4[bb]);
+                            if constexpr (a > 0) w = cmul(w, p16[a]);
+                        } else if constexpr (bb > 0) {
+                            w = p4[bb];
+                            if constexpr (a > 0) w = cmul(w, p16[a]);
+                        } else {
+                            w = p16[a];
+                        }
+                        v[o + r] = cmul(v[o + r], w);
+                    });
+                } else
+#endif
                 static_for<R - 1>([&](auto r1) {
                     constexpr int r = decltype(r1)::value + 1;
                     v[o + r] = cmul(v[o + r], t[decltype(r1)::value * NS]);
