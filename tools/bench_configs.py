@@ -179,6 +179,30 @@ def main():
         M = torch.randn((B, 40, 2584), device="cuda")
         ms_d = timed(lambda: ap.delta(M), args.iters)
         report("f3b", f"delta width 9 on ({B}, 40, 2584) MFCCs", B * 60.0, ms_d, 2 * M.numel() * 4, 2 * 9 * M.numel())
+    if "f4" in want:  # section 8(f) ranks 3 / 4, second halves: whole-signal transforms and time-domain filters
+        B, L = max(1, int(64 * sc)), 480000
+        y = clips(B, L, 16000)
+        M = lambda n: 1 << max(0, (2 * n - 2)).bit_length()
+        n_out = int(round(L * 22050 / 16000))
+        ms = timed(lambda: ap.resample(y, 16000, 22050), max(2, args.iters // 2))
+        passes = lambda m: (m.bit_length() - 1 + 4) // 5
+        by = B * 8 * 2 * (2 * passes(M(L)) * M(L) + 2 * passes(M(n_out)) * M(n_out))  # pass traffic, not compulsory bytes
+        report("f4a", f"resample fft 16k -> 22.05k {B}x30 s (two chirp-z transforms; bytes = pass traffic)", B * 30.0, ms, by,
+               B * 5 * (2 * M(L) * math.log2(M(L)) + 2 * M(n_out) * math.log2(M(n_out))))
+        ms = timed(lambda: ap.resample_poly(y, 147, 160), max(2, args.iters // 2))
+        n_poly = -(-L * 147 // 160)
+        report("f4b", f"resample_poly 147/160 {B}x30 s", B * 30.0, ms, B * 4 * (L + n_poly), B * n_poly * 2 * (20 * 160 + 1) / 147)
+        yp = ap.preemphasis(y)
+        ms = timed(lambda: ap.deemphasis(yp), args.iters)
+        report("f4c", f"deemphasis {B}x30 s (scan of the recurrence, float64 inside)", B * 30.0, ms, B * 8 * L, B * L * 6)
+        ms = timed(lambda: ap.autocorrelation(y, max_lag=1000), args.iters)
+        report("f4d", f"autocorrelation 1000 lags {B}x30 s (direct)", B * 30.0, ms, B * 4 * (L + 1000), B * 2.0 * L * 1000)
+        ms = timed(lambda: ap.autocorrelation(y), args.iters)
+        report("f4e", f"autocorrelation all lags {B}x30 s (two transforms; bytes = pass traffic)", B * 30.0, ms,
+               B * 8 * 2 * 2 * passes(M(L)) * M(L), B * 5 * 2 * M(L) * math.log2(M(L)))
+        ms = timed(lambda: ap.periodicity(y, sr=16000), args.iters)
+        T = 1 + L // 512
+        report("f4f", f"periodicity 2048/512 {B}x30 s", B * 30.0, ms, B * (4 * L + 4 * T), B * T * (2 * fft_flops(4096) + 3 * 2049 + 2 * 2048))
 
 
 if __name__ == "__main__":
