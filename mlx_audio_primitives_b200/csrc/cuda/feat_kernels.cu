@@ -316,21 +316,31 @@ __global__ void savgol_kernel(const float* __restrict__ x, long long rows, long 
 // Polyphase rational resampling (reference resample.py:215-300 = scipy.signal.resample_poly on the host):
 // out[r, j] = sum_i x[r, i] * h[(j + pre_remove)*down - i*up], h the zero-padded, up-scaled Kaiser low-pass designed on
 // the host; one thread per output sample, the taps it meets are `up` apart.
-__global__ void resample_poly_kernel(const float* __restrict__ x, long long rows, long long n_in, const float* __restrict__ h,
-                                     int len_h, int up, int down, long long pre_remove, long long n_out,
-                                     float* __restrict__ out) {
-    const long long n = rows * n_out;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-        const long long r = idx / n_out, j = idx - r * n_out;
-        const long long m = (j + pre_remove) * down;
-        long long i_hi = m / up;
-        if (i_hi > n_in - 1) i_hi = n_in - 1;
-        const long long lo_num = m - len_h + 1;
-        long long i_lo = lo_num <= 0 ? 0 : (lo_num + up - 1) / up;
+// I: the integer type of the tap index (j + pre_remove) * down -- 32-bit whenever it fits (64-bit divisions cost ~100
+// instructions each); rows ride on grid.y.  (Taps re-laid per phase in shared memory measured slower: 0.37 vs 0.33 ms.)
+template <typename I>
+__global__ void __launch_bounds__(256) resample_poly_kernel(const float* __restrict__ x, long long rows, long long n_in,
+                                                            const float* __restrict__ h, int len_h, int up, int down,
+                                                            long long pre_remove, long long n_out, float* __restrict__ out) {
+    for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
         const float* xr = x + r * n_in;
-        float acc = 0.f;
-        for (long long i = i_lo; i <= i_hi; ++i) acc = fmaf(xr[i], __ldg(h + (m - i * up)), acc);
-        out[idx] = acc;
+        float* orow = out + r * n_out;
+        for (long long j = blockIdx.x * 256LL + threadIdx.x; j < n_out; j += 256LL * gridDim.x) {
+            const I m = I(j + pre_remove) * I(down);
+            I i_hi = m / I(up);
+            if (i_hi > I(n_in - 1)) i_hi = I(n_in - 1);
+            const I lo_num = m - I(len_h) + 1;
+            const I i_lo = lo_num <= 0 ? I(0) : (lo_num + I(up) - 1) / I(up);
+            const float* hp = h + (m - i_lo * I(up));
+            const float* xp = xr + i_lo;
+            float acc = 0.f;
+            for (int c = int(i_hi - i_lo); c >= 0; --c) {  // ascending i: the reference's (upfirdn's) order
+                acc = fmaf(*xp, __ldg(hp), acc);
+                ++xp;
+                hp -= up;
+            }
+            orow[j] = acc;
+        }
     }
 }
 // Linear-interpolation resampling (resample.py:142-212): positions linspace(0, n_in - 1, n_out) and the blend in
@@ -562,9 +572,11 @@ cudaError_t run_savgol(const float* x, long long rows, long long T, const float*
 }
 cudaError_t run_resample_poly(const float* x, long long rows, long long n_in, const float* h, int len_h, int up, int down,
                               long long pre_remove, long long n_out, float* out, cudaStream_t s) {
-    const long long n = rows * n_out, g = (n + 255) / 256;
-    resample_poly_kernel<<<(unsigned)(g < 1 ? 1 : (g > 148LL * 64 ? 148LL * 64 : g)), 256, 0, s>>>(x, rows, n_in, h, len_h, up, down,
-                                                                                                 pre_remove, n_out, out);
+    const long long gx = (n_out + 255) / 256;
+    dim3 grid((unsigned)(gx < 1 ? 1 : (gx > 148LL * 64 ? 148LL * 64 : gx)), (unsigned)(rows > 65535 ? 65535 : rows));
+    const bool small = (n_out + pre_remove) * (long long)down < (1LL << 31) && n_in < (1LL << 31);
+    if (small) resample_poly_kernel<int><<<grid, 256, 0, s>>>(x, rows, n_in, h, len_h, up, down, pre_remove, n_out, out);
+    else resample_poly_kernel<long long><<<grid, 256, 0, s>>>(x, rows, n_in, h, len_h, up, down, pre_remove, n_out, out);
     return cudaGetLastError();
 }
 cudaError_t run_resample_linear(const float* x, long long rows, long long n_in, long long n_out, double step, double gain,
