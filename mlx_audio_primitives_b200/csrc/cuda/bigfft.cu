@@ -308,8 +308,10 @@ cudaError_t run_resample_fft(const float* x, long long B, long long n, long long
     const long long M1 = pow2_at_least(2 * n - 1), M2 = pow2_at_least(2 * num - 1);
     const long long Mx = M1 > M2 ? M1 : M2;
     float2 *W1, *W2, *wn, *wm, *bh1, *bh2;
+    // held until every launch that reads the cached tables is enqueued: a flush (below) synchronises the device first, so
+    // tables can only be freed when nothing enqueued still reads them
+    std::lock_guard<std::mutex> lk(g_mu);
     {
-        std::lock_guard<std::mutex> lk(g_mu);
         cudaError_t e;
         if (g_cache.size() + 6 > kMaxEntries) {  // rare (many distinct lengths): drop everything once the device is idle
             if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
@@ -356,9 +358,14 @@ cudaError_t run_autocorr_fft(const float* y, long long B, long long n, long long
                              void* work, cudaStream_t s) {
     const long long M = pow2_at_least(2 * n - 1);
     float2* W;
+    std::lock_guard<std::mutex> lk(g_mu);  // until the launches are enqueued (see run_resample_fft)
     {
-        std::lock_guard<std::mutex> lk(g_mu);
         cudaError_t e;
+        if (g_cache.size() + 1 > kMaxEntries) {
+            if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
+            for (auto& kv : g_cache) cudaFree(kv.second);
+            g_cache.clear();
+        }
         if ((e = cache_get(0, M, s, &W)) != cudaSuccess) return e;
     }
     float2* a = static_cast<float2*>(work);

@@ -348,6 +348,12 @@ def test_resample_fft_matches_reference_and_oracle():
             got = mb.resample(torch.from_numpy(y).cuda(), a, b, scale=scale).cpu().numpy()
             assert got.shape == want.shape, (B, n, a, b)
             assert np.abs(got - want).max() < 2e-5 * np.abs(want).max(), (B, n, a, b, np.abs(got - want).max())
+    # many distinct lengths: the per-length table cache is flushed and rebuilt along the way
+    for i in range(10):
+        y = rng.standard_normal((2, 3000 + 37 * i)).astype(np.float32)
+        want = of.resample_fft(y, 3, 2)
+        got = mb.resample(torch.from_numpy(y).cuda(), 3, 2).cpu().numpy()
+        assert got.shape == want.shape and np.abs(got - want).max() < 2e-5 * np.abs(want).max(), i
     # same length -> the input itself; other axes; deterministic
     y = torch.from_numpy(rng.standard_normal((3, 5, 700)).astype(np.float32)).cuda()
     assert mb.resample(y, 8000, 8000) is y
