@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MLXA_ABI_VERSION 3
+#define MLXA_ABI_VERSION 4
 
 #define MLXA_E_INVALID (-1)   /* bad size / null pointer / unknown mode            */
 #define MLXA_E_UNSUPPORTED (-2)
