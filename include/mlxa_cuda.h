@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MLXA_ABI_VERSION 4
+#define MLXA_ABI_VERSION 5
 
 #define MLXA_E_INVALID (-1)   /* bad size / null pointer / unknown mode            */
 #define MLXA_E_UNSUPPORTED (-2)
@@ -94,8 +94,9 @@ int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float
 /* 1 when mlxa_spectral_feature_f32 serves n_fft (a compiled plan whose lane groups fit one warp). */
 int mlxa_has_fused_feature(int n_fft);
 
-/* How the mel kernel that serves n_fft wants its filterbank packed: the lanes per transform (4..32;
- * 32 for sizes without a compiled plan), or 1 = ROW format (n_fft = 400). */
+/* How the mel kernel that serves n_fft wants its filterbank packed: -GP < 0 = ROW-PAIR format whose GP
+ * adjacent bands (the bands one warp step of the projection covers) share a trip count -- every compiled plan;
+ * 32 = lane-group format of the O(n^2) kernels that serve sizes without a compiled plan. */
 int mlxa_plan_group(int n_fft);
 
 /* Packed band-sparse filterbank ("bank") for a lane group of `group` = mlxa_plan_group(n_fft):
@@ -107,10 +108,15 @@ int mlxa_plan_group(int n_fft);
  *     int32   len[n_bands]      support length in bins
  *     int32   goff[n_groups], glen[n_groups]      n_groups = ceil(n_bands / group)
  * padded to mlxa_packed_bank_words(n_bands, n_wt, group) words (a multiple of 4).
- * ROW format (group == 1; the projection runs with lanes along frames, weights are warp-uniform):
- *     float   wt[n_wt]          every band's contiguous run, zero-padded to whole quads (16-byte units)
- *     int32   desc[n_bands][4]  {first frequency bin of the run, quads in the run, first quad of the
- *                               run (wt + 4*off4), support length in bins}
+ * ROW-PAIR format (group = -GP < 0; the projection runs with lanes along frames, a lane holding two frames):
+ *     float   wt[n_wt]          per band 1 + nq entries of 4 words: entry 0 = {w[0], w[1], 0, 0} -- the pair of
+ *                               bins that is always there -- then nq quads of bins {w[2+4i] .. w[5+4i]};
+ *                               zero-padded; the GP adjacent bands m0*GP .. m0*GP + GP - 1 share nq
+ *                               (warp-uniform loops)
+ *     int32   desc[n_pad][4]    {first bin of the run (moved down where the run would leave the F + 3 rows of
+ *                               the kernel's power tile), nq, first entry of the run (wt + 4*entry), support
+ *                               length in bins}; n_pad = n_bands rounded up to a multiple of 32, the padding
+ *                               bands carry zero weights
  * The kernels
  * bulk-copy this blob into shared memory once per CTA.  mlxa_pack_filterbank builds it on the
  * HOST from a dense (n_bands, F) row-major matrix (rows must have contiguous support, which

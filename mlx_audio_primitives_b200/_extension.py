@@ -12,7 +12,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MLXA_CUDA_LIB", os.path.join(_HERE, "_lib", "libmlxaudio_cuda.so"))
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _i64, _i32, _f32, _f64, _p = C.c_int64, C.c_int, C.c_float, C.c_double, C.c_void_p
 

@@ -234,7 +234,8 @@ int64_t mlxa_packed_bank_words(int n_bands, int64_t n_wt, int group) { return pa
 int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, int group, float* packed_host,
                          int64_t capacity_words, int64_t* n_wt_out) {
     CHECK_ARG(dense_host && n_wt_out && n_bands > 0 && F > 0, "bad argument");
-    CHECK_ARG(group == 1 || group == 4 || group == 8 || group == 16 || group == 32, "group must be 1 (row format), 4, 8, 16 or 32");
+    CHECK_ARG((group < 0 && group >= -32) || group == 4 || group == 8 || group == 16 || group == 32,
+              "group must be -GP (row-pair format, GP <= 32 adjacent bands share a pair count), 4, 8, 16 or 32");
     std::vector<int> start(n_bands, 0), len(n_bands, 0);
     for (int m = 0; m < n_bands; ++m) {
         const float* row = dense_host + (int64_t)m * F;
@@ -243,19 +244,45 @@ int mlxa_pack_filterbank(const float* dense_host, int n_bands, int F, int group,
             if (row[k] != 0.f) { if (lo < 0) lo = k; hi = k; }
         if (lo >= 0) { start[m] = lo; len[m] = hi - lo + 1; }
     }
-    if (group == 1) {  // row format: every band's run zero-padded to whole quads
-        std::vector<int> off4(n_bands, 0);
+    if (group < 0) {
+        // row-pair format: per band 1 + nq entries of 4 words -- entry 0 = {w[0], w[1], 0, 0}, the pair of bins
+        // that is always there, entry 1 + i = {w[2 + 4i] .. w[5 + 4i]}, a quad of bins (a packed FFMA2 on a frame
+        // pair takes its weight as a broadcast scalar operand).  The GP adjacent bands one warp step covers share
+        // nq = the group's largest, so the accumulation loop is warp-uniform; descriptors (with zero weights)
+        // are padded to a multiple of 32 bands, so a warp step of any tile size finds one.  A run that would
+        // leave the F + 3 rows of the power tile is moved down (zero weights in front).
+        const int GP = -group;
+        const int n_pad = (n_bands + 31) / 32 * 32;
+        std::vector<int> nq(n_pad, 0), off(n_pad, 0), st(n_pad, 0);
+        for (int m0 = 0; m0 < n_pad; m0 += GP) {
+            int mx = 0;
+            for (int m = m0; m < std::min(n_bands, m0 + GP); ++m) mx = std::max(mx, (std::max(len[m] - 2, 0) + 3) / 4);
+            for (int m = m0; m < std::min(n_pad, m0 + GP); ++m) nq[m] = mx;
+        }
         int64_t total = 0;
-        for (int m = 0; m < n_bands; ++m) { off4[m] = (int)(total / 4); total += (int64_t)((len[m] + 3) / 4) * 4; }
-        *n_wt_out = total;
+        for (int m = 0; m < n_pad; ++m) {
+            const int rows = 2 + 4 * nq[m];
+            off[m] = (int)total;
+            total += 1 + nq[m];
+            st[m] = (m < n_bands) ? std::max(0, std::min(start[m], F + 3 - rows)) : 0;
+            CHECK_ARG(st[m] + rows <= F + 3, "filterbank row does not fit the power tile");
+        }
+        *n_wt_out = 4 * total;
         if (!packed_host) return 0;
-        const int64_t words = packed_bank_words(n_bands, total, 1);
+        const int64_t words = packed_bank_words(n_bands, 4 * total, group);
         CHECK_ARG(capacity_words >= words, "packed buffer too small");
         std::memset(packed_host, 0, sizeof(float) * words);
-        for (int m = 0; m < n_bands; ++m)
-            std::memcpy(packed_host + 4 * (int64_t)off4[m], dense_host + (int64_t)m * F + start[m], sizeof(float) * len[m]);
-        int32_t* ip = reinterpret_cast<int32_t*>(packed_host + total);
-        for (int m = 0; m < n_bands; ++m) { ip[4 * m] = start[m]; ip[4 * m + 1] = (len[m] + 3) / 4; ip[4 * m + 2] = off4[m]; ip[4 * m + 3] = len[m]; }
+        for (int m = 0; m < n_bands; ++m) {
+            const float* row = dense_host + (int64_t)m * F;
+            float* w = packed_host + 4 * (int64_t)off[m];
+            for (int i = 0; i < 2 + 4 * nq[m]; ++i) {
+                const int k = st[m] + i;
+                const float v = (k >= start[m] && k < start[m] + len[m]) ? row[k] : 0.f;
+                w[i < 2 ? i : i + 2] = v;
+            }
+        }
+        int32_t* ip = reinterpret_cast<int32_t*>(packed_host + 4 * total);
+        for (int m = 0; m < n_pad; ++m) { ip[4 * m] = st[m]; ip[4 * m + 1] = nq[m]; ip[4 * m + 2] = off[m]; ip[4 * m + 3] = m < n_bands ? len[m] : 0; }
         return 0;
     }
     const int n_groups = (n_bands + group - 1) / group;
@@ -300,7 +327,7 @@ int mlxa_melspec_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const fl
         p.xchg = to_xchg(xchg);
         p.blocks_per_clip = (int)((p.T + MLXA_MIN_BLOCK_FRAMES - 1) / MLXA_MIN_BLOCK_FRAMES);
         p.block_min = block_min ? block_min + b0 * p.blocks_per_clip : nullptr;
-        p.db_mode = db_mode; p.db_coef = db_coef; p.db_amin = db_amin; p.db_ref = db_ref;
+        p.db_mode = db_mode ? (db_amin >= 1.17549435e-38f ? 1 : 2) : 0; p.db_coef = db_coef; p.db_amin = db_amin; p.db_ref = db_ref;
         CHECK_CUDA(dispatch_fwd(EP_MEL, p, (cudaStream_t)stream), "melspec");
         return 0;
     });

@@ -64,7 +64,7 @@ constexpr double sin_turn(long long num, long long den) { return cos_units8(8 * 
 // occupies the FMA pipe for two passes -- the flop rate is unchanged (tools/probes/f32x2_probe.cu) --
 // but the transform kernels are issue-bound, not pipe-bound.  The host versions (CPU emulation of the
 // kernels, tests/emul) perform the same roundings in the same order.
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 typedef unsigned long long mlxa_u64;
 MLXA_D mlxa_u64 pk2(float a, float b) { mlxa_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 MLXA_D mlxa_u64 pk2(float2 a) { return pk2(a.x, a.y); }

@@ -27,12 +27,23 @@ MLXA_D float spectral_power(float2 X, float power) {
     return powf(a, power);
 }
 
-// coef * log10(max(x, amin) / refc): scale first, then log, like convert.py:52.  The quotient is a
-// multiplication by the (loop-invariant, correctly rounded) reciprocal of refc and the logarithm runs on the
-// SFU (MUFU.LG2): absolute error of lg2 is 2^-22, i.e. < 1e-5 dB, far inside the 1e-3 dB parity bound.
-// Every kernel that converts to dB uses this one function, so fused and two-pass paths give the same bits.
+// coef * log10(max(x, amin) / refc) (convert.py:48-52) as  c1 * log2(max(x, amin)) + c0  with
+// c1 = coef * log10(2), c0 = -c1 * log2(refc): one clamp, one MUFU.LG2 (absolute error 2^-22, i.e. < 1e-5 dB,
+// far inside the 1e-3 dB parity bound) and one FFMA per value.  Every kernel that converts to dB uses these
+// two functions, so fused and two-pass paths give the same bits (refc = 1 makes c0 an exact zero).
+struct DbConst {
+    float amin, c1, c0;
+};
+MLXA_D DbConst db_constants(float coef, float amin, float ref) {
+    DbConst c;
+    c.amin = amin;
+    c.c1 = coef * 0.30102999566398120f;
+    c.c0 = -c.c1 * log2f(fmaxf(ref, amin));
+    return c;
+}
 MLXA_D float to_db_one(float x, float coef, float amin, float refc) {
-    return (coef * 0.30102999566398120f) * __log2f(fmaxf(x, amin) * (1.0f / refc));
+    const DbConst c = db_constants(coef, amin, refc);
+    return fmaf(__log2f(fmaxf(x, amin)), c.c1, c.c0);
 }
 
 // EP_STFT / EP_GL: one bin straight to global memory

@@ -58,7 +58,7 @@ __host__ __device__ inline SmemLayout smem_layout(int ep, int NG, int hop, int T
     s.tw_f2 = TW_SMEM ? (TWP + TWU) : 0;  // both tables padded to even counts (16-byte multiples)
     const int pt_bytes = (ep == EP_MEL) ? power_tile_rows(NBINS) * power_tile_stride(TT) * 4 : 0;
     s.xch_bytes = (NG * P::BUF * 8 > pt_bytes) ? NG * P::BUF * 8 : ((pt_bytes + 15) & ~15);
-    s.mel_floats = (ep == EP_MEL && bank_in_smem) ? (int)packed_bank_words(n_bands, n_w4, 1) : 0;
+    s.mel_floats = (ep == EP_MEL && bank_in_smem) ? (int)packed_bank_words(n_bands, n_w4, -1) : 0;
     s.bytes = size_t(n_in_buf * s.in_floats + NFFT + s.mel_floats) * 4 + size_t(s.tw_f2) * 8 + size_t(s.xch_bytes) + 32;
     return s;
 }
@@ -186,7 +186,11 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
     const float2* tw_plan = TW_SMEM ? s_tw : p.tw_plan;
     const float2* tw_unpack = TW_SMEM ? s_tw + TWP : p.tw_unpack;
     RowBank rb{};
-    if constexpr (EP == EP_MEL) rb = row_bank_carve(p.bank_in_smem ? s_mel : p.bank, p.n_w4);
+    [[maybe_unused]] DbConst dbc{};
+    if constexpr (EP == EP_MEL) {
+        rb = row_bank_carve(p.bank_in_smem ? s_mel : p.bank, p.n_w4);
+        dbc = db_constants(p.db_coef, p.db_amin, p.db_ref);  // loop-invariant: one precise log2 per thread
+    }
     __syncthreads();
     mbar_wait(s_bar + 2, 0);
 
@@ -380,20 +384,21 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                     nxt.advance();
                     if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0, s_bar + 0);
                 }
-                if (va) {
-                    float* col = s_pw + f0;
+                if (va) {  // frame f of the tile lives in column power_tile_col(f): lanes of the projection own frames fl, fl + TT/2
+                    float* col = s_pw + power_tile_col(f0, TT >> 1);
+                    [[maybe_unused]] float* col1 = s_pw + power_tile_col(f0 + (FPT - 1), TT >> 1);
                     static_for<NQ>([&](auto q) {
                         constexpr int Q = decltype(q)::value;
                         const int k = g + Q * P::G;
                         if (Q + 1 < NQ || k < NBINS) {
                             if constexpr (PACK) col[k * PS] = pw[Q];
-                            else *reinterpret_cast<float2*>(col + k * PS) = make_float2(pw[2 * Q], pw[2 * Q + 1]);
+                            else { col[k * PS] = pw[2 * Q]; col1[k * PS] = pw[2 * Q + 1]; }
                         }
                     });
                 }
                 for (int i = threadIdx.x; i < 3 * PS; i += THREADS) s_pw[NBINS * PS + i] = 0.f;  // rows padded quads touch
                 __syncthreads();
-                project_power_tile<THREADS, 0, false>(p, rb, s_pw, TT, b, t0, nt, 1.f, vmax);
+                project_power_tile<THREADS, 0, false>(p, rb, dbc, s_pw, TT, b, t0, nt, 1.f, vmax);
             } else if constexpr (EP == EP_FEAT && P::G > 32) {
                 // (not reachable: the launcher refuses EP_FEAT for two-warp groups -- the reductions are warp shuffles)
             } else if constexpr (EP == EP_FEAT) {
@@ -519,7 +524,7 @@ struct MelRowsVariant {
     static cudaError_t run(FwdParams& p, cudaStream_t s) {
         constexpr size_t kMaxSmem = 227 * 1024 - 256;
         constexpr size_t kShare = (228 * 1024) / C::CTAS_PER_SM - 1024 - 64;  // an SM's shared memory split over the resident CTAs
-        long long bw = packed_bank_words(p.n_bands, p.n_w4, 1);
+        long long bw = packed_bank_words(p.n_bands, p.n_w4, -1);
         p.bank_in_smem = 1;
         if (C::smem_bytes(p.hop, 1, bw) > kMaxSmem) { p.bank_in_smem = 0; bw = 0; }
         if (C::smem_bytes(p.hop, 1, bw) > kMaxSmem) return cudaErrorInvalidConfiguration;
@@ -534,17 +539,11 @@ struct MelRowsVariant {
         return go<POW_GENERAL>(p, smem, s);
     }
 };
-// Default: two 8-warp CTAs (32-frame tiles) per SM, so one CTA's projection / barrier phases overlap the
-// other's transforms; MLXA_MEL_ROWS_THREADS=512 selects one 16-warp CTA with 64-frame tiles (A/B runs).
+// Two 8-warp CTAs (32-frame tiles) per SM, so one CTA's projection / barrier phases overlap the other's
+// transforms (one 16-warp CTA with 64-frame tiles measured slower in round 1).
 template <class PL>
 struct MelRowsLaunch<PL, true> {
-    static cudaError_t run(FwdParams& p, cudaStream_t s) {
-        static const int threads = [] {
-            const char* e = getenv("MLXA_MEL_ROWS_THREADS");
-            return (e && atoi(e) == 512) ? 512 : 256;
-        }();
-        return threads == 512 ? MelRowsVariant<PL, 512>::run(p, s) : MelRowsVariant<PL, 256>::run(p, s);
-    }
+    static cudaError_t run(FwdParams& p, cudaStream_t s) { return MelRowsVariant<PL, 256>::run(p, s); }
 };
 
 }  // namespace
@@ -596,8 +595,13 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
 }
 
 // host tables: plan twiddles and the real-unpack twiddle 0.5*exp(-i*pi*k/N)
-// how the mel kernel of this n_fft wants its filterbank packed: 1 = row format (every planned size)
-int MLXA_CAT(plan_group_, MLXA_NFFT)() { return 1; }
+// how the mel kernel of this n_fft wants its filterbank packed: -GP = row-pair format whose GP adjacent bands (the
+// bands one warp step of the projection covers: 64 / tile frames) share one pair count
+int MLXA_CAT(plan_group_, MLXA_NFFT)() {
+    constexpr int TT = PACK ? threads_for(EP_MEL) / P::G : 32;  // mel_rows_kernel: 32-frame tiles
+    constexpr int GP = TT >= 64 ? 1 : 64 / TT;
+    return -GP;
+}
 // the fused per-frame statistics reduce with warp shuffles: plans whose groups fit a warp
 int MLXA_CAT(plan_fused_feature_, MLXA_NFFT)() { return P::G <= 32 ? 1 : 0; }
 

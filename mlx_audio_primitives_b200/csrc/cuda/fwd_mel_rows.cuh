@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nbuf = p.n_in_buf;
     const int in_floats = C::in_floats(p.hop);
-    const long long bank_words = BANK_SMEM ? packed_bank_words(p.n_bands, p.n_w4, 1) : 0;
+    const long long bank_words = BANK_SMEM ? packed_bank_words(p.n_bands, p.n_w4, -1) : 0;
 
     float* s_in0 = reinterpret_cast<float*>(smem_raw);
     float* s_win = s_in0 + nbuf * in_floats;
@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
         for (int i = threadIdx.x; i < (int)bank_words; i += THREADS) s_bank[i] = __ldg(p.bank + i);
     }
     const RowBank rb = row_bank_carve(BANK_SMEM ? s_bank : p.bank, p.n_w4);
+    const DbConst dbc = db_constants(p.db_coef, p.db_amin, p.db_ref);  // loop-invariant: one precise log2 per thread
     const float pscale = (PW == POW_SQUARE) ? 0.25f : (PW == POW_ABS ? 0.5f : exp2f(-p.power));
     __syncthreads();
     mbar_wait(s_bar + 2, 0);
@@ -123,13 +124,13 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
         const float* tile = s_in + ti.lead;
         const int nt = ti.nt;
 
-        // ---- transform of the group's frame pair (f0, f0 + 1) ------------------------------------
-        float2 pp[R1];  // (|.|^p of frame f0, of frame f0 + 1) for the lane's R1 bins, times 1/pscale
+        // ---- transform of the group's frame pair (gi, gi + NG): columns 2*gi, 2*gi + 1 of the power tile ----
+        float2 pp[R1];  // (|.|^p of frame gi, of frame gi + NG) for the lane's R1 bins, times 1/pscale
         {
-            const int f0 = 2 * gi;
-            const bool va = f0 < nt, vb = f0 + 1 < nt;  // absent frames ride as copies: finite, never stored
-            const float* sa = tile + (va ? f0 * p.hop : 0) + g + sh;
-            const float* sb = tile + (vb ? (f0 + 1) * p.hop : (va ? f0 * p.hop : 0)) + g + sh;
+            const int fa = gi, fb = gi + C::NG;
+            const bool va = fa < nt, vb = fb < nt;  // absent frames ride as copies: finite, never stored
+            const float* sa = tile + (va ? fa * p.hop : 0) + g + sh;
+            const float* sb = tile + (vb ? fb * p.hop : (va ? fa * p.hop : 0)) + g + sh;
             const float* wp = s_win + g + sh;
             mirror_pass0<P>(g, [&](auto r_) {
                 constexpr int r = decltype(r_)::value;
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
         __syncthreads();
 
         // ---- band-sparse projection, lanes along frames (mel_project.cuh) -----------------------------
-        project_power_tile<THREADS, TT, !BANK_SMEM>(p, rb, s_pw, TT, ti.b, ti.t0, nt, pscale, vmax);
+        project_power_tile<THREADS, TT, !BANK_SMEM>(p, rb, dbc, s_pw, TT, ti.b, ti.t0, nt, pscale, vmax);
         __syncthreads();  // power tile consumed: the next tile's transforms may reuse the buffers
     }
     if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red, p.xchg);

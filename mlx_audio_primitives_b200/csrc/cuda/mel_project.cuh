@@ -1,15 +1,21 @@
-// Band-sparse filterbank projection of a tile of power spectra laid out [bin][frame] in shared memory
+// Band-sparse filterbank projection of a tile of power spectra laid out [bin][column] in shared memory
 // (replaces the dense matmul of reference mel.py:344): lanes run along FRAMES.  A band row of the tile is
-// TT/2 lanes x 2 frames (64-bit conflict-free reads, packed FFMA2), a warp covers 64/TT rows at once, the
-// weights are warp-uniform float4 quads of the ROW-format bank, and every (band, frame pair) goes straight to
-// global memory with the running max, the per-block minima and the optional dB fused.
+// TT/2 lanes x 2 frames -- the lane's float2 holds frames fl and fl + TT/2 of the tile (the transforms park
+// frame f in column 2*(f mod TT/2) + f / (TT/2)), so both stores of a band row are contiguous runs of TT/2
+// floats.  A warp covers 64/TT ADJACENT bands per step; the ROW-PAIR bank pads the bands of such a group to
+// one common count of bin quads, so the accumulation loop has a warp-uniform trip count (no divergence, no
+// per-lane loop bookkeeping); a quad's four weights arrive in one 128-bit shared-memory read and enter the packed
+// FFMA2 as broadcast scalar operands (no register moves).  Every (band, frame)
+// value goes from registers to global memory with the running max, the per-block minimum (3-input FMNMX) and
+// the optional dB conversion (one clamp, one MUFU.LG2, one FFMA) fused.
 #pragma once
 #include "fwd_epilogue.cuh"
 
 namespace mlxa {
 
-// bank packed in ROW format (mlxa_plan_group == 1, see include/mlxa_cuda.h): quad-padded weight runs, then
-// one int4 {start, n4, off4, len} per band
+// bank packed in ROW-PAIR format (mlxa_plan_group = -GP < 0, see include/mlxa_cuda.h): per band 1 + nq entries of
+// four weights ({w0, w1, -, -}, then quads of bins), then one int4 {first bin, nq, first entry, support length}
+// per band, bands padded to a multiple of 32
 struct RowBank {
     const float4* wt4;
     const int4* desc;
@@ -21,82 +27,103 @@ MLXA_D RowBank row_bank_carve(const float* base, long long n_wt) {
     return r;
 }
 
-// power-tile geometry for TT frames: row stride (floats; even, == 2 mod 4 so frame pairs of consecutive
-// rows spread over the banks) and row count (+3: rows the zero-padded weight quads may touch)
+// power-tile geometry for TT frames: row stride (floats; even, == 2 mod 4 so the 64-bit frame pairs of
+// consecutive rows spread over the banks) and row count (+3: rows the zero-padded weight pairs may touch)
 constexpr int power_tile_stride(int TT) { return TT + 2; }
 constexpr int power_tile_rows(int n_bins) { return n_bins + 3; }
+// column of the power tile that holds frame f of a TT-frame tile, and the frame a column holds
+MLXA_HD int power_tile_col(int f, int half) { return f < half ? 2 * f : 2 * (f - half) + 1; }
+
+#if defined(__CUDACC__)
+MLXA_D float max3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+MLXA_D float min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+#endif
+
+// DBM: 0 raw values, 1 dB with amin / ref in the normal range (flush-to-zero MUFU.LG2, no denormal fix-up),
+// 2 dB for any amin (same bits as 1 wherever 1 is valid).
+template <int DBM>
+MLXA_D float project_db(float v, float amin, float c1, float c0) {
+    if constexpr (DBM == 0) return v;
+    const float x = fmaxf(v, amin);
+    float l;
+    if constexpr (DBM == 1) asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    else l = __log2f(x);
+    return fmaf(l, c1, c0);
+}
 
 // TTC: tile frames when known at compile time, 0 -> tt (a power of two >= 2).  SCALE: multiply the sums by
 // pscale (pair transforms deliver 4|X|^2 and the bank could not be pre-scaled).
-template <int THREADS, int TTC, bool SCALE>
-MLXA_D void project_power_tile(const FwdParams& p, const RowBank& rb, const float* s_pw, int tt, int b, int t0, int nt,
-                               float pscale, float& vmax) {
+template <int THREADS, int TTC, bool SCALE, int DBM, bool FULL>
+MLXA_D void project_power_tile_impl(const FwdParams& p, const RowBank& rb, const DbConst& dbc, const float* s_pw, int tt, int b,
+                                    int t0, int nt, float pscale, float& vmax, float& tmin) {
     const int TT = TTC ? TTC : tt;
     const int PS = power_tile_stride(TT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int LB = TT / 2, per_warp = 32 / LB, SLOTS = (THREADS / 32) * per_warp;  // band slots of the CTA per step
-    const int fl = lane & (LB - 1), slot = warp * per_warp + lane / LB;
-    const float db_ref = fmaxf(p.db_ref, p.db_amin);
-    char* ob = reinterpret_cast<char*>(p.mel + (long long)b * p.n_bands * p.T + t0 + 2 * fl);
-    const float2* q_lane = reinterpret_cast<const float2*>(s_pw) + fl;
+    const int LB = TT / 2, NBW = 32 / LB;          // lanes per band row, bands per warp step
+    const int fl = lane & (LB - 1), sub = lane / LB;
+    constexpr int NW = THREADS / 32;
+    const int per_step = NW * NBW;                 // bands the CTA covers per step
+    const int n_pad = (p.n_bands + NBW - 1) / NBW * NBW;  // the bank carries descriptors (zero weights) up to here
+    char* ob = reinterpret_cast<char*>(p.mel + (long long)b * p.n_bands * p.T + t0 + fl);
     const unsigned row_bytes = unsigned(p.T) * 4u;
+    const float2* q_lane = reinterpret_cast<const float2*>(s_pw) + fl;
     const int rs = PS / 2;  // row stride in float2
-    // Bands are taken two at a time per lane (two independent accumulation chains and epilogues in flight:
-    // the phase is latency-bound otherwise); band m -> the lane's frames 2*fl, 2*fl + 1 of row m.  FULL:
-    // every frame of the tile exists.
-    float tmin = INFINITY;
-    auto quad = [&](const float4* w4, const float2* q, float2 acc) {
-        const float4 w = *w4;
-        const float2 q0 = q[0], q1 = q[rs], q2 = q[2 * rs], q3 = q[3 * rs];
-        return caxpy(w.w, q3, caxpy(w.z, q2, caxpy(w.y, q1, caxpy(w.x, q0, acc))));
-    };
-    auto band_pair = [&](auto full_, int mA, int mB) {
-        constexpr bool FULL = decltype(full_)::value;
-        const bool hasA = mA < p.n_bands, hasB = mB < p.n_bands;
-        const int4 dA = hasA ? rb.desc[mA] : make_int4(0, 0, 0, 0);  // start, quads, first quad
-        const int4 dB = hasB ? rb.desc[mB] : make_int4(0, 0, 0, 0);
-        const float4 *wA = rb.wt4 + dA.z, *wB = rb.wt4 + dB.z;
-        const float2 *qA = q_lane + dA.x * rs, *qB = q_lane + dB.x * rs;
-        float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
-        int nA = dA.y, nB = dB.y;
+    const bool ok0 = FULL || fl < nt, ok1 = FULL || fl + LB < nt;
+    // band groups go round the warps boustrophedon, so every warp gets short and long bands alike
+    const int m_even = warp * NBW + sub, m_odd = (NW - 1 - warp) * NBW + sub;
 #pragma unroll 1
-        for (; nA > 0 && nB > 0; --nA, --nB, ++wA, ++wB, qA += 4 * rs, qB += 4 * rs) {
-            accA = quad(wA, qA, accA);
-            accB = quad(wB, qB, accB);
+    for (int m0 = 0, odd = 0; m0 < n_pad; m0 += per_step, odd ^= 1) {
+        const int m = m0 + (odd ? m_odd : m_even);
+        if (m - sub >= n_pad) continue;  // warp-uniform: no band group left for this warp
+        const int4 d = rb.desc[m];  // {first bin, quads after the first pair, first weight entry, -}
+        const float4* w = rb.wt4 + d.z;
+        const float2* q = q_lane + d.x * rs;
+        // the first pair of bins is always there (entry 0 = {w0, w1, -, -}) ...
+        const float4 w0 = w[0];
+        mlxa_u64 a0 = mul2(pk2(q[0]), pk2(w0.x, w0.x));
+        mlxa_u64 a1 = mul2(pk2(q[rs]), pk2(w0.y, w0.y));
+        // ... then nq quads, nq the same for all bands of the warp step
+        const float4* wend = w + d.y;
+#pragma unroll 1
+        for (; w != wend; ++w, q += 4 * rs) {
+            const float4 wa = w[1];
+            a0 = fma2(pk2(q[2 * rs]), pk2(wa.x, wa.x), a0);
+            a1 = fma2(pk2(q[3 * rs]), pk2(wa.y, wa.y), a1);
+            a0 = fma2(pk2(q[4 * rs]), pk2(wa.z, wa.z), a0);
+            a1 = fma2(pk2(q[5 * rs]), pk2(wa.w, wa.w), a1);
         }
-#pragma unroll 1
-        for (; nA > 0; --nA, ++wA, qA += 4 * rs) accA = quad(wA, qA, accA);
-#pragma unroll 1
-        for (; nB > 0; --nB, ++wB, qB += 4 * rs) accB = quad(wB, qB, accB);
-        float v[4] = {accA.x, accA.y, accB.x, accB.y};
-        if constexpr (SCALE) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] *= pscale;
+        float2 v = up2(add2(a0, a1));
+        if constexpr (SCALE) v = cscale(v, pscale);
+        if (m < p.n_bands) {
+            float* o = reinterpret_cast<float*>(ob + (unsigned long long)unsigned(m) * row_bytes);
+            if (FULL || ok1) {  // frames fill a tile from column 0 up: ok1 implies ok0
+                vmax = max3(vmax, v.x, v.y);
+                tmin = min3(tmin, v.x, v.y);
+                o[0] = project_db<DBM>(v.x, dbc.amin, dbc.c1, dbc.c0);
+                o[LB] = project_db<DBM>(v.y, dbc.amin, dbc.c1, dbc.c0);
+            } else if (ok0) {
+                vmax = fmaxf(vmax, v.x);
+                tmin = fminf(tmin, v.x);
+                o[0] = project_db<DBM>(v.x, dbc.amin, dbc.c1, dbc.c0);
+            }
         }
-        const bool ok0 = FULL || 2 * fl < nt, ok1 = FULL || 2 * fl + 1 < nt;
-        const bool st[4] = {ok0 && hasA, ok1 && hasA, ok0 && hasB, ok1 && hasB};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (st[i]) { vmax = fmaxf(vmax, v[i]); tmin = fminf(tmin, v[i]); }
-        if (p.db_mode) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = to_db_one(v[i], p.db_coef, p.db_amin, db_ref);
-        }
-        float* oA = reinterpret_cast<float*>(ob + (unsigned long long)unsigned(mA) * row_bytes);
-        float* oB = reinterpret_cast<float*>(ob + (unsigned long long)unsigned(mB) * row_bytes);
-        if (st[0]) oA[0] = v[0];
-        if (st[1]) oA[1] = v[1];
-        if (st[2]) oB[0] = v[2];
-        if (st[3]) oB[1] = v[3];
-    };
-    // boustrophedon over the CTA's band slots: long and short bands mix
-    if (nt == TT) {
-#pragma unroll 1
-        for (int m0 = 0; m0 < p.n_bands; m0 += 2 * SLOTS) band_pair(std::true_type{}, m0 + slot, m0 + 2 * SLOTS - 1 - slot);
-    } else {
-#pragma unroll 1
-        for (int m0 = 0; m0 < p.n_bands; m0 += 2 * SLOTS) band_pair(std::false_type{}, m0 + slot, m0 + 2 * SLOTS - 1 - slot);
     }
+}
+
+template <int THREADS, int TTC, bool SCALE>
+MLXA_D void project_power_tile(const FwdParams& p, const RowBank& rb, const DbConst& dbc, const float* s_pw, int tt, int b, int t0,
+                               int nt, float pscale, float& vmax) {
+    const int TT = TTC ? TTC : tt;
+    float tmin = INFINITY;
+    // db_mode: 0 raw, 1 dB (fast form valid), 2 dB with a denormal amin / ref quotient (set by the host)
+    auto run = [&](auto dbm) {
+        constexpr int DBM = decltype(dbm)::value;
+        if (nt == TT) project_power_tile_impl<THREADS, TTC, SCALE, DBM, true>(p, rb, dbc, s_pw, tt, b, t0, nt, pscale, vmax, tmin);
+        else project_power_tile_impl<THREADS, TTC, SCALE, DBM, false>(p, rb, dbc, s_pw, tt, b, t0, nt, pscale, vmax, tmin);
+    };
+    if (p.db_mode == 0) run(std::integral_constant<int, 0>{});
+    else if (p.db_mode == 1) run(std::integral_constant<int, 1>{});
+    else run(std::integral_constant<int, 2>{});
     if (p.block_min != nullptr) block_min_to_global(p, b, t0, tmin);
 }
 

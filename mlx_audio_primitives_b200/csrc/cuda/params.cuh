@@ -53,7 +53,7 @@ struct FwdParams {
     PeakExchange xchg;    // optional: publish the final gmax to every peer
     float* block_min;     // optional (B, blocks_per_clip): min of the raw values per 64-frame block of a clip
     int blocks_per_clip;  // ceil(T / 64)
-    int db_mode;
+    int db_mode;          // 0 raw values, 1 dB, 2 dB with amin below the normal range (no flush-to-zero logarithm)
     float db_coef, db_amin, db_ref;
     // EP_FEAT: one per-frame spectral statistic (STAT_*), the spectrum never leaves the SM
     int feat_kind, feat_norm;
@@ -68,9 +68,9 @@ struct FwdParams {
 };
 
 // 32-bit words of a packed band-sparse filterbank (layout: fwd_epilogue.cuh / mlxa_cuda.h)
-// group == 1 is the ROW format (fwd_mel_rows.cuh): [wt][int4 {start, n4, off4, len} per band]
+// group = -GP < 0 is the ROW-PAIR format (mel_project.cuh): [wt][int4 {start, nq, off, len} per band, bands padded to a multiple of 32]
 __host__ __device__ inline long long packed_bank_words(int n_bands, long long n_wt, int group) {
-    if (group == 1) return n_wt + 4LL * n_bands;
+    if (group < 0) return n_wt + 4LL * ((n_bands + 31) / 32 * 32);
     return (n_wt + 2LL * n_bands + 2LL * ((n_bands + group - 1) / group) + 3) & ~3LL;
 }
 

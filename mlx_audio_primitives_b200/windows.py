@@ -78,9 +78,10 @@ def get_window(window, n_fft: int, fftbins: bool = True) -> torch.Tensor:
 
 def padded_window(window, win_length: int, n_fft: int) -> torch.Tensor:
     """Window zero-padded and centred to n_fft: left = (n_fft - win_length) // 2 (reference
-    ``_get_padded_window`` stft.py:88-107).  Named windows are cached per device; array windows are
-    keyed on (storage pointer, version) instead of the reference's device->host content hash
-    (stft.py:42), so no synchronising copy happens per call."""
+    ``_get_padded_window`` stft.py:88-107).  Named windows are cached per device; caller-owned CUDA tensors
+    are keyed on (storage pointer, version) -- with the tensor kept alive by the entry -- instead of the
+    reference's device->host content hash (stft.py:42), so no synchronising copy happens per call; host
+    arrays are uploaded per call and not cached."""
     def build(w: torch.Tensor) -> torch.Tensor:
         if win_length == n_fft:
             return w.contiguous()
@@ -95,8 +96,14 @@ def padded_window(window, win_length: int, n_fft: int) -> torch.Tensor:
         return _resident(("p", window.lower(), int(win_length), int(n_fft), dev),
                          lambda: build(get_window(window, win_length, True)))
     w = get_window(window, win_length, True)
+    if not (isinstance(window, torch.Tensor) and window.is_cuda):
+        # NumPy / DLPack / CPU windows are uploaded afresh on every call; the upload is freed on return and the
+        # allocator hands its block to the next upload, so a (pointer, version) key would alias different windows
+        return build(w)
+    # a caller-owned CUDA tensor: key on (pointer, version) and keep the tensor alive in the entry, so the
+    # pointer cannot be recycled for another window while the entry exists
     return _resident(("pa", w.data_ptr(), w._version, int(win_length), int(n_fft), w.device.index),
-                     lambda: build(w).clone())
+                     lambda: (build(w).clone(), w))[0]
 
 
 def clear_caches() -> None:

@@ -22,7 +22,7 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in mlxa_cuda.h but not exported"
     assert declared - {"mlxa_last_error", "mlxa_packed_bank_words"} == set(ext.SIGNATURES), "host-layer signature table out of sync"
-    assert ext._ext.mlxa_plan_group(400) == 1 and ext._ext.mlxa_plan_group(2048) == 1 and ext._ext.mlxa_plan_group(777) == 32
+    assert ext._ext.mlxa_plan_group(400) == -2 and ext._ext.mlxa_plan_group(2048) == -4 and ext._ext.mlxa_plan_group(777) == 32
     assert ext._ext.mlxa_abi_version() == ext.ABI_VERSION
     assert ext._ext.mlxa_has_fast_plan(400) == 1 and ext._ext.mlxa_has_fast_plan(2048) == 1
     assert ext._ext.mlxa_has_fast_plan(600) == 0
@@ -49,13 +49,23 @@ def test_host_constants_match_reference_fixtures(golden):
             fb = mel_filterbank_host(sr, n_fft, n_mels, fmin, fmax, bool(int(parts[6])), norm)
             assert np.array_equal(fb, golden[key]), key
             # the packed band-sparse forms (what the kernels consume) reproduce the dense matrix exactly
-            packed, n_wt = pack_bank_host(fb, 1)  # row format: quad-padded runs
-            start, n4, off4, ln = packed[n_wt:].view(np.int32).reshape(n_mels, 4).T
-            assert packed.size == n_wt + 4 * n_mels and np.array_equal(n4, (ln + 3) // 4)
-            dense = np.zeros((n_mels, fb.shape[1] + 3), np.float32)
-            for m in range(n_mels):
-                dense[m, start[m]:start[m] + 4 * n4[m]] = packed[4 * off4[m]:4 * (off4[m] + n4[m])]
-            assert n_wt % 4 == 0 and np.array_equal(dense[:, :fb.shape[1]], fb) and not dense[:, fb.shape[1]:].any()
+            # row-pair format (group = -GP): per band 1 + nq entries of 4 words ({w0, w1, 0, 0}, then quads), nq shared
+            # by GP adjacent bands, descriptors padded to a multiple of 32 bands, every run inside the F + 3 rows of
+            # the power tile
+            F = fb.shape[1]
+            for GP in (1, 2, 4, 8):
+                packed, n_wt = pack_bank_host(fb, -GP)
+                n_pad = -(-n_mels // 32) * 32
+                start, nq, off, ln = packed[n_wt:].view(np.int32).reshape(n_pad, 4).T
+                assert packed.size == n_wt + 4 * n_pad and n_wt == 4 * int((1 + nq).sum())
+                dense = np.zeros((n_pad, F + 3), np.float32)
+                for m in range(n_pad):
+                    ent = packed[4 * off[m]:4 * (off[m] + 1 + nq[m])]
+                    run = np.concatenate([ent[:2], ent[4:]])
+                    assert not ent[2:4].any() and start[m] >= 0 and start[m] + run.size <= F + 3
+                    dense[m, start[m]:start[m] + run.size] = run
+                    assert (nq[m // GP * GP:(m // GP + 1) * GP] == nq[m]).all()  # warp-uniform trip count
+                assert np.array_equal(dense[:n_mels, :F], fb) and not dense[:, F:].any() and not dense[n_mels:].any()
             for group in (16, 32):
                 packed, n_wt = pack_bank_host(fb, group)
                 n_groups = -(-n_mels // group)
