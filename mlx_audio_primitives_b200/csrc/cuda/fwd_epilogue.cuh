@@ -140,10 +140,10 @@ MLXA_D void mel_project_group(const MelSmem ms, int n_bands, int g, const float*
 // ordering; one atomic per warp.
 constexpr int kMinBlockFrames = 64;
 MLXA_D void block_min_to_global(const FwdParams& p, int b, int t0, float vmin) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    // one REDUX instead of five shuffle + min rounds (the bit patterns of values >= 0 order like integers)
+    const int m = __reduce_min_sync(0xffffffffu, __float_as_int(vmin));
     if ((threadIdx.x & 31) == 0)
-        atomicMin(reinterpret_cast<int*>(p.block_min) + (long long)b * p.blocks_per_clip + t0 / kMinBlockFrames, __float_as_int(vmin));
+        atomicMin(reinterpret_cast<int*>(p.block_min) + (long long)b * p.blocks_per_clip + t0 / kMinBlockFrames, m);
 }
 
 // Tile store: s_out [n_bands][TT+1] -> mel (B, n_bands, T), lanes along the frames (coalesced),

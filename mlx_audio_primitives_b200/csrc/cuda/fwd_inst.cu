@@ -133,6 +133,7 @@ struct TileWalk {
 };
 
 #include "fwd_mel_rows.cuh"
+#include "fwd_mel_ws.cuh"
 
 template <int EP, int PW>
 // 16 warps per SM (register cap 128), except the 64-values-per-lane plan: one 8-warp CTA, 255 registers
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 }
                 for (int i = threadIdx.x; i < 3 * PS; i += THREADS) s_pw[NBINS * PS + i] = 0.f;  // rows padded quads touch
                 __syncthreads();
-                project_power_tile<THREADS, 0, false>(p, rb, dbc, s_pw, TT, b, t0, nt, 1.f, vmax);
+                project_power_tile<THREADS / 32, 0, false>(p, rb, dbc, s_pw, TT, b, t0, nt, 1.f, threadIdx.x >> 5, vmax);
             } else if constexpr (EP == EP_FEAT && P::G > 32) {
                 // (not reachable: the launcher refuses EP_FEAT for two-warp groups -- the reductions are warp shuffles)
             } else if constexpr (EP == EP_FEAT) {
@@ -543,7 +544,41 @@ struct MelRowsVariant {
 // transforms (one 16-warp CTA with 64-frame tiles measured slower in round 1).
 template <class PL>
 struct MelRowsLaunch<PL, true> {
-    static cudaError_t run(FwdParams& p, cudaStream_t s) { return MelRowsVariant<PL, 256>::run(p, s); }
+    // two barrier-phased 8-warp CTAs per SM (fwd_mel_rows.cuh); MLXA_MEL_WS=1 selects the warp-specialised kernel
+    // (fwd_mel_ws.cuh) where its single-CTA shared-memory layout fits (A/B runs: it measures within 2 % of the default)
+    template <int PW, bool BS>
+    static cudaError_t ws_go(FwdParams& p, size_t smem, cudaStream_t s) {
+        using C = MelWs<PL>;
+        auto kern = mel_ws_kernel<PL, PW, BS>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int dev = 0, n_sm = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        const long long total = (long long)p.B * ((p.T + C::TT - 1) / C::TT);
+        kern<<<(unsigned)(total < n_sm ? total : n_sm), C::THREADS, smem, s>>>(p);
+        return cudaGetLastError();
+    }
+    static cudaError_t run(FwdParams& p, cudaStream_t s) {
+        using C = MelWs<PL>;
+        static const bool no_ws = getenv("MLXA_MEL_WS") == nullptr;
+        constexpr size_t kMaxSmem = 227 * 1024 - 256;
+        long long bw = packed_bank_words(p.n_bands, p.n_w4, -1);
+        bool bank_smem = true;
+        if (C::smem_bytes(p.hop, bw) > kMaxSmem) { bank_smem = false; bw = 0; }
+        if (no_ws || C::smem_bytes(p.hop, bw) > kMaxSmem) return MelRowsVariant<PL, 256>::run(p, s);
+        p.bank_in_smem = bank_smem;
+        p.n_in_buf = 1;
+        p.tile_frames = C::TT;
+        const size_t smem = C::smem_bytes(p.hop, bw);
+        auto go = [&](auto pw) {
+            constexpr int PW = decltype(pw)::value;
+            return bank_smem ? ws_go<PW, true>(p, smem, s) : ws_go<PW, false>(p, smem, s);
+        };
+        if (p.power_mode == POW_SQUARE) return go(std::integral_constant<int, POW_SQUARE>{});
+        if (p.power_mode == POW_ABS) return go(std::integral_constant<int, POW_ABS>{});
+        return go(std::integral_constant<int, POW_GENERAL>{});
+    }
 };
 
 }  // namespace
@@ -597,11 +632,16 @@ cudaError_t MLXA_CAT(launch_fwd_, MLXA_NFFT)(int ep, FwdParams& p, cudaStream_t 
 // host tables: plan twiddles and the real-unpack twiddle 0.5*exp(-i*pi*k/N)
 // how the mel kernel of this n_fft wants its filterbank packed: -GP = row-pair format whose GP adjacent bands (the
 // bands one warp step of the projection covers: 64 / tile frames) share one pair count
-int MLXA_CAT(plan_group_, MLXA_NFFT)() {
-    constexpr int TT = PACK ? threads_for(EP_MEL) / P::G : 32;  // mel_rows_kernel: 32-frame tiles
-    constexpr int GP = TT >= 64 ? 1 : 64 / TT;
-    return -GP;
-}
+template <class PL, bool PAIR>
+struct BankGroup {  // packed plans: the bands one warp step of fwd_kernel<EP_MEL> covers
+    static constexpr int TT = threads_for(EP_MEL) / PL::G;
+    static constexpr int value = TT >= 64 ? 1 : 64 / TT;
+};
+template <class PL>
+struct BankGroup<PL, true> {  // pair-mode plans: mel_rows_kernel, 32-frame tiles, two bands per warp step
+    static constexpr int value = 2;
+};
+int MLXA_CAT(plan_group_, MLXA_NFFT)() { return -BankGroup<P, !PACK>::value; }
 // the fused per-frame statistics reduce with warp shuffles: plans whose groups fit a warp
 int MLXA_CAT(plan_fused_feature_, MLXA_NFFT)() { return P::G <= 32 ? 1 : 0; }
 

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
         __syncthreads();
 
         // ---- band-sparse projection, lanes along frames (mel_project.cuh) -----------------------------
-        project_power_tile<THREADS, TT, !BANK_SMEM>(p, rb, dbc, s_pw, TT, ti.b, ti.t0, nt, pscale, vmax);
+        project_power_tile<THREADS / 32, TT, !BANK_SMEM, true>(p, rb, dbc, s_pw, TT, ti.b, ti.t0, nt, pscale, warp, vmax);
         __syncthreads();  // power tile consumed: the next tile's transforms may reuse the buffers
     }
     if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red, p.xchg);

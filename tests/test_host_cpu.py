@@ -53,7 +53,7 @@ def test_host_constants_match_reference_fixtures(golden):
             # by GP adjacent bands, descriptors padded to a multiple of 32 bands, every run inside the F + 3 rows of
             # the power tile
             F = fb.shape[1]
-            for GP in (1, 2, 4, 8):
+            for GP in (1, 2, 4, 8, 20):
                 packed, n_wt = pack_bank_host(fb, -GP)
                 n_pad = -(-n_mels // 32) * 32
                 start, nq, off, ln = packed[n_wt:].view(np.int32).reshape(n_pad, 4).T
