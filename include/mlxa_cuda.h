@@ -153,19 +153,22 @@ int mlxa_istft_f32(const mlxa_c64* spec, int64_t B, int64_t T, int F_in, const f
                    const float* wss, int n_fft, int hop, int64_t ola_len, int64_t trim,
                    int64_t out_len, float* y, int64_t ldy, void* stream);
 
-/* Same kernel with the Griffin-Lim extrapolation (griffinlim.py:176-178) fused into its loader: the
- * spectrum that is inverted is spec + momentum*(spec - spec_prev).  spec_prev may be NULL when
- * momentum == 0.  Needs a compiled plan for n_fft (mlxa_has_fast_plan). */
-int mlxa_istft_extrap_f32(const mlxa_c64* spec, const mlxa_c64* spec_prev, float momentum,
-                          int64_t B, int64_t T, int F_in, const float* window, const float* wss,
-                          int n_fft, int hop, int64_t ola_len, int64_t trim, int64_t out_len,
-                          float* y, int64_t ldy, void* stream);
+/* Same kernel with Griffin-Lim's momentum step (griffinlim.py:176-178: rebuilt = new + m*(new - tprev),
+ * then istft(rebuilt)) applied in the SIGNAL domain -- the inverse STFT is linear:
+ *   u = istft(spec);  y = u + momentum*(u - u_prev)   (y = u when u_prev is NULL or momentum == 0).
+ * u_out (optional) receives u, the u_prev of the next iteration; u_prev, u_out and y are distinct (B, out_len)
+ * buffers of row stride ldy.  The previous projection is never read again (8*F*T bytes per clip saved for
+ * 8*L bytes of signal traffic).  Works for every n_fft (the O(n^2) path adds one small kernel). */
+int mlxa_istft_momentum_f32(const mlxa_c64* spec, const float* u_prev, float momentum, float* u_out,
+                            int64_t B, int64_t T, int F_in, const float* window, const float* wss,
+                            int n_fft, int hop, int64_t ola_len, int64_t trim, int64_t out_len,
+                            float* y, int64_t ldy, void* stream);
 
 /* One Griffin-Lim projection (griffinlim.py:143-169) fused into the STFT epilogue:
  *   X = stft(y); projected = mag * X/|X|  (mag + 0j where X == 0, i.e. angle 0).
  * mag and projected are (B, T, F); frames t >= T_valid see X = 0 (zero-padded frames,
  * griffinlim.py:159-165).  The momentum step rebuilt = new + m*(new - prev) is NOT materialised:
- * feed (projected, previous projected, m) to mlxa_istft_extrap_f32. */
+ * mlxa_istft_momentum_f32 applies it to the inverse transforms of the projections. */
 int mlxa_griffinlim_project_f32(const float* y, int64_t B, int64_t L, int64_t ldy,
                                 const float* window, int n_fft, int hop, int center,
                                 int pad_mode, int64_t T, int64_t T_valid, const float* mag,

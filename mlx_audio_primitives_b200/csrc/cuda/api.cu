@@ -352,26 +352,26 @@ int mlxa_griffinlim_project_f32(const float* y, int64_t B, int64_t L, int64_t ld
     });
 }
 
-static int istft_impl(const mlxa_c64* spec, const mlxa_c64* spec_prev, float momentum, int64_t B, int64_t T, int F_in,
+static int istft_impl(const mlxa_c64* spec, const float* u_prev, float momentum, float* u_out, int64_t B, int64_t T, int F_in,
                       const float* window, const float* wss, int n_fft, int hop, int64_t ola_len, int64_t trim,
                       int64_t out_len, float* y, int64_t ldy, void* stream);
 
 int mlxa_istft_f32(const mlxa_c64* spec, int64_t B, int64_t T, int F_in, const float* window, const float* wss,
                    int n_fft, int hop, int64_t ola_len, int64_t trim, int64_t out_len, float* y, int64_t ldy,
                    void* stream) {
-    return istft_impl(spec, nullptr, 0.f, B, T, F_in, window, wss, n_fft, hop, ola_len, trim, out_len, y, ldy, stream);
+    return istft_impl(spec, nullptr, 0.f, nullptr, B, T, F_in, window, wss, n_fft, hop, ola_len, trim, out_len, y, ldy, stream);
 }
 
-int mlxa_istft_extrap_f32(const mlxa_c64* spec, const mlxa_c64* spec_prev, float momentum, int64_t B, int64_t T,
-                          int F_in, const float* window, const float* wss, int n_fft, int hop, int64_t ola_len,
-                          int64_t trim, int64_t out_len, float* y, int64_t ldy, void* stream) {
-    CHECK_ARG(spec_prev || momentum == 0.f, "spec_prev required when momentum != 0");
-    return istft_impl(spec, spec_prev, momentum, B, T, F_in, window, wss, n_fft, hop, ola_len, trim, out_len, y, ldy, stream);
+int mlxa_istft_momentum_f32(const mlxa_c64* spec, const float* u_prev, float momentum, float* u_out, int64_t B, int64_t T,
+                            int F_in, const float* window, const float* wss, int n_fft, int hop, int64_t ola_len,
+                            int64_t trim, int64_t out_len, float* y, int64_t ldy, void* stream) {
+    CHECK_ARG(u_out != y && (u_prev == nullptr || (u_prev != y && u_prev != u_out)), "u_prev, u_out and y must be distinct buffers");
+    return istft_impl(spec, u_prev, momentum, u_out, B, T, F_in, window, wss, n_fft, hop, ola_len, trim, out_len, y, ldy, stream);
 }
 
 }  // extern "C"
 
-static int istft_impl(const mlxa_c64* spec, const mlxa_c64* spec_prev, float momentum, int64_t B, int64_t T, int F_in,
+static int istft_impl(const mlxa_c64* spec, const float* u_prev, float momentum, float* u_out, int64_t B, int64_t T, int F_in,
                       const float* window, const float* wss, int n_fft, int hop, int64_t ola_len, int64_t trim,
                       int64_t out_len, float* y, int64_t ldy, void* stream) {
     CHECK_ARG(spec && window && wss && y, "null pointer");
@@ -386,7 +386,8 @@ static int istft_impl(const mlxa_c64* spec, const mlxa_c64* spec_prev, float mom
             InvParams p;
             std::memset(&p, 0, sizeof(p));
             p.spec = reinterpret_cast<const float2*>(spec) + b0 * T * F_in;
-            p.spec_prev = (spec_prev && momentum != 0.f) ? reinterpret_cast<const float2*>(spec_prev) + b0 * T * F_in : nullptr;
+            p.u_prev = (u_prev && momentum != 0.f) ? u_prev + b0 * ldy : nullptr;
+            p.u_out = u_out ? u_out + b0 * ldy : nullptr;
             p.momentum = momentum;
             p.const_bulk = ((uintptr_t)window & 15) == 0;
             p.B = (int)nb; p.T = (int)T; p.F_in = F_in; p.n_fft = n_fft; p.hop = hop;
@@ -403,13 +404,15 @@ static int istft_impl(const mlxa_c64* spec, const mlxa_c64* spec_prev, float mom
             return 0;
         });
     }
-    // no compiled plan: O(n^2) inverse DFT into stream-ordered scratch, then the gather OLA
-    CHECK_ARG(!(spec_prev && momentum != 0.f), "fused extrapolation needs a compiled plan; combine the spectra first");
+    // no compiled plan: O(n^2) inverse DFT into stream-ordered scratch, then the gather OLA (+ the momentum step)
     float* frames = nullptr;
     CHECK_CUDA(cudaMallocAsync(&frames, sizeof(float) * (size_t)B * T * n_fft, s), "istft scratch");
     cudaError_t e = launch_irdft_naive(reinterpret_cast<const float2*>(spec), B * T, F_in, n_fft, t.tw_plan, frames, s);
-    if (e == cudaSuccess) e = run_ola(frames, window, B, T, n_fft, hop, ola_len, trim, out_len, ldy, y, s);
+    float* u = u_out ? u_out : y;
+    if (e == cudaSuccess) e = run_ola(frames, window, B, T, n_fft, hop, ola_len, trim, out_len, ldy, u, s);
     cudaFreeAsync(frames, s);
+    if (e == cudaSuccess && (u_out || (u_prev && momentum != 0.f)))
+        e = run_momentum(u, (momentum != 0.f) ? u_prev : nullptr, momentum, B, out_len, ldy, y, s);
     CHECK_CUDA(e, "istft (dft fallback)");
     return 0;
 }

@@ -12,9 +12,12 @@
 // (deterministic results).  The (B, T, n_fft) frame tensor of the reference
 // (stft.py:295 -> overlap_add.metal:16) never exists.
 //
-// Optionally the spectrum is formed on the fly as spec + momentum*(spec - spec_prev): the
-// Griffin-Lim extrapolation (griffinlim.py:176-178) fused into the loader, so the chain keeps
-// only the projected spectra in HBM.
+// Griffin-Lim's momentum extrapolation (griffinlim.py:176-178: rebuilt = new + m*(new - tprev), then
+// istft(rebuilt)) is applied in the SIGNAL domain: the inverse STFT is linear, so
+// istft(new + m*(new - tprev)) = u + m*(u - u_prev) with u = istft(new), u_prev = istft(tprev).  The kernel
+// writes u (for the next iteration) and y = u + m*(u - u_prev) from its normalise-and-store loop: the
+// previous projection (8*F*T bytes per clip) is never read again and the per-bin extrapolation arithmetic
+// disappears from the transform loop; the price is 8*L bytes per clip of signal traffic.
 #include "fft_plans_list.cuh"
 #include "params.cuh"
 
@@ -47,20 +50,12 @@ constexpr bool TW_SMEM = (TWP + TWU) * 8 <= 20 * 1024;
 
 constexpr int round_up4(int v) { return (v + 3) & ~3; }
 
-template <bool EXTRAP>
-MLXA_D float2 load_bin(const float2* __restrict__ X, const float2* __restrict__ Xp, int k, bool ok, float m) {
-    float2 a = make_float2(0.f, 0.f);
-    if (ok) {
-        a = __ldg(X + k);
-        if constexpr (EXTRAP) {
-            const float2 c = __ldg(Xp + k);
-            a = make_float2(fmaf(m, a.x - c.x, a.x), fmaf(m, a.y - c.y, a.y));
-        }
-    }
-    return a;
+MLXA_D float2 load_bin(const float2* __restrict__ X, int k, bool ok) {
+    return ok ? __ldg(X + k) : make_float2(0.f, 0.f);
 }
 
-template <bool EXTRAP>
+// FULLF: the spectra carry all N + 1 bins the plan reads (the usual case: no per-bin range checks)
+template <bool FULLF>
 __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TS = p.tile_hops * p.hop;
@@ -84,6 +79,11 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
         if (cbulk) bulk_copy_g2s(s_win, p.window, NFFT * 4, s_bar);
     }
     for (int i = threadIdx.x; i < TS; i += THREADS) s_acc[i] = 0.f;
+    if (p.u_prev != nullptr) {  // the previous inverse of this tile is read at the very end: pull its lines into L2 now
+        const long long j0 = max(0LL, o0 - p.trim), j1 = min(p.out_len, o0 + TS - p.trim);
+        const char* up = reinterpret_cast<const char*>(p.u_prev + (long long)b * p.ldy);
+        for (long long off = j0 * 4 + threadIdx.x * 128LL; off < j1 * 4; off += THREADS * 128LL) prefetch_l2(up + off);
+    }
     if (!cbulk)
         for (int i = threadIdx.x; i < NFFT; i += THREADS) s_win[i] = __ldg(p.window + i);
     const float2* tw_plan = TW_SMEM ? s_tw : p.tw_plan;
@@ -96,11 +96,13 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
     const int f_hi = (o_end > o0) ? int(min((long long)(p.T - 1), (o_end - 1) / p.hop)) : -1;
     __syncthreads();
     mbar_wait(s_bar, 0);
+    // the 1/N of the inverse transform rides on the staged window: the overlap-add is one packed FFMA per sample pair
+    for (int i = threadIdx.x; i < NFFT; i += THREADS) s_win[i] *= 1.0f / float(P::N);
+    __syncthreads();
 
     const int gi = threadIdx.x / P::G, g = threadIdx.x % P::G;
     float2* buf = s_buf + gi * P::BUF;
     const long long clip = (long long)b * p.T * p.F_in;
-    const float inv_n = 1.0f / float(P::N);
     const bool hop_even = (p.hop & 1) == 0;
 
     // PACK plans: the spectrum of a group's NEXT frame is fetched by per-lane async copies
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
     // read it, so the HBM latency of round r+1 hides behind the butterflies and the overlap-add of
     // round r; the previous-projection lines of the Griffin-Lim extrapolation are pulled into L2.
     constexpr int NSPEC = PACK ? P::N + 1 : 0;
-    [[maybe_unused]] const int kmax_c = min(p.F_in, NSPEC);
+    [[maybe_unused]] const int kmax_c = FULLF ? NSPEC : min(p.F_in, NSPEC);
     [[maybe_unused]] auto prefetch_frame = [&](int f) {
         if constexpr (PACK) {
             constexpr int NQ1 = ceil_div(NSPEC, P::G);
@@ -118,15 +120,11 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
                 constexpr int Q = decltype(q)::value;
                 const int k = g + Q * P::G;
                 if (Q + 1 < NQ1 || k < NSPEC) {
-                    if (k < kmax_c) cp_async8(buf + k, X + k);
+                    if (FULLF || k < kmax_c) cp_async8(buf + k, X + k);
                     else buf[k] = make_float2(0.f, 0.f);
                 }
             });
             cp_async_commit();
-            if constexpr (EXTRAP) {
-                const char* lp = reinterpret_cast<const char*>(p.spec_prev + fo);
-                for (int off = g * 128; off < kmax_c * 8 + 128; off += P::G * 128) prefetch_l2(lp + off);
-            }
         }
     };
     // frame of (round q, this group, slot `which` of a frame pair)
@@ -158,19 +156,6 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
             constexpr int NQ1 = ceil_div(N + 1, P::G), NQ2 = ceil_div(N / 2 + 1, P::G);
             static_assert(P::BUF >= N + 1, "exchange buffer must hold the Nyquist bin");
             cp_async_wait_all();
-            if constexpr (EXTRAP) {
-                if (va) {  // lane-owned bins: X + m*(X - X_prev) in place
-                    const float2* Xp = p.spec_prev + clip + (long long)fa * p.F_in;
-                    static_for<NQ1>([&](auto q) {
-                        constexpr int Q = decltype(q)::value;
-                        const int k = g + Q * P::G;
-                        if ((Q + 1 < NQ1 || k <= N) && k < kmax_c) {
-                            const float2 a = buf[k], c = __ldg(Xp + k);
-                            buf[k] = make_float2(fmaf(p.momentum, a.x - c.x, a.x), fmaf(p.momentum, a.y - c.y, a.y));
-                        }
-                    });
-                }
-            }
             group_sync<P::G>(gi);
             static_for<NQ2>([&](auto q) {
                 constexpr int Q = decltype(q)::value;
@@ -193,13 +178,12 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
             const bool vb = fb <= f_hi;
             const long long foa = clip + (long long)(va ? fa : 0) * p.F_in, fob = clip + (long long)(vb ? fb : 0) * p.F_in;
             const float2 *Xa = p.spec + foa, *Xb = p.spec + fob;
-            const float2 *Xpa = EXTRAP ? p.spec_prev + foa : nullptr, *Xpb = EXTRAP ? p.spec_prev + fob : nullptr;
             static_for<NQ>([&](auto q) {
                 constexpr int Q = decltype(q)::value;
                 const int k = g + Q * P::G;
                 if (Q + 1 < NQ || k <= N / 2) {
-                    float2 a = load_bin<EXTRAP>(Xa, Xpa, k, va && k < p.F_in, p.momentum);
-                    float2 c = load_bin<EXTRAP>(Xb, Xpb, k, vb && k < p.F_in, p.momentum);
+                    float2 a = load_bin(Xa, k, va && (FULLF || k < p.F_in));
+                    float2 c = load_bin(Xb, k, vb && (FULLF || k < p.F_in));
                     if ((Q == 0 && k == 0) || 2 * k == N) { a.y = 0.f; c.y = 0.f; }
                     buf[k] = make_float2(a.y + c.x, a.x - c.y);  // swap(Xa + i*Xb)
                     if (!(Q == 0 && k == 0) && 2 * k < N) buf[N - k] = make_float2(c.x - a.y, a.x + c.y);  // swap(conj Xa + i*conj Xb)
@@ -239,17 +223,13 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
                         float2* acc2 = reinterpret_cast<float2*>(s_acc + off);
                         const float2* w2 = reinterpret_cast<const float2*>(s_win);
                         pass_store_fn<P, P::NPASS - 1>(g, v, [&](int n, float2 val) {
-                            float2 a = acc2[n];
-                            const float2 w = w2[n];
-                            a.x = fmaf(w.x, val.y * inv_n, a.x);
-                            a.y = fmaf(w.y, val.x * inv_n, a.y);
-                            acc2[n] = a;
+                            acc2[n] = pfma(val.y, val.x, w2[n].x, w2[n].y, acc2[n]);  // samples 2n, 2n + 1 = (im, re) of the swapped inverse
                         });
                     } else {
                         pass_store_fn<P, P::NPASS - 1>(g, v, [&](int n, float2 val) {
                             const int q = off + 2 * n;
-                            if (q >= 0 && q < TS) s_acc[q] = fmaf(s_win[2 * n], val.y * inv_n, s_acc[q]);
-                            if (q + 1 >= 0 && q + 1 < TS) s_acc[q + 1] = fmaf(s_win[2 * n + 1], val.x * inv_n, s_acc[q + 1]);
+                            if (q >= 0 && q < TS) s_acc[q] = fmaf(s_win[2 * n], val.y, s_acc[q]);
+                            if (q + 1 >= 0 && q + 1 < TS) s_acc[q + 1] = fmaf(s_win[2 * n + 1], val.x, s_acc[q + 1]);
                         });
                     }
                 }
@@ -263,7 +243,7 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
                         pass_store_fn<P, P::NPASS - 1>(g, v, [&](int n, float2 val) {
                             const int q = off + n;
                             if (inside || (q >= 0 && q < TS))
-                                s_acc[q] = fmaf(s_win[n], (which ? val.x : val.y) * inv_n, s_acc[q]);
+                                s_acc[q] = fmaf(s_win[n], which ? val.x : val.y, s_acc[q]);
                         });
                     }
                 }
@@ -287,13 +267,71 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
         mbar_wait(s_bar, 1);
     }
     float* yb = p.y + (long long)b * p.ldy;
-    for (int i = threadIdx.x; i < TS; i += THREADS) {
-        const long long o = o0 + i;
-        const long long j = o - p.trim;
-        if (j < 0 || j >= p.out_len) continue;
+    const float* upb = p.u_prev ? p.u_prev + (long long)b * p.ldy : nullptr;
+    float* uob = p.u_out ? p.u_out + (long long)b * p.ldy : nullptr;
+    auto one = [&](int i, float up) {  // sample i of the tile: normalise, keep u, momentum step, store
+        const long long o = o0 + i, j = o - p.trim;
         float val = 0.f;
         if (o < p.ola_len) val = __fdividef(s_acc[i], fmaxf(wbulk ? s_wss[i] : __ldg(p.wss + o), 1e-8f));
+        if (uob) uob[j] = val;                                    // u = istft(spec), kept for the next call
+        if (upb) val = fmaf(p.momentum, val - up, val);           // y = u + m * (u - u_prev)
         yb[j] = val;
+    };
+    // 128-bit path: tile, trim and rows are multiples of four samples and the whole quad lies inside the output
+    const bool vec = ((TS | int(p.trim & 3) | int(p.ldy & 3)) & 3) == 0 && wbulk &&
+                     ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.u_prev) | reinterpret_cast<uintptr_t>(p.u_out)) & 15) == 0;
+    if (vec) {
+        constexpr int U = 4;  // quads per thread in flight (the u_prev reads are the only long-latency operation here)
+        for (int i0 = threadIdx.x * 4; i0 < TS; i0 += THREADS * 4 * U) {
+            float4 up[U];
+            bool full[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * THREADS * 4;
+                const long long j = o0 + i - p.trim;
+                full[u] = i < TS && j >= 0 && j + 3 < p.out_len && o0 + i + 3 < p.ola_len;
+                up[u] = (full[u] && upb) ? __ldg(reinterpret_cast<const float4*>(upb + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * THREADS * 4;
+                if (i >= TS) continue;
+                const long long j = o0 + i - p.trim;
+                if (full[u]) {
+                    const float4 a = *reinterpret_cast<const float4*>(s_acc + i), w = *reinterpret_cast<const float4*>(s_wss + i);
+                    float4 v = make_float4(__fdividef(a.x, fmaxf(w.x, 1e-8f)), __fdividef(a.y, fmaxf(w.y, 1e-8f)),
+                                           __fdividef(a.z, fmaxf(w.z, 1e-8f)), __fdividef(a.w, fmaxf(w.w, 1e-8f)));
+                    if (uob) *reinterpret_cast<float4*>(uob + j) = v;
+                    if (upb) {
+                        const float m = p.momentum;
+                        v = make_float4(fmaf(m, v.x - up[u].x, v.x), fmaf(m, v.y - up[u].y, v.y), fmaf(m, v.z - up[u].z, v.z),
+                                        fmaf(m, v.w - up[u].w, v.w));
+                    }
+                    *reinterpret_cast<float4*>(yb + j) = v;
+                } else {  // a quad that straddles the trim, the end of the signal or the end of the overlap-add
+                    for (int e = 0; e < 4; ++e) {
+                        const long long je = j + e;
+                        if (je >= 0 && je < p.out_len) one(i + e, upb ? __ldg(upb + je) : 0.f);
+                    }
+                }
+            }
+        }
+    } else {
+        constexpr int U = 4;
+        for (int i0 = threadIdx.x; i0 < TS; i0 += THREADS * U) {
+            float up[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * THREADS;
+                const long long j = o0 + i - p.trim;
+                ok[u] = i < TS && j >= 0 && j < p.out_len;
+                up[u] = (ok[u] && upb) ? __ldg(upb + j) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ok[u]) one(i0 + u * THREADS, up[u]);
+        }
     }
 }
 
@@ -351,7 +389,8 @@ cudaError_t MLXA_CAT(launch_inv_, MLXA_NFFT)(InvParams& p, cudaStream_t s) {
     const long long TS = (long long)TH * p.hop;
     dim3 grid((unsigned)((span + TS - 1) / TS), p.B);
     cudaError_t e;
-    if (p.spec_prev != nullptr && p.momentum != 0.f) {
+    constexpr int NSPEC_ALL = PACK ? P::N + 1 : P::N / 2 + 1;
+    if (p.F_in >= NSPEC_ALL) {
         e = cudaFuncSetAttribute(inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         inv_kernel<true><<<grid, THREADS, smem, s>>>(p);

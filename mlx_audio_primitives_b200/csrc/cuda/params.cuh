@@ -76,7 +76,8 @@ __host__ __device__ inline long long packed_bank_words(int n_bands, long long n_
 
 struct InvParams {
     const float2* spec;       // (B, T, F_in)
-    const float2* spec_prev;  // optional (B, T, F_in): the transform input is spec + momentum*(spec - spec_prev)
+    const float* u_prev;      // optional (B, out_len), stride ldy: y = u + momentum * (u - u_prev), u = istft(spec)
+    float* u_out;             // optional (B, out_len), stride ldy: receives u
     float momentum;
     int const_bulk;           // window pointer is 16-byte aligned -> bulk async copy
     int B, T, F_in;

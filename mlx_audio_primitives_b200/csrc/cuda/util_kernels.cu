@@ -106,6 +106,16 @@ __global__ void polar_kernel(const float* __restrict__ mag, const float* __restr
         out[i] = make_float2(m * c, m * s);
     }
 }
+// y = u + m * (u - u_prev) over (B, n) rows of stride ld (u_prev == nullptr: y = u): the signal-domain form of
+// Griffin-Lim's momentum step for transforms that do not fuse it into their store loop (the O(n^2) fallback)
+__global__ void momentum_kernel(const float* __restrict__ u, const float* __restrict__ u_prev, float m, long long B,
+                                long long n, long long ld, float* __restrict__ y) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B * n; i += (long long)gridDim.x * blockDim.x) {
+        const long long o = (i / n) * ld + i % n;
+        const float v = u[o];
+        y[o] = u_prev ? fmaf(m, v - u_prev[o], v) : v;
+    }
+}
 __global__ void fill_kernel(float* x, long long n, float v) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = v;
 }
@@ -500,6 +510,12 @@ cudaError_t run_phase(const float2* z, long long n, float* out, cudaStream_t s) 
 }
 cudaError_t run_polar(const float* mag, const float* ang, long long n, float2* out, cudaStream_t s) {
     polar_kernel<<<grid_for(n, kThreads), kThreads, 0, s>>>(mag, ang, n, out);
+    return cudaGetLastError();
+}
+cudaError_t run_momentum(const float* u, const float* u_prev, float m, long long B, long long n, long long ld, float* y,
+                         cudaStream_t s) {
+    if (u == y && u_prev == nullptr) return cudaSuccess;
+    momentum_kernel<<<grid_for(B * n, kThreads), kThreads, 0, s>>>(u, u_prev, m, B, n, ld, y);
     return cudaGetLastError();
 }
 cudaError_t run_fill(float* x, long long n, float v, cudaStream_t s) {

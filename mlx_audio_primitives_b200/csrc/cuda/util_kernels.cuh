@@ -12,6 +12,8 @@ cudaError_t run_magnitude(const float2* z, long long n, float* out, cudaStream_t
 cudaError_t run_phase(const float2* z, long long n, float* out, cudaStream_t s);
 cudaError_t run_polar(const float* mag, const float* ang, long long n, float2* out, cudaStream_t s);
 cudaError_t run_fill(float* x, long long n, float v, cudaStream_t s);
+cudaError_t run_momentum(const float* u, const float* u_prev, float m, long long B, long long n, long long ld, float* y,
+                         cudaStream_t s);
 cudaError_t run_transpose_f32(const float* in, long long B, long long R, long long C, float* out, cudaStream_t s);
 cudaError_t run_transpose_c64(const float2* in, long long B, long long R, long long C, float2* out, cudaStream_t s);
 cudaError_t run_max(const float* x, long long n, float* gmax, cudaStream_t s);

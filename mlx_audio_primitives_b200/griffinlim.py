@@ -9,7 +9,7 @@ from ._extension import _ext, check
 from ._tensor import f32c, ptr, stream_ptr
 from ._validation import validate_positive, validate_range
 from .mel import frames_or_raise, pad_mode_code
-from .stft import _istft_physical, istft, magnitude, phase, stft
+from .stft import _istft_geometry, _istft_physical, istft, magnitude, phase, stft
 from .windows import padded_window
 
 
@@ -74,28 +74,32 @@ def griffinlim(S, n_iter: int = 32, hop_length: int | None = None, win_length: i
     win = padded_window(window, win_length, n_fft)
     mag = _to_physical_f32(S)                 # (B, T, F)
     ang = _to_physical_f32(angles)
-    # Only the PROJECTED spectra live in HBM (two ping-pong buffers); the momentum extrapolation
-    # rebuilt = new + m*(new - prev) is formed inside the inverse transform's loader.
+    # One projected spectrum lives in HBM.  The momentum extrapolation rebuilt = new + m*(new - tprev) is taken
+    # through the (linear) inverse transform: istft(rebuilt) = u + m*(u - u_prev) with u = istft(new), so each
+    # iteration keeps the previous inverse (a signal) instead of the previous projection (a spectrum).
     cur = torch.empty((B, T, F, 2), dtype=torch.float32, device=S.device)
     check(_ext.mlxa_polar_f32(ptr(mag), ptr(ang), mag.numel(), ptr(cur), stream_ptr(S)), "polar")
     del ang, angles
-    prev = cur  # tprev = rebuilt at the start (reference griffinlim.py:126)
-    y = None
-    for _ in range(n_iter):
-        y = _istft_physical(torch.view_as_complex(cur), n_fft, hop_length, win, center, length, out=y,
-                            prev=torch.view_as_complex(prev) if prev is not cur else None, momentum=momentum)
+    spec = torch.view_as_complex(cur)
+    y = u = u_prev = None
+    for it in range(n_iter + 1):  # n_iter projections, n_iter + 1 inverse transforms (reference griffinlim.py:129-183)
+        if momentum > 0:
+            if u is None:
+                ola_len, trim, out_len = _istft_geometry(T, n_fft, hop_length, center, length)
+                u, spare = (torch.empty((B, max(out_len, 0)), dtype=torch.float32, device=S.device) for _ in range(2))
+            else:
+                u_prev, u = u, (spare if u_prev is None else u_prev)  # tprev of the first update is the initial spectrum
+            y = _istft_physical(spec, n_fft, hop_length, win, center, length, out=y, u_prev=u_prev if it > 0 else None,
+                                momentum=momentum, u_out=u)
+        else:
+            y = _istft_physical(spec, n_fft, hop_length, win, center, length, out=y)
+        if it == n_iter:
+            break
         L = y.shape[1]
         T_new = frames_or_raise(L, n_fft, hop_length, center, pad_mode)
-        if momentum > 0:  # the older projection is dead once the inverse transform has consumed it
-            dst = prev if prev is not cur else torch.empty_like(cur)
-        else:
-            dst = cur
         check(_ext.mlxa_griffinlim_project_f32(ptr(y), B, L, y.stride(0), ptr(win), n_fft, hop_length, int(center),
-                                               mode, T, min(T, T_new), ptr(mag), ptr(dst), stream_ptr(S)),
+                                               mode, T, min(T, T_new), ptr(mag), ptr(cur), stream_ptr(S)),
               "griffinlim")
-        prev, cur = (cur, dst) if momentum > 0 else (cur, cur)
-    y = _istft_physical(torch.view_as_complex(cur), n_fft, hop_length, win, center, length, out=y,
-                        prev=torch.view_as_complex(prev) if prev is not cur else None, momentum=momentum)
     return y if batched else y[0]
 
 

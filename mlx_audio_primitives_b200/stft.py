@@ -97,10 +97,11 @@ def _istft_geometry(T: int, n_fft: int, hop: int, center: bool, length):
 
 
 def _istft_physical(P: torch.Tensor, n_fft: int, hop: int, win: torch.Tensor, center: bool, length,
-                    out: torch.Tensor | None = None, prev: torch.Tensor | None = None,
-                    momentum: float = 0.0) -> torch.Tensor:
-    """physical (B, T, F_in) complex64 -> (B, out_len) float32.  With ``prev`` the inverted spectrum is
-    P + momentum*(P - prev), formed inside the kernel's loader."""
+                    out: torch.Tensor | None = None, u_prev: torch.Tensor | None = None,
+                    momentum: float = 0.0, u_out: torch.Tensor | None = None) -> torch.Tensor:
+    """physical (B, T, F_in) complex64 -> (B, out_len) float32.  With ``u_out`` / ``u_prev`` (Griffin-Lim) the
+    kernel also stores u = istft(P) and returns u + momentum*(u - u_prev): the momentum step of
+    griffinlim.py:176-178 taken through the (linear) inverse transform."""
     B, T, F_in = P.shape
     ola_len, trim, out_len = _istft_geometry(T, n_fft, hop, center, length)
     if out_len <= 0 or ola_len <= 0:
@@ -108,12 +109,11 @@ def _istft_physical(P: torch.Tensor, n_fft: int, hop: int, win: torch.Tensor, ce
     wss = _window_sumsquare(win, n_fft, hop, T, ola_len)
     if out is None:
         out = torch.empty((B, out_len), dtype=torch.float32, device=P.device)
-    if prev is not None and momentum != 0.0 and _ext.mlxa_has_fast_plan(n_fft):
-        check(_ext.mlxa_istft_extrap_f32(ptr(P), ptr(prev), float(momentum), B, T, F_in, ptr(win), ptr(wss), n_fft, hop,
-                                         ola_len, trim, out_len, ptr(out), out.stride(0), stream_ptr(P)), "istft")
+    if u_out is not None or (u_prev is not None and momentum != 0.0):
+        check(_ext.mlxa_istft_momentum_f32(ptr(P), ptr(u_prev), float(momentum), ptr(u_out), B, T, F_in, ptr(win), ptr(wss),
+                                           n_fft, hop, ola_len, trim, out_len, ptr(out), out.stride(0), stream_ptr(P)),
+              "istft")
         return out
-    if prev is not None and momentum != 0.0:  # no compiled plan for this n_fft: combine first
-        P = torch.view_as_complex(torch.view_as_real(P) * (1.0 + momentum) - torch.view_as_real(prev) * momentum)
     check(_ext.mlxa_istft_f32(ptr(P), B, T, F_in, ptr(win), ptr(wss), n_fft, hop, ola_len, trim, out_len,
                               ptr(out), out.stride(0), stream_ptr(P)), "istft")
     return out
