@@ -10,6 +10,10 @@ one-float all-reduce(MAX) that top_db's batch-global max needs.
 Metric: audio-seconds per second.  `value` times the step with inputs resident in HBM;
 `e2e` times the same step through the C-ABI host-buffer entry point (pinned host in, host out).
 `--impl reference` times the CPU restatement of the reference path (oracle/) on the host cores.
+The same line also carries `configs` (one row per other BASELINE.json config: c1 stft+istft, c3 music mel +
+dB(ref=max) at 128 clips per GPU -- the 1024-clip batch at 8 GPUs --, c4 MFCC at 256 clips, c5 Griffin-Lim),
+`sustained` (the headline step looped for >= 2 s with its own clock record) and, under torchrun,
+`sharded_parity` (every rank's shard bit-equal to the unsharded public API fed the batch-global peak).
 """
 from __future__ import annotations
 
@@ -99,26 +103,30 @@ def cpu_baseline(w, threads, clips):
 
 
 def run_reference_arm(args, w):
+    """The reference's CPU path (float32 restatement; MLX is not installable here) on this host's cores: the full
+    batch per step, exactly --steps timed steps after --warmup untimed ones.  Under torchrun rank 0 alone runs it:
+    the number describes ONE host, whatever --gpus says."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     L = int(w["sr"] * w["seconds"])
-    clips = min(w["clips"], 16)  # bounded sample per step
+    clips = w["clips"]
     y = synth_clips_np(clips, L, w["sr"])
-    for _ in range(max(1, min(args.warmup, 2))):
+    warm, steps = max(0, args.warmup), max(1, args.steps)
+    for _ in range(warm):
         cpu_reference_pass(y, w, threads)
-    steps = max(1, min(args.steps, 5))
     t = [cpu_reference_pass(y, w, threads)[0] for _ in range(steps)]
     dt = sum(t) / len(t)
     val = clips * w["seconds"] / dt
     line = {"impl": "reference", "metric": "audio-seconds per second, log-mel", "value": val, "unit": "audio-s/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["label"], "sample_clips_per_step": clips},
+            "config": {"workload": w["label"], "clips_per_step": clips,
+                       "scope": "one CPU process on rank 0 using every host core; the same number whatever --gpus is"},
             "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                             "sample": f"{clips} clips x {w['seconds']:.0f} s per step (bounded sample of the "
-                                       f"{w['clips']}-clip batch), float32 restatement of the reference CPU path"},
+                             "sample": f"{clips} clips x {w['seconds']:.0f} s per step (the full per-GPU batch), float32 "
+                                       f"NumPy/pocketfft restatement of the reference CPU path (MLX not installable)"},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -208,6 +216,8 @@ def main():
     ap_.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap_.add_argument("--e2e-steps", type=int, default=10)
     ap_.add_argument("--no-cpu-baseline", action="store_true")
+    ap_.add_argument("--no-configs", action="store_true", help="skip the rows of the other BASELINE configs")
+    ap_.add_argument("--sustained-seconds", type=float, default=2.0, help="0 skips the sustained loop")
     args = ap_.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -254,6 +264,39 @@ def main():
             ev[1].record()
         plan.db(out)
         return out
+
+    # ---- sharded parity on the record (world > 1): the ranks hold clips of DIFFERENT levels, so a rank that used
+    # its local peak for top_db would get other bits.  Expected shard = the unsharded public API
+    # (melspectrogram -> power_to_db, reference convert.py:42-58) over this rank's clips plus one extra row that
+    # carries the batch-global peak of the raw mel values (gathered over NCCL). -------------------------------
+    sharded_parity = None
+    if world > 1:
+        yp = ys[0][:8] * (10.0 ** (-3.0 + 3.0 * rank / (world - 1)))
+        plan_p = ap.LogMelPlan(yp.shape[0], L, sr=sr, n_fft=w["n_fft"], hop_length=w["hop"], n_mels=w["n_mels"],
+                               ref=1.0, amin=1e-10, top_db=80.0)
+        got = [plan_p(yp).clone() for _ in range(2)][-1]
+        ap.distributed.disable()
+        mel = ap.melspectrogram(yp, sr=sr, n_fft=w["n_fft"], hop_length=w["hop"], n_mels=w["n_mels"])
+        peaks = [torch.zeros(1, device=dev) for _ in range(world)]
+        dist.all_gather(peaks, mel.max().reshape(1))
+        gpeak = torch.stack(peaks).max()
+        want = ap.power_to_db(torch.cat([mel, gpeak.expand(1, mel.shape[1], mel.shape[2])]), ref=1.0, amin=1e-10,
+                              top_db=80.0)[:-1]
+        local_only = ap.power_to_db(mel, ref=1.0, amin=1e-10, top_db=80.0)
+        ap.distributed.enable()
+        flag = torch.tensor([1.0 if torch.equal(got, want) else 0.0,
+                             1.0 if torch.equal(local_only, want) else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        sharded_parity = {"bit_equal_on_every_rank": bool(flag[0].item() == 1.0),
+                          "test_is_sensitive": bool(flag[1].item() == 0.0),  # some rank's local-peak result differs
+                          "clips_per_rank": int(yp.shape[0]), "levels": "1e-3 .. 1 across ranks",
+                          "exchange": "peer memory" if plan_p.xchg is not None else "NCCL all-reduce"}
+        del plan_p, got, want, mel, local_only
+        if not sharded_parity["bit_equal_on_every_rank"]:
+            if rank == 0:
+                emit({"error": "sharded parity failed", "sharded_parity": sharded_parity})
+            dist.destroy_process_group()
+            sys.exit(1)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -310,6 +353,39 @@ def main():
     torch.cuda.synchronize()
     e2e_match = bool(torch.equal(ref_out.cpu(), oh)) if world == 1 else None  # N>1: resident path uses the global peak
 
+    # ---- sustained: the same step looped for >= 2 s (a burst of 20 steps runs at boost clocks; this is what a
+    # serving loop gets), with its own clock record ----------------------------------------------------------
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_sus = max(K, int(args.sustained_seconds / (ms_step * 1e-3)) + 1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts0 = time.perf_counter()
+        s0.record()
+        for i in range(n_sus):
+            step(i)
+        s1.record()
+        torch.cuda.synchronize()
+        ts1 = time.perf_counter()
+        tt = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sus_ms = float(tt.item()) / n_sus
+        sustained = {"steps": n_sus, "seconds": float(tt.item()) * 1e-3, "ms_per_step": sus_ms,
+                     "value": audio_s / (sus_ms * 1e-3), "unit": "audio-s/s",
+                     "clocks": sampler.summary(ts0, ts1) if sampler else None}
+
+    # ---- the other BASELINE configs, through the public API (tools/bench_configs.py) ------------------------
+    config_rows = None
+    if not args.no_configs:
+        del ys, outs, yh, oh
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        config_rows = bench_configs.collect(["c1", "c3", "c4", "c5"], iters=10)
+
     if sampler:
         sampler.stop()
 
@@ -354,7 +430,9 @@ def main():
                 "frac_of_roofline_time": max(bytes_clip * B / (hbm_peak * 1e9), flops_clip * B / (fp32_measured * 1e12)) * 1e3 / k_ms}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            roofline["traffic"] = json.load(f).get(args.workload)
+            tj = json.load(f)
+        roofline["traffic"] = tj.get(args.workload)
+        roofline["traffic_source"] = tj.get("_source")  # an ncu --set full capture of this kernel (a profiler cannot run inside the bench)
     except Exception:
         pass
 
@@ -373,7 +451,10 @@ def main():
                     "api": "LogMelPlan.run_host -> mlxa_logmel_host_f32 (pinned host in/out, chunked copy/compute overlap)",
                     "matches_resident_path": e2e_match},
             "gpu_launches": K * plan.kernel_launches_per_call,
-            "clocks": sampler.summary(t_start, t_end) if sampler else None}
+            "clocks": sampler.summary(t_start, t_end) if sampler else None,
+            "sustained": sustained, "configs": config_rows}
+    if sharded_parity is not None:
+        line["sharded_parity"] = sharded_parity
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(w, os.cpu_count() or 1, min(B, 64))
     emit(line)

@@ -67,6 +67,9 @@ def timed(fn, iters, warm=3):
     return ms
 
 
+_ROWS = None  # collect() gathers the rows here instead of printing them
+
+
 def report(name, label, audio_s, ms, bytes_, flops, extra=None):
     # under torchrun every rank holds the same share (weak scaling): whole-job units over the slowest rank's time
     audio_s, bytes_, flops = audio_s * WORLD, bytes_ * WORLD, flops * WORLD
@@ -79,7 +82,36 @@ def report(name, label, audio_s, ms, bytes_, flops, extra=None):
             "achieved_GBs": bytes_ / (ms * 1e-3) / 1e9, "achieved_TFLOPs": flops / (ms * 1e-3) / 1e12}
     if extra:
         line.update(extra)
-    print(json.dumps(line), flush=True)
+    if _ROWS is not None:
+        _ROWS.append(line)
+    else:
+        print(json.dumps(line), flush=True)
+
+
+def event_ms(fn, iters):
+    """mean device time of fn() over iters calls (CUDA events on the current stream, after warm-up)."""
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def collect(configs, iters=20, clips_scale=1.0):
+    """The rows of `configs` as dicts (bench.py puts them into its JSON line).  The process group, if any, is the
+    caller's: under torchrun every rank must call this."""
+    global _ROWS
+    _ROWS = []
+    try:
+        run(configs, iters, clips_scale)
+        return _ROWS
+    finally:
+        _ROWS = None
 
 
 def main():
@@ -92,8 +124,14 @@ def main():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
         ap.distributed.enable()
-    want = args.configs.split(",")
-    sc = args.clips_scale
+    run(args.configs.split(","), args.iters, args.clips_scale)
+
+
+def run(want, iters, sc):
+    class _A:
+        pass
+    args = _A()
+    args.iters = iters
 
     if "c1" in want:  # stft + istft round trip, 1 x 10 s @ 22.05 kHz, 2048/512
         L, N, hop = 220500, 2048, 512
@@ -107,7 +145,9 @@ def main():
         by = (4 * L + 8 * F * T) * 2
         fl = T * (2 * fft_flops(N) + N + 4 * N)
         report("c1", "stft+istft 2048/512 hann 1x10 s @22.05k", 10.0, ms_f + ms_i, by, fl,
-               {"ms_stft": ms_f, "ms_istft": ms_i, "round_trip_max_err": err})
+               {"ms_stft": ms_f, "ms_istft": ms_i, "round_trip_max_err": err, "clips": 1,
+                "kernel": "fwd_kernel<EP_STFT> + inv_kernel n_fft=2048 (one launch each; launch/latency bound: 432 frames)",
+                "kernel_ms": ms_f + ms_i})
     if "c2" in want:
         B, L = max(1, int(64 * sc)), 480000
         y = clips(B, L, 16000)
@@ -117,32 +157,61 @@ def main():
         report("c2", f"log-mel 16k 400/160 80 mels {B}x30 s", B * 30.0, ms, B * (4 * L + 4 * 80 * T),
                B * T * (fft_flops(400) + 400 + 7 * F + 3 * 80))
     if "c3" in want:
-        B, L = max(1, int(1024 * sc * 0.125)), 661500  # one GPU's share of the 8-GPU batch by default
+        # BASELINE configs[2]: 1024 x 30 s sharded over 8 GPUs = 128 clips per GPU; under torchrun every rank owns 128
+        # clips and the batch-global peak of ref=max crosses the GPUs (peer-memory exchange / NCCL)
+        B, L = max(1, int(1024 * sc * 0.125)), 661500
         y = clips(B, L, 22050)
         fn = lambda: ap.power_to_db(ap.melspectrogram(y, sr=22050, n_fft=2048, hop_length=512, n_mels=128), ref=torch.max)
         ms = timed(fn, args.iters)
+        plan = ap.LogMelPlan(B, L, sr=22050, n_fft=2048, hop_length=512, n_mels=128, ref="max", top_db=80.0)
+        out = plan.empty_output()
+        def both():
+            plan.mel(y, out); plan.db(out)
+        both(); both()
+        k_ms = event_ms(lambda: plan.mel(y, out), 5) if WORLD == 1 else None  # (alone only without the exchange's pairing)
+        if WORLD > 1:
+            both()
         T, F = 1 + L // 512, 1025
-        report("c3", f"mel+power_to_db(ref=max) 22.05k 2048/512 128 mels {B}x30 s", B * 30.0, ms,
-               B * (4 * L + 4 * 128 * T), B * T * (fft_flops(2048) + 2048 + 7 * F + 3 * 128))
+        report("c3", f"mel+power_to_db(ref=max) 22.05k 2048/512 128 mels {B}x30 s per GPU", B * 30.0, ms,
+               B * (4 * L + 4 * 128 * T), B * T * (fft_flops(2048) + 2048 + 7 * F + 3 * 128),
+               {"clips": B * WORLD, "kernel": "fwd_kernel<EP_MEL> n_fft=2048", "kernel_ms": k_ms})
+        del plan, out
     if "c4" in want:
-        B, L = max(1, int(256 * sc * 0.25)), 2646000  # 64 clips by default (0.68 GB input)
+        B, L = max(1, int(256 * sc)), 2646000  # BASELINE configs[3]: 256 x 60 s (2.7 GB of input per GPU)
         y = clips(B, L, 44100)
         fn = lambda: ap.mfcc(y, sr=44100, n_mfcc=40, n_fft=4096, hop_length=1024)
-        ms = timed(fn, args.iters)
+        ms = timed(fn, max(3, args.iters // 2))
+        k_ms = event_ms(lambda: ap.melspectrogram(y, sr=44100, n_fft=4096, hop_length=1024), 3)
         T, F = 1 + L // 1024, 2049
-        report("c4", f"MFCC-40 44.1k 4096/1024 128 mels {B}x60 s", B * 60.0, ms, B * (4 * L + 4 * 40 * T),
-               B * T * (fft_flops(4096) + 4096 + 7 * F + 3 * 128 + 2 * 128 * 40))
+        report("c4", f"MFCC-40 44.1k 4096/1024 128 mels {B}x60 s per GPU", B * 60.0, ms, B * (4 * L + 4 * 40 * T),
+               B * T * (fft_flops(4096) + 4096 + 7 * F + 3 * 128 + 2 * 128 * 40),
+               {"clips": B * WORLD, "kernel": "fwd_kernel<EP_MEL> n_fft=4096 (melspectrogram alone; mfcc adds mfcc_tail_kernel)",
+                "kernel_ms": k_ms})
+        del y
+        torch.cuda.empty_cache()
     if "c5" in want:
         B, L, N, hop, iters = max(1, int(128 * sc)), 220500, 1024, 256, 32
         y = clips(B, L, 22050)
-        S = ap.magnitude(ap.stft(y, N, hop))
+        Sc = ap.stft(y, N, hop)
+        S = ap.magnitude(Sc)
         fn = lambda: ap.griffinlim(S, n_iter=iters, hop_length=hop, random_state=0)
         ms = timed(fn, max(2, args.iters // 5), warm=1)
         T, F = S.shape[-1], N // 2 + 1
-        per_it = 8 * F * T + 4 * L + 4 * L + 4 * F * T + 8 * F * T + 16 * F * T
-        by = B * (iters * per_it + 8 * F * T + 4 * L)
+        # dominant kernel: the inverse transform with the signal-domain momentum step (one launch of 33 per call)
+        from mlx_audio_primitives_b200.stft import _istft_physical, _spectrum_physical
+        from mlx_audio_primitives_b200.windows import padded_window
+        win = padded_window("hann", N, N)
+        P = _spectrum_physical(Sc)
+        u0, u1, yy = (torch.empty((B, L), device="cuda") for _ in range(3))
+        k_ms = event_ms(lambda: _istft_physical(P, N, hop, win, True, None, out=yy, u_prev=u0, momentum=0.99, u_out=u1), 5)
+        # per iteration: inverse reads 8FT + 4L (previous inverse), writes 8L; projection reads 4L + 4FT, writes 8FT
+        per_it = 8 * F * T + 4 * L + 8 * L + 4 * L + 4 * F * T + 8 * F * T
+        by = B * (iters * per_it + 8 * F * T + 12 * L)
         fl = B * T * (iters * (2 * fft_flops(N) + N + 4 * N + 40 * F) + fft_flops(N) + 4 * N)
-        report("c5", f"Griffin-Lim 32 it 1024/256 {B}x10 s @22.05k (incl. host RNG init + upload)", B * 10.0, ms, by, fl)
+        report("c5", f"Griffin-Lim 32 it 1024/256 {B}x10 s @22.05k (device RNG init included)", B * 10.0, ms, by, fl,
+               {"clips": B, "kernel": "inv_kernel n_fft=1024 (momentum form; 33 launches per call, 32 x fwd_kernel<EP_GL> beside them)",
+                "kernel_ms": k_ms, "kernel_alg_bytes": B * (8 * F * T + 12 * L)})
+        del y, Sc, S, P, u0, u1, yy
     if "f1" in want:  # section 8(f) rank 1: the four spectral features of a music batch (C3's shape), from audio
         B, L, N, hop = max(1, int(1024 * sc * 0.125)), 661500, 2048, 512
         y = clips(B, L, 22050)
