@@ -24,6 +24,31 @@ from . import distributed
 
 __version__ = "0.1.0"
 
+
+def _scope_entry_points():
+    """Every array-taking entry point runs on the device of its input (``_tensor.on_input_device``); the wrapped
+    function replaces the plain one in its home module too, so ``from mlx_audio_primitives_b200.stft import stft``
+    gets the same behaviour."""
+    import sys
+    from ._tensor import on_input_device
+    names = ["stft", "istft", "magnitude", "phase", "melspectrogram", "power_to_db", "amplitude_to_db", "db_to_power",
+             "db_to_amplitude", "dct", "mfcc", "griffinlim", "griffinlim_iter", "frame", "pad_signal", "overlap_add",
+             "spectral_centroid", "spectral_bandwidth", "spectral_rolloff", "spectral_flatness", "spectral_contrast",
+             "zero_crossing_rate", "rms", "preemphasis", "delta", "pitch_detect_acf", "autocorrelation", "periodicity",
+             "deemphasis", "resample", "resample_poly"]
+    pkg = sys.modules[__name__]
+    for name in names:
+        fn = getattr(pkg, name)
+        wrapped = on_input_device(fn)
+        setattr(pkg, name, wrapped)
+        home = sys.modules.get(fn.__module__)
+        if home is not None and getattr(home, name, None) is fn:
+            setattr(home, name, wrapped)
+
+
+_scope_entry_points()
+del _scope_entry_points
+
 __all__ = [
     "stft", "istft", "magnitude", "phase", "check_nola", "get_window",
     "mel_filterbank", "melspectrogram", "hz_to_mel", "mel_to_hz",

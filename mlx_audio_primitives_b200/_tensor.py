@@ -1,6 +1,8 @@
 """PyTorch / DLPack plumbing: device tensors in, raw pointers to the C ABI, current stream."""
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 import torch
 
@@ -26,6 +28,23 @@ def to_tensor(x, dtype=None, device=None) -> torch.Tensor:
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t
+
+
+def on_input_device(fn):
+    """Run a public entry point with the CUDA device of its first CUDA-tensor argument current.  The C ABI launches
+    on the current device and the constant caches (windows, filterbanks, twiddles) are keyed on it, so an input on
+    cuda:1 while cuda:0 is current would otherwise mix a device-1 stream with device-0 launches and constants
+    (PyTorch ops handle that case transparently; so do these).  Host inputs go to the current device."""
+    @functools.wraps(fn)
+    def scoped(*args, **kwargs):
+        for a in (*args, *kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.device.type == "cuda":
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return scoped
 
 
 def f32c(x) -> torch.Tensor:

@@ -441,15 +441,19 @@ int mlxa_phase_f32(const mlxa_c64* z, int64_t n, float* out, void* stream) {
     return 0;
 }
 int mlxa_transpose_f32(const float* in, int64_t B, int64_t R, int64_t C, float* out, void* stream) {
-    CHECK_ARG(in && out && B > 0 && R > 0 && C > 0 && B <= 65535, "bad argument");
-    CHECK_CUDA(run_transpose_f32(in, B, R, C, out, (cudaStream_t)stream), "transpose");
-    return 0;
+    CHECK_ARG(in && out && B > 0 && R > 0 && C > 0, "bad argument");
+    return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {  // the batch rides on grid.z: slabs of <= 65535
+        CHECK_CUDA(run_transpose_f32(in + b0 * R * C, nb, R, C, out + b0 * R * C, (cudaStream_t)stream), "transpose");
+        return 0;
+    });
 }
 int mlxa_transpose_c64(const mlxa_c64* in, int64_t B, int64_t R, int64_t C, mlxa_c64* out, void* stream) {
-    CHECK_ARG(in && out && B > 0 && R > 0 && C > 0 && B <= 65535, "bad argument");
-    CHECK_CUDA(run_transpose_c64(reinterpret_cast<const float2*>(in), B, R, C, reinterpret_cast<float2*>(out),
-                                 (cudaStream_t)stream), "transpose");
-    return 0;
+    CHECK_ARG(in && out && B > 0 && R > 0 && C > 0, "bad argument");
+    return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {
+        CHECK_CUDA(run_transpose_c64(reinterpret_cast<const float2*>(in) + b0 * R * C, nb, R, C,
+                                     reinterpret_cast<float2*>(out) + b0 * R * C, (cudaStream_t)stream), "transpose");
+        return 0;
+    });
 }
 int mlxa_max_f32(const float* x, int64_t n, float* gmax, void* stream) {
     CHECK_ARG(x && gmax && n > 0, "bad argument");

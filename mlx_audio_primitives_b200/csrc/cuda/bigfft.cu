@@ -255,17 +255,24 @@ long long pow2_at_least(long long v) {
 
 cudaError_t cache_get(int kind, long long n, cudaStream_t s, float2** out);
 
+// Every table is complete (stream synchronised) before its pointer is published in the cache: another stream or
+// thread that hits the entry later may read it without an event.  Built once per (device, kind, length).
 cudaError_t cache_build(int kind, long long n, cudaStream_t s, float2** out) {
     cudaError_t e;
-    if (kind == 0) {  // roots of unity of order n
+    *out = nullptr;
+    auto fail = [&](cudaError_t err, float2* tmp) {
+        if (*out) cudaFree(*out);
+        if (tmp) cudaFree(tmp);
+        *out = nullptr;
+        return err;
+    };
+    if (kind == 0 || kind == 1) {  // roots of unity of order n / chirp of length n
         if ((e = cudaMalloc(out, size_t(n) * 8)) != cudaSuccess) return e;
-        root_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(*out, n);
-        return cudaGetLastError();
-    }
-    if (kind == 1) {  // chirp of length n
-        if ((e = cudaMalloc(out, size_t(n) * 8)) != cudaSuccess) return e;
-        chirp_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(*out, n);
-        return cudaGetLastError();
+        if (kind == 0) root_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(*out, n);
+        else chirp_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(*out, n);
+        if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, nullptr);
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, nullptr);
+        return cudaSuccess;
     }
     // kind 2 / 3: FFT_M of the wrapped chirp / of its conjugate
     const long long M = pow2_at_least(2 * n - 1);
@@ -273,13 +280,14 @@ cudaError_t cache_build(int kind, long long n, cudaStream_t s, float2** out) {
     if ((e = cache_get(1, n, s, &w)) != cudaSuccess) return e;
     if ((e = cache_get(0, M, s, &W)) != cudaSuccess) return e;
     if ((e = cudaMalloc(out, size_t(M) * 8)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&tmp, size_t(M) * 8)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&tmp, size_t(M) * 8)) != cudaSuccess) return fail(e, nullptr);
     chirp_wrap_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(w, n, M, kind == 3, *out);
-    if ((e = bigfft(*out, tmp, M, 1, W, IN_PLAIN, OUT_PLAIN, PassIO{}, s, &res)) != cudaSuccess) return e;
+    if ((e = bigfft(*out, tmp, M, 1, W, IN_PLAIN, OUT_PLAIN, PassIO{}, s, &res)) != cudaSuccess) return fail(e, tmp);
     if (res != *out) e = cudaMemcpyAsync(*out, res, size_t(M) * 8, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fail(e, tmp);
     cudaFree(tmp);
-    return e;
+    return cudaSuccess;
 }
 
 cudaError_t cache_get(int kind, long long n, cudaStream_t s, float2** out) {  // g_mu held by the caller

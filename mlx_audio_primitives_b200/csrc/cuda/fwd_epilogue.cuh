@@ -276,16 +276,20 @@ MLXA_D void peak_publish(const PeakExchange& x, float* gmax, unsigned n_ctas) {
     const unsigned long long v = ((unsigned long long)x.epoch << 32) | (unsigned)__float_as_int(peak);
     for (int r = 0; r < x.world; ++r) st_relaxed_sys_u64(x.peer_slots[r] + (x.epoch & 1u) * x.world + x.rank, v);
 }
-// any thread of a consumer kernel: the maximum over all ranks (spins until every rank has published this
-// epoch; a rank that never arrives traps instead of hanging the GPU)
+// any thread of a consumer kernel: the maximum over all ranks.  Waits like a collective would: a slow rank (a
+// stalled data loader, a first-call module load) only delays the others.  The poll backs off to ~1 us; a peer
+// that never publishes (a dead rank) ends the wait after ~2 minutes with a trap, as a hung NCCL kernel would be
+// ended by its watchdog, instead of leaving the GPU spinning for ever.
 MLXA_D float peak_collect(const PeakExchange& x, const unsigned long long* my_slots) {
     float m = 0.f;
     for (int r = 0; r < x.world; ++r) {
         const unsigned long long* s = my_slots + (x.epoch & 1u) * x.world + r;
         unsigned long long v = ld_relaxed_sys_u64(s);
+        unsigned ns = 32;
         for (unsigned spins = 0; (unsigned)(v >> 32) != x.epoch; ++spins) {
-            if (spins > (1u << 26)) __trap();
-            __nanosleep(64);
+            if (spins > (1u << 27)) __trap();
+            __nanosleep(ns);
+            if (ns < 1024) ns <<= 1;
             v = ld_relaxed_sys_u64(s);
         }
         m = fmaxf(m, __int_as_float((int)(unsigned)v));

@@ -206,6 +206,8 @@ def _melspec_from_bank(y, bank: SparseBank, n_fft, hop, win_length, window, cent
     T = frames_or_raise(L, n_fft, hop, center, pad_mode)
     win = padded_window(window, win_length, n_fft)
     out = torch.empty((B, bank.n_bands, T), dtype=torch.float32, device=y.device)
+    if B == 0:  # an empty batch gives an empty result (PyTorch semantics), not an error
+        return out
     peak = torch.zeros(1, dtype=torch.float32, device=y.device) if want_peak else None
     db = fused_db or (0, 10.0, 1e-10, 1.0)
     check(_ext.mlxa_melspec_f32(ptr(y), B, L, y.stride(0), ptr(win), n_fft, hop, int(center), mode, float(power),

@@ -57,6 +57,7 @@ class LogMelPlan:
         # ref a constant: the mel kernel's epilogue writes dB itself and top_db is a read-mostly floor pass
         self.fused_db = self.to_db and not self.ref_is_max
         self.kernel_launches_per_call = 1 + (1 if self.need_peak else 0)
+        self._awaiting_db = False  # with a peer exchange every mel() must be followed by its db() (epochs pair up)
 
     def empty_output(self) -> torch.Tensor:
         return torch.empty((self.B, self.n_mels, self.T), dtype=torch.float32, device=self.device)
@@ -66,7 +67,11 @@ class LogMelPlan:
         s = torch.cuda.current_stream(self.device).cuda_stream
         fuse = self.fused_db  # the peak slot was zeroed by the previous call's dB / floor kernel
         if self.xchg is not None:
+            if self._awaiting_db:
+                raise RuntimeError("LogMelPlan.mel() was called twice without db(): with a peer-memory peak exchange the "
+                                   "two launches pair up by epoch on every rank")
             self.xchg.next_epoch()
+            self._awaiting_db = True
         check(_ext.mlxa_melspec_f32(ptr(y), self.B, self.L, y.stride(0), ptr(self.win), self.n_fft, self.hop,
                                     int(self.center), self.mode, self.power, ptr(self.bank.packed),
                                     self.n_mels, self.bank.n_w4, ptr(out), self._peak_ptr() if self.need_peak else None,
@@ -81,6 +86,7 @@ class LogMelPlan:
         if not self.need_peak:
             return
         xr = self.xchg.ref if self.xchg is not None else None
+        self._awaiting_db = False
         if xr is None:
             distributed.all_reduce_max_(self.peaks[self._slot:self._slot + 1])
         s = torch.cuda.current_stream(self.device).cuda_stream

@@ -28,6 +28,8 @@ def _stft_physical(y2d: torch.Tensor, n_fft: int, hop: int, win: torch.Tensor, c
     T = frames_or_raise(L, n_fft, hop, center, pad_mode)
     F = n_fft // 2 + 1
     out = torch.empty((B, T, F, 2), dtype=torch.float32, device=y2d.device)
+    if B == 0:  # an empty batch gives an empty result (PyTorch semantics), not an error
+        return torch.view_as_complex(out)
     check(_ext.mlxa_stft_f32(ptr(y2d), B, L, y2d.stride(0), ptr(win), n_fft, hop, int(center), mode, ptr(out),
                              stream_ptr(y2d)), "stft")
     return torch.view_as_complex(out)
@@ -109,6 +111,8 @@ def _istft_physical(P: torch.Tensor, n_fft: int, hop: int, win: torch.Tensor, ce
     wss = _window_sumsquare(win, n_fft, hop, T, ola_len)
     if out is None:
         out = torch.empty((B, out_len), dtype=torch.float32, device=P.device)
+    if B == 0:
+        return out
     if u_out is not None or (u_prev is not None and momentum != 0.0):
         check(_ext.mlxa_istft_momentum_f32(ptr(P), ptr(u_prev), float(momentum), ptr(u_out), B, T, F_in, ptr(win), ptr(wss),
                                            n_fft, hop, ola_len, trim, out_len, ptr(out), out.stride(0), stream_ptr(P)),

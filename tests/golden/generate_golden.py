@@ -14,7 +14,7 @@ The only restated piece is the inline Metal overlap-add kernel
 (stft.py:548-596), re-expressed in the shim because Metal cannot run here.
 
 The fixtures are small on purpose; they pin the oracle (tests/test_oracle_golden.py)
-and are compared directly with the CUDA path (tests/test_gpu_golden.py).
+and are compared directly with the CUDA path (tests/test_gpu_parity.py).
 """
 from __future__ import annotations
 
@@ -65,6 +65,13 @@ for (sr, n_fft, n_mels, fmin, fmax, htk, norm) in [
     out[f"melfb/{sr}/{n_fft}/{n_mels}/{fmin}/{fmax}/{int(htk)}/{norm}"] = A(
         ref.mel_filterbank(sr, n_fft, n_mels, fmin, fmax, htk, norm))
 out["linfb/22050/1024/32"] = A(ref.linear_filterbank(22050, 1024, 32))
+for (sr, n_fft, n_bands, fmin, fmax, formula, norm) in [
+    (22050, 1024, 24, 0.0, None, "zwicker", "slaney"),
+    (16000, 512, 20, 50.0, 7000.0, "traunmuller", None),
+    (44100, 2048, 32, 0.0, None, "zwicker", None),
+]:
+    out[f"barkfb/{sr}/{n_fft}/{n_bands}/{fmin}/{fmax}/{formula}/{norm}"] = A(
+        ref.bark_filterbank(sr, n_fft, n_bands, fmin, fmax, formula, norm))
 hz = np.array([0.0, 55.0, 440.0, 999.0, 1000.0, 4000.0, 11025.0])
 out["hz"] = hz
 out["hz_to_mel/slaney"] = ref.hz_to_mel(hz)

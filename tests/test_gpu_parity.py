@@ -2,10 +2,14 @@
 and the committed reference fixtures.  Tolerances are the ones BASELINE.json's north_star states:
 pad/frame indices bit-exact; STFT and mel within 1e-5 of peak magnitude; ISTFT round trip <= 1e-5;
 dB within 1e-3 dB; MFCC at the reference tests' rtol=atol=1e-4 scale."""
+import os
+
 import numpy as np
 import pytest
 
 from oracle import spectral as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -266,6 +270,11 @@ def test_constants_bit_exact_on_device(ap, golden):
             norm = None if parts[3] == "None" else parts[3]
             assert np.array_equal(H(ap.dct_matrix(int(parts[1]), int(parts[2]), norm)), golden[key]), key
     assert np.array_equal(H(ap.linear_filterbank(22050, 1024, 32)), golden["linfb/22050/1024/32"])
+    for key in [k for k in golden.files if k.startswith("barkfb/")]:  # reference filterbanks.py:159-231, bit for bit
+        _, sr, n_fft, nb, fmin, fmax, formula, norm = key.split("/")
+        fb = ap.bark_filterbank(int(sr), int(n_fft), int(nb), float(fmin), None if fmax == "None" else float(fmax), formula,
+                                None if norm == "None" else norm)
+        assert np.array_equal(H(fb), golden[key]), key
     assert ap.get_window("hann", 512) is ap.get_window("HANN", 512)  # device-resident cache hit
     with pytest.raises(ValueError, match="cannot exceed Nyquist"):
         ap.mel_filterbank(16000, 512, fmax=9000.0)
@@ -437,3 +446,77 @@ def test_griffinlim_quality_and_errors(ap):
         ap.griffinlim(S, init="ones")
     ang, reb, err = ap.griffinlim_iter(S, np.zeros_like(S), 256, 1024, 1024)
     assert tuple(ang.shape) == S.shape and float(err) >= 0
+
+
+def test_array_windows_are_not_aliased(ap):
+    """Two different host windows of equal length, back to back: each upload is freed on return and the allocator
+    hands the same block to the next one, so a (pointer, version) cache key would serve the first window's
+    contents to the second call.  Also a caller-owned CUDA window modified in place."""
+    rng = np.random.default_rng(7)
+    y = rng.standard_normal(6000).astype(np.float32)
+    w1 = np.hanning(512).astype(np.float32)
+    w2 = np.hamming(512).astype(np.float32)
+    for w in (w1, w2, w1, w2):
+        got = H(ap.stft(y, 512, 128, window=w))
+        ref = o.stft(y, 512, 128, window=w, dtype=np.float64)
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+        M = H(ap.melspectrogram(y, sr=16000, n_fft=512, hop_length=128, n_mels=40, window=w))
+        Mr = o.melspectrogram(y, sr=16000, n_fft=512, hop_length=128, n_mels=40, window=w, dtype=np.float64)
+        assert np.abs(M - Mr).max() <= 1e-5 * Mr.max()
+    wd = torch.from_numpy(w1).cuda()
+    a = H(ap.stft(y, 512, 128, window=wd))
+    wd.copy_(torch.from_numpy(w2).cuda())  # same storage, new version
+    b = H(ap.stft(y, 512, 128, window=wd))
+    ref = o.stft(y, 512, 128, window=w2, dtype=np.float64)
+    assert np.abs(b - ref).max() <= 1e-5 * np.abs(ref).max() and np.abs(a - b).max() > 1e-3
+
+
+def test_empty_batch_returns_empty(ap):
+    y = torch.zeros((0, 4000), device="cuda")
+    assert tuple(ap.stft(y, 512, 128).shape) == (0, 257, 32)
+    assert tuple(ap.melspectrogram(y, sr=16000, n_fft=400, hop_length=160, n_mels=80).shape) == (0, 80, 26)
+    assert tuple(ap.istft(torch.zeros((0, 257, 32), dtype=torch.complex64, device="cuda"), 128).shape) == (0, 31 * 128)
+
+
+def test_griffinlim_momentum_is_signal_domain_linear(ap):
+    """The inverse kernel takes Griffin-Lim's momentum step through the (linear) inverse transform: with u_prev
+    given it must return u + m (u - u_prev) where u is the plain inverse of the same spectrum, and hand u back."""
+    from mlx_audio_primitives_b200.stft import _istft_physical, _spectrum_physical
+    from mlx_audio_primitives_b200.windows import padded_window
+    rng = np.random.default_rng(11)
+    for n_fft, hop, L in [(1024, 256, 30000), (400, 160, 16000), (600, 150, 9000)]:  # planned pack / pair, O(n^2) path
+        y = torch.from_numpy(rng.standard_normal((3, L)).astype(np.float32)).cuda()
+        P = _spectrum_physical(ap.stft(y, n_fft, hop))
+        win = padded_window("hann", n_fft, n_fft)
+        u = _istft_physical(P, n_fft, hop, win, True, None)
+        up = torch.from_numpy(rng.standard_normal(tuple(u.shape)).astype(np.float32)).cuda()
+        uo = torch.empty_like(u)
+        got = _istft_physical(P, n_fft, hop, win, True, None, u_prev=up, momentum=0.99, u_out=uo)
+        assert torch.equal(uo, u)
+        want = u + 0.99 * (u - up)
+        assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max())
+
+
+def test_warp_specialised_mel_kernel_matches(ap):
+    """MLXA_MEL_WS=1 selects the warp-specialised n_fft = 400 kernel (fwd_mel_ws.cuh); it is an A/B variant of the
+    default kernel and must produce the same log-mel (the environment switch is read once per process)."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, sys; sys.path.insert(0, %r)\n"
+        "import mlx_audio_primitives_b200 as ap\n"
+        "from oracle import spectral as o\n"
+        "rng = np.random.default_rng(3)\n"
+        "for B, L in [(3, 16000), (2, 160 * 64 * 3 + 77), (70, 48000)]:\n"
+        "    y = rng.standard_normal((B, L)).astype(np.float32) * np.logspace(-3, 0, B)[:, None].astype(np.float32)\n"
+        "    M = ap.melspectrogram(torch.from_numpy(y).cuda(), sr=16000, n_fft=400, hop_length=160, n_mels=80)\n"
+        "    for b in (0, B - 1):\n"
+        "        ref = o.melspectrogram(y[b], sr=16000, n_fft=400, hop_length=160, n_mels=80, dtype=np.float64)\n"
+        "        assert np.abs(M[b].cpu().numpy() - ref).max() <= 1e-5 * ref.max()\n"
+        "    plan = ap.LogMelPlan(B, L, sr=16000, n_fft=400, hop_length=160, n_mels=80)\n"
+        "    D = plan(torch.from_numpy(y).cuda())\n"
+        "    assert torch.equal(D, ap.power_to_db(M))\n"
+        "print('ws ok')\n" % ROOT)
+    env = dict(os.environ, MLXA_MEL_WS="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "ws ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

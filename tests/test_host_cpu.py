@@ -83,6 +83,12 @@ def test_host_constants_match_reference_fixtures(golden):
             norm = None if parts[3] == "None" else parts[3]
             assert np.array_equal(dct_matrix_host(int(parts[1]), int(parts[2]), norm), golden[key]), key
     assert np.array_equal(_linear_host(22050, 1024, 32, 0.0, 11025.0, "slaney"), golden["linfb/22050/1024/32"])
+    from mlx_audio_primitives_b200.filterbanks import _bark_host
+    for key in [k for k in golden.files if k.startswith("barkfb/")]:  # reference filterbanks.py:159-231, bit for bit
+        _, sr, n_fft, nb, fmin, fmax, formula, norm = key.split("/")
+        fmax = int(sr) / 2.0 if fmax == "None" else float(fmax)
+        fb = _bark_host(int(sr), int(n_fft), int(nb), float(fmin), fmax, formula, None if norm == "None" else norm)
+        assert np.array_equal(fb, golden[key]), key
     assert np.array_equal(hz_to_mel(golden["hz"]), golden["hz_to_mel/slaney"])
     assert np.array_equal(hz_to_mel(golden["hz"], True), golden["hz_to_mel/htk"])
     assert np.array_equal(mel_to_hz(hz_to_mel(golden["hz"])), golden["mel_to_hz/slaney"])
