@@ -328,13 +328,15 @@ int mlxa_preemphasis_f32(const float* y, int64_t B, int64_t L, int64_t ldy, floa
 /* ---- host-buffer convenience (the e2e path: pinned or pageable HOST pointers) ------------ */
 /* log-mel of host clips with chunked H2D / compute / D2H overlap on internal streams.
  * y_host (B, L), out_host (B, n_bands, T), bank_host: packed filterbank in HOST memory.  The dB step is power_to_db(ref, amin, top_db)
- * with the max taken over the whole batch; ref_is_max != 0 means ref = max(mel).
+ * with the max taken over the whole batch; ref_is_max != 0 means ref = max(mel).  xchg (optional): this
+ * rank's clips are a shard of the batch -- the rank's peak is published once after the last chunk and the
+ * dB kernels use the maximum over all ranks (epoch advanced by the caller, once per call, on every rank).
  * Synchronous: returns when out_host is complete. */
 int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float* window_host,
                          int n_fft, int hop, int center, int pad_mode, float power,
                          const float* bank_host, int n_bands, int64_t n_wt,
                          int apply_db, int ref_is_max, float ref, float amin,
-                         int use_top_db, float top_db, float* out_host);
+                         int use_top_db, float top_db, const mlxa_peak_exchange* xchg, float* out_host);
 
 /* Measurement aid: launches blocks x threads threads, each running 8 independent chains of
  * `iters` FFMAs (16*iters flops per thread).  bench.py times it to get the FP32 CUDA-core peak

@@ -64,7 +64,7 @@ SIGNATURES = {
     "mlxa_dct_f32": [_p, _i64, _i32, _p, _i32, _p, _p],
     "mlxa_mfcc_tail_f32": [_p, _i64, _i32, _i64, _p, _i32, _p, _i32, _f32, _f32, _i32, _f32, _p, _p, _p],
     "mlxa_logmel_host_f32": [_p, _i64, _i64, _p, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i64,
-                             _i32, _i32, _f32, _f32, _i32, _f32, _p],
+                             _i32, _i32, _f32, _f32, _i32, _f32, _p, _p],
     "mlxa_ffma_probe": [_p, _i32, _i32, _i32, _p],
 }
 

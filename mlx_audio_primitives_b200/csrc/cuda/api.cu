@@ -703,8 +703,9 @@ extern "C" {
 int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float* window_host, int n_fft, int hop,
                          int center, int pad_mode, float power, const float* bank_host, int n_bands, int64_t n_w4,
                          int apply_db, int ref_is_max, float ref, float amin, int use_top_db, float top_db,
-                         float* out_host) {
+                         const mlxa_peak_exchange* xchg, float* out_host) {
     CHECK_ARG(y_host && window_host && out_host && bank_host, "null pointer");
+    CHECK_ARG(xchg == nullptr || (xchg->rank >= 0 && xchg->rank < xchg->world && xchg->ticket), "bad peak exchange");
     CHECK_ARG(B > 0 && L > 0 && n_bands > 0 && n_w4 > 0, "bad shape");
     const int64_t bank_words = packed_bank_words(n_bands, n_w4, mlxa_plan_group(n_fft));
     int pad = 0;
@@ -787,13 +788,21 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
         for (int i = 0; i < NS; ++i)
             for (int j = 0; j < NS; ++j)
                 if (i != j) CHECK_CUDA(cudaStreamWaitEvent(ws.st[i], ws.done[j], 0), "wait");
+        // sharded batch: every chunk has added to this rank's peak; publish it once, the dB / floor kernels below
+        // collect the maximum over the ranks (the batch-global peak of convert.py:42-58)
+        const PeakExchange px = to_xchg(xchg);
+        if (px.peer_slots != nullptr) {
+            CHECK_CUDA(run_peak_publish(px, ws.d_gmax, s0), "peak publish");
+            CHECK_CUDA(cudaEventRecord(ws.done[0], s0), "event");
+            for (int i = 1; i < NS; ++i) CHECK_CUDA(cudaStreamWaitEvent(ws.st[i], ws.done[0], 0), "wait");
+        }
         ci = 0;
         for (int64_t b0 = 0; b0 < B && !speculate; b0 += chunk, ++ci) {
             const int64_t nb = std::min(chunk, B - b0);
             cudaStream_t s = ws.st[ci % NS];
             float* m = ws.d_mel + b0 * mel_per_clip;
             int rc = mlxa_to_db_f32(m, nb * mel_per_clip, 10.0f, amin, ref, ref_is_max ? ws.d_gmax : nullptr, use_top_db,
-                                    top_db, ws.d_gmax, m, nullptr, nullptr, s);
+                                    top_db, ws.d_gmax, m, nullptr, xchg, s);
             if (rc) return rc;
             CHECK_CUDA(d2h(b0, nb, s), "d2h");
         }
@@ -807,7 +816,7 @@ int mlxa_logmel_host_f32(const float* y_host, int64_t B, int64_t L, const float*
             else
                 (void)cudaGetLastError();
             CHECK_CUDA(run_db_floor_blocks(ws.d_mel, B, n_bands, T, 10.0f, amin, ref, top_db, ws.d_gmax, ws.d_bmin, nullptr,
-                                           mirror ? nullptr : ws.d_raised, PeakExchange{}, mirror, s0), "db_floor_blocks");
+                                           mirror ? nullptr : ws.d_raised, px, mirror, s0), "db_floor_blocks");
             if (!mirror) {
                 CHECK_CUDA(cudaMemcpyAsync(ws.h_raised, ws.d_raised, sizeof(int) * (size_t)(1 + B * nblk), cudaMemcpyDeviceToHost, s0), "d2h list");
                 for (int i = 0; i < NS; ++i) CHECK_CUDA(cudaStreamSynchronize(ws.st[i]), "sync");

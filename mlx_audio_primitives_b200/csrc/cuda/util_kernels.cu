@@ -165,6 +165,9 @@ __global__ void max_kernel(const float* __restrict__ x, long long n, float* gmax
     }
 }
 
+// one thread: this rank's finished peak to every peer (the host-buffer path publishes once, after its last chunk)
+__global__ void peak_publish_kernel(PeakExchange xchg, float* gmax) { peak_publish(xchg, gmax, 1u); }
+
 // ---- dB family (convert.py:14-60) ---------------------------------------------------------
 __global__ void to_db_kernel(const float* __restrict__ x, long long n, float coef, float amin, float ref_host,
                              const float* __restrict__ ref_dev, int use_top, float top_db,
@@ -530,6 +533,10 @@ cudaError_t run_transpose_f32(const float* in, long long B, long long R, long lo
 cudaError_t run_transpose_c64(const float2* in, long long B, long long R, long long C, float2* out, cudaStream_t s) {
     dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)B), blk(32, 8);
     transpose_kernel<float2><<<grid, blk, 0, s>>>(in, R, C, out);
+    return cudaGetLastError();
+}
+cudaError_t run_peak_publish(const PeakExchange& xchg, float* gmax, cudaStream_t s) {
+    peak_publish_kernel<<<1, 1, 0, s>>>(xchg, gmax);
     return cudaGetLastError();
 }
 cudaError_t run_max(const float* x, long long n, float* gmax, cudaStream_t s) {

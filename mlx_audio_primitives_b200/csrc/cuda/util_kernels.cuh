@@ -17,6 +17,7 @@ cudaError_t run_momentum(const float* u, const float* u_prev, float m, long long
 cudaError_t run_transpose_f32(const float* in, long long B, long long R, long long C, float* out, cudaStream_t s);
 cudaError_t run_transpose_c64(const float2* in, long long B, long long R, long long C, float2* out, cudaStream_t s);
 cudaError_t run_max(const float* x, long long n, float* gmax, cudaStream_t s);
+cudaError_t run_peak_publish(const PeakExchange& xchg, float* gmax, cudaStream_t s);
 cudaError_t run_to_db(const float* x, long long n, float coef, float amin, float ref_host, const float* ref_dev,
                       int use_top, float top_db, const float* gmax, float* out, float* reset_next, const PeakExchange& xchg,
                       cudaStream_t s);

@@ -114,16 +114,26 @@ class LogMelPlan:
     # -- host buffers in, host buffers out (H2D / kernels / D2H overlapped inside the library) --
     def run_host(self, y_host: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
         """y_host (B, L) and out_host (B, n_mels, T): contiguous float32 CPU tensors (pinned for full
-        copy bandwidth).  Synchronous.  Single-GPU semantics: the batch-global max is local."""
+        copy bandwidth).  Synchronous.  With sharding enabled the batch-global max crosses the GPUs like in the
+        resident path (peer-memory exchange), so every rank gets the bits of the unsharded computation."""
         if y_host.is_cuda or out_host.is_cuda or not y_host.is_contiguous() or not out_host.is_contiguous():
             raise ValueError("run_host takes contiguous CPU tensors")
         if tuple(y_host.shape) != (self.B, self.L) or tuple(out_host.shape) != (self.B, self.n_mels, self.T):
             raise ValueError("shape mismatch with the plan")
         vp = lambda a: a.ctypes.data_as(C.c_void_p).value
+        use_x = self.xchg is not None and self.need_peak
+        if not use_x and self.need_peak and distributed.is_enabled():
+            raise RuntimeError("run_host needs the peer-memory peak exchange when the batch is sharded "
+                               "(symmetric memory unavailable: use the resident path, which falls back to NCCL)")
+        if use_x:
+            if self._awaiting_db:
+                raise RuntimeError("LogMelPlan.mel() is awaiting its db(): finish the pair before run_host()")
+            self.xchg.next_epoch()
         with torch.cuda.device(self.device):
             check(_ext.mlxa_logmel_host_f32(y_host.data_ptr(), self.B, self.L, vp(self._win_host), self.n_fft, self.hop,
                                             int(self.center), self.mode, self.power, vp(self.bank.host),
                                             self.n_mels, self.bank.n_w4, int(self.to_db), int(self.ref_is_max),
                                             self.ref, self.amin, int(self.top_db is not None),
-                                            float(self.top_db or 0.0), out_host.data_ptr()), "logmel_host")
+                                            float(self.top_db or 0.0), self.xchg.ref if use_x else None,
+                                            out_host.data_ptr()), "logmel_host")
         return out_host
