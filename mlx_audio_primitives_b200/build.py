@@ -21,7 +21,18 @@ SRC = os.path.join(PKG, "csrc", "cuda")
 OBJ = os.path.join(PKG, "csrc", "build")
 LIBDIR = os.path.join(PKG, "_lib")
 LIB = os.path.join(LIBDIR, "libmlxaudio_cuda.so")
-PLANNED_NFFT = (64, 128, 256, 400, 512, 1024, 2048, 4096)
+
+
+def _sizes(macro: str) -> tuple[int, ...]:
+    """the n_fft list of a MLXA_FOR_EACH_* macro in csrc/cuda/fft_sizes.cuh (the one list of planned sizes)"""
+    import re
+    text = open(os.path.join(SRC, "fft_sizes.cuh")).read().replace("\\\n", " ")
+    m = re.search(r"#define\s+" + macro + r"\(X\)\s+(.*)", text)
+    return tuple(int(v) for v in re.findall(r"X\((\d+)\)", m.group(1)))
+
+
+PLANNED_NFFT = _sizes("MLXA_FOR_EACH_NFFT")
+ACF_NFFT = _sizes("MLXA_FOR_EACH_ACF_NFFT")
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "--expt-relaxed-constexpr",
@@ -56,7 +67,7 @@ def _units():
         if os.environ.get(f"MLXA_INV_THREADS_{nf}"):  # experiments: threads per CTA of the inverse kernel
             inv_flags.append(f"-DMLXA_INV_THREADS={os.environ[f'MLXA_INV_THREADS_{nf}']}")
         units.append((f"inv_{nf}.o", "inv_inst.cu", inv_flags))
-        if nf != 400:  # packed plans only
+        if nf in ACF_NFFT:  # the pitch kernels: power-of-two transform sizes
             units.append((f"acf_{nf}.o", "acf_inst.cu", [f"-DMLXA_NFFT={nf}"]))
     return units
 

@@ -11,11 +11,15 @@
 
 #include "../../../include/mlxa_cuda.h"
 #include "common.cuh"
+#include "fft_sizes.cuh"
 #include "util_kernels.cuh"
 
 namespace mlxa {
 #define X(NF) MLXA_DECL_LAUNCHERS(NF)
-X(64) X(128) X(256) X(400) X(512) X(1024) X(2048) X(4096)
+MLXA_FOR_EACH_NFFT(X)
+#undef X
+#define X(NF) cudaError_t launch_acf_##NF(const AcfParams& p, cudaStream_t s);
+MLXA_FOR_EACH_ACF_NFFT(X)
 #undef X
 }  // namespace mlxa
 
@@ -51,7 +55,10 @@ PeakExchange to_xchg(const mlxa_peak_exchange* x) {
 
 bool has_plan(int n_fft) {
     switch (n_fft) {
-        case 64: case 128: case 256: case 400: case 512: case 1024: case 2048: case 4096: return true;
+#define X(NF) case NF:
+        MLXA_FOR_EACH_NFFT(X)
+#undef X
+            return true;
     }
     return false;
 }
@@ -89,7 +96,7 @@ cudaError_t get_tables(int n_fft, Tables* out) {
         plan.resize(np); unpack.resize(nu);                          \
         plan_tables_##NF(plan.data(), &np, unpack.data(), &nu);      \
         break;
-        X(64) X(128) X(256) X(400) X(512) X(1024) X(2048) X(4096)
+        MLXA_FOR_EACH_NFFT(X)
 #undef X
         default:
             plan.resize(n_fft);
@@ -109,7 +116,7 @@ cudaError_t get_tables(int n_fft, Tables* out) {
 cudaError_t dispatch_fwd(int ep, FwdParams& p, cudaStream_t s) {
     switch (p.n_fft) {
 #define X(NF) case NF: return launch_fwd_##NF(ep, p, s);
-        X(64) X(128) X(256) X(400) X(512) X(1024) X(2048) X(4096)
+        MLXA_FOR_EACH_NFFT(X)
 #undef X
     }
     return launch_fwd_naive(ep, p, s);
@@ -214,7 +221,7 @@ int mlxa_stft_f32(const float* y, int64_t B, int64_t L, int64_t ldy, const float
 int mlxa_plan_group(int n_fft) {
     switch (n_fft) {
 #define X(NF) case NF: return plan_group_##NF();
-        X(64) X(128) X(256) X(400) X(512) X(1024) X(2048) X(4096)
+        MLXA_FOR_EACH_NFFT(X)
 #undef X
     }
     return 32;  // O(n^2) DFT kernels: one warp per frame
@@ -223,7 +230,7 @@ int mlxa_plan_group(int n_fft) {
 int mlxa_has_fused_feature(int n_fft) {
     switch (n_fft) {
 #define X(NF) case NF: return plan_fused_feature_##NF();
-        X(64) X(128) X(256) X(400) X(512) X(1024) X(2048) X(4096)
+        MLXA_FOR_EACH_NFFT(X)
 #undef X
     }
     return 0;
@@ -397,7 +404,7 @@ static int istft_impl(const mlxa_c64* spec, const float* u_prev, float momentum,
             cudaError_t e = cudaErrorInvalidValue;
             switch (n_fft) {
 #define X(NF) case NF: e = launch_inv_##NF(p, s); break;
-                X(64) X(128) X(256) X(400) X(512) X(1024) X(2048) X(4096)
+                MLXA_FOR_EACH_NFFT(X)
 #undef X
             }
             CHECK_CUDA(e, "istft");
@@ -520,7 +527,7 @@ static int acf_frames(const float* y, int64_t B, int64_t L, int64_t ldy, int fra
     cudaError_t e = cudaErrorInvalidValue;
     switch (n_fft) {
 #define X(NF) case NF: e = launch_acf_##NF(p, (cudaStream_t)stream); break;
-        X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
+        MLXA_FOR_EACH_ACF_NFFT(X)
 #undef X
     }
     CHECK_CUDA(e, what);

@@ -28,7 +28,7 @@ struct FftPlan {
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
     static constexpr int E = cmax(regs(0), cmax(regs(1), NPASS == 3 ? regs(2) : 0));
     static constexpr int PAD = (R0 & 1) ? 2 : 1;  // (R0 + PAD) odd -> conflict-free strides
-    static constexpr int BUF = N + PAD * (N / R0);  // float2 slots per transform
+    static constexpr int BUF = (N + PAD * (N / R0) + 1) & ~1;  // float2 slots per transform (even: 16-byte multiples)
     static MLXA_HD int phys(int i) { return i + PAD * (i / R0); }
     // inter-pass twiddles: pass p >= 1 uses tw[tw_off(p) + (r-1)*ns(p) + (b mod ns(p))]
     static constexpr int tw_off(int p) { return p <= 1 ? 0 : (R1 - 1) * R0; }

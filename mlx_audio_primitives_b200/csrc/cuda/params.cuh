@@ -109,7 +109,6 @@ struct AcfParams {  // acf_inst.cu: autocorrelation pitch detector (pitch.py:118
 #define MLXA_DECL_LAUNCHERS(NF)                                                            \
     cudaError_t launch_fwd_##NF(int ep, FwdParams& p, cudaStream_t s);                     \
     cudaError_t launch_inv_##NF(InvParams& p, cudaStream_t s);                             \
-    cudaError_t launch_acf_##NF(const AcfParams& p, cudaStream_t s);                        \
     int plan_group_##NF();                                                                  \
     int plan_fused_feature_##NF();                                                          \
     void plan_tables_##NF(float2* tw_plan_host, int* n_plan, float2* tw_unpack_host, int* n_unpack);

@@ -10,7 +10,8 @@ from oracle import spectral as o
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
-N_FFTS = [64, 128, 256, 400, 512, 1024, 2048, 4096, 96, 250, 777]
+PLANNED = [32, 64, 128, 256, 400, 480, 512, 600, 800, 1000, 1024, 1200, 1600, 2000, 2048, 3072, 4096, 8192]
+N_FFTS = PLANNED + [96, 250, 777]
 WINDOWS = ["hann", "hamming", "blackman", "bartlett", "rectangular"]
 
 
@@ -108,3 +109,46 @@ def test_many_clips_persistent_schedule(ap):
     S = ap.stft(y, 512, 128)
     r = ap.istft(S, 128, length=4000)
     assert float((r[:, 1:] - y[:, 1:]).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("n_fft", PLANNED)
+def test_every_planned_size(ap, n_fft):
+    """Every compiled plan (powers of two 32..8192 and the 2^a 3^b 5^c sizes) through the fused kernels: forward
+    transform, mel epilogue, inverse + overlap-add round trip, Griffin-Lim projection chain, against the float64
+    oracle at the north-star tolerances.  mlxa_has_fast_plan says the O(n^2) path is not what is being tested."""
+    from mlx_audio_primitives_b200._extension import _ext
+    assert _ext.mlxa_has_fast_plan(n_fft) == 1
+    rng = np.random.default_rng(n_fft)
+    for hop, center, B, frames in [(n_fft // 4, True, 3, 70), (max(1, n_fft // 3 + 1), False, 2, 37)]:
+        L = (frames - 1) * hop + (0 if center else n_fft) + int(rng.integers(0, hop))
+        y = misaligned(rng, B, L)
+        yh = H(y)
+        kw = dict(n_fft=n_fft, hop_length=hop, center=center)
+        S = ap.stft(y, **kw)
+        ref = o.stft(yh, dtype=np.float64, **kw)
+        assert tuple(S.shape) == ref.shape
+        assert np.abs(H(S) - ref).max() <= 1e-5 * np.abs(ref).max(), kw
+        r = H(ap.istft(S, hop, center=center, length=L if center else None))
+        want = o.istft(ref, hop, center=center, length=L if center else None, dtype=np.float64)
+        n_ola = n_fft + (S.shape[-1] - 1) * hop
+        wss = o.window_sumsquare(o.padded_window("hann", n_fft, n_fft), S.shape[-1], hop, n_ola)
+        if center:
+            wss = wss[n_fft // 2:]
+        ok = np.zeros(r.shape[-1], bool)
+        m = min(ok.size, wss.size)
+        ok[:m] = wss[:m] >= 1e-2 * wss.max()
+        assert np.abs(r - want)[:, ok].max(initial=0.0) <= 2e-5 * max(1.0, np.abs(want).max()), kw
+        if n_fft >= 128:
+            mk = dict(sr=16000, n_mels=40, **kw)
+            M = ap.melspectrogram(y, **mk)
+            mref = o.melspectrogram(yh, dtype=np.float64, **mk)
+            assert np.abs(H(M) - mref).max() <= 1e-5 * mref.max(), mk
+            D = ap.power_to_db(M)
+            dref = o.power_to_db(mref, dtype=np.float64)
+            assert np.abs(H(D) - dref).max() <= 1e-3
+    if n_fft >= 64:
+        y = torch.from_numpy(rng.standard_normal((2, 20 * (n_fft // 4))).astype(np.float32)).cuda()
+        mag = ap.magnitude(ap.stft(y, n_fft))
+        got = H(ap.griffinlim(mag, n_iter=2, n_fft=n_fft, random_state=3))
+        ref = o.griffinlim(H(mag), 2, n_fft // 4, n_fft=n_fft, random_state=3)
+        assert np.abs(got - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max())

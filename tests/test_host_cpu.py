@@ -25,7 +25,7 @@ def test_abi_exports_every_declared_symbol():
     assert ext._ext.mlxa_plan_group(400) == -2 and ext._ext.mlxa_plan_group(2048) == -4 and ext._ext.mlxa_plan_group(777) == 32
     assert ext._ext.mlxa_abi_version() == ext.ABI_VERSION
     assert ext._ext.mlxa_has_fast_plan(400) == 1 and ext._ext.mlxa_has_fast_plan(2048) == 1
-    assert ext._ext.mlxa_has_fast_plan(600) == 0
+    assert ext._ext.mlxa_has_fast_plan(600) == 1 and ext._ext.mlxa_has_fast_plan(601) == 0 and ext._ext.mlxa_has_fast_plan(8192) == 1
     # argument validation happens before any CUDA call, so it is testable without a GPU
     rc = ext._ext.mlxa_pad_signal_f32(None, 1, 10, 3, 0, None, None)
     assert rc == -1 and b"null" in ext._ext.mlxa_last_error()
@@ -187,7 +187,22 @@ def test_in_register_dft(emul, R):
     assert np.abs(out - ref).max() <= 5e-7 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("n_fft", [64, 128, 256, 400, 512, 1024, 2048, 4096])
+PLANNED = [32, 64, 128, 256, 400, 480, 512, 600, 800, 1000, 1024, 1200, 1600, 2000, 2048, 3072, 4096, 8192]
+
+
+def test_planned_sizes_are_one_list():
+    """csrc/cuda/fft_sizes.cuh is the one list of compiled plans: the build script, the library and the tests agree."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_b", os.path.join(ROOT, "mlx_audio_primitives_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert list(b.PLANNED_NFFT) == PLANNED
+    from mlx_audio_primitives_b200 import _extension as ext
+    for n in range(16, 8300):
+        assert ext._ext.mlxa_has_fast_plan(n) == int(n in PLANNED), n
+
+
+@pytest.mark.parametrize("n_fft", PLANNED)
 def test_plan_fft_emulated(emul, n_fft):
     """The same __host__ __device__ pass functions the kernels run, lanes executed sequentially."""
     N = emul.emul_plan_length(n_fft)
