@@ -186,10 +186,12 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
     }
     const float2* tw_plan = TW_SMEM ? s_tw : p.tw_plan;
     const float2* tw_unpack = TW_SMEM ? s_tw + TWP : p.tw_unpack;
-    RowBank rb{};
+    // (two carvings: a pointer that may be shared OR global would make every weight read a generic load)
+    [[maybe_unused]] RowBank rb_smem{}, rb_glob{};
     [[maybe_unused]] DbConst dbc{};
     if constexpr (EP == EP_MEL) {
-        rb = row_bank_carve(p.bank_in_smem ? s_mel : p.bank, p.n_w4);
+        rb_smem = row_bank_carve(s_mel, p.n_w4);
+        rb_glob = row_bank_carve(p.bank, p.n_w4);
         dbc = db_constants(p.db_coef, p.db_amin, p.db_ref);  // loop-invariant: one precise log2 per thread
     }
     __syncthreads();
@@ -399,7 +401,8 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 }
                 for (int i = threadIdx.x; i < 3 * PS; i += THREADS) s_pw[NBINS * PS + i] = 0.f;  // rows padded quads touch
                 __syncthreads();
-                project_power_tile<THREADS / 32, 0, false>(p, rb, dbc, s_pw, TT, b, t0, nt, 1.f, threadIdx.x >> 5, vmax);
+                if (p.bank_in_smem) project_power_tile<THREADS / 32, 0, false>(p, rb_smem, dbc, s_pw, TT, b, t0, nt, 1.f, threadIdx.x >> 5, vmax);
+                else project_power_tile<THREADS / 32, 0, false>(p, rb_glob, dbc, s_pw, TT, b, t0, nt, 1.f, threadIdx.x >> 5, vmax);
             } else if constexpr (EP == EP_FEAT && P::G > 32) {
                 // (not reachable: the launcher refuses EP_FEAT for two-warp groups -- the reductions are warp shuffles)
             } else if constexpr (EP == EP_FEAT) {
