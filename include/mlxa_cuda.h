@@ -174,6 +174,10 @@ int mlxa_griffinlim_project_f32(const float* y, int64_t B, int64_t L, int64_t ld
                                 int pad_mode, int64_t T, int64_t T_valid, const float* mag,
                                 mlxa_c64* projected, void* stream);
 
+/* out = x + momentum * (x - x_prev) over n floats (complex arrays: 2n): the Griffin-Lim momentum step
+ * (griffinlim.py:176-178) as a standalone elementwise kernel, for callers that drive single iterations. */
+int mlxa_momentum_f32(const float* x, const float* x_prev, float momentum, int64_t n, float* out, void* stream);
+
 /* rebuilt = mag * exp(i*angles) elementwise over n values (griffinlim.py:123) */
 int mlxa_polar_f32(const float* mag, const float* angles, int64_t n, mlxa_c64* out, void* stream);
 

@@ -34,6 +34,7 @@ SIGNATURES = {
     "mlxa_istft_momentum_f32": [_p, _p, _f32, _p, _i64, _i64, _i32, _p, _p, _i32, _i32, _i64, _i64, _i64, _p, _i64, _p],
     "mlxa_griffinlim_project_f32": [_p, _i64, _i64, _i64, _p, _i32, _i32, _i32, _i32, _i64, _i64, _p, _p, _p],
     "mlxa_polar_f32": [_p, _p, _i64, _p, _p],
+    "mlxa_momentum_f32": [_p, _p, _f32, _i64, _p, _p],
     "mlxa_pcg64_uniform_f32": [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_double, _i64, _p, _p],
     "mlxa_magnitude_f32": [_p, _i64, _p, _p],
     "mlxa_phase_f32": [_p, _i64, _p, _p],

@@ -426,6 +426,11 @@ static int istft_impl(const mlxa_c64* spec, const float* u_prev, float momentum,
 
 extern "C" {
 
+int mlxa_momentum_f32(const float* x, const float* x_prev, float momentum, int64_t n, float* out, void* stream) {
+    CHECK_ARG(x && x_prev && out && n > 0, "bad argument");
+    CHECK_CUDA(run_momentum(x, x_prev, momentum, 1, n, n, out, (cudaStream_t)stream), "momentum");
+    return 0;
+}
 int mlxa_polar_f32(const float* mag, const float* angles, int64_t n, mlxa_c64* out, void* stream) {
     CHECK_ARG(mag && angles && out && n > 0, "bad argument");
     CHECK_CUDA(run_polar(mag, angles, n, reinterpret_cast<float2*>(out), (cudaStream_t)stream), "polar");

@@ -48,8 +48,9 @@ def griffinlim(S, n_iter: int = 32, hop_length: int | None = None, win_length: i
     """Reconstruct a signal from a magnitude spectrogram (reference griffinlim.py:17-196).
 
     The update is the reference's: new = S*exp(j*angle(stft(istft(rebuilt)))),
-    rebuilt = new + momentum*(new - tprev), tprev = new.  The random initial phase is drawn on the
-    host with NumPy's default_rng in (B, F, T) order, like the reference, so seeds reproduce."""
+    rebuilt = new + momentum*(new - tprev), tprev = new.  The random initial phase is NumPy's
+    default_rng(random_state).uniform(-pi, pi) stream in (B, F, T) order, like the reference, so seeds
+    reproduce -- generated on the device by a bit-identical PCG64 kernel (no host draw, no upload)."""
     validate_positive(n_iter, "n_iter")
     validate_range(momentum, "momentum", min_val=0.0, max_val=1.0, max_inclusive=False)
     S = f32c(S)
@@ -103,21 +104,34 @@ def griffinlim(S, n_iter: int = 32, hop_length: int | None = None, win_length: i
     return y if batched else y[0]
 
 
+def _polar(S: torch.Tensor, angles: torch.Tensor) -> torch.Tensor:
+    """S * exp(j * angles), complex64, by the library's polar kernel (any common dense layout)."""
+    S, angles = S.contiguous(), angles.contiguous()
+    out = torch.empty(tuple(S.shape) + (2,), dtype=torch.float32, device=S.device)
+    check(_ext.mlxa_polar_f32(ptr(S), ptr(angles), S.numel(), ptr(out), stream_ptr(S)), "polar")
+    return torch.view_as_complex(out)
+
+
 def griffinlim_iter(S, angles, hop_length: int, win_length: int, n_fft: int, window="hann", center: bool = True,
                     pad_mode: str = "constant", momentum: float = 0.99, tprev=None):
-    """One iteration + reconstruction MSE (reference griffinlim.py:199-284), composed from the
-    public kernels; meant for custom stopping rules, not for speed."""
+    """One iteration + reconstruction MSE (reference griffinlim.py:199-284), composed from the public kernels
+    (polar, istft, stft, magnitude, phase, momentum step); meant for custom stopping rules, not for speed.  Only
+    the scalar MSE diagnostic is a torch reduction."""
     S = f32c(S)
     angles = f32c(angles)
-    rebuilt = torch.polar(S, angles)
+    rebuilt = _polar(S, angles)
     y = istft(rebuilt, hop_length=hop_length, win_length=win_length, n_fft=n_fft, window=window, center=center)
     new = stft(y, n_fft=n_fft, hop_length=hop_length, win_length=win_length, window=window, center=center,
                pad_mode=pad_mode)
     error = torch.mean((S - magnitude(new)) ** 2)
     new_angles = phase(new)
-    new = torch.polar(S, new_angles)
+    new = _polar(S, new_angles)
     if momentum > 0 and tprev is not None:
-        out = new + momentum * (new - tprev)
+        tp = torch.view_as_real(tprev.to(torch.complex64).contiguous())
+        nw = torch.view_as_real(new)
+        out = torch.empty_like(nw)
+        check(_ext.mlxa_momentum_f32(ptr(nw), ptr(tp), float(momentum), nw.numel(), ptr(out), stream_ptr(nw)), "momentum")
+        out = torch.view_as_complex(out)
     else:
         out = new
     return new_angles, out, error

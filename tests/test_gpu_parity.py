@@ -446,6 +446,13 @@ def test_griffinlim_quality_and_errors(ap):
         ap.griffinlim(S, init="ones")
     ang, reb, err = ap.griffinlim_iter(S, np.zeros_like(S), 256, 1024, 1024)
     assert tuple(ang.shape) == S.shape and float(err) >= 0
+    # one iteration with momentum against the same step written out (reference griffinlim.py:199-284)
+    St = torch.from_numpy(np.asarray(S)).cuda() if not torch.is_tensor(S) else S
+    tprev = torch.polar(St, torch.zeros_like(St))
+    ang2, reb2, _ = ap.griffinlim_iter(S, np.zeros_like(H(St)), 256, 1024, 1024, tprev=tprev)
+    new = torch.polar(St, ang2)
+    want = new + 0.99 * (new - tprev)
+    assert float((reb2 - want).abs().max()) <= 1e-5 * float(want.abs().max())
 
 
 def test_array_windows_are_not_aliased(ap):
