@@ -47,6 +47,14 @@ def on_input_device(fn):
     return scoped
 
 
+def publish(t):
+    """Call before a freshly built device constant goes into a cache: the stream that filled it is synchronised, so a
+    later hit from ANOTHER stream (or thread) never reads a table whose fill is still in flight.  Once per entry."""
+    if torch.cuda.is_available():
+        torch.cuda.current_stream().synchronize()
+    return t
+
+
 def f32c(x) -> torch.Tensor:
     """float32, contiguous, on the GPU."""
     return to_tensor(x, torch.float32).contiguous()

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from ._extension import _ext, check
-from ._tensor import f32c, ptr, require_cuda, stream_ptr, to_tensor
+from ._tensor import f32c, ptr, publish, require_cuda, stream_ptr, to_tensor
 from .mel import _resolve_stft_args, frames_or_raise, pad_mode_code
 from .stft import _stft_physical
 from .windows import padded_window
@@ -34,7 +34,7 @@ def fft_frequencies_device(sr: int, n_fft: int) -> torch.Tensor:
         f = _freq_cache.get(key)
         if f is None:
             f = torch.from_numpy(np.linspace(0, sr / 2.0, n_fft // 2 + 1).astype(np.float32)).cuda()
-            _freq_cache[key] = f
+            _freq_cache[key] = publish(f)
         return f
 
 

@@ -18,7 +18,7 @@ import torch
 
 from . import _peaks
 from ._extension import _ext, check
-from ._tensor import f32c, ptr, require_cuda, stream_ptr
+from ._tensor import f32c, ptr, publish, require_cuda, stream_ptr
 from ._validation import validate_non_negative, validate_positive
 from .windows import padded_window
 
@@ -129,7 +129,7 @@ def dense_bank_device(key: tuple, host_fn) -> torch.Tensor:
         t = _dense_cache.get(k)
         if t is None:
             t = torch.from_numpy(np.array(host_fn())).cuda()
-            _dense_cache[k] = t
+            _dense_cache[k] = publish(t)
         return t
 
 
@@ -143,7 +143,7 @@ def sparse_bank_device(key: tuple, host_fn) -> SparseBank:
             n_fft = 2 * (dense.shape[1] - 1)
             packed, n_w4 = pack_bank_host(dense, int(_ext.mlxa_plan_group(n_fft)))
             sb = SparseBank(torch.from_numpy(packed).cuda(), dense.shape[0], n_w4, packed)
-            _sparse_cache[k] = sb
+            _sparse_cache[k] = publish(sb)
         return sb
 
 

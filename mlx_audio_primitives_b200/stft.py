@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from ._extension import _ext, check
-from ._tensor import dense_like, f32c, ptr, stream_ptr, to_tensor
+from ._tensor import dense_like, f32c, ptr, publish, stream_ptr, to_tensor
 from .mel import _resolve_stft_args, frames_or_raise, pad_mode_code
 from .windows import get_window, padded_window
 
@@ -79,7 +79,7 @@ def _window_sumsquare(win: torch.Tensor, n_fft: int, hop: int, T: int, ola_len: 
               "window_sumsquare")
         if len(_wss_cache) >= 32:
             _wss_cache.pop(next(iter(_wss_cache)))
-        _wss_cache[key] = (w, win)  # keep the window alive so its pointer cannot be recycled
+        _wss_cache[key] = (publish(w), win)  # keep the window alive so its pointer cannot be recycled
         return w
 
 

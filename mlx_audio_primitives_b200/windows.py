@@ -8,7 +8,7 @@ from functools import lru_cache
 import numpy as np
 import torch
 
-from ._tensor import require_cuda, to_tensor
+from ._tensor import publish, require_cuda, to_tensor
 
 # generalized-cosine coefficient sets a0 - a1 cos + a2 cos ... (reference windows.py:63-67)
 _COSINE_TERMS = {"hann": (0.5, 0.5), "hamming": (0.54, 0.46), "blackman": (0.42, 0.5, 0.08)}
@@ -52,7 +52,7 @@ def _resident(key: tuple, make) -> torch.Tensor:
     with _lock:
         t = _device_windows.get(key)
         if t is None:
-            t = make()
+            t = publish(make())
             if len(_device_windows) >= 256:
                 _device_windows.pop(next(iter(_device_windows)))
             _device_windows[key] = t
