@@ -200,6 +200,13 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
     const int gi = threadIdx.x / P::G, g = threadIdx.x % P::G;
     float2* buf = s_buf + gi * P::BUF;
     const int PS = power_tile_stride(TT);
+    // The lane's bins are k = g + Q*G: 0.5 exp(-i pi k / N) = (0.5 exp(-i pi g / N)) * exp(-i pi Q G / N) -- one table read
+    // per kernel and a product with compile-time constants per bin instead of one table read per bin.  Taken where
+    // it measured faster (profiles/r03a_*): the store-through epilogues (c1, c5) and the plans whose tables do not
+    // fit shared memory (n_fft 4096: c4 -4.6 %); the mel / feature kernels with resident tables sit at their
+    // register limit and lose to the two extra registers (c3 +0.8 %).
+    constexpr bool UNPACK_IMM = PACK && ((EP != EP_MEL && EP != EP_FEAT) || !TW_SMEM);
+    [[maybe_unused]] const float2 tw_base = UNPACK_IMM ? tw_unpack[g] : make_float2(0.f, 0.f);
     uint32_t ph0 = 0u, ph1 = 0u;  // parity of the next completion on each staging barrier
     float vmax = 0.f;
 
@@ -345,14 +352,18 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                         const float2 own = v[rd * R1 + dft_pos(R1, rd == 0 ? (R1 - kk) % R1 : R1 - 1 - kk)];
                         if (g == 0) zm = own;
                     }
-                    const float2 w = tw_unpack[k];
+                    float2 w;
+                    if constexpr (UNPACK_IMM) w = mul_tw<Q * P::G, 2 * P::N>(tw_base);
+                    else w = tw_unpack[k];
                     const float2 E = cadd_conj(zk, zm), D = csub_conj(zk, zm);  // O = -i D
                     return caxpy(0.5f, E, cmul(mul_neg_i(D), w));
                 } else if constexpr (PACK) {
                     constexpr int N = P::N;
                     const float2 zk = buf[(Q + 1 == NQ && k == N) ? 0 : k];
                     const float2 zm = buf[(Q == 0 && k == 0) ? 0 : N - k];
-                    const float2 w = tw_unpack[k];
+                    float2 w;
+                    if constexpr (UNPACK_IMM) w = mul_tw<Q * P::G, 2 * P::N>(tw_base);
+                    else w = tw_unpack[k];
                     const float2 E = cadd_conj(zk, zm), D = csub_conj(zk, zm);  // O = -i D
                     return caxpy(0.5f, E, cmul(mul_neg_i(D), w));
                 } else {

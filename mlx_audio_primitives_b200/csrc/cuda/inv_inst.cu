@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
 
     const int gi = threadIdx.x / P::G, g = threadIdx.x % P::G;
     float2* buf = s_buf + gi * P::BUF;
+    [[maybe_unused]] const float2 tw_base = PACK ? tw_unpack[g] : make_float2(0.f, 0.f);
     const long long clip = (long long)b * p.T * p.F_in;
     const bool hop_even = (p.hop & 1) == 0;
 
@@ -163,7 +164,8 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
                 if (Q + 1 < NQ2 || k <= N / 2) {
                     float2 xk = buf[k], xm = buf[N - k];
                     if (Q == 0 && k == 0) { xk.y = 0.f; xm.y = 0.f; }  // c2r ignores imag of DC / Nyquist
-                    const float2 w = tw_unpack[k];  // 0.5 * exp(-i*pi*k/N): the 1/2 of O is in the table
+                    // 0.5 * exp(-i*pi*k/N) (the 1/2 of O rides on it) = the lane's table entry for k = g times a compile-time constant
+                    const float2 w = mul_tw<Q * P::G, 2 * P::N>(tw_base);
                     const float ex = 0.5f * (xk.x + xm.x), ey = 0.5f * (xk.y - xm.y);
                     const float2 d = make_float2(xk.x - xm.x, xk.y + xm.y);
                     const float2 o = cmul_conj(d, w);
