@@ -307,6 +307,16 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             }
             pass_load_buf<P, 1>(g, v, buf);
             group_sync<P::G>(gi);
+            // Griffin-Lim: the first GL_EARLY target magnitudes of the lane go out before the last pass' butterflies, so
+            // their (L2) latency hides under the arithmetic; the rest follow in the epilogue (registers: E + NQ would
+            // not fit beside the transform)
+            constexpr int NQ_ = ceil_div(NBINS, P::G);
+            constexpr int GL_EARLY = (EP == EP_GL && PACK && P::NPASS == 2) ? (NQ_ / 2) : 0;
+            [[maybe_unused]] float mg[EP == EP_GL ? NQ_ : 1];
+            if constexpr (GL_EARLY > 0) {
+                const float* mrow = p.mag + ((long long)b * p.T + t0 + (va ? f0 : 0)) * p.F + g;
+                static_for<GL_EARLY>([&](auto q) { mg[decltype(q)::value] = __ldg(mrow + decltype(q)::value * P::G); });
+            }
             pass_compute<P, 1>(g, v, tw_plan);
             if constexpr (P::NPASS == 3) {
                 pass_store_buf<P, 1>(g, v, buf);
@@ -455,12 +465,11 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             } else if (va) {
                 const long long obase = ((long long)b * p.T + t0 + f0) * p.F;
                 if constexpr (PACK) {
-                    [[maybe_unused]] float mg[EP == EP_GL ? NQ : 1];
-                    if constexpr (EP == EP_GL) {  // all target magnitudes of the lane in flight before the first bin needs one
+                    if constexpr (EP == EP_GL) {  // the remaining target magnitudes of the lane in flight before the first bin needs one
                         static_for<NQ>([&](auto q) {
                             constexpr int Q = decltype(q)::value;
                             const int k = g + Q * P::G;
-                            mg[Q] = (Q + 1 < NQ || k < NBINS) ? __ldg(p.mag + obase + k) : 0.f;
+                            if constexpr (Q >= GL_EARLY) mg[Q] = (Q + 1 < NQ || k < NBINS) ? __ldg(p.mag + obase + k) : 0.f;
                         });
                     }
                     static_for<NQ>([&](auto q) {
