@@ -47,9 +47,32 @@ MLXA_HD void mirror_pass0(int g, LoadF&& load, float2* buf) {
     static_for<M::R0>([&](auto i) { dst[dft_perm(M::R0, decltype(i)::value)] = v[decltype(i)::value]; });
 }
 
+// The last pass' inter-pass twiddles of lane g are t_r = exp(-2 pi i g r / N), r = 1 .. R1-1: powers of ONE per-lane root.
+// MirrorTwiddles keeps t_1, t_2, t_3, t_4, t_8, t_12 (the first three from the table, exact to one rounding; t_2, t_3, t_8,
+// t_12 read from the table too, so no power carries more than one rounding) in registers for the whole persistent
+// kernel and forms t_r = t_(r mod 4) * t_(r - r mod 4) on the fly: at most one complex product per twiddle instead of one
+// shared-memory read per twiddle and tile.
+template <class P>
+struct MirrorTwiddles {
+    static constexpr int R1 = Mirror<P>::R1, R0 = Mirror<P>::R0;
+    static_assert(R1 == 16, "digits 1..3 and 4, 8, 12");
+    float2 lo[4], hi[4];  // lo[c] = t_c (c = 1..3), hi[b] = t_(4b) (b = 1..3)
+    MLXA_HD void load(int g, const float2* __restrict__ tw) {
+        for (int c = 1; c < 4; ++c) lo[c] = tw[(c - 1) * R0 + g];
+        for (int b = 1; b < 4; ++b) hi[b] = tw[(4 * b - 1) * R0 + g];
+    }
+    template <int r>
+    MLXA_HD float2 get() const {
+        constexpr int c = r & 3, b = r >> 2;
+        if constexpr (b == 0) return lo[c];
+        else if constexpr (c == 0) return hi[b];
+        else return cmul(lo[c], hi[b]);
+    }
+};
+
 // last pass + powers: pp[k] = (4^(p/2) |A[bin]|^p, 4^(p/2) |B[bin]|^p), bin = Mirror::row(g, k)
-template <class P, int PW>
-MLXA_HD void mirror_last_pass_powers(int g, const float2* buf, const float2* __restrict__ tw, float power, float2* pp) {
+template <class P, int PW, class TW>
+MLXA_HD void mirror_last_pass_powers(int g, const float2* buf, const TW& tw, float power, float2* pp) {
     using M = Mirror<P>;
     constexpr int R0 = M::R0, R1 = M::R1, RS = M::RS;
     float2 a[R1], m[R1];
@@ -61,7 +84,7 @@ MLXA_HD void mirror_last_pass_powers(int g, const float2* buf, const float2* __r
     });
     static_for<R1 - 1>([&](auto r1) {
         constexpr int r = decltype(r1)::value + 1;
-        const float2 t = tw[(r - 1) * R0 + g];
+        const float2 t = tw.template get<r>();
         a[r] = cmul(a[r], t);
         m[r] = cmul_conj(m[r], t);
     });
@@ -77,5 +100,14 @@ MLXA_HD void mirror_last_pass_powers(int g, const float2* buf, const float2* __r
         pp[k] = make_float2(qa, qb);
     });
 }
+
+// the table-read form (one shared-memory read per twiddle): what the last pass used before MirrorTwiddles
+template <class P>
+struct MirrorTwiddleTable {
+    const float2* tw;
+    int g;
+    template <int r>
+    MLXA_HD float2 get() const { return tw[(r - 1) * Mirror<P>::R0 + g]; }
+};
 
 }  // namespace mlxa

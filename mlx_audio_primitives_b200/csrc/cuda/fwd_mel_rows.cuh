@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
     const int o_last = (gi & 1) ? -G : G * (R0 - 1);
     uint32_t ph0 = 0u, ph1 = 0u;
     float vmax = 0.f;
+    MirrorTwiddles<P> mtw;  // the lane's last-pass twiddle roots, resident for the whole kernel
+    mtw.load(g, s_tw);
 
     for (int it = 0; cur.b < p.B; ++it, cur.advance()) {
         const int c = (nbuf == 2) ? (it & 1) : 0;
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
             }, buf);
         }
         __syncwarp();
-        mirror_last_pass_powers<P, PW>(g, buf, s_tw, p.power, pp);
+        mirror_last_pass_powers<P, PW>(g, buf, mtw, p.power, pp);
         __syncthreads();  // every exchange buffer is dead: the power tile may overwrite them
 
         // ---- powers -> tile [bin][frame]; bin of leg k: g + R0*k (k < R1/2) or its mirror ---------

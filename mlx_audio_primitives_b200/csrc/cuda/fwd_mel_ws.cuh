@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(MelWs<P>::THREADS, 1) mel_ws_kernel(const FwdP
         float2* buf = reinterpret_cast<float2*>(s_x) + gi * P::BUF;
         const int sh = (gi & 1) ? G : 0;                    // odd group of a warp: frames rotated by 16 samples
         const int o_last = (gi & 1) ? -G : G * (R0 - 1);
+        MirrorTwiddles<P> mtw;  // the lane's last-pass twiddle roots, resident for the whole kernel
+        mtw.load(g, s_tw);
         for (int it = 0; cur.b < p.B; ++it, cur.advance()) {
             const Tile ti = tile_at(p, TT, cur.b, cur.tile);
             if (ti.n_bulk > 0) {
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(MelWs<P>::THREADS, 1) mel_ws_kernel(const FwdP
                     if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in, bar_in);
                 }
             }
-            mirror_last_pass_powers<P, PW>(g, buf, s_tw, p.power, pp);
+            mirror_last_pass_powers<P, PW>(g, buf, mtw, p.power, pp);
             if (it > 0) mbar_wait(bar_ptfree, (it - 1) & 1);  // the projection of the previous tile has read the power tile
             if (g <= R0 / 2) {
                 float2* lo = reinterpret_cast<float2*>(s_pw) + g * (PS / 2) + gi;

@@ -57,7 +57,9 @@ static void run_mirror(const float* fa, const float* fb, const float* win, int r
         }, buf.data());
     for (int g = 0; g < M::OWNERS; ++g) {
         float2 pp[P::R1];
-        mirror_last_pass_powers<P, POW_SQUARE>(g, buf.data(), tw.data(), 2.f, pp);
+        MirrorTwiddles<P> mtw;
+        mtw.load(g, tw.data());
+        mirror_last_pass_powers<P, POW_SQUARE>(g, buf.data(), mtw, 2.f, pp);
         for (int k = 0; k < P::R1; ++k) { pa[M::row(g, k)] = pp[k].x; pb[M::row(g, k)] = pp[k].y; }
     }
 }
