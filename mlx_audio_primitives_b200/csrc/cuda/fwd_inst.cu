@@ -533,7 +533,12 @@ struct MelRowsVariant {
     }
     template <int PW, bool BS>
     static cudaError_t go2(FwdParams& p, size_t smem, cudaStream_t s) {
-        auto kern = mel_rows_kernel<PL, C::THREADS, PW, BS>;
+        return p.n_in_buf == 0 ? go3<PW, BS, true>(p, smem, s) : go3<PW, BS, false>(p, smem, s);
+    }
+    template <int PW, bool BS, bool SEP>
+    static cudaError_t go3(FwdParams& p, size_t smem, cudaStream_t s) {
+        if (SEP) p.n_in_buf = 1;
+        auto kern = mel_rows_kernel<PL, C::THREADS, PW, BS, SEP>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int dev = 0, n_sm = 0, per_sm = 0;
@@ -552,19 +557,27 @@ struct MelRowsVariant {
         p.bank_in_smem = 1;
         if (C::smem_bytes(p.hop, 1, bw) > kMaxSmem) { p.bank_in_smem = 0; bw = 0; }
         if (C::smem_bytes(p.hop, 1, bw) > kMaxSmem) return cudaErrorInvalidConfiguration;
+        p.tile_frames = C::TT;
+        // preferred: the power tile in shared memory of its own + one staging buffer, when that still leaves the SM
+        // its full set of resident CTAs (MLXA_MEL_NO_SEP=1: the aliased layout, for A/B runs)
+        static const bool no_sep = getenv("MLXA_MEL_NO_SEP") != nullptr;
+        if (!no_sep && C::smem_bytes_sep(p.hop, bw) <= kShare) {
+            p.n_in_buf = 0;  // (marks the SEP instantiation for go2)
+            const size_t smem = C::smem_bytes_sep(p.hop, bw);
+            if (p.power_mode == POW_SQUARE) return go<POW_SQUARE>(p, smem, s);
+            if (p.power_mode == POW_ABS) return go<POW_ABS>(p, smem, s);
+            return go<POW_GENERAL>(p, smem, s);
+        }
         // double-buffer the staging when it does not cost a resident CTA
         const bool fits1 = C::smem_bytes(p.hop, 1, bw) <= kShare;
         const size_t lim = fits1 ? kShare : kMaxSmem;
         p.n_in_buf = (C::smem_bytes(p.hop, 2, bw) <= lim) ? 2 : 1;
-        p.tile_frames = C::TT;
         const size_t smem = C::smem_bytes(p.hop, p.n_in_buf, bw);
         if (p.power_mode == POW_SQUARE) return go<POW_SQUARE>(p, smem, s);
         if (p.power_mode == POW_ABS) return go<POW_ABS>(p, smem, s);
         return go<POW_GENERAL>(p, smem, s);
     }
 };
-// Two 8-warp CTAs (32-frame tiles) per SM, so one CTA's projection / barrier phases overlap the other's
-// transforms (one 16-warp CTA with 64-frame tiles measured slower in round 1).
 template <class PL>
 struct MelRowsLaunch<PL, true> {
     // two barrier-phased 8-warp CTAs per SM (fwd_mel_rows.cuh); MLXA_MEL_WS=1 selects the warp-specialised kernel

@@ -35,15 +35,24 @@ struct MelRows {
     static constexpr size_t smem_bytes(int hop, int nbuf, long long bank_words) {
         return size_t(nbuf) * in_floats(hop) * 4 + size_t(N) * 4 + size_t(TWP) * 8 + size_t(XCH_BYTES) + size_t(bank_words) * 4 + 32;
     }
+    // SEP layout: one staging buffer, and the power tile in shared memory of its own (not over the exchange buffers)
+    static constexpr int XCH_ONLY = NG * P::BUF * 8, PT_BYTES = (PROWS * PS * 4 + 15) & ~15;
+    static constexpr size_t smem_bytes_sep(int hop, long long bank_words) {
+        return size_t(in_floats(hop)) * 4 + size_t(N) * 4 + size_t(TWP) * 8 + size_t(XCH_ONLY) + size_t(PT_BYTES) + size_t(bank_words) * 4 + 32;
+    }
 };
 
-template <class P, int THREADS_, int PW, bool BANK_SMEM>
+// SEP: the power tile has shared memory of its own and the samples a single staging buffer.  The transforms then need
+// no CTA barrier before they park their powers (the barrier that waited for the slowest warp of the tile: 8 % of
+// the warp time, ncu r03d) -- a warp writes as soon as its own last pass is done -- and the next tile's bulk copy
+// is issued right behind the barrier that follows the writes, so it lands under the projection.
+template <class P, int THREADS_, int PW, bool BANK_SMEM, bool SEP = false>
 __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(const FwdParams p) {
     using C = MelRows<P, THREADS_>;
     constexpr int THREADS = C::THREADS, G = C::G, TT = C::TT, N = C::N, R0 = C::R0, R1 = C::R1, PS = C::PS;
     constexpr int NBINS = C::NBINS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nbuf = p.n_in_buf;
+    const int nbuf = SEP ? 1 : p.n_in_buf;
     const int in_floats = C::in_floats(p.hop);
     const long long bank_words = BANK_SMEM ? packed_bank_words(p.n_bands, p.n_w4, -1) : 0;
 
@@ -51,9 +60,10 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
     float* s_win = s_in0 + nbuf * in_floats;
     float2* s_tw = reinterpret_cast<float2*>(s_win + N);
     unsigned char* s_x = reinterpret_cast<unsigned char*>(s_tw + C::TWP);
-    float* s_bank = reinterpret_cast<float*>(s_x + C::XCH_BYTES);
+    // power tile [PROWS][PS]: over the exchange buffers, or (SEP) behind them
+    float* s_pw = reinterpret_cast<float*>(SEP ? s_x + C::XCH_ONLY : s_x);
+    float* s_bank = reinterpret_cast<float*>(s_x + (SEP ? C::XCH_ONLY + C::PT_BYTES : C::XCH_BYTES));
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bank + bank_words);
-    float* s_pw = reinterpret_cast<float*>(s_x);  // power tile [PROWS][PS], aliases the exchange buffers
     __shared__ float s_red[THREADS / 32];
 
     const int tiles_per_clip = (p.T + TT - 1) / TT;
@@ -111,7 +121,7 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
                 TileWalk nxt = cur;
                 nxt.advance();
                 if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0 + (c ^ 1) * in_floats, s_bar + (c ^ 1));
-            } else if (it > 0) {
+            } else if (it > 0 && !SEP) {
                 tile_issue_bulk(ti, s_in0, s_bar + 0);
             }
         }
@@ -142,7 +152,7 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
         }
         __syncwarp();
         mirror_last_pass_powers<P, PW>(g, buf, mtw, p.power, pp);
-        __syncthreads();  // every exchange buffer is dead: the power tile may overwrite them
+        if constexpr (!SEP) __syncthreads();  // every exchange buffer is dead: the power tile may overwrite them
 
         // ---- powers -> tile [bin][frame]; bin of leg k: g + R0*k (k < R1/2) or its mirror ---------
         if (g <= R0 / 2) {
@@ -153,11 +163,18 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
                 if constexpr (k < R1 / 2) lo[R0 * k * (PS / 2)] = pp[k];
                 else hi[R0 * (R1 - 1 - k) * (PS / 2)] = pp[k];
             });
-        } else if (g == R0 / 2 + 1) {
+        } else if (g == R0 / 2 + 1 && (!SEP || it == 0)) {  // (a tile of its own keeps its zero rows)
             float2* z = reinterpret_cast<float2*>(s_pw) + NBINS * (PS / 2) + gi;
             z[0] = z[PS / 2] = z[2 * (PS / 2)] = make_float2(0.f, 0.f);
         }
         __syncthreads();
+        if constexpr (SEP) {  // every warp is past its reads of the staged samples: fetch the next tile under the projection
+            if (threadIdx.x == 0) {
+                TileWalk nxt = cur;
+                nxt.advance();
+                if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0, s_bar + 0);
+            }
+        }
 
         // ---- band-sparse projection, lanes along frames (mel_project.cuh) -----------------------------
         project_power_tile<THREADS / 32, TT, !BANK_SMEM, true>(p, rb, dbc, s_pw, TT, ti.b, ti.t0, nt, pscale, warp, vmax);
