@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
         mbar_init(s_bar + 0, 1);
         mbar_init(s_bar + 1, 1);
         mbar_init(s_bar + 2, 1);
+        if constexpr (SEP) mbar_init(s_bar + 3, THREADS / 32);  // "every warp has projected its share of the tile"
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
         __syncwarp();
         mirror_last_pass_powers<P, PW>(g, buf, mtw, p.power, pp);
         if constexpr (!SEP) __syncthreads();  // every exchange buffer is dead: the power tile may overwrite them
+        else if (it > 0) mbar_wait(s_bar + 3, (it - 1) & 1);  // every warp has read the previous tile's powers (long since)
 
         // ---- powers -> tile [bin][frame]; bin of leg k: g + R0*k (k < R1/2) or its mirror ---------
         if (g <= R0 / 2) {
@@ -178,7 +180,14 @@ __global__ void __launch_bounds__(THREADS_, 512 / THREADS_) mel_rows_kernel(cons
 
         // ---- band-sparse projection, lanes along frames (mel_project.cuh) -----------------------------
         project_power_tile<THREADS / 32, TT, !BANK_SMEM, true>(p, rb, dbc, s_pw, TT, ti.b, ti.t0, nt, pscale, warp, vmax);
-        __syncthreads();  // power tile consumed: the next tile's transforms may reuse the buffers
+        if constexpr (SEP) {
+            // no CTA barrier here: a warp goes straight on to the next tile's transforms (its exchange buffers are its
+            // own) and only checks, before it parks the next powers, that every warp has arrived here
+            __syncwarp();
+            if (lane == 0) mbar_arrive_one(s_bar + 3);
+        } else {
+            __syncthreads();  // power tile consumed: the next tile's transforms may reuse the buffers
+        }
     }
     if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red, p.xchg);
 }
