@@ -53,15 +53,15 @@ MLXA_D void epilogue_bin_global(const FwdParams& p, long long o, float2 X, float
     if constexpr (EP == EP_STFT) {
         p.spec[o] = X;
     } else {
+        // mag * X / |X| with the bare SFU reciprocal square root (rsqrtf() wraps it in a denormal rescue: two
+        // multiplies and a compare per bin).  |X|^2 below the smallest normal (|X| < 1.1e-19) counts as zero.
         const float n2 = fmaf(X.x, X.x, X.y * X.y);
-        float2 nw;
-        if (n2 > 0.f) {
-            const float sc = m * rsqrtf(n2);
-            nw = make_float2(X.x * sc, X.y * sc);
-        } else {
-            nw = make_float2(m, 0.f);  // angle(0) = 0 -> mag * exp(0)
-        }
-        p.rebuilt[o] = nw;  // the momentum extrapolation is fused into the next inverse transform's loader
+        float r;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n2));
+        const float sc = m * r;
+        float2 nw = pmul(X, sc, sc);
+        if (!(n2 >= 1.17549435e-38f)) nw = make_float2(m, 0.f);  // angle(0) = 0 -> mag * exp(0)
+        p.rebuilt[o] = nw;  // (the momentum step happens in the signal domain, inside the next inverse transform)
     }
 }
 template <int EP>

@@ -49,6 +49,13 @@ constexpr int TWP = (P::TW + 1) & ~1, TWU = (NUNPACK + 1) & ~1;
 constexpr bool TW_SMEM = (TWP + TWU) * 8 <= 20 * 1024;
 
 constexpr int round_up4(int v) { return (v + 3) & ~3; }
+// PACK plans: the spectrum -> packed-input step happens inside pass 0's loads (-DMLXA_INV_UNPACK_IN_PLACE: the
+// earlier form, which rewrites the buffer in place and reads it back)
+#ifdef MLXA_INV_UNPACK_IN_PLACE
+constexpr bool FUSED_UNPACK = false;
+#else
+constexpr bool FUSED_UNPACK = PACK;
+#endif
 
 MLXA_D float2 load_bin(const float2* __restrict__ X, int k, bool ok) {
     return ok ? __ldg(X + k) : make_float2(0.f, 0.f);
@@ -154,10 +161,35 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
             //    Z[k] = E + iO, Z[N-k] = conj(E) + i*conj(O), E = (X[k] + conj X[N-k])/2,
             //    O = conj(w^k) (X[k] - conj X[N-k])/2.
             constexpr int N = P::N;
-            constexpr int NQ1 = ceil_div(N + 1, P::G), NQ2 = ceil_div(N / 2 + 1, P::G);
             static_assert(P::BUF >= N + 1, "exchange buffer must hold the Nyquist bin");
             cp_async_wait_all();
             group_sync<P::G>(gi);
+            if constexpr (FUSED_UNPACK) {
+                // ... and pass 0 builds each of its inputs Z[n] from X[n] and X[N-n] as it loads them: the same formula
+                // holds for every n in [0, N) (E[N-k] = conj E[k], and conj(w^(N-k)) = -w^k makes O[N-k] = conj O[k]).
+                // Each pair is evaluated twice (once per end) but Z never takes a round trip through shared memory.
+                constexpr int R = P::radix(0), NB = P::nb(0), RD = P::rounds(0);
+                static_for<RD>([&](auto rd_) {
+                    constexpr int rd = decltype(rd_)::value;
+                    const int bb = g + rd * P::G;
+                    if ((NB % P::G == 0) || bb < NB) {
+                        static_for<R>([&](auto r_) {
+                            constexpr int r = decltype(r_)::value;
+                            constexpr int C = rd * P::G + r * NB;
+                            const int n = g + C;
+                            float2 xk = buf[n], xm = buf[N - n];
+                            if constexpr (C == 0) {
+                                if (g == 0) { xk.y = 0.f; xm.y = 0.f; }  // c2r ignores imag of DC / Nyquist
+                            }
+                            const float2 w = mul_tw<C, 2 * P::N>(tw_base);  // 0.5 * exp(-i*pi*n/N)
+                            const float ex = 0.5f * (xk.x + xm.x), ey = 0.5f * (xk.y - xm.y);
+                            const float2 o = cmul_conj(make_float2(xk.x - xm.x, xk.y + xm.y), w);
+                            v[rd * R + r] = make_float2(ey + o.x, ex - o.y);  // swap(E + iO)
+                        });
+                    }
+                });
+            } else {
+            constexpr int NQ2 = ceil_div(N / 2 + 1, P::G);
             static_for<NQ2>([&](auto q) {
                 constexpr int Q = decltype(q)::value;
                 const int k = g + Q * P::G;
@@ -173,6 +205,7 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
                     if (!(Q == 0 && k == 0)) buf[N - k] = make_float2(o.x - ey, ex + o.y);      // swap(conj E + i conj O)
                 }
             });
+            }
         } else {
             constexpr int N = P::N;
             constexpr int NQ = ceil_div(N / 2 + 1, P::G);
@@ -192,8 +225,10 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
                 }
             });
         }
-        group_sync<P::G>(gi);
-        pass_load_fn<P, 0>(g, v, [&](int n) { return buf[n]; });
+        if constexpr (!FUSED_UNPACK) {
+            group_sync<P::G>(gi);
+            pass_load_fn<P, 0>(g, v, [&](int n) { return buf[n]; });
+        }
         group_sync<P::G>(gi);
         pass_compute<P, 0>(g, v, tw_plan);
         pass_store_buf<P, 0>(g, v, buf);
@@ -282,7 +317,42 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
     // 128-bit path: tile, trim and rows are multiples of four samples and the whole quad lies inside the output
     const bool vec = ((TS | int(p.trim & 3) | int(p.ldy & 3)) & 3) == 0 && wbulk &&
                      ((reinterpret_cast<uintptr_t>(p.y) | reinterpret_cast<uintptr_t>(p.u_prev) | reinterpret_cast<uintptr_t>(p.u_out)) & 15) == 0;
-    if (vec) {
+    // a tile that lies wholly inside the trimmed output (all but a clip's first and last): no per-quad range checks,
+    // 32-bit indexing, every previous-inverse read of the thread in flight before the first quad is finished
+    const long long jb = o0 - p.trim;
+    const bool interior = vec && jb >= 0 && jb + TS <= p.out_len && o0 + TS <= p.ola_len;
+    if (interior) {
+        const float4* a4 = reinterpret_cast<const float4*>(s_acc);
+        const float4* w4 = reinterpret_cast<const float4*>(s_wss);
+        float4* y4 = reinterpret_cast<float4*>(yb + jb);
+        const float4* up4 = upb ? reinterpret_cast<const float4*>(upb + jb) : nullptr;
+        float4* uo4 = uob ? reinterpret_cast<float4*>(uob + jb) : nullptr;
+        const int nq = TS >> 2;
+        const float m = p.momentum;
+        constexpr int U = 8;
+        for (int i0 = threadIdx.x; i0 < nq; i0 += THREADS * U) {
+            float4 up[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * THREADS;
+                up[u] = (up4 && i < nq) ? __ldg(up4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * THREADS;
+                if (i < nq) {
+                    const float4 a = a4[i], w = w4[i];
+                    float4 v = make_float4(__fdividef(a.x, fmaxf(w.x, 1e-8f)), __fdividef(a.y, fmaxf(w.y, 1e-8f)),
+                                           __fdividef(a.z, fmaxf(w.z, 1e-8f)), __fdividef(a.w, fmaxf(w.w, 1e-8f)));
+                    if (uo4) uo4[i] = v;
+                    if (up4)
+                        v = make_float4(fmaf(m, v.x - up[u].x, v.x), fmaf(m, v.y - up[u].y, v.y), fmaf(m, v.z - up[u].z, v.z),
+                                        fmaf(m, v.w - up[u].w, v.w));
+                    y4[i] = v;
+                }
+            }
+        }
+    } else if (vec) {
         constexpr int U = 4;  // quads per thread in flight (the u_prev reads are the only long-latency operation here)
         for (int i0 = threadIdx.x * 4; i0 < TS; i0 += THREADS * 4 * U) {
             float4 up[U];
