@@ -69,7 +69,8 @@ def _units():
         units.append((f"inv_{nf}.o", "inv_inst.cu", inv_flags))
         if nf in ACF_NFFT:  # the pitch kernels: power-of-two transform sizes
             units.append((f"acf_{nf}.o", "acf_inst.cu", [f"-DMLXA_NFFT={nf}"]))
-    return units
+    extra = os.environ.get("MLXA_EXTRA_FLAGS", "").split()  # experiments: e.g. MLXA_EXTRA_FLAGS=-DMLXA_NO_PAIRED_STORE
+    return [(o, src, flags + extra) for o, src, flags in units]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -257,10 +257,40 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
                 if (va && (spaced || ((fa - f_lo) % r) == ph)) {
                     const int off = int((long long)fa * p.hop - o0);  // tile-local start of the frame
                     if (off >= 0 && off + NFFT <= TS && hop_even) {  // frame fully inside the tile
+                        // samples 2n, 2n + 1 = (im, re) of the swapped inverse.  Taken OLA_CH elements at a time -- all window
+                        // and accumulator reads of a chunk, then the packed FMAs, then the writes -- because the compiler
+                        // cannot tell that the window and the accumulator never overlap and would otherwise leave every
+                        // read behind the previous element's write (one exposed shared-memory latency per element).
                         float2* acc2 = reinterpret_cast<float2*>(s_acc + off);
                         const float2* w2 = reinterpret_cast<const float2*>(s_win);
-                        pass_store_fn<P, P::NPASS - 1>(g, v, [&](int n, float2 val) {
-                            acc2[n] = pfma(val.y, val.x, w2[n].x, w2[n].y, acc2[n]);  // samples 2n, 2n + 1 = (im, re) of the swapped inverse
+                        constexpr int LP = P::NPASS - 1;
+                        constexpr int R = P::radix(LP), NB = P::nb(LP), RD = P::rounds(LP), NS = P::ns(LP);
+                        constexpr int OLA_CH = (R % 8 == 0) ? 8 : (R % 5 == 0) ? 5 : (R % 4 == 0) ? 4 : (R % 3 == 0) ? 3 : (R % 2 == 0) ? 2 : 1;
+                        static_for<RD>([&](auto rd_) {
+                            constexpr int rd = decltype(rd_)::value;
+                            const int bb = g + rd * P::G;
+                            if ((NB % P::G == 0) || bb < NB) {
+                                const int base = (bb / NS) * NS * R + (bb % NS);
+                                static_for<R / OLA_CH>([&](auto c_) {
+                                    constexpr int c0 = decltype(c_)::value * OLA_CH;
+                                    float2 wv[OLA_CH], av[OLA_CH];
+                                    static_for<OLA_CH>([&](auto j_) {
+                                        constexpr int j = decltype(j_)::value;
+                                        const int n = base + dft_perm(R, c0 + j) * NS;
+                                        wv[j] = w2[n];
+                                        av[j] = acc2[n];
+                                    });
+                                    static_for<OLA_CH>([&](auto j_) {
+                                        constexpr int j = decltype(j_)::value;
+                                        const float2 val = v[rd * R + c0 + j];
+                                        av[j] = pfma(val.y, val.x, wv[j].x, wv[j].y, av[j]);
+                                    });
+                                    static_for<OLA_CH>([&](auto j_) {
+                                        constexpr int j = decltype(j_)::value;
+                                        acc2[base + dft_perm(R, c0 + j) * NS] = av[j];
+                                    });
+                                });
+                            }
                         });
                     } else {
                         pass_store_fn<P, P::NPASS - 1>(g, v, [&](int n, float2 val) {

@@ -204,13 +204,22 @@ def run(want, iters, sc):
         P = _spectrum_physical(Sc)
         u0, u1, yy = (torch.empty((B, L), device="cuda") for _ in range(3))
         k_ms = event_ms(lambda: _istft_physical(P, N, hop, win, True, None, out=yy, u_prev=u0, momentum=0.99, u_out=u1), 5)
+        # the other kernel of an iteration: forward transform + projection onto the target magnitudes
+        from mlx_audio_primitives_b200._extension import _ext, check
+        from mlx_audio_primitives_b200._tensor import ptr, stream_ptr
+        magp = S.transpose(1, 2).contiguous()
+        cur = torch.empty((B, T, F, 2), dtype=torch.float32, device="cuda")
+        f_ms = event_ms(lambda: check(_ext.mlxa_griffinlim_project_f32(ptr(yy), B, L, yy.stride(0), ptr(win), N, hop, 1, 0, T, T,
+                                                                     ptr(magp), ptr(cur), stream_ptr(yy)), "griffinlim"), 5)
+        del magp, cur
         # per iteration: inverse reads 8FT + 4L (previous inverse), writes 8L; projection reads 4L + 4FT, writes 8FT
         per_it = 8 * F * T + 4 * L + 8 * L + 4 * L + 4 * F * T + 8 * F * T
         by = B * (iters * per_it + 8 * F * T + 12 * L)
         fl = B * T * (iters * (2 * fft_flops(N) + N + 4 * N + 40 * F) + fft_flops(N) + 4 * N)
         report("c5", f"Griffin-Lim 32 it 1024/256 {B}x10 s @22.05k (device RNG init included)", B * 10.0, ms, by, fl,
                {"clips": B, "kernel": "inv_kernel n_fft=1024 (momentum form; 33 launches per call, 32 x fwd_kernel<EP_GL> beside them)",
-                "kernel_ms": k_ms, "kernel_alg_bytes": B * (8 * F * T + 12 * L)})
+                "kernel_ms": k_ms, "kernel_alg_bytes": B * (8 * F * T + 12 * L), "project_kernel_ms": f_ms,
+                "project_kernel_alg_bytes": B * (4 * L + 12 * F * T)})
         del y, Sc, S, P, u0, u1, yy
     if "f1" in want:  # section 8(f) rank 1: the four spectral features of a music batch (C3's shape), from audio
         B, L, N, hop = max(1, int(1024 * sc * 0.125)), 661500, 2048, 512
