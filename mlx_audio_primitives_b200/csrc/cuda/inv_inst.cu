@@ -49,6 +49,17 @@ constexpr int TWP = (P::TW + 1) & ~1, TWU = (NUNPACK + 1) & ~1;
 constexpr bool TW_SMEM = (TWP + TWU) * 8 <= 20 * 1024;
 
 constexpr int round_up4(int v) { return (v + 3) & ~3; }
+// Spaced rounds: a frame only overlaps frames of its own lane group (earlier rounds, same lanes) and of the two
+// neighbouring groups, which live in the same or an adjacent warp.  So a round's overlap-add does not need the whole
+// CTA behind a barrier: a warp waits until its two neighbour warps have finished the PREVIOUS round's adds (one
+// mbarrier per warp and round parity: a neighbour can be at most one round ahead) and signals its own.  The summation
+// order is unchanged.  Two-warp groups (G = 64) keep the CTA barrier.  -DMLXA_INV_CTA_ROUNDS: the barrier everywhere.
+constexpr int NW = THREADS / 32;
+#ifdef MLXA_INV_CTA_ROUNDS
+constexpr bool NEIGHBOUR_ROUNDS = false;
+#else
+constexpr bool NEIGHBOUR_ROUNDS = (P::G <= 32) && NW >= 2;
+#endif
 // PACK plans: the spectrum -> packed-input step happens inside pass 0's loads (-DMLXA_INV_UNPACK_IN_PLACE: the
 // earlier form, which rewrites the buffer in place and reads it back)
 #ifdef MLXA_INV_UNPACK_IN_PLACE
@@ -71,11 +82,15 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
     float2* s_tw = reinterpret_cast<float2*>(s_win + NFFT);
     float2* s_buf = s_tw + (TW_SMEM ? TWP + TWU : 0);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_buf + NG * P::BUF);
+    uint64_t* s_done = s_bar + 2;  // [warp][round parity]: "this warp's overlap-add of the round has landed"
 
     const int b = blockIdx.y;
     const long long o0 = (long long)blockIdx.x * TS;
     const bool cbulk = p.const_bulk != 0;
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
+    if constexpr (NEIGHBOUR_ROUNDS) {
+        if (threadIdx.x < 2 * NW) mbar_init(s_done + threadIdx.x, 1);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(s_bar, (TW_SMEM ? (TWP + TWU) * 8 : 0) + (cbulk ? NFFT * 4 : 0));
@@ -252,6 +267,13 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
 
         // ---- windowed overlap-add into the tile accumulator, r conflict-free phases -------
         // lane-private part of each frame: last pass leaves element n = b + k*NS in v[], i.e. samples 2n, 2n+1
+        const bool nbr = NEIGHBOUR_ROUNDS && spaced;
+        if (nbr && q > 0) {  // the neighbours' adds of round q - 1 (k-th use of that parity's barrier: parity k & 1)
+            const int w = threadIdx.x >> 5;
+            const uint32_t par = uint32_t((q - 1) >> 1) & 1u;
+            mbar_wait(s_done + 2 * ((w + NW - 1) % NW) + ((q - 1) & 1), par);
+            mbar_wait(s_done + 2 * ((w + 1) % NW) + ((q - 1) & 1), par);
+        }
         for (int ph = 0; ph < n_phases; ++ph) {
             if constexpr (PACK) {
                 if (va && (spaced || ((fa - f_lo) % r) == ph)) {
@@ -315,7 +337,12 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
                     }
                 }
             }
-            __syncthreads();
+            if (nbr) {
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) mbar_arrive_one(s_done + 2 * (threadIdx.x >> 5) + (q & 1));
+            } else {
+                __syncthreads();
+            }
         }
     }
     __syncthreads();
@@ -439,7 +466,7 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
 
 static size_t inv_smem_bytes(int hop, int TH) {
     return size_t(round_up4(TH * hop)) * 4 + size_t(NFFT) * 4 + size_t(TW_SMEM ? TWP + TWU : 0) * 8 +
-           size_t(NG) * P::BUF * 8 + 16;
+           size_t(NG) * P::BUF * 8 + 16 + size_t(2 * NW) * 8;
 }
 
 }  // namespace
