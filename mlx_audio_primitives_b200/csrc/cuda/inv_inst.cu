@@ -197,9 +197,9 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
                                 if (g == 0) { xk.y = 0.f; xm.y = 0.f; }  // c2r ignores imag of DC / Nyquist
                             }
                             const float2 w = mul_tw<C, 2 * P::N>(tw_base);  // 0.5 * exp(-i*pi*n/N)
-                            const float ex = 0.5f * (xk.x + xm.x), ey = 0.5f * (xk.y - xm.y);
-                            const float2 o = cmul_conj(make_float2(xk.x - xm.x, xk.y + xm.y), w);
-                            v[rd * R + r] = make_float2(ey + o.x, ex - o.y);  // swap(E + iO)
+                            const float2 e2 = cadd_conj(xk, xm);                   // 2 E
+                            const float2 o = cmul_conj(csub_conj(xk, xm), w);      // O (the 1/2 rides on w)
+                            v[rd * R + r] = pfma(e2.y, e2.x, 0.5f, 0.5f, make_float2(o.x, -o.y));  // swap(E + iO)
                         });
                     }
                 });
