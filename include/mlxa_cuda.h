@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MLXA_ABI_VERSION 5
+#define MLXA_ABI_VERSION 6
 
 #define MLXA_E_INVALID (-1)   /* bad size / null pointer / unknown mode            */
 #define MLXA_E_UNSUPPORTED (-2)
@@ -187,6 +187,13 @@ int mlxa_polar_f32(const float* mag, const float* angles, int64_t n, mlxa_c64* o
  * the Griffin-Lim phase init (griffinlim.py:112-115) while keeping seeds reproducible. */
 int mlxa_pcg64_uniform_f32(uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo,
                            double low, double high, int64_t n, float* out, void* stream);
+
+/* Griffin-Lim's random start in one pass (griffinlim.py:112-123): out[b,t,f] = mag[b,t,f] * exp(i * a), a the
+ * ((b*F + f)*T + t)-th value of the stream above -- the phases are drawn in the reference's logical (B, F, T) order
+ * while magnitudes and spectrum live in the physical (B, T, F) layout; the angle tensor never exists in HBM.
+ * Bit-identical to mlxa_pcg64_uniform_f32 + a transpose + mlxa_polar_f32. */
+int mlxa_pcg64_polar_f32(uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo, double low, double high,
+                         const float* mag, int64_t B, int64_t F, int64_t T, mlxa_c64* out, void* stream);
 
 /* |z| and atan2(im, re) over n complex values (stft.py:347-379) */
 int mlxa_magnitude_f32(const mlxa_c64* z, int64_t n, float* out, void* stream);

@@ -12,7 +12,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MLXA_CUDA_LIB", os.path.join(_HERE, "_lib", "libmlxaudio_cuda.so"))
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _i64, _i32, _f32, _f64, _p = C.c_int64, C.c_int, C.c_float, C.c_double, C.c_void_p
 
@@ -36,6 +36,7 @@ SIGNATURES = {
     "mlxa_polar_f32": [_p, _p, _i64, _p, _p],
     "mlxa_momentum_f32": [_p, _p, _f32, _i64, _p, _p],
     "mlxa_pcg64_uniform_f32": [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_double, _i64, _p, _p],
+    "mlxa_pcg64_polar_f32": [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_double, _p, _i64, _i64, _i64, _p, _p],
     "mlxa_magnitude_f32": [_p, _i64, _p, _p],
     "mlxa_phase_f32": [_p, _i64, _p, _p],
     "mlxa_transpose_f32": [_p, _i64, _i64, _i64, _p, _p],

@@ -12,6 +12,7 @@
 #include "../../../include/mlxa_cuda.h"
 #include "common.cuh"
 #include "fft_sizes.cuh"
+#include "pcg64.cuh"
 #include "util_kernels.cuh"
 
 namespace mlxa {
@@ -441,6 +442,21 @@ int mlxa_pcg64_uniform_f32(uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi
     CHECK_ARG(out && n > 0, "bad argument");
     CHECK_CUDA(run_pcg64_uniform(state_hi, state_lo, inc_hi, inc_lo, low, high - low, n, out, (cudaStream_t)stream), "pcg64_uniform");
     return 0;
+}
+int mlxa_pcg64_polar_f32(uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo, double low, double high,
+                         const float* mag, int64_t B, int64_t F, int64_t T, mlxa_c64* out, void* stream) {
+    CHECK_ARG(mag && out && B > 0 && F > 0 && T > 0, "bad argument");
+    CHECK_ARG(B * F * T < (int64_t(1) << 47), "stream offset too large");
+    return for_clip_slabs(B, [&](int64_t b0, int64_t nb) {  // the batch rides on grid.z: slabs of <= 65535 clips
+        // a slab starts b0*F*T draws into the stream: fold that offset into the state on the host
+        unsigned __int128 st = ((unsigned __int128)state_hi << 64) | state_lo;
+        const unsigned __int128 inc = ((unsigned __int128)inc_hi << 64) | inc_lo;
+        if (b0) st = mlxa::pcg_advance(st, inc, (unsigned long long)(b0 * F * T));
+        CHECK_CUDA(run_pcg64_polar((unsigned long long)(st >> 64), (unsigned long long)st, inc_hi, inc_lo, low, high - low,
+                                   mag + b0 * F * T, nb, F, T, reinterpret_cast<float2*>(out) + b0 * F * T, (cudaStream_t)stream),
+                   "pcg64_polar");
+        return 0;
+    });
 }
 int mlxa_magnitude_f32(const mlxa_c64* z, int64_t n, float* out, void* stream) {
     CHECK_ARG(z && out && n > 0, "bad argument");

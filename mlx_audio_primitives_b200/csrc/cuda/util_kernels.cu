@@ -468,6 +468,7 @@ cudaError_t launch_irdft_naive(const float2* spec, long long rows, int F_in, int
 
 // ---- NumPy-compatible uniform stream (pcg64.cuh): each thread jumps to its chunk ---------------
 constexpr int kPcgChunk = 32;
+constexpr int kPcgJumpBits = 48;  // stream offsets below 2^48 draws
 __global__ void pcg64_uniform_kernel(unsigned long long s_hi, unsigned long long s_lo, unsigned long long i_hi,
                                      unsigned long long i_lo, double low, double range, long long n, float* __restrict__ out) {
     const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -482,6 +483,62 @@ cudaError_t run_pcg64_uniform(unsigned long long s_hi, unsigned long long s_lo, 
                               unsigned long long i_lo, double low, double range, long long n, float* out, cudaStream_t s) {
     const long long chunks = (n + kPcgChunk - 1) / kPcgChunk;
     pcg64_uniform_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, s>>>(s_hi, s_lo, i_hi, i_lo, low, range, n, out);
+    return cudaGetLastError();
+}
+
+// ---- Griffin-Lim's random start in one pass: S * exp(i * uniform(-pi, pi)) in the physical (B, T, F) layout -----
+// The phases are NumPy's stream drawn in LOGICAL (B, F, T) order (reference griffinlim.py:112-123), so value
+// n = (b*F + f)*T + t belongs at physical element (b, t, f).  A block owns 32 bins x kInitT frames of one clip: each
+// thread jumps to the start of a run of kInitRun frames of one bin (one multiply-add per set bit of the offset, from the
+// host-built table of 2^i-step multipliers), draws the run into a shared tile, and the block then walks the tile
+// along the bins: coalesced reads of the magnitudes and writes of the complex spectrum.  The angles never exist in HBM.
+constexpr int kInitT = 256, kInitRun = 32;
+struct PcgJumpTable {
+    unsigned long long m_hi[kPcgJumpBits], m_lo[kPcgJumpBits], p_hi[kPcgJumpBits], p_lo[kPcgJumpBits];
+};
+__global__ void __launch_bounds__(256) pcg64_polar_kernel(const PcgJumpTable tbl, unsigned long long s_hi, unsigned long long s_lo,
+                                                          unsigned long long i_hi, unsigned long long i_lo, double low, double range,
+                                                          const float* __restrict__ mag, long long F, long long T,
+                                                          float2* __restrict__ out) {
+    __shared__ float s_ang[kInitT][33];
+    const int fi = threadIdx.x & 31, ch = threadIdx.x >> 5;
+    const long long b = blockIdx.z, f = (long long)blockIdx.y * 32 + fi, t0 = (long long)blockIdx.x * kInitT;
+    const long long ts = t0 + ch * kInitRun;
+    if (f < F && ts < T) {
+        const u128 inc = ((u128)i_hi << 64) | i_lo;
+        u128 st = ((u128)s_hi << 64) | s_lo;
+        unsigned long long delta = (unsigned long long)((b * F + f) * T + ts);
+        for (int i = 0; delta != 0; ++i, delta >>= 1)
+            if (delta & 1) st = st * (((u128)tbl.m_hi[i] << 64) | tbl.m_lo[i]) + (((u128)tbl.p_hi[i] << 64) | tbl.p_lo[i]);
+        const int m = (int)min((long long)kInitRun, T - ts);
+        for (int j = 0; j < m; ++j) s_ang[ch * kInitRun + j][fi] = pcg_uniform_f32(st, inc, low, range);
+    }
+    __syncthreads();
+    if (f < F) {
+        const int m = (int)max(0LL, min((long long)kInitRun, T - ts));
+#pragma unroll 4
+        for (int j = 0; j < m; ++j) {
+            const long long o = (b * T + ts + j) * F + f;
+            float sn, cs;
+            sincosf(s_ang[ch * kInitRun + j][fi], &sn, &cs);
+            const float mg = __ldg(mag + o);
+            out[o] = make_float2(mg * cs, mg * sn);
+        }
+    }
+}
+cudaError_t run_pcg64_polar(unsigned long long s_hi, unsigned long long s_lo, unsigned long long i_hi, unsigned long long i_lo,
+                            double low, double range, const float* mag, long long B, long long F, long long T, float2* out,
+                            cudaStream_t s) {
+    PcgJumpTable tbl;  // step 2^i of s <- s*mult + inc:  M_0 = mult, P_0 = inc;  M_{i+1} = M_i^2, P_{i+1} = (M_i + 1) P_i
+    u128 m = pcg_mult(), pl = ((u128)i_hi << 64) | i_lo;
+    for (int i = 0; i < kPcgJumpBits; ++i) {
+        tbl.m_hi[i] = (unsigned long long)(m >> 64); tbl.m_lo[i] = (unsigned long long)m;
+        tbl.p_hi[i] = (unsigned long long)(pl >> 64); tbl.p_lo[i] = (unsigned long long)pl;
+        pl = (m + 1) * pl;
+        m *= m;
+    }
+    dim3 grid((unsigned)((T + kInitT - 1) / kInitT), (unsigned)((F + 31) / 32), (unsigned)B);
+    pcg64_polar_kernel<<<grid, 256, 0, s>>>(tbl, s_hi, s_lo, i_hi, i_lo, low, range, mag, F, T, out);
     return cudaGetLastError();
 }
 

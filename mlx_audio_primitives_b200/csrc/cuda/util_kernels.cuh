@@ -31,6 +31,9 @@ cudaError_t run_dct(const float* x, long long rows, int n_in, const float* D, in
 cudaError_t run_mfcc_tail(const float* mel, long long B, int n_mels, long long T, const float* D, int n_mfcc,
                           const float* lifter, int apply_db, float amin, float ref, int use_top, float top_db,
                           const float* gmax, float* out, cudaStream_t s);
+cudaError_t run_pcg64_polar(unsigned long long s_hi, unsigned long long s_lo, unsigned long long i_hi, unsigned long long i_lo,
+                            double low, double range, const float* mag, long long B, long long F, long long T, float2* out,
+                            cudaStream_t s);
 cudaError_t run_pcg64_uniform(unsigned long long s_hi, unsigned long long s_lo, unsigned long long i_hi,
                               unsigned long long i_lo, double low, double range, long long n, float* out, cudaStream_t s);
 // feat_kernels.cu

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from ._extension import _ext, check
-from ._tensor import f32c, ptr, stream_ptr
+from ._tensor import f32c, ptr, stream_ptr, to_tensor
 from ._validation import validate_positive, validate_range
 from .mel import frames_or_raise, pad_mode_code
 from .stft import _istft_geometry, _istft_physical, istft, magnitude, phase, stft
@@ -14,7 +14,8 @@ from .windows import padded_window
 
 
 def _to_physical_f32(x: torch.Tensor) -> torch.Tensor:
-    """logical (B, F, T) float32 -> contiguous (B, T, F)."""
+    """logical (B, F, T) float32 -> contiguous (B, T, F).  A spectrogram that already is a transposed view of the
+    physical layout -- what magnitude(stft(y)) returns -- is used as it lies: no copy."""
     P = x.transpose(1, 2)
     if P.is_contiguous():
         return P
@@ -53,7 +54,9 @@ def griffinlim(S, n_iter: int = 32, hop_length: int | None = None, win_length: i
     reproduce -- generated on the device by a bit-identical PCG64 kernel (no host draw, no upload)."""
     validate_positive(n_iter, "n_iter")
     validate_range(momentum, "momentum", min_val=0.0, max_val=1.0, max_inclusive=False)
-    S = f32c(S)
+    S = to_tensor(S, torch.float32)  # (made dense in the physical layout below: a (B, T, F)-backed view costs nothing)
+    if S.ndim not in (2, 3):
+        raise ValueError(f"S must be (freq_bins, n_frames) or (batch, freq_bins, n_frames), got shape {tuple(S.shape)}")
     batched = S.ndim == 3
     if not batched:
         S = S[None]
@@ -66,21 +69,29 @@ def griffinlim(S, n_iter: int = 32, hop_length: int | None = None, win_length: i
         win_length = n_fft
     mode = pad_mode_code(pad_mode)
     rng = np.random.default_rng(random_state)
-    if init == "random":
-        angles = _uniform_phase(rng, (B, F, T), S.device)
-    elif init == "zeros":
-        angles = torch.zeros((B, F, T), dtype=torch.float32, device=S.device)
-    else:
+    if init not in ("random", "zeros"):
         raise ValueError(f"Unknown init: '{init}'. Supported: 'random', 'zeros'")
     win = padded_window(window, win_length, n_fft)
     mag = _to_physical_f32(S)                 # (B, T, F)
-    ang = _to_physical_f32(angles)
     # One projected spectrum lives in HBM.  The momentum extrapolation rebuilt = new + m*(new - tprev) is taken
     # through the (linear) inverse transform: istft(rebuilt) = u + m*(u - u_prev) with u = istft(new), so each
     # iteration keeps the previous inverse (a signal) instead of the previous projection (a spectrum).
     cur = torch.empty((B, T, F, 2), dtype=torch.float32, device=S.device)
-    check(_ext.mlxa_polar_f32(ptr(mag), ptr(ang), mag.numel(), ptr(cur), stream_ptr(S)), "polar")
-    del ang, angles
+    st = rng.bit_generator.state
+    if init == "random" and mag.numel() and st.get("bit_generator") == "PCG64":
+        # S * exp(i * uniform(-pi, pi)) in one kernel: the phases of the reference's (B, F, T)-ordered draw land
+        # at their physical (B, T, F) positions, the angle tensor is never written
+        state, inc, m64 = int(st["state"]["state"]), int(st["state"]["inc"]), (1 << 64) - 1
+        check(_ext.mlxa_pcg64_polar_f32(state >> 64, state & m64, inc >> 64, inc & m64, -np.pi, np.pi, ptr(mag), B, F, T,
+                                        ptr(cur), stream_ptr(S)), "pcg64_polar")
+        rng.bit_generator.advance(B * F * T)  # keep a caller-supplied Generator in step with what was consumed
+    else:
+        angles = (_uniform_phase(rng, (B, F, T), S.device) if init == "random"
+                  else torch.zeros((B, F, T), dtype=torch.float32, device=S.device))
+        ang = _to_physical_f32(angles)
+        if mag.numel():
+            check(_ext.mlxa_polar_f32(ptr(mag), ptr(ang), mag.numel(), ptr(cur), stream_ptr(S)), "polar")
+        del ang, angles
     spec = torch.view_as_complex(cur)
     y = u = u_prev = None
     for it in range(n_iter + 1):  # n_iter projections, n_iter + 1 inverse transforms (reference griffinlim.py:129-183)

@@ -426,6 +426,33 @@ def test_device_rng_is_numpy_pcg64(ap):
     assert np.array_equal(a, ref[:1000].astype(np.float32)) and np.array_equal(b, ref[1000:])
 
 
+def test_fused_random_start_matches_draw_transpose_polar(ap):
+    """S * exp(i * uniform) in one kernel (phases drawn in logical (B, F, T) order, written at their physical
+    (B, T, F) positions) == NumPy's stream, transposed, through cos / sin: bit for bit against the unfused kernels,
+    and against NumPy to float32 rounding of cos / sin."""
+    from mlx_audio_primitives_b200._extension import _ext, check
+    from mlx_audio_primitives_b200._tensor import ptr, stream_ptr
+    from mlx_audio_primitives_b200.griffinlim import _polar, _uniform_phase
+    for seed, (B, F, T) in [(0, (2, 257, 33)), (9, (1, 513, 300)), (3, (3, 5, 1000)), (4, (2, 33, 1))]:
+        mag = torch.rand((B, T, F), device="cuda") + 0.1  # physical layout
+        st = np.random.default_rng(seed).bit_generator.state["state"]
+        m64 = (1 << 64) - 1
+        out = torch.empty((B, T, F, 2), device="cuda")
+        check(_ext.mlxa_pcg64_polar_f32(st["state"] >> 64, st["state"] & m64, st["inc"] >> 64, st["inc"] & m64, -np.pi, np.pi,
+                                        ptr(mag), B, F, T, ptr(out), stream_ptr(mag)), "pcg64_polar")
+        ang = _uniform_phase(np.random.default_rng(seed), (B, F, T), torch.device("cuda"))
+        want = torch.view_as_real(_polar(mag.transpose(1, 2).contiguous(), ang)).permute(0, 2, 1, 3)  # -> (B, T, F, 2)
+        assert torch.equal(out, want.contiguous())
+        a = np.random.default_rng(seed).uniform(-np.pi, np.pi, (B, F, T)).transpose(0, 2, 1)
+        ref = H(mag).astype(np.float64)[..., None] * np.stack([np.cos(a), np.sin(a)], -1)
+        assert np.abs(H(out) - ref).max() <= 1e-6
+    # the public entry point takes the fused path and leaves a caller's generator where the reference would
+    S = torch.rand((2, 65, 40), device="cuda") + 0.1
+    g = np.random.default_rng(11)
+    ap.griffinlim(S, n_iter=1, hop_length=32, random_state=g)
+    assert g.uniform() == np.random.default_rng(11).uniform(size=2 * 65 * 40 + 1)[-1]
+
+
 def test_griffinlim_quality_and_errors(ap):
     """reference tests/test_griffinlim.py:31,100-121: spectral MSE thresholds per iteration count"""
     t = np.arange(22050) / 22050.0  # chirp + noise, the reference's benchmark signal (benchmarks/utils.py:92-115)
