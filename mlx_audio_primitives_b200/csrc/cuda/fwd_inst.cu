@@ -59,7 +59,7 @@ __host__ __device__ inline SmemLayout smem_layout(int ep, int NG, int hop, int T
     const int pt_bytes = (ep == EP_MEL) ? power_tile_rows(NBINS) * power_tile_stride(TT) * 4 : 0;
     s.xch_bytes = (NG * P::BUF * 8 > pt_bytes) ? NG * P::BUF * 8 : ((pt_bytes + 15) & ~15);
     s.mel_floats = (ep == EP_MEL && bank_in_smem) ? (int)packed_bank_words(n_bands, n_w4, -1) : 0;
-    s.bytes = size_t(n_in_buf * s.in_floats + NFFT + s.mel_floats) * 4 + size_t(s.tw_f2) * 8 + size_t(s.xch_bytes) + 32;
+    s.bytes = size_t(n_in_buf * s.in_floats + NFFT + s.mel_floats) * 4 + size_t(s.tw_f2) * 8 + size_t(s.xch_bytes) + 48;
     return s;
 }
 
@@ -140,6 +140,18 @@ template <int EP, int PW>
 __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threads_for(EP)) fwd_kernel(const FwdParams p) {
     constexpr int THREADS = threads_for(EP);
     constexpr int NG = THREADS / P::G;  // transforms in flight per CTA
+    // Mel epilogue of the register-unpack plans: two of the three CTA barriers per tile are split into an arrival and
+    // a wait with work between them (mbarriers counted per warp).  "Exchange buffers are free" is signalled right
+    // after a warp's last read of its buffer and awaited only before the powers are parked -- the whole last pass and
+    // the unpack lie between; "projection done" is signalled after a warp's bands and awaited before the NEXT tile's
+    // first write into the exchange buffers -- its window/sample loads and pass-0 butterflies lie between.  Only the
+    // barrier between parking the powers and projecting them (every warp reads every column) stays a barrier.
+#ifdef MLXA_NO_SPLIT_SYNC
+    constexpr bool SPLIT_SYNC = false;
+#else
+    constexpr bool SPLIT_SYNC = EP == EP_MEL && PF::MODE == MODE_PACK && P::NPASS == 2 && P::G <= 32 &&
+                                (P::nb(P::NPASS - 1) % P::G == 0) && P::rounds(1) <= 2;  // = REG_UNPACK below
+#endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TT = p.tile_frames;
     const int nbuf = p.n_in_buf;
@@ -165,6 +177,10 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
         mbar_init(s_bar + 0, 1);
         mbar_init(s_bar + 1, 1);
         mbar_init(s_bar + 2, 1);
+        if constexpr (SPLIT_SYNC) {
+            mbar_init(s_bar + 3, THREADS / 32);  // "this warp has read its exchange buffer for the last time" (this tile)
+            mbar_init(s_bar + 4, THREADS / 32);  // "this warp has projected its share of the tile"
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -208,6 +224,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
     constexpr bool UNPACK_IMM = PACK && ((EP != EP_MEL && EP != EP_FEAT) || !TW_SMEM);
     [[maybe_unused]] const float2 tw_base = UNPACK_IMM ? tw_unpack[g] : make_float2(0.f, 0.f);
     uint32_t ph0 = 0u, ph1 = 0u;  // parity of the next completion on each staging barrier
+    [[maybe_unused]] uint32_t ph_free = 0u, ph_proj = 0u;  // ... and on the two split barriers
     float vmax = 0.f;
 
     for (int it = 0; cur.b < p.B; ++it, cur.advance()) {
@@ -291,6 +308,12 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 pair_zero_b = __all_sync(gm, (orb << 1) == 0u);
             }
             pass_compute<P, 0>(g, v, tw_plan);
+            if constexpr (SPLIT_SYNC) {
+                if (it > 0 && base == 0) {  // the previous tile's power tile (over the exchange buffers) has been projected by every warp
+                    mbar_wait(s_bar + 4, ph_proj);
+                    ph_proj ^= 1u;
+                }
+            }
             pass_store_buf<P, 0>(g, v, buf);
             if (nbuf == 1 && EP != EP_MEL && base + NG * FPT >= nt) {
                 // One staging buffer, last round of the tile: every transform has read its samples, so the next
@@ -307,6 +330,9 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             }
             pass_load_buf<P, 1>(g, v, buf);
             group_sync<P::G>(gi);
+            if constexpr (SPLIT_SYNC) {
+                if ((threadIdx.x & 31) == 0) mbar_arrive_one(s_bar + 3);
+            }
             // Griffin-Lim: the first GL_EARLY target magnitudes of the lane go out before the last pass' butterflies, so
             // their (L2) latency hides under the arithmetic; the rest follow in the epilogue (registers: E + NQ would
             // not fit beside the transform)
@@ -400,7 +426,12 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                     }
                 });
                 // every group is past its unpack reads: the power tile may overwrite the exchange buffers
-                __syncthreads();
+                if constexpr (SPLIT_SYNC) {
+                    mbar_wait(s_bar + 3, ph_free);
+                    ph_free ^= 1u;
+                } else {
+                    __syncthreads();
+                }
                 // ... and past its reads of the staged samples: with a single staging buffer the next tile's
                 // bulk copy starts now and lands under the projection instead of stalling the next transforms
                 if (nbuf == 1 && threadIdx.x == 0) {
@@ -424,6 +455,10 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 __syncthreads();
                 if (p.bank_in_smem) project_power_tile<THREADS / 32, 0, false>(p, rb_smem, dbc, s_pw, TT, b, t0, nt, 1.f, threadIdx.x >> 5, vmax);
                 else project_power_tile<THREADS / 32, 0, false>(p, rb_glob, dbc, s_pw, TT, b, t0, nt, 1.f, threadIdx.x >> 5, vmax);
+                if constexpr (SPLIT_SYNC) {
+                    __syncwarp();
+                    if ((threadIdx.x & 31) == 0) mbar_arrive_one(s_bar + 4);
+                }
             } else if constexpr (EP == EP_FEAT && P::G > 32) {
                 // (not reachable: the launcher refuses EP_FEAT for two-warp groups -- the reductions are warp shuffles)
             } else if constexpr (EP == EP_FEAT) {
@@ -496,7 +531,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             group_sync<P::G>(gi);
         }
 
-        __syncthreads();  // tile done: its staging buffer and the power tile may be overwritten
+        if constexpr (!SPLIT_SYNC) __syncthreads();  // tile done: its staging buffer and the power tile may be overwritten
     }
     if constexpr (EP == EP_MEL) {
         if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red, p.xchg);
