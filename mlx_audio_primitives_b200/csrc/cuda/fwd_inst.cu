@@ -152,6 +152,17 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
     constexpr bool SPLIT_SYNC = EP == EP_MEL && PF::MODE == MODE_PACK && P::NPASS == 2 && P::G <= 32 &&
                                 (P::nb(P::NPASS - 1) % P::G == 0) && P::rounds(1) <= 2;  // = REG_UNPACK below
 #endif
+    // Store-through and feature epilogues: lane groups never share an exchange buffer, so the only CTA-wide hazard is
+    // the staging buffer being refilled while a slow warp still reads the previous tile from it.  That is the classic
+    // full / empty pair: every warp signals "my reads of this buffer are done" on an mbarrier after its last pass-0
+    // load of the tile, and only the thread that issues the next bulk copy waits for it -- no CTA barrier per tile.
+#ifdef MLXA_NO_EMPTY_SYNC
+    constexpr bool EMPTY_SYNC = false;
+#else
+    // Measured per epilogue (profiles/r04u_*): the store-through kernels gain 1-11 % on every plan but n_fft = 4096
+    // (one 8-warp CTA per SM: +5 %); the feature kernels lose 20 % without the per-tile barrier and keep it.
+    constexpr bool EMPTY_SYNC = (EP == EP_STFT || EP == EP_GL) && NFFT != 4096;
+#endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TT = p.tile_frames;
     const int nbuf = p.n_in_buf;
@@ -180,6 +191,10 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
         if constexpr (SPLIT_SYNC) {
             mbar_init(s_bar + 3, THREADS / 32);  // "this warp has read its exchange buffer for the last time" (this tile)
             mbar_init(s_bar + 4, THREADS / 32);  // "this warp has projected its share of the tile"
+        }
+        if constexpr (EMPTY_SYNC) {
+            mbar_init(s_bar + 3, THREADS / 32);  // "this warp has read staging buffer 0 for the last time" (this tile)
+            mbar_init(s_bar + 4, THREADS / 32);  // ... staging buffer 1
         }
     }
     __syncthreads();
@@ -237,10 +252,15 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             if (nbuf == 2) {
                 TileWalk nxt = cur;
                 nxt.advance();
-                if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0 + (c ^ 1) * lay.in_floats, s_bar + (c ^ 1));
+                if (nxt.b < p.B) {
+                    // buffer c ^ 1 held tile it - 1: its ((it - 1) / 2)-th use
+                    if (EMPTY_SYNC && it > 0) mbar_wait(s_bar + 3 + (c ^ 1), uint32_t((it - 1) >> 1) & 1u);
+                    tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0 + (c ^ 1) * lay.in_floats, s_bar + (c ^ 1));
+                }
             }  // one buffer: the copy was started as soon as the previous tile's samples had been read (below)
         }
         if (ti.nl + ti.nr) {  // CTA-uniform: a clip's first / last tile
+            if constexpr (EMPTY_SYNC) __syncthreads();  // (no warp may still be reading an earlier tile from this buffer)
             tile_fill_edges<THREADS>(p, ti, s_in);
             __syncthreads();
         }
@@ -315,10 +335,24 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 }
             }
             pass_store_buf<P, 0>(g, v, buf);
-            if (nbuf == 1 && EP != EP_MEL && base + NG * FPT >= nt) {
-                // One staging buffer, last round of the tile: every transform has read its samples, so the next
-                // tile's bulk copy starts now and lands under the rest of this round instead of stalling the
-                // next tile (EP_MEL does the same at its first CTA barrier).
+            if constexpr (EMPTY_SYNC) {
+                if (base + NG * FPT >= nt) {  // last round of the tile: this warp is done with the staged samples
+                    __syncwarp();
+                    if ((threadIdx.x & 31) == 0) mbar_arrive_one(s_bar + 3 + c);
+                    // One staging buffer: as soon as every warp has said so, the next tile's bulk copy starts and lands
+                    // under the rest of this round instead of stalling the next tile (only the issuing thread waits)
+                    if (nbuf == 1 && threadIdx.x == 0) {
+                        TileWalk nxt = cur;
+                        nxt.advance();
+                        if (nxt.b < p.B) {
+                            mbar_wait(s_bar + 3, uint32_t(it) & 1u);
+                            tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0, s_bar + 0);
+                        }
+                    }
+                }
+                group_sync<P::G>(gi);
+            } else if (nbuf == 1 && EP != EP_MEL && base + NG * FPT >= nt) {
+                // (the CTA-barrier form of the above)
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     TileWalk nxt = cur;
@@ -531,7 +565,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             group_sync<P::G>(gi);
         }
 
-        if constexpr (!SPLIT_SYNC) __syncthreads();  // tile done: its staging buffer and the power tile may be overwritten
+        if constexpr (!SPLIT_SYNC && !EMPTY_SYNC) __syncthreads();  // tile done: its staging buffer and the power tile may be overwritten
     }
     if constexpr (EP == EP_MEL) {
         if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red, p.xchg);
