@@ -171,6 +171,9 @@ MLXA_D void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, 
 MLXA_D void cp_async8(void* dst_smem, const void* src_gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
+MLXA_D void cp_async4(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
 MLXA_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 MLXA_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 MLXA_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }

@@ -3,6 +3,7 @@
 // elementwise complex helpers and the O(n^2) DFT used for n_fft values without a compiled plan.
 #include <algorithm>
 #include "fwd_epilogue.cuh"
+#include <cstdlib>
 #include "pcg64.cuh"
 #include "util_kernels.cuh"
 
@@ -344,6 +345,97 @@ __global__ void mfcc_tail_kernel(const float* __restrict__ mel, int n_mels, long
     }
 }
 
+// The same tail as a register-tiled product (the default): a CTA takes 128 frames of one clip; every thread first
+// converts its own mel column to dB into a shared [n_mels][128] tile (coalesced reads along T, no transposition);
+// then a warp owns 32 frames x all coefficients, lane = (coefficient group of KT, four consecutive frames): per mel
+// band KT/2 64-bit reads of the transposed, zero-padded DCT row, one 128-bit read of four dB values and 2*KT packed
+// FMAs -- 0.65 instructions and 0.005 shared-memory wavefronts per multiply-add; the kernel above spends 3 and 0.06,
+// and reloads the DCT matrix for every 32 frames (c4: 0.92 ms of 6.4).
+constexpr int kTailFrames = 128;
+template <int KT>
+__global__ void __launch_bounds__(kTailFrames)
+mfcc_tail_tiled_kernel(const float* __restrict__ mel, int n_mels, long long T, const float* __restrict__ D, int n_mfcc,
+                       const float* __restrict__ lifter, int apply_db, float amin, float ref, int use_top, float top_db,
+                       const float* __restrict__ gmax, float* __restrict__ out) {
+    static_assert(KT % 2 == 0, "coefficient pairs");
+    constexpr int ROW = 4 * KT;                   // padded coefficients per DCT row
+    extern __shared__ __align__(16) float s_tail[];
+    float* s_x = s_tail;                          // [n_mels][128] dB values
+    float* s_d = s_tail + n_mels * kTailFrames;   // [n_mels][ROW]: D^T, zero beyond n_mfcc
+    const long long b = blockIdx.y, t0 = (long long)blockIdx.x * kTailFrames, t = t0 + threadIdx.x;
+    const float refc = fmaxf(ref, amin);
+    float floor_db = -INFINITY;
+    if (apply_db && use_top) floor_db = to_db_one(__ldg(gmax), 10.0f, amin, refc) - top_db;
+    for (int i = threadIdx.x; i < n_mels * ROW; i += kTailFrames) {
+        const int m = i / ROW, k = i - m * ROW;
+        s_d[i] = (k < n_mfcc) ? __ldg(D + (long long)k * n_mels + m) : 0.f;
+    }
+    // the thread's column: n_mels 4-byte async copies, all in flight at once (a register-staged loop keeps 8 of them
+    // in flight per thread and leaves the kernel waiting on HBM latency), then converted in place
+    const float* col = mel + b * n_mels * T + (t < T ? t : 0);
+    for (int m = 0; m < n_mels; ++m) cp_async4(s_x + m * kTailFrames + threadIdx.x, col + (long long)m * T);
+    cp_async_commit();
+    cp_async_wait_all();
+    if (apply_db) {
+#pragma unroll 8
+        for (int m = 0; m < n_mels; ++m) {
+            float* px = s_x + m * kTailFrames + threadIdx.x;
+            *px = fmaxf(to_db_one(*px, 10.0f, amin, refc), floor_db);
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kg = lane >> 3, tj = lane & 7;      // coefficients kg*KT .. +KT, frames 32*warp + 4*tj .. +4
+    float2 acc[4][KT / 2];
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int i = 0; i < KT / 2; ++i) acc[f][i] = make_float2(0.f, 0.f);
+    const float4* xr = reinterpret_cast<const float4*>(s_x + 32 * warp + 4 * tj);
+    const float2* dr = reinterpret_cast<const float2*>(s_d + kg * KT);
+#pragma unroll 2
+    for (int m = 0; m < n_mels; ++m) {
+        const float4 x = xr[m * (kTailFrames / 4)];
+        float2 d[KT / 2];
+#pragma unroll
+        for (int i = 0; i < KT / 2; ++i) d[i] = dr[m * (ROW / 2) + i];
+#pragma unroll
+        for (int i = 0; i < KT / 2; ++i) {
+            acc[0][i] = pfma(d[i].x, d[i].y, x.x, x.x, acc[0][i]);
+            acc[1][i] = pfma(d[i].x, d[i].y, x.y, x.y, acc[1][i]);
+            acc[2][i] = pfma(d[i].x, d[i].y, x.z, x.z, acc[2][i]);
+            acc[3][i] = pfma(d[i].x, d[i].y, x.w, x.w, acc[3][i]);
+        }
+    }
+    const long long tf = t0 + 32 * warp + 4 * tj;
+#pragma unroll
+    for (int i = 0; i < KT / 2; ++i) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = kg * KT + 2 * i + h;
+            if (k < n_mfcc) {
+                const float l = lifter ? __ldg(lifter + k) : 1.f;
+                float* o = out + (b * n_mfcc + k) * T + tf;
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+                    if (tf + f < T) o[f] = (h ? acc[f][i].y : acc[f][i].x) * l;
+            }
+        }
+    }
+}
+template <int KT>
+cudaError_t launch_mfcc_tail_tiled(const float* mel, long long B, int n_mels, long long T, const float* D, int n_mfcc,
+                                   const float* lifter, int apply_db, float amin, float ref, int use_top, float top_db,
+                                   const float* gmax, float* out, cudaStream_t s) {
+    const size_t smem = size_t(n_mels) * (kTailFrames + 4 * KT) * 4;
+    cudaError_t e = cudaFuncSetAttribute(mfcc_tail_tiled_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((T + kTailFrames - 1) / kTailFrames), (unsigned)B);
+    mfcc_tail_tiled_kernel<KT><<<grid, kTailFrames, smem, s>>>(mel, n_mels, T, D, n_mfcc, lifter, apply_db, amin, ref, use_top,
+                                                            top_db, gmax, out);
+    return cudaGetLastError();
+}
+
 // ---- O(n^2) DFT fallback: any n_fft, same epilogues as the planned kernels -----------------
 template <int EP>
 __global__ void __launch_bounds__(256) fwd_naive_kernel(const FwdParams p, int nwarps) {
@@ -637,6 +729,22 @@ cudaError_t run_dct(const float* x, long long rows, int n_in, const float* D, in
 cudaError_t run_mfcc_tail(const float* mel, long long B, int n_mels, long long T, const float* D, int n_mfcc,
                           const float* lifter, int apply_db, float amin, float ref, int use_top, float top_db,
                           const float* gmax, float* out, cudaStream_t s) {
+    const int kt = 2 * ((n_mfcc + 7) / 8);  // coefficients per lane group (four groups per warp), even
+    static const bool rows_only = getenv("MLXA_MFCC_TAIL_ROWS") != nullptr;  // the earlier kernel, for A/B runs
+    if (!rows_only && kt <= 16 && size_t(n_mels) * (kTailFrames + 4 * kt) * 4 <= 113 * 1024 && B <= 65535) {
+#define MLXA_TAIL(KT) return launch_mfcc_tail_tiled<KT>(mel, B, n_mels, T, D, n_mfcc, lifter, apply_db, amin, ref, use_top, top_db, gmax, out, s)
+        switch (kt) {
+            case 2: MLXA_TAIL(2);
+            case 4: MLXA_TAIL(4);
+            case 6: MLXA_TAIL(6);
+            case 8: MLXA_TAIL(8);
+            case 10: MLXA_TAIL(10);
+            case 12: MLXA_TAIL(12);
+            case 14: MLXA_TAIL(14);
+            default: MLXA_TAIL(16);
+        }
+#undef MLXA_TAIL
+    }
     const size_t smem = size_t(n_mels) * 33 * 4 + size_t(n_mels) * n_mfcc * 4;
     cudaError_t e = cudaFuncSetAttribute(mfcc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
