@@ -175,6 +175,8 @@ MLXA_D void cp_async4(void* dst_smem, const void* src_gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
 MLXA_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+MLXA_D void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 MLXA_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 MLXA_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 

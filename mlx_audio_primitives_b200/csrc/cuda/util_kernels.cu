@@ -366,22 +366,19 @@ mfcc_tail_tiled_kernel(const float* __restrict__ mel, int n_mels, long long T, c
     const float refc = fmaxf(ref, amin);
     float floor_db = -INFINITY;
     if (apply_db && use_top) floor_db = to_db_one(__ldg(gmax), 10.0f, amin, refc) - top_db;
+    // the thread's column: n_mels 4-byte async copies in four groups, all in flight at once (a register-staged loop
+    // keeps 8 loads per thread in flight and leaves the kernel waiting on HBM latency); the DCT rows are fetched
+    // while they travel, and each quarter is converted and consumed as it lands
+    const float* col = mel + b * n_mels * T + (t < T ? t : 0);
+    const int mq = (n_mels + 3) / 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        for (int m = q * mq; m < min(n_mels, (q + 1) * mq); ++m) cp_async4(s_x + m * kTailFrames + threadIdx.x, col + (long long)m * T);
+        cp_async_commit();
+    }
     for (int i = threadIdx.x; i < n_mels * ROW; i += kTailFrames) {
         const int m = i / ROW, k = i - m * ROW;
         s_d[i] = (k < n_mfcc) ? __ldg(D + (long long)k * n_mels + m) : 0.f;
-    }
-    // the thread's column: n_mels 4-byte async copies, all in flight at once (a register-staged loop keeps 8 of them
-    // in flight per thread and leaves the kernel waiting on HBM latency), then converted in place
-    const float* col = mel + b * n_mels * T + (t < T ? t : 0);
-    for (int m = 0; m < n_mels; ++m) cp_async4(s_x + m * kTailFrames + threadIdx.x, col + (long long)m * T);
-    cp_async_commit();
-    cp_async_wait_all();
-    if (apply_db) {
-#pragma unroll 8
-        for (int m = 0; m < n_mels; ++m) {
-            float* px = s_x + m * kTailFrames + threadIdx.x;
-            *px = fmaxf(to_db_one(*px, 10.0f, amin, refc), floor_db);
-        }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -393,8 +390,23 @@ mfcc_tail_tiled_kernel(const float* __restrict__ mel, int n_mels, long long T, c
         for (int i = 0; i < KT / 2; ++i) acc[f][i] = make_float2(0.f, 0.f);
     const float4* xr = reinterpret_cast<const float4*>(s_x + 32 * warp + 4 * tj);
     const float2* dr = reinterpret_cast<const float2*>(s_d + kg * KT);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (q == 0) cp_async_wait_group<3>();
+        else if (q == 1) cp_async_wait_group<2>();
+        else if (q == 2) cp_async_wait_group<1>();
+        else cp_async_wait_group<0>();
+        const int m_lo = q * mq, m_hi = min(n_mels, (q + 1) * mq);
+        if (apply_db) {
+#pragma unroll 8
+            for (int m = m_lo; m < m_hi; ++m) {
+                float* px = s_x + m * kTailFrames + threadIdx.x;
+                *px = fmaxf(to_db_one(*px, 10.0f, amin, refc), floor_db);
+            }
+        }
+        __syncwarp();  // a lane reads four columns of its own warp
 #pragma unroll 2
-    for (int m = 0; m < n_mels; ++m) {
+    for (int m = m_lo; m < m_hi; ++m) {
         const float4 x = xr[m * (kTailFrames / 4)];
         float2 d[KT / 2];
 #pragma unroll
@@ -406,6 +418,7 @@ mfcc_tail_tiled_kernel(const float* __restrict__ mel, int n_mels, long long T, c
             acc[2][i] = pfma(d[i].x, d[i].y, x.z, x.z, acc[2][i]);
             acc[3][i] = pfma(d[i].x, d[i].y, x.w, x.w, acc[3][i]);
         }
+    }
     }
     const long long tf = t0 + 32 * warp + 4 * tj;
 #pragma unroll
