@@ -111,6 +111,42 @@ def test_many_clips_persistent_schedule(ap):
     assert float((r[:, 1:] - y[:, 1:]).abs().max()) <= 1e-5
 
 
+def test_many_clips_barrier_free_loops(ap):
+    """The tile loops without a CTA barrier per tile (staging buffers handed over by full / empty mbarriers, split
+    arrive / wait barriers around the power tile, neighbour-warp overlap-add rounds): many more (clip, tile) items
+    than resident CTAs, every tile an edge tile, against torch.stft in float64 and the oracle -- and run three
+    times: a race would show up as results that change from run to run."""
+    rng = np.random.default_rng(23)
+    y = torch.from_numpy(rng.standard_normal((600, 9000)).astype(np.float32)).cuda()
+    win = torch.hann_window(2048, periodic=True, dtype=torch.float64, device="cuda")
+    ref = torch.stft(y.double(), 2048, 512, window=win, center=True, pad_mode="constant", return_complex=True)
+    S = ap.stft(y, 2048, 512)
+    assert float((S - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    M = ap.melspectrogram(y, sr=22050, n_fft=2048, hop_length=512, n_mels=128)
+    for b in [0, 147, 148, 295, 296, 599]:
+        mref = o.melspectrogram(H(y[b]), sr=22050, n_fft=2048, hop_length=512, n_mels=128, dtype=np.float64)
+        assert np.abs(H(M[b]) - mref).max() <= 1e-5 * mref.max(), b
+    mag = ap.magnitude(S[:96])
+    g = ap.griffinlim(mag, n_iter=2, hop_length=512, random_state=0)
+    r = ap.istft(S, 512, length=9000)
+    assert float((r[:, 1:] - y[:, 1:]).abs().max()) <= 1e-5
+    for _ in range(2):
+        assert torch.equal(ap.stft(y, 2048, 512), S)
+        assert torch.equal(ap.melspectrogram(y, sr=22050, n_fft=2048, hop_length=512, n_mels=128), M)
+        assert torch.equal(ap.griffinlim(mag, n_iter=2, hop_length=512, random_state=0), g)
+        assert torch.equal(ap.istft(S, 512, length=9000), r)
+    # long clips: interior tiles, both staging buffers in rotation
+    y2 = torch.from_numpy(rng.standard_normal((5, 300000)).astype(np.float32)).cuda()
+    for n_fft, hop in [(1024, 256), (512, 128), (4096, 1024)]:
+        w = torch.hann_window(n_fft, periodic=True, dtype=torch.float64, device="cuda")
+        ref2 = torch.stft(y2.double(), n_fft, hop, window=w, center=True, pad_mode="constant", return_complex=True)
+        S2 = ap.stft(y2, n_fft, hop)
+        assert float((S2 - ref2).abs().max()) <= 1e-5 * float(ref2.abs().max()), n_fft
+        r2 = ap.istft(S2, hop, length=300000)
+        assert float((r2[:, 1:] - y2[:, 1:]).abs().max()) <= 1e-5, n_fft
+        assert torch.equal(ap.stft(y2, n_fft, hop), S2) and torch.equal(ap.istft(S2, hop, length=300000), r2)
+
+
 @pytest.mark.parametrize("n_fft", PLANNED)
 def test_every_planned_size(ap, n_fft):
     """Every compiled plan (powers of two 32..8192 and the 2^a 3^b 5^c sizes) through the fused kernels: forward
