@@ -154,14 +154,18 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
 #endif
     // Store-through and feature epilogues: lane groups never share an exchange buffer, so the only CTA-wide hazard is
     // the staging buffer being refilled while a slow warp still reads the previous tile from it.  That is the classic
-    // full / empty pair: every warp signals "my reads of this buffer are done" on an mbarrier after its last pass-0
-    // load of the tile, and only the thread that issues the next bulk copy waits for it -- no CTA barrier per tile.
+    // full / empty pair, with a ticket for "empty": after its last pass-0 load of a tile every warp draws a ticket from
+    // a shared counter, and the warp that draws the tile's LAST ticket -- all warps are done with the buffer -- issues
+    // the bulk copy that refills it (the next tile with one staging buffer, the tile after next with two).  Nobody
+    // waits: no CTA barrier per tile, and no thread parked on an mbarrier until the slowest warp arrives.
 #ifdef MLXA_NO_EMPTY_SYNC
     constexpr bool EMPTY_SYNC = false;
 #else
-    // Measured per epilogue (profiles/r04u_*): the store-through kernels gain 1-11 % on every plan but n_fft = 4096
-    // (one 8-warp CTA per SM: +5 %); the feature kernels lose 20 % without the per-tile barrier and keep it.
-    constexpr bool EMPTY_SYNC = (EP == EP_STFT || EP == EP_GL) && NFFT != 4096;
+    // Measured (profiles/r04u_*, r05e_*): against the per-tile CTA barrier STFT gains 3-20 % on every plan, the
+    // Griffin-Lim projection 8 %, the feature kernels 8 %.  (A first form -- per-warp arrivals on an mbarrier, thread 0
+    // waiting for them before issuing the copy -- lost 20 % on the feature kernels and 5 % at n_fft 4096: the issuing
+    // warp falls behind by its wait every tile and becomes the slowest arrival of the next one.)
+    constexpr bool EMPTY_SYNC = EP != EP_MEL;
 #endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int TT = p.tile_frames;
@@ -192,9 +196,9 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             mbar_init(s_bar + 3, THREADS / 32);  // "this warp has read its exchange buffer for the last time" (this tile)
             mbar_init(s_bar + 4, THREADS / 32);  // "this warp has projected its share of the tile"
         }
-        if constexpr (EMPTY_SYNC) {
-            mbar_init(s_bar + 3, THREADS / 32);  // "this warp has read staging buffer 0 for the last time" (this tile)
-            mbar_init(s_bar + 4, THREADS / 32);  // ... staging buffer 1
+        if constexpr (EMPTY_SYNC) {  // tickets drawn so far, per staging buffer
+            reinterpret_cast<int*>(s_bar + 3)[0] = 0;
+            reinterpret_cast<int*>(s_bar + 3)[1] = 0;
         }
     }
     __syncthreads();
@@ -252,11 +256,9 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             if (nbuf == 2) {
                 TileWalk nxt = cur;
                 nxt.advance();
-                if (nxt.b < p.B) {
-                    // buffer c ^ 1 held tile it - 1: its ((it - 1) / 2)-th use
-                    if (EMPTY_SYNC && it > 0) mbar_wait(s_bar + 3 + (c ^ 1), uint32_t((it - 1) >> 1) & 1u);
+                // (ticket form: only tile 1 is fetched from here; tile it + 2 is fetched by the warp that finishes tile it last)
+                if (nxt.b < p.B && (!EMPTY_SYNC || it == 0))
                     tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0 + (c ^ 1) * lay.in_floats, s_bar + (c ^ 1));
-                }
             }  // one buffer: the copy was started as soon as the previous tile's samples had been read (below)
         }
         if (ti.nl + ti.nr) {  // CTA-uniform: a clip's first / last tile
@@ -338,15 +340,17 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             if constexpr (EMPTY_SYNC) {
                 if (base + NG * FPT >= nt) {  // last round of the tile: this warp is done with the staged samples
                     __syncwarp();
-                    if ((threadIdx.x & 31) == 0) mbar_arrive_one(s_bar + 3 + c);
-                    // One staging buffer: as soon as every warp has said so, the next tile's bulk copy starts and lands
-                    // under the rest of this round instead of stalling the next tile (only the issuing thread waits)
-                    if (nbuf == 1 && threadIdx.x == 0) {
-                        TileWalk nxt = cur;
-                        nxt.advance();
-                        if (nxt.b < p.B) {
-                            mbar_wait(s_bar + 3, uint32_t(it) & 1u);
-                            tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in0, s_bar + 0);
+                    if ((threadIdx.x & 31) == 0) {
+                        __threadfence_block();
+                        // One counter per buffer; the k-th tile staged in a buffer owns tickets (THREADS / 32) * k ... + THREADS / 32 - 1.
+                        // The (k + 1)-th tile is only fetched once those are gone, so draws of successive tiles never mix.
+                        const int use = (nbuf == 2) ? (it >> 1) : it;
+                        const int tk = atomicAdd(reinterpret_cast<int*>(s_bar + 3) + c, 1);
+                        if (tk == (THREADS / 32) * (use + 1) - 1) {
+                            TileWalk nxt = cur;
+                            nxt.advance();
+                            if (nbuf == 2) nxt.advance();
+                            if (nxt.b < p.B) tile_issue_bulk(tile_at(p, TT, nxt.b, nxt.tile), s_in, s_bar + c);
                         }
                     }
                 }

@@ -137,7 +137,7 @@ def test_many_clips_barrier_free_loops(ap):
         assert torch.equal(ap.istft(S, 512, length=9000), r)
     # long clips: interior tiles, both staging buffers in rotation
     y2 = torch.from_numpy(rng.standard_normal((5, 300000)).astype(np.float32)).cuda()
-    for n_fft, hop in [(1024, 256), (512, 128), (4096, 1024)]:
+    for n_fft, hop in [(1024, 256), (512, 128), (4096, 1024), (64, 16), (256, 64), (2048, 512)]:
         w = torch.hann_window(n_fft, periodic=True, dtype=torch.float64, device="cuda")
         ref2 = torch.stft(y2.double(), n_fft, hop, window=w, center=True, pad_mode="constant", return_complex=True)
         S2 = ap.stft(y2, n_fft, hop)
