@@ -40,12 +40,18 @@ constexpr int FPT = PACK ? 1 : 2;
 #ifdef MLXA_INV_THREADS
 constexpr int THREADS = MLXA_INV_THREADS;
 #else
-// n_fft 1024 (16 lanes x 32 values): 12 groups, so that a tile of 12 * r hops (spaced rounds) fits twice per SM
-constexpr int THREADS = (P::E > 32) ? 256 : ((P::G >= 32) ? 512 : ((P::G == 16 && P::E == 32) ? 192 : 256));
+// n_fft 1024 (16 lanes x 32 values): 8 groups, so that a tile of 8 * r hops (spaced rounds) fits THREE times per SM --
+// the same 12 warps as two CTAs of 12 groups, but three CTAs interleave their prologue / transform / store phases
+// more finely (inverse kernel 270 -> 258 us; four CTAs of 6 groups: 282 us, the halo recompute grows to 3 in 24)
+constexpr int THREADS = (P::E > 32) ? 256 : ((P::G >= 32) ? 512 : ((P::G == 16 && P::E == 32) ? 128 : 256));
+#endif
+#ifndef MLXA_INV_CTAS
+#define MLXA_INV_CTAS ((P::G == 16 && P::E == 32 && THREADS == 128) ? 3 : 2)
 #endif
 constexpr int NG = THREADS / P::G;
-constexpr int NUNPACK = PACK ? P::N + 1 : 0;
-constexpr int TWP = (P::TW + 1) & ~1, TWU = (NUNPACK + 1) & ~1;
+// (the unpack table is read once per thread -- entry g, the base of the compile-time multiples -- straight from
+// global memory: it takes no shared memory)
+constexpr int TWP = (P::TW + 1) & ~1, TWU = 0;
 constexpr bool TW_SMEM = (TWP + TWU) * 8 <= 20 * 1024;
 
 constexpr int round_up4(int v) { return (v + 3) & ~3; }
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
     if (!cbulk)
         for (int i = threadIdx.x; i < NFFT; i += THREADS) s_win[i] = __ldg(p.window + i);
     const float2* tw_plan = TW_SMEM ? s_tw : p.tw_plan;
-    const float2* tw_unpack = TW_SMEM ? s_tw + TWP : p.tw_unpack;
+    const float2* tw_unpack = p.tw_unpack;
 
     // frames touching [o0, min(o0 + TS, ola_len))
     const long long o_end = min(o0 + (long long)TS, p.ola_len);
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(THREADS) inv_kernel(const InvParams p) {
 
     const int gi = threadIdx.x / P::G, g = threadIdx.x % P::G;
     float2* buf = s_buf + gi * P::BUF;
-    [[maybe_unused]] const float2 tw_base = PACK ? tw_unpack[g] : make_float2(0.f, 0.f);
+    [[maybe_unused]] const float2 tw_base = PACK ? __ldg(tw_unpack + g) : make_float2(0.f, 0.f);
     const long long clip = (long long)b * p.T * p.F_in;
     const bool hop_even = (p.hop & 1) == 0;
 
@@ -486,7 +492,7 @@ cudaError_t MLXA_CAT(launch_inv_, MLXA_NFFT)(InvParams& p, cudaStream_t s) {
     // spaced rounds: a tile of m * per_round * r - (r - 1) hops keeps every slot of every round busy; taken when two
     // such CTAs fit per SM and the clip is long enough to fill the tile
     {
-        constexpr size_t kHalf = (228 * 1024) / 2 - 1024;
+        constexpr size_t kHalf = (228 * 1024) / MLXA_INV_CTAS - 1024;
         const int per_super = per_round * r;
         auto th_sp = [&](int m) { return m * per_super - (r - 1); };
         static const bool no_spaced = getenv("MLXA_INV_NO_SPACED") != nullptr;
