@@ -152,6 +152,12 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
     constexpr bool SPLIT_SYNC = EP == EP_MEL && PF::MODE == MODE_PACK && P::NPASS == 2 && P::G <= 32 &&
                                 (P::nb(P::NPASS - 1) % P::G == 0) && P::rounds(1) <= 2;  // = REG_UNPACK below
 #endif
+    // (the second of the two, "projection done", does not depend on how the spectrum is unpacked: every packed plan has it)
+#ifdef MLXA_NO_SPLIT_SYNC
+    constexpr bool SPLIT_C = false;
+#else
+    constexpr bool SPLIT_C = EP == EP_MEL && PF::MODE == MODE_PACK;
+#endif
     // Store-through and feature epilogues: lane groups never share an exchange buffer, so the only CTA-wide hazard is
     // the staging buffer being refilled while a slow warp still reads the previous tile from it.  That is the classic
     // full / empty pair, with a ticket for "empty": after its last pass-0 load of a tile every warp draws a ticket from
@@ -192,10 +198,8 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
         mbar_init(s_bar + 0, 1);
         mbar_init(s_bar + 1, 1);
         mbar_init(s_bar + 2, 1);
-        if constexpr (SPLIT_SYNC) {
-            mbar_init(s_bar + 3, THREADS / 32);  // "this warp has read its exchange buffer for the last time" (this tile)
-            mbar_init(s_bar + 4, THREADS / 32);  // "this warp has projected its share of the tile"
-        }
+        if constexpr (SPLIT_SYNC) mbar_init(s_bar + 3, THREADS / 32);  // "this warp has read its exchange buffer for the last time" (this tile)
+        if constexpr (SPLIT_C) mbar_init(s_bar + 4, THREADS / 32);     // "this warp has projected its share of the tile"
         if constexpr (EMPTY_SYNC) {  // tickets drawn so far, per staging buffer
             reinterpret_cast<int*>(s_bar + 3)[0] = 0;
             reinterpret_cast<int*>(s_bar + 3)[1] = 0;
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 pair_zero_b = __all_sync(gm, (orb << 1) == 0u);
             }
             pass_compute<P, 0>(g, v, tw_plan);
-            if constexpr (SPLIT_SYNC) {
+            if constexpr (SPLIT_C) {
                 if (it > 0 && base == 0) {  // the previous tile's power tile (over the exchange buffers) has been projected by every warp
                     mbar_wait(s_bar + 4, ph_proj);
                     ph_proj ^= 1u;
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
                 __syncthreads();
                 if (p.bank_in_smem) project_power_tile<THREADS / 32, 0, false>(p, rb_smem, dbc, s_pw, TT, b, t0, nt, 1.f, threadIdx.x >> 5, vmax);
                 else project_power_tile<THREADS / 32, 0, false>(p, rb_glob, dbc, s_pw, TT, b, t0, nt, 1.f, threadIdx.x >> 5, vmax);
-                if constexpr (SPLIT_SYNC) {
+                if constexpr (SPLIT_C) {
                     __syncwarp();
                     if ((threadIdx.x & 31) == 0) mbar_arrive_one(s_bar + 4);
                 }
@@ -569,7 +573,7 @@ __global__ void __launch_bounds__(threads_for(EP), (P::E > 32) ? 1 : 512 / threa
             group_sync<P::G>(gi);
         }
 
-        if constexpr (!SPLIT_SYNC && !EMPTY_SYNC) __syncthreads();  // tile done: its staging buffer and the power tile may be overwritten
+        if constexpr (!SPLIT_C && !EMPTY_SYNC) __syncthreads();  // tile done: its staging buffer and the power tile may be overwritten
     }
     if constexpr (EP == EP_MEL) {
         if (p.gmax != nullptr) block_max_to_global<THREADS>(vmax, p.gmax, s_red, p.xchg);
